@@ -1,0 +1,183 @@
+"""Host-side mirror of the reference crate's acquisition API over libgnss_b200.
+
+Names and argument meaning follow src/acquisition/do_acquisition.rs and doppler_shift.rs:
+DopplerShiftTable::new (doppler_shift.rs:11-21), AcquisitionWorker::{new, search_satellite}
+(do_acquisition.rs:131-226), AcquisitionResult (:93-102), AcquisitionManager (:39-74).  The batched
+engine replaces the rayon loop over 32 workers (:302-313) with one fused launch.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _ffi
+
+FREQ_SEARCH_ACQUISITION_HZ = 14e3  # do_acquisition.rs:20
+FREQ_SEARCH_STEP_HZ = 500          # :21
+PRN_SEARCH_ACQUISITION_TOTAL = 32  # :22
+LONG_SAMPLES_LENGTH = 10           # :23
+GPS_L1_CA_CODE_RATE_CHIPS_PER_S = np.float32(1.023e6)
+
+
+def fft_size_for(fs):
+    """round(fs / (code_rate / 1023)) as at do_acquisition.rs:249-251."""
+    return _ffi.lib().gb_num_samples_per_code(float(GPS_L1_CA_CODE_RATE_CHIPS_PER_S), float(fs))
+
+
+def reference_doppler_grid():
+    """The 29 bins of run(): -7000 + 500*i (do_acquisition.rs:248-262)."""
+    cap = int(np.uint16(FREQ_SEARCH_ACQUISITION_HZ) // FREQ_SEARCH_STEP_HZ) + 1
+    return [np.float32(-FREQ_SEARCH_ACQUISITION_HZ / 2.0 + i * FREQ_SEARCH_STEP_HZ) for i in range(cap)]
+
+
+class AcquisitionManager:
+    """do_acquisition.rs:39-74 (host-only pacing logic)."""
+    COLD, WARM, STEADY = 0, 1, 2
+
+    def __init__(self):
+        self.mode = self.COLD
+
+    def update_mode(self, tracked_count):
+        self.mode = self.COLD if tracked_count == 0 else (self.WARM if tracked_count <= 4 else self.STEADY)
+
+    def get_pacing_and_list(self, active_prns):
+        interval, size = {self.COLD: (500, 32), self.WARM: (1000, 8), self.STEADY: (2000, 5)}[self.mode]
+        cands = [p for p in range(1, PRN_SEARCH_ACQUISITION_TOTAL + 1) if p not in active_prns][:size]
+        mask = 0
+        for p in cands:
+            mask |= 1 << (p - 1)
+        return interval, mask
+
+
+class AcquisitionEngine:
+    """All AcquisitionWorkers of one receiver on one GPU."""
+
+    def __init__(self, handle, fft_size, fs, n_prn=32, codes=None):
+        self.hd = handle
+        self.n, self.fs, self.n_prn = int(fft_size), float(fs), int(n_prn)
+        cp = None
+        if codes is not None:
+            codes = np.ascontiguousarray(codes, np.int8)
+            assert codes.shape == (n_prn, fft_size)
+            cp = _ffi.ptr(codes)
+        handle.call("gb_acq_configure", self.n, self.fs, self.n_prn, cp)
+        self.carr = None
+        self.n_coh = 1
+
+    # DopplerShiftTable::new for a list of Doppler offsets, built on the device
+    def make_doppler_tables(self, f_if, dopplers):
+        d = np.ascontiguousarray(dopplers, np.float32)
+        carr = np.zeros(len(d), np.float32)
+        self.hd.call("gb_acq_make_doppler_tables", float(f_if), _ffi.ptr(d), len(d), _ffi.ptr(carr))
+        self.carr = carr
+        return carr
+
+    # caller-built tables (the reference's pub `table` / `doppler_freq_hz` fields)
+    def set_doppler_tables(self, tables, carr):
+        t = np.ascontiguousarray(tables, np.complex64)
+        c = np.ascontiguousarray(carr, np.float32)
+        assert t.shape == (len(c), self.n)
+        self.hd.call("gb_acq_set_doppler_tables", _ffi.ptr(t), _ffi.ptr(c), len(c))
+        self.carr = c.copy()
+
+    def get_doppler_tables(self):
+        t = np.zeros((len(self.carr), self.n), np.complex64)
+        self.hd.call("gb_acq_get_doppler_tables", _ffi.ptr(t), None)
+        return t
+
+    def set_coherent(self, n_coh):
+        self.hd.call("gb_acq_set_coherent", int(n_coh))
+        self.n_coh = int(n_coh)
+
+    def set_detector(self, threshold=7.0, samples_per_chip=0):
+        self.hd.call("gb_acq_set_detector", float(threshold), int(samples_per_chip))
+
+    def _enable(self, enable):
+        return None if enable is None else np.ascontiguousarray(enable, np.uint8)
+
+    def search_cells(self, samples, num_integrations, prn_mask=0xFFFFFFFF, enable=None):
+        """Full PRN x Doppler grid -> structured array [n_prn, D] of {peak, argmax, sum8, peak2}."""
+        x = samples if isinstance(samples, int) else np.ascontiguousarray(samples, np.complex64)
+        cells = np.zeros((self.n_prn, len(self.carr)), _ffi.CELL_DTYPE)
+        en = self._enable(enable)
+        self.hd.call("gb_acq_search_cells", _ffi.ptr(x), int(num_integrations), int(prn_mask), _ffi.ptr(en),
+                     _ffi.ptr(cells))
+        return cells
+
+    def search_cells_ring(self, local_tail, num_integrations, prn_mask=0xFFFFFFFF, enable=None, want_cells=True):
+        cells = np.zeros((self.n_prn, len(self.carr)), _ffi.CELL_DTYPE) if want_cells else None
+        en = self._enable(enable)
+        self.hd.call("gb_acq_search_cells_ring", int(local_tail), int(num_integrations), int(prn_mask), _ffi.ptr(en),
+                     _ffi.ptr(cells))
+        return cells
+
+    def search(self, samples, num_integrations, local_tail=0, prn_mask=0xFFFFFFFF, enable=None):
+        """search_satellite for every selected PRN: list of AcquisitionResult dicts or None."""
+        x = samples if isinstance(samples, int) else np.ascontiguousarray(samples, np.complex64)
+        res = (_ffi.AcqResult * self.n_prn)()
+        en = self._enable(enable)
+        self.hd.call("gb_acq_search", _ffi.ptr(x), int(num_integrations), int(local_tail), int(prn_mask),
+                     _ffi.ptr(en), res)
+        return [r.as_dict() if r.found else None for r in res]
+
+    def search_ring(self, local_tail, num_integrations, prn_mask=0xFFFFFFFF, enable=None):
+        res = (_ffi.AcqResult * self.n_prn)()
+        en = self._enable(enable)
+        self.hd.call("gb_acq_search_ring", int(local_tail), int(num_integrations), int(prn_mask), _ffi.ptr(en), res)
+        return [r.as_dict() if r.found else None for r in res]
+
+    def bin_power(self, samples, num_integrations, prn, doppler_bin):
+        x = np.ascontiguousarray(samples, np.complex64)
+        out = np.zeros(self.n, np.float32)
+        self.hd.call("gb_acq_bin_power", _ffi.ptr(x), int(num_integrations), int(prn), int(doppler_bin), _ffi.ptr(out))
+        return out
+
+    def last_kernel_ms(self):
+        return float(self.hd.L.gb_acq_last_kernel_ms(self.hd.h))
+
+
+def decide(cells_row, carr, prn, fft_size, fs, local_tail=0, threshold=7.0):
+    """search_satellite's decision on one PRN's cells (gb_acq_decide)."""
+    cells_row = np.ascontiguousarray(cells_row, _ffi.CELL_DTYPE)
+    carr = np.ascontiguousarray(carr, np.float32)
+    r = _ffi.AcqResult()
+    _ffi.check(_ffi.lib().gb_acq_decide(_ffi.ptr(cells_row), _ffi.ptr(carr), len(carr), int(prn), int(fft_size),
+                                        float(fs), int(local_tail), float(threshold), C.byref(r)), "gb_acq_decide")
+    return r.as_dict() if r.found else None
+
+
+class FFT:
+    """fft.rs:5-30 FFT<f32>."""
+
+    def __init__(self, handle, length):
+        self.hd, self.len = handle, int(length)
+
+    def execute(self, x, inverse=False):
+        x = np.ascontiguousarray(x, np.complex64)
+        batch = x.size // self.len
+        out = np.zeros_like(x)
+        self.hd.call("gb_fft_c2c", self.len, int(inverse), _ffi.ptr(x), _ffi.ptr(out), batch)
+        return out
+
+    def power_spectrum(self, x):
+        x = np.ascontiguousarray(x, np.complex64)
+        out = np.zeros(x.shape, np.float32)
+        self.hd.call("gb_fft_power_spectrum", self.len, _ffi.ptr(x), _ffi.ptr(out), x.size // self.len)
+        return out
+
+
+class RealFFT:
+    """fft.rs:32-56 RealFFT<f32>."""
+
+    def __init__(self, handle, length):
+        self.hd, self.len = handle, int(length)
+
+    def execute(self, x):
+        x = np.ascontiguousarray(x, np.float32)
+        batch = x.size // self.len
+        out = np.zeros((batch, self.len // 2 + 1), np.complex64)
+        self.hd.call("gb_rfft", self.len, _ffi.ptr(x), _ffi.ptr(out), batch)
+        return out[0] if x.ndim == 1 else out
+
+    def power_spectrum(self, x):
+        y = self.execute(x)
+        return (y.real * y.real + y.imag * y.imag).astype(np.float32)

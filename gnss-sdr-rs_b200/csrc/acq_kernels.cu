@@ -1,0 +1,522 @@
+// acq_kernels.cu -- fused parallel code-phase search, sm_100a.
+//
+// One CTA owns one (PRN, Doppler bin) cell row and runs, per 1 ms block (or per coherent group),
+//   carrier wipe-off (doppler_shift.rs:25-58)  -> forward FFT (do_acquisition.rs:182)
+//   -> x conj(code spectrum) (:184-186)        -> inverse FFT (:188)
+//   -> |.|^2 accumulate (:190-192)
+// entirely in shared memory / registers, then reduces the accumulated row to
+// {peak, first argmax, 8-lane sum, second peak} (:195-202, :229-234) -- 16 bytes to HBM per cell row.
+// The only HBM/L2 reads are the IQ chunk, the wipe-off table and the code spectrum.
+#include "acq_kernels.cuh"
+#include "fft_smem.cuh"
+
+namespace gb {
+
+// ------------------------------------------------------------------ plans
+//                 N      T  MINB PAD  radices (forward DIF order; odd radices last => no padding needed)
+using P1024 = Plan<1024, 64, 8, 4, 4, 16, 16>;
+using P2048 = Plan<2048, 128, 4, 4, 8, 16, 16>;
+using P4092 = Plan<4092, 192, 2, 0, 12, 11, 31>;
+using P4096 = Plan<4096, 256, 2, 4, 16, 16, 16>;
+using P8184 = Plan<8184, 288, 1, 0, 8, 3, 11, 31>;
+using P16368 = Plan<16368, 288, 1, 0, 16, 3, 11, 31>;
+using P20000 = Plan<20000, 512, 1, 0, 8, 4, 25, 25>;
+
+#define GB_FOR_EACH_PLAN(X) X(0, P1024) X(1, P2048) X(2, P4092) X(3, P4096) X(4, P8184) X(5, P16368) X(6, P20000)
+static const int kPlanSizes[] = {1024, 2048, 4092, 4096, 8184, 16368, 20000};
+static const int kNumPlans = sizeof(kPlanSizes) / sizeof(int);
+
+// reference arithmetic of multiply_simd_block (doppler_shift.rs:43-58): separate roundings, no FMA
+__device__ __forceinline__ float2 wipe(float2 x, float2 w)
+{
+    return make_float2(__fadd_rn(__fmul_rn(x.x, w.x), -__fmul_rn(x.y, w.y)),
+                       __fadd_rn(__fmul_rn(x.x, w.y), __fmul_rn(x.y, w.x)));
+}
+
+__device__ __forceinline__ float2 ld_iq(const AcqArgs& a, unsigned long long idx)
+{
+    return __ldg(&a.iq[(a.iq_start + idx) & a.iq_mask]);
+}
+
+struct PeakIdx {
+    float v;
+    unsigned idx;
+};
+// "first index of the strict maximum": larger value wins, ties go to the smaller index; NaN never wins
+__device__ __forceinline__ PeakIdx peak_merge(PeakIdx a, PeakIdx b)
+{
+    const bool take_b = (b.v > a.v) || (b.v == a.v && b.idx < a.idx);
+    return take_b ? b : a;
+}
+__device__ __forceinline__ PeakIdx warp_peak(PeakIdx p)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        PeakIdx q;
+        q.v = __shfl_xor_sync(0xffffffffu, p.v, o);
+        q.idx = __shfl_xor_sync(0xffffffffu, p.idx, o);
+        p = peak_merge(p, q);
+    }
+    return p;
+}
+__device__ __forceinline__ float warp_sum(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <class P, bool WANT_ROW> __global__ void __launch_bounds__(P::T, P::MINB) acq_fused_kernel(const AcqArgs a)
+{
+    extern __shared__ float2 line[];
+    constexpr int LASTS = P::NSTAGE - 1;
+    using G0 = StageGeo<P, 0>;
+    using GM = StageGeo<P, LASTS>;
+    constexpr int N = P::N;
+
+    const int d = WANT_ROW ? a.d0 : (int)(blockIdx.x % (unsigned)a.D);
+    const int row = a.rows[WANT_ROW ? 0 : (int)(blockIdx.x / (unsigned)a.D)];
+    const float2* __restrict__ w = a.tables + (size_t)d * N;
+    const float2* __restrict__ code = a.code_fft + (size_t)row * N;
+    const float2* __restrict__ tw = a.tw;
+    const float2* __restrict__ rot = a.rot ? a.rot + (size_t)d * a.n_coh : nullptr;
+    const int n_coh = a.n_coh;
+    const int n_groups = a.K / n_coh;
+
+    float acc[G0::ITERS][G0::R];
+#pragma unroll
+    for (int it = 0; it < G0::ITERS; it++)
+#pragma unroll
+        for (int j = 0; j < G0::R; j++) acc[it][j] = 0.f;
+
+    for (int g = 0; g < n_groups; g++) {
+        // ---- stage 0 (DIF, L = N): wipe-off fused into the load, straight from global memory
+#pragma unroll
+        for (int it = 0; it < G0::ITERS; it++) {
+            const int i = threadIdx.x + it * P::T;
+            if (G0::NB % P::T == 0 || i < G0::NB) {
+                float2 v[G0::R];
+                if (n_coh == 1) {
+                    const unsigned long long blk0 = (unsigned long long)g * N;
+#pragma unroll
+                    for (int j = 0; j < G0::R; j++)
+                        v[j] = wipe(ld_iq(a, blk0 + i + j * G0::SUB), __ldg(&w[i + j * G0::SUB]));
+                } else {
+                    float2 wv[G0::R];
+#pragma unroll
+                    for (int j = 0; j < G0::R; j++) {
+                        wv[j] = __ldg(&w[i + j * G0::SUB]);
+                        v[j] = make_float2(0.f, 0.f);
+                    }
+                    for (int c = 0; c < n_coh; c++) {
+                        const float2 r = __ldg(&rot[c]);
+                        const unsigned long long blk0 = (unsigned long long)(g * n_coh + c) * N;
+#pragma unroll
+                        for (int j = 0; j < G0::R; j++) {
+                            const float2 t = wipe(ld_iq(a, blk0 + i + j * G0::SUB), wv[j]);
+                            v[j].x = fmaf(t.x, r.x, fmaf(-t.y, r.y, v[j].x));
+                            v[j].y = fmaf(t.x, r.y, fmaf(t.y, r.x, v[j].y));
+                        }
+                    }
+                }
+                Dft<G0::R, false>::run(v);
+                line[P::phys(i)] = v[0];
+#pragma unroll
+                for (int q = 1; q < G0::R; q++) line[P::phys(i + q * G0::SUB)] = cmul(v[q], __ldg(&tw[i * q]));
+            }
+        }
+        __syncthreads();
+        DifRange<P, 1, LASTS, false>::run(line, tw);
+
+        // ---- last forward stage + x conj(code) + first inverse stage, in registers
+#pragma unroll
+        for (int it = 0; it < GM::ITERS; it++) {
+            const int b = threadIdx.x + it * P::T;
+            if (GM::NB % P::T == 0 || b < GM::NB) {
+                const int base = b * GM::R;
+                float2 v[GM::R];
+#pragma unroll
+                for (int j = 0; j < GM::R; j++) v[j] = line[P::phys(base + j)];
+                Dft<GM::R, false>::run(v);
+#pragma unroll
+                for (int q = 0; q < GM::R; q++) v[q] = cmul_conj(v[q], __ldg(&code[q * GM::NB + b]));
+                Dft<GM::R, true>::run(v);
+#pragma unroll
+                for (int j = 0; j < GM::R; j++) line[P::phys(base + j)] = v[j];
+            }
+        }
+        __syncthreads();
+        DitRange<P, LASTS - 1, 0, true>::run(line, tw);
+
+        // ---- stage 0 inverse (DIT, L = N) fused with |.|^2 accumulate; natural order
+#pragma unroll
+        for (int it = 0; it < G0::ITERS; it++) {
+            const int i = threadIdx.x + it * P::T;
+            if (G0::NB % P::T == 0 || i < G0::NB) {
+                float2 v[G0::R];
+                v[0] = line[P::phys(i)];
+#pragma unroll
+                for (int q = 1; q < G0::R; q++) v[q] = cmul_conj(line[P::phys(i + q * G0::SUB)], __ldg(&tw[i * q]));
+                Dft<G0::R, true>::run(v);
+#pragma unroll
+                for (int j = 0; j < G0::R; j++) acc[it][j] += v[j].x * v[j].x + v[j].y * v[j].y;
+            }
+        }
+        __syncthreads();  // the next group's stage 0 overwrites the line
+    }
+
+    if (WANT_ROW) {
+#pragma unroll
+        for (int it = 0; it < G0::ITERS; it++) {
+            const int i = threadIdx.x + it * P::T;
+            if (G0::NB % P::T == 0 || i < G0::NB)
+#pragma unroll
+                for (int j = 0; j < G0::R; j++) a.row_out[i + j * G0::SUB] = acc[it][j];
+        }
+        return;
+    }
+
+    // ---- reduce the row: peak / first argmax / 8-lane sum (Q2: only the first 8*floor(N/8) bins)
+    constexpr int NSUM = (N / 8) * 8;
+    constexpr int NW = P::T / 32;
+    PeakIdx pk;
+    pk.v = 0.f;
+    pk.idx = 0u;
+    float sum = 0.f;
+#pragma unroll
+    for (int it = 0; it < G0::ITERS; it++) {
+        const int i = threadIdx.x + it * P::T;
+        if (G0::NB % P::T == 0 || i < G0::NB) {
+#pragma unroll
+            for (int j = 0; j < G0::R; j++) {
+                const int n = i + j * G0::SUB;
+                const float v = acc[it][j];
+                PeakIdx c;
+                c.v = v;
+                c.idx = (unsigned)n;
+                if (v > 0.f) pk = peak_merge(pk, c);
+                if (NSUM == N || n < NSUM) sum += v;
+            }
+        }
+    }
+    pk = warp_peak(pk);
+    sum = warp_sum(sum);
+    float* red_v = reinterpret_cast<float*>(line);
+    unsigned* red_i = reinterpret_cast<unsigned*>(line) + 64;
+    float* red_s = reinterpret_cast<float*>(line) + 128;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) {
+        red_v[warp] = pk.v;
+        red_i[warp] = pk.idx;
+        red_s[warp] = sum;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        PeakIdx q;
+        q.v = lane < NW ? red_v[lane] : 0.f;
+        q.idx = lane < NW ? red_i[lane] : 0u;
+        float s = lane < NW ? red_s[lane] : 0.f;
+        q = warp_peak(q);
+        s = warp_sum(s);
+        if (lane == 0) {
+            red_v[32] = q.v;
+            red_i[32] = q.idx;
+            red_s[32] = s;
+        }
+    }
+    __syncthreads();
+    const float peak = red_v[32];
+    const unsigned arg = red_i[32];
+    const float total = red_s[32];
+
+    // ---- second peak outside +-spc samples (circular) of the first (legacy two-peak metric)
+    float p2 = 0.f;
+    if (a.spc > 0) {
+#pragma unroll
+        for (int it = 0; it < G0::ITERS; it++) {
+            const int i = threadIdx.x + it * P::T;
+            if (G0::NB % P::T == 0 || i < G0::NB) {
+#pragma unroll
+                for (int j = 0; j < G0::R; j++) {
+                    const int n = i + j * G0::SUB;
+                    int dist = abs(n - (int)arg);
+                    dist = min(dist, N - dist);
+                    if (dist > a.spc) p2 = fmaxf(p2, acc[it][j]);
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) p2 = fmaxf(p2, __shfl_xor_sync(0xffffffffu, p2, o));
+        __syncthreads();
+        if (lane == 0) red_v[warp] = p2;
+        __syncthreads();
+        if (warp == 0) {
+            float v = lane < NW ? red_v[lane] : 0.f;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+            p2 = v;
+        }
+    }
+    if (threadIdx.x == 0) {
+        gb_acq_cell c;
+        c.peak = peak;
+        c.argmax = arg;
+        c.sum8 = total;
+        c.peak2 = p2;
+        a.cells[(size_t)row * a.D + d] = c;
+    }
+}
+
+// ------------------------------------------------------------------ code spectra (AcquisitionWorker::new, :133-138)
+// One CTA per PRN: +-1 code samples -> forward DIF -> scrambled spectrum, stored transposed
+// ([q][b] for the last radix) so the fused middle stage reads it coalesced.
+template <class P> __global__ void __launch_bounds__(P::T) code_fft_kernel(const int8_t* __restrict__ codes,
+                                                                           float2* __restrict__ code_fft,
+                                                                           const float2* __restrict__ tw)
+{
+    extern __shared__ float2 line[];
+    constexpr int LASTS = P::NSTAGE - 1;
+    using G0 = StageGeo<P, 0>;
+    using GM = StageGeo<P, LASTS>;
+    const int8_t* c = codes + (size_t)blockIdx.x * P::N;
+    float2* out = code_fft + (size_t)blockIdx.x * P::N;
+#pragma unroll
+    for (int it = 0; it < G0::ITERS; it++) {
+        const int i = threadIdx.x + it * P::T;
+        if (G0::NB % P::T == 0 || i < G0::NB) {
+            float2 v[G0::R];
+#pragma unroll
+            for (int j = 0; j < G0::R; j++) v[j] = make_float2((float)c[i + j * G0::SUB], 0.f);
+            Dft<G0::R, false>::run(v);
+            line[P::phys(i)] = v[0];
+#pragma unroll
+            for (int q = 1; q < G0::R; q++) line[P::phys(i + q * G0::SUB)] = cmul(v[q], __ldg(&tw[i * q]));
+        }
+    }
+    __syncthreads();
+    DifRange<P, 1, LASTS, false>::run(line, tw);
+#pragma unroll
+    for (int it = 0; it < GM::ITERS; it++) {
+        const int b = threadIdx.x + it * P::T;
+        if (GM::NB % P::T == 0 || b < GM::NB) {
+            float2 v[GM::R];
+#pragma unroll
+            for (int j = 0; j < GM::R; j++) v[j] = line[P::phys(b * GM::R + j)];
+            Dft<GM::R, false>::run(v);
+#pragma unroll
+            for (int q = 0; q < GM::R; q++) out[q * GM::NB + b] = v[q];
+        }
+    }
+}
+
+// ------------------------------------------------------------------ FFT facade (fft.rs:5-56)
+// Natural-order in, natural-order out: DIF in the requested direction, un-scrambled on the store.
+template <class P, bool INV> __global__ void __launch_bounds__(P::T) fft_c2c_kernel(const FftArgs a)
+{
+    extern __shared__ float2 line[];
+    constexpr int LASTS = P::NSTAGE - 1;
+    using G0 = StageGeo<P, 0>;
+    using GM = StageGeo<P, LASTS>;
+    const size_t boff = (size_t)blockIdx.x * P::N;
+    const float2* __restrict__ tw = a.tw;
+#pragma unroll
+    for (int it = 0; it < G0::ITERS; it++) {
+        const int i = threadIdx.x + it * P::T;
+        if (G0::NB % P::T == 0 || i < G0::NB) {
+            float2 v[G0::R];
+#pragma unroll
+            for (int j = 0; j < G0::R; j++) {
+                const size_t idx = boff + i + j * G0::SUB;
+                v[j] = a.real_in ? make_float2(reinterpret_cast<const float*>(a.in)[idx], 0.f)
+                                 : reinterpret_cast<const float2*>(a.in)[idx];
+            }
+            Dft<G0::R, INV>::run(v);
+            line[P::phys(i)] = v[0];
+#pragma unroll
+            for (int q = 1; q < G0::R; q++) {
+                const float2 t = __ldg(&tw[i * q]);
+                line[P::phys(i + q * G0::SUB)] = INV ? cmul_conj(v[q], t) : cmul(v[q], t);
+            }
+        }
+    }
+    __syncthreads();
+    DifRange<P, 1, LASTS, INV>::run(line, tw);
+    const size_t ooff = (size_t)blockIdx.x * a.n_out;
+#pragma unroll
+    for (int it = 0; it < GM::ITERS; it++) {
+        const int b = threadIdx.x + it * P::T;
+        if (GM::NB % P::T == 0 || b < GM::NB) {
+            float2 v[GM::R];
+#pragma unroll
+            for (int j = 0; j < GM::R; j++) v[j] = line[P::phys(b * GM::R + j)];
+            Dft<GM::R, INV>::run(v);
+#pragma unroll
+            for (int q = 0; q < GM::R; q++) {
+                const int k = a.freq_of_pos[b * GM::R + q];
+                if (k < a.n_out) {
+                    if (a.power_out) reinterpret_cast<float*>(a.out)[ooff + k] = v[q].x * v[q].x + v[q].y * v[q].y;
+                    else reinterpret_cast<float2*>(a.out)[ooff + k] = v[q];
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------ DopplerShiftTable::new (doppler_shift.rs:11-21)
+// steps[d] = 2*pi*(f_if+f_d)/fs is evaluated on the host in f32 in the reference's order;
+// phase = (i as f32) * step, table = (cos, -sin) with the full-range device cosf/sinf.
+__global__ void doppler_table_kernel(const float* __restrict__ steps, int n, float2* __restrict__ tables)
+{
+    const float step = steps[blockIdx.y];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const float phase = __fmul_rn((float)i, step);
+        tables[(size_t)blockIdx.y * n + i] = make_float2(cosf(phase), -sinf(phase));
+    }
+}
+
+// ------------------------------------------------------------------ host-side dispatch
+int acq_plan_index(int n)
+{
+    for (int i = 0; i < kNumPlans; i++)
+        if (kPlanSizes[i] == n) return i;
+    return -1;
+}
+int acq_plan_sizes(int* sizes, int cap)
+{
+    for (int i = 0; i < kNumPlans && i < cap; i++) sizes[i] = kPlanSizes[i];
+    return kNumPlans;
+}
+
+template <class P> static int plan_radices(int* r)
+{
+    for (int s = 0; s < P::NSTAGE; s++) r[s] = P::radix(s);
+    return P::NSTAGE;
+}
+template <class P> static size_t plan_smem() { return sizeof(float2) * (size_t)(P::LINE < 160 ? 160 : P::LINE); }
+
+int acq_plan_radices(int plan, int* radices)
+{
+    switch (plan) {
+#define X(i, P) \
+    case i: return plan_radices<P>(radices);
+        GB_FOR_EACH_PLAN(X)
+#undef X
+    }
+    return 0;
+}
+int acq_plan_threads(int plan)
+{
+    switch (plan) {
+#define X(i, P) \
+    case i: return P::T;
+        GB_FOR_EACH_PLAN(X)
+#undef X
+    }
+    return 0;
+}
+size_t acq_plan_smem(int plan)
+{
+    switch (plan) {
+#define X(i, P) \
+    case i: return plan_smem<P>();
+        GB_FOR_EACH_PLAN(X)
+#undef X
+    }
+    return 0;
+}
+
+template <class K> static cudaError_t set_smem(K kernel, size_t bytes)
+{
+    if (bytes > 48 * 1024) return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    return cudaSuccess;
+}
+
+template <class P> static cudaError_t launch_search(const AcqArgs& a, cudaStream_t st)
+{
+    const size_t smem = plan_smem<P>();
+    cudaError_t e = set_smem(acq_fused_kernel<P, false>, smem);
+    if (e != cudaSuccess) return e;
+    acq_fused_kernel<P, false><<<a.n_active * a.D, P::T, smem, st>>>(a);
+    return cudaGetLastError();
+}
+template <class P> static cudaError_t launch_row(const AcqArgs& a, cudaStream_t st)
+{
+    const size_t smem = plan_smem<P>();
+    cudaError_t e = set_smem(acq_fused_kernel<P, true>, smem);
+    if (e != cudaSuccess) return e;
+    acq_fused_kernel<P, true><<<1, P::T, smem, st>>>(a);
+    return cudaGetLastError();
+}
+template <class P> static cudaError_t launch_code_fft(const int8_t* codes, int n_prn, float2* code_fft, const float2* tw,
+                                                     cudaStream_t st)
+{
+    const size_t smem = plan_smem<P>();
+    cudaError_t e = set_smem(code_fft_kernel<P>, smem);
+    if (e != cudaSuccess) return e;
+    code_fft_kernel<P><<<n_prn, P::T, smem, st>>>(codes, code_fft, tw);
+    return cudaGetLastError();
+}
+template <class P> static cudaError_t launch_fft(int inverse, const FftArgs& a, int batch, cudaStream_t st)
+{
+    const size_t smem = plan_smem<P>();
+    cudaError_t e;
+    if (inverse) {
+        if ((e = set_smem(fft_c2c_kernel<P, true>, smem)) != cudaSuccess) return e;
+        fft_c2c_kernel<P, true><<<batch, P::T, smem, st>>>(a);
+    } else {
+        if ((e = set_smem(fft_c2c_kernel<P, false>, smem)) != cudaSuccess) return e;
+        fft_c2c_kernel<P, false><<<batch, P::T, smem, st>>>(a);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t acq_launch_search(int plan, const AcqArgs& a, cudaStream_t st)
+{
+    switch (plan) {
+#define X(i, P) \
+    case i: return launch_search<P>(a, st);
+        GB_FOR_EACH_PLAN(X)
+#undef X
+    }
+    return cudaErrorInvalidValue;
+}
+cudaError_t acq_launch_row(int plan, const AcqArgs& a, cudaStream_t st)
+{
+    switch (plan) {
+#define X(i, P) \
+    case i: return launch_row<P>(a, st);
+        GB_FOR_EACH_PLAN(X)
+#undef X
+    }
+    return cudaErrorInvalidValue;
+}
+cudaError_t acq_launch_code_fft(int plan, const int8_t* codes, int n_prn, float2* code_fft, const float2* tw,
+                                cudaStream_t st)
+{
+    switch (plan) {
+#define X(i, P) \
+    case i: return launch_code_fft<P>(codes, n_prn, code_fft, tw, st);
+        GB_FOR_EACH_PLAN(X)
+#undef X
+    }
+    return cudaErrorInvalidValue;
+}
+cudaError_t acq_launch_fft(int plan, int inverse, const FftArgs& a, int batch, cudaStream_t st)
+{
+    switch (plan) {
+#define X(i, P) \
+    case i: return launch_fft<P>(inverse, a, batch, st);
+        GB_FOR_EACH_PLAN(X)
+#undef X
+    }
+    return cudaErrorInvalidValue;
+}
+cudaError_t acq_launch_doppler_tables(const float* steps_dev, int D, int n, float2* tables, cudaStream_t st)
+{
+    dim3 grid((n + 255) / 256, D);
+    doppler_table_kernel<<<grid, 256, 0, st>>>(steps_dev, n, tables);
+    return cudaGetLastError();
+}
+
+}  // namespace gb

@@ -1,0 +1,48 @@
+// acq_kernels.cuh -- launch interface of the fused acquisition kernels (acq_kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/gnss_b200.h"
+
+namespace gb {
+
+struct AcqArgs {
+    const float2* iq;        // sample ring / chunk base
+    unsigned long long iq_start;  // absolute index of sample 0 of block 0
+    unsigned long long iq_mask;   // ring mask (all ones for a linear chunk)
+    const float2* tables;    // D x N wipe-off tables (DopplerShiftTable::table)
+    const float2* code_fft;  // n_prn x N code spectra, scrambled + transposed for the middle stage
+    const float2* tw;        // N stage twiddles exp(-2 pi i k / N)
+    const float2* rot;       // D x n_coh coherent rotators or nullptr
+    const int* rows;         // active PRN rows (index into code_fft / cells rows)
+    int D, K, n_coh, n_active;
+    int spc;                 // samples per chip for the two-peak exclusion (0 = off)
+    gb_acq_cell* cells;      // n_prn x D
+    float* row_out;          // diagnostics: accumulated power row of (rows[0], d0)
+    int d0;                  // Doppler bin for row_out
+};
+
+struct FftArgs {
+    const void* in;          // float2 (or float if real_in) batch x n, natural order
+    void* out;               // float2 (or float if power_out) batch x n_out
+    const float2* tw;
+    const int* freq_of_pos;  // scrambled position -> natural frequency index
+    int real_in, power_out, n_out;
+};
+
+int acq_plan_index(int n);                    // -1 if there is no plan for n
+int acq_plan_sizes(int* sizes, int cap);      // list of planned sizes
+int acq_plan_radices(int plan, int* radices); // returns number of stages
+int acq_plan_threads(int plan);
+size_t acq_plan_smem(int plan);
+
+cudaError_t acq_launch_search(int plan, const AcqArgs& a, cudaStream_t st);
+cudaError_t acq_launch_row(int plan, const AcqArgs& a, cudaStream_t st);
+cudaError_t acq_launch_code_fft(int plan, const int8_t* codes, int n_prn, float2* code_fft, const float2* tw,
+                                cudaStream_t st);
+cudaError_t acq_launch_fft(int plan, int inverse, const FftArgs& a, int batch, cudaStream_t st);
+// steps_dev[d] = 2*pi*(f_if+f_d)/fs (f32, host-evaluated in the reference's order)
+cudaError_t acq_launch_doppler_tables(const float* steps_dev, int D, int n, float2* tables, cudaStream_t st);
+
+}  // namespace gb

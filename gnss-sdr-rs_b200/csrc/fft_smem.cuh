@@ -1,0 +1,325 @@
+// fft_smem.cuh -- in-place mixed-radix FFT stages on a shared-memory line, sm_100a.
+//
+// Replaces the rustfft plans the reference builds at do_acquisition.rs:132-142 (forward at :182,
+// inverse at :188, both unnormalised).  Design (not a translation of rustfft):
+//   * forward = decimation-in-frequency, radices r1..rm, output left in mixed-radix digit-reversed
+//     order; inverse = decimation-in-time over the same stages in reverse, consuming that order and
+//     producing natural order.  The pointwise multiply by the conjugated code spectrum happens in
+//     the scrambled domain (the code spectra are produced by the same forward stages), so no
+//     permutation pass exists anywhere on the hot path.
+//   * one thread owns one radix-R butterfly entirely in registers; radix-R DFTs of odd primes use
+//     the conjugate-symmetric half form with compile-time constants (FFMA-immediate).
+//   * stage twiddles W_L^(i*q) come from one N-entry table (f64-evaluated, f32-rounded) through the
+//     read-only path.
+//   * power-of-two plans use a padded line (one complex of padding per 16) so the short-stride
+//     stages are bank-conflict free; plans whose last radix is odd need no padding.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "radix_tables.cuh"
+
+namespace gb {
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b)
+{
+    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ float2 cmul_conj(float2 a, float2 b)  // a * conj(b)
+{
+    return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
+}
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// multiply by -i (forward W_4) or +i (inverse)
+template <bool INV> __device__ __forceinline__ float2 rot90(float2 a)
+{
+    return INV ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x);
+}
+
+// ------------------------------------------------------------------ in-register DFTs
+// Dft<R,INV>::run(v): v[q] <- sum_j v[j] * exp(-/+ 2 pi i j q / R), unnormalised.
+template <int R, bool INV> struct Dft;
+
+template <bool INV> struct Dft<1, INV> {
+    static __device__ __forceinline__ void run(float2 (&)[1]) {}
+};
+
+template <bool INV> struct Dft<2, INV> {
+    static __device__ __forceinline__ void run(float2 (&v)[2])
+    {
+        const float2 a = v[0], b = v[1];
+        v[0] = cadd(a, b);
+        v[1] = csub(a, b);
+    }
+};
+
+template <bool INV> struct Dft<4, INV> {
+    static __device__ __forceinline__ void run(float2 (&v)[4])
+    {
+        const float2 a = cadd(v[0], v[2]), b = csub(v[0], v[2]);
+        const float2 c = cadd(v[1], v[3]), d = rot90<INV>(csub(v[1], v[3]));
+        v[0] = cadd(a, c);
+        v[1] = cadd(b, d);
+        v[2] = csub(a, c);
+        v[3] = csub(b, d);
+    }
+};
+
+// multiply by W_8^k (forward) / conj (inverse), k = 1, 3
+template <bool INV> __device__ __forceinline__ float2 mulw8_1(float2 a)
+{
+    const float h = 0.70710678118654752440f;
+    return INV ? make_float2((a.x - a.y) * h, (a.x + a.y) * h) : make_float2((a.x + a.y) * h, (a.y - a.x) * h);
+}
+template <bool INV> __device__ __forceinline__ float2 mulw8_3(float2 a)
+{
+    const float h = 0.70710678118654752440f;
+    return INV ? make_float2(-(a.x + a.y) * h, (a.x - a.y) * h) : make_float2((a.y - a.x) * h, -(a.x + a.y) * h);
+}
+
+template <bool INV> struct Dft<8, INV> {
+    static __device__ __forceinline__ void run(float2 (&v)[8])
+    {
+        // 2 x radix-4 over even / odd inputs, then radix-2 combine with W_8^q
+        float2 e[4] = {v[0], v[2], v[4], v[6]};
+        float2 o[4] = {v[1], v[3], v[5], v[7]};
+        Dft<4, INV>::run(e);
+        Dft<4, INV>::run(o);
+        o[1] = mulw8_1<INV>(o[1]);
+        o[2] = rot90<INV>(o[2]);
+        o[3] = mulw8_3<INV>(o[3]);
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            v[q] = cadd(e[q], o[q]);
+            v[q + 4] = csub(e[q], o[q]);
+        }
+    }
+};
+
+// multiply by exp(-/+ 2 pi i k / R) with compile-time k (generic constant twiddle)
+template <int R, bool INV> __device__ __forceinline__ float2 mulw(float2 a, int k)
+{
+    const float c = RT<R>::c(k), s = INV ? RT<R>::s(k) : -RT<R>::s(k);
+    return make_float2(a.x * c - a.y * s, a.x * s + a.y * c);
+}
+
+template <bool INV> struct Dft<16, INV> {
+    static __device__ __forceinline__ void run(float2 (&v)[16])
+    {
+        // 4 x 4: j = 4*j1 + j2, q = q1 + 4*q2
+        float2 t[4][4];
+#pragma unroll
+        for (int j2 = 0; j2 < 4; j2++) {
+            float2 c[4] = {v[j2], v[4 + j2], v[8 + j2], v[12 + j2]};
+            Dft<4, INV>::run(c);
+#pragma unroll
+            for (int q1 = 0; q1 < 4; q1++) t[q1][j2] = c[q1];
+        }
+#pragma unroll
+        for (int q1 = 0; q1 < 4; q1++) {
+            float2 c[4];
+            c[0] = t[q1][0];
+#pragma unroll
+            for (int j2 = 1; j2 < 4; j2++) {
+                const int k = j2 * q1;
+                if (k == 0) c[j2] = t[q1][j2];
+                else if (k == 4) c[j2] = rot90<INV>(t[q1][j2]);
+                else if (k == 2) c[j2] = mulw8_1<INV>(t[q1][j2]);
+                else if (k == 6) c[j2] = mulw8_3<INV>(t[q1][j2]);
+                else c[j2] = mulw<16, INV>(t[q1][j2], k);
+            }
+            Dft<4, INV>::run(c);
+#pragma unroll
+            for (int q2 = 0; q2 < 4; q2++) v[q1 + 4 * q2] = c[q2];
+        }
+    }
+};
+
+// Odd prime radix, conjugate-symmetric half form:
+//   a_j = v_j + v_{R-j}, b_j = v_j - v_{R-j}
+//   X_q, X_{R-q} = v_0 + sum_j a_j cos(2 pi j q/R)  +/-  (-/+ i) sum_j b_j sin(2 pi j q/R)
+template <int R, bool INV> struct DftOddPrime {
+    static __device__ __forceinline__ void run(float2 (&v)[R])
+    {
+        constexpr int H = (R - 1) / 2;
+        float2 a[H + 1], b[H + 1];
+        float2 x0 = v[0];
+#pragma unroll
+        for (int j = 1; j <= H; j++) {
+            a[j] = cadd(v[j], v[R - j]);
+            b[j] = csub(v[j], v[R - j]);
+            x0 = cadd(x0, a[j]);
+        }
+        const float2 v0 = v[0];
+        v[0] = x0;
+#pragma unroll
+        for (int q = 1; q <= H; q++) {
+            float cr = v0.x, ci = v0.y, sr = 0.f, si = 0.f;
+#pragma unroll
+            for (int j = 1; j <= H; j++) {
+                const int k = (j * q) % R;
+                const float c = RT<R>::c(k);
+                const float s = INV ? RT<R>::s(k) : -RT<R>::s(k);  // Im of exp(-/+ i theta)
+                cr = fmaf(a[j].x, c, cr);
+                ci = fmaf(a[j].y, c, ci);
+                sr = fmaf(-b[j].y, s, sr);  // i*s*b = s*(-b.y, b.x)
+                si = fmaf(b[j].x, s, si);
+            }
+            v[q] = make_float2(cr + sr, ci + si);
+            v[R - q] = make_float2(cr - sr, ci - si);
+        }
+    }
+};
+template <bool INV> struct Dft<3, INV> : DftOddPrime<3, INV> {};
+template <bool INV> struct Dft<5, INV> : DftOddPrime<5, INV> {};
+template <bool INV> struct Dft<7, INV> : DftOddPrime<7, INV> {};
+template <bool INV> struct Dft<11, INV> : DftOddPrime<11, INV> {};
+template <bool INV> struct Dft<13, INV> : DftOddPrime<13, INV> {};
+template <bool INV> struct Dft<17, INV> : DftOddPrime<17, INV> {};
+template <bool INV> struct Dft<19, INV> : DftOddPrime<19, INV> {};
+template <bool INV> struct Dft<23, INV> : DftOddPrime<23, INV> {};
+template <bool INV> struct Dft<29, INV> : DftOddPrime<29, INV> {};
+template <bool INV> struct Dft<31, INV> : DftOddPrime<31, INV> {};
+
+// Composite R = A*B in registers: j = j1*B + j2, q = q1 + A*q2
+template <int A, int B, bool INV> struct DftComposite {
+    static constexpr int R = A * B;
+    static __device__ __forceinline__ void run(float2 (&v)[R])
+    {
+        float2 t[A][B];
+#pragma unroll
+        for (int j2 = 0; j2 < B; j2++) {
+            float2 c[A];
+#pragma unroll
+            for (int j1 = 0; j1 < A; j1++) c[j1] = v[j1 * B + j2];
+            Dft<A, INV>::run(c);
+#pragma unroll
+            for (int q1 = 0; q1 < A; q1++) t[q1][j2] = (j2 * q1 == 0) ? c[q1] : mulw<R, INV>(c[q1], (j2 * q1) % R);
+        }
+#pragma unroll
+        for (int q1 = 0; q1 < A; q1++) {
+            float2 c[B];
+#pragma unroll
+            for (int j2 = 0; j2 < B; j2++) c[j2] = t[q1][j2];
+            Dft<B, INV>::run(c);
+#pragma unroll
+            for (int q2 = 0; q2 < B; q2++) v[q1 + A * q2] = c[q2];
+        }
+    }
+};
+template <bool INV> struct Dft<12, INV> : DftComposite<4, 3, INV> {};
+template <bool INV> struct Dft<25, INV> : DftComposite<5, 5, INV> {};
+template <bool INV> struct Dft<32, INV> : DftComposite<4, 8, INV> {};
+
+// ------------------------------------------------------------------ plan geometry
+// A plan is a compile-time list of up to 6 radices (1 = unused), the CTA size and the padding.
+template <int N_, int T_, int MINB_, int PAD_, int R0, int R1 = 1, int R2 = 1, int R3 = 1, int R4 = 1, int R5 = 1> struct Plan {
+    static constexpr int N = N_;
+    static constexpr int T = T_;
+    static constexpr int MINB = MINB_;  // CTAs per SM the register allocation must allow
+    static constexpr int PAD = PAD_;  // 0: dense; s>0: one complex of padding every 2^s
+    static constexpr int NSTAGE = (R0 > 1) + (R1 > 1) + (R2 > 1) + (R3 > 1) + (R4 > 1) + (R5 > 1);
+    static constexpr int radix(int s) { return s == 0 ? R0 : s == 1 ? R1 : s == 2 ? R2 : s == 3 ? R3 : s == 4 ? R4 : R5; }
+    // block length seen by stage s
+    static constexpr int len(int s) { return s == 0 ? N : len(s - 1) / radix(s - 1); }
+    static constexpr int sub(int s) { return len(s) / radix(s); }
+    static constexpr int LINE = PAD ? N + (N >> PAD) + 1 : N;  // complex elements of shared memory
+    static_assert(R0 * R1 * R2 * R3 * R4 * R5 == N, "radices must multiply to N");
+    static_assert(NSTAGE >= 2, "need at least two stages");
+    __device__ static __forceinline__ int phys(int i) { return PAD ? i + (i >> PAD) : i; }
+};
+
+// ------------------------------------------------------------------ stage workers
+// Iterates the butterflies of stage S owned by this thread.  F(b_iter, base, i) is called with the
+// compile-time iteration number, the logical index of element j=0 and the position i within the
+// sub-block; elements are at base + j*SUB.
+template <class P, int S> struct StageGeo {
+    static constexpr int R = P::radix(S);
+    static constexpr int L = P::len(S);
+    static constexpr int SUB = P::sub(S);
+    static constexpr int NB = P::N / R;                    // butterflies in the stage
+    static constexpr int ITERS = (NB + P::T - 1) / P::T;   // per-thread iterations
+    static constexpr int TWS = P::N / L;                   // W_L^x = tw[x * TWS]
+};
+
+// DIF stage S (INV=false: forward sign), smem -> smem
+template <class P, int S, bool INV> __device__ __forceinline__ void dif_stage(float2* __restrict__ s, const float2* __restrict__ tw)
+{
+    using G = StageGeo<P, S>;
+#pragma unroll
+    for (int it = 0; it < G::ITERS; it++) {
+        const int b = threadIdx.x + it * P::T;
+        if (G::NB % P::T == 0 || b < G::NB) {
+            const int blk = b / G::SUB, i = b - blk * G::SUB;
+            const int base = blk * G::L + i;
+            float2 v[G::R];
+#pragma unroll
+            for (int j = 0; j < G::R; j++) v[j] = s[P::phys(base + j * G::SUB)];
+            Dft<G::R, INV>::run(v);
+            s[P::phys(base)] = v[0];
+#pragma unroll
+            for (int q = 1; q < G::R; q++) {
+                if (G::SUB == 1) {
+                    s[P::phys(base + q)] = v[q];
+                } else {
+                    const float2 w = __ldg(&tw[i * q * G::TWS]);
+                    s[P::phys(base + q * G::SUB)] = INV ? cmul_conj(v[q], w) : cmul(v[q], w);
+                }
+            }
+        }
+    }
+}
+
+// DIT stage S (INV=true: inverse sign), smem -> smem; exact inverse (x radix) of dif_stage<P,S,false>
+template <class P, int S, bool INV> __device__ __forceinline__ void dit_stage(float2* __restrict__ s, const float2* __restrict__ tw)
+{
+    using G = StageGeo<P, S>;
+#pragma unroll
+    for (int it = 0; it < G::ITERS; it++) {
+        const int b = threadIdx.x + it * P::T;
+        if (G::NB % P::T == 0 || b < G::NB) {
+            const int blk = b / G::SUB, i = b - blk * G::SUB;
+            const int base = blk * G::L + i;
+            float2 v[G::R];
+            v[0] = s[P::phys(base)];
+#pragma unroll
+            for (int q = 1; q < G::R; q++) {
+                const float2 u = s[P::phys(base + q * G::SUB)];
+                if (G::SUB == 1) {
+                    v[q] = u;
+                } else {
+                    const float2 w = __ldg(&tw[i * q * G::TWS]);
+                    v[q] = INV ? cmul_conj(u, w) : cmul(u, w);
+                }
+            }
+            Dft<G::R, INV>::run(v);
+#pragma unroll
+            for (int j = 0; j < G::R; j++) s[P::phys(base + j * G::SUB)] = v[j];
+        }
+    }
+}
+
+// DIF stages [S, LAST) with a barrier after each
+template <class P, int S, int LAST, bool INV> struct DifRange {
+    static __device__ __forceinline__ void run(float2* s, const float2* tw)
+    {
+        if constexpr (S < LAST) {
+            dif_stage<P, S, INV>(s, tw);
+            __syncthreads();
+            DifRange<P, S + 1, LAST, INV>::run(s, tw);
+        }
+    }
+};
+// DIT stages S, S-1, ..., LAST+1, barrier after each
+template <class P, int S, int LAST, bool INV> struct DitRange {
+    static __device__ __forceinline__ void run(float2* s, const float2* tw)
+    {
+        if constexpr (S > LAST) {
+            dit_stage<P, S, INV>(s, tw);
+            __syncthreads();
+            DitRange<P, S - 1, LAST, INV>::run(s, tw);
+        }
+    }
+};
+
+}  // namespace gb

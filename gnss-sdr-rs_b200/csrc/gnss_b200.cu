@@ -1,0 +1,916 @@
+// gnss_b200.cu -- the C-ABI of libgnss_b200 (include/gnss_b200.h): handle, device memory, streams,
+// plan set-up and the host-side O(D) decision scan.  All sample-rate work runs in acq_kernels.cu /
+// trk_kernels.cu; there is no CPU implementation of the hot path in this library.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/gnss_b200.h"
+#include "acq_kernels.cuh"
+#include "trk_kernels.cuh"
+
+namespace {
+
+const float kCodeRate = 1.023e6f;  // GPS_L1_CA_CODE_RATE_CHIPS_PER_S (gps_property_constants.rs:4)
+const float kPiF = 3.14159265358979323846f;
+
+struct FftRes {
+    float2* tw = nullptr;
+    int* fop = nullptr;
+};
+
+}  // namespace
+
+struct gb_handle {
+    int device = 0;
+    cudaStream_t s_acq = nullptr, s_trk = nullptr, s_copy = nullptr;
+    cudaEvent_t ev_copy = nullptr, ev_a0 = nullptr, ev_a1 = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+    std::string last_err;
+
+    // sample ring
+    float2* ring = nullptr;
+    uint64_t ring_cap = 0, ring_head = 0;
+    int8_t* i8_stage = nullptr;
+    size_t i8_cap = 0;
+
+    // acquisition
+    int plan = -1, N = 0, n_prn = 0, D = 0, n_coh = 1, spc = 0;
+    float fs = 0.f, threshold = 7.0f;
+    float2 *tw = nullptr, *code_fft = nullptr, *tables = nullptr, *rot = nullptr, *chunk = nullptr;
+    int8_t* codes_dev = nullptr;
+    size_t chunk_cap = 0, tables_cap = 0, rot_cap = 0;
+    std::vector<float> carr;
+    gb_acq_cell *cells_dev = nullptr, *cells_pin = nullptr;
+    size_t cells_cap = 0;
+    int *rows_dev = nullptr, *rows_pin = nullptr;
+    float* row_dev = nullptr;
+    float last_acq_ms = 0.f;
+
+    // FFT facade
+    FftRes fft[16];
+
+    // tracking
+    int8_t* ca_table_dev = nullptr;
+    gb_trk_channel* ch_dev = nullptr;
+    int n_ch = 0, ch_cap = 0;
+    gb_trk_corr* corr_dev = nullptr;
+    uint8_t *ran_dev = nullptr, *lost_dev = nullptr;
+    float* hist_dev = nullptr;
+    size_t hist_cap = 0;
+    float2* trk_data = nullptr;
+    size_t trk_data_cap = 0;
+    unsigned long long* offs_dev = nullptr;
+    float trk_fs_max = 0.f;
+    float last_trk_ms = 0.f;
+};
+
+namespace {
+
+int fail(gb_handle* h, cudaError_t e, const char* what)
+{
+    if (h) {
+        char buf[512];
+        snprintf(buf, sizeof(buf), "%s: %s", what, cudaGetErrorString(e));
+        h->last_err = buf;
+    }
+    return (e == cudaErrorMemoryAllocation) ? GB_ENOMEM : GB_ECUDA;
+}
+#define CK(call)                                              \
+    do {                                                      \
+        cudaError_t e__ = (call);                             \
+        if (e__ != cudaSuccess) return fail(h, e__, #call);   \
+    } while (0)
+
+template <class T> int ensure(gb_handle* h, T** p, size_t* cap, size_t need)
+{
+    if (*cap >= need && *p) return GB_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *cap = 0;
+    cudaError_t e = cudaMalloc((void**)p, need * sizeof(T));
+    if (e != cudaSuccess) return fail(h, e, "cudaMalloc");
+    *cap = need;
+    return GB_OK;
+}
+
+// Rust `as usize` on f32 (saturating, NaN -> 0)
+size_t f32_as_usize(float v)
+{
+    if (!(v > 0.0f)) return 0;
+    if (v >= 18446744073709551616.0f) return (size_t)-1;
+    return (size_t)v;
+}
+
+// G2 phase-selector taps for PRN 1..32 (IS-GPS-200)
+const uint8_t kG2Taps[32][2] = {{2, 6}, {3, 7}, {4, 8}, {5, 9}, {1, 9}, {2, 10}, {1, 8}, {2, 9}, {3, 10}, {2, 3}, {3, 4},
+                                {5, 6}, {6, 7}, {7, 8}, {8, 9}, {9, 10}, {1, 4}, {2, 5}, {3, 6}, {4, 7}, {5, 8}, {6, 9},
+                                {1, 3}, {4, 6}, {5, 7}, {6, 8}, {7, 9}, {8, 10}, {1, 6}, {2, 7}, {3, 8}, {4, 9}};
+
+void ca_chips(int prn, int8_t* out)
+{
+    // two 10-bit Fibonacci LFSRs kept as bit masks: bit (k-1) = stage k
+    unsigned g1 = 0x3ff, g2 = 0x3ff;
+    const int ta = kG2Taps[prn - 1][0] - 1, tb = kG2Taps[prn - 1][1] - 1;
+    for (int c = 0; c < 1023; c++) {
+        const unsigned bit = ((g1 >> 9) ^ (g2 >> ta) ^ (g2 >> tb)) & 1u;
+        out[c] = bit ? 1 : -1;
+        const unsigned f1 = ((g1 >> 2) ^ (g1 >> 9)) & 1u;
+        const unsigned f2 = ((g2 >> 1) ^ (g2 >> 2) ^ (g2 >> 5) ^ (g2 >> 7) ^ (g2 >> 8) ^ (g2 >> 9)) & 1u;
+        g1 = ((g1 << 1) | f1) & 0x3ff;
+        g2 = ((g2 << 1) | f2) & 0x3ff;
+    }
+}
+
+// position of natural frequency k after the forward DIF with these radices
+int scrambled_pos(int k, int n, const int* radix, int ns)
+{
+    int pos = 0;
+    for (int s = 0; s < ns; s++) {
+        const int r = radix[s], m = n / r;
+        pos += (k % r) * m;
+        k /= r;
+        n = m;
+    }
+    return pos;
+}
+
+int fft_resources(gb_handle* h, int plan, int n, FftRes** out)
+{
+    FftRes& r = h->fft[plan];
+    if (!r.tw) {
+        std::vector<float2> tw(n);
+        for (int k = 0; k < n; k++) {
+            const double ang = -2.0 * M_PI * (double)k / (double)n;
+            tw[k] = make_float2((float)cos(ang), (float)sin(ang));
+        }
+        int radix[8];
+        const int ns = gb::acq_plan_radices(plan, radix);
+        std::vector<int> fop(n);
+        for (int k = 0; k < n; k++) fop[scrambled_pos(k, n, radix, ns)] = k;
+        CK(cudaMalloc((void**)&r.tw, sizeof(float2) * n));
+        CK(cudaMalloc((void**)&r.fop, sizeof(int) * n));
+        CK(cudaMemcpy(r.tw, tw.data(), sizeof(float2) * n, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(r.fop, fop.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
+    }
+    *out = &r;
+    return GB_OK;
+}
+
+__global__ void i8_to_ring_kernel(const int8_t* __restrict__ src, float2* __restrict__ ring, unsigned long long start,
+                                  unsigned long long mask, unsigned long long n)
+{
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) ring[(start + i) & mask] = make_float2((float)src[i], 0.f);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ misc
+extern "C" const char* gb_strerror(int code)
+{
+    switch (code) {
+        case GB_OK: return "ok";
+        case GB_EINVAL: return "invalid argument";
+        case GB_ENODEVICE: return "no CUDA device";
+        case GB_ECUDA: return "CUDA error";
+        case GB_EUNSUPPORTED: return "fft_size has no sm_100a plan";
+        case GB_ESTATE: return "call out of order";
+        case GB_ENOMEM: return "out of memory";
+        case GB_ERANGE: return "samples not in the ring";
+    }
+    return "unknown error";
+}
+extern "C" const char* gb_last_cuda_error(gb_handle* h) { return h ? h->last_err.c_str() : ""; }
+extern "C" int gb_version(void) { return GB_VERSION; }
+extern "C" int gb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+extern "C" int gb_create(const gb_config* cfg, gb_handle** out)
+{
+    if (!out) return GB_EINVAL;
+    *out = nullptr;
+    const int dev = cfg ? cfg->device : 0;
+    if (dev < 0 || dev >= gb_device_count()) return GB_ENODEVICE;
+    gb_handle* h = new gb_handle();
+    h->device = dev;
+    *out = h;
+    CK(cudaSetDevice(dev));
+    CK(cudaStreamCreateWithFlags(&h->s_acq, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->s_trk, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming));
+    CK(cudaEventCreate(&h->ev_a0));
+    CK(cudaEventCreate(&h->ev_a1));
+    CK(cudaEventCreate(&h->ev_t0));
+    CK(cudaEventCreate(&h->ev_t1));
+    {
+        std::vector<int8_t> tab(32 * 1023);
+        for (int p = 1; p <= 32; p++) ca_chips(p, tab.data() + (p - 1) * 1023);
+        CK(cudaMalloc((void**)&h->ca_table_dev, tab.size()));
+        CK(cudaMemcpy(h->ca_table_dev, tab.data(), tab.size(), cudaMemcpyHostToDevice));
+    }
+    CK(cudaMallocHost((void**)&h->rows_pin, sizeof(int) * 256));
+    CK(cudaMalloc((void**)&h->rows_dev, sizeof(int) * 256));
+    if (cfg && cfg->ring_capacity) return gb_ring_create(h, cfg->ring_capacity);
+    return GB_OK;
+}
+
+extern "C" int gb_destroy(gb_handle* h)
+{
+    if (!h) return GB_EINVAL;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    void* dev_ptrs[] = {h->ring, h->i8_stage, h->tw, h->code_fft, h->tables, h->rot, h->chunk, h->codes_dev, h->cells_dev,
+                        h->rows_dev, h->row_dev, h->ca_table_dev, h->ch_dev, h->corr_dev, h->ran_dev, h->lost_dev,
+                        h->hist_dev, h->trk_data, h->offs_dev};
+    for (void* p : dev_ptrs)
+        if (p) cudaFree(p);
+    for (auto& r : h->fft) {
+        if (r.tw) cudaFree(r.tw);
+        if (r.fop) cudaFree(r.fop);
+    }
+    if (h->cells_pin) cudaFreeHost(h->cells_pin);
+    if (h->rows_pin) cudaFreeHost(h->rows_pin);
+    if (h->s_acq) cudaStreamDestroy(h->s_acq);
+    if (h->s_trk) cudaStreamDestroy(h->s_trk);
+    if (h->s_copy) cudaStreamDestroy(h->s_copy);
+    cudaEvent_t evs[] = {h->ev_copy, h->ev_a0, h->ev_a1, h->ev_t0, h->ev_t1};
+    for (cudaEvent_t e : evs)
+        if (e) cudaEventDestroy(e);
+    delete h;
+    return GB_OK;
+}
+
+extern "C" int gb_synchronize(gb_handle* h)
+{
+    if (!h) return GB_EINVAL;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->s_copy));
+    CK(cudaStreamSynchronize(h->s_acq));
+    CK(cudaStreamSynchronize(h->s_trk));
+    return GB_OK;
+}
+
+// ------------------------------------------------------------------ C/A code (host)
+extern "C" int gb_ca_code_chips(int prn, int8_t* out1023)
+{
+    if (prn < 1 || prn > 32 || !out1023) return GB_EINVAL;
+    ca_chips(prn, out1023);
+    return GB_OK;
+}
+// ca_code.rs:13-17
+extern "C" int gb_num_samples_per_code(float code_rate, float fs) { return (int)f32_as_usize(roundf(fs / (code_rate / 1023.0f))); }
+// ca_code.rs:12-27; the index arithmetic stays in f32 in the reference's order (Q3)
+extern "C" int gb_generate_ca_code_samples(int prn, float code_rate, float fs, int8_t* out, int cap)
+{
+    if (prn < 1 || prn > 32 || !out) return GB_EINVAL;
+    int8_t chips[1023];
+    ca_chips(prn, chips);
+    const int n = gb_num_samples_per_code(code_rate, fs);
+    for (int x = 0; x < n && x < cap; x++) {
+        const size_t ind = f32_as_usize(floorf((float)x * code_rate / fs));
+        if (ind >= 1023) return GB_EINVAL;  // the reference panics (index out of bounds)
+        out[x] = chips[ind];
+    }
+    return n;
+}
+
+// ------------------------------------------------------------------ sample ring
+extern "C" int gb_ring_create(gb_handle* h, uint64_t cap)
+{
+    if (!h || cap == 0 || (cap & (cap - 1))) return GB_EINVAL;  // MulticastRingBuffer::new asserts power of two
+    CK(cudaSetDevice(h->device));
+    if (h->ring) cudaFree(h->ring);
+    h->ring = nullptr;
+    CK(cudaMalloc((void**)&h->ring, cap * sizeof(float2)));
+    CK(cudaMemset(h->ring, 0, cap * sizeof(float2)));
+    h->ring_cap = cap;
+    h->ring_head = 0;
+    return GB_OK;
+}
+extern "C" int gb_ring_reset(gb_handle* h)
+{
+    if (!h || !h->ring) return GB_ESTATE;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->s_copy));
+    h->ring_head = 0;
+    return GB_OK;
+}
+// write_samples (multicast_ring_buffer.rs:66-101): wrap-aware copy at head & mask, then head += n
+extern "C" int gb_ring_write(gb_handle* h, const gb_c32* samples, uint64_t n)
+{
+    if (!h || !h->ring) return GB_ESTATE;
+    if (!samples || n > h->ring_cap) return GB_EINVAL;
+    CK(cudaSetDevice(h->device));
+    const uint64_t start = h->ring_head & (h->ring_cap - 1);
+    const uint64_t first = (start + n <= h->ring_cap) ? n : h->ring_cap - start;
+    CK(cudaMemcpyAsync(h->ring + start, samples, first * sizeof(float2), cudaMemcpyHostToDevice, h->s_copy));
+    if (first < n)
+        CK(cudaMemcpyAsync(h->ring, samples + first, (n - first) * sizeof(float2), cudaMemcpyHostToDevice, h->s_copy));
+    CK(cudaEventRecord(h->ev_copy, h->s_copy));
+    h->ring_head += n;
+    return GB_OK;
+}
+extern "C" int gb_ring_write_i8(gb_handle* h, const int8_t* samples, uint64_t n)
+{
+    if (!h || !h->ring) return GB_ESTATE;
+    if (!samples || n > h->ring_cap) return GB_EINVAL;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->s_copy));  // the staging buffer is reused
+    int rc = ensure(h, &h->i8_stage, &h->i8_cap, (size_t)n);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(h->i8_stage, samples, n, cudaMemcpyHostToDevice, h->s_copy));
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    i8_to_ring_kernel<<<blocks, 256, 0, h->s_copy>>>(h->i8_stage, h->ring, h->ring_head, h->ring_cap - 1, n);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(h->ev_copy, h->s_copy));
+    h->ring_head += n;
+    return GB_OK;
+}
+extern "C" uint64_t gb_ring_head(gb_handle* h) { return h ? h->ring_head : 0; }
+// copy_to_slice (multicast_ring_buffer.rs:107-129)
+extern "C" int gb_ring_copy_to_slice(gb_handle* h, uint64_t start, gb_c32* dest, uint64_t n)
+{
+    if (!h || !h->ring) return GB_ESTATE;
+    if (!dest || n > h->ring_cap) return GB_EINVAL;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->s_copy));
+    const uint64_t ps = start & (h->ring_cap - 1);
+    const uint64_t first = (ps + n <= h->ring_cap) ? n : h->ring_cap - ps;
+    CK(cudaMemcpy(dest, h->ring + ps, first * sizeof(float2), cudaMemcpyDeviceToHost));
+    if (first < n) CK(cudaMemcpy(dest + first, h->ring, (n - first) * sizeof(float2), cudaMemcpyDeviceToHost));
+    return GB_OK;
+}
+
+// ------------------------------------------------------------------ acquisition set-up
+extern "C" int gb_acq_supported_sizes(int* sizes, int cap) { return gb::acq_plan_sizes(sizes, cap); }
+
+extern "C" int gb_acq_configure(gb_handle* h, int fft_size, float fs, int n_prn, const int8_t* codes)
+{
+    if (!h || n_prn < 1 || n_prn > 255 || !(fs > 0.f)) return GB_EINVAL;
+    if (!codes && n_prn > 32) return GB_EINVAL;
+    if (fft_size % 4 != 0) return GB_EUNSUPPORTED;  // apply_doppler_shift leaves len%4 samples stale (A3)
+    const int plan = gb::acq_plan_index(fft_size);
+    if (plan < 0) return GB_EUNSUPPORTED;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->s_acq));
+    std::vector<int8_t> host_codes;
+    if (!codes) {
+        // AcquisitionWorker::new (:133-135): generate_ca_code_samples(prn, 1.023e6, fs)
+        const int n_code = gb_num_samples_per_code(kCodeRate, fs);
+        if (n_code != fft_size) return GB_EINVAL;  // rustfft would panic on the length mismatch
+        host_codes.resize((size_t)n_prn * fft_size);
+        for (int p = 1; p <= n_prn; p++) {
+            const int rc = gb_generate_ca_code_samples(p, kCodeRate, fs, host_codes.data() + (size_t)(p - 1) * fft_size, fft_size);
+            if (rc < 0) return rc;
+        }
+        codes = host_codes.data();
+    }
+    FftRes* fr;
+    int rc = fft_resources(h, plan, fft_size, &fr);
+    if (rc) return rc;
+    if (h->code_fft) cudaFree(h->code_fft);
+    if (h->codes_dev) cudaFree(h->codes_dev);
+    if (h->row_dev) cudaFree(h->row_dev);
+    h->code_fft = nullptr; h->codes_dev = nullptr; h->row_dev = nullptr;
+    const size_t total = (size_t)n_prn * fft_size;
+    CK(cudaMalloc((void**)&h->code_fft, total * sizeof(float2)));
+    CK(cudaMalloc((void**)&h->codes_dev, total));
+    CK(cudaMalloc((void**)&h->row_dev, sizeof(float) * fft_size));
+    CK(cudaMemcpyAsync(h->codes_dev, codes, total, cudaMemcpyHostToDevice, h->s_acq));
+    CK(gb::acq_launch_code_fft(plan, h->codes_dev, n_prn, h->code_fft, fr->tw, h->s_acq));
+    CK(cudaStreamSynchronize(h->s_acq));
+    h->plan = plan; h->N = fft_size; h->n_prn = n_prn; h->fs = fs; h->tw = fr->tw;
+    h->D = 0; h->n_coh = 1;
+    h->carr.clear();
+    return GB_OK;
+}
+
+static int upload_rotators(gb_handle* h)
+{
+    if (h->n_coh <= 1 || h->D == 0) return GB_OK;
+    // rot[d][c] = exp(-j 2 pi carr_d c N / fs), f64-evaluated
+    std::vector<float2> rot((size_t)h->D * h->n_coh);
+    for (int d = 0; d < h->D; d++)
+        for (int c = 0; c < h->n_coh; c++) {
+            const double cyc = (double)h->carr[d] * (double)c * (double)h->N / (double)h->fs;
+            const double ang = -2.0 * M_PI * (cyc - floor(cyc));
+            rot[(size_t)d * h->n_coh + c] = make_float2((float)cos(ang), (float)sin(ang));
+        }
+    int rc = ensure(h, &h->rot, &h->rot_cap, rot.size());
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(h->rot, rot.data(), rot.size() * sizeof(float2), cudaMemcpyHostToDevice, h->s_acq));
+    CK(cudaStreamSynchronize(h->s_acq));
+    return GB_OK;
+}
+
+extern "C" int gb_acq_make_doppler_tables(gb_handle* h, float f_if, const float* dopplers, int D, float* carr_out)
+{
+    if (!h || !dopplers || D < 1 || D > 32767) return GB_EINVAL;
+    if (h->plan < 0) return GB_ESTATE;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->s_acq));
+    int rc = ensure(h, &h->tables, &h->tables_cap, (size_t)D * h->N);
+    if (rc) return rc;
+    std::vector<float> steps(D);
+    h->carr.resize(D);
+    for (int d = 0; d < D; d++) {
+        const float carr = f_if + dopplers[d];                 // doppler_shift.rs:13
+        steps[d] = 2.0f * kPiF * carr / h->fs;                 // :14
+        h->carr[d] = carr;                                     // :20
+        if (carr_out) carr_out[d] = carr;
+    }
+    float* steps_dev = nullptr;
+    CK(cudaMalloc((void**)&steps_dev, sizeof(float) * D));
+    CK(cudaMemcpyAsync(steps_dev, steps.data(), sizeof(float) * D, cudaMemcpyHostToDevice, h->s_acq));
+    cudaError_t e = gb::acq_launch_doppler_tables(steps_dev, D, h->N, h->tables, h->s_acq);
+    cudaStreamSynchronize(h->s_acq);
+    cudaFree(steps_dev);
+    if (e != cudaSuccess) return fail(h, e, "doppler_table_kernel");
+    h->D = D;
+    return upload_rotators(h);
+}
+
+extern "C" int gb_acq_set_doppler_tables(gb_handle* h, const gb_c32* tables, const float* carr, int D)
+{
+    if (!h || !tables || !carr || D < 1 || D > 32767) return GB_EINVAL;
+    if (h->plan < 0) return GB_ESTATE;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->s_acq));
+    int rc = ensure(h, &h->tables, &h->tables_cap, (size_t)D * h->N);
+    if (rc) return rc;
+    CK(cudaMemcpy(h->tables, tables, (size_t)D * h->N * sizeof(float2), cudaMemcpyHostToDevice));
+    h->carr.assign(carr, carr + D);
+    h->D = D;
+    return upload_rotators(h);
+}
+
+extern "C" int gb_acq_get_doppler_tables(gb_handle* h, gb_c32* tables_out, float* carr_out)
+{
+    if (!h) return GB_EINVAL;
+    if (h->plan < 0 || h->D == 0) return GB_ESTATE;
+    CK(cudaSetDevice(h->device));
+    if (tables_out) CK(cudaMemcpy(tables_out, h->tables, (size_t)h->D * h->N * sizeof(float2), cudaMemcpyDeviceToHost));
+    if (carr_out) memcpy(carr_out, h->carr.data(), sizeof(float) * h->D);
+    return GB_OK;
+}
+
+extern "C" int gb_acq_set_coherent(gb_handle* h, int n_coh)
+{
+    if (!h || n_coh < 1 || n_coh > 1024) return GB_EINVAL;
+    if (h->plan < 0) return GB_ESTATE;
+    CK(cudaSetDevice(h->device));
+    h->n_coh = n_coh;
+    return upload_rotators(h);
+}
+
+extern "C" int gb_acq_set_detector(gb_handle* h, float threshold, int samples_per_chip)
+{
+    if (!h || samples_per_chip < 0) return GB_EINVAL;
+    h->threshold = threshold;
+    h->spc = samples_per_chip;
+    return GB_OK;
+}
+
+// ------------------------------------------------------------------ acquisition search
+static int build_rows(gb_handle* h, uint32_t prn_mask, const uint8_t* enable)
+{
+    int n = 0;
+    for (int p = 0; p < h->n_prn; p++) {
+        const bool on = enable ? enable[p] != 0 : (p < 32 ? ((prn_mask >> p) & 1u) != 0 : true);
+        if (on) h->rows_pin[n++] = p;
+    }
+    return n;
+}
+
+static int search_cells(gb_handle* h, const float2* iq_dev, uint64_t start, uint64_t mask, int K, uint32_t prn_mask,
+                        const uint8_t* enable, gb_acq_cell* cells_out)
+{
+    if (h->plan < 0 || h->D == 0) return GB_ESTATE;
+    if (K < 1 || K % h->n_coh != 0) return GB_EINVAL;
+    const size_t n_cells = (size_t)h->n_prn * h->D;
+    if (h->cells_cap < n_cells) {
+        if (h->cells_dev) cudaFree(h->cells_dev);
+        if (h->cells_pin) cudaFreeHost(h->cells_pin);
+        h->cells_dev = nullptr; h->cells_pin = nullptr; h->cells_cap = 0;
+        CK(cudaMalloc((void**)&h->cells_dev, n_cells * sizeof(gb_acq_cell)));
+        CK(cudaMallocHost((void**)&h->cells_pin, n_cells * sizeof(gb_acq_cell)));
+        h->cells_cap = n_cells;
+    }
+    const int n_active = build_rows(h, prn_mask, enable);
+    CK(cudaMemsetAsync(h->cells_dev, 0, n_cells * sizeof(gb_acq_cell), h->s_acq));
+    if (n_active > 0) {
+        CK(cudaMemcpyAsync(h->rows_dev, h->rows_pin, sizeof(int) * n_active, cudaMemcpyHostToDevice, h->s_acq));
+        gb::AcqArgs a;
+        a.iq = iq_dev; a.iq_start = start; a.iq_mask = mask;
+        a.tables = h->tables; a.code_fft = h->code_fft; a.tw = h->tw;
+        a.rot = h->n_coh > 1 ? h->rot : nullptr;
+        a.rows = h->rows_dev;
+        a.D = h->D; a.K = K; a.n_coh = h->n_coh; a.n_active = n_active; a.spc = h->spc;
+        a.cells = h->cells_dev; a.row_out = nullptr; a.d0 = 0;
+        CK(cudaEventRecord(h->ev_a0, h->s_acq));
+        CK(gb::acq_launch_search(h->plan, a, h->s_acq));
+        CK(cudaEventRecord(h->ev_a1, h->s_acq));
+    }
+    CK(cudaMemcpyAsync(h->cells_pin, h->cells_dev, n_cells * sizeof(gb_acq_cell), cudaMemcpyDeviceToHost, h->s_acq));
+    CK(cudaStreamSynchronize(h->s_acq));
+    if (n_active > 0) CK(cudaEventElapsedTime(&h->last_acq_ms, h->ev_a0, h->ev_a1));
+    else h->last_acq_ms = 0.f;
+    if (cells_out) memcpy(cells_out, h->cells_pin, n_cells * sizeof(gb_acq_cell));
+    return GB_OK;
+}
+
+static int stage_chunk(gb_handle* h, const gb_c32* iq, int K)
+{
+    if (!iq || K < 1) return GB_EINVAL;
+    if (h->plan < 0) return GB_ESTATE;
+    const size_t n = (size_t)K * h->N;
+    int rc = ensure(h, &h->chunk, &h->chunk_cap, n);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(h->chunk, iq, n * sizeof(float2), cudaMemcpyHostToDevice, h->s_acq));
+    return GB_OK;
+}
+
+extern "C" int gb_acq_search_cells(gb_handle* h, const gb_c32* iq, int K, uint32_t prn_mask, const uint8_t* enable,
+                                   gb_acq_cell* cells_out)
+{
+    if (!h) return GB_EINVAL;
+    CK(cudaSetDevice(h->device));
+    int rc = stage_chunk(h, iq, K);
+    if (rc) return rc;
+    return search_cells(h, h->chunk, 0, ~0ull, K, prn_mask, enable, cells_out);
+}
+
+static int ring_range_ok(gb_handle* h, uint64_t local_tail, uint64_t n)
+{
+    if (!h->ring) return GB_ESTATE;
+    if (local_tail + n > h->ring_head) return GB_ERANGE;             // not written yet
+    if (h->ring_head - local_tail > h->ring_cap) return GB_ERANGE;   // already overwritten
+    return GB_OK;
+}
+
+extern "C" int gb_acq_search_cells_ring(gb_handle* h, uint64_t local_tail, int K, uint32_t prn_mask,
+                                        const uint8_t* enable, gb_acq_cell* cells_out)
+{
+    if (!h || K < 1) return GB_EINVAL;
+    if (h->plan < 0) return GB_ESTATE;
+    CK(cudaSetDevice(h->device));
+    int rc = ring_range_ok(h, local_tail, (uint64_t)K * h->N);
+    if (rc) return rc;
+    CK(cudaStreamWaitEvent(h->s_acq, h->ev_copy, 0));
+    return search_cells(h, h->ring, local_tail, h->ring_cap - 1, K, prn_mask, enable, cells_out);
+}
+
+// is_good_satellite on a cell (do_acquisition.rs:235-237)
+static inline float cell_metric(float peak, float sum8, int fft_size)
+{
+    const float avg = (sum8 - peak) / (float)(fft_size - 1);
+    return peak / avg;
+}
+
+// search_satellite's control flow (do_acquisition.rs:171-223) on per-bin cells (Q1): running best with strict '>',
+// tested after every bin; the first bin at which the running best passes wins.
+extern "C" int gb_acq_decide(const gb_acq_cell* cells, const float* carr, int D, int prn, int fft_size, float fs,
+                             uint64_t local_tail, float threshold, gb_acq_result* out)
+{
+    if (!cells || !carr || !out || D < 1 || fft_size < 2) return GB_EINVAL;
+    memset(out, 0, sizeof(*out));
+    out->prn = (uint8_t)prn;
+    out->doppler_bin = -1;
+    float gmax = 0.0f, gsum = 0.0f, gfreq = 0.0f, gp2 = 0.0f;
+    uint32_t gphase = 0;
+    int gbin = -1;
+    for (int d = 0; d < D; d++) {
+        if (cells[d].peak > gmax) {
+            gmax = cells[d].peak; gsum = cells[d].sum8; gphase = cells[d].argmax; gfreq = carr[d]; gp2 = cells[d].peak2;
+            gbin = d;
+        }
+        const float metric = cell_metric(gmax, gsum, fft_size);  // 0/0 = NaN before any record -> false
+        if (metric > threshold) {
+            out->found = 1;
+            out->doppler_bin = (int16_t)gbin;
+            out->code_phase_samples = gphase;
+            out->code_phase_chips = (float)gphase * kCodeRate / fs;  // :213-214
+            out->carrier_freq = gfreq;
+            out->fs = fs;
+            out->mag_relative = gmax;
+            out->sample_global_index = local_tail + gphase;
+            out->metric = metric;
+            out->peak_ratio = gp2 > 0.f ? sqrtf(gmax / gp2) : 0.f;
+            return GB_OK;
+        }
+    }
+    return GB_OK;
+}
+
+static int decide_all(gb_handle* h, uint64_t local_tail, uint32_t prn_mask, const uint8_t* enable, gb_acq_result* results)
+{
+    for (int p = 0; p < h->n_prn; p++) {
+        const bool on = enable ? enable[p] != 0 : (p < 32 ? ((prn_mask >> p) & 1u) != 0 : true);
+        if (on) {
+            int rc = gb_acq_decide(h->cells_pin + (size_t)p * h->D, h->carr.data(), h->D, p + 1, h->N, h->fs, local_tail,
+                                   h->threshold, &results[p]);
+            if (rc) return rc;
+        } else {
+            memset(&results[p], 0, sizeof(gb_acq_result));
+            results[p].prn = (uint8_t)(p + 1);
+            results[p].doppler_bin = -1;
+        }
+    }
+    return GB_OK;
+}
+
+extern "C" int gb_acq_search(gb_handle* h, const gb_c32* iq, int K, uint64_t local_tail, uint32_t prn_mask,
+                             const uint8_t* enable, gb_acq_result* results)
+{
+    if (!results) return GB_EINVAL;
+    int rc = gb_acq_search_cells(h, iq, K, prn_mask, enable, nullptr);
+    if (rc) return rc;
+    return decide_all(h, local_tail, prn_mask, enable, results);
+}
+
+extern "C" int gb_acq_search_ring(gb_handle* h, uint64_t local_tail, int K, uint32_t prn_mask, const uint8_t* enable,
+                                  gb_acq_result* results)
+{
+    if (!results) return GB_EINVAL;
+    int rc = gb_acq_search_cells_ring(h, local_tail, K, prn_mask, enable, nullptr);
+    if (rc) return rc;
+    return decide_all(h, local_tail, prn_mask, enable, results);
+}
+
+extern "C" int gb_acq_bin_power(gb_handle* h, const gb_c32* iq, int K, int prn, int doppler_bin, float* power_out)
+{
+    if (!h || !power_out) return GB_EINVAL;
+    if (h->plan < 0 || h->D == 0) return GB_ESTATE;
+    if (prn < 1 || prn > h->n_prn || doppler_bin < 0 || doppler_bin >= h->D || K % h->n_coh != 0) return GB_EINVAL;
+    CK(cudaSetDevice(h->device));
+    int rc = stage_chunk(h, iq, K);
+    if (rc) return rc;
+    h->rows_pin[0] = prn - 1;
+    CK(cudaMemcpyAsync(h->rows_dev, h->rows_pin, sizeof(int), cudaMemcpyHostToDevice, h->s_acq));
+    gb::AcqArgs a;
+    a.iq = h->chunk; a.iq_start = 0; a.iq_mask = ~0ull;
+    a.tables = h->tables; a.code_fft = h->code_fft; a.tw = h->tw;
+    a.rot = h->n_coh > 1 ? h->rot : nullptr;
+    a.rows = h->rows_dev;
+    a.D = h->D; a.K = K; a.n_coh = h->n_coh; a.n_active = 1; a.spc = 0;
+    a.cells = nullptr; a.row_out = h->row_dev; a.d0 = doppler_bin;
+    CK(gb::acq_launch_row(h->plan, a, h->s_acq));
+    CK(cudaMemcpyAsync(power_out, h->row_dev, sizeof(float) * h->N, cudaMemcpyDeviceToHost, h->s_acq));
+    CK(cudaStreamSynchronize(h->s_acq));
+    return GB_OK;
+}
+
+extern "C" float gb_acq_last_kernel_ms(gb_handle* h) { return h ? h->last_acq_ms : 0.f; }
+
+// ------------------------------------------------------------------ FFT facade (fft.rs:5-56)
+static int fft_common(gb_handle* h, int n, int inverse, const void* in, void* out, int batch, int real_in, int power_out,
+                      int n_out)
+{
+    if (!h || !in || !out || batch < 1) return GB_EINVAL;
+    const int plan = gb::acq_plan_index(n);
+    if (plan < 0) return GB_EUNSUPPORTED;
+    CK(cudaSetDevice(h->device));
+    FftRes* fr;
+    int rc = fft_resources(h, plan, n, &fr);
+    if (rc) return rc;
+    const size_t in_bytes = (size_t)batch * n * (real_in ? sizeof(float) : sizeof(float2));
+    const size_t out_bytes = (size_t)batch * n_out * (power_out ? sizeof(float) : sizeof(float2));
+    void *din = nullptr, *dout = nullptr;
+    CK(cudaMalloc(&din, in_bytes));
+    cudaError_t e = cudaMalloc(&dout, out_bytes);
+    if (e != cudaSuccess) { cudaFree(din); return fail(h, e, "cudaMalloc"); }
+    gb::FftArgs a;
+    a.in = din; a.out = dout; a.tw = fr->tw; a.freq_of_pos = fr->fop;
+    a.real_in = real_in; a.power_out = power_out; a.n_out = n_out;
+    e = cudaMemcpyAsync(din, in, in_bytes, cudaMemcpyHostToDevice, h->s_acq);
+    if (e == cudaSuccess) e = gb::acq_launch_fft(plan, inverse, a, batch, h->s_acq);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, dout, out_bytes, cudaMemcpyDeviceToHost, h->s_acq);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->s_acq);
+    cudaFree(din);
+    cudaFree(dout);
+    if (e != cudaSuccess) return fail(h, e, "fft");
+    return GB_OK;
+}
+extern "C" int gb_fft_c2c(gb_handle* h, int n, int inverse, const gb_c32* in, gb_c32* out, int batch)
+{
+    return fft_common(h, n, inverse, in, out, batch, 0, 0, n);
+}
+extern "C" int gb_fft_power_spectrum(gb_handle* h, int n, const gb_c32* in, float* out, int batch)
+{
+    return fft_common(h, n, 0, in, out, batch, 0, 1, n);
+}
+extern "C" int gb_rfft(gb_handle* h, int n, const float* in, gb_c32* out, int batch)
+{
+    return fft_common(h, n, 0, in, out, batch, 1, 0, n / 2 + 1);
+}
+
+// ------------------------------------------------------------------ tracking: host helpers
+// LoopFilter::new (do_tracking.rs:59-64)
+extern "C" int gb_loop_filter_new(float noise_bw, float damping, float gain, float* tau1, float* tau2)
+{
+    if (!tau1 || !tau2) return GB_EINVAL;
+    const float w = noise_bw * 8.0f * damping / (4.0f * powf(damping, 2.0f) + 1.0f);
+    *tau1 = gain / (w * w);
+    *tau2 = (2.0f * damping) / w;
+    return GB_OK;
+}
+// TrackingChannel::new (do_tracking.rs:118-146, constants :16-29)
+extern "C" int gb_trk_channel_init(gb_trk_channel* c, uint8_t id, float fs)
+{
+    if (!c) return GB_EINVAL;
+    memset(c, 0, sizeof(*c));
+    c->id = id;
+    c->state = GB_TRK_IDLE;
+    c->fs = fs;
+    c->num_samples_per_code = (uint64_t)gb_num_samples_per_code(kCodeRate, fs);
+    c->code_rate = kCodeRate;
+    gb_loop_filter_new(25.0f, 0.7f, 0.25f, &c->pll_tau1, &c->pll_tau2);
+    gb_loop_filter_new(2.0f, 0.7f, 1.0f, &c->dll_tau1, &c->dll_tau2);
+    return GB_OK;
+}
+// TrackingChannel::start (do_tracking.rs:148-154, Q8); code_row = prn reproduces Q6
+extern "C" int gb_trk_channel_start(gb_trk_channel* c, const gb_acq_result* r)
+{
+    if (!c || !r) return GB_EINVAL;
+    c->prn = r->prn;
+    c->code_row = r->prn;
+    c->carrier_freq = r->carrier_freq;
+    c->code_phase = r->code_phase_chips;
+    c->next_sample_index = r->sample_global_index;
+    c->state = GB_TRK_TRACKING;
+    return GB_OK;
+}
+// TrackingChannel::reset (do_tracking.rs:311-326, Q9)
+extern "C" int gb_trk_channel_reset(gb_trk_channel* c)
+{
+    if (!c) return GB_EINVAL;
+    c->prn = 0; c->code_row = 0; c->state = GB_TRK_IDLE; c->lost_counter = 0; c->next_sample_index = 0;
+    c->carrier_freq = 0; c->carrier_phase = 0; c->carrier_error = 0; c->carrier_nco = 0;
+    c->code_phase = 0; c->code_error = 0; c->code_nco = 0; c->code_rate = 0;
+    c->i_prompt = 0; c->q_prompt = 0;
+    return GB_OK;
+}
+
+// ------------------------------------------------------------------ tracking: device
+static int trk_reserve(gb_handle* h, int n)
+{
+    if (n <= h->ch_cap) return GB_OK;
+    void* olds[] = {h->ch_dev, h->corr_dev, h->ran_dev, h->lost_dev, h->offs_dev};
+    for (void* p : olds)
+        if (p) cudaFree(p);
+    h->ch_dev = nullptr; h->corr_dev = nullptr; h->ran_dev = nullptr; h->lost_dev = nullptr; h->offs_dev = nullptr;
+    h->ch_cap = 0;
+    CK(cudaMalloc((void**)&h->ch_dev, sizeof(gb_trk_channel) * n));
+    CK(cudaMalloc((void**)&h->corr_dev, sizeof(gb_trk_corr) * n));
+    CK(cudaMalloc((void**)&h->ran_dev, n));
+    CK(cudaMalloc((void**)&h->lost_dev, n));
+    CK(cudaMalloc((void**)&h->offs_dev, sizeof(unsigned long long) * n));
+    h->ch_cap = n;
+    return GB_OK;
+}
+
+static int trk_validate(const gb_trk_channel* ch, int n, float* fs_max)
+{
+    float m = 0.f;
+    for (int c = 0; c < n; c++) {
+        if (ch[c].code_row >= 32) return GB_EINVAL;  // GPS_CA_CODE_32_PRN[32] is out of bounds in the reference (Q6)
+        if (ch[c].fs > m) m = ch[c].fs;
+    }
+    *fs_max = m;
+    return GB_OK;
+}
+
+static int trk_n_max(float fs_max)
+{
+    const int nominal = gb_num_samples_per_code(kCodeRate, fs_max);
+    return nominal + nominal / 64 + 16;
+}
+
+extern "C" int gb_trk_upload(gb_handle* h, const gb_trk_channel* ch, int n)
+{
+    if (!h || !ch || n < 1) return GB_EINVAL;
+    CK(cudaSetDevice(h->device));
+    float fs_max;
+    int rc = trk_validate(ch, n, &fs_max);
+    if (rc) return rc;
+    rc = trk_reserve(h, n);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(h->ch_dev, ch, sizeof(gb_trk_channel) * n, cudaMemcpyHostToDevice, h->s_trk));
+    CK(cudaMemsetAsync(h->corr_dev, 0, sizeof(gb_trk_corr) * n, h->s_trk));
+    CK(cudaStreamSynchronize(h->s_trk));
+    h->n_ch = n;
+    h->trk_fs_max = fs_max;
+    return GB_OK;
+}
+
+extern "C" int gb_trk_download(gb_handle* h, gb_trk_channel* ch, int n)
+{
+    if (!h || !ch || n < 1 || n > h->n_ch) return GB_EINVAL;
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync(ch, h->ch_dev, sizeof(gb_trk_channel) * n, cudaMemcpyDeviceToHost, h->s_trk));
+    CK(cudaStreamSynchronize(h->s_trk));
+    return GB_OK;
+}
+
+static int trk_launch_ring(gb_handle* h, int n_epochs, int mode, int filters, float* hist_dev)
+{
+    gb::TrkArgs a;
+    a.samples = h->ring; a.mask = h->ring_cap - 1; a.head = h->ring_head; a.capacity = h->ring_cap;
+    a.offsets = nullptr;
+    a.ch = h->ch_dev; a.ca_table = h->ca_table_dev;
+    a.n_channels = h->n_ch; a.n_epochs = n_epochs; a.filters = filters; a.n_max = trk_n_max(h->trk_fs_max);
+    a.corr = h->corr_dev; a.prompt_hist = hist_dev; a.ran = h->ran_dev; a.lost = h->lost_dev;
+    CK(cudaStreamWaitEvent(h->s_trk, h->ev_copy, 0));
+    CK(cudaEventRecord(h->ev_t0, h->s_trk));
+    CK(gb::trk_launch(a, mode, h->s_trk));
+    CK(cudaEventRecord(h->ev_t1, h->s_trk));
+    return GB_OK;
+}
+
+extern "C" int gb_trk_run(gb_handle* h, int n_epochs, int mode, float* prompt_hist)
+{
+    if (!h || n_epochs < 1 || (mode != GB_TRK_FAST && mode != GB_TRK_ORDERED)) return GB_EINVAL;
+    if (!h->ring || h->n_ch == 0) return GB_ESTATE;
+    CK(cudaSetDevice(h->device));
+    float* hist_dev = nullptr;
+    const size_t hist_n = (size_t)n_epochs * h->n_ch * 2;
+    if (prompt_hist) {
+        int rc = ensure(h, &h->hist_dev, &h->hist_cap, hist_n);
+        if (rc) return rc;
+        CK(cudaMemsetAsync(h->hist_dev, 0, hist_n * sizeof(float), h->s_trk));
+        hist_dev = h->hist_dev;
+    }
+    int rc = trk_launch_ring(h, n_epochs, mode, 1, hist_dev);
+    if (rc) return rc;
+    if (prompt_hist) CK(cudaMemcpyAsync(prompt_hist, h->hist_dev, hist_n * sizeof(float), cudaMemcpyDeviceToHost, h->s_trk));
+    CK(cudaStreamSynchronize(h->s_trk));
+    CK(cudaEventElapsedTime(&h->last_trk_ms, h->ev_t0, h->ev_t1));
+    return GB_OK;
+}
+
+extern "C" int gb_trk_epoch(gb_handle* h, gb_trk_channel* ch, int n, int mode, gb_trk_corr* out, uint8_t* ran, uint8_t* lost)
+{
+    if (!h || !ch || n < 1 || (mode != GB_TRK_FAST && mode != GB_TRK_ORDERED)) return GB_EINVAL;
+    if (!h->ring) return GB_ESTATE;
+    int rc = gb_trk_upload(h, ch, n);
+    if (rc) return rc;
+    rc = trk_launch_ring(h, 1, mode, 1, nullptr);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(ch, h->ch_dev, sizeof(gb_trk_channel) * n, cudaMemcpyDeviceToHost, h->s_trk));
+    if (out) CK(cudaMemcpyAsync(out, h->corr_dev, sizeof(gb_trk_corr) * n, cudaMemcpyDeviceToHost, h->s_trk));
+    if (ran) CK(cudaMemcpyAsync(ran, h->ran_dev, n, cudaMemcpyDeviceToHost, h->s_trk));
+    if (lost) CK(cudaMemcpyAsync(lost, h->lost_dev, n, cudaMemcpyDeviceToHost, h->s_trk));
+    CK(cudaStreamSynchronize(h->s_trk));
+    CK(cudaEventElapsedTime(&h->last_trk_ms, h->ev_t0, h->ev_t1));
+    return GB_OK;
+}
+
+extern "C" int gb_trk_correlate(gb_handle* h, gb_trk_channel* ch, int n, const gb_c32* data, const uint64_t* offsets,
+                                int mode, gb_trk_corr* out)
+{
+    if (!h || !ch || !data || !offsets || !out || n < 1 || (mode != GB_TRK_FAST && mode != GB_TRK_ORDERED))
+        return GB_EINVAL;
+    int rc = gb_trk_upload(h, ch, n);
+    if (rc) return rc;
+    size_t total = 0;
+    for (int c = 0; c < n; c++) {
+        const size_t end = (size_t)offsets[c] + (size_t)ch[c].num_samples_per_code;
+        if (end > total) total = end;
+    }
+    rc = ensure(h, &h->trk_data, &h->trk_data_cap, total);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(h->trk_data, data, total * sizeof(float2), cudaMemcpyHostToDevice, h->s_trk));
+    CK(cudaMemcpyAsync(h->offs_dev, offsets, sizeof(unsigned long long) * n, cudaMemcpyHostToDevice, h->s_trk));
+    gb::TrkArgs a;
+    a.samples = h->trk_data; a.mask = ~0ull; a.head = total; a.capacity = 0;
+    a.offsets = h->offs_dev;
+    a.ch = h->ch_dev; a.ca_table = h->ca_table_dev;
+    a.n_channels = n; a.n_epochs = 1; a.filters = 0;
+    int n_max = 0;
+    for (int c = 0; c < n; c++)
+        if ((int)ch[c].num_samples_per_code > n_max) n_max = (int)ch[c].num_samples_per_code;
+    a.n_max = n_max;
+    a.corr = h->corr_dev; a.prompt_hist = nullptr; a.ran = h->ran_dev; a.lost = h->lost_dev;
+    CK(cudaEventRecord(h->ev_t0, h->s_trk));
+    CK(gb::trk_launch(a, mode, h->s_trk));
+    CK(cudaEventRecord(h->ev_t1, h->s_trk));
+    CK(cudaMemcpyAsync(ch, h->ch_dev, sizeof(gb_trk_channel) * n, cudaMemcpyDeviceToHost, h->s_trk));
+    CK(cudaMemcpyAsync(out, h->corr_dev, sizeof(gb_trk_corr) * n, cudaMemcpyDeviceToHost, h->s_trk));
+    CK(cudaStreamSynchronize(h->s_trk));
+    CK(cudaEventElapsedTime(&h->last_trk_ms, h->ev_t0, h->ev_t1));
+    return GB_OK;
+}
+
+extern "C" float gb_trk_last_kernel_ms(gb_handle* h) { return h ? h->last_trk_ms : 0.f; }

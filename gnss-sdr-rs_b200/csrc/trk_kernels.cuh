@@ -1,0 +1,27 @@
+// trk_kernels.cuh -- launch interface of the batched E/P/L correlator + loop kernels (trk_kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/gnss_b200.h"
+
+namespace gb {
+
+struct TrkArgs {
+    const float2* samples;          // device ring (or linear buffer when offsets != nullptr)
+    unsigned long long mask;        // ring mask (all ones for a linear buffer)
+    unsigned long long head;        // absolute index one past the newest sample
+    unsigned long long capacity;    // ring capacity (0 = unbounded linear buffer)
+    const unsigned long long* offsets;  // correlate-only: per-channel start of its samples
+    gb_trk_channel* ch;             // n_channels channel states (device)
+    const int8_t* ca_table;         // 32 x 1023 chips (device)
+    int n_channels, n_epochs, filters, n_max;
+    gb_trk_corr* corr;              // last epoch's six sums per channel
+    float* prompt_hist;             // n_epochs x n_channels x 2 or nullptr
+    uint8_t* ran;                   // per channel: epochs consumed in this launch (saturating at 255)
+    uint8_t* lost;                  // per channel: SatelliteLost emitted
+};
+
+cudaError_t trk_launch(const TrkArgs& a, int mode, cudaStream_t st);
+
+}  // namespace gb

@@ -1,0 +1,33 @@
+"""MulticastRingBuffer (utilities/multicast_ring_buffer.rs:36-130) backed by the device sample ring."""
+import numpy as np
+
+from . import _ffi
+
+
+class MulticastRingBuffer:
+    def __init__(self, handle, buf_size):
+        if buf_size <= 0 or (buf_size & (buf_size - 1)):
+            raise AssertionError("Buffer size must be a power of two")  # multicast_ring_buffer.rs:47-50
+        self.hd = handle
+        self.buf_size = buf_size
+        handle.call("gb_ring_create", int(buf_size))
+
+    def write_samples(self, samples):
+        if isinstance(samples, np.ndarray) and samples.dtype == np.int8:
+            x = np.ascontiguousarray(samples)
+            self.hd.call("gb_ring_write_i8", _ffi.ptr(x), x.size)
+        else:
+            x = np.ascontiguousarray(samples, np.complex64)
+            self.hd.call("gb_ring_write", _ffi.ptr(x), x.size)
+            self.hd.call("gb_synchronize")  # the source array may be a temporary
+
+    def get_head(self):
+        return int(self.hd.L.gb_ring_head(self.hd.h))
+
+    def copy_to_slice(self, start, n):
+        dest = np.zeros(n, np.complex64)
+        self.hd.call("gb_ring_copy_to_slice", int(start), _ffi.ptr(dest), int(n))
+        return dest
+
+    def reset(self):
+        self.hd.call("gb_ring_reset")

@@ -1,0 +1,102 @@
+"""Deterministic synthetic IQ source.
+
+The reference's sdr_mock (src/sdr_mock/device_mock.rs) is a control-plane mock that produces no
+samples, and its bundled recording is missing, so the build needs its own seeded generator:
+  * `if_recording`: int8 real IF samples shaped like src/test_data/GPS_recordings/config.txt:2-17
+    (fs 16.3676 MHz, IF 4.1304 MHz, the ten listed PRNs with their carriers / code phases);
+  * `baseband`: complex baseband GPS L1 C/A at any sample rate (BASELINE configs 2 and 3);
+  * `reference_test_signal`: the noise-free waveform of do_tracking.rs:434-462, quirk included.
+All phases are evaluated in f64 and rounded once.
+"""
+import numpy as np
+
+# config.txt:8-17: PRN, carrier (Hz), code phase (1-based samples), strongest first
+CONFIG_TXT = [(2, 4.128460e6, 15042), (3, 4.127190e6, 1618), (19, 4.129280e6, 6184), (14, 4.133130e6, 14540),
+              (18, 4.127310e6, 344), (11, 4.133280e6, 2955), (32, 4.134060e6, 6857), (6, 4.127220e6, 7828),
+              (28, 4.132022e6, 15203), (9, 4.132420e6, 9437)]
+CONFIG_FS = 16367600.0
+CONFIG_IF = 4130400.0
+
+_G2_TAPS = [(2, 6), (3, 7), (4, 8), (5, 9), (1, 9), (2, 10), (1, 8), (2, 9), (3, 10), (2, 3), (3, 4), (5, 6), (6, 7),
+            (7, 8), (8, 9), (9, 10), (1, 4), (2, 5), (3, 6), (4, 7), (5, 8), (6, 9), (1, 3), (4, 6), (5, 7), (6, 8),
+            (7, 9), (8, 10), (1, 6), (2, 7), (3, 8), (4, 9)]
+
+
+def ca_code(prn):
+    """1023 chips, +1 for bit 1 (the convention of constants/gps_ca_constants.rs)."""
+    g1 = [1] * 10
+    g2 = [1] * 10
+    a, b = _G2_TAPS[prn - 1]
+    out = np.empty(1023, np.int8)
+    for c in range(1023):
+        out[c] = 1 if (g1[9] ^ g2[a - 1] ^ g2[b - 1]) else -1
+        f1 = g1[2] ^ g1[9]
+        f2 = g2[1] ^ g2[2] ^ g2[5] ^ g2[7] ^ g2[8] ^ g2[9]
+        g1 = [f1] + g1[:9]
+        g2 = [f2] + g2[:9]
+    return out
+
+
+def _signal(prn, n_samples, fs, carrier_hz, code_phase_samples, amp, code_doppler=0.0, nav_seed=None, phase0=0.0,
+            real=False):
+    t = np.arange(n_samples, dtype=np.float64)
+    code = ca_code(prn).astype(np.float64)
+    rate = 1.023e6 * (1.0 + code_doppler)
+    # the code period starts at sample `code_phase_samples`
+    chip = ((t - code_phase_samples) * rate / fs) % 1023.0
+    sig = code[np.floor(chip).astype(np.int64) % 1023]
+    if nav_seed is not None:
+        rng = np.random.default_rng(nav_seed)
+        periods = np.floor((t - code_phase_samples) * rate / fs / 1023.0).astype(np.int64)
+        bits = rng.integers(0, 2, size=int(periods.max() // 20 + 3)) * 2 - 1
+        sig = sig * bits[(periods // 20) + 1]
+    ph = 2.0 * np.pi * ((carrier_hz * t / fs) % 1.0) + phase0
+    if real:
+        return amp * sig * np.cos(ph)
+    return amp * sig * np.exp(1j * ph)
+
+
+def if_recording(n_ms=10, seed=0x6E55, noise_sigma=8.0, amp0=4.0, amp_step=0.9, prns=None):
+    """int8 real IF stand-in for gioveAandB_short.bin."""
+    n = int(round(CONFIG_FS / 1000.0)) * n_ms
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal(n) * noise_sigma
+    truth = []
+    for k, (prn, carr, phase1) in enumerate(CONFIG_TXT):
+        if prns is not None and prn not in prns:
+            continue
+        amp = amp0 * (amp_step ** k)
+        x += _signal(prn, n, CONFIG_FS, carr, phase1 - 1, amp, phase0=rng.uniform(0, 2 * np.pi), real=True)
+        truth.append({"prn": prn, "carrier": carr, "code_phase": phase1 - 1, "amp": amp})
+    return np.clip(np.round(x), -128, 127).astype(np.int8), truth
+
+
+def i8_to_c32(x):
+    """do_acquisition.rs:420-424: Complex32::new(x as i8 as f32, 0.0)."""
+    return x.astype(np.float32).astype(np.complex64)
+
+
+def baseband(fs, n_ms, sats, seed=0x6E56, noise_sigma=1.0, nav=False):
+    """Complex baseband.  sats: list of dicts {prn, doppler, code_phase (samples), cn0_dbhz}."""
+    n = int(round(fs / 1000.0)) * n_ms
+    rng = np.random.default_rng(seed)
+    x = (rng.standard_normal(n) + 1j * rng.standard_normal(n)) * (noise_sigma / np.sqrt(2.0))
+    for k, s in enumerate(sats):
+        # C/N0 = A^2 / (sigma^2 / fs)  =>  A = sigma * sqrt(10^(cn0/10) / fs)
+        amp = noise_sigma * np.sqrt(10.0 ** (s["cn0_dbhz"] / 10.0) / fs)
+        x += _signal(s["prn"], n, fs, s["doppler"], s["code_phase"], amp, code_doppler=s["doppler"] / 1575.42e6,
+                     nav_seed=(seed * 131 + k) if nav else None, phase0=rng.uniform(0, 2 * np.pi))
+    return x.astype(np.complex64)
+
+
+def reference_test_signal(code_samples, doppler, carrier_phase0, code_phase0, fs):
+    """generate_synthetic_signal (do_tracking.rs:434-462) in f32, including its quirk of indexing the
+    already-resampled code with a chip index."""
+    n = int(np.float32(fs) / np.float32(1000.0))
+    i = np.arange(n, dtype=np.float32)
+    step = np.float32(1.023e6) / np.float32(fs)
+    cph = np.float32(carrier_phase0) + (np.float32(2.0) * np.float32(np.pi) * np.float32(doppler) / np.float32(fs) * i)
+    cur = np.float32(code_phase0) + step * i
+    idx = np.floor(cur).astype(np.int64) % 1023
+    cv = np.asarray(code_samples)[idx].astype(np.float32)
+    return (cv * np.cos(cph).astype(np.float32) + 1j * (cv * np.sin(cph).astype(np.float32))).astype(np.complex64)

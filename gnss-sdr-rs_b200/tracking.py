@@ -1,0 +1,83 @@
+"""Host-side mirror of src/tracking/do_tracking.rs over libgnss_b200: TrackingChannel state (pub
+fields, :88-115), start/reset (:148-154, :311-326), and the batched replacements of
+early_late_correlation (:231-272), do_work (:183-210) and TrackingManager::process_channels (:350-372)."""
+import ctypes as C
+
+import numpy as np
+
+from . import _ffi
+from ._ffi import GB_TRK_FAST, GB_TRK_ORDERED, GB_TRK_IDLE, GB_TRK_TRACKING, TrkChannel  # noqa: F401
+
+NUM_OF_CHANNELS = 15  # do_tracking.rs:18
+
+
+def channel_array(n, fs):
+    """n x TrackingChannel::new(id, fs)."""
+    arr = (TrkChannel * n)()
+    L = _ffi.lib()
+    for i in range(n):
+        _ffi.check(L.gb_trk_channel_init(C.byref(arr[i]), i & 0xFF, float(fs)), "gb_trk_channel_init")
+    return arr
+
+
+def start(ch, prn, carrier_freq, code_phase_chips, sample_global_index, fs, code_row=None):
+    """TrackingChannel::start(AcquisitionResult).  code_row=None keeps the reference's row (= prn, Q6)."""
+    r = _ffi.AcqResult()
+    r.prn, r.found = int(prn), 1
+    r.carrier_freq, r.code_phase_chips, r.fs = float(carrier_freq), float(code_phase_chips), float(fs)
+    r.sample_global_index = int(sample_global_index)
+    _ffi.check(_ffi.lib().gb_trk_channel_start(C.byref(ch), C.byref(r)), "gb_trk_channel_start")
+    if code_row is not None:
+        ch.code_row = int(code_row)
+
+
+def loop_filter(noise_bw, damping, gain):
+    t1, t2 = C.c_float(), C.c_float()
+    _ffi.check(_ffi.lib().gb_loop_filter_new(float(noise_bw), float(damping), float(gain), C.byref(t1), C.byref(t2)),
+               "gb_loop_filter_new")
+    return t1.value, t2.value
+
+
+class TrackingEngine:
+    """All tracking channels of one GPU."""
+
+    def __init__(self, handle):
+        self.hd = handle
+
+    def correlate(self, channels, data_list, mode=GB_TRK_FAST):
+        """early_late_correlation for each channel on its own samples (data_list[c])."""
+        n = len(channels)
+        offs = np.zeros(n, np.uint64)
+        total = 0
+        for c in range(n):
+            offs[c] = total
+            total += len(data_list[c])
+        data = np.concatenate([np.ascontiguousarray(d, np.complex64) for d in data_list])
+        out = np.zeros(n, _ffi.CORR_DTYPE)
+        self.hd.call("gb_trk_correlate", channels, n, _ffi.ptr(data), _ffi.ptr(offs), int(mode), _ffi.ptr(out))
+        return out
+
+    def epoch(self, channels, mode=GB_TRK_FAST):
+        """One do_work per active channel whose samples are in the ring."""
+        n = len(channels)
+        out = np.zeros(n, _ffi.CORR_DTYPE)
+        ran = np.zeros(n, np.uint8)
+        lost = np.zeros(n, np.uint8)
+        self.hd.call("gb_trk_epoch", channels, n, int(mode), _ffi.ptr(out), _ffi.ptr(ran), _ffi.ptr(lost))
+        return out, ran, lost
+
+    def upload(self, channels):
+        self.n = len(channels)
+        self.hd.call("gb_trk_upload", channels, self.n)
+
+    def run(self, n_epochs, mode=GB_TRK_FAST, want_hist=False):
+        hist = np.zeros((n_epochs, self.n, 2), np.float32) if want_hist else None
+        self.hd.call("gb_trk_run", int(n_epochs), int(mode), _ffi.ptr(hist))
+        return hist
+
+    def download(self, channels):
+        self.hd.call("gb_trk_download", channels, len(channels))
+        return channels
+
+    def last_kernel_ms(self):
+        return float(self.hd.L.gb_trk_last_kernel_ms(self.hd.h))

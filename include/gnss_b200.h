@@ -1,0 +1,208 @@
+/*
+ * gnss_b200.h -- C-ABI of libgnss_b200: the B200 (sm_100a) implementation of the gnss-sdr-rs
+ * acquisition / correlator hot path.
+ *
+ * Pure C, bindgen-friendly (fixed-width ints, POD structs, opaque handle); it is meant to be added
+ * to the reference crate's wrapper.h next to src/include/rtl-sdr.h and linked through build.rs
+ * exactly like libconvenience (reference build.rs:11-27).  Every entry point names the reference
+ * item it replaces.  Conventions follow the reference's C side (src/include/convenience.h:52,62):
+ * int return, 0 = success, negative = error (gb_strerror()); "satellite not found" is NOT an
+ * error (found[] = 0), mirroring Option::None at do_acquisition.rs:225.
+ *
+ * Ownership: the caller owns every host buffer passed in or out; the library owns all device
+ * memory behind gb_handle and frees it in gb_destroy().  No callbacks, no global state.
+ * Threading: one handle may be used from an acquisition thread and a tracking thread at the same
+ * time (separate CUDA streams, like main.rs:205-227); calls of the same family on one handle must
+ * be serialised by the caller (the reference's &mut self).
+ * There is NO CPU fallback: every compute entry point returns GB_ENODEVICE without a CUDA device.
+ */
+#ifndef GNSS_B200_H
+#define GNSS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GB_VERSION 100
+
+/* ---- error codes ---- */
+#define GB_OK 0
+#define GB_EINVAL (-1)       /* bad argument */
+#define GB_ENODEVICE (-2)    /* no CUDA device / driver */
+#define GB_ECUDA (-3)        /* a CUDA call failed; gb_last_cuda_error() has the text */
+#define GB_EUNSUPPORTED (-4) /* fft_size has no sm_100a plan */
+#define GB_ESTATE (-5)       /* call order (e.g. search before configure) */
+#define GB_ENOMEM (-6)
+#define GB_ERANGE (-7)       /* samples requested that the ring no longer / not yet holds */
+
+typedef struct gb_handle gb_handle;
+
+typedef struct { float re, im; } gb_c32; /* num_complex::Complex32 */
+
+typedef struct {
+    int32_t device;        /* CUDA ordinal */
+    uint64_t ring_capacity; /* device sample ring, complex samples, power of two (0 = none yet) */
+    uint32_t flags;        /* reserved, 0 */
+} gb_config;
+
+const char *gb_strerror(int code);
+const char *gb_last_cuda_error(gb_handle *h);
+int gb_version(void);
+int gb_device_count(void);
+
+int gb_create(const gb_config *cfg, gb_handle **out);
+int gb_destroy(gb_handle *h);
+int gb_synchronize(gb_handle *h);
+
+/* ------------------------------------------------------------------ C/A code (host, no device)
+ * replaces utilities/ca_code.rs:12-27 and the table constants/gps_ca_constants.rs (G1/G2 LFSR). */
+int gb_ca_code_chips(int prn, int8_t *out1023);
+int gb_num_samples_per_code(float code_rate, float fs);
+int gb_generate_ca_code_samples(int prn, float code_rate, float fs, int8_t *out, int cap);
+
+/* ------------------------------------------------------------------ sample ring (device + pinned staging)
+ * replaces MulticastRingBuffer::{new, write_samples, get_head, copy_to_slice}
+ * (utilities/multicast_ring_buffer.rs:46-129): monotonically increasing absolute sample index,
+ * power-of-two capacity, single writer.  gb_ring_write stages through pinned host memory and
+ * issues cudaMemcpyAsync on the copy stream; the acquisition/tracking streams wait on its event. */
+int gb_ring_create(gb_handle *h, uint64_t capacity_pow2);
+int gb_ring_write(gb_handle *h, const gb_c32 *samples, uint64_t n);
+/* signed 8-bit real samples (the reference recordings, do_acquisition.rs:420-424): im = 0 */
+int gb_ring_write_i8(gb_handle *h, const int8_t *samples, uint64_t n);
+uint64_t gb_ring_head(gb_handle *h);
+int gb_ring_copy_to_slice(gb_handle *h, uint64_t start, gb_c32 *dest, uint64_t n);
+int gb_ring_reset(gb_handle *h);
+
+/* ------------------------------------------------------------------ acquisition
+ * replaces AcquisitionWorker::{new, search_satellite, is_good_satellite}
+ * (do_acquisition.rs:118-239) for ALL PRNs at once (the rayon loop at :302-313),
+ * DopplerShiftTable::new / apply_doppler_shift (doppler_shift.rs:11-58). */
+typedef struct {
+    float peak;      /* max of the accumulated power over code phase (local_max, :195-202) */
+    uint32_t argmax; /* first index attaining it (local_best_phase) */
+    float sum8;      /* sum over the first 8*floor(N/8) bins (is_good_satellite's SIMD sum, :229-234) */
+    float peak2;     /* largest power outside +-samples_per_chip of argmax (legacy two-peak metric,
+                        acquisition_bk.rs:342-399); 0 if disabled */
+} gb_acq_cell;
+
+typedef struct {
+    uint8_t prn;
+    uint8_t found; /* 1 = Some(result), 0 = None */
+    int16_t doppler_bin; /* index into the Doppler table list, -1 if none */
+    uint64_t code_phase_samples;
+    float code_phase_chips;
+    float carrier_freq; /* = f_if + f_d (doppler_shift.rs:20) */
+    float fs;
+    float mag_relative;
+    uint64_t sample_global_index;
+    float metric;       /* peak / ((sum8 - peak)/(N-1)) of the deciding bin */
+    float peak_ratio;   /* sqrt(peak/peak2) of the deciding bin (0 if disabled) */
+} gb_acq_result; /* AcquisitionResult, do_acquisition.rs:93-102, plus diagnostics */
+
+/* Plan the search: AcquisitionWorker::new for prn = 1..n_prn (do_acquisition.rs:131-156).
+ * codes == NULL: GPS C/A resampled per ca_code.rs:12-27 (n_prn <= 32).
+ * codes != NULL: n_prn x fft_size +-1 samples (other constellations / the reference's test codes).
+ * Supported fft_size: see gb_acq_supported_sizes(). */
+int gb_acq_configure(gb_handle *h, int fft_size, float fs, int n_prn, const int8_t *codes);
+int gb_acq_supported_sizes(int *sizes, int cap);
+
+/* DopplerShiftTable::new for each f_d in dopplers[] (doppler_shift.rs:11-21), evaluated on the
+ * device in f32 in the reference's operation order.  carr_out[d] = f_if + f_d (may be NULL). */
+int gb_acq_make_doppler_tables(gb_handle *h, float f_if, const float *dopplers, int n_doppler, float *carr_out);
+/* Caller-built tables (the pub `table` field): n_doppler x fft_size complex + stored doppler_freq_hz */
+int gb_acq_set_doppler_tables(gb_handle *h, const gb_c32 *tables, const float *carr, int n_doppler);
+int gb_acq_get_doppler_tables(gb_handle *h, gb_c32 *tables_out, float *carr_out);
+
+/* EXTENSION (BASELINE config 2, not in the reference): n_coh consecutive 1 ms blocks are summed
+ * coherently (block c rotated by exp(-j 2 pi carr c N / fs)) before |.|^2.  1 = reference. */
+int gb_acq_set_coherent(gb_handle *h, int n_coh);
+/* samples_per_chip > 0 enables peak2; threshold is is_good_satellite's 7.0 */
+int gb_acq_set_detector(gb_handle *h, float threshold, int samples_per_chip);
+
+/* The fused search over the PRN x Doppler grid.  iq = num_integrations*fft_size host samples
+ * (search_satellite's samples_chunk); prn_mask bit (prn-1) selects PRNs as at do_acquisition.rs:307
+ * (for n_prn > 32 pass enable[] instead, NULL = all).  cells_out: n_prn x n_doppler, rows of PRNs
+ * that were not searched are zero.  May be NULL. */
+int gb_acq_search_cells(gb_handle *h, const gb_c32 *iq, int num_integrations, uint32_t prn_mask,
+                        const uint8_t *enable, gb_acq_cell *cells_out);
+/* same, reading the chunk from the device ring at absolute index local_tail (do_acquisition.rs:297-301) */
+int gb_acq_search_cells_ring(gb_handle *h, uint64_t local_tail, int num_integrations, uint32_t prn_mask,
+                             const uint8_t *enable, gb_acq_cell *cells_out);
+/* search_satellite's decision (early-exit order, Q1) on one PRN's cells; host-side O(D) scan */
+int gb_acq_decide(const gb_acq_cell *cells, const float *carr, int n_doppler, int prn, int fft_size, float fs,
+                  uint64_t local_tail, float threshold, gb_acq_result *out);
+/* cells + decide for every selected PRN: results[n_prn] */
+int gb_acq_search(gb_handle *h, const gb_c32 *iq, int num_integrations, uint64_t local_tail, uint32_t prn_mask,
+                  const uint8_t *enable, gb_acq_result *results);
+int gb_acq_search_ring(gb_handle *h, uint64_t local_tail, int num_integrations, uint32_t prn_mask,
+                       const uint8_t *enable, gb_acq_result *results);
+/* accumulated power row of one (prn, doppler bin) -- diagnostics / tests */
+int gb_acq_bin_power(gb_handle *h, const gb_c32 *iq, int num_integrations, int prn, int doppler_bin, float *power_out);
+/* device time of the last search's kernels in milliseconds (CUDA events on the acquisition stream) */
+float gb_acq_last_kernel_ms(gb_handle *h);
+
+/* ------------------------------------------------------------------ FFT facade
+ * replaces FFT<f32>::{execute, power_spectrum}, RealFFT<f32>::{execute, power_spectrum} (fft.rs:5-56)
+ * for the planned sizes; natural-order, unnormalised. batch transforms of length n. */
+int gb_fft_c2c(gb_handle *h, int n, int inverse, const gb_c32 *in, gb_c32 *out, int batch);
+int gb_fft_power_spectrum(gb_handle *h, int n, const gb_c32 *in, float *out, int batch);
+int gb_rfft(gb_handle *h, int n, const float *in, gb_c32 *out /* batch x (n/2+1) */, int batch);
+
+/* ------------------------------------------------------------------ tracking
+ * replaces TrackingChannel::{early_late_correlation, get_ca_chip, run_loop_filters, do_work, update}
+ * and the rayon loop of TrackingManager::process_channels (do_tracking.rs:160-302, 364-371). */
+#define GB_TRK_IDLE 0
+#define GB_TRK_TRACKING 1
+
+typedef struct {
+    uint8_t id, prn;
+    uint8_t state;      /* GB_TRK_IDLE / GB_TRK_TRACKING */
+    uint8_t code_row;   /* C/A table row used by get_ca_chip; the reference uses prn (Q6), not prn-1 */
+    uint32_t lost_counter;
+    float fs;
+    uint32_t epochs_done;
+    uint64_t next_sample_index;
+    uint64_t num_samples_per_code;
+    float carrier_freq, carrier_phase, carrier_error, carrier_nco;
+    float code_phase, code_error, code_nco, code_rate;
+    float i_prompt, q_prompt;
+    float pll_tau1, pll_tau2, dll_tau1, dll_tau2; /* LoopFilter, do_tracking.rs:52-71 */
+} gb_trk_channel; /* TrackingChannel's pub state, do_tracking.rs:88-115 */
+
+typedef struct { float i_p, q_p, i_e, q_e, i_l, q_l; } gb_trk_corr;
+
+/* modes */
+#define GB_TRK_FAST 0     /* tree reductions, device sincosf                                   */
+#define GB_TRK_ORDERED 1  /* six sums accumulated in sample order, f64-evaluated sin/cos; for
+                             closed-loop parity runs (SURVEY note E3)                            */
+
+/* host helpers (no device): TrackingChannel::new / start / reset, LoopFilter::new */
+int gb_trk_channel_init(gb_trk_channel *c, uint8_t id, float fs);
+int gb_trk_channel_start(gb_trk_channel *c, const gb_acq_result *r);
+int gb_trk_channel_reset(gb_trk_channel *c);
+int gb_loop_filter_new(float noise_bw, float damping, float gain, float *tau1, float *tau2);
+
+/* early_late_correlation for n_channels channels, each on its own n = num_samples_per_code host
+ * samples laid out back to back in data (offsets[c] = start of channel c's samples).  Updates
+ * carrier_phase, code_phase, i_prompt, q_prompt like the reference does; no loop filters. */
+int gb_trk_correlate(gb_handle *h, gb_trk_channel *ch, int n_channels, const gb_c32 *data, const uint64_t *offsets,
+                     int mode, gb_trk_corr *out);
+/* do_work for every active channel whose samples are in the ring (TrackingChannel::update,
+ * do_tracking.rs:160-210): one launch, correlators + lock test + loop filters + bookkeeping.
+ * ran[c] = 1 if the channel consumed an epoch; lost[c] = 1 if it emitted SatelliteLost. */
+int gb_trk_epoch(gb_handle *h, gb_trk_channel *ch, int n_channels, int mode, gb_trk_corr *out, uint8_t *ran,
+                 uint8_t *lost);
+/* persistent form: state stays on the device; n_epochs epochs per channel (or until the ring head)
+ * in one launch.  prompt_hist (optional): n_epochs x n_channels x {i_p, q_p}. */
+int gb_trk_upload(gb_handle *h, const gb_trk_channel *ch, int n_channels);
+int gb_trk_run(gb_handle *h, int n_epochs, int mode, float *prompt_hist);
+int gb_trk_download(gb_handle *h, gb_trk_channel *ch, int n_channels);
+float gb_trk_last_kernel_ms(gb_handle *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,190 @@
+/*
+ * gnss_oracle.h -- CPU restatement ("oracle") of the gnss-sdr-rs hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing that ships (gnss-sdr-rs_b200/, the C-ABI
+ * library libgnss_b200.so) may include, link or call this.  It is used by
+ * tests/, by __graft_entry__.smoke() as the checker, and by bench.py's
+ * cpu_baseline / --impl reference legs.
+ *
+ * PARITY STATUS: the reference (Rust nightly + rustfft 6.1.0) cannot be built
+ * in this environment and its bundled IQ recording is missing, so FFT output
+ * VALUES are "parity unpinned".  What IS pinned against the reference's own
+ * vectors: the C/A table (PRN-1 1023-chip KAT from src/bk/gps_ca_prn.rs:72-123
+ * and the sha256 of src/constants/gps_ca_constants.rs), the AcquisitionManager
+ * masks (do_acquisition.rs:371-394), the ring-buffer wrap test
+ * (multicast_ring_buffer.rs:147-209) and the loop-filter constants.  The FFT is
+ * pinned against scipy.fft (pocketfft) and an f64 DFT in tests/.
+ *
+ * Every function cites the reference file:line it follows.  All arithmetic is
+ * IEEE f32 in the reference's operation order; build with -ffp-contract=off.
+ */
+#ifndef GNSS_ORACLE_H
+#define GNSS_ORACLE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct { float re, im; } go_c32;
+typedef struct { double re, im; } go_c64;
+
+/* ---- constants (src/constants/gps_property_constants.rs:3-5) ---- */
+#define GO_CA_CODE_RATE 1.023e6f
+#define GO_CA_CODE_LEN 1023
+
+/* ---- C/A code ---- */
+/* G1/G2 LFSR with phase-selector taps; chips are +1 for bit 1, -1 for bit 0
+ * (the convention of src/constants/gps_ca_constants.rs).  prn in 1..=32. */
+int go_ca_code_chips(int prn, int8_t out[GO_CA_CODE_LEN]);
+/* the whole 32x1023 table, row r = PRN r+1 (GPS_CA_CODE_32_PRN) */
+const int8_t *go_ca_table(void);
+
+/* utilities/ca_code.rs:12-27.  Returns the number of samples
+ * round(fs / (code_rate / 1023)); writes min(n, cap) of them. */
+int go_generate_ca_code_samples(int prn, float code_rate, float fs, int8_t *out, int cap);
+int go_num_samples_per_code(float code_rate, float fs);
+
+/* ---- FFT (stands in for rustfft 6.1.0: unnormalised, any N) ---- */
+typedef struct go_fft_plan go_fft_plan;
+go_fft_plan *go_fft_plan_new(int n, int inverse);
+void go_fft_plan_free(go_fft_plan *p);
+void go_fft_process(const go_fft_plan *p, go_c32 *data);          /* in place, f32 */
+typedef struct go_fft64_plan go_fft64_plan;
+go_fft64_plan *go_fft64_plan_new(int n, int inverse);
+void go_fft64_plan_free(go_fft64_plan *p);
+void go_fft64_process(const go_fft64_plan *p, go_c64 *data);      /* in place, f64 */
+/* src/fft.rs:5-56 facade */
+void go_fft_forward(int n, go_c32 *data);
+void go_fft_power_spectrum(int n, go_c32 *data, float *out);
+void go_rfft_forward(int n, const float *in, go_c32 *out /* n/2+1 */);
+
+/* ---- acquisition ---- */
+/* acquisition/doppler_shift.rs:11-21: table[i] = (cos(i*step), -sin(i*step)),
+ * step = 2*pi*(f_if+f_d)/fs ; returns the stored doppler_freq_hz = f_if+f_d. */
+float go_doppler_table(float f_if, float f_d, float fs, int n, go_c32 *table);
+/* acquisition/doppler_shift.rs:25-58 (tail of len%4 samples left untouched) */
+void go_apply_doppler_shift(const go_c32 *samples, const go_c32 *table, go_c32 *out, int len);
+
+typedef struct {
+    uint8_t prn;
+    uint64_t code_phase_samples;
+    float code_phase_chips;
+    float carrier_freq;
+    float fs;
+    float mag_relative;
+    uint64_t sample_global_index;
+} go_acq_result; /* do_acquisition.rs:93-102 */
+
+typedef struct {
+    float peak;      /* max accumulated power in the bin            */
+    uint32_t argmax; /* first index of the strict maximum (init 0.0) */
+    float sum8;      /* 8-lane sum over chunks_exact(8) (Q2)         */
+} go_acq_cell;
+
+typedef struct go_acq_worker go_acq_worker;
+/* do_acquisition.rs:131-156 */
+go_acq_worker *go_acq_worker_new(int prn, int fft_size, float fs);
+/* generic-code variant (extension: any +-1 code of length fft_size already resampled) */
+go_acq_worker *go_acq_worker_new_code(int prn, int fft_size, float fs, const int8_t *code_samples);
+void go_acq_worker_free(go_acq_worker *w);
+const go_c32 *go_acq_worker_code_fft(const go_acq_worker *w);
+
+/* do_acquisition.rs:158-226, reference semantics incl. early exit (Q1).
+ * tables: D contiguous tables of fft_size entries; carr[D] = stored doppler_freq_hz.
+ * Returns 1 and fills *out when a satellite is found, else 0. */
+int go_acq_search(go_acq_worker *w, const go_c32 *samples, const go_c32 *tables, const float *carr,
+                  int n_doppler, uint64_t local_tail, int num_integrations, go_acq_result *out);
+
+/* Full grid (no early exit): cells[d] for every Doppler bin.  n_coh = 1 is the
+ * reference's per-bin arithmetic (do_acquisition.rs:171-202, 229-234).
+ * n_coh > 1 is the EXTENSION named by BASELINE config 2: the complex
+ * correlations of n_coh consecutive blocks are summed, block c rotated by
+ * rot[d*n_coh + c] (see go_coh_rotators), before |.|^2; num_integrations must be a
+ * multiple of n_coh.  presum != 0 sums the wiped blocks BEFORE the FFT
+ * (mathematically identical by linearity, n_coh x fewer FFTs). */
+void go_acq_cells(go_acq_worker *w, const go_c32 *samples, const go_c32 *tables, int n_doppler,
+                  int num_integrations, int n_coh, const go_c32 *rot, int presum, go_acq_cell *cells);
+/* accumulated power of one bin (for tests), same options */
+void go_acq_bin_power(go_acq_worker *w, const go_c32 *samples, const go_c32 *table, int num_integrations,
+                      int n_coh, const go_c32 *rot, int presum, float *power);
+/* rot[c] = exp(-j*2*pi*carr*(c*n)/fs) evaluated in f64, rounded to f32 */
+void go_coh_rotators(float carr, float fs, int n, int n_coh, go_c32 *rot);
+
+/* do_acquisition.rs:229-238 on a cell */
+int go_is_good_cell(float peak, float sum8, int fft_size, float threshold);
+/* Q1 scan over cells in table order == search_satellite's decision */
+int go_acq_decide(const go_acq_cell *cells, const float *carr, int n_doppler, int prn, int fft_size,
+                  float fs, uint64_t local_tail, float threshold, go_acq_result *out, int *bin_out);
+/* legacy two-peak metric, acquisition_bk.rs:342-399 restated on a power row */
+float go_two_peak_ratio(const float *power, int n, int samples_per_chip, uint32_t *first, uint32_t *second);
+
+/* threaded search over PRNs (one worker per PRN, as rayon does at do_acquisition.rs:302-313).
+ * found[p] = 1/0, results[p]; early_exit=0 runs the full grid + decide. */
+void go_acq_search_all(go_acq_worker **workers, int n_workers, const go_c32 *samples, const go_c32 *tables,
+                       const float *carr, int n_doppler, uint64_t local_tail, int num_integrations,
+                       int early_exit, int n_threads, int *found, go_acq_result *results);
+void go_acq_cells_all(go_acq_worker **workers, int n_workers, const go_c32 *samples, const go_c32 *tables,
+                      int n_doppler, int num_integrations, int n_coh, const go_c32 *rot, int presum,
+                      int n_threads, go_acq_cell *cells /* n_workers x n_doppler */);
+
+/* do_acquisition.rs:39-74 */
+typedef struct { int mode; /* 0 cold, 1 warm, 2 steady */ } go_acq_manager;
+void go_acq_manager_update_mode(go_acq_manager *m, size_t tracked);
+void go_acq_manager_pacing(const go_acq_manager *m, uint32_t active_mask /* bit prn-1 */, uint64_t *interval_ms,
+                           uint32_t *mask);
+
+/* ---- tracking ---- */
+typedef struct { float tau1, tau2; } go_loop_filter; /* do_tracking.rs:52-71 */
+go_loop_filter go_loop_filter_new(float noise_bw, float damping, float gain);
+float go_loop_filter_update(const go_loop_filter *f, float d_err, float err, float dt);
+
+enum { GO_IDLE = 0, GO_TRACKING = 1 };
+typedef struct {
+    uint8_t id, prn;
+    int32_t state;       /* GO_IDLE / GO_TRACKING(prn) */
+    int32_t code_row;    /* row of the C/A table used by get_ca_chip: reference = prn (Q6) */
+    uint32_t lost_counter;
+    float fs;
+    uint64_t next_sample_index;
+    uint64_t num_samples_per_code;
+    float carrier_freq, carrier_phase, carrier_error, carrier_nco;
+    float code_phase, code_error, code_nco, code_rate;
+    float i_prompt, q_prompt;
+    go_loop_filter pll_filter, dll_filter;
+} go_trk_channel; /* do_tracking.rs:88-115 */
+
+void go_trk_channel_init(go_trk_channel *c, uint8_t id, float fs);    /* :118-146 */
+void go_trk_channel_start(go_trk_channel *c, const go_acq_result *r); /* :148-154 */
+void go_trk_channel_reset(go_trk_channel *c);                         /* :311-326 */
+float go_trk_get_ca_chip(const go_trk_channel *c, float phase);       /* :274-277 */
+/* :231-272; data is rotated in place exactly as the reference does */
+void go_trk_early_late(go_trk_channel *c, go_c32 *data, float out6[6]);
+void go_trk_run_loop_filters(go_trk_channel *c, const float in6[6]);  /* :279-302 */
+/* :183-210; returns 0 = no message, 1 = SatelliteLost(msg_prn) */
+int go_trk_do_work(go_trk_channel *c, go_c32 *data, float out6[6], uint8_t *msg_prn);
+
+/* ---- ring buffer (utilities/multicast_ring_buffer.rs:36-130) ---- */
+typedef struct {
+    go_c32 *buffer;
+    size_t buf_size, mask, head;
+} go_ring;
+int go_ring_init(go_ring *r, size_t buf_size); /* power of two or returns -1 */
+void go_ring_free(go_ring *r);
+void go_ring_write(go_ring *r, const go_c32 *samples, size_t n);
+size_t go_ring_head(const go_ring *r);
+void go_ring_copy_to_slice(const go_ring *r, size_t start, go_c32 *dest, size_t n);
+/* intended TrackingChannel::update (do_tracking.rs:160-180, Q5): 1 if an epoch ran */
+int go_trk_update(go_trk_channel *c, const go_ring *ring, go_c32 *scratch, float out6[6], int *msg, uint8_t *msg_prn);
+
+/* many channels x many epochs over one shared stream (threaded over channels,
+ * do_tracking.rs:364-371).  hist (optional) = n_epochs x n_channels x 2 prompt I/Q. */
+void go_trk_run_all(go_trk_channel *ch, int n_channels, const go_c32 *stream, size_t stream_len, int n_epochs,
+                    int n_threads, float *hist);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

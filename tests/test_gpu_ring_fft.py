@@ -1,0 +1,72 @@
+"""Device sample ring (multicast_ring_buffer.rs:147-209 restated) and the FFT facade (fft.rs:5-56)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_multicast_ring_buffer_reference_case(gpu):
+    """The reference's own test: 1024-entry ring, writes of 500 / 530 / 20 samples, wrap at 1024."""
+    from gnss_sdr_rs_b200 import ring
+    rb = ring.MulticastRingBuffer(gpu, 1024)
+    rb.write_samples(np.arange(0, 500, dtype=np.float32).astype(np.complex64))
+    assert rb.get_head() == 500
+    rb.write_samples(np.arange(500, 1030, dtype=np.float32).astype(np.complex64))
+    assert rb.get_head() == 1030
+    assert (rb.copy_to_slice(1020, 4).real == np.arange(1020, 1024)).all()
+    assert (rb.copy_to_slice(1024, 6).real == np.arange(1024, 1030)).all()      # physical 0..6
+    assert (rb.copy_to_slice(1020, 10).real == np.arange(1020, 1030)).all()     # across the wrap
+    rb.write_samples(np.arange(1030, 1050, dtype=np.float32).astype(np.complex64))
+    assert rb.get_head() == 1050
+    assert (rb.copy_to_slice(1030, 10).real == np.arange(1030, 1040)).all()
+    with pytest.raises(AssertionError):
+        ring.MulticastRingBuffer(gpu, 1000)  # not a power of two
+
+
+def test_ring_i8_and_acquisition_from_ring(gpu, oracle):
+    """run()'s data path: head -> local_tail = head - 10*N -> search (do_acquisition.rs:297-313), int8 ingest."""
+    from gnss_sdr_rs_b200 import acquisition, ring, sdr_mock
+    n, fs, f_if, K = 16368, 16367600.0, 4130400.0, 4
+    raw, _ = sdr_mock.if_recording(K + 1, prns={2, 3, 19})
+    rb = ring.MulticastRingBuffer(gpu, 1 << 16)   # smaller than the recording: forces a wrap
+    rb.write_samples(raw[:30000])
+    rb.write_samples(raw[30000:])
+    head = rb.get_head()
+    assert head == len(raw)
+    local_tail = head - K * n
+    x = sdr_mock.i8_to_c32(raw)[local_tail:]
+    assert (rb.copy_to_slice(local_tail, 100) == x[:100]).all()
+    eng = acquisition.AcquisitionEngine(gpu, n, fs)
+    d = np.array(acquisition.reference_doppler_grid(), np.float32)
+    carr, tabs = oracle.doppler_tables(f_if, d, fs, n)
+    eng.set_doppler_tables(tabs, carr)
+    a = eng.search_cells_ring(local_tail, K, prn_mask=0b110)
+    b = eng.search_cells(x, K, prn_mask=0b110)
+    assert a.tobytes() == b.tobytes()
+    r = eng.search_ring(local_tail, K, prn_mask=0b110)
+    assert r[1] is not None and r[1]["sample_global_index"] == local_tail + r[1]["code_phase_samples"]
+    import gnss_sdr_rs_b200._ffi as ffi
+    with pytest.raises(ffi.GnssB200Error) as e:
+        eng.search_cells_ring(head, K)          # not written yet
+    assert e.value.code == ffi.GB_ERANGE
+    with pytest.raises(ffi.GnssB200Error) as e:
+        eng.search_cells_ring(0, K)             # overwritten
+    assert e.value.code == ffi.GB_ERANGE
+
+
+@pytest.mark.parametrize("n", [1024, 2048, 4092, 4096, 8184, 16368, 20000])
+def test_fft_facade(gpu, n):
+    from gnss_sdr_rs_b200 import acquisition
+    rng = np.random.default_rng(n)
+    x = (rng.standard_normal((3, n)) + 1j * rng.standard_normal((3, n))).astype(np.complex64)
+    f = acquisition.FFT(gpu, n)
+    ref = np.fft.fft(x.astype(np.complex128), axis=1)
+    got = f.execute(x)
+    assert np.abs(got - ref).max() / np.abs(ref).max() < 5e-7
+    inv = f.execute(got, inverse=True) / n
+    assert np.abs(inv - x).max() < 5e-6
+    np.testing.assert_allclose(f.power_spectrum(x), np.abs(ref) ** 2, rtol=2e-5, atol=1e-3)
+    r = rng.standard_normal(n).astype(np.float32)
+    rf = acquisition.RealFFT(gpu, n)
+    ref_r = np.fft.rfft(r.astype(np.float64))
+    assert np.abs(rf.execute(r) - ref_r).max() / np.abs(ref_r).max() < 5e-7
