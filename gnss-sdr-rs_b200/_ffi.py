@@ -80,6 +80,7 @@ SIGNATURES = {
     "gb_acq_search_ring": (_i32, [_vp, _u64, _i32, _u32, _vp, _vp]),
     "gb_acq_bin_power": (_i32, [_vp, _vp, _i32, _i32, _i32, _vp]),
     "gb_acq_last_kernel_ms": (_f32, [_vp]),
+    "gb_bench_fp32_tflops": (_i32, [_vp, _vp]),
     "gb_fft_c2c": (_i32, [_vp, _i32, _i32, _vp, _vp, _i32]),
     "gb_fft_power_spectrum": (_i32, [_vp, _i32, _vp, _vp, _i32]),
     "gb_rfft": (_i32, [_vp, _i32, _vp, _vp, _i32]),

@@ -160,6 +160,20 @@ int fft_resources(gb_handle* h, int plan, int n, FftRes** out)
     return GB_OK;
 }
 
+// FP32 FMA throughput probe: 8 independent FMA chains per thread, 4096 iterations
+__global__ void fp32_peak_kernel(float* out, float a, float b)
+{
+    float x0 = threadIdx.x, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f, x4 = x0 + 4.f, x5 = x0 + 5.f, x6 = x0 + 6.f,
+          x7 = x0 + 7.f;
+#pragma unroll 1
+    for (int i = 0; i < 4096; i++) {
+        x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+        x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+    }
+    const float s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+    if (s == 12345.678f) out[0] = s;
+}
+
 __global__ void i8_to_ring_kernel(const int8_t* __restrict__ src, float2* __restrict__ ring, unsigned long long start,
                                   unsigned long long mask, unsigned long long n)
 {
@@ -673,6 +687,34 @@ extern "C" int gb_acq_bin_power(gb_handle* h, const gb_c32* iq, int K, int prn, 
 }
 
 extern "C" float gb_acq_last_kernel_ms(gb_handle* h) { return h ? h->last_acq_ms : 0.f; }
+
+// Measured FP32 (non-tensor) FMA throughput of this GPU, for the roofline denominator
+extern "C" int gb_bench_fp32_tflops(gb_handle* h, float* tflops_out)
+{
+    if (!h || !tflops_out) return GB_EINVAL;
+    CK(cudaSetDevice(h->device));
+    int sms = 0;
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
+    float* d = nullptr;
+    CK(cudaMalloc((void**)&d, 4));
+    const int blocks = sms * 8, threads = 256;
+    float best = 0.f;
+    for (int rep = 0; rep < 6; rep++) {
+        cudaEventRecord(h->ev_a0, h->s_acq);
+        fp32_peak_kernel<<<blocks, threads, 0, h->s_acq>>>(d, 1.0000001f, 1e-9f);
+        cudaEventRecord(h->ev_a1, h->s_acq);
+        cudaError_t e = cudaStreamSynchronize(h->s_acq);
+        if (e != cudaSuccess) { cudaFree(d); return fail(h, e, "fp32_peak_kernel"); }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, h->ev_a0, h->ev_a1);
+        const double flops = 2.0 * 8.0 * 4096.0 * (double)blocks * threads;
+        const float tf = (float)(flops / (ms * 1e-3) / 1e12);
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaFree(d);
+    *tflops_out = best;
+    return GB_OK;
+}
 
 // ------------------------------------------------------------------ FFT facade (fft.rs:5-56)
 static int fft_common(gb_handle* h, int n, int inverse, const void* in, void* out, int batch, int real_in, int power_out,

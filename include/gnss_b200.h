@@ -144,6 +144,10 @@ int gb_acq_bin_power(gb_handle *h, const gb_c32 *iq, int num_integrations, int p
 /* device time of the last search's kernels in milliseconds (CUDA events on the acquisition stream) */
 float gb_acq_last_kernel_ms(gb_handle *h);
 
+/* measured FP32 FMA throughput of the device (TFLOP/s): the roofline denominator for these kernels,
+ * which are FP32-pipe / shared-memory bound, not HBM- or tensor-bound */
+int gb_bench_fp32_tflops(gb_handle *h, float *tflops_out);
+
 /* ------------------------------------------------------------------ FFT facade
  * replaces FFT<f32>::{execute, power_spectrum}, RealFFT<f32>::{execute, power_spectrum} (fft.rs:5-56)
  * for the planned sizes; natural-order, unnormalised. batch transforms of length n. */
