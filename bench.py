@@ -1,0 +1,370 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the acquisition / correlator hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload acq|trk]
+    (N > 1: python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...)
+
+Workload "acq" (default) = BASELINE.json configs[1]: synthetic GPS L1 C/A at 4.092 Msps, 32 PRNs,
+10 ms coherent x 20 non-coherent (200 ms of signal), 50 Hz Doppler step over +-5 kHz (D = 201).
+A step = one full search of one recording; metric = PRN x Doppler x code-phase cells per second
+(P*D*N = 26 319 744 cells per step).  With N GPUs every rank searches its own recording (sharding by
+recording) and the per-PRN results are all-gathered over NCCL each step: weak scaling.
+
+`value`  : device time (CUDA events on the library's acquisition stream) with the IQ already in the
+           HBM sample ring; L2 is flushed between timed steps.
+`e2e`    : wall clock through the C-ABI call gb_acq_search() with PINNED HOST IQ: H2D copy, kernel,
+           D2H of the cells and the host decision scan inside the timed region.
+`roofline`: the fused kernel is FP32-pipe / shared-memory bound, so the denominator is the
+           FP32 FMA rate measured live by gb_bench_fp32_tflops(); the HBM view is reported beside it.
+`cpu_baseline` / --impl reference: the CPU oracle (oracle/, the C restatement of the reference's
+           algorithm -- the Rust reference cannot be built here) on all host cores, on a bounded sample.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FS, N_FFT, N_PRN = 4.092e6, 4092, 32
+N_COH, N_NONCOH = 10, 20
+K_MS = N_COH * N_NONCOH
+DOPPLERS = np.arange(-5000.0, 5000.0 + 1e-3, 50.0, dtype=np.float32)
+SATS = [(3, 1230.0, 100, 45.0), (7, -2210.0, 2000, 40.0), (11, 3370.0, 3100, 42.0), (14, -440.0, 777, 50.0),
+        (19, 4120.0, 1500, 38.0), (22, -3900.0, 4000, 36.0), (28, 60.0, 2500, 47.0), (31, 2780.0, 300, 35.0)]
+
+
+def make_recording(seed):
+    from gnss_sdr_rs_b200 import sdr_mock
+    sats = [{"prn": p, "doppler": d, "code_phase": c, "cn0_dbhz": cn} for p, d, c, cn in SATS]
+    return sdr_mock.baseband(FS, K_MS, sats, seed=seed, nav=True)
+
+
+def acq_flops():
+    """Algorithmic FLOPs of one step (conventions of SURVEY 8d: FFT = 5 N log2 N, cmul 6, |.|^2 3, add 1,
+    wipe-off cmul 6, rotate-accumulate 8)."""
+    P, D, N, K, G = N_PRN, len(DOPPLERS), N_FFT, K_MS, N_NONCOH
+    lg = math.log2(N)
+    shared_per_d = K * N * 14 + G * 5 * N * lg          # wipe-off + coherent pre-sum + forward FFT
+    per_pd = G * N * (6 + 5 * lg + 3 + 1)               # x conj(code), IFFT, |.|^2, accumulate
+    minimal = D * shared_per_d + P * D * per_pd         # forward path shared by the 32 PRNs
+    as_run = P * D * (shared_per_d + per_pd)            # what the fused kernel executes (per-CTA forward path)
+    return minimal, as_run
+
+
+def acq_bytes():
+    P, D, N, K = N_PRN, len(DOPPLERS), N_FFT, K_MS
+    return 8 * N * K + 8 * N * P + 8 * N * D + 16 * P * D
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag, self.proc = index, [], False, None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+                if self.stop_flag:
+                    break
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_baseline_acq(x, n_threads, max_prns=None):
+    """The oracle (kind "port") on a bounded sample: one worker per PRN on all host threads, all 201 bins,
+    200 ms, same coherent/non-coherent plan (pre-summed, the cheaper of the oracle's two forms)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pyoracle as orc
+    n_prn = min(N_PRN, max_prns or max(8, n_threads))
+    carr, tabs = orc.doppler_tables(0.0, DOPPLERS, FS, N_FFT)
+    rot = orc.coh_rotators(carr, FS, N_FFT, N_COH)
+    workers = [orc.AcqWorker(p, N_FFT, FS) for p in range(1, n_prn + 1)]
+    t0 = time.perf_counter()
+    cells = orc.acq_cells_all(workers, x, tabs, K_MS, n_coh=N_COH, rot=rot, presum=1, n_threads=n_threads)
+    dt = time.perf_counter() - t0
+    n_cells = n_prn * len(DOPPLERS) * N_FFT
+    return n_cells / dt, dt, n_prn, cells
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    x = make_recording(0x6E56)
+    vals = []
+    for s in range(args.warmup + args.steps):
+        v, dt, n_prn, _ = cpu_baseline_acq(x, cores, max_prns=max(8, cores) if cores <= 32 else 32)
+        if s >= args.warmup:
+            vals.append((v, dt))
+    value = float(np.mean([v for v, _ in vals]))
+    sample = "%d of 32 PRNs x %d Doppler bins x %d ms (pre-summed %d ms coherent x %d)" % (
+        n_prn, len(DOPPLERS), K_MS, N_COH, N_NONCOH)
+    line = {"impl": "reference", "metric": "acq_cells_per_sec", "value": value, "unit": "cells/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean([d for _, d in vals])) * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(),
+            "cpu_baseline": {"value": value, "unit": "cells/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "CPU oracle (C restatement of the reference algorithm; the Rust/rustfft reference cannot be built "
+                    "here). rustfft+AVX is expected to be 2-4x faster than this scalar mixed-radix FFT."}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config():
+    return {"workload": "BASELINE configs[1]: GPS L1 C/A 4.092 Msps, 32 PRNs, 10 ms coherent x 20 non-coherent, "
+                        "50 Hz Doppler step (+-5 kHz, D=201), 200 ms recording per step",
+            "fft_size": N_FFT, "n_prn": N_PRN, "n_doppler": len(DOPPLERS), "n_coherent": N_COH,
+            "n_noncoherent": N_NONCOH, "cells_per_step": N_PRN * len(DOPPLERS) * N_FFT,
+            "l2": "flushed between timed steps (256 MiB write)", "sharding": "one recording per GPU + NCCL all_gather"}
+
+
+def tracking_numbers(hd, ffi, n_channels=1024, n_epochs=1000):
+    """BASELINE configs[2] shape, shortened: 1024 channels (32 PRN-slots x 32 hand-over perturbations) on one shared
+    2.048 Msps stream, persistent kernel, FAST mode.  Returns channel-epochs/s from the kernel's CUDA events."""
+    from gnss_sdr_rs_b200 import ring, sdr_mock, tracking
+    fs, n = 2.048e6, 2048
+    prns = [2, 5, 9, 12, 17, 21, 25, 30]
+    sats = [{"prn": p, "doppler": float(-2000 + 500 * i), "code_phase": 137 * (i + 1), "cn0_dbhz": 48.0}
+            for i, p in enumerate(prns)]
+    base_ms = 100
+    # periodic construction: Dopplers are multiples of 10 Hz and there is no code Doppler, so a 100 ms tile repeats
+    tile = np.zeros(n * base_ms, np.complex64)
+    rng = np.random.default_rng(0x6E57)
+    t = np.arange(n * base_ms, dtype=np.float64)
+    for s in sats:
+        code = sdr_mock.ca_code(s["prn"]).astype(np.float64)
+        chip = ((t - s["code_phase"]) * 1.023e6 / fs) % 1023.0
+        amp = np.sqrt(10.0 ** (s["cn0_dbhz"] / 10.0) / fs)
+        tile += (amp * code[np.floor(chip).astype(np.int64) % 1023]
+                 * np.exp(2j * np.pi * ((s["doppler"] * t / fs) % 1.0))).astype(np.complex64)
+    reps = (n_epochs + 2 + base_ms - 1) // base_ms + 1
+    rb = ring.MulticastRingBuffer(hd, 1 << int(math.ceil(math.log2(n * base_ms * reps))))
+    for r in range(reps):
+        noise = (rng.standard_normal(len(tile)) + 1j * rng.standard_normal(len(tile))).astype(np.complex64) * np.float32(
+            1 / np.sqrt(2))
+        rb.write_samples(tile + noise)
+    ch = tracking.channel_array(n_channels, fs)
+    for c in range(n_channels):
+        s = sats[c % len(sats)]
+        tracking.start(ch[c], s["prn"], s["doppler"] + float(rng.uniform(-50, 50)), float(rng.uniform(0, 0.3)),
+                       s["code_phase"], fs, code_row=s["prn"] - 1)
+    eng = tracking.TrackingEngine(hd)
+    eng.upload(ch)
+    eng.run(20)  # warm-up epochs
+    eng.run(n_epochs)
+    ms = eng.last_kernel_ms()
+    eng.download(ch)
+    locked = sum(1 for c in range(n_channels) if ch[c].state == 1)
+    done = sum(int(ch[c].epochs_done) for c in range(n_channels)) - 20 * n_channels
+    return {"metric": "tracking_channel_epochs_per_sec", "value": done / (ms * 1e-3), "unit": "channel-epochs/s",
+            "channels": n_channels, "epochs": n_epochs, "kernel_ms": ms, "locked_channels": locked,
+            "x_realtime": (n_epochs * 1e-3) / (ms * 1e-3), "mode": "fast (persistent kernel, on-device loop filters)",
+            "fs": fs}
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import gnss_sdr_rs_b200._ffi as ffi
+    from gnss_sdr_rs_b200 import acquisition, ring
+
+    if not torch.cuda.is_available() or ffi.lib().gb_device_count() < 1:
+        raise RuntimeError("bench.py needs a CUDA device: libgnss_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    hd = ffi.Handle(local_rank)
+    x = make_recording(0x6E56 + rank)
+    rb = ring.MulticastRingBuffer(hd, 1 << 20)
+    rb.write_samples(x)
+    x_pin = torch.from_numpy(x.view(np.float32).copy()).pin_memory()
+    x_pin_ptr = x_pin.data_ptr()
+
+    eng = acquisition.AcquisitionEngine(hd, N_FFT, FS, N_PRN)
+    carr = eng.make_doppler_tables(0.0, DOPPLERS)
+    eng.set_coherent(N_COH)
+    eng.set_detector(7.0, 4)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    gather_buf = [torch.zeros(N_PRN, 4, device="cuda") for _ in range(world)] if world > 1 else None
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        flush.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        res = eng.search_ring(0, K_MS)
+        ms = eng.last_kernel_ms()
+        g_ms = 0.0
+        if dist is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            mine = torch.tensor([[r["prn"], r["code_phase_samples"], r["carrier_freq"], r["mag_relative"]] if r
+                                 else [0, 0, 0, 0] for r in res], dtype=torch.float32).cuda()
+            e0.record()
+            dist.all_gather(gather_buf, mine)
+            e1.record()
+            torch.cuda.synchronize()
+            g_ms = e0.elapsed_time(e1)
+        return ms + g_ms, (time.perf_counter() - t0) * 1e3, res
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    t_wall0 = time.perf_counter()
+    dev_ms, res = 0.0, None
+    for _ in range(args.steps):
+        ms, _, res = step_device()
+        dev_ms += ms
+    barrier()
+    wall_ms = (time.perf_counter() - t_wall0) * 1e3
+    kernel_ms_avg = dev_ms / args.steps
+
+    # e2e: pinned host IQ -> gb_acq_search (H2D + kernel + D2H + decision) per step
+    for _ in range(2):
+        eng.search(x_pin_ptr, K_MS)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res_e2e = eng.search(x_pin_ptr, K_MS)
+        if dist is not None:
+            mine = torch.tensor([[r["prn"], r["code_phase_samples"], r["carrier_freq"], r["mag_relative"]] if r
+                                 else [0, 0, 0, 0] for r in res_e2e], dtype=torch.float32).cuda()
+            dist.all_gather(gather_buf, mine)
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    clocks = sampler.finish()
+
+    if dist is not None:
+        t = torch.tensor([dev_ms, e2e_ms, wall_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, e2e_ms, wall_ms = [float(v) for v in t.cpu()]
+    cells = N_PRN * len(DOPPLERS) * N_FFT
+    ms_per_step = dev_ms / args.steps
+    value = world * cells / (ms_per_step * 1e-3)
+    e2e_value = world * cells / (e2e_ms * 1e-3)
+
+    if rank == 0:
+        peak_tf = ctypes_float(hd, "gb_bench_fp32_tflops")
+        minimal, as_run = acq_flops()
+        achieved = minimal / (kernel_ms_avg * 1e-3) / 1e12
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("acq_fused_4092_bytes_per_launch")
+        except Exception:
+            pass
+        found = sorted(r["prn"] for r in res if r)
+        line = {"metric": "acq_cells_per_sec", "value": value, "unit": "cells/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(),
+                "wall_ms_per_step_incl_l2_flush": wall_ms / args.steps,
+                "x_realtime": world * (K_MS * 1e-3) / (ms_per_step * 1e-3),
+                "e2e": {"value": e2e_value, "unit": "cells/s", "ms_per_step": e2e_ms,
+                        "h2d_bytes_per_step": int(x.nbytes), "d2h_bytes_per_step": int(N_PRN * len(DOPPLERS) * 16),
+                        "api": "gb_acq_search (pinned host IQ -> results)"},
+                "gpu_launches": args.steps * 1,
+                "roofline": {"bound": "fp32", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+                             "frac": achieved / peak_tf if peak_tf else None, "traffic": traffic,
+                             "peak_source": "measured live: gb_bench_fp32_tflops FMA probe (MEASURED_PEAKS.json has no "
+                                            "FP32 figure; theoretical 148*128*2*1.965 GHz = 74.5)",
+                             "flops_per_launch_minimal": minimal, "flops_per_launch_as_run": as_run,
+                             "achieved_as_run": as_run / (kernel_ms_avg * 1e-3) / 1e12,
+                             "kernel": "acq_fused_kernel<Plan<4092,...>>", "kernel_ms": kernel_ms_avg,
+                             "hbm_view": {"bound": "hbm", "algorithmic_bytes": acq_bytes(),
+                                          "achieved": acq_bytes() / (kernel_ms_avg * 1e-3) / 1e9, "peak": hbm_peak,
+                                          "unit": "GB/s", "frac": acq_bytes() / (kernel_ms_avg * 1e-3) / 1e9 / hbm_peak,
+                                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback"}},
+                "clocks": clocks, "detected_prns": found}
+        if world == 1:
+            cores = os.cpu_count() or 1
+            v, dt, n_prn, ocells = cpu_baseline_acq(x, cores)
+            line["cpu_baseline"] = {"value": v, "unit": "cells/s", "cores": cores, "kind": "port",
+                                    "sample": "%d of 32 PRNs x 201 bins x 200 ms, %.1f s" % (n_prn, dt)}
+            # the bench doubles as a full-size parity check on the sampled PRNs
+            gcells = eng.search_cells_ring(0, K_MS)
+            strong = ocells["peak"] > 4.0 * np.median(ocells["peak"], axis=1, keepdims=True)
+            line["parity_vs_oracle"] = {
+                "prns": n_prn, "max_rel_peak_err": float(np.abs(gcells["peak"][:n_prn] / ocells["peak"] - 1).max()),
+                "argmax_equal_frac": float((gcells["argmax"][:n_prn] == ocells["argmax"]).mean()),
+                "argmax_equal_strong_cells": bool((gcells["argmax"][:n_prn][strong] == ocells["argmax"][strong]).all())}
+            try:
+                line["tracking"] = tracking_numbers(hd, ffi)
+            except Exception as e:  # report, never hide
+                line["tracking"] = {"error": repr(e)}
+        print(json.dumps(line), flush=True)
+    hd.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def ctypes_float(hd, name):
+    import ctypes as C
+    v = C.c_float(0)
+    hd.call(name, C.byref(v))
+    return float(v.value)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()
