@@ -219,6 +219,7 @@ def run_ours(args, rank, world, local_rank):
     carr = eng.make_doppler_tables(0.0, DOPPLERS)
     eng.set_coherent(N_COH)
     eng.set_detector(7.0, 4)
+    eng.set_mode(ffi.GB_ACQ_FUSED if args.acq_mode == "fused" else ffi.GB_ACQ_SHARED)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     gather_buf = [torch.zeros(N_PRN, 4, device="cuda") for _ in range(world)] if world > 1 else None
 
@@ -307,14 +308,14 @@ def run_ours(args, rank, world, local_rank):
                 "e2e": {"value": e2e_value, "unit": "cells/s", "ms_per_step": e2e_ms,
                         "h2d_bytes_per_step": int(x.nbytes), "d2h_bytes_per_step": int(N_PRN * len(DOPPLERS) * 16),
                         "api": "gb_acq_search (pinned host IQ -> results)"},
-                "gpu_launches": args.steps * 1,
+                "gpu_launches": args.steps * (1 if args.acq_mode == "fused" else 2),
                 "roofline": {"bound": "fp32", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                              "frac": achieved / peak_tf if peak_tf else None, "traffic": traffic,
                              "peak_source": "measured live: gb_bench_fp32_tflops FMA probe (MEASURED_PEAKS.json has no "
                                             "FP32 figure; theoretical 148*128*2*1.965 GHz = 74.5)",
                              "flops_per_launch_minimal": minimal, "flops_per_launch_as_run": as_run,
                              "achieved_as_run": as_run / (kernel_ms_avg * 1e-3) / 1e12,
-                             "kernel": "acq_fused_kernel<Plan<4092,...>>", "kernel_ms": kernel_ms_avg,
+                             "kernel": ("acq_fused_kernel" if args.acq_mode == "fused" else "acq_forward_kernel + acq_inverse_kernel") + "<Plan<4092,...>>", "kernel_ms": kernel_ms_avg,
                              "hbm_view": {"bound": "hbm", "algorithmic_bytes": acq_bytes(),
                                           "achieved": acq_bytes() / (kernel_ms_avg * 1e-3) / 1e9, "peak": hbm_peak,
                                           "unit": "GB/s", "frac": acq_bytes() / (kernel_ms_avg * 1e-3) / 1e9 / hbm_peak,
@@ -356,6 +357,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--acq-mode", default="shared", choices=["shared", "fused"])
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -10,6 +10,7 @@ LIB_PATH = os.path.join(_HERE, "libgnss_b200.so")
 GB_OK, GB_EINVAL, GB_ENODEVICE, GB_ECUDA, GB_EUNSUPPORTED, GB_ESTATE, GB_ENOMEM, GB_ERANGE = 0, -1, -2, -3, -4, -5, -6, -7
 GB_TRK_IDLE, GB_TRK_TRACKING = 0, 1
 GB_TRK_FAST, GB_TRK_ORDERED = 0, 1
+GB_ACQ_FUSED, GB_ACQ_SHARED = 0, 1
 
 
 class GnssB200Error(RuntimeError):
@@ -72,6 +73,7 @@ SIGNATURES = {
     "gb_acq_set_doppler_tables": (_i32, [_vp, _vp, _vp, _i32]),
     "gb_acq_get_doppler_tables": (_i32, [_vp, _vp, _vp]),
     "gb_acq_set_coherent": (_i32, [_vp, _i32]),
+    "gb_acq_set_mode": (_i32, [_vp, _i32]),
     "gb_acq_set_detector": (_i32, [_vp, _f32, _i32]),
     "gb_acq_search_cells": (_i32, [_vp, _vp, _i32, _u32, _vp, _vp]),
     "gb_acq_search_cells_ring": (_i32, [_vp, _u64, _i32, _u32, _vp, _vp]),

@@ -88,6 +88,10 @@ class AcquisitionEngine:
         self.hd.call("gb_acq_set_coherent", int(n_coh))
         self.n_coh = int(n_coh)
 
+    def set_mode(self, mode):
+        """_ffi.GB_ACQ_FUSED (single kernel) or _ffi.GB_ACQ_SHARED (forward path shared by all PRNs, default)."""
+        self.hd.call("gb_acq_set_mode", int(mode))
+
     def set_detector(self, threshold=7.0, samples_per_chip=0):
         self.hd.call("gb_acq_set_detector", float(threshold), int(samples_per_chip))
 

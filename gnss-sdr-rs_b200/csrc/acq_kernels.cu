@@ -66,117 +66,59 @@ __device__ __forceinline__ float warp_sum(float v)
     return v;
 }
 
-template <class P, bool WANT_ROW> __global__ void __launch_bounds__(P::T, P::MINB) acq_fused_kernel(const AcqArgs a)
+// Stage 0 of the forward DIF (L = N) with the carrier wipe-off (and, for n_coh > 1, the coherent
+// pre-sum of n_coh rotated blocks) fused into the global-memory load.
+template <class P>
+__device__ __forceinline__ void stage0_wipe_forward(const AcqArgs& a, const float2* __restrict__ w,
+                                                    const float2* __restrict__ rot, int n_coh, int g,
+                                                    float2* __restrict__ line, const float2* __restrict__ tw)
 {
-    extern __shared__ float2 line[];
-    constexpr int LASTS = P::NSTAGE - 1;
     using G0 = StageGeo<P, 0>;
-    using GM = StageGeo<P, LASTS>;
     constexpr int N = P::N;
-
-    const int d = WANT_ROW ? a.d0 : (int)(blockIdx.x % (unsigned)a.D);
-    const int row = a.rows[WANT_ROW ? 0 : (int)(blockIdx.x / (unsigned)a.D)];
-    const float2* __restrict__ w = a.tables + (size_t)d * N;
-    const float2* __restrict__ code = a.code_fft + (size_t)row * N;
-    const float2* __restrict__ tw = a.tw;
-    const float2* __restrict__ rot = a.rot ? a.rot + (size_t)d * a.n_coh : nullptr;
-    const int n_coh = a.n_coh;
-    const int n_groups = a.K / n_coh;
-
-    float acc[G0::ITERS][G0::R];
 #pragma unroll
-    for (int it = 0; it < G0::ITERS; it++)
+    for (int it = 0; it < G0::ITERS; it++) {
+        const int i = threadIdx.x + it * P::T;
+        if (G0::NB % P::T == 0 || i < G0::NB) {
+            float2 v[G0::R];
+            if (n_coh == 1) {
+                const unsigned long long blk0 = (unsigned long long)g * N;
 #pragma unroll
-        for (int j = 0; j < G0::R; j++) acc[it][j] = 0.f;
-
-    for (int g = 0; g < n_groups; g++) {
-        // ---- stage 0 (DIF, L = N): wipe-off fused into the load, straight from global memory
+                for (int j = 0; j < G0::R; j++)
+                    v[j] = wipe(ld_iq(a, blk0 + i + j * G0::SUB), __ldg(&w[i + j * G0::SUB]));
+            } else {
+                float2 wv[G0::R];
 #pragma unroll
-        for (int it = 0; it < G0::ITERS; it++) {
-            const int i = threadIdx.x + it * P::T;
-            if (G0::NB % P::T == 0 || i < G0::NB) {
-                float2 v[G0::R];
-                if (n_coh == 1) {
-                    const unsigned long long blk0 = (unsigned long long)g * N;
-#pragma unroll
-                    for (int j = 0; j < G0::R; j++)
-                        v[j] = wipe(ld_iq(a, blk0 + i + j * G0::SUB), __ldg(&w[i + j * G0::SUB]));
-                } else {
-                    float2 wv[G0::R];
+                for (int j = 0; j < G0::R; j++) {
+                    wv[j] = __ldg(&w[i + j * G0::SUB]);
+                    v[j] = make_float2(0.f, 0.f);
+                }
+                for (int c = 0; c < n_coh; c++) {
+                    const float2 r = __ldg(&rot[c]);
+                    const unsigned long long blk0 = (unsigned long long)(g * n_coh + c) * N;
 #pragma unroll
                     for (int j = 0; j < G0::R; j++) {
-                        wv[j] = __ldg(&w[i + j * G0::SUB]);
-                        v[j] = make_float2(0.f, 0.f);
-                    }
-                    for (int c = 0; c < n_coh; c++) {
-                        const float2 r = __ldg(&rot[c]);
-                        const unsigned long long blk0 = (unsigned long long)(g * n_coh + c) * N;
-#pragma unroll
-                        for (int j = 0; j < G0::R; j++) {
-                            const float2 t = wipe(ld_iq(a, blk0 + i + j * G0::SUB), wv[j]);
-                            v[j].x = fmaf(t.x, r.x, fmaf(-t.y, r.y, v[j].x));
-                            v[j].y = fmaf(t.x, r.y, fmaf(t.y, r.x, v[j].y));
-                        }
+                        const float2 t = wipe(ld_iq(a, blk0 + i + j * G0::SUB), wv[j]);
+                        v[j].x = fmaf(t.x, r.x, fmaf(-t.y, r.y, v[j].x));
+                        v[j].y = fmaf(t.x, r.y, fmaf(t.y, r.x, v[j].y));
                     }
                 }
-                Dft<G0::R, false>::run(v);
-                line[P::phys(i)] = v[0];
-#pragma unroll
-                for (int q = 1; q < G0::R; q++) line[P::phys(i + q * G0::SUB)] = cmul(v[q], __ldg(&tw[i * q]));
             }
+            Dft<G0::R, false>::run(v);
+            line[P::phys(i)] = v[0];
+#pragma unroll
+            for (int q = 1; q < G0::R; q++) line[P::phys(i + q * G0::SUB)] = cmul(v[q], __ldg(&tw[i * q]));
         }
-        __syncthreads();
-        DifRange<P, 1, LASTS, false>::run(line, tw);
-
-        // ---- last forward stage + x conj(code) + first inverse stage, in registers
-#pragma unroll
-        for (int it = 0; it < GM::ITERS; it++) {
-            const int b = threadIdx.x + it * P::T;
-            if (GM::NB % P::T == 0 || b < GM::NB) {
-                const int base = b * GM::R;
-                float2 v[GM::R];
-#pragma unroll
-                for (int j = 0; j < GM::R; j++) v[j] = line[P::phys(base + j)];
-                Dft<GM::R, false>::run(v);
-#pragma unroll
-                for (int q = 0; q < GM::R; q++) v[q] = cmul_conj(v[q], __ldg(&code[q * GM::NB + b]));
-                Dft<GM::R, true>::run(v);
-#pragma unroll
-                for (int j = 0; j < GM::R; j++) line[P::phys(base + j)] = v[j];
-            }
-        }
-        __syncthreads();
-        DitRange<P, LASTS - 1, 0, true>::run(line, tw);
-
-        // ---- stage 0 inverse (DIT, L = N) fused with |.|^2 accumulate; natural order
-#pragma unroll
-        for (int it = 0; it < G0::ITERS; it++) {
-            const int i = threadIdx.x + it * P::T;
-            if (G0::NB % P::T == 0 || i < G0::NB) {
-                float2 v[G0::R];
-                v[0] = line[P::phys(i)];
-#pragma unroll
-                for (int q = 1; q < G0::R; q++) v[q] = cmul_conj(line[P::phys(i + q * G0::SUB)], __ldg(&tw[i * q]));
-                Dft<G0::R, true>::run(v);
-#pragma unroll
-                for (int j = 0; j < G0::R; j++) acc[it][j] += v[j].x * v[j].x + v[j].y * v[j].y;
-            }
-        }
-        __syncthreads();  // the next group's stage 0 overwrites the line
     }
+}
 
-    if (WANT_ROW) {
-#pragma unroll
-        for (int it = 0; it < G0::ITERS; it++) {
-            const int i = threadIdx.x + it * P::T;
-            if (G0::NB % P::T == 0 || i < G0::NB)
-#pragma unroll
-                for (int j = 0; j < G0::R; j++) a.row_out[i + j * G0::SUB] = acc[it][j];
-        }
-        return;
-    }
-
-    // ---- reduce the row: peak / first argmax / 8-lane sum (Q2: only the first 8*floor(N/8) bins)
+// Row reduction shared by the fused and the shared-forward kernels: peak / first argmax / 8-lane sum
+// (Q2: only the first 8*floor(N/8) bins) / second peak outside +-spc of the first.
+template <class P>
+__device__ __forceinline__ void reduce_row_to_cell(float (&acc)[StageGeo<P, 0>::ITERS][StageGeo<P, 0>::R], float2* line,
+                                                   int spc, gb_acq_cell* out)
+{
+    using G0 = StageGeo<P, 0>;
+    constexpr int N = P::N;
     constexpr int NSUM = (N / 8) * 8;
     constexpr int NW = P::T / 32;
     PeakIdx pk;
@@ -228,10 +170,8 @@ template <class P, bool WANT_ROW> __global__ void __launch_bounds__(P::T, P::MIN
     const float peak = red_v[32];
     const unsigned arg = red_i[32];
     const float total = red_s[32];
-
-    // ---- second peak outside +-spc samples (circular) of the first (legacy two-peak metric)
     float p2 = 0.f;
-    if (a.spc > 0) {
+    if (spc > 0) {
 #pragma unroll
         for (int it = 0; it < G0::ITERS; it++) {
             const int i = threadIdx.x + it * P::T;
@@ -241,7 +181,7 @@ template <class P, bool WANT_ROW> __global__ void __launch_bounds__(P::T, P::MIN
                     const int n = i + j * G0::SUB;
                     int dist = abs(n - (int)arg);
                     dist = min(dist, N - dist);
-                    if (dist > a.spc) p2 = fmaxf(p2, acc[it][j]);
+                    if (dist > spc) p2 = fmaxf(p2, acc[it][j]);
                 }
             }
         }
@@ -263,8 +203,173 @@ template <class P, bool WANT_ROW> __global__ void __launch_bounds__(P::T, P::MIN
         c.argmax = arg;
         c.sum8 = total;
         c.peak2 = p2;
-        a.cells[(size_t)row * a.D + d] = c;
+        *out = c;
     }
+}
+
+// Final inverse stage (DIT, L = N) fused with |.|^2 accumulate; outputs are in natural order.
+template <class P>
+__device__ __forceinline__ void final_stage_accumulate(const float2* __restrict__ line, const float2* __restrict__ tw,
+                                                       float (&acc)[StageGeo<P, 0>::ITERS][StageGeo<P, 0>::R])
+{
+    using G0 = StageGeo<P, 0>;
+#pragma unroll
+    for (int it = 0; it < G0::ITERS; it++) {
+        const int i = threadIdx.x + it * P::T;
+        if (G0::NB % P::T == 0 || i < G0::NB) {
+            float2 v[G0::R];
+            v[0] = line[P::phys(i)];
+#pragma unroll
+            for (int q = 1; q < G0::R; q++) v[q] = cmul_conj(line[P::phys(i + q * G0::SUB)], __ldg(&tw[i * q]));
+            Dft<G0::R, true>::run(v);
+#pragma unroll
+            for (int j = 0; j < G0::R; j++) acc[it][j] += v[j].x * v[j].x + v[j].y * v[j].y;
+        }
+    }
+}
+
+template <class P, bool WANT_ROW> __global__ void __launch_bounds__(P::T, P::MINB) acq_fused_kernel(const AcqArgs a)
+{
+    extern __shared__ float2 line[];
+    constexpr int LASTS = P::NSTAGE - 1;
+    using G0 = StageGeo<P, 0>;
+    using GM = StageGeo<P, LASTS>;
+    constexpr int N = P::N;
+
+    const int d = WANT_ROW ? a.d0 : (int)(blockIdx.x % (unsigned)a.D);
+    const int row = a.rows[WANT_ROW ? 0 : (int)(blockIdx.x / (unsigned)a.D)];
+    const float2* __restrict__ w = a.tables + (size_t)d * N;
+    const float2* __restrict__ code = a.code_fft + (size_t)row * N;
+    const float2* __restrict__ tw = a.tw;
+    const float2* __restrict__ rot = a.rot ? a.rot + (size_t)d * a.n_coh : nullptr;
+    const int n_coh = a.n_coh;
+    const int n_groups = a.K / n_coh;
+
+    float acc[G0::ITERS][G0::R];
+#pragma unroll
+    for (int it = 0; it < G0::ITERS; it++)
+#pragma unroll
+        for (int j = 0; j < G0::R; j++) acc[it][j] = 0.f;
+
+    for (int g = 0; g < n_groups; g++) {
+        stage0_wipe_forward<P>(a, w, rot, n_coh, g, line, tw);
+        __syncthreads();
+        DifRange<P, 1, LASTS, false>::run(line, tw);
+
+        // ---- last forward stage + x conj(code) + first inverse stage, in registers
+#pragma unroll
+        for (int it = 0; it < GM::ITERS; it++) {
+            const int b = threadIdx.x + it * P::T;
+            if (GM::NB % P::T == 0 || b < GM::NB) {
+                const int base = b * GM::R;
+                float2 v[GM::R];
+#pragma unroll
+                for (int j = 0; j < GM::R; j++) v[j] = line[P::phys(base + j)];
+                Dft<GM::R, false>::run(v);
+#pragma unroll
+                for (int q = 0; q < GM::R; q++) v[q] = cmul_conj(v[q], __ldg(&code[q * GM::NB + b]));
+                Dft<GM::R, true>::run(v);
+#pragma unroll
+                for (int j = 0; j < GM::R; j++) line[P::phys(base + j)] = v[j];
+            }
+        }
+        __syncthreads();
+        DitRange<P, LASTS - 1, 0, true>::run(line, tw);
+
+        final_stage_accumulate<P>(line, tw, acc);
+        __syncthreads();  // the next group's stage 0 overwrites the line
+    }
+
+    if (WANT_ROW) {
+#pragma unroll
+        for (int it = 0; it < G0::ITERS; it++) {
+            const int i = threadIdx.x + it * P::T;
+            if (G0::NB % P::T == 0 || i < G0::NB)
+#pragma unroll
+                for (int j = 0; j < G0::R; j++) a.row_out[i + j * G0::SUB] = acc[it][j];
+        }
+        return;
+    }
+
+    reduce_row_to_cell<P>(acc, line, a.spc, &a.cells[(size_t)row * a.D + d]);
+}
+
+// ------------------------------------------------------------------ shared-forward chain
+// The forward path (wipe-off, coherent pre-sum, forward FFT) does not depend on the PRN, yet the
+// reference recomputes it in each of its 32 workers (do_acquisition.rs:176-182).  Kernel A computes
+// it once per (Doppler bin, group) and leaves the scrambled spectrum in L2/HBM (transposed like the
+// code spectra); kernel B then runs, per (PRN, Doppler bin), x conj(code) -> inverse FFT -> |.|^2
+// accumulate -> cell.  Same arithmetic as the fused kernel, bit for bit.
+template <class P> __global__ void __launch_bounds__(P::T, P::MINB) acq_forward_kernel(const AcqArgs a)
+{
+    extern __shared__ float2 line[];
+    constexpr int LASTS = P::NSTAGE - 1;
+    using GM = StageGeo<P, LASTS>;
+    constexpr int N = P::N;
+    const int n_groups = a.K / a.n_coh;
+    const int d = a.d_lo + (int)(blockIdx.x / (unsigned)n_groups);
+    const int g = (int)(blockIdx.x % (unsigned)n_groups);
+    const float2* __restrict__ w = a.tables + (size_t)d * N;
+    const float2* __restrict__ rot = a.rot ? a.rot + (size_t)d * a.n_coh : nullptr;
+    float2* __restrict__ out = a.spec + (size_t)blockIdx.x * N;
+    stage0_wipe_forward<P>(a, w, rot, a.n_coh, g, line, a.tw);
+    __syncthreads();
+    DifRange<P, 1, LASTS, false>::run(line, a.tw);
+#pragma unroll
+    for (int it = 0; it < GM::ITERS; it++) {
+        const int b = threadIdx.x + it * P::T;
+        if (GM::NB % P::T == 0 || b < GM::NB) {
+            float2 v[GM::R];
+#pragma unroll
+            for (int j = 0; j < GM::R; j++) v[j] = line[P::phys(b * GM::R + j)];
+            Dft<GM::R, false>::run(v);
+#pragma unroll
+            for (int q = 0; q < GM::R; q++) out[q * GM::NB + b] = v[q];
+        }
+    }
+}
+
+template <class P> __global__ void __launch_bounds__(P::T, P::MINB) acq_inverse_kernel(const AcqArgs a)
+{
+    extern __shared__ float2 line[];
+    constexpr int LASTS = P::NSTAGE - 1;
+    using G0 = StageGeo<P, 0>;
+    using GM = StageGeo<P, LASTS>;
+    constexpr int N = P::N;
+    const int n_groups = a.K / a.n_coh;
+    // Doppler-major block order: the n_active CTAs that share one bin's spectra run together (L2 reuse)
+    const int dl = (int)(blockIdx.x / (unsigned)a.n_active);
+    const int row = a.rows[blockIdx.x % (unsigned)a.n_active];
+    const float2* __restrict__ code = a.code_fft + (size_t)row * N;
+    const float2* __restrict__ tw = a.tw;
+    const float2* __restrict__ spec = a.spec + (size_t)dl * n_groups * N;
+
+    float acc[G0::ITERS][G0::R];
+#pragma unroll
+    for (int it = 0; it < G0::ITERS; it++)
+#pragma unroll
+        for (int j = 0; j < G0::R; j++) acc[it][j] = 0.f;
+
+    for (int g = 0; g < n_groups; g++) {
+        const float2* __restrict__ sg = spec + (size_t)g * N;
+#pragma unroll
+        for (int it = 0; it < GM::ITERS; it++) {
+            const int b = threadIdx.x + it * P::T;
+            if (GM::NB % P::T == 0 || b < GM::NB) {
+                float2 v[GM::R];
+#pragma unroll
+                for (int q = 0; q < GM::R; q++) v[q] = cmul_conj(__ldg(&sg[q * GM::NB + b]), __ldg(&code[q * GM::NB + b]));
+                Dft<GM::R, true>::run(v);
+#pragma unroll
+                for (int j = 0; j < GM::R; j++) line[P::phys(b * GM::R + j)] = v[j];
+            }
+        }
+        __syncthreads();
+        DitRange<P, LASTS - 1, 0, true>::run(line, tw);
+        final_stage_accumulate<P>(line, tw, acc);
+        __syncthreads();
+    }
+    reduce_row_to_cell<P>(acc, line, a.spc, &a.cells[(size_t)row * a.D + a.d_lo + dl]);
 }
 
 // ------------------------------------------------------------------ code spectra (AcquisitionWorker::new, :133-138)
@@ -440,6 +545,17 @@ template <class P> static cudaError_t launch_search(const AcqArgs& a, cudaStream
     acq_fused_kernel<P, false><<<a.n_active * a.D, P::T, smem, st>>>(a);
     return cudaGetLastError();
 }
+template <class P> static cudaError_t launch_shared(const AcqArgs& a, int n_d, cudaStream_t st)
+{
+    const size_t smem = plan_smem<P>();
+    cudaError_t e = set_smem(acq_forward_kernel<P>, smem);
+    if (e != cudaSuccess) return e;
+    if ((e = set_smem(acq_inverse_kernel<P>, smem)) != cudaSuccess) return e;
+    acq_forward_kernel<P><<<n_d * (a.K / a.n_coh), P::T, smem, st>>>(a);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    acq_inverse_kernel<P><<<n_d * a.n_active, P::T, smem, st>>>(a);
+    return cudaGetLastError();
+}
 template <class P> static cudaError_t launch_row(const AcqArgs& a, cudaStream_t st)
 {
     const size_t smem = plan_smem<P>();
@@ -476,6 +592,16 @@ cudaError_t acq_launch_search(int plan, const AcqArgs& a, cudaStream_t st)
     switch (plan) {
 #define X(i, P) \
     case i: return launch_search<P>(a, st);
+        GB_FOR_EACH_PLAN(X)
+#undef X
+    }
+    return cudaErrorInvalidValue;
+}
+cudaError_t acq_launch_shared(int plan, const AcqArgs& a, int n_d, cudaStream_t st)
+{
+    switch (plan) {
+#define X(i, P) \
+    case i: return launch_shared<P>(a, n_d, st);
         GB_FOR_EACH_PLAN(X)
 #undef X
     }

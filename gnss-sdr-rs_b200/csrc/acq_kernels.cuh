@@ -21,6 +21,8 @@ struct AcqArgs {
     gb_acq_cell* cells;      // n_prn x D
     float* row_out;          // diagnostics: accumulated power row of (rows[0], d0)
     int d0;                  // Doppler bin for row_out
+    float2* spec;            // shared-forward chain: n_d x n_groups x N scrambled spectra (scratch)
+    int d_lo;                // shared-forward chain: first Doppler bin of this slab
 };
 
 struct FftArgs {
@@ -38,6 +40,8 @@ int acq_plan_threads(int plan);
 size_t acq_plan_smem(int plan);
 
 cudaError_t acq_launch_search(int plan, const AcqArgs& a, cudaStream_t st);
+// forward kernel over n_d bins [a.d_lo, a.d_lo+n_d) then inverse kernel over n_active x n_d cells
+cudaError_t acq_launch_shared(int plan, const AcqArgs& a, int n_d, cudaStream_t st);
 cudaError_t acq_launch_row(int plan, const AcqArgs& a, cudaStream_t st);
 cudaError_t acq_launch_code_fft(int plan, const int8_t* codes, int n_prn, float2* code_fft, const float2* tw,
                                 cudaStream_t st);

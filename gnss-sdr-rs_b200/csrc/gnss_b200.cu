@@ -38,7 +38,9 @@ struct gb_handle {
     size_t i8_cap = 0;
 
     // acquisition
-    int plan = -1, N = 0, n_prn = 0, D = 0, n_coh = 1, spc = 0;
+    int plan = -1, N = 0, n_prn = 0, D = 0, n_coh = 1, spc = 0, mode = GB_ACQ_SHARED;
+    float2* spec = nullptr;
+    size_t spec_cap = 0;
     float fs = 0.f, threshold = 7.0f;
     float2 *tw = nullptr, *code_fft = nullptr, *tables = nullptr, *rot = nullptr, *chunk = nullptr;
     int8_t* codes_dev = nullptr;
@@ -245,7 +247,7 @@ extern "C" int gb_destroy(gb_handle* h)
     if (!h) return GB_EINVAL;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
-    void* dev_ptrs[] = {h->ring, h->i8_stage, h->tw, h->code_fft, h->tables, h->rot, h->chunk, h->codes_dev, h->cells_dev,
+    void* dev_ptrs[] = {h->spec, h->ring, h->i8_stage, h->tw, h->code_fft, h->tables, h->rot, h->chunk, h->codes_dev, h->cells_dev,
                         h->rows_dev, h->row_dev, h->ca_table_dev, h->ch_dev, h->corr_dev, h->ran_dev, h->lost_dev,
                         h->hist_dev, h->trk_data, h->offs_dev};
     for (void* p : dev_ptrs)
@@ -489,6 +491,13 @@ extern "C" int gb_acq_set_coherent(gb_handle* h, int n_coh)
     return upload_rotators(h);
 }
 
+extern "C" int gb_acq_set_mode(gb_handle* h, int mode)
+{
+    if (!h || (mode != GB_ACQ_FUSED && mode != GB_ACQ_SHARED)) return GB_EINVAL;
+    h->mode = mode;
+    return GB_OK;
+}
+
 extern "C" int gb_acq_set_detector(gb_handle* h, float threshold, int samples_per_chip)
 {
     if (!h || samples_per_chip < 0) return GB_EINVAL;
@@ -532,10 +541,28 @@ static int search_cells(gb_handle* h, const float2* iq_dev, uint64_t start, uint
         a.rot = h->n_coh > 1 ? h->rot : nullptr;
         a.rows = h->rows_dev;
         a.D = h->D; a.K = K; a.n_coh = h->n_coh; a.n_active = n_active; a.spc = h->spc;
-        a.cells = h->cells_dev; a.row_out = nullptr; a.d0 = 0;
-        CK(cudaEventRecord(h->ev_a0, h->s_acq));
-        CK(gb::acq_launch_search(h->plan, a, h->s_acq));
-        CK(cudaEventRecord(h->ev_a1, h->s_acq));
+        a.cells = h->cells_dev; a.row_out = nullptr; a.d0 = 0; a.spec = nullptr; a.d_lo = 0;
+        if (h->mode == GB_ACQ_SHARED) {
+            // scratch for the forward spectra, processed in Doppler slabs of at most 1 GiB
+            const size_t per_d = (size_t)(K / h->n_coh) * h->N;
+            size_t slab = ((size_t)1 << 27) / per_d;  // complex elements: 2^27 * 8 B = 1 GiB
+            if (slab < 1) slab = 1;
+            if (slab > (size_t)h->D) slab = h->D;
+            int rc = ensure(h, &h->spec, &h->spec_cap, slab * per_d);
+            if (rc) return rc;
+            a.spec = h->spec;
+            CK(cudaEventRecord(h->ev_a0, h->s_acq));
+            for (int d_lo = 0; d_lo < h->D; d_lo += (int)slab) {
+                a.d_lo = d_lo;
+                const int n_d = (h->D - d_lo) < (int)slab ? (h->D - d_lo) : (int)slab;
+                CK(gb::acq_launch_shared(h->plan, a, n_d, h->s_acq));
+            }
+            CK(cudaEventRecord(h->ev_a1, h->s_acq));
+        } else {
+            CK(cudaEventRecord(h->ev_a0, h->s_acq));
+            CK(gb::acq_launch_search(h->plan, a, h->s_acq));
+            CK(cudaEventRecord(h->ev_a1, h->s_acq));
+        }
     }
     CK(cudaMemcpyAsync(h->cells_pin, h->cells_dev, n_cells * sizeof(gb_acq_cell), cudaMemcpyDeviceToHost, h->s_acq));
     CK(cudaStreamSynchronize(h->s_acq));
@@ -679,7 +706,7 @@ extern "C" int gb_acq_bin_power(gb_handle* h, const gb_c32* iq, int K, int prn, 
     a.rot = h->n_coh > 1 ? h->rot : nullptr;
     a.rows = h->rows_dev;
     a.D = h->D; a.K = K; a.n_coh = h->n_coh; a.n_active = 1; a.spc = 0;
-    a.cells = nullptr; a.row_out = h->row_dev; a.d0 = doppler_bin;
+    a.cells = nullptr; a.row_out = h->row_dev; a.d0 = doppler_bin; a.spec = nullptr; a.d_lo = 0;
     CK(gb::acq_launch_row(h->plan, a, h->s_acq));
     CK(cudaMemcpyAsync(power_out, h->row_dev, sizeof(float) * h->N, cudaMemcpyDeviceToHost, h->s_acq));
     CK(cudaStreamSynchronize(h->s_acq));

@@ -119,6 +119,14 @@ int gb_acq_get_doppler_tables(gb_handle *h, gb_c32 *tables_out, float *carr_out)
 /* EXTENSION (BASELINE config 2, not in the reference): n_coh consecutive 1 ms blocks are summed
  * coherently (block c rotated by exp(-j 2 pi carr c N / fs)) before |.|^2.  1 = reference. */
 int gb_acq_set_coherent(gb_handle *h, int n_coh);
+/* Kernel organisation (results are bit-identical):
+ *   GB_ACQ_FUSED : one kernel, one CTA per (PRN, Doppler) does the whole chain in shared memory;
+ *   GB_ACQ_SHARED: two-kernel chain -- the PRN-independent forward path (wipe-off, coherent sum,
+ *                  forward FFT) once per (Doppler, group), spectra left in L2, then per (PRN, Doppler)
+ *                  x conj(code) -> IFFT -> |.|^2 -> cell.  Default. */
+#define GB_ACQ_FUSED 0
+#define GB_ACQ_SHARED 1
+int gb_acq_set_mode(gb_handle *h, int mode);
 /* samples_per_chip > 0 enables peak2; threshold is is_good_satellite's 7.0 */
 int gb_acq_set_detector(gb_handle *h, float threshold, int samples_per_chip);
 

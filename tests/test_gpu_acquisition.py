@@ -24,6 +24,26 @@ def _engine(gpu, n, fs, **kw):
 
 
 @pytest.mark.parametrize("n", [1024, 2048, 4092, 4096, 8184, 16368, 20000])
+def test_fused_and_shared_chains_are_bit_identical(gpu, oracle, ffi, n):
+    """GB_ACQ_FUSED (one kernel) and GB_ACQ_SHARED (forward path shared by all PRNs) run the same arithmetic."""
+    from gnss_sdr_rs_b200 import sdr_mock
+    fs = float(n) * 1000.0
+    K = 4
+    x = sdr_mock.baseband(fs, K, _sats(n, 7 * n), seed=n + 1)
+    eng = _engine(gpu, n, fs)
+    eng.make_doppler_tables(0.0, np.arange(-1000, 1001, 250, dtype=np.float32))
+    eng.set_detector(7.0, 2)
+    out = {}
+    for n_coh in (1, 2):
+        eng.set_coherent(n_coh)
+        for mode in (ffi.GB_ACQ_FUSED, ffi.GB_ACQ_SHARED):
+            eng.set_mode(mode)
+            out[(n_coh, mode)] = eng.search_cells(x, K, prn_mask=0x80000F0F)
+        assert out[(n_coh, 0)].tobytes() == out[(n_coh, 1)].tobytes()
+    assert out[(1, 0)]["peak"][0].max() > 0 and out[(1, 0)]["peak"][4].max() == 0
+
+
+@pytest.mark.parametrize("n", [1024, 2048, 4092, 4096, 8184, 16368, 20000])
 def test_cells_match_oracle_every_plan(gpu, oracle, n):
     from gnss_sdr_rs_b200 import sdr_mock
     fs = float(n) * 1000.0
