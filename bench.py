@@ -208,8 +208,11 @@ def run_ours(args, rank, world, local_rank):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
+    from gnss_sdr_rs_b200 import sharding
+    by_prn = args.shard == "prn" and world > 1
+    prn_mask = sharding.prn_mask_for_rank(rank, world, N_PRN) if by_prn else 0xFFFFFFFF
     hd = ffi.Handle(local_rank)
-    x = make_recording(0x6E56 + rank)
+    x = make_recording(0x6E56 + (0 if by_prn else rank))
     rb = ring.MulticastRingBuffer(hd, 1 << 20)
     rb.write_samples(x)
     x_pin = torch.from_numpy(x.view(np.float32).copy()).pin_memory()
@@ -221,7 +224,7 @@ def run_ours(args, rank, world, local_rank):
     eng.set_detector(7.0, 4)
     eng.set_mode(ffi.GB_ACQ_FUSED if args.acq_mode == "fused" else ffi.GB_ACQ_SHARED)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    gather_buf = [torch.zeros(N_PRN, 4, device="cuda") for _ in range(world)] if world > 1 else None
+    cuda_dev = torch.device("cuda", local_rank)
 
     def barrier():
         if dist is not None:
@@ -232,18 +235,20 @@ def run_ours(args, rank, world, local_rank):
         flush.zero_()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        res = eng.search_ring(0, K_MS)
+        res = eng.search_ring(0, K_MS, prn_mask=prn_mask)
         ms = eng.last_kernel_ms()
         g_ms = 0.0
         if dist is not None:
+            # the one collective of the path: per-PRN results of every rank, NCCL over NVLink
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            mine = torch.tensor([[r["prn"], r["code_phase_samples"], r["carrier_freq"], r["mag_relative"]] if r
-                                 else [0, 0, 0, 0] for r in res], dtype=torch.float32).cuda()
             e0.record()
-            dist.all_gather(gather_buf, mine)
+            gathered = sharding.all_gather_results(sharding.pack_results(res), dist, cuda_dev)
             e1.record()
             torch.cuda.synchronize()
             g_ms = e0.elapsed_time(e1)
+            if by_prn:
+                merged = sharding.merge_prn_shards(gathered)
+                res = [({"prn": p + 1, "found": 1} if merged[p, 0] else None) for p in range(N_PRN)]
         return ms + g_ms, (time.perf_counter() - t0) * 1e3, res
 
     for _ in range(max(args.warmup, 3)):
@@ -262,15 +267,13 @@ def run_ours(args, rank, world, local_rank):
 
     # e2e: pinned host IQ -> gb_acq_search (H2D + kernel + D2H + decision) per step
     for _ in range(2):
-        eng.search(x_pin_ptr, K_MS)
+        eng.search(x_pin_ptr, K_MS, prn_mask=prn_mask)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        res_e2e = eng.search(x_pin_ptr, K_MS)
+        res_e2e = eng.search(x_pin_ptr, K_MS, prn_mask=prn_mask)
         if dist is not None:
-            mine = torch.tensor([[r["prn"], r["code_phase_samples"], r["carrier_freq"], r["mag_relative"]] if r
-                                 else [0, 0, 0, 0] for r in res_e2e], dtype=torch.float32).cuda()
-            dist.all_gather(gather_buf, mine)
+            sharding.all_gather_results(sharding.pack_results(res_e2e), dist, cuda_dev)
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
     clocks = sampler.finish()
@@ -281,8 +284,9 @@ def run_ours(args, rank, world, local_rank):
         dev_ms, e2e_ms, wall_ms = [float(v) for v in t.cpu()]
     cells = N_PRN * len(DOPPLERS) * N_FFT
     ms_per_step = dev_ms / args.steps
-    value = world * cells / (ms_per_step * 1e-3)
-    e2e_value = world * cells / (e2e_ms * 1e-3)
+    units = 1 if by_prn else world   # recordings searched per step by the whole job
+    value = units * cells / (ms_per_step * 1e-3)
+    e2e_value = units * cells / (e2e_ms * 1e-3)
 
     if rank == 0:
         peak_tf = ctypes_float(hd, "gb_bench_fp32_tflops")
@@ -301,10 +305,10 @@ def run_ours(args, rank, world, local_rank):
             pass
         found = sorted(r["prn"] for r in res if r)
         line = {"metric": "acq_cells_per_sec", "value": value, "unit": "cells/s", "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if by_prn else "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(),
                 "wall_ms_per_step_incl_l2_flush": wall_ms / args.steps,
-                "x_realtime": world * (K_MS * 1e-3) / (ms_per_step * 1e-3),
+                "x_realtime": units * (K_MS * 1e-3) / (ms_per_step * 1e-3),
                 "e2e": {"value": e2e_value, "unit": "cells/s", "ms_per_step": e2e_ms,
                         "h2d_bytes_per_step": int(x.nbytes), "d2h_bytes_per_step": int(N_PRN * len(DOPPLERS) * 16),
                         "api": "gb_acq_search (pinned host IQ -> results)"},
@@ -358,6 +362,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--acq-mode", default="shared", choices=["shared", "fused"])
+    ap.add_argument("--shard", default="recording", choices=["recording", "prn"],
+                    help="N>1: one recording per GPU (weak scaling, default) or the PRNs of ONE recording dealt to the GPUs (strong)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

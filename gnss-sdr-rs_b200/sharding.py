@@ -1,0 +1,59 @@
+"""Multi-GPU sharding of the hot path: the units are independent, so ranks never exchange
+samples or spectra; the only collective is one small gather of per-PRN results (NCCL over NVLink on
+the GPU box, gloo in the CPU tests).
+
+  * acquisition of ONE recording: PRNs are dealt round-robin to ranks (`prn_mask_for_rank`), each rank
+    runs the full Doppler grid for its PRNs, `all_gather_results` merges the per-PRN results;
+  * batch acquisition: recordings are dealt to ranks (`items_for_rank`), results gathered at the end;
+  * tracking: channels are dealt to ranks (`items_for_rank`), no collective during the run.
+"""
+import numpy as np
+
+RESULT_FIELDS = ("found", "doppler_bin", "code_phase_samples", "carrier_freq", "mag_relative", "metric")
+
+
+def prn_mask_for_rank(rank, world, n_prn=32, base_mask=0xFFFFFFFF):
+    """Bit (prn-1) set for the PRNs this rank searches (the reference's mask convention, do_acquisition.rs:307)."""
+    mask = 0
+    k = 0
+    for p in range(n_prn):
+        if (base_mask >> p) & 1:
+            if k % world == rank:
+                mask |= 1 << p
+            k += 1
+    return mask
+
+
+def items_for_rank(n_items, rank, world):
+    """Contiguous block partition of recordings / channels."""
+    per = (n_items + world - 1) // world
+    lo = min(n_items, rank * per)
+    return range(lo, min(n_items, lo + per))
+
+
+def pack_results(results):
+    """List (one per PRN) of result dicts / None -> float64 [n_prn, 6] tensor-ready array."""
+    out = np.zeros((len(results), len(RESULT_FIELDS)), np.float64)
+    for i, r in enumerate(results):
+        if r:
+            out[i] = [1.0, r["doppler_bin"], r["code_phase_samples"], r["carrier_freq"], r["mag_relative"],
+                      r.get("metric", 0.0)]
+    return out
+
+
+def merge_prn_shards(packed_per_rank):
+    """Every PRN is owned by exactly one rank: the merged table takes each row from the rank that found / searched it."""
+    stack = np.stack(packed_per_rank)                      # [world, n_prn, 6]
+    owner = stack[:, :, 0].argmax(axis=0)                  # rank that reports found=1 (or 0 if none)
+    return stack[owner, np.arange(stack.shape[1])]
+
+
+def all_gather_results(packed, dist, device=None):
+    """One all_gather of a [n_prn, 6] array; returns the list of every rank's array."""
+    import torch
+    t = torch.from_numpy(np.ascontiguousarray(packed))
+    if device is not None:
+        t = t.to(device)
+    bufs = [torch.empty_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(bufs, t)
+    return [b.cpu().numpy() for b in bufs]

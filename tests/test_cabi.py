@@ -1,0 +1,146 @@
+"""The C-ABI library: loads, exports every symbol include/gnss_b200.h declares, host-only entry points agree with
+the oracle, and compute entry points fail loudly without a device (no CPU fallback).  CPU only."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    hdr = open(os.path.join(ROOT, "include", "gnss_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(gb_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def test_every_declared_symbol_is_exported_and_bound(ffi):
+    names = _declared()
+    assert len(names) >= 40
+    out = subprocess.run(["nm", "-D", "--defined-only", ffi.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r" T (gb_[a-z0-9_]+)", out))
+    assert set(names) <= exported, sorted(set(names) - exported)
+    assert set(names) == set(ffi.SIGNATURES), sorted(set(names) ^ set(ffi.SIGNATURES))
+    L = ffi.lib()
+    for n in names:
+        assert getattr(L, n) is not None
+
+
+def test_library_is_sm100a_native_cuda(ffi):
+    out = subprocess.run(["cuobjdump", "-lelf", ffi.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_header_is_plain_c(tmp_path):
+    src = tmp_path / "t.c"
+    src.write_text('#include "gnss_b200.h"\nint main(void){gb_acq_cell c; gb_trk_channel t; (void)c; (void)t; return sizeof(gb_acq_result) > 0 ? 0 : 1;}\n')
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), "-c", str(src),
+                    "-o", str(tmp_path / "t.o")], check=True)
+
+
+def test_struct_layouts_match_header(ffi, tmp_path):
+    src = tmp_path / "s.c"
+    src.write_text('#include <stdio.h>\n#include "gnss_b200.h"\nint main(void){printf("%zu %zu %zu %zu %zu\\n", sizeof(gb_acq_cell),'
+                   ' sizeof(gb_acq_result), sizeof(gb_trk_channel), sizeof(gb_trk_corr), sizeof(gb_config));return 0;}\n')
+    exe = tmp_path / "s"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    sizes = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    assert sizes == [ffi.CELL_DTYPE.itemsize, C.sizeof(ffi.AcqResult), C.sizeof(ffi.TrkChannel), ffi.CORR_DTYPE.itemsize,
+                     C.sizeof(ffi.Config)]
+
+
+def test_no_device_means_error_not_fallback(ffi):
+    L = ffi.lib()
+    if L.gb_device_count() > 0:
+        return  # on the GPU box the gpu-marked tests cover the device path
+    h = C.c_void_p()
+    assert L.gb_create(None, C.byref(h)) == ffi.GB_ENODEVICE
+    assert h.value is None
+    try:
+        ffi.Handle(0)
+        raise AssertionError("Handle() must raise without a device")
+    except ffi.GnssB200Error as e:
+        assert e.code == ffi.GB_ENODEVICE
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "gnss-sdr-rs_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp", ".sh")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "pyoracle" not in txt and "gnss_oracle" not in txt and "libgnss_oracle" not in txt, f
+
+
+def test_host_helpers_match_oracle(ffi, oracle):
+    L, O = ffi.lib(), oracle.lib()
+    tab = oracle.ca_table()
+    for prn in range(1, 33):
+        out = np.zeros(1023, np.int8)
+        assert L.gb_ca_code_chips(prn, ffi.ptr(out)) == 0
+        assert (out == tab[prn - 1]).all()
+    assert L.gb_ca_code_chips(33, ffi.ptr(np.zeros(1023, np.int8))) == ffi.GB_EINVAL
+    for fs in (2.048e6, 4.092e6, 4.096e6, 16367600.0, 20e6):
+        n = L.gb_num_samples_per_code(1.023e6, fs)
+        assert n == O.go_num_samples_per_code(1.023e6, fs)
+        a = np.zeros(n, np.int8)
+        assert L.gb_generate_ca_code_samples(19, 1.023e6, fs, ffi.ptr(a), n) == n
+        assert (a == oracle.ca_code_samples(19, 1.023e6, fs)).all()
+    # loop filter + channel init / start / reset
+    t1, t2 = C.c_float(), C.c_float()
+    for args in ((25.0, 0.7, 0.25), (2.0, 0.7, 1.0)):
+        L.gb_loop_filter_new(*args, C.byref(t1), C.byref(t2))
+        ref = O.go_loop_filter_new(*args)
+        assert (t1.value, t2.value) == (ref.tau1, ref.tau2)
+    ch = ffi.TrkChannel()
+    L.gb_trk_channel_init(C.byref(ch), 4, 4.096e6)
+    och = oracle.trk_channel(4, 4.096e6)
+    for k in ("id", "prn", "state", "lost_counter", "fs", "next_sample_index", "num_samples_per_code", "code_rate"):
+        assert getattr(ch, k) == getattr(och, k), k
+    assert (ch.pll_tau1, ch.pll_tau2, ch.dll_tau1, ch.dll_tau2) == (och.pll_filter.tau1, och.pll_filter.tau2,
+                                                                     och.dll_filter.tau1, och.dll_filter.tau2)
+
+
+def test_decide_matches_oracle_on_random_cells(ffi, oracle):
+    """gb_acq_decide (host O(D) scan, Q1) against the oracle's go_acq_decide on adversarial cell tables."""
+    from gnss_sdr_rs_b200 import acquisition
+    rng = np.random.default_rng(5)
+    n, fs = 4092, 4.092e6
+    for trial in range(300):
+        D = int(rng.integers(1, 40))
+        cells = np.zeros(D, ffi.CELL_DTYPE)
+        base = rng.uniform(0.5, 2.0, D).astype(np.float32)
+        cells["sum8"] = base * n
+        cells["peak"] = base * rng.choice([3.0, 6.9, 7.0, 7.2, 9.0, 30.0], D).astype(np.float32)
+        if trial % 7 == 0:
+            cells["peak"][:] = 0  # nothing above zero: 0/0 = NaN -> None
+            cells["sum8"][:] = 0
+        cells["argmax"] = rng.integers(0, n, D)
+        carr = (np.arange(D) * 500.0 - 7000.0).astype(np.float32)
+        got = acquisition.decide(cells, carr, 9, n, fs, local_tail=1000)
+        ocells = np.zeros(D, oracle.CELL_DTYPE)
+        for k in ("peak", "argmax", "sum8"):
+            ocells[k] = cells[k]
+        ref = oracle.acq_decide(ocells, carr, 9, n, fs, local_tail=1000)
+        assert (got is None) == (ref is None)
+        if ref:
+            assert got["doppler_bin"] == ref["bin"]
+            for k in ("code_phase_samples", "code_phase_chips", "carrier_freq", "mag_relative", "sample_global_index"):
+                assert got[k] == ref[k], k
+
+
+def test_acquisition_manager_mirror():
+    """do_acquisition.rs:339-395 on the host mirror."""
+    from gnss_sdr_rs_b200.acquisition import AcquisitionManager
+    m = AcquisitionManager()
+    assert m.mode == m.COLD
+    assert m.get_pacing_and_list(set()) == (500, 0xFFFFFFFF)
+    m.update_mode(3)
+    assert m.mode == m.WARM
+    assert m.get_pacing_and_list({1, 2, 3}) == (1000, 2040)
+    m.update_mode(5)
+    assert m.mode == m.STEADY
+    m.update_mode(0)
+    assert m.mode == m.COLD
