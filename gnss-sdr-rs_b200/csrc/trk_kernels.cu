@@ -102,27 +102,59 @@ template <int MODE> __global__ void __launch_bounds__(TRK_T) trk_kernel(const Tr
         const float code_step = st.code_rate / fs;                 // (code_rate / fs)
 
         float ip = 0.f, qp = 0.f, ie = 0.f, qe = 0.f, il = 0.f, ql = 0.f;
-        for (int i = threadIdx.x; i < n; i += TRK_T) {
-            const float2 x = __ldg(&a.samples[(start + (unsigned long long)i) & a.mask]);
-            const float phase = carrier_phase + (w * (float)i) / fs;  // :233
-            float cs, sn;
-            carrier<MODE>(phase, cs, sn);
-            const float sin_p = -sn;
-            const float re = x.x * cs - x.y * sin_p;   // Complex32 multiply (:237)
-            const float im = x.x * sin_p + x.y * cs;
-            const float chip_idx = mod1023(code_phase + ((float)i * code_step));  // :251
-            const float pc = ca_chip(row, chip_idx);
-            const float ec = ca_chip(row, chip_idx + 0.5f);
-            const float lc = ca_chip(row, chip_idx - 0.5f);
-            if (MODE == GB_TRK_ORDERED) {
+        if (MODE == GB_TRK_FAST) {
+            // Throughput form.  The f32 phase / chip arguments are evaluated exactly as the reference does
+            // (same roundings; the division is a reciprocal + one FMA-residual correction, correctly rounded
+            // in all but vanishingly rare halfway cases); sin/cos use a 2-term Cody-Waite reduction to
+            // [-pi, pi] and the SFU (abs error < 1e-6); the six sums are per-thread partials + tree reduction.
+            const float rcp_fs = 1.0f / fs;
+            const float inv_2pi = 0.15915494309189535f;
+            const float c1 = 6.28318548202514648f;        // fl(2 pi)
+            const float c2 = -1.74845553146951715e-7f;    // 2 pi - fl(2 pi)
+#pragma unroll 4
+            for (int i = threadIdx.x; i < n; i += TRK_T) {
+                const float2 x = __ldg(&a.samples[(start + (unsigned long long)i) & a.mask]);
+                const float fi = (float)i;
+                const float t = w * fi;
+                const float q0 = t * rcp_fs;
+                const float q = fmaf(fmaf(-q0, fs, t), rcp_fs, q0);      // (w * i) / fs
+                const float phase = carrier_phase + q;
+                const float k = rintf(phase * inv_2pi);
+                const float r = fmaf(-k, c2, fmaf(-k, c1, phase));
+                const float cs = __cosf(r), sn = __sinf(r);
+                const float re = fmaf(x.x, cs, x.y * sn);               // x * (cos, -sin)
+                const float im = fmaf(x.y, cs, -(x.x * sn));
+                float tc = code_phase + (fi * code_step);
+                if (!(tc >= 0.f && tc < 2046.f)) tc = fmodf(tc, 1023.f);
+                else if (tc >= 1023.f) tc -= 1023.f;
+                float pc, ec, lc;
+                if (tc >= 0.f) {                                          // always, unless the NCO diverged
+                    const int ipx = (int)tc;                              // tc in [0, 1023): trunc == floor
+                    int iex = (int)(tc + 0.5f);
+                    iex = iex >= 1023 ? iex - 1023 : iex;
+                    const int ilx = max((int)(tc - 0.5f), 0);             // Q7: negative saturates to chip 0
+                    pc = row[ipx]; ec = row[iex]; lc = row[ilx];
+                } else {
+                    pc = ca_chip(row, tc); ec = ca_chip(row, tc + 0.5f); lc = ca_chip(row, tc - 0.5f);
+                }
+                ip = fmaf(re, pc, ip); qp = fmaf(im, pc, qp);
+                ie = fmaf(re, ec, ie); qe = fmaf(im, ec, qe);
+                il = fmaf(re, lc, il); ql = fmaf(im, lc, ql);
+            }
+        } else {
+            for (int i = threadIdx.x; i < n; i += TRK_T) {
+                const float2 x = __ldg(&a.samples[(start + (unsigned long long)i) & a.mask]);
+                const float phase = carrier_phase + (w * (float)i) / fs;  // :233
+                float cs, sn;
+                carrier<MODE>(phase, cs, sn);
+                const float sin_p = -sn;
+                const float re = x.x * cs - x.y * sin_p;   // Complex32 multiply (:237)
+                const float im = x.x * sin_p + x.y * cs;
+                const float chip_idx = mod1023(code_phase + ((float)i * code_step));  // :251
                 rot[i] = make_float2(re, im);
-                chips[i] = (int8_t)pc;
-                chips[a.n_max + i] = (int8_t)ec;
-                chips[2 * a.n_max + i] = (int8_t)lc;
-            } else {
-                ip += re * pc; qp += im * pc;
-                ie += re * ec; qe += im * ec;
-                il += re * lc; ql += im * lc;
+                chips[i] = (int8_t)ca_chip(row, chip_idx);
+                chips[a.n_max + i] = (int8_t)ca_chip(row, chip_idx + 0.5f);
+                chips[2 * a.n_max + i] = (int8_t)ca_chip(row, chip_idx - 0.5f);
             }
         }
         if (MODE == GB_TRK_ORDERED) {

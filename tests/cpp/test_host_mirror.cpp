@@ -1,0 +1,213 @@
+// The reference's own unit tests restated against the C++ host mirror (gnss_sdr_rs.hpp over the C-ABI):
+//   do_acquisition.rs:339-395 (manager), multicast_ring_buffer.rs:147-209 (ring wrap),
+//   do_tracking.rs:464-570 (test_pll_frequency_pull_in), do_tracking.rs:572-655 (test_dll_code_phase_tracking),
+//   do_acquisition.rs:399-466 (acquisition on a recording; here a noise-free synthetic one).
+// usage: test_host_mirror [--cpu]   (--cpu: only the tests that need no device)
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "../../gnss-sdr-rs_b200/host/gnss_sdr_rs.hpp"
+
+using namespace gnss_sdr_rs;
+
+static int failures = 0;
+#define CHECK(cond)                                                        \
+    do {                                                                   \
+        if (!(cond)) { printf("FAIL %s:%d  %s\n", __FILE__, __LINE__, #cond); failures++; } \
+    } while (0)
+
+// generate_synthetic_signal, do_tracking.rs:434-462 (including its habit of indexing the resampled code by chip)
+static std::vector<Complex32> generate_synthetic_signal(const std::vector<int8_t>& ca_code, float doppler, float phase0,
+                                                        float code_phase0, float fs)
+{
+    const size_t n = (size_t)(fs / 1000.0f);
+    std::vector<Complex32> s;
+    const float step = GPS_L1_CA_CODE_RATE_CHIPS_PER_S / fs;
+    for (size_t i = 0; i < n; i++) {
+        const float cp = phase0 + (2.0f * 3.14159265358979323846f * doppler / fs * (float)i);
+        const float cur = code_phase0 + (step * (float)i);
+        const size_t idx = ((size_t)floorf(cur)) % 1023;
+        const float v = (float)ca_code[idx];
+        s.push_back(Complex32{v * cosf(cp), v * sinf(cp)});
+    }
+    return s;
+}
+
+static void test_manager()
+{
+    AcquisitionManager m;
+    CHECK(m.mode == SearchMode::ColdStart);
+    m.update_mode(3); CHECK(m.mode == SearchMode::WarmStart);
+    m.update_mode(5); CHECK(m.mode == SearchMode::SteadyState);
+    m.update_mode(0); CHECK(m.mode == SearchMode::ColdStart);
+    auto a = m.get_pacing_and_list({});
+    CHECK(a.first == 500 && a.second == 0xFFFFFFFFu);
+    m.update_mode(3);
+    auto b = m.get_pacing_and_list({1, 2, 3});
+    CHECK(b.first == 1000 && b.second == 2040);
+}
+
+static void test_host_helpers()
+{
+    LoopFilter pll(25.0f, 0.7f, 0.25f), dll(2.0f, 0.7f, 1.0f);
+    CHECK(fabsf(pll.tau1 - 1.117551e-4f) < 1e-9f && fabsf(dll.tau2 - 0.37f) < 1e-6f);
+    auto code = generate_ca_code_samples(1, GPS_L1_CA_CODE_RATE_CHIPS_PER_S, 4.092e6f);
+    CHECK(code.size() == 4092 && code[0] == 1 && code[8] == -1);
+    TrackingChannel c(0, 4.096e6f);
+    CHECK(!c.is_active() && c.s.num_samples_per_code == 4096);
+    AcquisitionResult r; r.prn = 7; r.carrier_freq = 10.f; r.code_phase_chips = 0.5f; r.sample_global_index = 99;
+    c.start(r);
+    CHECK(c.is_active() && c.s.prn == 7 && c.s.code_row == 7 && c.s.next_sample_index == 99);
+    c.reset();
+    CHECK(!c.is_active() && c.s.code_rate == 0.0f);
+}
+
+static void test_ring(std::shared_ptr<GpuEngine> e)
+{
+    MulticastRingBuffer ring(e, 1024);
+    auto mk = [](int lo, int hi) { std::vector<Complex32> v; for (int i = lo; i < hi; i++) v.push_back(Complex32{(float)i, 0.f}); return v; };
+    ring.write_samples(mk(0, 500));
+    CHECK(ring.get_head() == 500);
+    ring.write_samples(mk(500, 1030));
+    CHECK(ring.get_head() == 1030);
+    std::vector<Complex32> dest(10);
+    ring.copy_to_slice(1020, dest.data(), 10);
+    for (int i = 0; i < 10; i++) CHECK(dest[i].re == (float)(1020 + i));
+    ring.write_samples(mk(1030, 1050));
+    CHECK(ring.get_head() == 1050);
+    ring.copy_to_slice(1030, dest.data(), 10);
+    for (int i = 0; i < 10; i++) CHECK(dest[i].re == (float)(1030 + i));
+    bool threw = false;
+    try { MulticastRingBuffer bad(e, 1000); } catch (const std::invalid_argument&) { threw = true; }
+    CHECK(threw);
+}
+
+static void test_pll_frequency_pull_in(std::shared_ptr<GpuEngine> e)
+{
+    const uint8_t prn = 2;
+    const float fs = 4096000.0f;
+    auto mock = generate_ca_code_samples(prn, GPS_L1_CA_CODE_RATE_CHIPS_PER_S, fs);
+    const float true_doppler = 3000.0f;
+    auto sig = generate_synthetic_signal(mock, true_doppler, 0.f, 0.f, fs);
+    MulticastRingBuffer buf(e, 8 * sig.size());
+    buf.write_samples(sig);
+    CHECK(buf.get_head() == sig.size());
+    TrackingChannel ch(0, fs);
+    AcquisitionResult r; r.prn = prn; r.carrier_freq = 2950.0f; r.fs = fs; r.mag_relative = 10.f;
+    ch.start(r);
+    ch.update(buf);
+    const float err1 = ch.s.carrier_error;
+    CHECK(ch.s.carrier_error > 0.0f);
+    CHECK(ch.s.carrier_nco > 0.0f);
+    CHECK(ch.s.carrier_freq > 2950.0f);
+    buf.write_samples(sig);
+    buf.write_samples(sig);
+    CHECK(buf.get_head() == 3 * sig.size());
+    CHECK(ch.s.next_sample_index == ch.s.num_samples_per_code);
+    const size_t spc = ch.s.num_samples_per_code;
+    ch.update(buf);
+    const float err2 = ch.s.carrier_error;
+    CHECK(fabsf(true_doppler - err2) < fabsf(true_doppler - err1));
+    buf.write_samples(sig);
+    CHECK(buf.get_head() == 4 * sig.size());
+    CHECK(ch.s.next_sample_index == spc + ch.s.num_samples_per_code);
+    const size_t before = ch.s.next_sample_index;
+    ch.update(buf);
+    CHECK(ch.s.next_sample_index == before + ch.s.num_samples_per_code);
+    CHECK(fabsf(true_doppler - ch.s.carrier_error) < fabsf(true_doppler - err2));
+}
+
+static void test_dll_code_phase_tracking(std::shared_ptr<GpuEngine> e)
+{
+    const float fs = 4096000.0f;
+    const uint8_t prn = 3;
+    auto mock = generate_ca_code_samples(prn, GPS_L1_CA_CODE_RATE_CHIPS_PER_S, fs);
+    auto sig = generate_synthetic_signal(mock, 0.f, 0.f, 0.25f, fs);
+    MulticastRingBuffer buf(e, 2 * sig.size());
+    buf.write_samples(sig);
+    TrackingChannel ch(prn, fs);
+    AcquisitionResult r; r.prn = prn; r.fs = fs; r.mag_relative = 10.f;
+    ch.start(r);
+    ch.update(buf);
+    buf.write_samples(sig);
+    buf.write_samples(sig);
+    CHECK(buf.get_head() == 3 * sig.size());
+    CHECK(ch.s.next_sample_index == ch.s.num_samples_per_code);
+    const size_t spc = ch.s.num_samples_per_code;
+    ch.update(buf);
+    buf.write_samples(sig);
+    CHECK(ch.s.next_sample_index == spc + ch.s.num_samples_per_code);
+    const size_t before = ch.s.next_sample_index;
+    ch.update(buf);
+    CHECK(ch.s.next_sample_index == before + ch.s.num_samples_per_code);
+}
+
+static void test_acquisition(std::shared_ptr<GpuEngine> e)
+{
+    // PRN 6 at IF 4.1304 MHz + 1 kHz, code start at sample 7827, amplitude 4 in Gaussian noise sigma 8, rounded to
+    // int8 like the reference recording (noise is essential: on a noise-free input the 7.0 threshold already fires
+    // on far-off Doppler sidelobes and on cross-correlation peaks)
+    const float FS = 16367600.0f, IF = 4130400.0f;
+    const size_t N = 16368, K = 10;
+    int8_t chips[1023];
+    gb_ca_code_chips(6, chips);
+    std::vector<Complex32> raw(N * K);
+    uint64_t lcg = 0x6E55;
+    auto uni = [&lcg]() { lcg = lcg * 6364136223846793005ull + 1442695040888963407ull; return ((lcg >> 11) + 1) * (1.0 / 9007199254740993.0); };
+    for (size_t i = 0; i < N * K; i++) {
+        const double t = (double)i;
+        const double chip = fmod((t - 7827.0 + 10.0 * N) * 1.023e6 / FS, 1023.0);
+        const double ph = 2.0 * M_PI * fmod((IF + 1000.0) * t / FS, 1.0);
+        const double noise = 8.0 * sqrt(-2.0 * log(uni())) * cos(2.0 * M_PI * uni());
+        raw[i] = Complex32{(float)(int)lrint(4.0 * chips[(int)chip] * cos(ph) + noise), 0.f};
+    }
+    std::vector<DopplerShiftTable> tables;
+    for (float d = -7000.0f; d <= 7000.0f; d += 500.0f) tables.emplace_back(IF, d, FS, N);
+    CHECK(tables.size() == 29);
+    AcquisitionWorker w6(e, 6, N, FS);
+    auto r = w6.search_satellite(raw, tables, 0, K);
+    CHECK(r.has_value());
+    if (r) {
+        // the code period is 16367.6 samples at this rate, so the 10 ms average peak sits a few samples before 7827
+        CHECK(r->prn == 6 && (r->code_phase_samples + 8 >= 7827 && r->code_phase_samples <= 7830));
+        CHECK(r->sample_global_index == r->code_phase_samples);
+        CHECK(fabsf(r->carrier_freq - (IF + 1000.0f)) <= 4000.0f);  // the early exit stops on the first passing sidelobe (Q1)
+        CHECK(r->code_phase_chips == (float)r->code_phase_samples * GPS_L1_CA_CODE_RATE_CHIPS_PER_S / FS);
+    }
+    // batched form: same answer for PRN 6 (the reference's 7.0 threshold also false-alarms on a few absent PRNs;
+    // those decisions are compared with the oracle in tests/test_gpu_acquisition.py, not asserted here)
+    auto all = AcquisitionWorker::search_all(*e, raw, 500, K, 0xFFFFFFFFu);
+    bool saw6 = false;
+    for (const auto& a : all)
+        if (a.prn == 6) { saw6 = true; CHECK(r && a.code_phase_samples == r->code_phase_samples && a.sample_global_index == 500 + a.code_phase_samples); }
+    CHECK(saw6);
+    // FFT facade
+    FFT f(e, 2048);
+    std::vector<Complex32> x(2048, Complex32{0.f, 0.f});
+    x[1] = Complex32{1.f, 0.f};
+    auto X = f.execute(x);
+    CHECK(fabsf(X[512].re - 0.f) < 1e-6f && fabsf(X[512].im + 1.f) < 1e-6f);  // exp(-j pi/2)
+}
+
+int main(int argc, char** argv)
+{
+    const bool cpu_only = argc > 1 && !strcmp(argv[1], "--cpu");
+    test_manager();
+    test_host_helpers();
+    if (cpu_only) {
+        bool threw = false;
+        if (gb_device_count() == 0) {
+            try { GpuEngine e(0); } catch (const AcqError& err) { threw = err.code == GB_ENODEVICE; }
+            CHECK(threw);  // no CPU fallback
+        }
+    } else {
+        auto e = std::make_shared<GpuEngine>(0);
+        test_ring(e);
+        test_pll_frequency_pull_in(e);
+        test_dll_code_phase_tracking(e);
+        test_acquisition(e);
+    }
+    printf(failures ? "FAILED (%d)\n" : "ok\n", failures);
+    return failures ? 1 : 0;
+}

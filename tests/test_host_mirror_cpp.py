@@ -1,0 +1,28 @@
+"""Builds and runs tests/cpp/test_host_mirror.cpp: the reference's own unit tests restated against the C++ host
+mirror (gnss-sdr-rs_b200/host/gnss_sdr_rs.hpp) over the C-ABI."""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _build(tmp_path, ffi):
+    exe = str(tmp_path / "test_host_mirror")
+    libdir = os.path.dirname(ffi.LIB_PATH)
+    subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", os.path.join(ROOT, "tests", "cpp", "test_host_mirror.cpp"), "-o", exe,
+                    "-L", libdir, "-lgnss_b200", "-Wl,-rpath," + libdir], check=True)
+    return exe
+
+
+def test_cpp_host_mirror_cpu_part(tmp_path, ffi):
+    r = subprocess.run([_build(tmp_path, ffi), "--cpu"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+def test_cpp_host_mirror_reference_tests(tmp_path, ffi):
+    r = subprocess.run([_build(tmp_path, ffi)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "ok" in r.stdout
