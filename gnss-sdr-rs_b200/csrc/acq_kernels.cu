@@ -10,6 +10,8 @@
 #include "acq_kernels.cuh"
 #include "fft_smem.cuh"
 
+#include <stdlib.h>
+
 namespace gb {
 
 // ------------------------------------------------------------------ plans
@@ -22,8 +24,15 @@ using P8184 = Plan<8184, 288, 1, 0, 8, 3, 11, 31>;
 using P16368 = Plan<16368, 288, 1, 0, 16, 3, 11, 31>;
 using P20000 = Plan<20000, 512, 1, 0, 8, 4, 25, 25>;
 
-#define GB_FOR_EACH_PLAN(X) X(0, P1024) X(1, P2048) X(2, P4092) X(3, P4096) X(4, P8184) X(5, P16368) X(6, P20000)
-static const int kPlanSizes[] = {1024, 2048, 4092, 4096, 8184, 16368, 20000};
+// tuning variants of the headline plan (selected with the environment variable GB_ACQ_VARIANT=1..4)
+using P4092v1 = Plan<4092, 192, 3, 0, 12, 11, 31>;
+using P4092v2 = Plan<4092, 160, 3, 0, 12, 11, 31>;
+using P4092v3 = Plan<4092, 160, 4, 0, 12, 11, 31>;
+using P4092v4 = Plan<4092, 384, 1, 0, 12, 11, 31>;
+
+#define GB_FOR_EACH_PLAN(X) X(0, P1024) X(1, P2048) X(2, P4092) X(3, P4096) X(4, P8184) X(5, P16368) X(6, P20000) \
+    X(7, P4092v1) X(8, P4092v2) X(9, P4092v3) X(10, P4092v4)
+static const int kPlanSizes[] = {1024, 2048, 4092, 4096, 8184, 16368, 20000, -1, -1, -1, -1};
 static const int kNumPlans = sizeof(kPlanSizes) / sizeof(int);
 
 // reference arithmetic of multiply_simd_block (doppler_shift.rs:43-58): separate roundings, no FMA
@@ -106,7 +115,7 @@ __device__ __forceinline__ void stage0_wipe_forward(const AcqArgs& a, const floa
             Dft<G0::R, false>::run(v);
             line[P::phys(i)] = v[0];
 #pragma unroll
-            for (int q = 1; q < G0::R; q++) line[P::phys(i + q * G0::SUB)] = cmul(v[q], __ldg(&tw[i * q]));
+            for (int q = 1; q < G0::R; q++) line[P::phys(i + q * G0::SUB)] = cmul(v[q], __ldg(&tw[(q - 1) * G0::SUB + i]));
         }
     }
 }
@@ -220,7 +229,7 @@ __device__ __forceinline__ void final_stage_accumulate(const float2* __restrict_
             float2 v[G0::R];
             v[0] = line[P::phys(i)];
 #pragma unroll
-            for (int q = 1; q < G0::R; q++) v[q] = cmul_conj(line[P::phys(i + q * G0::SUB)], __ldg(&tw[i * q]));
+            for (int q = 1; q < G0::R; q++) v[q] = cmul_conj(line[P::phys(i + q * G0::SUB)], __ldg(&tw[(q - 1) * G0::SUB + i]));
             Dft<G0::R, true>::run(v);
 #pragma unroll
             for (int j = 0; j < G0::R; j++) acc[it][j] += v[j].x * v[j].x + v[j].y * v[j].y;
@@ -395,7 +404,7 @@ template <class P> __global__ void __launch_bounds__(P::T) code_fft_kernel(const
             Dft<G0::R, false>::run(v);
             line[P::phys(i)] = v[0];
 #pragma unroll
-            for (int q = 1; q < G0::R; q++) line[P::phys(i + q * G0::SUB)] = cmul(v[q], __ldg(&tw[i * q]));
+            for (int q = 1; q < G0::R; q++) line[P::phys(i + q * G0::SUB)] = cmul(v[q], __ldg(&tw[(q - 1) * G0::SUB + i]));
         }
     }
     __syncthreads();
@@ -439,7 +448,7 @@ template <class P, bool INV> __global__ void __launch_bounds__(P::T) fft_c2c_ker
             line[P::phys(i)] = v[0];
 #pragma unroll
             for (int q = 1; q < G0::R; q++) {
-                const float2 t = __ldg(&tw[i * q]);
+                const float2 t = __ldg(&tw[(q - 1) * G0::SUB + i]);
                 line[P::phys(i + q * G0::SUB)] = INV ? cmul_conj(v[q], t) : cmul(v[q], t);
             }
         }
@@ -483,14 +492,23 @@ __global__ void doppler_table_kernel(const float* __restrict__ steps, int n, flo
 // ------------------------------------------------------------------ host-side dispatch
 int acq_plan_index(int n)
 {
+    if (n == 4092) {
+        const char* v = getenv("GB_ACQ_VARIANT");
+        if (v && v[0] >= '1' && v[0] <= '4' && !v[1]) return 6 + (v[0] - '0');
+    }
     for (int i = 0; i < kNumPlans; i++)
         if (kPlanSizes[i] == n) return i;
     return -1;
 }
 int acq_plan_sizes(int* sizes, int cap)
 {
-    for (int i = 0; i < kNumPlans && i < cap; i++) sizes[i] = kPlanSizes[i];
-    return kNumPlans;
+    int n = 0;
+    for (int i = 0; i < kNumPlans; i++)
+        if (kPlanSizes[i] > 0) {
+            if (n < cap) sizes[n] = kPlanSizes[i];
+            n++;
+        }
+    return n;
 }
 
 template <class P> static int plan_radices(int* r)
@@ -505,6 +523,16 @@ int acq_plan_radices(int plan, int* radices)
     switch (plan) {
 #define X(i, P) \
     case i: return plan_radices<P>(radices);
+        GB_FOR_EACH_PLAN(X)
+#undef X
+    }
+    return 0;
+}
+int acq_plan_twiddles(int plan)
+{
+    switch (plan) {
+#define X(i, P) \
+    case i: return plan_twiddle_count<P>();
         GB_FOR_EACH_PLAN(X)
 #undef X
     }

@@ -13,7 +13,7 @@ struct AcqArgs {
     unsigned long long iq_mask;   // ring mask (all ones for a linear chunk)
     const float2* tables;    // D x N wipe-off tables (DopplerShiftTable::table)
     const float2* code_fft;  // n_prn x N code spectra, scrambled + transposed for the middle stage
-    const float2* tw;        // N stage twiddles exp(-2 pi i k / N)
+    const float2* tw;        // per-stage twiddles W_L^(i q), layout [stage][q-1][i]
     const float2* rot;       // D x n_coh coherent rotators or nullptr
     const int* rows;         // active PRN rows (index into code_fft / cells rows)
     int D, K, n_coh, n_active;
@@ -37,6 +37,7 @@ int acq_plan_index(int n);                    // -1 if there is no plan for n
 int acq_plan_sizes(int* sizes, int cap);      // list of planned sizes
 int acq_plan_radices(int plan, int* radices); // returns number of stages
 int acq_plan_threads(int plan);
+int acq_plan_twiddles(int plan);             // length of the per-stage twiddle buffer ([stage][q-1][i])
 size_t acq_plan_smem(int plan);
 
 cudaError_t acq_launch_search(int plan, const AcqArgs& a, cudaStream_t st);

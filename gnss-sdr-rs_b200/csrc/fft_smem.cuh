@@ -9,8 +9,8 @@
 //     permutation pass exists anywhere on the hot path.
 //   * one thread owns one radix-R butterfly entirely in registers; radix-R DFTs of odd primes use
 //     the conjugate-symmetric half form with compile-time constants (FFMA-immediate).
-//   * stage twiddles W_L^(i*q) come from one N-entry table (f64-evaluated, f32-rounded) through the
-//     read-only path.
+//   * stage twiddles W_L^(i*q) come from per-stage tables laid out [q][i] (f64-evaluated, f32-rounded)
+//     so a warp's loads are contiguous; read through the read-only path.
 //   * power-of-two plans use a padded line (one complex of padding per 16) so the short-stride
 //     stages are bank-conflict free; plans whose last radix is odd need no padding.
 #pragma once
@@ -239,8 +239,13 @@ template <class P, int S> struct StageGeo {
     static constexpr int SUB = P::sub(S);
     static constexpr int NB = P::N / R;                    // butterflies in the stage
     static constexpr int ITERS = (NB + P::T - 1) / P::T;   // per-thread iterations
-    static constexpr int TWS = P::N / L;                   // W_L^x = tw[x * TWS]
+    // Stage twiddles W_L^(i*q) are stored per stage as [q-1][i] (coalesced across the threads of a
+    // warp, which walk i); TWOFF is where this stage's block starts in the plan's twiddle buffer.
+    static constexpr int twoff(int s) { return s == 0 ? 0 : twoff(s - 1) + (P::radix(s - 1) - 1) * P::sub(s - 1); }
+    static constexpr int TWOFF = twoff(S);
 };
+// total number of twiddles of a plan
+template <class P> constexpr int plan_twiddle_count() { return StageGeo<P, P::NSTAGE - 1>::TWOFF + (P::radix(P::NSTAGE - 1) - 1) * P::sub(P::NSTAGE - 1); }
 
 // DIF stage S (INV=false: forward sign), smem -> smem
 template <class P, int S, bool INV> __device__ __forceinline__ void dif_stage(float2* __restrict__ s, const float2* __restrict__ tw)
@@ -262,7 +267,7 @@ template <class P, int S, bool INV> __device__ __forceinline__ void dif_stage(fl
                 if (G::SUB == 1) {
                     s[P::phys(base + q)] = v[q];
                 } else {
-                    const float2 w = __ldg(&tw[i * q * G::TWS]);
+                    const float2 w = __ldg(&tw[G::TWOFF + (q - 1) * G::SUB + i]);
                     s[P::phys(base + q * G::SUB)] = INV ? cmul_conj(v[q], w) : cmul(v[q], w);
                 }
             }
@@ -288,7 +293,7 @@ template <class P, int S, bool INV> __device__ __forceinline__ void dit_stage(fl
                 if (G::SUB == 1) {
                     v[q] = u;
                 } else {
-                    const float2 w = __ldg(&tw[i * q * G::TWS]);
+                    const float2 w = __ldg(&tw[G::TWOFF + (q - 1) * G::SUB + i]);
                     v[q] = INV ? cmul_conj(u, w) : cmul(u, w);
                 }
             }

@@ -144,18 +144,26 @@ int fft_resources(gb_handle* h, int plan, int n, FftRes** out)
 {
     FftRes& r = h->fft[plan];
     if (!r.tw) {
-        std::vector<float2> tw(n);
-        for (int k = 0; k < n; k++) {
-            const double ang = -2.0 * M_PI * (double)k / (double)n;
-            tw[k] = make_float2((float)cos(ang), (float)sin(ang));
-        }
         int radix[8];
         const int ns = gb::acq_plan_radices(plan, radix);
+        // per-stage twiddles W_L^(i q) = exp(-2 pi i (i q) / L), layout [stage][q-1][i], f64-evaluated
+        std::vector<float2> tw;
+        tw.reserve(gb::acq_plan_twiddles(plan));
+        for (int s = 0, L = n; s < ns; s++) {
+            const int r = radix[s], sub = L / r;
+            for (int q = 1; q < r; q++)
+                for (int i = 0; i < sub; i++) {
+                    const double ang = -2.0 * M_PI * (double)(((long long)i * q) % L) / (double)L;
+                    tw.push_back(make_float2((float)cos(ang), (float)sin(ang)));
+                }
+            L = sub;
+        }
+        if ((int)tw.size() != gb::acq_plan_twiddles(plan)) return GB_EINVAL;
         std::vector<int> fop(n);
         for (int k = 0; k < n; k++) fop[scrambled_pos(k, n, radix, ns)] = k;
-        CK(cudaMalloc((void**)&r.tw, sizeof(float2) * n));
+        CK(cudaMalloc((void**)&r.tw, sizeof(float2) * tw.size()));
         CK(cudaMalloc((void**)&r.fop, sizeof(int) * n));
-        CK(cudaMemcpy(r.tw, tw.data(), sizeof(float2) * n, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(r.tw, tw.data(), sizeof(float2) * tw.size(), cudaMemcpyHostToDevice));
         CK(cudaMemcpy(r.fop, fop.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
     }
     *out = &r;

@@ -1,0 +1,46 @@
+#!/usr/bin/env python3
+"""Times the acquisition kernels (CUDA events inside the library) for one workload; tuning helper.
+usage: time_acq.py [config2|config1|n=<N>,k=<K>,d=<D>,coh=<n_coh>] [shared|fused] [reps]"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import gnss_sdr_rs_b200._ffi as ffi  # noqa: E402
+from gnss_sdr_rs_b200 import acquisition  # noqa: E402
+
+
+def main():
+    wl = sys.argv[1] if len(sys.argv) > 1 else "config2"
+    mode = sys.argv[2] if len(sys.argv) > 2 else "shared"
+    reps = int(sys.argv[3]) if len(sys.argv) > 3 else 5
+    if wl == "config2":
+        n, K, D, coh = 4092, 200, 201, 10
+    elif wl == "config1":
+        n, K, D, coh = 16368, 10, 29, 1
+    else:
+        kv = dict(p.split("=") for p in wl.split(","))
+        n, K, D, coh = int(kv["n"]), int(kv["k"]), int(kv["d"]), int(kv.get("coh", 1))
+    fs = n * 1000.0
+    rng = np.random.default_rng(0)
+    x = (rng.standard_normal(n * K) + 1j * rng.standard_normal(n * K)).astype(np.complex64)
+    hd = ffi.Handle(0)
+    eng = acquisition.AcquisitionEngine(hd, n, fs)
+    eng.make_doppler_tables(0.0, np.linspace(-5000, 5000, D).astype(np.float32))
+    eng.set_coherent(coh)
+    eng.set_mode(ffi.GB_ACQ_FUSED if mode == "fused" else ffi.GB_ACQ_SHARED)
+    ms = []
+    for r in range(reps + 2):
+        eng.search_cells(x, K)
+        ms.append(eng.last_kernel_ms())
+    ms = ms[2:]
+    cells = 32 * D * n
+    print("%s %s variant=%s  N=%d K=%d D=%d coh=%d  kernel_ms min %.3f med %.3f  cells/s %.3e" % (
+        wl, mode, os.environ.get("GB_ACQ_VARIANT", "0"), n, K, D, coh, min(ms), float(np.median(ms)), cells / (min(ms) * 1e-3)))
+    hd.close()
+
+
+if __name__ == "__main__":
+    main()
