@@ -18,7 +18,7 @@ namespace gb {
 //                 N      T  MINB PAD  radices (forward DIF order; odd radices last => no padding needed)
 using P1024 = Plan<1024, 64, 8, 4, 4, 16, 16>;
 using P2048 = Plan<2048, 128, 4, 4, 8, 16, 16>;
-using P4092 = Plan<4092, 192, 2, 0, 12, 11, 31>;
+using P4092 = Plan<4092, 160, 4, 0, 12, 11, 31>;
 using P4096 = Plan<4096, 256, 2, 4, 16, 16, 16>;
 using P8184 = Plan<8184, 288, 1, 0, 8, 3, 11, 31>;
 using P16368 = Plan<16368, 288, 1, 0, 16, 3, 11, 31>;
@@ -27,7 +27,7 @@ using P20000 = Plan<20000, 512, 1, 0, 8, 4, 25, 25>;
 // tuning variants of the headline plan (selected with the environment variable GB_ACQ_VARIANT=1..4)
 using P4092v1 = Plan<4092, 192, 3, 0, 12, 11, 31>;
 using P4092v2 = Plan<4092, 160, 3, 0, 12, 11, 31>;
-using P4092v3 = Plan<4092, 160, 4, 0, 12, 11, 31>;
+using P4092v3 = Plan<4092, 192, 2, 0, 12, 11, 31>;
 using P4092v4 = Plan<4092, 384, 1, 0, 12, 11, 31>;
 
 #define GB_FOR_EACH_PLAN(X) X(0, P1024) X(1, P2048) X(2, P4092) X(3, P4096) X(4, P8184) X(5, P16368) X(6, P20000) \
@@ -277,9 +277,7 @@ template <class P, bool WANT_ROW> __global__ void __launch_bounds__(P::T, P::MIN
                 Dft<GM::R, false>::run(v);
 #pragma unroll
                 for (int q = 0; q < GM::R; q++) v[q] = cmul_conj(v[q], __ldg(&code[q * GM::NB + b]));
-                Dft<GM::R, true>::run(v);
-#pragma unroll
-                for (int j = 0; j < GM::R; j++) line[P::phys(base + j)] = v[j];
+                dft_emit<GM::R, true>(v, [&](int j, float2 y) { line[P::phys(base + j)] = y; });
             }
         }
         __syncthreads();
@@ -331,9 +329,7 @@ template <class P> __global__ void __launch_bounds__(P::T, P::MINB) acq_forward_
             float2 v[GM::R];
 #pragma unroll
             for (int j = 0; j < GM::R; j++) v[j] = line[P::phys(b * GM::R + j)];
-            Dft<GM::R, false>::run(v);
-#pragma unroll
-            for (int q = 0; q < GM::R; q++) out[q * GM::NB + b] = v[q];
+            dft_emit<GM::R, false>(v, [&](int q, float2 y) { out[q * GM::NB + b] = y; });
         }
     }
 }
@@ -368,9 +364,7 @@ template <class P> __global__ void __launch_bounds__(P::T, P::MINB) acq_inverse_
                 float2 v[GM::R];
 #pragma unroll
                 for (int q = 0; q < GM::R; q++) v[q] = cmul_conj(__ldg(&sg[q * GM::NB + b]), __ldg(&code[q * GM::NB + b]));
-                Dft<GM::R, true>::run(v);
-#pragma unroll
-                for (int j = 0; j < GM::R; j++) line[P::phys(b * GM::R + j)] = v[j];
+                dft_emit<GM::R, true>(v, [&](int j, float2 y) { line[P::phys(b * GM::R + j)] = y; });
             }
         }
         __syncthreads();

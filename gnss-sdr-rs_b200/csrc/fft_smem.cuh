@@ -170,6 +170,52 @@ template <int R, bool INV> struct DftOddPrime {
         }
     }
 };
+// Same arithmetic as DftOddPrime::run, but every output is handed to `emit(q, X_q)` the moment it is
+// final instead of being written back into v[]: the a/b half-sums are the only long-lived registers, so
+// a radix-31 butterfly needs ~75 registers instead of ~130.
+template <int R, bool INV, class Emit> __device__ __forceinline__ void dft_odd_prime_emit(float2 (&v)[R], Emit emit)
+{
+    constexpr int H = (R - 1) / 2;
+    float2 a[H + 1], b[H + 1];
+    float2 x0 = v[0];
+    const float2 v0 = v[0];
+#pragma unroll
+    for (int j = 1; j <= H; j++) {
+        a[j] = cadd(v[j], v[R - j]);
+        b[j] = csub(v[j], v[R - j]);
+        x0 = cadd(x0, a[j]);
+    }
+    emit(0, x0);
+#pragma unroll
+    for (int q = 1; q <= H; q++) {
+        float cr = v0.x, ci = v0.y, sr = 0.f, si = 0.f;
+#pragma unroll
+        for (int j = 1; j <= H; j++) {
+            const int k = (j * q) % R;
+            const float c = RT<R>::c(k);
+            const float s = INV ? RT<R>::s(k) : -RT<R>::s(k);
+            cr = fmaf(a[j].x, c, cr);
+            ci = fmaf(a[j].y, c, ci);
+            sr = fmaf(-b[j].y, s, sr);
+            si = fmaf(b[j].x, s, si);
+        }
+        emit(q, make_float2(cr + sr, ci + si));
+        emit(R - q, make_float2(cr - sr, ci - si));
+    }
+}
+
+// dft_emit<R,INV>(v, emit): DFT of v with outputs delivered through emit(q, X_q).
+template <int R, bool INV, class Emit> __device__ __forceinline__ void dft_emit(float2 (&v)[R], Emit emit)
+{
+    if constexpr (R == 3 || R == 5 || R == 7 || R == 11 || R == 13 || R == 17 || R == 19 || R == 23 || R == 29 || R == 31) {
+        dft_odd_prime_emit<R, INV>(v, emit);
+    } else {
+        Dft<R, INV>::run(v);
+#pragma unroll
+        for (int q = 0; q < R; q++) emit(q, v[q]);
+    }
+}
+
 template <bool INV> struct Dft<3, INV> : DftOddPrime<3, INV> {};
 template <bool INV> struct Dft<5, INV> : DftOddPrime<5, INV> {};
 template <bool INV> struct Dft<7, INV> : DftOddPrime<7, INV> {};

@@ -17,6 +17,7 @@ namespace {
 
 const float kCodeRate = 1.023e6f;  // GPS_L1_CA_CODE_RATE_CHIPS_PER_S (gps_property_constants.rs:4)
 const float kPiF = 3.14159265358979323846f;
+const size_t kStageSamples = (size_t)1 << 19;  // 4 MiB per pinned staging slot
 
 struct FftRes {
     float2* tw = nullptr;
@@ -36,6 +37,10 @@ struct gb_handle {
     uint64_t ring_cap = 0, ring_head = 0;
     int8_t* i8_stage = nullptr;
     size_t i8_cap = 0;
+    // pinned host staging (two slots) so pageable caller buffers are released at once and the H2D DMA is asynchronous
+    float2* pin_stage[2] = {nullptr, nullptr};
+    cudaEvent_t pin_free[2] = {nullptr, nullptr};
+    int pin_next = 0;
 
     // acquisition
     int plan = -1, N = 0, n_prn = 0, D = 0, n_coh = 1, spc = 0, mode = GB_ACQ_SHARED;
@@ -244,6 +249,10 @@ extern "C" int gb_create(const gb_config* cfg, gb_handle** out)
         CK(cudaMalloc((void**)&h->ca_table_dev, tab.size()));
         CK(cudaMemcpy(h->ca_table_dev, tab.data(), tab.size(), cudaMemcpyHostToDevice));
     }
+    for (int s = 0; s < 2; s++) {
+        CK(cudaMallocHost((void**)&h->pin_stage[s], kStageSamples * sizeof(float2)));
+        CK(cudaEventCreateWithFlags(&h->pin_free[s], cudaEventDisableTiming));
+    }
     CK(cudaMallocHost((void**)&h->rows_pin, sizeof(int) * 256));
     CK(cudaMalloc((void**)&h->rows_dev, sizeof(int) * 256));
     if (cfg && cfg->ring_capacity) return gb_ring_create(h, cfg->ring_capacity);
@@ -263,6 +272,10 @@ extern "C" int gb_destroy(gb_handle* h)
     for (auto& r : h->fft) {
         if (r.tw) cudaFree(r.tw);
         if (r.fop) cudaFree(r.fop);
+    }
+    for (int s = 0; s < 2; s++) {
+        if (h->pin_stage[s]) cudaFreeHost(h->pin_stage[s]);
+        if (h->pin_free[s]) cudaEventDestroy(h->pin_free[s]);
     }
     if (h->cells_pin) cudaFreeHost(h->cells_pin);
     if (h->rows_pin) cudaFreeHost(h->rows_pin);
@@ -331,20 +344,38 @@ extern "C" int gb_ring_reset(gb_handle* h)
     h->ring_head = 0;
     return GB_OK;
 }
-// write_samples (multicast_ring_buffer.rs:66-101): wrap-aware copy at head & mask, then head += n
+// write_samples (multicast_ring_buffer.rs:66-101): wrap-aware copy at head & mask, then head += n.
+// The caller's buffer is copied into a pinned staging slot (double-buffered) and DMA'd with cudaMemcpyAsync on
+// the copy stream, so the call returns as soon as the bytes are staged and the caller may reuse its buffer.
+static int ring_put(gb_handle* h, const float2* src, uint64_t n)
+{
+    uint64_t done = 0;
+    while (done < n) {
+        const uint64_t chunk = (n - done) < kStageSamples ? (n - done) : kStageSamples;
+        const int s = h->pin_next;
+        h->pin_next ^= 1;
+        CK(cudaEventSynchronize(h->pin_free[s]));  // the DMA that last used this slot has finished
+        memcpy(h->pin_stage[s], src + done, chunk * sizeof(float2));
+        const uint64_t start = (h->ring_head + done) & (h->ring_cap - 1);
+        const uint64_t first = (start + chunk <= h->ring_cap) ? chunk : h->ring_cap - start;
+        CK(cudaMemcpyAsync(h->ring + start, h->pin_stage[s], first * sizeof(float2), cudaMemcpyHostToDevice, h->s_copy));
+        if (first < chunk)
+            CK(cudaMemcpyAsync(h->ring, h->pin_stage[s] + first, (chunk - first) * sizeof(float2), cudaMemcpyHostToDevice,
+                               h->s_copy));
+        CK(cudaEventRecord(h->pin_free[s], h->s_copy));
+        done += chunk;
+    }
+    CK(cudaEventRecord(h->ev_copy, h->s_copy));
+    h->ring_head += n;
+    return GB_OK;
+}
+
 extern "C" int gb_ring_write(gb_handle* h, const gb_c32* samples, uint64_t n)
 {
     if (!h || !h->ring) return GB_ESTATE;
     if (!samples || n > h->ring_cap) return GB_EINVAL;
     CK(cudaSetDevice(h->device));
-    const uint64_t start = h->ring_head & (h->ring_cap - 1);
-    const uint64_t first = (start + n <= h->ring_cap) ? n : h->ring_cap - start;
-    CK(cudaMemcpyAsync(h->ring + start, samples, first * sizeof(float2), cudaMemcpyHostToDevice, h->s_copy));
-    if (first < n)
-        CK(cudaMemcpyAsync(h->ring, samples + first, (n - first) * sizeof(float2), cudaMemcpyHostToDevice, h->s_copy));
-    CK(cudaEventRecord(h->ev_copy, h->s_copy));
-    h->ring_head += n;
-    return GB_OK;
+    return ring_put(h, reinterpret_cast<const float2*>(samples), n);
 }
 extern "C" int gb_ring_write_i8(gb_handle* h, const int8_t* samples, uint64_t n)
 {
@@ -533,7 +564,11 @@ static int search_cells(gb_handle* h, const float2* iq_dev, uint64_t start, uint
     const size_t n_cells = (size_t)h->n_prn * h->D;
     if (h->cells_cap < n_cells) {
         if (h->cells_dev) cudaFree(h->cells_dev);
-        if (h->cells_pin) cudaFreeHost(h->cells_pin);
+        for (int s = 0; s < 2; s++) {
+        if (h->pin_stage[s]) cudaFreeHost(h->pin_stage[s]);
+        if (h->pin_free[s]) cudaEventDestroy(h->pin_free[s]);
+    }
+    if (h->cells_pin) cudaFreeHost(h->cells_pin);
         h->cells_dev = nullptr; h->cells_pin = nullptr; h->cells_cap = 0;
         CK(cudaMalloc((void**)&h->cells_dev, n_cells * sizeof(gb_acq_cell)));
         CK(cudaMallocHost((void**)&h->cells_pin, n_cells * sizeof(gb_acq_cell)));

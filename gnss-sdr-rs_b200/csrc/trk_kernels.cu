@@ -13,7 +13,6 @@
 
 namespace gb {
 
-#define TRK_T 128
 static __device__ __constant__ float kTwoPi = 6.28318530717958647692f;  // 2.0 * std::f32::consts::PI
 
 // Rust `as usize` for f32: saturating, NaN -> 0 (Q7)
@@ -60,14 +59,14 @@ __device__ __forceinline__ float block_sum(float v, float* red)
     return v;
 }
 
-template <int MODE> __global__ void __launch_bounds__(TRK_T) trk_kernel(const TrkArgs a)
+template <int MODE, int TRK_T> __global__ void __launch_bounds__(TRK_T) trk_kernel(const TrkArgs a)
 {
     extern __shared__ unsigned char smem_raw[];
     float* row = reinterpret_cast<float*>(smem_raw);          // 1024 floats: this channel's C/A row
-    float* red = row + 1024;                                  // 6 x (TRK_T/32) partials + 8
+    float* red = row + 1024;                                  // 8 + 6 x (TRK_T/32) partials (128 floats reserved)
     __shared__ gb_trk_channel st;
     __shared__ int s_go;
-    float2* rot = reinterpret_cast<float2*>(red + 64);        // ORDERED: n_max rotated samples
+    float2* rot = reinterpret_cast<float2*>(red + 128);       // ORDERED: n_max rotated samples
     int8_t* chips = reinterpret_cast<int8_t*>(rot + (MODE == GB_TRK_ORDERED ? a.n_max : 0));  // 3 x n_max
 
     const int c = blockIdx.x;
@@ -250,21 +249,30 @@ template <int MODE> __global__ void __launch_bounds__(TRK_T) trk_kernel(const Tr
     }
 }
 
-cudaError_t trk_launch(const TrkArgs& a, int mode, cudaStream_t st)
+template <int T> static cudaError_t launch_t(const TrkArgs& a, int mode, cudaStream_t st)
 {
-    if (a.n_channels <= 0) return cudaSuccess;
-    size_t smem = (1024 + 64) * sizeof(float);
+    size_t smem = (1024 + 128) * sizeof(float);
     if (mode == GB_TRK_ORDERED) {
         smem += (size_t)a.n_max * (sizeof(float2) + 3) + 16;
         if (smem > 48 * 1024) {
-            cudaError_t e = cudaFuncSetAttribute(trk_kernel<GB_TRK_ORDERED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaError_t e = cudaFuncSetAttribute(trk_kernel<GB_TRK_ORDERED, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
         }
-        trk_kernel<GB_TRK_ORDERED><<<a.n_channels, TRK_T, smem, st>>>(a);
+        trk_kernel<GB_TRK_ORDERED, T><<<a.n_channels, T, smem, st>>>(a);
     } else {
-        trk_kernel<GB_TRK_FAST><<<a.n_channels, TRK_T, smem, st>>>(a);
+        trk_kernel<GB_TRK_FAST, T><<<a.n_channels, T, smem, st>>>(a);
     }
     return cudaGetLastError();
+}
+
+// CTA size: with >= 600 channels 128 threads keep every SM full of independent channels; with fewer channels the
+// run is bound by the per-epoch latency of one CTA, so each channel gets more threads.
+cudaError_t trk_launch(const TrkArgs& a, int mode, cudaStream_t st)
+{
+    if (a.n_channels <= 0) return cudaSuccess;
+    if (a.n_channels >= 600) return launch_t<128>(a, mode, st);
+    if (a.n_channels >= 250) return launch_t<256>(a, mode, st);
+    return launch_t<512>(a, mode, st);
 }
 
 }  // namespace gb

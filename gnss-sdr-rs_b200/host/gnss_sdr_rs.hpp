@@ -83,8 +83,7 @@ class MulticastRingBuffer {
     }
     void write_samples(const std::vector<Complex32>& s)
     {
-        int rc = gb_ring_write(e_->raw(), s.data(), s.size());
-        if (!rc) rc = gb_synchronize(e_->raw());  // the caller may free `s` right away
+        const int rc = gb_ring_write(e_->raw(), s.data(), s.size());  // staged through pinned memory
         if (rc) throw MulticastRingBuffError(rc);
     }
     size_t get_head() const { return (size_t)gb_ring_head(e_->raw()); }

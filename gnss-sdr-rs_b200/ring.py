@@ -18,8 +18,7 @@ class MulticastRingBuffer:
             self.hd.call("gb_ring_write_i8", _ffi.ptr(x), x.size)
         else:
             x = np.ascontiguousarray(samples, np.complex64)
-            self.hd.call("gb_ring_write", _ffi.ptr(x), x.size)
-            self.hd.call("gb_synchronize")  # the source array may be a temporary
+            self.hd.call("gb_ring_write", _ffi.ptr(x), x.size)  # staged through pinned memory: x may be freed now
 
     def get_head(self):
         return int(self.hd.L.gb_ring_head(self.hd.h))
