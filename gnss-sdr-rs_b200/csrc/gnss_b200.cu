@@ -564,11 +564,7 @@ static int search_cells(gb_handle* h, const float2* iq_dev, uint64_t start, uint
     const size_t n_cells = (size_t)h->n_prn * h->D;
     if (h->cells_cap < n_cells) {
         if (h->cells_dev) cudaFree(h->cells_dev);
-        for (int s = 0; s < 2; s++) {
-        if (h->pin_stage[s]) cudaFreeHost(h->pin_stage[s]);
-        if (h->pin_free[s]) cudaEventDestroy(h->pin_free[s]);
-    }
-    if (h->cells_pin) cudaFreeHost(h->cells_pin);
+        if (h->cells_pin) cudaFreeHost(h->cells_pin);
         h->cells_dev = nullptr; h->cells_pin = nullptr; h->cells_cap = 0;
         CK(cudaMalloc((void**)&h->cells_dev, n_cells * sizeof(gb_acq_cell)));
         CK(cudaMallocHost((void**)&h->cells_pin, n_cells * sizeof(gb_acq_cell)));
