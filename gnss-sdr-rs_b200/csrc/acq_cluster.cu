@@ -1,0 +1,235 @@
+// acq_cluster.cu -- acquisition for code periods that do not fit one CTA's shared memory (sm_100a).
+//
+// N = 80000 (Galileo-E1-like 4 ms code at 20 Msps, BASELINE config 4) is 640 KB of complex f32.  The line
+// is spread over a thread-block CLUSTER of RO = 4 CTAs (4 SMs, 160 KB each): the first forward stage is a
+// radix-4 decimation-in-frequency step whose four output sub-blocks are independent length-20000 problems,
+// one per CTA (existing Plan<20000>), and the last inverse stage is the matching radix-4 DIT step that reads
+// the four sub-blocks through DISTRIBUTED SHARED MEMORY (cluster.map_shared_rank) -- the 640 KB line never
+// leaves the four SMs.  The accumulated |.|^2 row (N floats) lives in L2/HBM and is reduced to a cell by
+// reduce_rows_kernel.  Same arithmetic and quirks as acq_fused_kernel; n_coh = 1 only.
+#include <cooperative_groups.h>
+
+#include "acq_common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace gb {
+
+constexpr int kRO = 4;
+using PI80k = P20000;
+constexpr int kN80k = PI80k::N * kRO;
+
+// multiply by W_4^k (forward: (-i)^k, inverse: (+i)^k)
+template <bool INV> __device__ __forceinline__ float2 rot4(float2 a, int k)
+{
+    k &= 3;
+    if (k == 0) return a;
+    if (k == 2) return make_float2(-a.x, -a.y);
+    const bool plus_i = INV ? (k == 1) : (k == 3);
+    return plus_i ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x);
+}
+
+// outer forward stage for sub-block r: V_r[i] = (sum_j x[i + j*NI] W_4^(j r)) * W_N^(i r)
+template <class PI, class Load>
+__device__ __forceinline__ void outer_forward(int r, const float2* __restrict__ otw, float2* __restrict__ line, Load load)
+{
+    constexpr int NI = PI::N;
+    for (int i = threadIdx.x; i < NI; i += PI::T) {
+        float2 v = load(i);
+#pragma unroll
+        for (int j = 1; j < kRO; j++) v = cadd(v, rot4<false>(load(i + j * NI), j * r));
+        if (r > 0) v = cmul(v, __ldg(&otw[(r - 1) * NI + i]));
+        line[PI::phys(i)] = v;
+    }
+}
+
+// inner length-NI chain on this CTA's sub-block: forward FFT, x conj(code), inverse FFT (all in shared memory)
+template <class PI>
+__device__ __forceinline__ void inner_chain(float2* __restrict__ line, const float2* __restrict__ tw,
+                                            const float2* __restrict__ code)
+{
+    constexpr int LASTS = PI::NSTAGE - 1;
+    using GM = StageGeo<PI, LASTS>;
+    DifRange<PI, 0, LASTS, false>::run(line, tw);
+#pragma unroll
+    for (int it = 0; it < GM::ITERS; it++) {
+        const int b = threadIdx.x + it * PI::T;
+        if (GM::NB % PI::T == 0 || b < GM::NB) {
+            const int base = b * GM::R;
+            float2 v[GM::R];
+#pragma unroll
+            for (int j = 0; j < GM::R; j++) v[j] = line[PI::phys(base + j)];
+            Dft<GM::R, false>::run(v);
+#pragma unroll
+            for (int q = 0; q < GM::R; q++) v[q] = cmul_conj(v[q], __ldg(&code[q * GM::NB + b]));
+            dft_emit<GM::R, true>(v, [&](int j, float2 y) { line[PI::phys(base + j)] = y; });
+        }
+    }
+    __syncthreads();
+    DitRange<PI, LASTS - 1, -1, true>::run(line, tw);
+}
+
+template <class PI> __global__ void __cluster_dims__(kRO, 1, 1) __launch_bounds__(PI::T, 1) acq_cluster_kernel(const AcqArgs a)
+{
+    extern __shared__ float2 line[];
+    constexpr int NI = PI::N;
+    constexpr int N = NI * kRO;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int r = (int)cluster.block_rank();
+    const int cell = (int)(blockIdx.x / kRO);
+    const int d = cell % a.D;
+    const int row = a.rows[cell / a.D];
+    const float2* __restrict__ w = a.tables + (size_t)d * N;
+    const float2* __restrict__ code = a.code_fft + (size_t)row * N + (size_t)r * NI;
+    const float2* __restrict__ otw = a.otw;
+    float* __restrict__ acc = a.acc_rows + (size_t)cell * N + (size_t)r * NI;
+    const float2* peer[kRO];
+#pragma unroll
+    for (int q = 0; q < kRO; q++) peer[q] = cluster.map_shared_rank(line, q);
+
+    for (int k = 0; k < a.K; k++) {
+        const unsigned long long blk0 = (unsigned long long)k * N;
+        outer_forward<PI>(r, otw, line, [&](int n) { return wipe(ld_iq(a, blk0 + n), __ldg(&w[n])); });
+        __syncthreads();
+        inner_chain<PI>(line, a.tw, code);
+        cluster.sync();  // every sub-block now holds u_q[i] in natural order
+        // outer inverse stage (DIT radix 4) for the outputs this CTA owns: n = i + r*NI
+        for (int i = threadIdx.x; i < NI; i += PI::T) {
+            float2 y = peer[0][PI::phys(i)];
+#pragma unroll
+            for (int q = 1; q < kRO; q++) {
+                const float2 u = cmul_conj(peer[q][PI::phys(i)], __ldg(&otw[(q - 1) * NI + i]));
+                y = cadd(y, rot4<true>(u, q * r));
+            }
+            const float p = y.x * y.x + y.y * y.y;
+            acc[i] = (k == 0) ? p : acc[i] + p;
+        }
+        cluster.sync();  // peers are done reading this CTA's line before the next block overwrites it
+    }
+}
+
+// code spectra for the cluster plan: same forward path on the +-1 code samples, one CTA per (PRN, sub-block)
+template <class PI> __global__ void __launch_bounds__(PI::T, 1) code_fft_cluster_kernel(const int8_t* __restrict__ codes,
+                                                                                      float2* __restrict__ code_fft,
+                                                                                      const float2* __restrict__ tw,
+                                                                                      const float2* __restrict__ otw)
+{
+    extern __shared__ float2 line[];
+    constexpr int NI = PI::N;
+    constexpr int N = NI * kRO;
+    constexpr int LASTS = PI::NSTAGE - 1;
+    using GM = StageGeo<PI, LASTS>;
+    const int r = (int)(blockIdx.x % kRO);
+    const int prn = (int)(blockIdx.x / kRO);
+    const int8_t* c = codes + (size_t)prn * N;
+    float2* out = code_fft + (size_t)prn * N + (size_t)r * NI;
+    outer_forward<PI>(r, otw, line, [&](int n) { return make_float2((float)c[n], 0.f); });
+    __syncthreads();
+    DifRange<PI, 0, LASTS, false>::run(line, tw);
+#pragma unroll
+    for (int it = 0; it < GM::ITERS; it++) {
+        const int b = threadIdx.x + it * PI::T;
+        if (GM::NB % PI::T == 0 || b < GM::NB) {
+            float2 v[GM::R];
+#pragma unroll
+            for (int j = 0; j < GM::R; j++) v[j] = line[PI::phys(b * GM::R + j)];
+            dft_emit<GM::R, false>(v, [&](int q, float2 y) { out[q * GM::NB + b] = y; });
+        }
+    }
+}
+
+// accumulated power row (global) -> cell; also used for diagnostics rows
+__global__ void __launch_bounds__(512) reduce_rows_kernel(const float* __restrict__ acc_rows, int n, int D, const int* rows,
+                                                         int spc, gb_acq_cell* cells)
+{
+    __shared__ float red_v[33];
+    __shared__ unsigned red_i[33];
+    __shared__ float red_s[33];
+    const int cell = blockIdx.x;
+    const float* __restrict__ acc = acc_rows + (size_t)cell * n;
+    const int nsum = (n / 8) * 8;
+    PeakIdx pk;
+    pk.v = 0.f;
+    pk.idx = 0u;
+    float sum = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const float v = acc[i];
+        PeakIdx c;
+        c.v = v;
+        c.idx = (unsigned)i;
+        if (v > 0.f) pk = peak_merge(pk, c);
+        if (i < nsum) sum += v;
+    }
+    pk = warp_peak(pk);
+    sum = warp_sum(sum);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    if (lane == 0) { red_v[warp] = pk.v; red_i[warp] = pk.idx; red_s[warp] = sum; }
+    __syncthreads();
+    if (warp == 0) {
+        PeakIdx q;
+        q.v = lane < nw ? red_v[lane] : 0.f;
+        q.idx = lane < nw ? red_i[lane] : 0u;
+        float s = lane < nw ? red_s[lane] : 0.f;
+        q = warp_peak(q);
+        s = warp_sum(s);
+        if (lane == 0) { red_v[32] = q.v; red_i[32] = q.idx; red_s[32] = s; }
+    }
+    __syncthreads();
+    const float peak = red_v[32];
+    const unsigned arg = red_i[32];
+    const float total = red_s[32];
+    float p2 = 0.f;
+    if (spc > 0) {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            int dist = abs(i - (int)arg);
+            dist = min(dist, n - dist);
+            if (dist > spc) p2 = fmaxf(p2, acc[i]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) p2 = fmaxf(p2, __shfl_xor_sync(0xffffffffu, p2, o));
+        __syncthreads();
+        if (lane == 0) red_v[warp] = p2;
+        __syncthreads();
+        if (warp == 0) {
+            float v = lane < nw ? red_v[lane] : 0.f;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+            p2 = v;
+        }
+    }
+    if (threadIdx.x == 0) {
+        gb_acq_cell c;
+        c.peak = peak; c.argmax = arg; c.sum8 = total; c.peak2 = p2;
+        cells[(size_t)rows[cell / D] * D + (cell % D)] = c;
+    }
+}
+
+// ------------------------------------------------------------------ host side
+int acq_cluster_supported(int n) { return n == kN80k; }
+int acq_cluster_inner(int n) { return n == kN80k ? PI80k::N : 0; }
+int acq_cluster_outer(int n) { return n == kN80k ? kRO : 0; }
+
+static size_t cluster_smem() { return sizeof(float2) * (size_t)PI80k::LINE; }
+
+cudaError_t acq_cluster_launch_search(const AcqArgs& a, cudaStream_t st)
+{
+    const size_t smem = cluster_smem();
+    cudaError_t e = cudaFuncSetAttribute(acq_cluster_kernel<PI80k>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    acq_cluster_kernel<PI80k><<<a.n_active * a.D * kRO, PI80k::T, smem, st>>>(a);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    reduce_rows_kernel<<<a.n_active * a.D, 512, 0, st>>>(a.acc_rows, kN80k, a.D, a.rows, a.spc, a.cells);
+    return cudaGetLastError();
+}
+
+cudaError_t acq_cluster_launch_code_fft(const int8_t* codes, int n_prn, float2* code_fft, const float2* tw, const float2* otw,
+                                        cudaStream_t st)
+{
+    const size_t smem = cluster_smem();
+    cudaError_t e = cudaFuncSetAttribute(code_fft_cluster_kernel<PI80k>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    code_fft_cluster_kernel<PI80k><<<n_prn * kRO, PI80k::T, smem, st>>>(codes, code_fft, tw, otw);
+    return cudaGetLastError();
+}
+
+}  // namespace gb

@@ -7,73 +7,16 @@
 // entirely in shared memory / registers, then reduces the accumulated row to
 // {peak, first argmax, 8-lane sum, second peak} (:195-202, :229-234) -- 16 bytes to HBM per cell row.
 // The only HBM/L2 reads are the IQ chunk, the wipe-off table and the code spectrum.
-#include "acq_kernels.cuh"
-#include "fft_smem.cuh"
+#include "acq_common.cuh"
 
 #include <stdlib.h>
 
 namespace gb {
 
-// ------------------------------------------------------------------ plans
-//                 N      T  MINB PAD  radices (forward DIF order; odd radices last => no padding needed)
-using P1024 = Plan<1024, 64, 8, 4, 4, 16, 16>;
-using P2048 = Plan<2048, 128, 4, 4, 8, 16, 16>;
-using P4092 = Plan<4092, 160, 4, 0, 12, 11, 31>;
-using P4096 = Plan<4096, 256, 2, 4, 16, 16, 16>;
-using P8184 = Plan<8184, 288, 1, 0, 8, 3, 11, 31>;
-using P16368 = Plan<16368, 288, 1, 0, 16, 3, 11, 31>;
-using P20000 = Plan<20000, 512, 1, 0, 8, 4, 25, 25>;
-
-// tuning variants of the headline plan (selected with the environment variable GB_ACQ_VARIANT=1..4)
-using P4092v1 = Plan<4092, 192, 3, 0, 12, 11, 31>;
-using P4092v2 = Plan<4092, 160, 3, 0, 12, 11, 31>;
-using P4092v3 = Plan<4092, 192, 2, 0, 12, 11, 31>;
-using P4092v4 = Plan<4092, 384, 1, 0, 12, 11, 31>;
-
 #define GB_FOR_EACH_PLAN(X) X(0, P1024) X(1, P2048) X(2, P4092) X(3, P4096) X(4, P8184) X(5, P16368) X(6, P20000) \
     X(7, P4092v1) X(8, P4092v2) X(9, P4092v3) X(10, P4092v4)
 static const int kPlanSizes[] = {1024, 2048, 4092, 4096, 8184, 16368, 20000, -1, -1, -1, -1};
 static const int kNumPlans = sizeof(kPlanSizes) / sizeof(int);
-
-// reference arithmetic of multiply_simd_block (doppler_shift.rs:43-58): separate roundings, no FMA
-__device__ __forceinline__ float2 wipe(float2 x, float2 w)
-{
-    return make_float2(__fadd_rn(__fmul_rn(x.x, w.x), -__fmul_rn(x.y, w.y)),
-                       __fadd_rn(__fmul_rn(x.x, w.y), __fmul_rn(x.y, w.x)));
-}
-
-__device__ __forceinline__ float2 ld_iq(const AcqArgs& a, unsigned long long idx)
-{
-    return __ldg(&a.iq[(a.iq_start + idx) & a.iq_mask]);
-}
-
-struct PeakIdx {
-    float v;
-    unsigned idx;
-};
-// "first index of the strict maximum": larger value wins, ties go to the smaller index; NaN never wins
-__device__ __forceinline__ PeakIdx peak_merge(PeakIdx a, PeakIdx b)
-{
-    const bool take_b = (b.v > a.v) || (b.v == a.v && b.idx < a.idx);
-    return take_b ? b : a;
-}
-__device__ __forceinline__ PeakIdx warp_peak(PeakIdx p)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        PeakIdx q;
-        q.v = __shfl_xor_sync(0xffffffffu, p.v, o);
-        q.idx = __shfl_xor_sync(0xffffffffu, p.idx, o);
-        p = peak_merge(p, q);
-    }
-    return p;
-}
-__device__ __forceinline__ float warp_sum(float v)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
 
 // Stage 0 of the forward DIF (L = N) with the carrier wipe-off (and, for n_coh > 1, the coherent
 // pre-sum of n_coh rotated blocks) fused into the global-memory load.

@@ -23,6 +23,8 @@ struct AcqArgs {
     int d0;                  // Doppler bin for row_out
     float2* spec;            // shared-forward chain: n_d x n_groups x N scrambled spectra (scratch)
     int d_lo;                // shared-forward chain: first Doppler bin of this slab
+    const float2* otw;       // cluster plans: outer twiddles W_N^(i q), layout [q-1][i]
+    float* acc_rows;         // cluster plans: (n_active*D) x N accumulated power rows (scratch)
 };
 
 struct FftArgs {
@@ -49,5 +51,13 @@ cudaError_t acq_launch_code_fft(int plan, const int8_t* codes, int n_prn, float2
 cudaError_t acq_launch_fft(int plan, int inverse, const FftArgs& a, int batch, cudaStream_t st);
 // steps_dev[d] = 2*pi*(f_if+f_d)/fs (f32, host-evaluated in the reference's order)
 cudaError_t acq_launch_doppler_tables(const float* steps_dev, int D, int n, float2* tables, cudaStream_t st);
+
+// cluster plans (code period larger than one CTA's shared memory): radix-RO outer stage over a thread-block cluster
+int acq_cluster_supported(int n);
+int acq_cluster_inner(int n);   // inner plan length (has a regular plan)
+int acq_cluster_outer(int n);   // outer radix = cluster size
+cudaError_t acq_cluster_launch_search(const AcqArgs& a, cudaStream_t st);
+cudaError_t acq_cluster_launch_code_fft(const int8_t* codes, int n_prn, float2* code_fft, const float2* tw, const float2* otw,
+                                        cudaStream_t st);
 
 }  // namespace gb

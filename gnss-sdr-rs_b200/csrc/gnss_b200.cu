@@ -46,6 +46,11 @@ struct gb_handle {
     int plan = -1, N = 0, n_prn = 0, D = 0, n_coh = 1, spc = 0, mode = GB_ACQ_SHARED;
     float2* spec = nullptr;
     size_t spec_cap = 0;
+    // cluster plans (code period > one CTA's shared memory)
+    bool cluster = false;
+    float2* otw = nullptr;
+    float* acc_rows = nullptr;
+    size_t acc_cap = 0;
     float fs = 0.f, threshold = 7.0f;
     float2 *tw = nullptr, *code_fft = nullptr, *tables = nullptr, *rot = nullptr, *chunk = nullptr;
     int8_t* codes_dev = nullptr;
@@ -264,7 +269,7 @@ extern "C" int gb_destroy(gb_handle* h)
     if (!h) return GB_EINVAL;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
-    void* dev_ptrs[] = {h->spec, h->ring, h->i8_stage, h->tw, h->code_fft, h->tables, h->rot, h->chunk, h->codes_dev, h->cells_dev,
+    void* dev_ptrs[] = {h->otw, h->acc_rows, h->spec, h->ring, h->i8_stage, h->tw, h->code_fft, h->tables, h->rot, h->chunk, h->codes_dev, h->cells_dev,
                         h->rows_dev, h->row_dev, h->ca_table_dev, h->ch_dev, h->corr_dev, h->ran_dev, h->lost_dev,
                         h->hist_dev, h->trk_data, h->offs_dev};
     for (void* p : dev_ptrs)
@@ -409,14 +414,22 @@ extern "C" int gb_ring_copy_to_slice(gb_handle* h, uint64_t start, gb_c32* dest,
 }
 
 // ------------------------------------------------------------------ acquisition set-up
-extern "C" int gb_acq_supported_sizes(int* sizes, int cap) { return gb::acq_plan_sizes(sizes, cap); }
+extern "C" int gb_acq_supported_sizes(int* sizes, int cap)
+{
+    int n = gb::acq_plan_sizes(sizes, cap);
+    if (n < cap && sizes) sizes[n] = 80000;  // thread-block-cluster plan (acq_cluster.cu)
+    return n + 1;
+}
 
 extern "C" int gb_acq_configure(gb_handle* h, int fft_size, float fs, int n_prn, const int8_t* codes)
 {
     if (!h || n_prn < 1 || n_prn > 255 || !(fs > 0.f)) return GB_EINVAL;
     if (!codes && n_prn > 32) return GB_EINVAL;
     if (fft_size % 4 != 0) return GB_EUNSUPPORTED;  // apply_doppler_shift leaves len%4 samples stale (A3)
-    const int plan = gb::acq_plan_index(fft_size);
+    const bool cluster = gb::acq_cluster_supported(fft_size) != 0;
+    if (cluster && !codes) return GB_EINVAL;  // no built-in code has an 80000-sample period
+    const int inner = cluster ? gb::acq_cluster_inner(fft_size) : fft_size;
+    const int plan = gb::acq_plan_index(inner);
     if (plan < 0) return GB_EUNSUPPORTED;
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->s_acq));
@@ -433,8 +446,22 @@ extern "C" int gb_acq_configure(gb_handle* h, int fft_size, float fs, int n_prn,
         codes = host_codes.data();
     }
     FftRes* fr;
-    int rc = fft_resources(h, plan, fft_size, &fr);
+    int rc = fft_resources(h, plan, inner, &fr);
     if (rc) return rc;
+    if (cluster) {
+        // outer twiddles W_N^(i q), q = 1..RO-1, i < inner, layout [q-1][i], f64-evaluated
+        const int ro = gb::acq_cluster_outer(fft_size);
+        std::vector<float2> otw((size_t)(ro - 1) * inner);
+        for (int q = 1; q < ro; q++)
+            for (int i = 0; i < inner; i++) {
+                const double ang = -2.0 * M_PI * (double)(((long long)i * q) % fft_size) / (double)fft_size;
+                otw[(size_t)(q - 1) * inner + i] = make_float2((float)cos(ang), (float)sin(ang));
+            }
+        if (h->otw) cudaFree(h->otw);
+        h->otw = nullptr;
+        CK(cudaMalloc((void**)&h->otw, otw.size() * sizeof(float2)));
+        CK(cudaMemcpy(h->otw, otw.data(), otw.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    }
     if (h->code_fft) cudaFree(h->code_fft);
     if (h->codes_dev) cudaFree(h->codes_dev);
     if (h->row_dev) cudaFree(h->row_dev);
@@ -444,8 +471,10 @@ extern "C" int gb_acq_configure(gb_handle* h, int fft_size, float fs, int n_prn,
     CK(cudaMalloc((void**)&h->codes_dev, total));
     CK(cudaMalloc((void**)&h->row_dev, sizeof(float) * fft_size));
     CK(cudaMemcpyAsync(h->codes_dev, codes, total, cudaMemcpyHostToDevice, h->s_acq));
-    CK(gb::acq_launch_code_fft(plan, h->codes_dev, n_prn, h->code_fft, fr->tw, h->s_acq));
+    if (cluster) CK(gb::acq_cluster_launch_code_fft(h->codes_dev, n_prn, h->code_fft, fr->tw, h->otw, h->s_acq));
+    else CK(gb::acq_launch_code_fft(plan, h->codes_dev, n_prn, h->code_fft, fr->tw, h->s_acq));
     CK(cudaStreamSynchronize(h->s_acq));
+    h->cluster = cluster;
     h->plan = plan; h->N = fft_size; h->n_prn = n_prn; h->fs = fs; h->tw = fr->tw;
     h->D = 0; h->n_coh = 1;
     h->carr.clear();
@@ -581,7 +610,16 @@ static int search_cells(gb_handle* h, const float2* iq_dev, uint64_t start, uint
         a.rows = h->rows_dev;
         a.D = h->D; a.K = K; a.n_coh = h->n_coh; a.n_active = n_active; a.spc = h->spc;
         a.cells = h->cells_dev; a.row_out = nullptr; a.d0 = 0; a.spec = nullptr; a.d_lo = 0;
-        if (h->mode == GB_ACQ_SHARED) {
+        a.otw = h->otw; a.acc_rows = nullptr;
+        if (h->cluster) {
+            if (h->n_coh != 1) return GB_EUNSUPPORTED;
+            int rc = ensure(h, &h->acc_rows, &h->acc_cap, (size_t)n_active * h->D * h->N);
+            if (rc) return rc;
+            a.acc_rows = h->acc_rows;
+            CK(cudaEventRecord(h->ev_a0, h->s_acq));
+            CK(gb::acq_cluster_launch_search(a, h->s_acq));
+            CK(cudaEventRecord(h->ev_a1, h->s_acq));
+        } else if (h->mode == GB_ACQ_SHARED) {
             // scratch for the forward spectra, processed in Doppler slabs of at most 1 GiB
             const size_t per_d = (size_t)(K / h->n_coh) * h->N;
             size_t slab = ((size_t)1 << 27) / per_d;  // complex elements: 2^27 * 8 B = 1 GiB
@@ -746,6 +784,28 @@ extern "C" int gb_acq_bin_power(gb_handle* h, const gb_c32* iq, int K, int prn, 
     a.rows = h->rows_dev;
     a.D = h->D; a.K = K; a.n_coh = h->n_coh; a.n_active = 1; a.spc = 0;
     a.cells = nullptr; a.row_out = h->row_dev; a.d0 = doppler_bin; a.spec = nullptr; a.d_lo = 0;
+    a.otw = h->otw; a.acc_rows = nullptr;
+    if (h->cluster) {
+        // one (prn, bin) cell row: the cluster kernel leaves the accumulated power row in acc_rows
+        if (h->n_coh != 1) return GB_EUNSUPPORTED;
+        rc = ensure(h, &h->acc_rows, &h->acc_cap, (size_t)h->N);
+        if (rc) return rc;
+        const size_t need = (size_t)h->n_prn * h->D;
+        if (h->cells_cap < need) {
+            if (h->cells_dev) cudaFree(h->cells_dev);
+            if (h->cells_pin) cudaFreeHost(h->cells_pin);
+            h->cells_dev = nullptr; h->cells_pin = nullptr; h->cells_cap = 0;
+            CK(cudaMalloc((void**)&h->cells_dev, need * sizeof(gb_acq_cell)));
+            CK(cudaMallocHost((void**)&h->cells_pin, need * sizeof(gb_acq_cell)));
+            h->cells_cap = need;
+        }
+        a.tables = h->tables + (size_t)doppler_bin * h->N;
+        a.D = 1; a.acc_rows = h->acc_rows; a.cells = h->cells_dev;
+        CK(gb::acq_cluster_launch_search(a, h->s_acq));
+        CK(cudaMemcpyAsync(power_out, h->acc_rows, sizeof(float) * h->N, cudaMemcpyDeviceToHost, h->s_acq));
+        CK(cudaStreamSynchronize(h->s_acq));
+        return GB_OK;
+    }
     CK(gb::acq_launch_row(h->plan, a, h->s_acq));
     CK(cudaMemcpyAsync(power_out, h->row_dev, sizeof(float) * h->N, cudaMemcpyDeviceToHost, h->s_acq));
     CK(cudaStreamSynchronize(h->s_acq));

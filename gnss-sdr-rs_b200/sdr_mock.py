@@ -100,3 +100,67 @@ def reference_test_signal(code_samples, doppler, carrier_phase0, code_phase0, fs
     idx = np.floor(cur).astype(np.int64) % 1023
     cv = np.asarray(code_samples)[idx].astype(np.float32)
     return (cv * np.cos(cph).astype(np.float32) + 1j * (cv * np.sin(cph).astype(np.float32))).astype(np.complex64)
+
+
+# ---------------------------------------------------------------------------------------------
+# Other constellations (BASELINE configs 4-5).  NOTHING here comes from the reference (GPS L1 C/A only);
+# values are recalled from the public ICDs and cannot be verified offline.  They are
+# used consistently by the generator and the correlator, so they only affect synthetic self-consistency.
+_B1I_TAPS = [(1, 3), (1, 4), (1, 5), (1, 6), (1, 8), (1, 9), (1, 10), (1, 11), (2, 7), (3, 4), (3, 5), (3, 6), (3, 8),
+             (3, 9), (3, 10), (3, 11), (4, 5), (4, 6), (4, 8), (4, 9), (4, 10), (4, 11), (5, 6), (5, 8), (5, 9), (5, 10),
+             (5, 11), (6, 8), (6, 9), (6, 10), (6, 11), (8, 9), (8, 10), (8, 11), (9, 10), (9, 11), (10, 11)]
+
+
+def b1i_code(prn):
+    """BeiDou B1I ranging code: 2046 chips of the truncated 11-stage Gold sequence, +1 for bit 1.
+    G1 = x^11+x^10+x^9+x^8+x^7+x+1, G2 = x^11+x^9+x^8+x^5+x^4+x^3+x^2+x+1, both initialised 01010101010."""
+    g1 = [0, 1, 0, 1, 0, 1, 0, 1, 0, 1, 0]
+    g2 = list(g1)
+    a, b = _B1I_TAPS[prn - 1]
+    out = np.empty(2046, np.int8)
+    for c in range(2046):
+        out[c] = 1 if (g1[10] ^ g2[a - 1] ^ g2[b - 1]) else -1
+        f1 = g1[0] ^ g1[6] ^ g1[7] ^ g1[8] ^ g1[9] ^ g1[10]
+        f2 = g2[0] ^ g2[1] ^ g2[2] ^ g2[3] ^ g2[4] ^ g2[7] ^ g2[8] ^ g2[10]
+        g1 = [f1] + g1[:10]
+        g2 = [f2] + g2[:10]
+    return out
+
+
+def e1_surrogate_code(prn, seed=0xE1C0DE):
+    """Galileo E1 primary codes are ICD memory codes (not LFSR-generable, not available offline): a clearly
+    labelled deterministic SURROGATE of 4092 +-1 chips per PRN from a seeded PRNG."""
+    rng = np.random.default_rng(seed + 7919 * prn)
+    return (rng.integers(0, 2, 4092) * 2 - 1).astype(np.int8)
+
+
+def resample_code(chips, chip_rate, fs, n_samples, boc11=False):
+    """Code samples at fs over n_samples (one code period): chip index = floor(x * chip_rate / fs) (the f32 index
+    arithmetic of ca_code.rs:18-22), optionally times the BOC(1,1) sub-carrier sign(sin(2 pi chip_phase))."""
+    x = np.arange(n_samples, dtype=np.float32)
+    ph = (x * np.float32(chip_rate)) / np.float32(fs)
+    idx = np.floor(ph).astype(np.int64) % len(chips)
+    s = np.asarray(chips)[idx].astype(np.int8)
+    if boc11:
+        s = s * np.where((ph - np.floor(ph)) < 0.5, 1, -1).astype(np.int8)
+    return s
+
+
+def multi_gnss(fs, n_ms, sats, seed=0x6E58, noise_sigma=1.0):
+    """Complex baseband with GPS L1 C/A ('G'), BeiDou B1I ('C') and Galileo-E1-like BOC(1,1) ('E') signals.
+    sats: dicts {system, prn, doppler, code_phase (samples), cn0_dbhz}."""
+    n = int(round(fs / 1000.0)) * n_ms
+    rng = np.random.default_rng(seed)
+    x = (rng.standard_normal(n) + 1j * rng.standard_normal(n)) * (noise_sigma / np.sqrt(2.0))
+    t = np.arange(n, dtype=np.float64)
+    for s in sats:
+        sysname = s["system"]
+        chips, rate = {"G": (ca_code(s["prn"]), 1.023e6), "C": (b1i_code(s["prn"]), 2.046e6),
+                       "E": (e1_surrogate_code(s["prn"]), 1.023e6)}[sysname]
+        ph = ((t - s["code_phase"]) * rate / fs) % len(chips)
+        sig = chips[np.floor(ph).astype(np.int64) % len(chips)].astype(np.float64)
+        if sysname == "E":
+            sig = sig * np.where((ph - np.floor(ph)) < 0.5, 1.0, -1.0)
+        amp = noise_sigma * np.sqrt(10.0 ** (s["cn0_dbhz"] / 10.0) / fs)
+        x += amp * sig * np.exp(1j * (2.0 * np.pi * ((s["doppler"] * t / fs) % 1.0) + rng.uniform(0, 2 * np.pi)))
+    return x.astype(np.complex64)
