@@ -51,7 +51,7 @@ __device__ __forceinline__ void inner_chain(float2* __restrict__ line, const flo
     constexpr int LASTS = PI::NSTAGE - 1;
     using GM = StageGeo<PI, LASTS>;
     DifRange<PI, 0, LASTS, false>::run(line, tw);
-#pragma unroll
+#pragma unroll 1
     for (int it = 0; it < GM::ITERS; it++) {
         const int b = threadIdx.x + it * PI::T;
         if (GM::NB % PI::T == 0 || b < GM::NB) {
@@ -126,7 +126,7 @@ template <class PI> __global__ void __launch_bounds__(PI::T, 1) code_fft_cluster
     outer_forward<PI>(r, otw, line, [&](int n) { return make_float2((float)c[n], 0.f); });
     __syncthreads();
     DifRange<PI, 0, LASTS, false>::run(line, tw);
-#pragma unroll
+#pragma unroll 1
     for (int it = 0; it < GM::ITERS; it++) {
         const int b = threadIdx.x + it * PI::T;
         if (GM::NB % PI::T == 0 || b < GM::NB) {

@@ -14,8 +14,8 @@
 namespace gb {
 
 #define GB_FOR_EACH_PLAN(X) X(0, P1024) X(1, P2048) X(2, P4092) X(3, P4096) X(4, P8184) X(5, P16368) X(6, P20000) \
-    X(7, P4092v1) X(8, P4092v2) X(9, P4092v3) X(10, P4092v4)
-static const int kPlanSizes[] = {1024, 2048, 4092, 4096, 8184, 16368, 20000, -1, -1, -1, -1};
+    X(7, P4092v1) X(8, P4092v2) X(9, P4092v3) X(10, P4092v4) X(11, P16368v1) X(12, P16368v2)
+static const int kPlanSizes[] = {1024, 2048, 4092, 4096, 8184, 16368, 20000, -1, -1, -1, -1, -1, -1};
 static const int kNumPlans = sizeof(kPlanSizes) / sizeof(int);
 
 // Stage 0 of the forward DIF (L = N) with the carrier wipe-off (and, for n_coh > 1, the coherent
@@ -209,7 +209,7 @@ template <class P, bool WANT_ROW> __global__ void __launch_bounds__(P::T, P::MIN
         DifRange<P, 1, LASTS, false>::run(line, tw);
 
         // ---- last forward stage + x conj(code) + first inverse stage, in registers
-#pragma unroll
+#pragma unroll 1
         for (int it = 0; it < GM::ITERS; it++) {
             const int b = threadIdx.x + it * P::T;
             if (GM::NB % P::T == 0 || b < GM::NB) {
@@ -265,7 +265,7 @@ template <class P> __global__ void __launch_bounds__(P::T, P::MINB) acq_forward_
     stage0_wipe_forward<P>(a, w, rot, a.n_coh, g, line, a.tw);
     __syncthreads();
     DifRange<P, 1, LASTS, false>::run(line, a.tw);
-#pragma unroll
+#pragma unroll 1
     for (int it = 0; it < GM::ITERS; it++) {
         const int b = threadIdx.x + it * P::T;
         if (GM::NB % P::T == 0 || b < GM::NB) {
@@ -300,7 +300,7 @@ template <class P> __global__ void __launch_bounds__(P::T, P::MINB) acq_inverse_
 
     for (int g = 0; g < n_groups; g++) {
         const float2* __restrict__ sg = spec + (size_t)g * N;
-#pragma unroll
+#pragma unroll 1
         for (int it = 0; it < GM::ITERS; it++) {
             const int b = threadIdx.x + it * P::T;
             if (GM::NB % P::T == 0 || b < GM::NB) {
@@ -346,7 +346,7 @@ template <class P> __global__ void __launch_bounds__(P::T) code_fft_kernel(const
     }
     __syncthreads();
     DifRange<P, 1, LASTS, false>::run(line, tw);
-#pragma unroll
+#pragma unroll 1
     for (int it = 0; it < GM::ITERS; it++) {
         const int b = threadIdx.x + it * P::T;
         if (GM::NB % P::T == 0 || b < GM::NB) {
@@ -393,7 +393,7 @@ template <class P, bool INV> __global__ void __launch_bounds__(P::T) fft_c2c_ker
     __syncthreads();
     DifRange<P, 1, LASTS, INV>::run(line, tw);
     const size_t ooff = (size_t)blockIdx.x * a.n_out;
-#pragma unroll
+#pragma unroll 1
     for (int it = 0; it < GM::ITERS; it++) {
         const int b = threadIdx.x + it * P::T;
         if (GM::NB % P::T == 0 || b < GM::NB) {
@@ -432,6 +432,10 @@ int acq_plan_index(int n)
     if (n == 4092) {
         const char* v = getenv("GB_ACQ_VARIANT");
         if (v && v[0] >= '1' && v[0] <= '4' && !v[1]) return 6 + (v[0] - '0');
+    }
+    if (n == 16368) {
+        const char* v = getenv("GB_ACQ_VARIANT");
+        if (v && v[0] >= '1' && v[0] <= '2' && !v[1]) return 10 + (v[0] - '0');
     }
     for (int i = 0; i < kNumPlans; i++)
         if (kPlanSizes[i] == n) return i;

@@ -297,7 +297,7 @@ template <class P> constexpr int plan_twiddle_count() { return StageGeo<P, P::NS
 template <class P, int S, bool INV> __device__ __forceinline__ void dif_stage(float2* __restrict__ s, const float2* __restrict__ tw)
 {
     using G = StageGeo<P, S>;
-#pragma unroll
+#pragma unroll 1
     for (int it = 0; it < G::ITERS; it++) {
         const int b = threadIdx.x + it * P::T;
         if (G::NB % P::T == 0 || b < G::NB) {
@@ -325,7 +325,7 @@ template <class P, int S, bool INV> __device__ __forceinline__ void dif_stage(fl
 template <class P, int S, bool INV> __device__ __forceinline__ void dit_stage(float2* __restrict__ s, const float2* __restrict__ tw)
 {
     using G = StageGeo<P, S>;
-#pragma unroll
+#pragma unroll 1
     for (int it = 0; it < G::ITERS; it++) {
         const int b = threadIdx.x + it * P::T;
         if (G::NB % P::T == 0 || b < G::NB) {

@@ -1,0 +1,37 @@
+#!/usr/bin/env python3
+"""Breaks the end-to-end acquisition call down: H2D bandwidth, ring-resident search, host-buffer search."""
+import os, sys, time
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+import bench
+import gnss_sdr_rs_b200._ffi as ffi
+from gnss_sdr_rs_b200 import acquisition, ring
+
+hd = ffi.Handle(0)
+x = bench.make_recording(1)
+x_pin = torch.from_numpy(x.view(np.float32).copy()).pin_memory()
+dev = torch.empty_like(x_pin, device="cuda")
+for _ in range(3):
+    dev.copy_(x_pin, non_blocking=True); torch.cuda.synchronize()
+t0 = time.perf_counter()
+for _ in range(20):
+    dev.copy_(x_pin, non_blocking=True); torch.cuda.synchronize()
+dt = (time.perf_counter() - t0) / 20
+print("torch pinned H2D %.3f ms for %.1f MB = %.1f GB/s" % (dt * 1e3, x.nbytes / 1e6, x.nbytes / dt / 1e9))
+rb = ring.MulticastRingBuffer(hd, 1 << 20)
+rb.write_samples(x)
+eng = acquisition.AcquisitionEngine(hd, bench.N_FFT, bench.FS, 32)
+eng.make_doppler_tables(0.0, bench.DOPPLERS)
+eng.set_coherent(bench.N_COH)
+def timeit(f, n=20):
+    for _ in range(3): f()
+    t0 = time.perf_counter()
+    for _ in range(n): f()
+    return (time.perf_counter() - t0) / n * 1e3
+print("search_ring (results)      %.3f ms wall, kernel %.3f" % (timeit(lambda: eng.search_ring(0, bench.K_MS)), eng.last_kernel_ms()))
+print("search pinned host         %.3f ms wall, kernel %.3f" % (timeit(lambda: eng.search(x_pin.data_ptr(), bench.K_MS)), eng.last_kernel_ms()))
+print("search pageable host       %.3f ms wall, kernel %.3f" % (timeit(lambda: eng.search(x, bench.K_MS)), eng.last_kernel_ms()))
+print("search_cells_ring no cells %.3f ms wall" % timeit(lambda: eng.search_cells_ring(0, bench.K_MS, want_cells=False)))
+hd.close()
