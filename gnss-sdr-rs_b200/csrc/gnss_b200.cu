@@ -42,6 +42,14 @@ struct gb_handle {
     cudaEvent_t pin_free[2] = {nullptr, nullptr};
     int pin_next = 0;
 
+    // digital front-end (rf/frontend.rs): LUT + persistent NCO / DC-bias state on the device
+    float* fe_lut = nullptr;     // 2 x 2048 floats (re, im)
+    float* fe_state = nullptr;   // phase_accumulator, bias_re[8], bias_im[8]
+    float2* fe_stage = nullptr;
+    size_t fe_cap = 0;
+    float fe_step = 0.f;
+    bool fe_ready = false;
+
     // acquisition
     int plan = -1, N = 0, n_prn = 0, D = 0, n_coh = 1, spc = 0, mode = GB_ACQ_SHARED;
     float2* spec = nullptr;
@@ -194,6 +202,61 @@ __global__ void fp32_peak_kernel(float* out, float a, float b)
     if (s == 12345.678f) out[0] = s;
 }
 
+// DigitalFrontend::process_block (rf/frontend.rs:32-62) + write into the ring.  One CTA; per 2048-sample tile:
+// thread 0 runs the sequential f32 NCO phase accumulator (:48-52), 16 lanes of warp 1 run the 8+8 independent DC-bias
+// recurrences (rf/dc_remove.rs:23-29: lane j sees samples 8c+j), then all threads do the LUT mix (rf/nco_lut.rs:8-15,
+// verbatim: i' = I*re + Q*im, q' = I*im - Q*re with im = -sin) and store.  All roundings as in the reference.
+#define FE_TILE 2048
+__global__ void __launch_bounds__(256) frontend_kernel(const float2* __restrict__ src, float2* __restrict__ ring,
+                                                      unsigned long long head, unsigned long long mask, unsigned long long n,
+                                                      const float* __restrict__ lut, float* __restrict__ state, float step,
+                                                      float alpha, float con)
+{
+    __shared__ float2 tile[FE_TILE];
+    __shared__ unsigned short idx[FE_TILE];
+    __shared__ float s_acc;
+    __shared__ float s_bias[16];
+    if (threadIdx.x == 0) s_acc = state[0];
+    if (threadIdx.x < 16) s_bias[threadIdx.x] = state[1 + threadIdx.x];
+    __syncthreads();
+    for (unsigned long long t0 = 0; t0 < n; t0 += FE_TILE) {
+        const int tn = (int)((n - t0) < FE_TILE ? (n - t0) : FE_TILE);
+        for (int i = threadIdx.x; i < tn; i += blockDim.x) tile[i] = src[t0 + i];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float acc = s_acc;
+            for (int i = 0; i < tn; i++) {
+                idx[i] = (unsigned short)((acc > 0.f ? (unsigned)acc : 0u) & 2047u);  // `as usize % LUT_SIZE`
+                const float s = __fadd_rn(acc, step);
+                acc = (s >= 0.f && s < 4096.f) ? (s >= 2048.f ? s - 2048.f : s) : fmodf(s, 2048.f);
+            }
+            s_acc = acc;
+        } else if (threadIdx.x >= 32 && threadIdx.x < 48) {
+            const int l = threadIdx.x - 32, lane = l & 7, comp = l >> 3;
+            float b = s_bias[l];
+            float* t = reinterpret_cast<float*>(tile) + comp;
+            for (int cidx = lane; cidx < tn; cidx += 8) {
+                const float x = t[2 * cidx];
+                b = __fadd_rn(__fmul_rn(b, con), __fmul_rn(x, alpha));
+                t[2 * cidx] = __fsub_rn(x, b);
+            }
+            s_bias[l] = b;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < tn; i += blockDim.x) {
+            const float2 x = tile[i];
+            const float lc = lut[idx[i]], ls = lut[2048 + idx[i]];
+            float2 y;
+            y.x = __fadd_rn(__fmul_rn(x.x, lc), __fmul_rn(x.y, ls));
+            y.y = __fsub_rn(__fmul_rn(x.x, ls), __fmul_rn(x.y, lc));
+            ring[(head + t0 + i) & mask] = y;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) state[0] = s_acc;
+    if (threadIdx.x < 16) state[1 + threadIdx.x] = s_bias[threadIdx.x];
+}
+
 __global__ void i8_to_ring_kernel(const int8_t* __restrict__ src, float2* __restrict__ ring, unsigned long long start,
                                   unsigned long long mask, unsigned long long n)
 {
@@ -269,7 +332,7 @@ extern "C" int gb_destroy(gb_handle* h)
     if (!h) return GB_EINVAL;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
-    void* dev_ptrs[] = {h->otw, h->acc_rows, h->spec, h->ring, h->i8_stage, h->tw, h->code_fft, h->tables, h->rot, h->chunk, h->codes_dev, h->cells_dev,
+    void* dev_ptrs[] = {h->fe_lut, h->fe_state, h->fe_stage, h->otw, h->acc_rows, h->spec, h->ring, h->i8_stage, h->tw, h->code_fft, h->tables, h->rot, h->chunk, h->codes_dev, h->cells_dev,
                         h->rows_dev, h->row_dev, h->ca_table_dev, h->ch_dev, h->corr_dev, h->ran_dev, h->lost_dev,
                         h->hist_dev, h->trk_data, h->offs_dev};
     for (void* p : dev_ptrs)
@@ -398,6 +461,56 @@ extern "C" int gb_ring_write_i8(gb_handle* h, const int8_t* samples, uint64_t n)
     h->ring_head += n;
     return GB_OK;
 }
+// DigitalFrontend::new (rf/frontend.rs:18-30): NCO LUT (host libm, rf/nco_lut.rs:24-42), alpha = 0.001, zero state
+extern "C" int gb_frontend_configure(gb_handle* h, float f_if, float fs_in)
+{
+    if (!h || !(fs_in > 0.f)) return GB_EINVAL;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->s_copy));
+    std::vector<float> lut(4096);
+    for (int i = 0; i < 2048; i++) {
+        const float angle = (2.0f * kPiF * (float)i) / 2048.0f;
+        lut[i] = cosf(angle);
+        lut[2048 + i] = -sinf(angle);
+    }
+    if (!h->fe_lut) CK(cudaMalloc((void**)&h->fe_lut, sizeof(float) * 4096));
+    if (!h->fe_state) CK(cudaMalloc((void**)&h->fe_state, sizeof(float) * 17));
+    CK(cudaMemcpy(h->fe_lut, lut.data(), sizeof(float) * 4096, cudaMemcpyHostToDevice));
+    CK(cudaMemset(h->fe_state, 0, sizeof(float) * 17));
+    h->fe_step = (f_if / fs_in) * 2048.0f;  // nco_lut.rs:34
+    h->fe_ready = true;
+    return GB_OK;
+}
+
+// rf_thread's per-block work (rf/rf_thread.rs:44-48): front-end on n raw complex samples, result appended to the ring
+extern "C" int gb_frontend_write(gb_handle* h, const gb_c32* raw, uint64_t n)
+{
+    if (!h || !h->ring || !h->fe_ready) return GB_ESTATE;
+    if (!raw || n == 0 || n > h->ring_cap || (n % 8) != 0) return GB_EINVAL;  // chunks_exact_mut(16 floats)
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->s_copy));  // the staging buffer is reused
+    int rc = ensure(h, &h->fe_stage, &h->fe_cap, (size_t)n);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(h->fe_stage, raw, n * sizeof(float2), cudaMemcpyHostToDevice, h->s_copy));
+    frontend_kernel<<<1, 256, 0, h->s_copy>>>(h->fe_stage, h->ring, h->ring_head, h->ring_cap - 1, n, h->fe_lut, h->fe_state,
+                                               h->fe_step, 0.001f, 1.0f - 0.001f);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(h->ev_copy, h->s_copy));
+    h->ring_head += n;
+    return GB_OK;
+}
+
+// phase_accumulator, bias_re[8], bias_im[8] (diagnostics / tests)
+extern "C" int gb_frontend_state(gb_handle* h, float* state17)
+{
+    if (!h || !state17) return GB_EINVAL;
+    if (!h->fe_ready) return GB_ESTATE;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->s_copy));
+    CK(cudaMemcpy(state17, h->fe_state, sizeof(float) * 17, cudaMemcpyDeviceToHost));
+    return GB_OK;
+}
+
 extern "C" uint64_t gb_ring_head(gb_handle* h) { return h ? h->ring_head : 0; }
 // copy_to_slice (multicast_ring_buffer.rs:107-129)
 extern "C" int gb_ring_copy_to_slice(gb_handle* h, uint64_t start, gb_c32* dest, uint64_t n)

@@ -30,3 +30,20 @@ class MulticastRingBuffer:
 
     def reset(self):
         self.hd.call("gb_ring_reset")
+
+
+class DigitalFrontend:
+    """rf/frontend.rs:6-62 over the device ring: process_block + write_samples in one call."""
+
+    def __init__(self, handle, f_if, fs_in, fs_out=None):
+        self.hd = handle
+        handle.call("gb_frontend_configure", float(f_if), float(fs_in))
+
+    def process_block_into_ring(self, raw):
+        x = np.ascontiguousarray(raw, np.complex64)
+        self.hd.call("gb_frontend_write", _ffi.ptr(x), x.size)
+
+    def state(self):
+        s = np.zeros(17, np.float32)
+        self.hd.call("gb_frontend_state", _ffi.ptr(s))
+        return {"phase_accumulator": float(s[0]), "bias_re": s[1:9].copy(), "bias_im": s[9:17].copy()}

@@ -76,6 +76,16 @@ uint64_t gb_ring_head(gb_handle *h);
 int gb_ring_copy_to_slice(gb_handle *h, uint64_t start, gb_c32 *dest, uint64_t n);
 int gb_ring_reset(gb_handle *h);
 
+/* ------------------------------------------------------------------ digital front-end
+ * replaces DigitalFrontend::{new, process_block} (rf/frontend.rs:18-62), DcRemoverSimd (rf/dc_remove.rs:11-29),
+ * NcoLut / mix_simd (rf/nco_lut.rs:8-42) and the per-block body of rf_thread (rf/rf_thread.rs:44-48): raw complex
+ * samples -> DC removal (alpha 0.001, 8 interleaved lanes) -> 2048-entry NCO LUT mix -> appended to the ring.
+ * Bit-exact with the reference arithmetic (sequential f32 phase accumulator and bias recurrences included).
+ * n must be a multiple of 8 (the reference processes 16 floats at a time). */
+int gb_frontend_configure(gb_handle *h, float f_if, float fs_in);
+int gb_frontend_write(gb_handle *h, const gb_c32 *raw, uint64_t n);
+int gb_frontend_state(gb_handle *h, float *state17 /* phase_accumulator, bias_re[8], bias_im[8] */);
+
 /* ------------------------------------------------------------------ acquisition
  * replaces AcquisitionWorker::{new, search_satellite, is_good_satellite}
  * (do_acquisition.rs:118-239) for ALL PRNs at once (the rayon loop at :302-313),

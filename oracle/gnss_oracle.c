@@ -731,3 +731,40 @@ void go_trk_run_all(go_trk_channel *ch, int n_channels, const go_c32 *stream, si
     run_threads(trk_thread, &j, n_threads);
     pthread_mutex_destroy(&j.mu);
 }
+
+/* ------------------------------------------------------------------ digital front-end */
+/* rf/nco_lut.rs:24-42 + rf/dc_remove.rs:11-21 + rf/frontend.rs:18-30 */
+void go_frontend_init(go_frontend *f, float f_if, float fs_in)
+{
+    memset(f, 0, sizeof(*f));
+    for (int i = 0; i < GO_LUT_SIZE; i++) {
+        const float angle = (2.0f * GO_PI_F * (float)i) / (float)GO_LUT_SIZE;
+        f->lut_re[i] = cosf(angle);
+        f->lut_im[i] = -sinf(angle);
+    }
+    f->phase_step = (f_if / fs_in) * (float)GO_LUT_SIZE;
+    f->alpha = 0.001f;
+    f->con = 1.0f - f->alpha;
+}
+
+/* rf/frontend.rs:32-62: 8 complex samples per step; 8 independent DC-bias lanes; sequential f32 phase
+ * accumulator; mix_simd (nco_lut.rs:8-15) verbatim: i' = I*re + Q*im, q' = I*im - Q*re with im = -sin. */
+void go_frontend_process_block(go_frontend *f, go_c32 *s, size_t n)
+{
+    for (size_t c = 0; c + 8 <= n; c += 8) {
+        float re[8], im[8];
+        for (int j = 0; j < 8; j++) {
+            f->bias_re[j] = f->bias_re[j] * f->con + s[c + j].re * f->alpha;
+            f->bias_im[j] = f->bias_im[j] * f->con + s[c + j].im * f->alpha;
+            re[j] = s[c + j].re - f->bias_re[j];
+            im[j] = s[c + j].im - f->bias_im[j];
+        }
+        for (int j = 0; j < 8; j++) {
+            const size_t idx = f32_as_usize(f->phase_accumulator) % GO_LUT_SIZE;
+            f->phase_accumulator = fmodf(f->phase_accumulator + f->phase_step, (float)GO_LUT_SIZE);
+            const float lc = f->lut_re[idx], ls = f->lut_im[idx];
+            s[c + j].re = re[j] * lc + im[j] * ls;
+            s[c + j].im = re[j] * ls - im[j] * lc;
+        }
+    }
+}

@@ -184,6 +184,18 @@ int go_trk_update(go_trk_channel *c, const go_ring *ring, go_c32 *scratch, float
 void go_trk_run_all(go_trk_channel *ch, int n_channels, const go_c32 *stream, size_t stream_len, int n_epochs,
                     int n_threads, float *hist);
 
+/* ---- digital front-end: rf/frontend.rs:32-62, rf/dc_remove.rs:23-29, rf/nco_lut.rs:24-42 ---- */
+#define GO_LUT_SIZE 2048
+typedef struct {
+    float lut_re[GO_LUT_SIZE], lut_im[GO_LUT_SIZE];
+    float phase_accumulator, phase_step;
+    float bias_re[8], bias_im[8];
+    float alpha, con;
+} go_frontend;
+void go_frontend_init(go_frontend *f, float f_if, float fs_in);
+/* in place on n complex samples; processes floor(n/8)*8 samples, the tail is left untouched (chunks_exact_mut(16)) */
+void go_frontend_process_block(go_frontend *f, go_c32 *samples, size_t n);
+
 #ifdef __cplusplus
 }
 #endif

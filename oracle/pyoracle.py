@@ -42,6 +42,12 @@ class Ring(C.Structure):
     _fields_ = [("buffer", C.c_void_p), ("buf_size", C.c_size_t), ("mask", C.c_size_t), ("head", C.c_size_t)]
 
 
+class Frontend(C.Structure):
+    _fields_ = [("lut_re", C.c_float * 2048), ("lut_im", C.c_float * 2048), ("phase_accumulator", C.c_float),
+                ("phase_step", C.c_float), ("bias_re", C.c_float * 8), ("bias_im", C.c_float * 8),
+                ("alpha", C.c_float), ("con", C.c_float)]
+
+
 class AcqManager(C.Structure):
     _fields_ = [("mode", C.c_int)]
 
@@ -95,6 +101,8 @@ def lib():
         "go_ring_head": (sz, [vp]), "go_ring_copy_to_slice": (None, [vp, sz, vp, sz]),
         "go_trk_update": (i32, [vp, vp, vp, vp, vp, vp]),
         "go_trk_run_all": (None, [vp, i32, vp, sz, i32, i32, vp]),
+        "go_frontend_init": (None, [vp, f32, f32]),
+        "go_frontend_process_block": (None, [vp, vp, sz]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -299,3 +307,15 @@ def trk_run_all(channels, stream, n_epochs, n_threads=None, want_hist=True):
     lib().go_trk_run_all(channels, n, _p(stream), len(stream), n_epochs, n_threads or os.cpu_count(),
                          _p(hist) if want_hist else None)
     return hist
+
+
+def frontend(f_if, fs_in):
+    f = Frontend()
+    lib().go_frontend_init(C.byref(f), f_if, fs_in)
+    return f
+
+
+def frontend_process(f, samples):
+    x = np.ascontiguousarray(samples, c32).copy()
+    lib().go_frontend_process_block(C.byref(f), _p(x), len(x))
+    return x

@@ -70,3 +70,31 @@ def test_fft_facade(gpu, n):
     rf = acquisition.RealFFT(gpu, n)
     ref_r = np.fft.rfft(r.astype(np.float64))
     assert np.abs(rf.execute(r) - ref_r).max() / np.abs(ref_r).max() < 5e-7
+
+
+def test_digital_frontend_bit_exact(gpu, oracle):
+    """rf/frontend.rs process_block restated -- DC removal + NCO LUT mix, bit-exact incl. the sequential
+    f32 phase accumulator, across several rf_thread-sized blocks (2048) and one odd-sized write."""
+    from gnss_sdr_rs_b200 import ring
+    f_if, fs = 4130400.0, 16367600.0
+    rng = np.random.default_rng(3)
+    raw = ((rng.standard_normal(5 * 2048 + 1000) * 20 + 3.0) + 1j * (rng.standard_normal(5 * 2048 + 1000) * 20 - 2.0)).astype(np.complex64)
+    rb = ring.MulticastRingBuffer(gpu, 1 << 15)
+    fe = ring.DigitalFrontend(gpu, f_if, fs)
+    of = oracle.frontend(f_if, fs)
+    ref = []
+    pos = 0
+    for blk in (2048, 2048, 2048, 1000, 2048, 2048):
+        fe.process_block_into_ring(raw[pos:pos + blk])
+        ref.append(oracle.frontend_process(of, raw[pos:pos + blk]))
+        pos += blk
+    ref = np.concatenate(ref)
+    got = rb.copy_to_slice(0, pos)
+    assert rb.get_head() == pos
+    assert got.tobytes() == ref.tobytes()
+    st = fe.state()
+    assert st["phase_accumulator"] == of.phase_accumulator
+    assert (st["bias_re"] == np.array(of.bias_re[:], np.float32)).all() and (st["bias_im"] == np.array(of.bias_im[:], np.float32)).all()
+    import gnss_sdr_rs_b200._ffi as ffi
+    with pytest.raises(ffi.GnssB200Error):
+        fe.process_block_into_ring(raw[:13])  # not a multiple of 8

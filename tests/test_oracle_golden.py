@@ -294,3 +294,36 @@ def test_tracking_closed_loop_pull_in(oracle):
     assert chs[0].state == 1 and abs(chs[0].carrier_freq - 1000.0) < 5.0
     p = np.hypot(hist[100:, 0, 0], hist[100:, 0, 1])
     assert p.min() > 4.0  # prompt power stays far above LOCK_THRESHOLD = 15 (do_tracking.rs:741)
+
+
+def test_digital_frontend_against_numpy(oracle):
+    """rf/frontend.rs:32-62 / dc_remove.rs:23-29 / nco_lut.rs:8-42 restated independently in NumPy f32."""
+    f_if, fs = np.float32(4130400.0), np.float32(16367600.0)
+    f = oracle.frontend(f_if, fs)
+    i = np.arange(2048, dtype=np.float32)
+    ang = (np.float32(2.0) * np.float32(np.pi) * i) / np.float32(2048.0)
+    assert np.abs(np.array(f.lut_re[:]) - np.cos(ang.astype(np.float64))).max() < 1e-7
+    assert np.abs(np.array(f.lut_im[:]) + np.sin(ang.astype(np.float64))).max() < 1e-7
+    assert f.phase_step == (f_if / fs) * np.float32(2048.0) and f.alpha == np.float32(0.001)
+    rng = np.random.default_rng(0)
+    x = ((rng.standard_normal(4096 + 5) + 0.5) + 1j * (rng.standard_normal(4096 + 5) - 0.25)).astype(np.complex64)
+    y = oracle.frontend_process(f, x)
+    # independent restatement
+    lut_re, lut_im = np.array(f.lut_re[:], np.float32), np.array(f.lut_im[:], np.float32)
+    alpha, con = np.float32(0.001), np.float32(1.0) - np.float32(0.001)
+    bre, bim = np.zeros(8, np.float32), np.zeros(8, np.float32)
+    acc, step = np.float32(0.0), f.phase_step
+    out = x.copy()
+    for c in range(0, (len(x) // 8) * 8, 8):
+        re, im = x.real[c:c + 8].copy(), x.imag[c:c + 8].copy()
+        bre = bre * con + re * alpha
+        bim = bim * con + im * alpha
+        re, im = re - bre, im - bim
+        for j in range(8):
+            k = int(acc) % 2048
+            acc = np.float32(np.fmod(np.float32(acc + step), np.float32(2048.0)))
+            out[c + j] = complex(np.float32(re[j] * lut_re[k]) + np.float32(im[j] * lut_im[k]),
+                                 np.float32(re[j] * lut_im[k]) - np.float32(im[j] * lut_re[k]))
+    assert y.tobytes() == out.astype(np.complex64).tobytes()
+    assert (y[-5:] == x[-5:]).all()  # chunks_exact_mut(16 floats): the tail is left raw
+    assert f.phase_accumulator == acc
