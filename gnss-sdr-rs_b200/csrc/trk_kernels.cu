@@ -110,10 +110,12 @@ template <int MODE, int TRK_T> __global__ void __launch_bounds__(TRK_T) trk_kern
             const float inv_2pi = 0.15915494309189535f;
             const float c1 = 6.28318548202514648f;        // fl(2 pi)
             const float c2 = -1.74845553146951715e-7f;    // 2 pi - fl(2 pi)
-#pragma unroll 4
-            for (int i = threadIdx.x; i < n; i += TRK_T) {
-                const float2 x = __ldg(&a.samples[(start + (unsigned long long)i) & a.mask]);
-                const float fi = (float)i;
+            // Per-sample body.  `sane` (checked once per epoch, uniform) says that every chip argument of the epoch
+            // lies in [0, 3*1023): then `% 1023` is at most two exact subtractions and the E/P/L indices need no
+            // range checks, so the loop is branch-free.
+            const bool sane = code_phase >= 0.f && code_phase < 1023.f && code_step >= 0.f &&
+                              code_step * (float)n < 2040.f;
+            auto body = [&](const float2 x, const float fi) {
                 const float t = w * fi;
                 const float q0 = t * rcp_fs;
                 const float q = fmaf(fmaf(-q0, fs, t), rcp_fs, q0);      // (w * i) / fs
@@ -124,21 +126,34 @@ template <int MODE, int TRK_T> __global__ void __launch_bounds__(TRK_T) trk_kern
                 const float re = fmaf(x.x, cs, x.y * sn);               // x * (cos, -sin)
                 const float im = fmaf(x.y, cs, -(x.x * sn));
                 float tc = code_phase + (fi * code_step);
-                if (!(tc >= 0.f && tc < 2046.f)) tc = fmodf(tc, 1023.f);
-                else if (tc >= 1023.f) tc -= 1023.f;
                 float pc, ec, lc;
-                if (tc >= 0.f) {                                          // always, unless the NCO diverged
+                if (sane) {
+                    tc = tc >= 1023.f ? tc - 1023.f : tc;                 // exact (Sterbenz), == fmodf
+                    tc = tc >= 1023.f ? tc - 1023.f : tc;
                     const int ipx = (int)tc;                              // tc in [0, 1023): trunc == floor
                     int iex = (int)(tc + 0.5f);
-                    iex = iex >= 1023 ? iex - 1023 : iex;
+                    iex = iex >= 1023 ? iex - 1023 : iex;                 // (chip + 0.5).floor() % 1023
                     const int ilx = max((int)(tc - 0.5f), 0);             // Q7: negative saturates to chip 0
                     pc = row[ipx]; ec = row[iex]; lc = row[ilx];
                 } else {
+                    tc = fmodf(tc, 1023.f);
                     pc = ca_chip(row, tc); ec = ca_chip(row, tc + 0.5f); lc = ca_chip(row, tc - 0.5f);
                 }
                 ip = fmaf(re, pc, ip); qp = fmaf(im, pc, qp);
                 ie = fmaf(re, ec, ie); qe = fmaf(im, ec, qe);
                 il = fmaf(re, lc, il); ql = fmaf(im, lc, ql);
+            };
+            // the epoch's samples are contiguous unless they straddle the ring's wrap point
+            const unsigned long long s0 = start & a.mask;
+            const bool contiguous = (a.mask == ~0ull) || (s0 + (unsigned long long)n <= a.mask + 1ull);
+            if (contiguous) {
+                const float2* __restrict__ px = a.samples + s0;
+#pragma unroll 8
+                for (int i = threadIdx.x; i < n; i += TRK_T) body(__ldg(px + i), (float)i);
+            } else {
+#pragma unroll 4
+                for (int i = threadIdx.x; i < n; i += TRK_T)
+                    body(__ldg(&a.samples[(start + (unsigned long long)i) & a.mask]), (float)i);
             }
         } else {
             for (int i = threadIdx.x; i < n; i += TRK_T) {
