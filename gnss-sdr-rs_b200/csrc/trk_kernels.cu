@@ -114,7 +114,7 @@ template <int MODE, int TRK_T> __global__ void __launch_bounds__(TRK_T) trk_kern
             // lies in [0, 3*1023): then `% 1023` is at most two exact subtractions and the E/P/L indices need no
             // range checks, so the loop is branch-free.
             const bool sane = code_phase >= 0.f && code_phase < 1023.f && code_step >= 0.f &&
-                              code_step * (float)n < 2040.f;
+                              code_step * (float)(n + 8 * TRK_T) < 2040.f;
             auto body = [&](const float2 x, const float fi) {
                 const float t = w * fi;
                 const float q0 = t * rcp_fs;
@@ -146,9 +146,53 @@ template <int MODE, int TRK_T> __global__ void __launch_bounds__(TRK_T) trk_kern
             // the epoch's samples are contiguous unless they straddle the ring's wrap point
             const unsigned long long s0 = start & a.mask;
             const bool contiguous = (a.mask == ~0ull) || (s0 + (unsigned long long)n <= a.mask + 1ull);
-            if (contiguous) {
+            if (contiguous && sane) {
+                // batches of 8 samples per thread, software-pipelined by hand: all loads, then all carrier
+                // phases / SFU sin-cos, then the code look-ups and the 48 FMAs -- so the load and SFU latencies
+                // of one sample hide behind the arithmetic of the other seven.  Samples past n load as 0.
                 const float2* __restrict__ px = a.samples + s0;
-#pragma unroll 8
+                constexpr int U = TRK_T >= 512 ? 4 : 8;
+                for (int base = threadIdx.x; base < n; base += U * TRK_T) {
+                    float2 x[U];
+                    float cs[U], sn[U];
+#pragma unroll
+                    for (int u = 0; u < U; u++) {
+                        const int i = base + u * TRK_T;
+                        x[u] = i < n ? __ldg(px + i) : make_float2(0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; u++) {
+                        const float fi = (float)(base + u * TRK_T);
+                        const float t = w * fi;
+                        const float q0 = t * rcp_fs;
+                        const float q = fmaf(fmaf(-q0, fs, t), rcp_fs, q0);
+                        const float phase = carrier_phase + q;
+                        const float k = rintf(phase * inv_2pi);
+                        const float r = fmaf(-k, c2, fmaf(-k, c1, phase));
+                        cs[u] = __cosf(r);
+                        sn[u] = __sinf(r);
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; u++) {
+                        const float fi = (float)(base + u * TRK_T);
+                        const float re = fmaf(x[u].x, cs[u], x[u].y * sn[u]);
+                        const float im = fmaf(x[u].y, cs[u], -(x[u].x * sn[u]));
+                        float tc = code_phase + (fi * code_step);
+                        tc = tc >= 1023.f ? tc - 1023.f : tc;
+                        tc = tc >= 1023.f ? tc - 1023.f : tc;
+                        const int ipx = (int)tc;
+                        int iex = (int)(tc + 0.5f);
+                        iex = iex >= 1023 ? iex - 1023 : iex;
+                        const int ilx = max((int)(tc - 0.5f), 0);
+                        const float pc = row[ipx], ec = row[iex], lc = row[ilx];
+                        ip = fmaf(re, pc, ip); qp = fmaf(im, pc, qp);
+                        ie = fmaf(re, ec, ie); qe = fmaf(im, ec, qe);
+                        il = fmaf(re, lc, il); ql = fmaf(im, lc, ql);
+                    }
+                }
+            } else if (contiguous) {
+                const float2* __restrict__ px = a.samples + s0;
+#pragma unroll 4
                 for (int i = threadIdx.x; i < n; i += TRK_T) body(__ldg(px + i), (float)i);
             } else {
 #pragma unroll 4
