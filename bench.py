@@ -221,7 +221,18 @@ def run_ours(args, rank, world, local_rank):
     dist = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # NCCL prints its version banner on stdout during the first collective; keep stdout to the ONE JSON line
+        saved = os.dup(1)
+        devnull = os.open(os.devnull, os.O_WRONLY)
+        os.dup2(devnull, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            os.dup2(saved, 1)
+            os.close(devnull)
+            os.close(saved)
 
     from gnss_sdr_rs_b200 import sharding
     by_prn = args.shard == "prn" and world > 1
@@ -240,6 +251,7 @@ def run_ours(args, rank, world, local_rank):
     eng.set_mode(ffi.GB_ACQ_FUSED if args.acq_mode == "fused" else ffi.GB_ACQ_SHARED)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     cuda_dev = torch.device("cuda", local_rank)
+    gatherer = sharding.ResultGatherer(dist, cuda_dev, N_PRN) if dist is not None else None
 
     def barrier():
         if dist is not None:
@@ -257,7 +269,7 @@ def run_ours(args, rank, world, local_rank):
             # the one collective of the path: per-PRN results of every rank, NCCL over NVLink
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            gathered = sharding.all_gather_results(sharding.pack_results(res), dist, cuda_dev)
+            gathered = gatherer.gather(res)
             e1.record()
             torch.cuda.synchronize()
             g_ms = e0.elapsed_time(e1)
@@ -288,7 +300,7 @@ def run_ours(args, rank, world, local_rank):
     for _ in range(args.steps):
         res_e2e = eng.search(x_pin_ptr, K_MS, prn_mask=prn_mask)
         if dist is not None:
-            sharding.all_gather_results(sharding.pack_results(res_e2e), dist, cuda_dev)
+            gatherer.gather(res_e2e)
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
     clocks = sampler.finish()

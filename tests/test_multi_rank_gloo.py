@@ -25,6 +25,8 @@ def _worker(rank, world, port, out_dir):
     results = [(_fake_result(p + 1) if ((mask >> p) & 1 and (p + 1) in present) else None) for p in range(32)]
     gathered = sharding.all_gather_results(sharding.pack_results(results), dist)
     merged = sharding.merge_prn_shards(gathered)
+    again = sharding.ResultGatherer(dist, None, 32).gather(results)   # the preallocated form bench.py uses
+    assert all((a == b).all() for a, b in zip(gathered, again))
     np.save(os.path.join(out_dir, "merged_%d.npy" % rank), merged)
     np.save(os.path.join(out_dir, "mask_%d.npy" % rank), np.array([mask], np.uint64))
     # batch / channel partitioning
