@@ -210,6 +210,55 @@ def tracking_numbers(hd, ffi, n_channels=1024, n_epochs=1000):
             "fs": fs}
 
 
+def extra_numbers(hd, ffi):
+    """Secondary measurements on the other BASELINE configs / SURVEY 8f rows (kernel time from CUDA events)."""
+    import ctypes as C
+    from gnss_sdr_rs_b200 import acquisition, ring, sdr_mock
+    out = {}
+    rng = np.random.default_rng(1)
+    # config 1 (reference grid): N = 16368, 29 bins, 10 x 1 ms, 32 PRNs, int8 IF recording through the ring
+    raw, _ = sdr_mock.if_recording(10)
+    rb = ring.MulticastRingBuffer(hd, 1 << 18)
+    rb.write_samples(raw)
+    eng = acquisition.AcquisitionEngine(hd, 16368, 16367600.0)
+    eng.make_doppler_tables(4130400.0, np.array(acquisition.reference_doppler_grid(), np.float32))
+    ms = []
+    for _ in range(5):
+        res = eng.search_ring(0, 10)
+        ms.append(eng.last_kernel_ms())
+    out["config1_reference_grid"] = {"fft_size": 16368, "n_doppler": 29, "num_integrations": 10, "kernel_ms": min(ms),
+                                     "cells_per_sec": 32 * 29 * 16368 / (min(ms) * 1e-3),
+                                     "detected_prns": sorted(r["prn"] for r in res if r),
+                                     "x_realtime_vs_10ms_dwell": 10.0 / min(ms)}
+    # Galileo-E1-like 4 ms code at 20 Msps: cluster / DSMEM plan, 8 PRNs x 41 bins x 5 blocks (20 ms)
+    n = 80000
+    codes = np.stack([sdr_mock.resample_code(sdr_mock.e1_surrogate_code(p), 1.023e6, 20e6, n, boc11=True) for p in range(1, 9)])
+    x = (rng.standard_normal(5 * n) + 1j * rng.standard_normal(5 * n)).astype(np.complex64)
+    eng = acquisition.AcquisitionEngine(hd, n, 20e6, n_prn=8, codes=codes)
+    eng.make_doppler_tables(0.0, np.arange(-2500, 2501, 125, dtype=np.float32))
+    ms = []
+    for _ in range(4):
+        eng.search_cells(x, 5)
+        ms.append(eng.last_kernel_ms())
+    out["galileo_e1_like_n80000_cluster"] = {"fft_size": n, "n_prn": 8, "n_doppler": 41, "num_integrations": 5,
+                                             "kernel_ms": min(ms), "cells_per_sec": 8 * 41 * n / (min(ms) * 1e-3)}
+    # digital front-end (N2): 64 rf_thread blocks of 2048 raw samples into the ring
+    fe = ring.DigitalFrontend(hd, 4130400.0, 16367600.0)
+    rb = ring.MulticastRingBuffer(hd, 1 << 20)
+    blk = (rng.standard_normal(64 * 2048) + 1j * rng.standard_normal(64 * 2048)).astype(np.complex64)
+    fe.process_block_into_ring(blk)
+    hd.call("gb_synchronize")
+    t0 = time.perf_counter()
+    for _ in range(4):
+        fe.process_block_into_ring(blk)
+    hd.call("gb_synchronize")
+    dt = (time.perf_counter() - t0) / 4
+    out["digital_frontend"] = {"samples_per_call": int(blk.size), "wall_ms_per_call": dt * 1e3,
+                               "msamples_per_sec": blk.size / dt / 1e6,
+                               "note": "bit-exact sequential NCO/DC recurrences: one CTA per stream, latency-bound"}
+    return out
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import gnss_sdr_rs_b200._ffi as ffi
@@ -370,8 +419,13 @@ def run_ours(args, rank, world, local_rank):
                 "argmax_equal_strong_cells": bool((gcells["argmax"][:n_prn][strong] == ocells["argmax"][strong]).all())}
             try:
                 line["tracking"] = tracking_numbers(hd, ffi)
+                line["tracking_128ch"] = tracking_numbers(hd, ffi, 128, 1000)
             except Exception as e:  # report, never hide
                 line["tracking"] = {"error": repr(e)}
+            try:
+                line["extras"] = extra_numbers(hd, ffi)
+            except Exception as e:
+                line["extras"] = {"error": repr(e)}
         print(json.dumps(line), flush=True)
     hd.close()
     if dist is not None:

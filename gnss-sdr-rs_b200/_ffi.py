@@ -43,6 +43,8 @@ class TrkChannel(C.Structure):
                 ("pll_tau1", C.c_float), ("pll_tau2", C.c_float), ("dll_tau1", C.c_float), ("dll_tau2", C.c_float)]
 
 
+NAV_DTYPE = np.dtype([("flag_bit_sync", np.int32), ("frame_sync_ind", np.int32), ("sync_epoch", np.int32),
+                      ("n_bits", np.int32), ("bit_sync_buff", np.uint32, (20,))])
 CELL_DTYPE = np.dtype([("peak", np.float32), ("argmax", np.uint32), ("sum8", np.float32), ("peak2", np.float32)])
 CORR_DTYPE = np.dtype([("i_p", np.float32), ("q_p", np.float32), ("i_e", np.float32), ("q_e", np.float32),
                        ("i_l", np.float32), ("q_l", np.float32)])
@@ -99,6 +101,7 @@ SIGNATURES = {
     "gb_trk_run": (_i32, [_vp, _i32, _i32, _vp]),
     "gb_trk_download": (_i32, [_vp, _vp, _i32]),
     "gb_trk_last_kernel_ms": (_f32, [_vp]),
+    "gb_nav_bit_sync": (_i32, [_vp, _vp, _i32, _i32, _vp, _vp, _i32]),
 }
 
 _LIB = None

@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(256) frontend_kernel(const float2* __restrict_
                                                       float alpha, float con)
 {
     __shared__ float2 tile[FE_TILE];
-    __shared__ unsigned short idx[FE_TILE];
+    __shared__ __align__(4) unsigned short idx[FE_TILE];
     __shared__ float s_acc;
     __shared__ float s_bias[16];
     if (threadIdx.x == 0) s_acc = state[0];
@@ -224,18 +224,51 @@ __global__ void __launch_bounds__(256) frontend_kernel(const float2* __restrict_
         for (int i = threadIdx.x; i < tn; i += blockDim.x) tile[i] = src[t0 + i];
         __syncthreads();
         if (threadIdx.x == 0) {
+            // sequential f32 phase accumulator (frontend.rs:48-52).  Dependent chain per sample: FADD -> {FADD, FSETP}
+            // -> FSEL; the index conversion and the store hang off it.  Unrolled by 8, indices packed 2 per store.
             float acc = s_acc;
-            for (int i = 0; i < tn; i++) {
-                idx[i] = (unsigned short)((acc > 0.f ? (unsigned)acc : 0u) & 2047u);  // `as usize % LUT_SIZE`
+            const bool fast = step >= 0.f && step < 2048.f && acc >= 0.f && acc < 2048.f;
+            int i = 0;
+            if (fast) {
+                unsigned* idx32 = reinterpret_cast<unsigned*>(idx);
+                for (; i + 8 <= tn; i += 8) {
+                    unsigned k[8];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        k[u] = (unsigned)acc;                    // acc in [0, 2048): `as usize % LUT_SIZE`
+                        const float s = __fadd_rn(acc, step);    // < 4096
+                        const float s2 = __fsub_rn(s, 2048.f);   // exact when s >= 2048 (== fmodf)
+                        acc = s >= 2048.f ? s2 : s;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; u += 2) idx32[(i + u) >> 1] = k[u] | (k[u + 1] << 16);
+                }
+            }
+            for (; i < tn; i++) {
+                idx[i] = (unsigned short)((acc > 0.f ? (unsigned)acc : 0u) & 2047u);
                 const float s = __fadd_rn(acc, step);
                 acc = (s >= 0.f && s < 4096.f) ? (s >= 2048.f ? s - 2048.f : s) : fmodf(s, 2048.f);
             }
             s_acc = acc;
         } else if (threadIdx.x >= 32 && threadIdx.x < 48) {
+            // 8 + 8 independent DC-bias recurrences (dc_remove.rs:23-29); 8 values are loaded ahead of the chain
             const int l = threadIdx.x - 32, lane = l & 7, comp = l >> 3;
             float b = s_bias[l];
             float* t = reinterpret_cast<float*>(tile) + comp;
-            for (int cidx = lane; cidx < tn; cidx += 8) {
+            int cidx = lane;
+            for (; cidx + 56 < tn; cidx += 64) {
+                float x[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) x[u] = t[2 * (cidx + 8 * u)];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    b = __fadd_rn(__fmul_rn(b, con), __fmul_rn(x[u], alpha));
+                    x[u] = __fsub_rn(x[u], b);
+                }
+#pragma unroll
+                for (int u = 0; u < 8; u++) t[2 * (cidx + 8 * u)] = x[u];
+            }
+            for (; cidx < tn; cidx += 8) {
                 const float x = t[2 * cidx];
                 b = __fadd_rn(__fmul_rn(b, con), __fmul_rn(x, alpha));
                 t[2 * cidx] = __fsub_rn(x, b);
@@ -255,6 +288,49 @@ __global__ void __launch_bounds__(256) frontend_kernel(const float2* __restrict_
     }
     if (threadIdx.x == 0) state[0] = s_acc;
     if (threadIdx.x < 16) state[1 + threadIdx.x] = s_bias[threadIdx.x];
+}
+
+// Bit synchronisation + 20 ms prompt accumulation on the batched prompt history (legacy
+// decoding.rs:115-127, 164-213): one thread per channel walks its prompt-I column in epoch order.
+__global__ void nav_bit_sync_kernel(const float* __restrict__ hist, int n_epochs, int n_channels, gb_nav_sync* __restrict__ st,
+                                    int8_t* __restrict__ bits, int max_bits)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_channels) return;
+    gb_nav_sync s;
+    s.flag_bit_sync = 0; s.frame_sync_ind = 0; s.sync_epoch = -1; s.n_bits = 0;
+    unsigned buff[20];
+#pragma unroll
+    for (int i = 0; i < 20; i++) buff[i] = 0u;
+    float old_ip = 0.f, acc = 0.f;
+    int biti = 0;
+    for (int cnt = 0; cnt < n_epochs; cnt++) {
+        const float ip = hist[((size_t)cnt * n_channels + c) * 2];
+        if (!s.flag_bit_sync && cnt > 1000 && __fmul_rn(old_ip, ip) < 0.f) {
+            unsigned v_max = 0u;
+            int i_max = 0;
+#pragma unroll
+            for (int i = 0; i < 20; i++) {
+                if (i == biti) buff[i] += 1u;
+                if (buff[i] >= v_max) { v_max = buff[i]; i_max = i; }   // Iterator::max_by keeps the last maximum
+            }
+            s.frame_sync_ind = i_max;
+            if (v_max == 30u) { s.flag_bit_sync = 1; s.sync_epoch = cnt; }
+        }
+        if (s.flag_bit_sync) {
+            acc = (biti == s.frame_sync_ind) ? ip : __fadd_rn(acc, ip);
+            const int last = s.frame_sync_ind + 19 >= 20 ? s.frame_sync_ind - 1 : s.frame_sync_ind + 19;
+            if (biti == last) {
+                if (s.n_bits < max_bits) bits[(size_t)c * max_bits + s.n_bits] = acc > 0.f ? 1 : -1;
+                s.n_bits++;
+            }
+        }
+        old_ip = ip;
+        biti = biti == 19 ? 0 : biti + 1;
+    }
+#pragma unroll
+    for (int i = 0; i < 20; i++) s.bit_sync_buff[i] = buff[i];
+    st[c] = s;
 }
 
 __global__ void i8_to_ring_kernel(const int8_t* __restrict__ src, float2* __restrict__ ring, unsigned long long start,
@@ -1195,3 +1271,32 @@ extern "C" int gb_trk_correlate(gb_handle* h, gb_trk_channel* ch, int n, const g
 }
 
 extern "C" float gb_trk_last_kernel_ms(gb_handle* h) { return h ? h->last_trk_ms : 0.f; }
+
+// N4: bit sync + nav-bit accumulation over a prompt history [n_epochs][n_channels][2] (host memory)
+extern "C" int gb_nav_bit_sync(gb_handle* h, const float* prompt_hist, int n_epochs, int n_channels, gb_nav_sync* out,
+                               int8_t* bits, int max_bits)
+{
+    if (!h || !prompt_hist || !out || !bits || n_epochs < 1 || n_channels < 1 || max_bits < 1) return GB_EINVAL;
+    CK(cudaSetDevice(h->device));
+    const size_t hist_n = (size_t)n_epochs * n_channels * 2;
+    int rc = ensure(h, &h->hist_dev, &h->hist_cap, hist_n);
+    if (rc) return rc;
+    gb_nav_sync* st_dev = nullptr;
+    int8_t* bits_dev = nullptr;
+    CK(cudaMalloc((void**)&st_dev, sizeof(gb_nav_sync) * n_channels));
+    cudaError_t e = cudaMalloc((void**)&bits_dev, (size_t)n_channels * max_bits);
+    if (e != cudaSuccess) { cudaFree(st_dev); return fail(h, e, "cudaMalloc"); }
+    e = cudaMemcpyAsync(h->hist_dev, prompt_hist, hist_n * sizeof(float), cudaMemcpyHostToDevice, h->s_trk);
+    if (e == cudaSuccess) e = cudaMemsetAsync(bits_dev, 0, (size_t)n_channels * max_bits, h->s_trk);
+    if (e == cudaSuccess) {
+        nav_bit_sync_kernel<<<(n_channels + 63) / 64, 64, 0, h->s_trk>>>(h->hist_dev, n_epochs, n_channels, st_dev, bits_dev, max_bits);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, st_dev, sizeof(gb_nav_sync) * n_channels, cudaMemcpyDeviceToHost, h->s_trk);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(bits, bits_dev, (size_t)n_channels * max_bits, cudaMemcpyDeviceToHost, h->s_trk);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->s_trk);
+    cudaFree(st_dev);
+    cudaFree(bits_dev);
+    if (e != cudaSuccess) return fail(h, e, "nav_bit_sync");
+    return GB_OK;
+}

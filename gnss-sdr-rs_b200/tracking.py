@@ -81,3 +81,13 @@ class TrackingEngine:
 
     def last_kernel_ms(self):
         return float(self.hd.L.gb_trk_last_kernel_ms(self.hd.h))
+
+
+def nav_bit_sync(handle, prompt_hist, max_bits=4096):
+    """Bit sync + 20 ms prompt accumulation (N4) on a prompt history [n_epochs, n_channels, 2]."""
+    hist = np.ascontiguousarray(prompt_hist, np.float32)
+    n_epochs, n_channels = hist.shape[0], hist.shape[1]
+    st = np.zeros(n_channels, _ffi.NAV_DTYPE)
+    bits = np.zeros((n_channels, max_bits), np.int8)
+    handle.call("gb_nav_bit_sync", _ffi.ptr(hist), n_epochs, n_channels, _ffi.ptr(st), _ffi.ptr(bits), int(max_bits))
+    return st, bits

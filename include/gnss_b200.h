@@ -224,6 +224,22 @@ int gb_trk_run(gb_handle *h, int n_epochs, int mode, float *prompt_hist);
 int gb_trk_download(gb_handle *h, gb_trk_channel *ch, int n_channels);
 float gb_trk_last_kernel_ms(gb_handle *h);
 
+/* ------------------------------------------------------------------ bit sync + nav-bit accumulation
+ * restates the orphaned legacy check_bit_sync / bit_accumulation (decoding.rs:8, 115-127, 164-213) on the batched
+ * prompt history gb_trk_run() returns: per channel, sign changes of prompt-I are histogrammed by epoch % 20 (after
+ * epoch 1000) until one slot reaches 30 (BIT_SYNC_THRESHOLD); from then on 20 prompts are summed per bit and its sign
+ * emitted.  The legacy end-of-bit test omits the modulo (can only fire for frame_sync_ind == 0); the intended modular
+ * condition is used.  bits: n_channels x max_bits (+1 / -1). */
+typedef struct {
+    int32_t flag_bit_sync;
+    int32_t frame_sync_ind;
+    int32_t sync_epoch; /* epoch at which synchronisation was declared, -1 if never */
+    int32_t n_bits;
+    uint32_t bit_sync_buff[20];
+} gb_nav_sync;
+int gb_nav_bit_sync(gb_handle *h, const float *prompt_hist /* n_epochs x n_channels x 2 */, int n_epochs, int n_channels,
+                    gb_nav_sync *out, int8_t *bits, int max_bits);
+
 #ifdef __cplusplus
 }
 #endif

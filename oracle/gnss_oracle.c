@@ -768,3 +768,34 @@ void go_frontend_process_block(go_frontend *f, go_c32 *s, size_t n)
         }
     }
 }
+
+/* ------------------------------------------------------------------ bit sync / nav-bit accumulation (N4) */
+void go_nav_bit_sync(const float *prompt_i, int n_epochs, int stride, go_nav_sync *st, int8_t *bits, int max_bits)
+{
+    memset(st, 0, sizeof(*st));
+    st->sync_epoch = -1;
+    float old_ip = 0.0f, acc = 0.0f;
+    for (int cnt = 0; cnt < n_epochs; cnt++) {
+        const float ip = prompt_i[(size_t)cnt * stride];
+        const int biti = cnt % 20;
+        if (!st->flag_bit_sync && cnt > 1000) {         /* decoding.rs:121-123 */
+            if (old_ip * ip < 0.0f) {                   /* check_bit_sync, :164-180 */
+                st->bit_sync_buff[biti] += 1;
+                int i_max = 0;
+                uint32_t v_max = 0;
+                for (int i = 0; i < 20; i++)
+                    if (st->bit_sync_buff[i] >= v_max) { v_max = st->bit_sync_buff[i]; i_max = i; } /* max_by: last max */
+                st->frame_sync_ind = i_max;
+                if (v_max == 30) { st->flag_bit_sync = 1; st->sync_epoch = cnt; }
+            }
+        }
+        if (st->flag_bit_sync) {                        /* bit_accumulation, :182-213 */
+            if (biti == st->frame_sync_ind) acc = ip; else acc += ip;
+            if (biti == (st->frame_sync_ind + 19) % 20) {
+                if (st->n_bits < max_bits) bits[st->n_bits] = acc > 0.0f ? 1 : -1;
+                st->n_bits++;
+            }
+        }
+        old_ip = ip;
+    }
+}

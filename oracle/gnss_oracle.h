@@ -196,6 +196,23 @@ void go_frontend_init(go_frontend *f, float f_if, float fs_in);
 /* in place on n complex samples; processes floor(n/8)*8 samples, the tail is left untouched (chunks_exact_mut(16)) */
 void go_frontend_process_block(go_frontend *f, go_c32 *samples, size_t n);
 
+/* ---- bit synchronisation + 20 ms prompt accumulation (orphaned legacy decoding.rs:8,115-127,164-213) ----
+ * Per channel over its prompt-I history (one value per 1 ms epoch, cnt = epoch index):
+ *   biti = cnt % 20; while not synchronised and cnt > 1000: a sign change between consecutive prompts increments
+ *   bit_sync_buff[biti]; frame_sync_ind = index of the maximum (Iterator::max_by keeps the LAST of equal maxima);
+ *   synchronised when that maximum reaches BIT_SYNC_THRESHOLD = 30 (decoding.rs:164-180).
+ *   Once synchronised: i_p restarts at biti == frame_sync_ind and a bit (+1 if sum > 0 else -1) is emitted at the 20th
+ *   epoch of the window.  The legacy compares biti with frame_sync_ind + 19 WITHOUT the modulo (decoding.rs:199-201),
+ *   which can only fire for frame_sync_ind == 0; the intended modular condition is used here and stated as a deviation. */
+typedef struct {
+    int32_t flag_bit_sync;
+    int32_t frame_sync_ind;
+    int32_t sync_epoch;     /* cnt at which synchronisation was declared, -1 if never */
+    int32_t n_bits;
+    uint32_t bit_sync_buff[20];
+} go_nav_sync;
+void go_nav_bit_sync(const float *prompt_i, int n_epochs, int stride, go_nav_sync *st, int8_t *bits, int max_bits);
+
 #ifdef __cplusplus
 }
 #endif

@@ -48,6 +48,11 @@ class Frontend(C.Structure):
                 ("alpha", C.c_float), ("con", C.c_float)]
 
 
+class NavSync(C.Structure):
+    _fields_ = [("flag_bit_sync", C.c_int32), ("frame_sync_ind", C.c_int32), ("sync_epoch", C.c_int32),
+                ("n_bits", C.c_int32), ("bit_sync_buff", C.c_uint32 * 20)]
+
+
 class AcqManager(C.Structure):
     _fields_ = [("mode", C.c_int)]
 
@@ -101,6 +106,7 @@ def lib():
         "go_ring_head": (sz, [vp]), "go_ring_copy_to_slice": (None, [vp, sz, vp, sz]),
         "go_trk_update": (i32, [vp, vp, vp, vp, vp, vp]),
         "go_trk_run_all": (None, [vp, i32, vp, sz, i32, i32, vp]),
+        "go_nav_bit_sync": (None, [vp, i32, i32, vp, vp, i32]),
         "go_frontend_init": (None, [vp, f32, f32]),
         "go_frontend_process_block": (None, [vp, vp, sz]),
     }
@@ -319,3 +325,12 @@ def frontend_process(f, samples):
     x = np.ascontiguousarray(samples, c32).copy()
     lib().go_frontend_process_block(C.byref(f), _p(x), len(x))
     return x
+
+
+def nav_bit_sync(prompt_i, max_bits=4096):
+    """prompt_i: [n_epochs] float32 of ONE channel -> (NavSync, bits)."""
+    x = np.ascontiguousarray(prompt_i, np.float32)
+    st = NavSync()
+    bits = np.zeros(max_bits, np.int8)
+    lib().go_nav_bit_sync(_p(x), len(x), 1, C.byref(st), _p(bits), max_bits)
+    return st, bits[:min(st.n_bits, max_bits)].copy()

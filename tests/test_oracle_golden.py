@@ -327,3 +327,30 @@ def test_digital_frontend_against_numpy(oracle):
     assert y.tobytes() == out.astype(np.complex64).tobytes()
     assert (y[-5:] == x[-5:]).all()  # chunks_exact_mut(16 floats): the tail is left raw
     assert f.phase_accumulator == acc
+
+
+def test_nav_bit_sync_against_python(oracle):
+    """SURVEY 8f N4 (legacy decoding.rs:115-127, 164-213): independent restatement on a synthetic prompt sequence."""
+    rng = np.random.default_rng(2)
+    n, offset = 4000, 7                      # bit edges at epochs == 7 (mod 20)
+    bits = rng.integers(0, 2, n // 20 + 2) * 2 - 1
+    ip = np.array([bits[(e - offset) // 20 + 1] * 1000.0 for e in range(n)], np.float32) + rng.standard_normal(n).astype(np.float32) * 50
+    st, out = oracle.nav_bit_sync(ip, 512)
+    buff = [0] * 20
+    sync, ind, acc, got, old = False, 0, 0.0, [], np.float32(0)
+    for cnt in range(n):
+        biti = cnt % 20
+        if not sync and cnt > 1000 and old * ip[cnt] < 0:
+            buff[biti] += 1
+            vmax = max(buff)
+            ind = max(i for i in range(20) if buff[i] == vmax)
+            sync = vmax == 30
+        if sync:
+            acc = ip[cnt] if biti == ind else np.float32(acc + ip[cnt])
+            if biti == (ind + 19) % 20:
+                got.append(1 if acc > 0 else -1)
+        old = ip[cnt]
+    assert st.flag_bit_sync == 1 and st.frame_sync_ind == ind == offset
+    assert out.tolist() == got and list(st.bit_sync_buff) == buff
+    first = (st.sync_epoch - offset) // 20 + 1   # synchronisation is declared ON a bit edge: that bit is the first one out
+    assert out.tolist()[:20] == bits[first:first + 20].tolist()
