@@ -45,6 +45,9 @@ class TrkChannel(C.Structure):
 
 NAV_DTYPE = np.dtype([("flag_bit_sync", np.int32), ("frame_sync_ind", np.int32), ("sync_epoch", np.int32),
                       ("n_bits", np.int32), ("bit_sync_buff", np.uint32, (20,))])
+FINE_REQ_DTYPE = np.dtype([("prn", np.uint8), ("reserved", np.uint8, (3,)), ("code_phase", np.uint32)])
+FINE_RES_DTYPE = np.dtype([("fft_size", np.uint32), ("idx", np.uint32), ("mag", np.float32), ("carrier_freq", np.float32),
+                           ("ref_defined", np.int32)])
 CELL_DTYPE = np.dtype([("peak", np.float32), ("argmax", np.uint32), ("sum8", np.float32), ("peak2", np.float32)])
 CORR_DTYPE = np.dtype([("i_p", np.float32), ("q_p", np.float32), ("i_e", np.float32), ("q_e", np.float32),
                        ("i_l", np.float32), ("q_l", np.float32)])
@@ -87,6 +90,9 @@ SIGNATURES = {
     "gb_acq_search_ring": (_i32, [_vp, _u64, _i32, _u32, _vp, _vp]),
     "gb_acq_bin_power": (_i32, [_vp, _vp, _i32, _i32, _i32, _vp]),
     "gb_acq_last_kernel_ms": (_f32, [_vp]),
+    "gb_acq_fine_doppler": (_i32, [_vp, _vp, _u64, _f32, _i32, _i32, _vp, _i32, _vp, _vp, _vp]),
+    "gb_acq_fine_doppler_ring": (_i32, [_vp, _u64, _u64, _f32, _i32, _i32, _vp, _i32, _vp, _vp]),
+    "gb_acq_fine_last_kernel_ms": (_f32, [_vp]),
     "gb_bench_fp32_tflops": (_i32, [_vp, _vp]),
     "gb_fft_c2c": (_i32, [_vp, _i32, _i32, _vp, _vp, _i32]),
     "gb_fft_power_spectrum": (_i32, [_vp, _i32, _vp, _vp, _i32]),

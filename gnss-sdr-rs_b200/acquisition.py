@@ -149,6 +149,42 @@ def decide(cells_row, carr, prn, fft_size, fs, local_tail=0, threshold=7.0):
     return r.as_dict() if r.found else None
 
 
+LEGACY_LONG_SAMPLES_LENGTH = 11    # acquisition_bk.rs:21 (ms)
+
+
+def finer_doppler(handle, long_samples, requests, fs, long_ms=LEGACY_LONG_SAMPLES_LENGTH, is_complex=True, codes1023=None,
+                  want_mag=False):
+    """finer_doppler (acquisition_bk.rs:215-302) for a batch of acquired satellites on one recording.
+
+    long_samples: complex64 array (host), or an int = absolute index into the device ring (then `n_long` = long_ms*N
+    samples are read from it).  requests: iterable of (prn, code_phase_samples).  Returns a FINE_RES_DTYPE array
+    (fft_size, idx, mag, carrier_freq, ref_defined) and, if want_mag, the [n_req, fft_size] magnitudes.
+    """
+    req = np.zeros(len(requests), _ffi.FINE_REQ_DTYPE)
+    for i, (prn, cp) in enumerate(requests):
+        req[i]["prn"], req[i]["code_phase"] = int(prn), int(cp)
+    out = np.zeros(len(req), _ffi.FINE_RES_DTYPE)
+    codes = None if codes1023 is None else np.ascontiguousarray(codes1023, np.int8)
+    if codes is not None:
+        assert codes.shape == (len(req), 1023)
+    if isinstance(long_samples, (int, np.integer)):
+        n_long = int(long_ms) * fft_size_for(fs)
+        handle.call("gb_acq_fine_doppler_ring", int(long_samples), n_long, float(fs), int(long_ms), int(bool(is_complex)),
+                    _ffi.ptr(req), len(req), _ffi.ptr(codes), _ffi.ptr(out))
+        return out
+    x = np.ascontiguousarray(long_samples, np.complex64)
+    mag = None
+    if want_mag:
+        use = (int(long_ms) - 1) * fft_size_for(fs)
+        p2 = 1
+        while p2 < use:
+            p2 <<= 1
+        mag = np.zeros((len(req), 8 * p2), np.float32)
+    handle.call("gb_acq_fine_doppler", _ffi.ptr(x), len(x), float(fs), int(long_ms), int(bool(is_complex)), _ffi.ptr(req),
+                len(req), _ffi.ptr(codes), _ffi.ptr(out), _ffi.ptr(mag))
+    return (out, mag) if want_mag else out
+
+
 class FFT:
     """fft.rs:5-30 FFT<f32>."""
 

@@ -181,9 +181,7 @@ __global__ void __launch_bounds__(512) reduce_rows_kernel(const float* __restric
     float p2 = 0.f;
     if (spc > 0) {
         for (int i = threadIdx.x; i < n; i += blockDim.x) {
-            int dist = abs(i - (int)arg);
-            dist = min(dist, n - dist);
-            if (dist > spc) p2 = fmaxf(p2, acc[i]);
+            if (two_peak_searched(i, (int)arg, spc, n)) p2 = fmaxf(p2, acc[i]);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) p2 = fmaxf(p2, __shfl_xor_sync(0xffffffffu, p2, o));

@@ -20,6 +20,10 @@ using P4092v1 = Plan<4092, 192, 3, 0, 12, 11, 31>;
 using P4092v2 = Plan<4092, 160, 3, 0, 12, 11, 31>;
 using P4092v3 = Plan<4092, 192, 2, 0, 12, 11, 31>;
 using P4092v4 = Plan<4092, 384, 1, 0, 12, 11, 31>;
+using P4092v5 = Plan<4092, 224, 3, 0, 12, 11, 31>;
+using P4092v6 = Plan<4092, 192, 4, 0, 12, 11, 31>;
+using P4092v7 = Plan<4092, 256, 3, 0, 12, 11, 31>;
+using P4092v8 = Plan<4092, 224, 4, 0, 12, 11, 31>;
 using P16368v1 = Plan<16368, 288, 1, 0, 16, 3, 11, 31>;
 using P16368v2 = Plan<16368, 416, 1, 0, 16, 3, 11, 31>;
 
@@ -33,6 +37,19 @@ __device__ __forceinline__ float2 wipe(float2 x, float2 w)
 __device__ __forceinline__ float2 ld_iq(const AcqArgs& a, unsigned long long idx)
 {
     return __ldg(&a.iq[(a.iq_start + idx) & a.iq_mask]);
+}
+
+// satellite_detection_two_peaks' second-peak window (acquisition_bk.rs:371-390), slice bounds verbatim: with
+// left = cp - spc and right = cp + spc the second peak is searched in
+//   left < 1    : [right-1, N+left)          (code phase within spc of the start)
+//   right >= N  : [right-N-1, left)          (within spc of the end; the lower bound underflows for right == N, clamped)
+//   otherwise   : [0, left) u [right, N)     -- asymmetric: index cp+spc is searched, cp-spc is not
+__device__ __forceinline__ bool two_peak_searched(int n, int cp, int spc, int N)
+{
+    const int left = cp - spc, right = cp + spc;
+    if (left < 1) return n >= right - 1 && n < N + left;
+    if (right >= N) return n >= max(right - N - 1, 0) && n < left;
+    return n < left || n >= right;
 }
 
 struct PeakIdx {

@@ -14,8 +14,9 @@
 namespace gb {
 
 #define GB_FOR_EACH_PLAN(X) X(0, P1024) X(1, P2048) X(2, P4092) X(3, P4096) X(4, P8184) X(5, P16368) X(6, P20000) \
-    X(7, P4092v1) X(8, P4092v2) X(9, P4092v3) X(10, P4092v4) X(11, P16368v1) X(12, P16368v2)
-static const int kPlanSizes[] = {1024, 2048, 4092, 4096, 8184, 16368, 20000, -1, -1, -1, -1, -1, -1};
+    X(7, P4092v1) X(8, P4092v2) X(9, P4092v3) X(10, P4092v4) X(11, P16368v1) X(12, P16368v2) \
+    X(13, P4092v5) X(14, P4092v6) X(15, P4092v7) X(16, P4092v8)
+static const int kPlanSizes[] = {1024, 2048, 4092, 4096, 8184, 16368, 20000, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1};
 static const int kNumPlans = sizeof(kPlanSizes) / sizeof(int);
 
 // Stage 0 of the forward DIF (L = N) with the carrier wipe-off (and, for n_coh > 1, the coherent
@@ -131,9 +132,7 @@ __device__ __forceinline__ void reduce_row_to_cell(float (&acc)[StageGeo<P, 0>::
 #pragma unroll
                 for (int j = 0; j < G0::R; j++) {
                     const int n = i + j * G0::SUB;
-                    int dist = abs(n - (int)arg);
-                    dist = min(dist, N - dist);
-                    if (dist > spc) p2 = fmaxf(p2, acc[it][j]);
+                    if (two_peak_searched(n, (int)arg, spc, N)) p2 = fmaxf(p2, acc[it][j]);
                 }
             }
         }
@@ -277,9 +276,13 @@ template <class P> __global__ void __launch_bounds__(P::T, P::MINB) acq_forward_
     }
 }
 
-template <class P> __global__ void __launch_bounds__(P::T, P::MINB) acq_inverse_kernel(const AcqArgs a)
+// DB = true: the line is double-buffered (2 x N complex of shared memory).  The barrier at the end of a group
+// disappears: warps that finish the accumulate stage of group g early start loading and transforming group g+1 into
+// the other buffer, so the L2 latency at the head of stage A overlaps the slower warps' tail (the barrier after stage
+// A of g+1 is what guarantees everybody has left buffer g before stage A of g+2 overwrites it).
+template <class P, bool DB> __global__ void __launch_bounds__(P::T, P::MINB) acq_inverse_kernel(const AcqArgs a)
 {
-    extern __shared__ float2 line[];
+    extern __shared__ float2 smem_line[];
     constexpr int LASTS = P::NSTAGE - 1;
     using G0 = StageGeo<P, 0>;
     using GM = StageGeo<P, LASTS>;
@@ -299,6 +302,7 @@ template <class P> __global__ void __launch_bounds__(P::T, P::MINB) acq_inverse_
         for (int j = 0; j < G0::R; j++) acc[it][j] = 0.f;
 
     for (int g = 0; g < n_groups; g++) {
+        float2* __restrict__ line = DB ? smem_line + (g & 1) * P::LINE : smem_line;
         const float2* __restrict__ sg = spec + (size_t)g * N;
 #pragma unroll 1
         for (int it = 0; it < GM::ITERS; it++) {
@@ -313,9 +317,10 @@ template <class P> __global__ void __launch_bounds__(P::T, P::MINB) acq_inverse_
         __syncthreads();
         DitRange<P, LASTS - 1, 0, true>::run(line, tw);
         final_stage_accumulate<P>(line, tw, acc);
-        __syncthreads();
+        if (!DB) __syncthreads();
     }
-    reduce_row_to_cell<P>(acc, line, a.spc, &a.cells[(size_t)row * a.D + a.d_lo + dl]);
+    if (DB) __syncthreads();  // reduce_row_to_cell reuses the line as scratch
+    reduce_row_to_cell<P>(acc, smem_line, a.spc, &a.cells[(size_t)row * a.D + a.d_lo + dl]);
 }
 
 // ------------------------------------------------------------------ code spectra (AcquisitionWorker::new, :133-138)
@@ -432,6 +437,7 @@ int acq_plan_index(int n)
     if (n == 4092) {
         const char* v = getenv("GB_ACQ_VARIANT");
         if (v && v[0] >= '1' && v[0] <= '4' && !v[1]) return 6 + (v[0] - '0');
+        if (v && v[0] >= '5' && v[0] <= '8' && !v[1]) return 8 + (v[0] - '0');
     }
     if (n == 16368) {
         const char* v = getenv("GB_ACQ_VARIANT");
@@ -519,10 +525,13 @@ template <class P> static cudaError_t launch_shared(const AcqArgs& a, int n_d, c
     const size_t smem = plan_smem<P>();
     cudaError_t e = set_smem(acq_forward_kernel<P>, smem);
     if (e != cudaSuccess) return e;
-    if ((e = set_smem(acq_inverse_kernel<P>, smem)) != cudaSuccess) return e;
     acq_forward_kernel<P><<<n_d * (a.K / a.n_coh), P::T, smem, st>>>(a);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    acq_inverse_kernel<P><<<n_d * a.n_active, P::T, smem, st>>>(a);
+    // double-buffered line when two lines fit the 227 KB of one SM at the plan's CTA count
+    constexpr bool kDB = P::DB;
+    const size_t smem_inv = kDB ? 2 * smem : smem;
+    if ((e = set_smem(acq_inverse_kernel<P, kDB>, smem_inv)) != cudaSuccess) return e;
+    acq_inverse_kernel<P, kDB><<<n_d * a.n_active, P::T, smem_inv, st>>>(a);
     return cudaGetLastError();
 }
 template <class P> static cudaError_t launch_row(const AcqArgs& a, cudaStream_t st)

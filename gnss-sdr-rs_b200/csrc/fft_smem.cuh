@@ -20,6 +20,46 @@
 
 namespace gb {
 
+// ---- packed FP32 pairs (Blackwell FFMA2 / FADD2: one instruction, two IEEE-rn f32 operations) ----
+// A complex value lives in an aligned register pair anyway (it is loaded and stored as 64 bits), so complex
+// add/sub and "complex x real scalar + complex" map 1:1 onto the sm_100a packed instructions.  Measured on B200
+// (tools/ubench/ffma2.cu): FFMA2 sustains the same 128 FMA/clk/SM as FFMA with half the issue slots -- these kernels
+// are issue-bound, not FMA-pipe-bound, so halving the FP instruction count is the lever.  Each lane of a packed op
+// rounds exactly like the scalar instruction: results are bit-identical to the scalar formulation.
+typedef unsigned long long pk64;
+__device__ __forceinline__ pk64 pk(float x, float y)
+{
+    pk64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y));
+    return r;
+}
+__device__ __forceinline__ pk64 pk(float2 v) { return pk(v.x, v.y); }
+__device__ __forceinline__ float2 upk(pk64 v)
+{
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
+__device__ __forceinline__ pk64 add2(pk64 a, pk64 b)
+{
+    pk64 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ pk64 sub2(pk64 a, pk64 b)
+{
+    pk64 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+// a * (s, s) + c : the scalar becomes an FFMA2 immediate / scalar operand
+__device__ __forceinline__ pk64 fma2s(pk64 a, float s, pk64 c)
+{
+    pk64 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(pk(s, s)), "l"(c));
+    return r;
+}
+
 __device__ __forceinline__ float2 cmul(float2 a, float2 b)
 {
     return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
@@ -28,8 +68,8 @@ __device__ __forceinline__ float2 cmul_conj(float2 a, float2 b)  // a * conj(b)
 {
     return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
 }
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return upk(add2(pk(a), pk(b))); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return upk(sub2(pk(a), pk(b))); }
 // multiply by -i (forward W_4) or +i (inverse)
 template <bool INV> __device__ __forceinline__ float2 rot90(float2 a)
 {
@@ -142,65 +182,67 @@ template <int R, bool INV> struct DftOddPrime {
     static __device__ __forceinline__ void run(float2 (&v)[R])
     {
         constexpr int H = (R - 1) / 2;
-        float2 a[H + 1], b[H + 1];
-        float2 x0 = v[0];
+        pk64 a[H + 1], b[H + 1];
+        const pk64 v0 = pk(v[0]);
+        pk64 x0 = v0;
 #pragma unroll
         for (int j = 1; j <= H; j++) {
-            a[j] = cadd(v[j], v[R - j]);
-            b[j] = csub(v[j], v[R - j]);
-            x0 = cadd(x0, a[j]);
+            const pk64 p = pk(v[j]), m = pk(v[R - j]);
+            a[j] = add2(p, m);
+            b[j] = sub2(p, m);
+            x0 = add2(x0, a[j]);
         }
-        const float2 v0 = v[0];
-        v[0] = x0;
+        v[0] = upk(x0);
 #pragma unroll
         for (int q = 1; q <= H; q++) {
-            float cr = v0.x, ci = v0.y, sr = 0.f, si = 0.f;
+            // c2 = v0 + sum_j a_j cos;  s2 = sum_j b_j sin  (packed re/im);  i*s2 = (-s2.y, s2.x)
+            pk64 c2 = v0, s2 = pk(0.f, 0.f);
 #pragma unroll
             for (int j = 1; j <= H; j++) {
                 const int k = (j * q) % R;
                 const float c = RT<R>::c(k);
                 const float s = INV ? RT<R>::s(k) : -RT<R>::s(k);  // Im of exp(-/+ i theta)
-                cr = fmaf(a[j].x, c, cr);
-                ci = fmaf(a[j].y, c, ci);
-                sr = fmaf(-b[j].y, s, sr);  // i*s*b = s*(-b.y, b.x)
-                si = fmaf(b[j].x, s, si);
+                c2 = fma2s(a[j], c, c2);
+                s2 = fma2s(b[j], s, s2);
             }
-            v[q] = make_float2(cr + sr, ci + si);
-            v[R - q] = make_float2(cr - sr, ci - si);
+            const float2 cc = upk(c2), ss = upk(s2);
+            v[q] = make_float2(cc.x - ss.y, cc.y + ss.x);
+            v[R - q] = make_float2(cc.x + ss.y, cc.y - ss.x);
         }
     }
 };
 // Same arithmetic as DftOddPrime::run, but every output is handed to `emit(q, X_q)` the moment it is
 // final instead of being written back into v[]: the a/b half-sums are the only long-lived registers, so
-// a radix-31 butterfly needs ~75 registers instead of ~130.
+// a radix-31 butterfly needs ~75 registers instead of ~130.  450 FFMA2 + 45 FADD2 + 60 FADD for R = 31
+// (900 FFMA + 150 FADD in scalar form).
 template <int R, bool INV, class Emit> __device__ __forceinline__ void dft_odd_prime_emit(float2 (&v)[R], Emit emit)
 {
     constexpr int H = (R - 1) / 2;
-    float2 a[H + 1], b[H + 1];
-    float2 x0 = v[0];
-    const float2 v0 = v[0];
+    pk64 a[H + 1], b[H + 1];
+    const pk64 v0 = pk(v[0]);
+    pk64 x0 = v0;
 #pragma unroll
     for (int j = 1; j <= H; j++) {
-        a[j] = cadd(v[j], v[R - j]);
-        b[j] = csub(v[j], v[R - j]);
-        x0 = cadd(x0, a[j]);
+        const pk64 p = pk(v[j]), m = pk(v[R - j]);
+        a[j] = add2(p, m);
+        b[j] = sub2(p, m);
+        x0 = add2(x0, a[j]);
     }
-    emit(0, x0);
+    emit(0, upk(x0));
 #pragma unroll
     for (int q = 1; q <= H; q++) {
-        float cr = v0.x, ci = v0.y, sr = 0.f, si = 0.f;
+        pk64 c2 = v0, s2 = pk(0.f, 0.f);
 #pragma unroll
         for (int j = 1; j <= H; j++) {
             const int k = (j * q) % R;
             const float c = RT<R>::c(k);
             const float s = INV ? RT<R>::s(k) : -RT<R>::s(k);
-            cr = fmaf(a[j].x, c, cr);
-            ci = fmaf(a[j].y, c, ci);
-            sr = fmaf(-b[j].y, s, sr);
-            si = fmaf(b[j].x, s, si);
+            c2 = fma2s(a[j], c, c2);
+            s2 = fma2s(b[j], s, s2);
         }
-        emit(q, make_float2(cr + sr, ci + si));
-        emit(R - q, make_float2(cr - sr, ci - si));
+        const float2 cc = upk(c2), ss = upk(s2);
+        emit(q, make_float2(cc.x - ss.y, cc.y + ss.x));
+        emit(R - q, make_float2(cc.x + ss.y, cc.y - ss.x));
     }
 }
 
@@ -270,6 +312,8 @@ template <int N_, int T_, int MINB_, int PAD_, int R0, int R1 = 1, int R2 = 1, i
     static constexpr int len(int s) { return s == 0 ? N : len(s - 1) / radix(s - 1); }
     static constexpr int sub(int s) { return len(s) / radix(s); }
     static constexpr int LINE = PAD ? N + (N >> PAD) + 1 : N;  // complex elements of shared memory
+    // inverse kernel: double-buffer the line if MINB CTAs x 2 lines still fit one SM's shared memory
+    static constexpr bool DB = (size_t)MINB_ * 2 * LINE * 8 + (size_t)MINB_ * 1024 <= 227 * 1024;
     static_assert(R0 * R1 * R2 * R3 * R4 * R5 == N, "radices must multiply to N");
     static_assert(NSTAGE >= 2, "need at least two stages");
     __device__ static __forceinline__ int phys(int i) { return PAD ? i + (i >> PAD) : i; }

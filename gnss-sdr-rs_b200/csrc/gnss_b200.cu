@@ -12,6 +12,7 @@
 #include "../../include/gnss_b200.h"
 #include "acq_kernels.cuh"
 #include "trk_kernels.cuh"
+#include "fine_doppler.cuh"
 
 namespace {
 
@@ -70,8 +71,22 @@ struct gb_handle {
     float* row_dev = nullptr;
     float last_acq_ms = 0.f;
 
+    // fine Doppler (N3)
+    float2* fine_x = nullptr;
+    size_t fine_x_cap = 0;
+    float2* fine_y = nullptr;
+    size_t fine_y_cap = 0;
+    int8_t* fine_codes = nullptr;
+    size_t fine_codes_cap = 0;
+    unsigned long long* fine_u64 = nullptr;  // code_phase[n] then best[n]
+    size_t fine_u64_cap = 0;
+    float2* fine_mean = nullptr;
+    float* fine_mag = nullptr;
+    size_t fine_mag_cap = 0;
+    float last_fine_ms = 0.f;
+
     // FFT facade
-    FftRes fft[16];
+    FftRes fft[32];
 
     // tracking
     int8_t* ca_table_dev = nullptr;
@@ -188,15 +203,19 @@ int fft_resources(gb_handle* h, int plan, int n, FftRes** out)
     return GB_OK;
 }
 
-// FP32 FMA throughput probe: 8 independent FMA chains per thread, 4096 iterations
-__global__ void fp32_peak_kernel(float* out, float a, float b)
+// FP32 FMA throughput probe: 8 independent FMA chains per thread; the loop body is unrolled 32x (256 FFMA per
+// counter update / branch) so loop overhead is < 1 % and the figure is the FFMA issue rate, not the loop's.
+__global__ void __launch_bounds__(256) fp32_peak_kernel(float* out, float a, float b, int iters)
 {
     float x0 = threadIdx.x, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f, x4 = x0 + 4.f, x5 = x0 + 5.f, x6 = x0 + 6.f,
           x7 = x0 + 7.f;
 #pragma unroll 1
-    for (int i = 0; i < 4096; i++) {
-        x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
-        x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 32; u++) {
+            x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+            x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+        }
     }
     const float s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
     if (s == 12345.678f) out[0] = s;
@@ -410,7 +429,8 @@ extern "C" int gb_destroy(gb_handle* h)
     cudaDeviceSynchronize();
     void* dev_ptrs[] = {h->fe_lut, h->fe_state, h->fe_stage, h->otw, h->acc_rows, h->spec, h->ring, h->i8_stage, h->tw, h->code_fft, h->tables, h->rot, h->chunk, h->codes_dev, h->cells_dev,
                         h->rows_dev, h->row_dev, h->ca_table_dev, h->ch_dev, h->corr_dev, h->ran_dev, h->lost_dev,
-                        h->hist_dev, h->trk_data, h->offs_dev};
+                        h->hist_dev, h->trk_data, h->offs_dev, h->fine_x, h->fine_y, h->fine_codes, h->fine_u64, h->fine_mean,
+                        h->fine_mag};
     for (void* p : dev_ptrs)
         if (p) cudaFree(p);
     for (auto& r : h->fft) {
@@ -1001,6 +1021,103 @@ extern "C" int gb_acq_bin_power(gb_handle* h, const gb_c32* iq, int K, int prn, 
     return GB_OK;
 }
 
+// ------------------------------------------------------------------ fine Doppler
+// finer_doppler, acquisition_bk.rs:215-302.  Device work in fine_doppler.cu; the frequency mapping (:250-253, :282-299)
+// is a handful of f32 operations per request and stays on the host, in the reference's order.
+static int fine_common(gb_handle* h, const float2* x_dev, uint64_t start, uint64_t mask, uint64_t n_long, float fs,
+                       int long_ms, int is_complex, const gb_fine_req* req, int n_req, const int8_t* codes1023,
+                       gb_fine_result* out, float* mag_out)
+{
+    if (!req || !out || n_req < 1 || long_ms < 2 || !(fs > 0.f)) return GB_EINVAL;
+    const size_t n_code = f32_as_usize(roundf(fs / (kCodeRate / 1023.0f)));   // :236-239
+    const size_t use = (size_t)(long_ms - 1) * n_code;                         // :240
+    if (use < 2) return GB_EINVAL;
+    int m = 0;
+    while (((size_t)1 << m) < use) m++;                                        // next_power_of_two, :249
+    if (m < 12 || m > 19) return GB_EUNSUPPORTED;                              // 4096 <= P2 <= 524288 samples
+    const int log_a = m / 2 > 8 ? 8 : m / 2, log_b = m - log_a;
+    const size_t P2 = (size_t)1 << m, M = P2 * 8;
+    std::vector<int8_t> codes((size_t)n_req * 1023);
+    std::vector<unsigned long long> cps(n_req);
+    for (int i = 0; i < n_req; i++) {
+        // the legacy slice samples_iq[code_phase..size_signal_use + code_phase] panics when it runs past the end (:258)
+        if ((uint64_t)req[i].code_phase + use > n_long) return GB_ERANGE;
+        cps[i] = req[i].code_phase;
+        if (codes1023) memcpy(&codes[(size_t)i * 1023], codes1023 + (size_t)i * 1023, 1023);
+        else {
+            if (req[i].prn < 1 || req[i].prn > 32) return GB_EINVAL;
+            ca_chips(req[i].prn, &codes[(size_t)i * 1023]);
+        }
+    }
+    int rc;
+    if ((rc = ensure(h, &h->fine_codes, &h->fine_codes_cap, codes.size()))) return rc;
+    if ((rc = ensure(h, &h->fine_u64, &h->fine_u64_cap, (size_t)2 * n_req))) return rc;
+    if ((rc = ensure(h, &h->fine_y, &h->fine_y_cap, (size_t)n_req * M))) return rc;
+    if (!h->fine_mean) CK(cudaMalloc((void**)&h->fine_mean, sizeof(float2)));
+    if (mag_out && (rc = ensure(h, &h->fine_mag, &h->fine_mag_cap, (size_t)n_req * M))) return rc;
+    CK(cudaMemcpyAsync(h->fine_codes, codes.data(), codes.size(), cudaMemcpyHostToDevice, h->s_acq));
+    CK(cudaMemcpyAsync(h->fine_u64, cps.data(), sizeof(unsigned long long) * n_req, cudaMemcpyHostToDevice, h->s_acq));
+    gb::FineArgs a;
+    a.x = x_dev; a.start = start; a.mask = mask; a.use = (unsigned)use; a.fs = fs; a.log_a = log_a; a.log_b = log_b;
+    a.codes = h->fine_codes; a.code_phase = h->fine_u64; a.mean = h->fine_mean; a.Y = h->fine_y;
+    a.best = h->fine_u64 + n_req; a.mag_out = mag_out ? h->fine_mag : nullptr;
+    CK(cudaEventRecord(h->ev_a0, h->s_acq));
+    CK(gb::fine_launch(a, n_req, x_dev, start, mask, n_long, h->s_acq));
+    CK(cudaEventRecord(h->ev_a1, h->s_acq));
+    std::vector<unsigned long long> best(n_req);
+    CK(cudaMemcpyAsync(best.data(), h->fine_u64 + n_req, sizeof(unsigned long long) * n_req, cudaMemcpyDeviceToHost, h->s_acq));
+    if (mag_out) CK(cudaMemcpyAsync(mag_out, h->fine_mag, sizeof(float) * (size_t)n_req * M, cudaMemcpyDeviceToHost, h->s_acq));
+    CK(cudaStreamSynchronize(h->s_acq));
+    cudaEventElapsedTime(&h->last_fine_ms, h->ev_a0, h->ev_a1);
+    const size_t one_side = f32_as_usize(ceilf(((float)M + 1.0f) / 2.0f));     // :250
+    for (int i = 0; i < n_req; i++) {
+        const uint32_t idx = 0xffffffffu - (uint32_t)(best[i] & 0xffffffffull);
+        const uint32_t mbits = (uint32_t)(best[i] >> 32);
+        gb_fine_result& r = out[i];
+        r.fft_size = (uint32_t)M;
+        r.idx = idx;
+        memcpy(&r.mag, &mbits, 4);
+        if (idx < one_side) {
+            const float bin = (float)idx * fs / (float)M;                       // :251-253
+            r.carrier_freq = (is_complex ? -1.0f : 1.0f) * bin;                 // :296-298
+            r.ref_defined = 1;
+        } else {
+            // the legacy reads fft_freq_bins[one_side] (out of bounds) and panics; this is the value its arithmetic
+            // would produce had the Vec been long enough (:283-295): idx' = idx - one_side, carrier = +bins(one_side - idx')
+            const size_t i2 = (size_t)idx - one_side;
+            r.carrier_freq = (float)(one_side - i2) * fs / (float)M;
+            r.ref_defined = 0;
+        }
+    }
+    return GB_OK;
+}
+
+extern "C" int gb_acq_fine_doppler(gb_handle* h, const gb_c32* long_samples, uint64_t n_long, float fs, int long_ms,
+                                   int is_complex, const gb_fine_req* req, int n_req, const int8_t* codes1023,
+                                   gb_fine_result* out, float* mag_out)
+{
+    if (!h || !long_samples || n_long < 1) return GB_EINVAL;
+    CK(cudaSetDevice(h->device));
+    int rc = ensure(h, &h->fine_x, &h->fine_x_cap, (size_t)n_long);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(h->fine_x, long_samples, n_long * sizeof(float2), cudaMemcpyHostToDevice, h->s_acq));
+    return fine_common(h, h->fine_x, 0, ~0ull, n_long, fs, long_ms, is_complex, req, n_req, codes1023, out, mag_out);
+}
+
+extern "C" int gb_acq_fine_doppler_ring(gb_handle* h, uint64_t start, uint64_t n_long, float fs, int long_ms, int is_complex,
+                                        const gb_fine_req* req, int n_req, const int8_t* codes1023, gb_fine_result* out)
+{
+    if (!h || n_long < 1) return GB_EINVAL;
+    CK(cudaSetDevice(h->device));
+    int rc = ring_range_ok(h, start, n_long);
+    if (rc) return rc;
+    CK(cudaStreamWaitEvent(h->s_acq, h->ev_copy, 0));
+    return fine_common(h, h->ring, start, h->ring_cap - 1, n_long, fs, long_ms, is_complex, req, n_req, codes1023, out,
+                       nullptr);
+}
+
+extern "C" float gb_acq_fine_last_kernel_ms(gb_handle* h) { return h ? h->last_fine_ms : 0.f; }
+
 extern "C" float gb_acq_last_kernel_ms(gb_handle* h) { return h ? h->last_acq_ms : 0.f; }
 
 // Measured FP32 (non-tensor) FMA throughput of this GPU, for the roofline denominator
@@ -1012,17 +1129,17 @@ extern "C" int gb_bench_fp32_tflops(gb_handle* h, float* tflops_out)
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
     float* d = nullptr;
     CK(cudaMalloc((void**)&d, 4));
-    const int blocks = sms * 8, threads = 256;
+    const int blocks = sms * 8, threads = 256, kIters = 1024;  // 8 resident CTAs per SM, ~2 ms per launch
     float best = 0.f;
     for (int rep = 0; rep < 6; rep++) {
         cudaEventRecord(h->ev_a0, h->s_acq);
-        fp32_peak_kernel<<<blocks, threads, 0, h->s_acq>>>(d, 1.0000001f, 1e-9f);
+        fp32_peak_kernel<<<blocks, threads, 0, h->s_acq>>>(d, 1.0000001f, 1e-9f, kIters);
         cudaEventRecord(h->ev_a1, h->s_acq);
         cudaError_t e = cudaStreamSynchronize(h->s_acq);
         if (e != cudaSuccess) { cudaFree(d); return fail(h, e, "fp32_peak_kernel"); }
         float ms = 0.f;
         cudaEventElapsedTime(&ms, h->ev_a0, h->ev_a1);
-        const double flops = 2.0 * 8.0 * 4096.0 * (double)blocks * threads;
+        const double flops = 2.0 * 8.0 * 32.0 * (double)kIters * (double)blocks * threads;
         const float tf = (float)(flops / (ms * 1e-3) / 1e12);
         if (rep > 0 && tf > best) best = tf;
     }

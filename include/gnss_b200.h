@@ -94,8 +94,9 @@ typedef struct {
     float peak;      /* max of the accumulated power over code phase (local_max, :195-202) */
     uint32_t argmax; /* first index attaining it (local_best_phase) */
     float sum8;      /* sum over the first 8*floor(N/8) bins (is_good_satellite's SIMD sum, :229-234) */
-    float peak2;     /* largest power outside +-samples_per_chip of argmax (legacy two-peak metric,
-                        acquisition_bk.rs:342-399); 0 if disabled */
+    float peak2;     /* legacy two-peak metric (acquisition_bk.rs:342-399): largest power over the slices the
+                        legacy searches around argmax (:371-390, bounds verbatim: [0,cp-spc) u [cp+spc,N), and the
+                        two wrap cases [cp+spc-1, N+cp-spc) / [cp+spc-N-1, cp-spc)); 0 if disabled */
 } gb_acq_cell;
 
 typedef struct {
@@ -161,6 +162,37 @@ int gb_acq_search_ring(gb_handle *h, uint64_t local_tail, int num_integrations, 
 int gb_acq_bin_power(gb_handle *h, const gb_c32 *iq, int num_integrations, int prn, int doppler_bin, float *power_out);
 /* device time of the last search's kernels in milliseconds (CUDA events on the acquisition stream) */
 float gb_acq_last_kernel_ms(gb_handle *h);
+
+/* ------------------------------------------------------------------ fine Doppler
+ * replaces finer_doppler (acquisition_bk.rs:215-302), the legacy sub-bin carrier estimate used at the
+ * acquisition -> tracking hand-over: long_ms (LONG_SAMPLES_LENGTH = 11) ms of samples, complex mean removed,
+ * (long_ms-1) ms starting at code_phase stripped of the C/A code, zero-padded to 8 * next_power_of_two samples,
+ * forward FFT, FIRST index of the largest magnitude.  The zero padding is never materialised (fine_doppler.cu).
+ * Frequency mapping as in the legacy (:282-299): idx below one_side = ceil((fft_size+1)/2) gives
+ * carrier_freq = (is_complex ? -1 : +1) * idx * fs / fft_size and ref_defined = 1.  For idx >= one_side the legacy
+ * indexes its fft_freq_bins Vec out of bounds and panics; ref_defined = 0 and carrier_freq is what its arithmetic
+ * would have produced.  code_phase + (long_ms-1)*N > n_long returns GB_ERANGE (the legacy slice panics).
+ * codes1023: n_req x 1023 chips (+-1), or NULL for GPS C/A selected by req[i].prn.
+ * Supported: 4096 <= next_power_of_two((long_ms-1)*N) <= 524288, else GB_EUNSUPPORTED. */
+typedef struct {
+    uint8_t prn;
+    uint8_t reserved[3];
+    uint32_t code_phase; /* samples, AcquisitionResult::code_phase */
+} gb_fine_req;
+typedef struct {
+    uint32_t fft_size;
+    uint32_t idx;        /* first index of the maximum magnitude */
+    float mag;           /* that magnitude (Complex::abs) */
+    float carrier_freq;
+    int32_t ref_defined;
+} gb_fine_result;
+/* mag_out (optional, diagnostics): n_req x fft_size magnitudes */
+int gb_acq_fine_doppler(gb_handle *h, const gb_c32 *long_samples, uint64_t n_long, float fs, int long_ms, int is_complex,
+                        const gb_fine_req *req, int n_req, const int8_t *codes1023, gb_fine_result *out, float *mag_out);
+/* same, on n_long samples of the device ring starting at absolute index start */
+int gb_acq_fine_doppler_ring(gb_handle *h, uint64_t start, uint64_t n_long, float fs, int long_ms, int is_complex,
+                             const gb_fine_req *req, int n_req, const int8_t *codes1023, gb_fine_result *out);
+float gb_acq_fine_last_kernel_ms(gb_handle *h);
 
 /* measured FP32 FMA throughput of the device (TFLOP/s): the roofline denominator for these kernels,
  * which are FP32-pipe / shared-memory bound, not HBM- or tensor-bound */

@@ -395,17 +395,25 @@ int go_acq_decide(const go_acq_cell *cells, const float *carr, int D, int prn, i
     return 0;
 }
 
-/* acquisition_bk.rs:342-399 restated for one power row: second peak outside +-samples_per_chip
- * (circular) of the first; ratio of amplitudes (norm), threshold 1.4 applied by the caller */
+/* acquisition_bk.rs:342-399 restated for one power row (the legacy works on magnitudes; the ordering is the same):
+ * first peak = global maximum, second peak = maximum over the legacy's slices (:371-390), bounds verbatim:
+ *   left = cp - spc, right = cp + spc
+ *   left < 1   : row[right-1 .. N+left)
+ *   right >= N : row[right-N-1 .. left)     (the lower bound underflows usize when right == N; clamped to 0 here)
+ *   otherwise  : row[0 .. left) ++ row[right .. N)
+ * returns first/second as amplitudes; the threshold (1.4) is applied by the caller */
 float go_two_peak_ratio(const float *power, int n, int spc, uint32_t *first, uint32_t *second)
 {
     float p1, p2 = 0.0f;
     uint32_t i1, i2 = 0;
     acq_argmax(power, n, &p1, &i1);
+    const int left = (int)i1 - spc, right = (int)i1 + spc;
     for (int i = 0; i < n; i++) {
-        int dist = abs(i - (int)i1);
-        if (n - dist < dist) dist = n - dist;
-        if (dist <= spc) continue;
+        int searched;
+        if (left < 1) searched = i >= right - 1 && i < n + left;
+        else if (right >= n) searched = i >= (right - n - 1 < 0 ? 0 : right - n - 1) && i < left;
+        else searched = i < left || i >= right;
+        if (!searched) continue;
         if (power[i] > p2) { p2 = power[i]; i2 = (uint32_t)i; }
     }
     if (first) *first = i1;
@@ -798,4 +806,62 @@ void go_nav_bit_sync(const float *prompt_i, int n_epochs, int stride, go_nav_syn
         }
         old_ip = ip;
     }
+}
+
+/* ------------------------------------------------------------------ fine Doppler (N3), acquisition_bk.rs:215-302 */
+int go_fine_doppler(const go_c32 *x, size_t n_long, const int8_t *code1023, size_t code_phase, float fs, int long_ms,
+                    int is_complex, go_fine_result *out, float *mag_out)
+{
+    memset(out, 0, sizeof(*out));
+    /* :234-235 mean = iter().sum::<Complex32>() / len as f32 (sequential f32) */
+    float sre = 0.0f, sim = 0.0f;
+    for (size_t i = 0; i < n_long; i++) { sre += x[i].re; sim += x[i].im; }
+    const float mre = sre / (float)n_long, mim = sim / (float)n_long;
+    const size_t n_code = f32_as_usize(roundf(fs / (GO_CA_CODE_RATE / (float)GO_CA_CODE_LEN)));   /* :236-239 */
+    const size_t use = (size_t)(long_ms - 1) * n_code;                                              /* :240 */
+    if (use == 0 || code_phase + use > n_long) return -1;
+    size_t p2 = 1;
+    while (p2 < use) p2 <<= 1;
+    const size_t fft_size = 8 * p2;                                                                  /* :249 */
+    go_c32 *buf = (go_c32 *)calloc(fft_size, sizeof(go_c32));
+    if (!buf) return -1;
+    for (size_t i = 0; i < use; i++) {
+        const size_t ind = f32_as_usize(floorf((float)i * GO_CA_CODE_RATE / fs)) % GO_CA_CODE_LEN;   /* :241-247 */
+        const float c = (float)code1023[ind];
+        /* (x - mean) * Complex32::new(c, 0): re = a*c - b*0, im = a*0 + b*c  (:265-268) */
+        const float a = x[code_phase + i].re - mre, b = x[code_phase + i].im - mim;
+        buf[i].re = a * c - b * 0.0f;
+        buf[i].im = a * 0.0f + b * c;
+    }
+    go_fft_plan *pl = go_fft_plan_new((int)fft_size, 0);
+    go_fft_process(pl, buf);
+    go_fft_plan_free(pl);
+    float mx = -INFINITY;
+    for (size_t k = 0; k < fft_size; k++) {
+        const float m = hypotf(buf[k].re, buf[k].im);                                                /* :274 */
+        if (mag_out) mag_out[k] = m;
+        buf[k].re = m;
+        mx = fmaxf(mx, m);                                                                           /* :276 */
+    }
+    size_t idx = 0;
+    while (idx < fft_size && buf[idx].re != mx) idx++;                                               /* :277-280 */
+    const size_t one_side = f32_as_usize(ceilf(((float)fft_size + 1.0f) / 2.0f));                    /* :250 */
+    out->fft_size = (uint32_t)fft_size;
+    out->idx = (uint32_t)idx;
+    out->mag = mx;
+    if (idx < one_side) {
+        const float bin = (float)idx * fs / (float)fft_size;                                         /* :251-253 */
+        out->carrier_freq = (is_complex ? -1.0f : 1.0f) * bin;                                       /* :296-298 */
+        out->ref_defined = 1;
+    } else {
+        float m2 = -INFINITY;
+        for (size_t k = one_side; k < fft_size; k++) m2 = fmaxf(m2, buf[k].re);
+        size_t i2 = 0;
+        while (buf[one_side + i2].re != m2) i2++;
+        const float bin = (float)(one_side - i2) * fs / (float)fft_size;                             /* :283-295 */
+        out->carrier_freq = bin;
+        out->ref_defined = 0;
+    }
+    free(buf);
+    return 0;
 }

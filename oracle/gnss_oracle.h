@@ -213,6 +213,30 @@ typedef struct {
 } go_nav_sync;
 void go_nav_bit_sync(const float *prompt_i, int n_epochs, int stride, go_nav_sync *st, int8_t *bits, int max_bits);
 
+/* ---- fine Doppler: finer_doppler, acquisition_bk.rs:215-302 ----
+ * long_samples: LONG_SAMPLES_LENGTH (11) ms of complex samples (the legacy takes i16 I/Q pairs and converts to f32,
+ * :223-233).  Steps, in the reference's f32 operation order: complex mean (sequential f32 sum / len) removed (:234-235);
+ * N = round(fs / (1.023e6/1023)); size_signal_use = (long_ms-1)*N (:240); code index
+ * floor(x as f32 * 1.023e6 / fs) as usize % 1023 (:241-247); fft_size = 8 * next_power_of_two(size_signal_use) (:249);
+ * carrier_sig = (samples[code_phase + x] - mean) * code1023[idx[x]] zero-padded (:259-271); forward FFT (rustfft Radix4,
+ * restated by go_fft); magnitude = Complex::abs = hypot (:274); max by f32::max then FIRST index equal to it (:276-280).
+ * Frequency mapping (:282-299): one_side = ceil((fft_size as f32 + 1)/2); bins[x] = x as f32 * fs / fft_size as f32;
+ *   idx <  one_side : carrier = (is_complex ? -1 : +1) * bins[idx]                       -> ref_defined = 1
+ *   idx >= one_side : the legacy indexes fft_freq_bins[one_side] (a Vec of length one_side) and PANICS (:283-287, and
+ *                     :297 for idx == one_side).  ref_defined = 0 and carrier = the value the code would have produced
+ *                     had the Vec been long enough: idx' = argmax over mag[one_side..] (:288-295),
+ *                     carrier = +bins(one_side - idx').
+ * Returns 0, or -1 if the recording is shorter than code_phase + size_signal_use (the legacy slice would panic). */
+typedef struct {
+    uint32_t fft_size;
+    uint32_t idx;          /* first index of the maximum magnitude over the whole spectrum */
+    float mag;             /* that magnitude */
+    float carrier_freq;
+    int32_t ref_defined;
+} go_fine_result;
+int go_fine_doppler(const go_c32 *long_samples, size_t n_long, const int8_t *code1023, size_t code_phase, float fs,
+                    int long_ms, int is_complex, go_fine_result *out, float *mag_out /* fft_size or NULL */);
+
 #ifdef __cplusplus
 }
 #endif

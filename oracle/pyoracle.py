@@ -53,6 +53,11 @@ class NavSync(C.Structure):
                 ("n_bits", C.c_int32), ("bit_sync_buff", C.c_uint32 * 20)]
 
 
+class FineResult(C.Structure):
+    _fields_ = [("fft_size", C.c_uint32), ("idx", C.c_uint32), ("mag", C.c_float), ("carrier_freq", C.c_float),
+                ("ref_defined", C.c_int32)]
+
+
 class AcqManager(C.Structure):
     _fields_ = [("mode", C.c_int)]
 
@@ -109,6 +114,7 @@ def lib():
         "go_nav_bit_sync": (None, [vp, i32, i32, vp, vp, i32]),
         "go_frontend_init": (None, [vp, f32, f32]),
         "go_frontend_process_block": (None, [vp, vp, sz]),
+        "go_fine_doppler": (i32, [vp, sz, vp, sz, f32, i32, i32, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -334,3 +340,22 @@ def nav_bit_sync(prompt_i, max_bits=4096):
     bits = np.zeros(max_bits, np.int8)
     lib().go_nav_bit_sync(_p(x), len(x), 1, C.byref(st), _p(bits), max_bits)
     return st, bits[:min(st.n_bits, max_bits)].copy()
+
+
+def fine_doppler(long_samples, code1023, code_phase, fs, long_ms=11, is_complex=True, want_mag=False):
+    """finer_doppler (acquisition_bk.rs:215-302) -> (FineResult, mag or None); None if the recording is too short."""
+    x = np.ascontiguousarray(long_samples, c32)
+    code = np.ascontiguousarray(code1023, np.int8)
+    res = FineResult()
+    mag = None
+    if want_mag:
+        n_code = int(round(fs / 1000.0))
+        p2 = 1
+        while p2 < (long_ms - 1) * n_code:
+            p2 <<= 1
+        mag = np.zeros(8 * p2, np.float32)
+    rc = lib().go_fine_doppler(_p(x), len(x), _p(code), int(code_phase), fs, int(long_ms), int(bool(is_complex)),
+                               C.byref(res), _p(mag) if want_mag else None)
+    if rc != 0:
+        return None, None
+    return res, mag

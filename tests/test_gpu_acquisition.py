@@ -205,10 +205,12 @@ def test_coherent_extension_matches_oracle(gpu, oracle, n, n_coh, K):
         assert abs(float(d[best]) - s["doppler"]) <= step
 
 
-def test_two_peak_metric(gpu, oracle):
+@pytest.mark.parametrize("code_phase", [1000, 2, 4, 4093, 4091])
+def test_two_peak_metric(gpu, oracle, code_phase):
+    """peak2 follows the legacy's slice bounds verbatim (acquisition_bk.rs:371-390), wrap cases included."""
     from gnss_sdr_rs_b200 import sdr_mock
     n, fs, K = 4096, 4.096e6, 2
-    sats = [{"prn": 9, "doppler": 0.0, "code_phase": 1000, "cn0_dbhz": 50.0}]
+    sats = [{"prn": 9, "doppler": 0.0, "code_phase": code_phase, "cn0_dbhz": 50.0}]
     x = sdr_mock.baseband(fs, K, sats, seed=3)
     carr, tabs = oracle.doppler_tables(0.0, np.array([0.0, 500.0], np.float32), fs, n)
     eng = _engine(gpu, n, fs)
@@ -225,6 +227,7 @@ def test_two_peak_metric(gpu, oracle):
             ratio = L.go_two_peak_ratio(row.ctypes.data_as(C.c_void_p), n, spc, None, None)
             got = np.sqrt(cells[prn - 1]["peak"][b] / cells[prn - 1]["peak2"][b])
             assert abs(got / ratio - 1) < REL
+    assert cells[8]["argmax"][0] == code_phase
     assert np.sqrt(cells[8]["peak"][0] / cells[8]["peak2"][0]) > 1.4  # acquisition_bk.rs threshold
 
 

@@ -354,3 +354,70 @@ def test_nav_bit_sync_against_python(oracle):
     assert out.tolist() == got and list(st.bit_sync_buff) == buff
     first = (st.sync_epoch - offset) // 20 + 1   # synchronisation is declared ON a bit edge: that bit is the first one out
     assert out.tolist()[:20] == bits[first:first + 20].tolist()
+
+
+# ------------------------------------------------------------------ N3: finer_doppler (acquisition_bk.rs:215-302)
+@pytest.mark.parametrize("fs,dopp", [(2.048e6, 1234.5), (4.092e6, -2771.0)])
+def test_fine_doppler_oracle_vs_numpy_f64(oracle, fs, dopp):
+    """The oracle's restatement against an independent NumPy f64 evaluation of the same steps (mean removal, f32 code
+    index, zero-padded 8x FFT, first arg-max) and the legacy frequency mapping, including the half where it panics."""
+    from gnss_sdr_rs_b200 import sdr_mock
+    n = int(round(fs / 1000.0))
+    cp = 345
+    x = sdr_mock.baseband(fs, 11, [{"prn": 12, "doppler": dopp, "code_phase": cp, "cn0_dbhz": 50.0}], seed=3)
+    code = sdr_mock.ca_code(12)
+    res, mag = oracle.fine_doppler(x, code, cp, fs, want_mag=True)
+    use = 10 * n
+    p2 = 1 << int(np.ceil(np.log2(use)))
+    assert res.fft_size == 8 * p2
+    idx = np.floor(np.arange(use, dtype=np.float32) * np.float32(1.023e6) / np.float32(fs)).astype(np.int64) % 1023
+    buf = np.zeros(8 * p2, np.complex128)
+    buf[:use] = (x.astype(np.complex128) - x.astype(np.complex128).mean())[cp:cp + use] * code[idx]
+    M = np.abs(np.fft.fft(buf))
+    assert np.abs(M - mag).max() <= 2e-6 * M.max()
+    assert int(M.argmax()) == res.idx
+    df = fs / res.fft_size
+    one_side = res.fft_size // 2 + 1
+    if dopp > 0:      # positive signal frequency: lower half, defined, sign flipped for complex input (:296-298)
+        assert res.ref_defined == 1 and res.idx < one_side
+        assert res.carrier_freq == -np.float32(np.float32(res.idx) * np.float32(fs) / np.float32(res.fft_size))
+        assert abs(res.carrier_freq + dopp) <= df
+    else:             # upper half: the legacy indexes fft_freq_bins out of bounds (:283-287)
+        assert res.ref_defined == 0 and res.idx >= one_side
+        assert abs(res.carrier_freq - (res.fft_size - res.idx + 2) * df) < 1e-3 * df + 1e-2
+    # too short a recording: the legacy slice would panic -> None
+    assert oracle.fine_doppler(x[:10 * n + cp - 1], code, cp, fs)[0] is None
+
+
+# ------------------------------------------------------------------ A7: two-peak window (acquisition_bk.rs:342-399)
+def _legacy_two_peaks(row, spc):
+    """Literal slicing of satellite_detection_two_peaks for one Doppler row (acquisition_bk.rs:367-395)."""
+    n = len(row)
+    cp = int(np.argmax(row))
+    left, right = cp - spc, cp + spc
+    if left < 1:
+        new = row[right - 1:n + left]
+    elif right >= n:
+        new = row[right - n - 1:left]
+    else:
+        new = np.concatenate([row[0:left], row[right:n]])
+    return cp, float(row[cp]), float(new.max())
+
+
+@pytest.mark.parametrize("cp", [0, 1, 3, 4, 5, 500, 1017, 1018, 1020, 1022])
+def test_two_peak_window_matches_legacy_slices(oracle, cp):
+    # cp + spc == N (here 1019) is left out: the legacy computes `right_index - N - 1` in usize and panics there
+    import ctypes as C
+    n, spc = 1023, 4
+    rng = np.random.default_rng(cp)
+    row = rng.uniform(1.0, 2.0, n).astype(np.float32)
+    row[cp] = 50.0
+    # plant decoys on both edges of the exclusion window so an off-by-one changes the answer
+    for off, v in ((-spc, 9.0), (spc - 1, 8.0), (spc, 7.0), (-spc - 1, 6.0), (spc - 2, 10.0)):
+        row[(cp + off) % n] = v
+    _, p1, p2 = _legacy_two_peaks(row, spc)
+    first, second = C.c_uint32(), C.c_uint32()
+    ratio = oracle.lib().go_two_peak_ratio(row.ctypes.data_as(C.c_void_p), n, spc, C.byref(first), C.byref(second))
+    assert first.value == cp
+    assert row[second.value] == np.float32(p2)
+    assert abs(ratio - np.sqrt(p1) / np.sqrt(p2)) < 1e-5
