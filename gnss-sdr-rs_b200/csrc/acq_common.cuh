@@ -9,21 +9,21 @@ namespace gb {
 //                 N      T  MINB PAD  radices (forward DIF order; odd radices last => no padding needed)
 using P1024 = Plan<1024, 64, 8, 4, 4, 16, 16>;
 using P2048 = Plan<2048, 128, 4, 4, 8, 16, 16>;
-using P4092 = Plan<4092, 160, 4, 0, 12, 11, 31>;
+using P4092 = PfaPlan<4092, 160, 4, 0, 12, 11, 31>;
 using P4096 = Plan<4096, 256, 2, 4, 16, 16, 16>;
-using P8184 = Plan<8184, 288, 1, 0, 8, 3, 11, 31>;
-using P16368 = Plan<16368, 544, 1, 0, 16, 3, 11, 31>;
+using P8184 = PfaPlan<8184, 288, 1, 0, 8, 3, 11, 31>;
+using P16368 = PfaPlan<16368, 544, 1, 0, 16, 3, 11, 31>;
 using P20000 = Plan<20000, 512, 1, 0, 8, 4, 25, 25>;
 
 // tuning variants of the headline plan (selected with the environment variable GB_ACQ_VARIANT=1..4)
-using P4092v1 = Plan<4092, 192, 3, 0, 12, 11, 31>;
-using P4092v2 = Plan<4092, 160, 3, 0, 12, 11, 31>;
+using P4092v1 = Plan<4092, 160, 4, 0, 12, 11, 31>;   // the Cooley-Tukey form of the default plan (A/B)
+using P4092v2 = PfaPlan<4092, 160, 3, 0, 12, 11, 31>;
 using P4092v3 = Plan<4092, 192, 2, 0, 12, 11, 31>;
 using P4092v4 = Plan<4092, 384, 1, 0, 12, 11, 31>;
-using P4092v5 = Plan<4092, 224, 3, 0, 12, 11, 31>;
-using P4092v6 = Plan<4092, 192, 4, 0, 12, 11, 31>;
-using P4092v7 = Plan<4092, 256, 3, 0, 12, 11, 31>;
-using P4092v8 = Plan<4092, 224, 4, 0, 12, 11, 31>;
+using P4092v5 = PfaPlan<4092, 192, 3, 0, 12, 11, 31>;
+using P4092v6 = PfaPlan<4092, 192, 4, 0, 12, 11, 31>;
+using P4092v7 = PfaPlan<4092, 160, 5, 0, 12, 11, 31>;
+using P4092v8 = PfaPlan<4092, 224, 3, 0, 12, 11, 31>;
 using P16368v1 = Plan<16368, 288, 1, 0, 16, 3, 11, 31>;
 using P16368v2 = Plan<16368, 416, 1, 0, 16, 3, 11, 31>;
 

@@ -59,16 +59,18 @@ __device__ __forceinline__ void stage0_wipe_forward(const AcqArgs& a, const floa
             Dft<G0::R, false>::run(v);
             line[P::phys(i)] = v[0];
 #pragma unroll
-            for (int q = 1; q < G0::R; q++) line[P::phys(i + q * G0::SUB)] = cmul(v[q], __ldg(&tw[(q - 1) * G0::SUB + i]));
+            for (int q = 1; q < G0::R; q++)
+                line[P::phys(i + q * G0::SUB)] = P::PFA ? v[q] : cmul(v[q], __ldg(&tw[(q - 1) * G0::SUB + i]));
         }
     }
 }
 
 // Row reduction shared by the fused and the shared-forward kernels: peak / first argmax / 8-lane sum
 // (Q2: only the first 8*floor(N/8) bins) / second peak outside +-spc of the first.
+// For prime-factor plans the code-phase index of line position l is npos[l] (the Ruritanian map).
 template <class P>
 __device__ __forceinline__ void reduce_row_to_cell(float (&acc)[StageGeo<P, 0>::ITERS][StageGeo<P, 0>::R], float2* line,
-                                                   int spc, gb_acq_cell* out)
+                                                   int spc, gb_acq_cell* out, const int* __restrict__ npos)
 {
     using G0 = StageGeo<P, 0>;
     constexpr int N = P::N;
@@ -84,7 +86,7 @@ __device__ __forceinline__ void reduce_row_to_cell(float (&acc)[StageGeo<P, 0>::
         if (G0::NB % P::T == 0 || i < G0::NB) {
 #pragma unroll
             for (int j = 0; j < G0::R; j++) {
-                const int n = i + j * G0::SUB;
+                const int n = P::PFA ? __ldg(&npos[i + j * G0::SUB]) : i + j * G0::SUB;
                 const float v = acc[it][j];
                 PeakIdx c;
                 c.v = v;
@@ -131,7 +133,7 @@ __device__ __forceinline__ void reduce_row_to_cell(float (&acc)[StageGeo<P, 0>::
             if (G0::NB % P::T == 0 || i < G0::NB) {
 #pragma unroll
                 for (int j = 0; j < G0::R; j++) {
-                    const int n = i + j * G0::SUB;
+                    const int n = P::PFA ? __ldg(&npos[i + j * G0::SUB]) : i + j * G0::SUB;
                     if (two_peak_searched(n, (int)arg, spc, N)) p2 = fmaxf(p2, acc[it][j]);
                 }
             }
@@ -171,7 +173,10 @@ __device__ __forceinline__ void final_stage_accumulate(const float2* __restrict_
             float2 v[G0::R];
             v[0] = line[P::phys(i)];
 #pragma unroll
-            for (int q = 1; q < G0::R; q++) v[q] = cmul_conj(line[P::phys(i + q * G0::SUB)], __ldg(&tw[(q - 1) * G0::SUB + i]));
+            for (int q = 1; q < G0::R; q++) {
+                const float2 u = line[P::phys(i + q * G0::SUB)];
+                v[q] = P::PFA ? u : cmul_conj(u, __ldg(&tw[(q - 1) * G0::SUB + i]));
+            }
             Dft<G0::R, true>::run(v);
 #pragma unroll
             for (int j = 0; j < G0::R; j++) acc[it][j] += v[j].x * v[j].x + v[j].y * v[j].y;
@@ -235,12 +240,12 @@ template <class P, bool WANT_ROW> __global__ void __launch_bounds__(P::T, P::MIN
             const int i = threadIdx.x + it * P::T;
             if (G0::NB % P::T == 0 || i < G0::NB)
 #pragma unroll
-                for (int j = 0; j < G0::R; j++) a.row_out[i + j * G0::SUB] = acc[it][j];
+                for (int j = 0; j < G0::R; j++) a.row_out[P::PFA ? a.npos[i + j * G0::SUB] : i + j * G0::SUB] = acc[it][j];
         }
         return;
     }
 
-    reduce_row_to_cell<P>(acc, line, a.spc, &a.cells[(size_t)row * a.D + d]);
+    reduce_row_to_cell<P>(acc, line, a.spc, &a.cells[(size_t)row * a.D + d], a.npos);
 }
 
 // ------------------------------------------------------------------ shared-forward chain
@@ -320,7 +325,7 @@ template <class P, bool DB> __global__ void __launch_bounds__(P::T, P::MINB) acq
         if (!DB) __syncthreads();
     }
     if (DB) __syncthreads();  // reduce_row_to_cell reuses the line as scratch
-    reduce_row_to_cell<P>(acc, smem_line, a.spc, &a.cells[(size_t)row * a.D + a.d_lo + dl]);
+    reduce_row_to_cell<P>(acc, smem_line, a.spc, &a.cells[(size_t)row * a.D + a.d_lo + dl], a.npos);
 }
 
 // ------------------------------------------------------------------ code spectra (AcquisitionWorker::new, :133-138)
@@ -328,7 +333,8 @@ template <class P, bool DB> __global__ void __launch_bounds__(P::T, P::MINB) acq
 // ([q][b] for the last radix) so the fused middle stage reads it coalesced.
 template <class P> __global__ void __launch_bounds__(P::T) code_fft_kernel(const int8_t* __restrict__ codes,
                                                                            float2* __restrict__ code_fft,
-                                                                           const float2* __restrict__ tw)
+                                                                           const float2* __restrict__ tw,
+                                                                           const int* __restrict__ npos)
 {
     extern __shared__ float2 line[];
     constexpr int LASTS = P::NSTAGE - 1;
@@ -342,11 +348,13 @@ template <class P> __global__ void __launch_bounds__(P::T) code_fft_kernel(const
         if (G0::NB % P::T == 0 || i < G0::NB) {
             float2 v[G0::R];
 #pragma unroll
-            for (int j = 0; j < G0::R; j++) v[j] = make_float2((float)c[i + j * G0::SUB], 0.f);
+            for (int j = 0; j < G0::R; j++)
+                v[j] = make_float2((float)c[P::PFA ? npos[i + j * G0::SUB] : i + j * G0::SUB], 0.f);
             Dft<G0::R, false>::run(v);
             line[P::phys(i)] = v[0];
 #pragma unroll
-            for (int q = 1; q < G0::R; q++) line[P::phys(i + q * G0::SUB)] = cmul(v[q], __ldg(&tw[(q - 1) * G0::SUB + i]));
+            for (int q = 1; q < G0::R; q++)
+                line[P::phys(i + q * G0::SUB)] = P::PFA ? v[q] : cmul(v[q], __ldg(&tw[(q - 1) * G0::SUB + i]));
         }
     }
     __syncthreads();
@@ -382,7 +390,7 @@ template <class P, bool INV> __global__ void __launch_bounds__(P::T) fft_c2c_ker
             float2 v[G0::R];
 #pragma unroll
             for (int j = 0; j < G0::R; j++) {
-                const size_t idx = boff + i + j * G0::SUB;
+                const size_t idx = boff + (P::PFA ? a.npos[i + j * G0::SUB] : i + j * G0::SUB);
                 v[j] = a.real_in ? make_float2(reinterpret_cast<const float*>(a.in)[idx], 0.f)
                                  : reinterpret_cast<const float2*>(a.in)[idx];
             }
@@ -390,8 +398,12 @@ template <class P, bool INV> __global__ void __launch_bounds__(P::T) fft_c2c_ker
             line[P::phys(i)] = v[0];
 #pragma unroll
             for (int q = 1; q < G0::R; q++) {
-                const float2 t = __ldg(&tw[(q - 1) * G0::SUB + i]);
-                line[P::phys(i + q * G0::SUB)] = INV ? cmul_conj(v[q], t) : cmul(v[q], t);
+                if (P::PFA) {
+                    line[P::phys(i + q * G0::SUB)] = v[q];
+                } else {
+                    const float2 t = __ldg(&tw[(q - 1) * G0::SUB + i]);
+                    line[P::phys(i + q * G0::SUB)] = INV ? cmul_conj(v[q], t) : cmul(v[q], t);
+                }
             }
         }
     }
@@ -429,6 +441,26 @@ __global__ void doppler_table_kernel(const float* __restrict__ steps, int n, flo
         const float phase = __fmul_rn((float)i, step);
         tables[(size_t)blockIdx.y * n + i] = make_float2(cosf(phase), -sinf(phase));
     }
+}
+
+// ------------------------------------------------------------------ prime-factor plans: line-order permutations
+// dst[b * n + l] = src[(start + b * n + npos[l]) & mask]: IQ blocks (from the ring or an uploaded chunk) and the
+// wipe-off tables are put into line order once, so every kernel's global access stays coalesced.
+__global__ void permute_blocks_kernel(const float2* __restrict__ src, unsigned long long start, unsigned long long mask,
+                                      const int* __restrict__ npos, int n, float2* __restrict__ dst)
+{
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l < n) {
+        const unsigned long long b = blockIdx.y;
+        dst[b * n + l] = src[(start + b * n + (unsigned long long)__ldg(&npos[l])) & mask];
+    }
+}
+cudaError_t acq_launch_permute(const float2* src, unsigned long long start, unsigned long long mask, const int* npos, int n,
+                               int n_blocks, float2* dst, cudaStream_t st)
+{
+    dim3 grid((n + 255) / 256, n_blocks);
+    permute_blocks_kernel<<<grid, 256, 0, st>>>(src, start, mask, npos, n, dst);
+    return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------ host-side dispatch
@@ -470,6 +502,16 @@ int acq_plan_radices(int plan, int* radices)
     switch (plan) {
 #define X(i, P) \
     case i: return plan_radices<P>(radices);
+        GB_FOR_EACH_PLAN(X)
+#undef X
+    }
+    return 0;
+}
+int acq_plan_is_pfa(int plan)
+{
+    switch (plan) {
+#define X(i, P) \
+    case i: return P::PFA ? 1 : 0;
         GB_FOR_EACH_PLAN(X)
 #undef X
     }
@@ -543,12 +585,12 @@ template <class P> static cudaError_t launch_row(const AcqArgs& a, cudaStream_t 
     return cudaGetLastError();
 }
 template <class P> static cudaError_t launch_code_fft(const int8_t* codes, int n_prn, float2* code_fft, const float2* tw,
-                                                     cudaStream_t st)
+                                                     const int* npos, cudaStream_t st)
 {
     const size_t smem = plan_smem<P>();
     cudaError_t e = set_smem(code_fft_kernel<P>, smem);
     if (e != cudaSuccess) return e;
-    code_fft_kernel<P><<<n_prn, P::T, smem, st>>>(codes, code_fft, tw);
+    code_fft_kernel<P><<<n_prn, P::T, smem, st>>>(codes, code_fft, tw, npos);
     return cudaGetLastError();
 }
 template <class P> static cudaError_t launch_fft(int inverse, const FftArgs& a, int batch, cudaStream_t st)
@@ -596,11 +638,11 @@ cudaError_t acq_launch_row(int plan, const AcqArgs& a, cudaStream_t st)
     return cudaErrorInvalidValue;
 }
 cudaError_t acq_launch_code_fft(int plan, const int8_t* codes, int n_prn, float2* code_fft, const float2* tw,
-                                cudaStream_t st)
+                                const int* npos, cudaStream_t st)
 {
     switch (plan) {
 #define X(i, P) \
-    case i: return launch_code_fft<P>(codes, n_prn, code_fft, tw, st);
+    case i: return launch_code_fft<P>(codes, n_prn, code_fft, tw, npos, st);
         GB_FOR_EACH_PLAN(X)
 #undef X
     }

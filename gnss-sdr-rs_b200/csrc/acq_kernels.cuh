@@ -23,6 +23,7 @@ struct AcqArgs {
     int d0;                  // Doppler bin for row_out
     float2* spec;            // shared-forward chain: n_d x n_groups x N scrambled spectra (scratch)
     int d_lo;                // shared-forward chain: first Doppler bin of this slab
+    const int* npos;         // prime-factor plans: code-phase index n(l) of line position l (else unused)
     const float2* otw;       // cluster plans: outer twiddles W_N^(i q), layout [q-1][i]
     float* acc_rows;         // cluster plans: (n_active*D) x N accumulated power rows (scratch)
 };
@@ -32,6 +33,7 @@ struct FftArgs {
     void* out;               // float2 (or float if power_out) batch x n_out
     const float2* tw;
     const int* freq_of_pos;  // scrambled position -> natural frequency index
+    const int* npos;         // prime-factor plans: input index of line position l (else unused)
     int real_in, power_out, n_out;
 };
 
@@ -40,6 +42,7 @@ int acq_plan_sizes(int* sizes, int cap);      // list of planned sizes
 int acq_plan_radices(int plan, int* radices); // returns number of stages
 int acq_plan_threads(int plan);
 int acq_plan_twiddles(int plan);             // length of the per-stage twiddle buffer ([stage][q-1][i])
+int acq_plan_is_pfa(int plan);               // 1: Good-Thomas prime-factor plan (inputs in line order, see PfaPlan)
 size_t acq_plan_smem(int plan);
 
 cudaError_t acq_launch_search(int plan, const AcqArgs& a, cudaStream_t st);
@@ -47,7 +50,10 @@ cudaError_t acq_launch_search(int plan, const AcqArgs& a, cudaStream_t st);
 cudaError_t acq_launch_shared(int plan, const AcqArgs& a, int n_d, cudaStream_t st);
 cudaError_t acq_launch_row(int plan, const AcqArgs& a, cudaStream_t st);
 cudaError_t acq_launch_code_fft(int plan, const int8_t* codes, int n_prn, float2* code_fft, const float2* tw,
-                                cudaStream_t st);
+                                const int* npos, cudaStream_t st);
+// prime-factor plans: dst[b*n + l] = src[(start + b*n + npos[l]) & mask] for b < n_blocks
+cudaError_t acq_launch_permute(const float2* src, unsigned long long start, unsigned long long mask, const int* npos, int n,
+                               int n_blocks, float2* dst, cudaStream_t st);
 cudaError_t acq_launch_fft(int plan, int inverse, const FftArgs& a, int batch, cudaStream_t st);
 // steps_dev[d] = 2*pi*(f_if+f_d)/fs (f32, host-evaluated in the reference's order)
 cudaError_t acq_launch_doppler_tables(const float* steps_dev, int D, int n, float2* tables, cudaStream_t st);

@@ -317,6 +317,28 @@ template <int N_, int T_, int MINB_, int PAD_, int R0, int R1 = 1, int R2 = 1, i
     static_assert(R0 * R1 * R2 * R3 * R4 * R5 == N, "radices must multiply to N");
     static_assert(NSTAGE >= 2, "need at least two stages");
     __device__ static __forceinline__ int phys(int i) { return PAD ? i + (i >> PAD) : i; }
+    // Cooley-Tukey (inter-stage twiddles) unless overridden by PfaPlan
+    static constexpr bool PFA = false;
+};
+
+// Good-Thomas prime-factor plan: the stage radices are pairwise coprime, so with the index maps
+//   time      n(l) = sum_s n_s (N / R_s)                      mod N   (Ruritanian)
+//   frequency k(l) = sum_s k_s (N / R_s) ((N / R_s)^-1 mod R_s) mod N  (CRT)
+// over the digits l = sum_s d_s SUB_s of a line position, W_N^(n k) = prod_s W_(R_s)^(n_s k_s): the transform is a
+// plain multi-dimensional DFT and NO inter-stage twiddle exists (no twiddle loads, no complex multiplies between
+// stages).  The same stages, butterflies and shared-memory access pattern as the Cooley-Tukey plan; the maps appear
+// only where samples enter (the host pre-permutes IQ blocks, wipe-off tables and codes into line order, `npos`) and
+// where a code-phase index leaves (reduce_row_to_cell reads n(l)).  The circular correlation is computed in the
+// digit domain, which n(l) maps isomorphically onto Z_N, so the result is the same correlation, sample for sample.
+constexpr int plan_gcd(int a, int b) { return b == 0 ? a : plan_gcd(b, a % b); }
+template <int N_, int T_, int MINB_, int PAD_, int R0, int R1 = 1, int R2 = 1, int R3 = 1, int R4 = 1, int R5 = 1>
+struct PfaPlan : Plan<N_, T_, MINB_, PAD_, R0, R1, R2, R3, R4, R5> {
+    static constexpr bool PFA = true;
+    static_assert(plan_gcd(R0, R1) == 1 && plan_gcd(R0, R2) == 1 && plan_gcd(R0, R3) == 1 && plan_gcd(R0, R4) == 1 &&
+                      plan_gcd(R0, R5) == 1 && plan_gcd(R1, R2) == 1 && plan_gcd(R1, R3) == 1 && plan_gcd(R1, R4) == 1 &&
+                      plan_gcd(R1, R5) == 1 && plan_gcd(R2, R3) == 1 && plan_gcd(R2, R4) == 1 && plan_gcd(R2, R5) == 1 &&
+                      plan_gcd(R3, R4) == 1 && plan_gcd(R3, R5) == 1 && plan_gcd(R4, R5) == 1,
+                  "prime-factor plans need pairwise coprime radices");
 };
 
 // ------------------------------------------------------------------ stage workers
@@ -354,8 +376,8 @@ template <class P, int S, bool INV> __device__ __forceinline__ void dif_stage(fl
             s[P::phys(base)] = v[0];
 #pragma unroll
             for (int q = 1; q < G::R; q++) {
-                if (G::SUB == 1) {
-                    s[P::phys(base + q)] = v[q];
+                if (G::SUB == 1 || P::PFA) {
+                    s[P::phys(base + q * G::SUB)] = v[q];
                 } else {
                     const float2 w = __ldg(&tw[G::TWOFF + (q - 1) * G::SUB + i]);
                     s[P::phys(base + q * G::SUB)] = INV ? cmul_conj(v[q], w) : cmul(v[q], w);
@@ -380,7 +402,7 @@ template <class P, int S, bool INV> __device__ __forceinline__ void dit_stage(fl
 #pragma unroll
             for (int q = 1; q < G::R; q++) {
                 const float2 u = s[P::phys(base + q * G::SUB)];
-                if (G::SUB == 1) {
+                if (G::SUB == 1 || P::PFA) {
                     v[q] = u;
                 } else {
                     const float2 w = __ldg(&tw[G::TWOFF + (q - 1) * G::SUB + i]);

@@ -23,6 +23,7 @@ const size_t kStageSamples = (size_t)1 << 19;  // 4 MiB per pinned staging slot
 struct FftRes {
     float2* tw = nullptr;
     int* fop = nullptr;
+    int* npos = nullptr;  // prime-factor plans: input index of line position l
 };
 
 }  // namespace
@@ -62,6 +63,11 @@ struct gb_handle {
     size_t acc_cap = 0;
     float fs = 0.f, threshold = 7.0f;
     float2 *tw = nullptr, *code_fft = nullptr, *tables = nullptr, *rot = nullptr, *chunk = nullptr;
+    // prime-factor plans: wipe-off tables and IQ blocks in line order (PfaPlan, fft_smem.cuh)
+    bool pfa = false;
+    const int* npos = nullptr;
+    float2 *tables_perm = nullptr, *iq_perm = nullptr;
+    size_t tables_perm_cap = 0, iq_perm_cap = 0;
     int8_t* codes_dev = nullptr;
     size_t chunk_cap = 0, tables_cap = 0, rot_cap = 0;
     std::vector<float> carr;
@@ -193,7 +199,37 @@ int fft_resources(gb_handle* h, int plan, int n, FftRes** out)
         }
         if ((int)tw.size() != gb::acq_plan_twiddles(plan)) return GB_EINVAL;
         std::vector<int> fop(n);
-        for (int k = 0; k < n; k++) fop[scrambled_pos(k, n, radix, ns)] = k;
+        if (gb::acq_plan_is_pfa(plan)) {
+            // Good-Thomas maps over the digits d_s = (l / SUB_s) % R_s of a line position l (SUB_s = n / (R_0..R_s)):
+            //   input   n(l) = sum_s d_s (n/R_s)                       mod n   (Ruritanian)
+            //   output  k(l) = sum_s d_s (n/R_s) ((n/R_s)^-1 mod R_s)  mod n   (CRT: k = d_s mod R_s)
+            std::vector<int> npos(n);
+            long long cin[8], cout[8];
+            int sub[8];
+            for (int s = 0, L = n; s < ns; s++) {
+                const int rs = radix[s], m = n / rs;
+                sub[s] = L / rs;
+                L = sub[s];
+                int inv = 1;
+                while (((long long)(m % rs) * inv) % rs != 1) inv++;
+                cin[s] = m;
+                cout[s] = ((long long)m * inv) % n;
+            }
+            for (int l = 0; l < n; l++) {
+                long long ni = 0, ko = 0;
+                for (int s = 0; s < ns; s++) {
+                    const int d = (l / sub[s]) % radix[s];
+                    ni += d * cin[s];
+                    ko += d * cout[s];
+                }
+                npos[l] = (int)(ni % n);
+                fop[l] = (int)(ko % n);
+            }
+            CK(cudaMalloc((void**)&r.npos, sizeof(int) * n));
+            CK(cudaMemcpy(r.npos, npos.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
+        } else {
+            for (int k = 0; k < n; k++) fop[scrambled_pos(k, n, radix, ns)] = k;
+        }
         CK(cudaMalloc((void**)&r.tw, sizeof(float2) * tw.size()));
         CK(cudaMalloc((void**)&r.fop, sizeof(int) * n));
         CK(cudaMemcpy(r.tw, tw.data(), sizeof(float2) * tw.size(), cudaMemcpyHostToDevice));
@@ -430,12 +466,13 @@ extern "C" int gb_destroy(gb_handle* h)
     void* dev_ptrs[] = {h->fe_lut, h->fe_state, h->fe_stage, h->otw, h->acc_rows, h->spec, h->ring, h->i8_stage, h->tw, h->code_fft, h->tables, h->rot, h->chunk, h->codes_dev, h->cells_dev,
                         h->rows_dev, h->row_dev, h->ca_table_dev, h->ch_dev, h->corr_dev, h->ran_dev, h->lost_dev,
                         h->hist_dev, h->trk_data, h->offs_dev, h->fine_x, h->fine_y, h->fine_codes, h->fine_u64, h->fine_mean,
-                        h->fine_mag};
+                        h->fine_mag, h->tables_perm, h->iq_perm};
     for (void* p : dev_ptrs)
         if (p) cudaFree(p);
     for (auto& r : h->fft) {
         if (r.tw) cudaFree(r.tw);
         if (r.fop) cudaFree(r.fop);
+        if (r.npos) cudaFree(r.npos);
     }
     for (int s = 0; s < 2; s++) {
         if (h->pin_stage[s]) cudaFreeHost(h->pin_stage[s]);
@@ -681,17 +718,32 @@ extern "C" int gb_acq_configure(gb_handle* h, int fft_size, float fs, int n_prn,
     CK(cudaMalloc((void**)&h->row_dev, sizeof(float) * fft_size));
     CK(cudaMemcpyAsync(h->codes_dev, codes, total, cudaMemcpyHostToDevice, h->s_acq));
     if (cluster) CK(gb::acq_cluster_launch_code_fft(h->codes_dev, n_prn, h->code_fft, fr->tw, h->otw, h->s_acq));
-    else CK(gb::acq_launch_code_fft(plan, h->codes_dev, n_prn, h->code_fft, fr->tw, h->s_acq));
+    else CK(gb::acq_launch_code_fft(plan, h->codes_dev, n_prn, h->code_fft, fr->tw, fr->npos, h->s_acq));
     CK(cudaStreamSynchronize(h->s_acq));
     h->cluster = cluster;
     h->plan = plan; h->N = fft_size; h->n_prn = n_prn; h->fs = fs; h->tw = fr->tw;
+    h->pfa = !cluster && gb::acq_plan_is_pfa(plan) != 0;
+    h->npos = h->pfa ? fr->npos : nullptr;
     h->D = 0; h->n_coh = 1;
     h->carr.clear();
     return GB_OK;
 }
 
+// prime-factor plans: keep a copy of the wipe-off tables in line order (tables_perm[d][l] = tables[d][n(l)])
+static int permute_tables(gb_handle* h)
+{
+    if (!h->pfa || h->D == 0) return GB_OK;
+    int rc = ensure(h, &h->tables_perm, &h->tables_perm_cap, (size_t)h->D * h->N);
+    if (rc) return rc;
+    CK(gb::acq_launch_permute(h->tables, 0, ~0ull, h->npos, h->N, h->D, h->tables_perm, h->s_acq));
+    CK(cudaStreamSynchronize(h->s_acq));
+    return GB_OK;
+}
+
 static int upload_rotators(gb_handle* h)
 {
+    int prc = permute_tables(h);
+    if (prc) return prc;
     if (h->n_coh <= 1 || h->D == 0) return GB_OK;
     // rot[d][c] = exp(-j 2 pi carr_d c N / fs), f64-evaluated
     std::vector<float2> rot((size_t)h->D * h->n_coh);
@@ -794,6 +846,16 @@ static int build_rows(gb_handle* h, uint32_t prn_mask, const uint8_t* enable)
     return n;
 }
 
+// prime-factor plans: put the K IQ blocks into line order (inside the timed region) and point the kernels at the
+// permuted copies; the kernels' global reads then stay as coalesced as in the Cooley-Tukey plans
+static cudaError_t pfa_inputs(gb_handle* h, gb::AcqArgs& a, int K)
+{
+    cudaError_t e = gb::acq_launch_permute(a.iq, a.iq_start, a.iq_mask, h->npos, h->N, K, h->iq_perm, h->s_acq);
+    a.iq = h->iq_perm; a.iq_start = 0; a.iq_mask = ~0ull;
+    a.tables = h->tables_perm;
+    return e;
+}
+
 static int search_cells(gb_handle* h, const float2* iq_dev, uint64_t start, uint64_t mask, int K, uint32_t prn_mask,
                         const uint8_t* enable, gb_acq_cell* cells_out)
 {
@@ -819,7 +881,11 @@ static int search_cells(gb_handle* h, const float2* iq_dev, uint64_t start, uint
         a.rows = h->rows_dev;
         a.D = h->D; a.K = K; a.n_coh = h->n_coh; a.n_active = n_active; a.spc = h->spc;
         a.cells = h->cells_dev; a.row_out = nullptr; a.d0 = 0; a.spec = nullptr; a.d_lo = 0;
-        a.otw = h->otw; a.acc_rows = nullptr;
+        a.otw = h->otw; a.acc_rows = nullptr; a.npos = h->npos;
+        if (h->pfa) {
+            int rc = ensure(h, &h->iq_perm, &h->iq_perm_cap, (size_t)K * h->N);
+            if (rc) return rc;
+        }
         if (h->cluster) {
             if (h->n_coh != 1) return GB_EUNSUPPORTED;
             int rc = ensure(h, &h->acc_rows, &h->acc_cap, (size_t)n_active * h->D * h->N);
@@ -838,6 +904,7 @@ static int search_cells(gb_handle* h, const float2* iq_dev, uint64_t start, uint
             if (rc) return rc;
             a.spec = h->spec;
             CK(cudaEventRecord(h->ev_a0, h->s_acq));
+            if (h->pfa) CK(pfa_inputs(h, a, K));
             for (int d_lo = 0; d_lo < h->D; d_lo += (int)slab) {
                 a.d_lo = d_lo;
                 const int n_d = (h->D - d_lo) < (int)slab ? (h->D - d_lo) : (int)slab;
@@ -846,6 +913,7 @@ static int search_cells(gb_handle* h, const float2* iq_dev, uint64_t start, uint
             CK(cudaEventRecord(h->ev_a1, h->s_acq));
         } else {
             CK(cudaEventRecord(h->ev_a0, h->s_acq));
+            if (h->pfa) CK(pfa_inputs(h, a, K));
             CK(gb::acq_launch_search(h->plan, a, h->s_acq));
             CK(cudaEventRecord(h->ev_a1, h->s_acq));
         }
@@ -993,7 +1061,12 @@ extern "C" int gb_acq_bin_power(gb_handle* h, const gb_c32* iq, int K, int prn, 
     a.rows = h->rows_dev;
     a.D = h->D; a.K = K; a.n_coh = h->n_coh; a.n_active = 1; a.spc = 0;
     a.cells = nullptr; a.row_out = h->row_dev; a.d0 = doppler_bin; a.spec = nullptr; a.d_lo = 0;
-    a.otw = h->otw; a.acc_rows = nullptr;
+    a.otw = h->otw; a.acc_rows = nullptr; a.npos = h->npos;
+    if (h->pfa) {
+        rc = ensure(h, &h->iq_perm, &h->iq_perm_cap, (size_t)K * h->N);
+        if (rc) return rc;
+        CK(pfa_inputs(h, a, K));
+    }
     if (h->cluster) {
         // one (prn, bin) cell row: the cluster kernel leaves the accumulated power row in acc_rows
         if (h->n_coh != 1) return GB_EUNSUPPORTED;
@@ -1166,7 +1239,7 @@ static int fft_common(gb_handle* h, int n, int inverse, const void* in, void* ou
     cudaError_t e = cudaMalloc(&dout, out_bytes);
     if (e != cudaSuccess) { cudaFree(din); return fail(h, e, "cudaMalloc"); }
     gb::FftArgs a;
-    a.in = din; a.out = dout; a.tw = fr->tw; a.freq_of_pos = fr->fop;
+    a.in = din; a.out = dout; a.tw = fr->tw; a.freq_of_pos = fr->fop; a.npos = fr->npos;
     a.real_in = real_in; a.power_out = power_out; a.n_out = n_out;
     e = cudaMemcpyAsync(din, in, in_bytes, cudaMemcpyHostToDevice, h->s_acq);
     if (e == cudaSuccess) e = gb::acq_launch_fft(plan, inverse, a, batch, h->s_acq);
