@@ -11,6 +11,8 @@
 //   is inside one CTA, channels are independent => no inter-CTA communication at all).
 #include "trk_kernels.cuh"
 
+#include <stdlib.h>
+
 namespace gb {
 
 static __device__ __constant__ float kTwoPi = 6.28318530717958647692f;  // 2.0 * std::f32::consts::PI
@@ -52,6 +54,26 @@ template <int MODE> __device__ __forceinline__ void carrier(float phase, float& 
     }
 }
 
+// exact floor of x in (-1, 2^22) as an int without the conversion unit: a round-down add of 2^23 leaves floor(x) in
+// the mantissa (FADD.RM on the FP32 pipe + one integer subtract); negative x gives a negative result (callers clamp).
+__device__ __forceinline__ int floor_small(float x) { return __float_as_int(__fadd_rd(x, 8388608.0f)) - 0x4B000000; }
+// rintf for |x| < 2^22 (round-to-nearest-even through the 1.5 * 2^23 magic constant), again FP32-pipe only
+__device__ __forceinline__ float rint_small(float x) { return __fadd_rn(__fadd_rn(x, 12582912.0f), -12582912.0f); }
+
+// fmodf(x, y) for y > 0 and |x| < 2^20 y, bit-exact (fmod's result is always representable, so ONE fused
+// multiply-add from the original operand is exact once the integer quotient is right; a quotient that the rounded
+// product x * (1/y) puts off by one is detected by the sign / size of the remainder and the FMA redone from |x|).
+// Host restatement checked against glibc fmodf: tests/cpp/test_fmod_small.c.
+__device__ __forceinline__ float fmod_small(float x, float y, float inv_y)
+{
+    const float ax = fabsf(x);
+    const float kf = __fadd_rn(__fadd_rd(__fmul_rn(ax, inv_y), 8388608.0f), -8388608.0f);   // floor(ax / y), maybe +-1
+    float r = fmaf(-kf, y, ax);
+    if (r >= y) r = fmaf(-(kf + 1.0f), y, ax);
+    else if (r < 0.f) r = fmaf(-(kf - 1.0f), y, ax);
+    return copysignf(r, x);
+}
+
 __device__ __forceinline__ float block_sum(float v, float* red)
 {
 #pragma unroll
@@ -77,22 +99,28 @@ template <int MODE, int TRK_T> __global__ void __launch_bounds__(TRK_T) trk_kern
         for (int i = threadIdx.x; i < 1023; i += TRK_T) row[i] = (float)src[i];
     }
     int ran = 0, lost = 0;
+    // loop-invariant filter gains, rounded exactly as the reference evaluates them inside run_loop_filters (:286, :298)
+    const float pll_g1 = 0.001f / st.pll_tau1, pll_g2 = st.pll_tau2 / st.pll_tau1;
+    const float dll_g1 = 0.001f / st.dll_tau1, dll_g2 = st.dll_tau2 / st.dll_tau1;
+    // "may this channel consume an epoch now?" -- TrackingChannel::update (do_tracking.rs:160-172).  Evaluated for the
+    // first epoch here and for every later one at the end of the serial section (one barrier per epoch less).
+    auto may_go = [&]() -> int {
+        int go = (st.state == GB_TRK_TRACKING) || !a.filters;
+        const unsigned long long n = st.num_samples_per_code;
+        if (a.offsets == nullptr) {
+            if ((long long)(a.head - (st.next_sample_index + n)) < 0) go = 0;          // the ring does not hold it yet
+            if (a.capacity && a.head - st.next_sample_index > a.capacity) go = 0;      // already overwritten
+        }
+        if (n == 0 || n > (unsigned long long)a.n_max) go = 0;
+        return go;
+    };
+    if (threadIdx.x == 0) s_go = may_go();
+    __syncthreads();
 
     for (int e = 0; e < a.n_epochs; e++) {
-        if (threadIdx.x == 0) {
-            int go = (st.state == GB_TRK_TRACKING) || !a.filters;
-            const unsigned long long n = st.num_samples_per_code;
-            if (a.offsets == nullptr) {
-                // TrackingChannel::update (do_tracking.rs:168-172): wait until the ring holds the epoch
-                if ((long long)(a.head - (st.next_sample_index + n)) < 0) go = 0;
-                if (a.capacity && a.head - st.next_sample_index > a.capacity) go = 0;  // overwritten
-            }
-            if (n == 0 || n > (unsigned long long)a.n_max) go = 0;
-            s_go = go;
-        }
-        __syncthreads();
         if (!s_go) break;
 
+        const unsigned lc_old = st.lost_counter;   // read before the carrier half rewrites it
         const int n = (int)st.num_samples_per_code;
         const unsigned long long start = a.offsets ? a.offsets[c] : st.next_sample_index;
         const float carrier_phase = st.carrier_phase, fs = st.fs;
@@ -113,8 +141,11 @@ template <int MODE, int TRK_T> __global__ void __launch_bounds__(TRK_T) trk_kern
             // Per-sample body.  `sane` (checked once per epoch, uniform) says that every chip argument of the epoch
             // lies in [0, 3*1023): then `% 1023` is at most two exact subtractions and the E/P/L indices need no
             // range checks, so the loop is branch-free.
+            // (the batched loop evaluates indices up to n - 1 + (U - 1) * TRK_T; samples past n are zeros)
+            constexpr int U = TRK_T >= 512 ? 4 : 8;
+            const float i_end = (float)(n + (U - 1) * TRK_T);
             const bool sane = code_phase >= 0.f && code_phase < 1023.f && code_step >= 0.f &&
-                              code_step * (float)(n + 8 * TRK_T) < 2040.f;
+                              code_step * i_end < 2040.f && fabsf(carrier_phase) + fabsf(w) * (i_end * rcp_fs) < 1.0e6f;
             auto body = [&](const float2 x, const float fi) {
                 const float t = w * fi;
                 const float q0 = t * rcp_fs;
@@ -150,11 +181,13 @@ template <int MODE, int TRK_T> __global__ void __launch_bounds__(TRK_T) trk_kern
                 // batches of 8 samples per thread, software-pipelined by hand: all loads, then all carrier
                 // phases / SFU sin-cos, then the code look-ups and the 48 FMAs -- so the load and SFU latencies
                 // of one sample hide behind the arithmetic of the other seven.  Samples past n load as 0.
+                // Only the two MUFU calls per sample touch the quarter-rate XU pipe: sample indices are kept as floats
+                // (exact integers), floor / rint go through round-mode adds (floor_small / rint_small).
                 const float2* __restrict__ px = a.samples + s0;
-                constexpr int U = TRK_T >= 512 ? 4 : 8;
                 for (int base = threadIdx.x; base < n; base += U * TRK_T) {
                     float2 x[U];
                     float cs[U], sn[U];
+                    const float fbase = (float)base;
 #pragma unroll
                     for (int u = 0; u < U; u++) {
                         const int i = base + u * TRK_T;
@@ -162,28 +195,28 @@ template <int MODE, int TRK_T> __global__ void __launch_bounds__(TRK_T) trk_kern
                     }
 #pragma unroll
                     for (int u = 0; u < U; u++) {
-                        const float fi = (float)(base + u * TRK_T);
+                        const float fi = fbase + (float)(u * TRK_T);   // exact: integers below 2^24
                         const float t = w * fi;
                         const float q0 = t * rcp_fs;
                         const float q = fmaf(fmaf(-q0, fs, t), rcp_fs, q0);
                         const float phase = carrier_phase + q;
-                        const float k = rintf(phase * inv_2pi);
+                        const float k = rint_small(phase * inv_2pi);
                         const float r = fmaf(-k, c2, fmaf(-k, c1, phase));
                         cs[u] = __cosf(r);
                         sn[u] = __sinf(r);
                     }
 #pragma unroll
                     for (int u = 0; u < U; u++) {
-                        const float fi = (float)(base + u * TRK_T);
+                        const float fi = fbase + (float)(u * TRK_T);
                         const float re = fmaf(x[u].x, cs[u], x[u].y * sn[u]);
                         const float im = fmaf(x[u].y, cs[u], -(x[u].x * sn[u]));
                         float tc = code_phase + (fi * code_step);
                         tc = tc >= 1023.f ? tc - 1023.f : tc;
                         tc = tc >= 1023.f ? tc - 1023.f : tc;
-                        const int ipx = (int)tc;
-                        int iex = (int)(tc + 0.5f);
-                        iex = iex >= 1023 ? iex - 1023 : iex;
-                        const int ilx = max((int)(tc - 0.5f), 0);
+                        const int ipx = floor_small(tc);                     // tc in [0, 1023)
+                        int iex = floor_small(tc + 0.5f);
+                        iex = iex >= 1023 ? iex - 1023 : iex;                 // (chip + 0.5).floor() % 1023
+                        const int ilx = max(floor_small(tc - 0.5f), 0);       // Q7: negative saturates to chip 0
                         const float pc = row[ipx], ec = row[iex], lc = row[ilx];
                         ip = fmaf(re, pc, ip); qp = fmaf(im, pc, qp);
                         ie = fmaf(re, ec, ie); qe = fmaf(im, ec, qe);
@@ -237,72 +270,100 @@ template <int MODE, int TRK_T> __global__ void __launch_bounds__(TRK_T) trk_kern
                 red[8 + warp * 6 + 3] = qe; red[8 + warp * 6 + 4] = il; red[8 + warp * 6 + 5] = ql;
             }
             __syncthreads();
-            if (threadIdx.x < 6) {
-                float s = 0.f;
-#pragma unroll
-                for (int wv = 0; wv < TRK_T / 32; wv++) s += red[8 + wv * 6 + threadIdx.x];
-                red[threadIdx.x] = s;
-            }
-            __syncthreads();
         }
 
-        if (threadIdx.x == 0) {
-            const float i_p = red[0], q_p = red[1], i_e = red[2], q_e = red[3], i_l = red[4], q_l = red[5];
-            const float nf = (float)n;
-            // :240-242 and :265-267
-            st.carrier_phase = fmodf(st.carrier_phase + w * (nf / fs), kTwoPi);
-            st.code_phase = fmodf(st.code_phase + code_step * nf, 1023.f);
-            st.i_prompt = i_p;
-            st.q_prompt = q_p;
-            gb_trk_corr out;
-            out.i_p = i_p; out.q_p = q_p; out.i_e = i_e; out.q_e = q_e; out.i_l = i_l; out.q_l = q_l;
-            a.corr[c] = out;
-            if (a.prompt_hist) {
-                a.prompt_hist[((size_t)e * a.n_channels + c) * 2 + 0] = i_p;
-                a.prompt_hist[((size_t)e * a.n_channels + c) * 2 + 1] = q_p;
-            }
-            if (a.filters) {
-                const float power = i_p * i_p + q_p * q_p;  // :186
-                bool advance = true;
-                if (power > 15.0f) {
-                    st.lost_counter = 0;
-                    // run_loop_filters (:279-302)
-                    float pll_err;
-                    if (MODE == GB_TRK_ORDERED) pll_err = (float)atan((double)(q_p / i_p)) / kTwoPi;
-                    else pll_err = atanf(q_p / i_p) / kTwoPi;
-                    st.carrier_nco = pll_err * (0.001f / st.pll_tau1) + (pll_err - st.carrier_error) * (st.pll_tau2 / st.pll_tau1);
-                    st.carrier_error = pll_err;
-                    st.carrier_freq += st.carrier_nco;
-                    const float pow_e = sqrtf(i_e * i_e + q_e * q_e);
-                    const float pow_l = sqrtf(i_l * i_l + q_l * q_l);
-                    const float dll_err = ((pow_e + pow_l) != 0.f) ? (pow_e - pow_l) / (pow_e + pow_l) : 0.f;
-                    st.code_nco = dll_err * (0.001f / st.dll_tau1) + (dll_err - st.code_error) * (st.dll_tau2 / st.dll_tau1);
-                    st.code_error = dll_err;
-                    st.code_rate += st.code_nco;
+        // ---- epoch end (do_work, :183-210): the carrier half (lock bookkeeping, Costas PLL, prompt outputs) runs on
+        // thread 0 and the code half (DLL, sample bookkeeping, next epoch's go/no-go) on the first thread of warp 1, at
+        // the same time; they own disjoint fields of the channel.  Both read the six sums and the old lost_counter
+        // before anything is written; in FAST mode each sums the per-warp partials itself (no extra barrier).
+        if (threadIdx.x == 0 || threadIdx.x == 32) {
+            float six[6];
+#pragma unroll
+            for (int k = 0; k < 6; k++) {
+                if (MODE == GB_TRK_ORDERED) {
+                    six[k] = red[k];
                 } else {
-                    st.lost_counter += 1;
-                    if (st.lost_counter >= 20) {  // reset() (:311-326, Q9)
-                        st.prn = 0; st.code_row = 0; st.state = GB_TRK_IDLE; st.lost_counter = 0;
-                        st.next_sample_index = 0;
+                    float sfin = 0.f;
+#pragma unroll
+                    for (int wv = 0; wv < TRK_T / 32; wv++) sfin += red[8 + wv * 6 + k];
+                    six[k] = sfin;
+                }
+            }
+            const float i_p = six[0], q_p = six[1], i_e = six[2], q_e = six[3], i_l = six[4], q_l = six[5];
+            const float nf = (float)n;
+            const float power = i_p * i_p + q_p * q_p;                       // :186
+            const bool locked = power > 15.0f;
+            const bool resets = a.filters && !locked && lc_old + 1u >= 20u;   // reset() this epoch (:199-201)
+            if (threadIdx.x == 0) {
+                // :240-242 (fmod_small == fmodf bit for bit in the range the loops produce)
+                const float cph = st.carrier_phase + w * (nf / fs);
+                st.carrier_phase = fabsf(cph) < 1.0e6f ? fmod_small(cph, kTwoPi, 0.15915494309189535f) : fmodf(cph, kTwoPi);
+                st.i_prompt = i_p;
+                st.q_prompt = q_p;
+                if (MODE != GB_TRK_ORDERED) {
+#pragma unroll
+                    for (int k = 0; k < 6; k++) red[k] = six[k];             // the last epoch's sums leave at kernel end
+                }
+                if (a.prompt_hist)
+                    reinterpret_cast<float2*>(a.prompt_hist)[(size_t)e * a.n_channels + c] = make_float2(i_p, q_p);
+                if (a.filters) {
+                    if (locked) {
+                        st.lost_counter = 0;
+                        // run_loop_filters, carrier part (:279-290)
+                        float pll_err;
+                        if (MODE == GB_TRK_ORDERED) pll_err = (float)atan((double)(q_p / i_p)) / kTwoPi;
+                        else pll_err = atanf(q_p / i_p) / kTwoPi;
+                        st.carrier_nco = pll_err * pll_g1 + (pll_err - st.carrier_error) * pll_g2;
+                        st.carrier_error = pll_err;
+                        st.carrier_freq += st.carrier_nco;
+                    } else if (resets) {                                      // reset(), carrier fields (:311-326, Q9)
+                        st.lost_counter = 0;
                         st.carrier_freq = 0.f; st.carrier_phase = 0.f; st.carrier_error = 0.f; st.carrier_nco = 0.f;
-                        st.code_phase = 0.f; st.code_error = 0.f; st.code_nco = 0.f; st.code_rate = 0.f;
                         st.i_prompt = 0.f; st.q_prompt = 0.f;
                         lost = 1;
-                        advance = false;
+                    } else {
+                        st.lost_counter += 1;
                     }
                 }
-                if (advance) {
-                    st.next_sample_index += st.num_samples_per_code;
-                    st.num_samples_per_code = f32_as_usize(roundf(st.fs / (st.code_rate / 1023.0f)));
+                ran += 1;
+            } else {
+                // :265-267
+                const float cdp = st.code_phase + code_step * nf;
+                st.code_phase = fabsf(cdp) < 1.0e8f ? fmod_small(cdp, 1023.f, 9.775171065493646e-4f) : fmodf(cdp, 1023.f);
+                if (a.filters) {
+                    if (locked) {
+                        // run_loop_filters, code part (:291-301)
+                        const float pow_e = sqrtf(i_e * i_e + q_e * q_e);
+                        const float pow_l = sqrtf(i_l * i_l + q_l * q_l);
+                        const float dll_err = ((pow_e + pow_l) != 0.f) ? (pow_e - pow_l) / (pow_e + pow_l) : 0.f;
+                        st.code_nco = dll_err * dll_g1 + (dll_err - st.code_error) * dll_g2;
+                        st.code_error = dll_err;
+                        st.code_rate += st.code_nco;
+                    }
+                    if (resets) {                                             // reset(), code / bookkeeping fields
+                        st.prn = 0; st.code_row = 0; st.state = GB_TRK_IDLE;
+                        st.next_sample_index = 0;
+                        st.code_phase = 0.f; st.code_error = 0.f; st.code_nco = 0.f; st.code_rate = 0.f;
+                    } else {
+                        st.next_sample_index += st.num_samples_per_code;
+                        const float spc = roundf(st.fs / (st.code_rate / 1023.0f));
+                        // `as usize` (saturating, NaN -> 0); the 32-bit path covers every finite sample rate in use
+                        st.num_samples_per_code = (spc >= 0.f && spc < 2.0e9f) ? (unsigned long long)(unsigned)spc : f32_as_usize(spc);
+                    }
                 }
+                st.epochs_done += 1;
+                s_go = (e + 1 < a.n_epochs) ? may_go() : 0;
             }
-            st.epochs_done += 1;
-            ran += 1;
         }
         __syncthreads();
     }
     if (threadIdx.x == 0) {
         a.ch[c] = st;
+        if (ran > 0) {
+            gb_trk_corr out;
+            out.i_p = red[0]; out.q_p = red[1]; out.i_e = red[2]; out.q_e = red[3]; out.i_l = red[4]; out.q_l = red[5];
+            a.corr[c] = out;
+        }
         if (a.ran) a.ran[c] = (uint8_t)(ran > 255 ? 255 : ran);
         if (a.lost) a.lost[c] = (uint8_t)lost;
     }
@@ -329,9 +390,15 @@ template <int T> static cudaError_t launch_t(const TrkArgs& a, int mode, cudaStr
 cudaError_t trk_launch(const TrkArgs& a, int mode, cudaStream_t st)
 {
     if (a.n_channels <= 0) return cudaSuccess;
-    if (a.n_channels >= 600) return launch_t<128>(a, mode, st);
-    if (a.n_channels >= 250) return launch_t<256>(a, mode, st);
-    return launch_t<512>(a, mode, st);
+    if (const char* t = getenv("GB_TRK_T")) {   // tuning override (tools/time_trk.py)
+        const int v = atoi(t);
+        if (v == 64) return launch_t<64>(a, mode, st);
+        if (v == 128) return launch_t<128>(a, mode, st);
+        if (v == 256) return launch_t<256>(a, mode, st);
+        if (v == 512) return launch_t<512>(a, mode, st);
+    }
+    if (a.n_channels > 300) return launch_t<128>(a, mode, st);
+    return launch_t<256>(a, mode, st);
 }
 
 }  // namespace gb

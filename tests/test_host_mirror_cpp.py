@@ -26,3 +26,13 @@ def test_cpp_host_mirror_reference_tests(tmp_path, ffi):
     r = subprocess.run([_build(tmp_path, ffi)], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "ok" in r.stdout
+
+
+def test_fmod_small_is_bit_exact(tmp_path):
+    """The tracking kernel's exact fmod (one FMA from |x|, quotient fixed up by the remainder's sign/size) against glibc
+    fmodf on 2e7 arguments in the ranges the loops produce, including values adjacent to exact multiples."""
+    exe = str(tmp_path / "test_fmod_small")
+    subprocess.run(["gcc", "-O2", "-ffp-contract=off", "-frounding-math", os.path.join(ROOT, "tests", "cpp", "test_fmod_small.c"),
+                    "-o", exe, "-lm"], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and "bad=0" in r.stdout, r.stdout
