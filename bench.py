@@ -55,8 +55,8 @@ def acq_flops():
     shared_per_d = K * N * 14 + G * 5 * N * lg          # wipe-off + coherent pre-sum + forward FFT
     per_pd = G * N * (6 + 5 * lg + 3 + 1)               # x conj(code), IFFT, |.|^2, accumulate
     minimal = D * shared_per_d + P * D * per_pd         # forward path shared by the 32 PRNs
-    as_run = P * D * (shared_per_d + per_pd)            # what the fused kernel executes (per-CTA forward path)
-    return minimal, as_run
+    fused = P * D * (shared_per_d + per_pd)             # the single-kernel form repeats the forward path per PRN
+    return minimal, fused
 
 
 def acq_bytes(shared=True):
@@ -166,7 +166,7 @@ def workload_config():
             "l2": "flushed between timed steps (256 MiB write)", "sharding": "one recording per GPU + NCCL all_gather"}
 
 
-def tracking_numbers(hd, ffi, n_channels=1024, n_epochs=1000):
+def tracking_numbers(hd, ffi, n_channels=1024, n_epochs=1000, want_state=False):
     """BASELINE configs[2] shape, shortened: 1024 channels (32 PRN-slots x 32 hand-over perturbations) on one shared
     2.048 Msps stream, persistent kernel, FAST mode.  Returns channel-epochs/s from the kernel's CUDA events."""
     from gnss_sdr_rs_b200 import ring, sdr_mock, tracking
@@ -204,10 +204,13 @@ def tracking_numbers(hd, ffi, n_channels=1024, n_epochs=1000):
     eng.download(ch)
     locked = sum(1 for c in range(n_channels) if ch[c].state == 1)
     done = sum(int(ch[c].epochs_done) for c in range(n_channels)) - 20 * n_channels
-    return {"metric": "tracking_channel_epochs_per_sec", "value": done / (ms * 1e-3), "unit": "channel-epochs/s",
-            "channels": n_channels, "epochs": n_epochs, "kernel_ms": ms, "locked_channels": locked,
-            "x_realtime": (n_epochs * 1e-3) / (ms * 1e-3), "mode": "fast (persistent kernel, on-device loop filters)",
-            "fs": fs}
+    out = {"metric": "tracking_channel_epochs_per_sec", "value": done / (ms * 1e-3), "unit": "channel-epochs/s",
+           "channels": n_channels, "epochs": n_epochs, "kernel_ms": ms, "locked_channels": locked,
+           "x_realtime": (n_epochs * 1e-3) / (ms * 1e-3), "mode": "fast (persistent kernel, on-device loop filters)",
+           "fs": fs}
+    if want_state:
+        out["state"], out["sats"] = ch, sats
+    return out
 
 
 def extra_numbers(hd, ffi):
@@ -242,6 +245,20 @@ def extra_numbers(hd, ffi):
         ms.append(eng.last_kernel_ms())
     out["galileo_e1_like_n80000_cluster"] = {"fft_size": n, "n_prn": 8, "n_doppler": 41, "num_integrations": 5,
                                              "kernel_ms": min(ms), "cells_per_sec": 8 * 41 * n / (min(ms) * 1e-3)}
+    # fine Doppler (N3): the ten satellites of the config-1 stand-in, 11 ms at 16.3676 Msps, 2^21-point zero-padded
+    # spectrum each (never materialised)
+    raw11, truth = sdr_mock.if_recording(11)
+    x11 = sdr_mock.i8_to_c32(raw11)
+    reqs = [(t["prn"], t["code_phase"]) for t in truth]
+    fine = acquisition.finer_doppler(hd, x11, reqs, sdr_mock.CONFIG_FS, is_complex=False)
+    ms = []
+    for _ in range(3):
+        fine = acquisition.finer_doppler(hd, x11, reqs, sdr_mock.CONFIG_FS, is_complex=False)
+        ms.append(float(hd.L.gb_acq_fine_last_kernel_ms(hd.h)))
+    out["fine_doppler_config1"] = {"n_satellites": len(reqs), "fft_size": int(fine[0]["fft_size"]), "kernel_ms": min(ms),
+                                   "max_abs_err_hz": float(max(abs(float(f["carrier_freq"]) - t["carrier"])
+                                                               for f, t in zip(fine, truth))),
+                                   "bin_hz": sdr_mock.CONFIG_FS / float(fine[0]["fft_size"])}
     # digital front-end (N2): 64 rf_thread blocks of 2048 raw samples into the ring
     fe = ring.DigitalFrontend(hd, 4130400.0, 16367600.0)
     rb = ring.MulticastRingBuffer(hd, 1 << 20)
@@ -366,7 +383,8 @@ def run_ours(args, rank, world, local_rank):
 
     if rank == 0:
         peak_tf = ctypes_float(hd, "gb_bench_fp32_tflops")
-        minimal, as_run = acq_flops()
+        minimal, fused_flops = acq_flops()
+        as_run = fused_flops if args.acq_mode == "fused" else minimal   # the shared chain runs the minimal structure
         achieved = minimal / (kernel_ms_avg * 1e-3) / 1e12
         peaks = {}
         try:
@@ -389,16 +407,17 @@ def run_ours(args, rank, world, local_rank):
                 "e2e": {"value": e2e_value, "unit": "cells/s", "ms_per_step": e2e_ms,
                         "h2d_bytes_per_step": int(x.nbytes), "d2h_bytes_per_step": int(N_PRN * len(DOPPLERS) * 16),
                         "api": "gb_acq_search (pinned host IQ -> results)"},
-                "gpu_launches": args.steps * (1 if args.acq_mode == "fused" else 2),
+                # per step: line-order permutation of the IQ blocks (prime-factor plan) + forward + inverse kernels
+                "gpu_launches": args.steps * (2 if args.acq_mode == "fused" else 3),
                 "roofline": {"bound": "fp32", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                              "frac": achieved / peak_tf if peak_tf else None, "traffic": traffic,
                              "peak_source": "measured live: gb_bench_fp32_tflops FMA probe (MEASURED_PEAKS.json has no "
                                             "FP32 figure; theoretical 148*128*2*1.965 GHz = 74.5)",
                              "flops_per_launch_minimal": minimal, "flops_per_launch_as_run": as_run,
-                             "achieved_as_run": as_run / (kernel_ms_avg * 1e-3) / 1e12,
-                             "kernel": ("acq_fused_kernel" if args.acq_mode == "fused" else "acq_forward_kernel + acq_inverse_kernel") + "<Plan<4092,...>>", "kernel_ms": kernel_ms_avg,
-                             "kernel_shares_ncu": "acq_inverse_kernel 91% / acq_forward_kernel 9% of the chain "
-                                                  "(profiles/round1_v3_shared_chain.txt)",
+                             "kernel": ("acq_fused_kernel" if args.acq_mode == "fused" else "permute_blocks_kernel + acq_forward_kernel + acq_inverse_kernel") + "<PfaPlan<4092,160,4,12,11,31>>", "kernel_ms": kernel_ms_avg,
+                             "kernel_shares_ncu": "acq_inverse_kernel 90% / acq_forward_kernel 10% / permute < 1% of the chain; "
+                                                  "inverse kernel: FMA pipe 67% active, L1 data pipe 63%, issue 51% "
+                                                  "(profiles/round1_v5_pfa_ffma2.txt)",
                              "hbm_view": {"bound": "hbm", "algorithmic_bytes": acq_bytes(args.acq_mode != "fused"),
                                           "achieved": acq_bytes(args.acq_mode != "fused") / (kernel_ms_avg * 1e-3) / 1e9,
                                           "peak": hbm_peak, "unit": "GB/s",
@@ -420,6 +439,8 @@ def run_ours(args, rank, world, local_rank):
             try:
                 line["tracking"] = tracking_numbers(hd, ffi)
                 line["tracking_128ch"] = tracking_numbers(hd, ffi, 128, 1000)
+                # BASELINE configs[2] at full length: 1024 channels x 60 s = 61.44 M channel-epochs in one launch
+                line["tracking_config3_full_60s"] = tracking_numbers(hd, ffi, 1024, 60000)
             except Exception as e:  # report, never hide
                 line["tracking"] = {"error": repr(e)}
             try:

@@ -80,3 +80,35 @@ class ResultGatherer:
         self.dist.all_gather_into_tensor(self.dev_out, self.dev_in)
         out = self.dev_out.cpu().numpy().reshape(self.world, self.n_prn, len(RESULT_FIELDS))
         return [out[r] for r in range(self.world)]
+
+
+def gather_batch(local_packed, n_total, dist, device=None):
+    """Batch snapshot acquisition (BASELINE configs[4]): recordings are dealt to ranks with `items_for_rank`; each rank
+    holds a [n_local, n_prn, 6] array of packed results.  ONE padded all_gather at the end returns the [n_total, n_prn, 6]
+    table in recording order on every rank (NCCL over NVLink on the GPU box, gloo in the CPU tests)."""
+    import torch
+    world = dist.get_world_size() if dist is not None else 1
+    per = (n_total + world - 1) // world
+    local_packed = np.asarray(local_packed, np.float64)
+    n_prn = local_packed.shape[1] if local_packed.ndim == 3 else 32
+    pad = np.zeros((per, n_prn, len(RESULT_FIELDS)), np.float64)
+    pad[:local_packed.shape[0]] = local_packed
+    if dist is None or world == 1:
+        return pad[:n_total]
+    t = torch.from_numpy(pad)
+    if device is not None:
+        t = t.to(device)
+    out = torch.empty((world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(out.view(-1, *t.shape[1:]), t)
+    return out.cpu().numpy().reshape(world * per, n_prn, len(RESULT_FIELDS))[:n_total]
+
+
+def search_batch(engine, recordings, num_integrations, rank=0, world=1, dist=None, device=None):
+    """Runs `engine.search` on this rank's share of `recordings` (list of complex64 arrays, or a callable index -> array
+    so that a rank only materialises its own) and gathers the per-recording, per-PRN results."""
+    n_total = len(recordings) if not callable(recordings) else recordings(None)
+    mine = items_for_rank(n_total, rank, world)
+    local = [pack_results(engine.search(recordings(i) if callable(recordings) else recordings[i], num_integrations))
+             for i in mine]
+    local = np.stack(local) if local else np.zeros((0, engine.n_prn, len(RESULT_FIELDS)))
+    return gather_batch(local, n_total, dist, device)

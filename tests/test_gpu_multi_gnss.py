@@ -98,3 +98,29 @@ def test_gps_at_20msps(gpu, oracle):
     np.testing.assert_allclose(cells[4]["peak"], ref["peak"], rtol=REL)
     best = int(cells[4]["peak"].argmax())
     assert d[best] == 1250.0 and cells[4]["argmax"][best] == 12345
+
+
+def test_batch_snapshot_acquisition_config5_shape(gpu, oracle):
+    """BASELINE configs[4] shape on one rank: a batch of short snapshot recordings with different satellites in view,
+    searched one after the other through `sharding.search_batch`; every recording's decisions equal the oracle's
+    search_satellite (early-exit order included) for each PRN."""
+    from gnss_sdr_rs_b200 import acquisition, sdr_mock, sharding
+    fs, n, K = 4.092e6, 4092, 4
+    dopp = np.arange(-4000, 4001, 500, dtype=np.float32)
+    views = [[(3, 1500.0, 100), (17, -2500.0, 3000)], [(8, 0.0, 2222)], [], [(30, 3500.0, 4000), (3, -500.0, 17), (21, 1000.0, 999)]]
+    recs = [sdr_mock.baseband(fs, K, [{"prn": p, "doppler": d, "code_phase": c, "cn0_dbhz": 52.0} for p, d, c in v],
+                              seed=100 + i) for i, v in enumerate(views)]
+    eng = acquisition.AcquisitionEngine(gpu, n, fs)
+    carr, tabs = oracle.doppler_tables(0.0, dopp, fs, n)
+    eng.set_doppler_tables(tabs, carr)
+    table = sharding.search_batch(eng, recs, K)
+    assert table.shape == (len(recs), 32, 6)
+    workers = {p: oracle.AcqWorker(p, n, fs) for p in range(1, 33)}
+    for i, v in enumerate(views):
+        found = {p + 1 for p in range(32) if table[i, p, 0] == 1}
+        assert {p for p, _, _ in v} <= found
+        for p in range(1, 33):
+            ref = workers[p].search_satellite(recs[i], tabs, carr, 0, K)
+            assert (ref is not None) == (p in found), (i, p)
+            if ref:
+                assert table[i, p - 1, 2] == ref["code_phase_samples"] and table[i, p - 1, 3] == ref["carrier_freq"]

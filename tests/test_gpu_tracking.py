@@ -222,3 +222,28 @@ def test_nav_bit_sync_on_tracked_channels(gpu, oracle):
         # bit edges of the planted data sit where the code period count crosses a multiple of 20
         b = bits[c, :st[c]["n_bits"]].astype(np.int32)
         assert abs(int(np.abs(np.diff(b)).sum())) > 0            # there are transitions
+
+
+def test_config3_shape_long_run_properties(gpu):
+    """BASELINE configs[2] shape (1024 channels = 8 PRNs x 128 hand-over perturbations on one 2.048 Msps stream), 4 s in
+    ONE persistent launch.  Size-independent properties: every channel consumes every epoch, stays locked, ends on the
+    true carrier, keeps the code aligned (prompt power near the coherent maximum) and the per-channel sample bookkeeping
+    advances by exactly one code period per epoch (+-1 sample of code-rate slew)."""
+    import bench
+    r = bench.tracking_numbers(gpu, None, 1024, 4000, want_state=True)
+    ch, sats = r["state"], r["sats"]
+    assert r["locked_channels"] == 1024
+    n = 2048
+    ferr, ifrac = [], []
+    for c in range(1024):
+        s = sats[c % len(sats)]
+        assert ch[c].epochs_done == 4020 and ch[c].state == 1 and ch[c].lost_counter == 0
+        ferr.append(abs(ch[c].carrier_freq - s["doppler"]))
+        assert abs(int(ch[c].next_sample_index) - (s["code_phase"] + 4020 * n)) <= 2
+        amp2 = 10.0 ** (s["cn0_dbhz"] / 10.0) / 2.048e6 * n * n      # |sum|^2 of a perfectly aligned 1 ms prompt
+        p = ch[c].i_prompt ** 2 + ch[c].q_prompt ** 2
+        assert 0.4 * amp2 < p < 1.8 * amp2, (c, p, amp2)
+        ifrac.append(ch[c].i_prompt ** 2 / p)
+    # the instantaneous NCO frequency of a 1 ms Costas loop at 48 dB-Hz jitters by a few Hz around the truth
+    assert np.median(ferr) < 8.0 and max(ferr) < 60.0, (np.median(ferr), max(ferr))
+    assert np.median(ifrac) > 0.9, np.median(ifrac)                  # Costas-locked: the energy sits on I

@@ -29,6 +29,12 @@ def _worker(rank, world, port, out_dir):
     assert all((a == b).all() for a, b in zip(gathered, again))
     np.save(os.path.join(out_dir, "merged_%d.npy" % rank), merged)
     np.save(os.path.join(out_dir, "mask_%d.npy" % rank), np.array([mask], np.uint64))
+    # batch snapshot acquisition (BASELINE configs[4]): 13 recordings dealt to the ranks, one padded gather at the end
+    mine = sharding.items_for_rank(13, rank, world)
+    local = np.stack([sharding.pack_results([_fake_result(p + 1) if (p + i) % 5 == 0 else None for p in range(32)])
+                      for i in mine])
+    table = sharding.gather_batch(local, 13, dist)
+    np.save(os.path.join(out_dir, "batch_%d.npy" % rank), table)
     # batch / channel partitioning
     items = list(sharding.items_for_rank(13, rank, world))
     np.save(os.path.join(out_dir, "items_%d.npy" % rank), np.array(items))
@@ -52,6 +58,13 @@ def test_prn_sharding_and_gather_world2(tmp_path):
     assert abs(bin(k0).count("1") - bin(k1).count("1")) <= 1
     i0, i1 = np.load(tmp_path / "items_0.npy"), np.load(tmp_path / "items_1.npy")
     assert sorted(i0.tolist() + i1.tolist()) == list(range(13))
+    b0, b1 = np.load(tmp_path / "batch_0.npy"), np.load(tmp_path / "batch_1.npy")
+    assert b0.shape == (13, 32, 6) and (b0 == b1).all()
+    sys.path.insert(0, ROOT)
+    from gnss_sdr_rs_b200 import sharding
+    for i in range(13):     # recording order is preserved across the rank boundary
+        want = sharding.pack_results([_fake_result(p + 1) if (p + i) % 5 == 0 else None for p in range(32)])
+        assert (b0[i] == want).all()
 
 
 def test_partition_edge_cases():
