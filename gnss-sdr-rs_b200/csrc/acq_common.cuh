@@ -20,10 +20,10 @@ using P4092v1 = Plan<4092, 160, 4, 0, 12, 11, 31>;   // the Cooley-Tukey form of
 using P4092v2 = PfaPlan<4092, 160, 3, 0, 12, 11, 31>;
 using P4092v3 = Plan<4092, 192, 2, 0, 12, 11, 31>;
 using P4092v4 = Plan<4092, 384, 1, 0, 12, 11, 31>;
-using P4092v5 = PfaPlan<4092, 192, 3, 0, 12, 11, 31>;
-using P4092v6 = PfaPlan<4092, 192, 4, 0, 12, 11, 31>;
-using P4092v7 = PfaPlan<4092, 160, 5, 0, 12, 11, 31>;
-using P4092v8 = PfaPlan<4092, 224, 3, 0, 12, 11, 31>;
+using P4092v5 = PfaStreamPlan<3, 4092, 160, 4, 0, 12, 11, 31>;
+using P4092v6 = PfaStreamPlan<5, 4092, 160, 4, 0, 12, 11, 31>;
+using P4092v7 = PfaStreamPlan<3, 4092, 160, 3, 0, 12, 11, 31>;
+using P4092v8 = PfaStreamPlan<5, 4092, 160, 3, 0, 12, 11, 31>;
 using P16368v1 = Plan<16368, 288, 1, 0, 16, 3, 11, 31>;
 using P16368v2 = Plan<16368, 416, 1, 0, 16, 3, 11, 31>;
 

@@ -313,10 +313,17 @@ template <class P, bool DB> __global__ void __launch_bounds__(P::T, P::MINB) acq
         for (int it = 0; it < GM::ITERS; it++) {
             const int b = threadIdx.x + it * P::T;
             if (GM::NB % P::T == 0 || b < GM::NB) {
-                float2 v[GM::R];
+                if constexpr (GM::R == 31 && P::STREAM_A > 0) {
+                    // radix 31 from global memory: streamed inputs, accumulators in registers (see dft_odd_prime_stream)
+                    dft_odd_prime_stream<GM::R, true, P::STREAM_A>(
+                        [&](int q) { return cmul_conj(__ldg(&sg[q * GM::NB + b]), __ldg(&code[q * GM::NB + b])); },
+                        [&](int j, float2 y) { line[P::phys(b * GM::R + j)] = y; });
+                } else {
+                    float2 v[GM::R];
 #pragma unroll
-                for (int q = 0; q < GM::R; q++) v[q] = cmul_conj(__ldg(&sg[q * GM::NB + b]), __ldg(&code[q * GM::NB + b]));
-                dft_emit<GM::R, true>(v, [&](int j, float2 y) { line[P::phys(b * GM::R + j)] = y; });
+                    for (int q = 0; q < GM::R; q++) v[q] = cmul_conj(__ldg(&sg[q * GM::NB + b]), __ldg(&code[q * GM::NB + b]));
+                    dft_emit<GM::R, true>(v, [&](int j, float2 y) { line[P::phys(b * GM::R + j)] = y; });
+                }
             }
         }
         __syncthreads();

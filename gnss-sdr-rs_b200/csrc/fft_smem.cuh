@@ -246,6 +246,75 @@ template <int R, bool INV, class Emit> __device__ __forceinline__ void dft_odd_p
     }
 }
 
+// Streaming form for a first stage that reads its inputs from global memory: `load(j)` delivers input j when it is
+// needed, and the butterfly keeps the 2 x (R-1)/2 packed output accumulators in registers instead of the a/b half-sums
+// ("j outer, q inner").  The inputs need not be resident together, so the loads are issued a batch of BATCH pairs
+// ahead of the FFMA2s that consume them and the L2 latency of one batch hides behind the arithmetic of the previous
+// one inside the same thread.  Every accumulator receives its terms in the same order (j = 1, 2, ...) as in
+// dft_odd_prime_emit: the results are bit-identical.
+template <int R, bool INV, int BATCH, class Load, class Emit>
+__device__ __forceinline__ void dft_odd_prime_stream(Load load, Emit emit)
+{
+    constexpr int H = (R - 1) / 2;
+    pk64 c2[H + 1], s2[H + 1];
+    const pk64 v0 = pk(load(0));
+    pk64 x0 = v0;
+#pragma unroll
+    for (int q = 1; q <= H; q++) {
+        c2[q] = v0;
+        s2[q] = pk(0.f, 0.f);
+    }
+    float2 p[BATCH], m[BATCH];
+#pragma unroll
+    for (int u = 0; u < BATCH; u++) {
+        if (1 + u <= H) {
+            p[u] = load(1 + u);
+            m[u] = load(R - 1 - u);
+        }
+    }
+#pragma unroll
+    for (int j0 = 1; j0 <= H; j0 += BATCH) {
+        pk64 a[BATCH], b[BATCH];
+#pragma unroll
+        for (int u = 0; u < BATCH; u++) {
+            if (j0 + u <= H) {
+                a[u] = add2(pk(p[u]), pk(m[u]));
+                b[u] = sub2(pk(p[u]), pk(m[u]));
+            }
+        }
+        // next batch's loads are in flight while this batch is consumed
+#pragma unroll
+        for (int u = 0; u < BATCH; u++) {
+            if (j0 + BATCH + u <= H) {
+                p[u] = load(j0 + BATCH + u);
+                m[u] = load(R - (j0 + BATCH + u));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < BATCH; u++) {
+            if (j0 + u <= H) {
+                const int j = j0 + u;
+                x0 = add2(x0, a[u]);
+#pragma unroll
+                for (int q = 1; q <= H; q++) {
+                    const int k = (j * q) % R;
+                    const float c = RT<R>::c(k);
+                    const float s = INV ? RT<R>::s(k) : -RT<R>::s(k);
+                    c2[q] = fma2s(a[u], c, c2[q]);
+                    s2[q] = fma2s(b[u], s, s2[q]);
+                }
+            }
+        }
+    }
+    emit(0, upk(x0));
+#pragma unroll
+    for (int q = 1; q <= H; q++) {
+        const float2 cc = upk(c2[q]), ss = upk(s2[q]);
+        emit(q, make_float2(cc.x - ss.y, cc.y + ss.x));
+        emit(R - q, make_float2(cc.x + ss.y, cc.y - ss.x));
+    }
+}
+
 // dft_emit<R,INV>(v, emit): DFT of v with outputs delivered through emit(q, X_q).
 template <int R, bool INV, class Emit> __device__ __forceinline__ void dft_emit(float2 (&v)[R], Emit emit)
 {
@@ -319,6 +388,9 @@ template <int N_, int T_, int MINB_, int PAD_, int R0, int R1 = 1, int R2 = 1, i
     __device__ static __forceinline__ int phys(int i) { return PAD ? i + (i >> PAD) : i; }
     // Cooley-Tukey (inter-stage twiddles) unless overridden by PfaPlan
     static constexpr bool PFA = false;
+    // inverse kernel, radix-31 first stage: 0 = all inputs resident (dft_odd_prime_emit), n > 0 = streamed in batches of
+    // n input pairs (dft_odd_prime_stream)
+    static constexpr int STREAM_A = 0;
 };
 
 // Good-Thomas prime-factor plan: the stage radices are pairwise coprime, so with the index maps
@@ -334,11 +406,18 @@ constexpr int plan_gcd(int a, int b) { return b == 0 ? a : plan_gcd(b, a % b); }
 template <int N_, int T_, int MINB_, int PAD_, int R0, int R1 = 1, int R2 = 1, int R3 = 1, int R4 = 1, int R5 = 1>
 struct PfaPlan : Plan<N_, T_, MINB_, PAD_, R0, R1, R2, R3, R4, R5> {
     static constexpr bool PFA = true;
+    static constexpr int STREAM_A = 0;
     static_assert(plan_gcd(R0, R1) == 1 && plan_gcd(R0, R2) == 1 && plan_gcd(R0, R3) == 1 && plan_gcd(R0, R4) == 1 &&
                       plan_gcd(R0, R5) == 1 && plan_gcd(R1, R2) == 1 && plan_gcd(R1, R3) == 1 && plan_gcd(R1, R4) == 1 &&
                       plan_gcd(R1, R5) == 1 && plan_gcd(R2, R3) == 1 && plan_gcd(R2, R4) == 1 && plan_gcd(R2, R5) == 1 &&
                       plan_gcd(R3, R4) == 1 && plan_gcd(R3, R5) == 1 && plan_gcd(R4, R5) == 1,
                   "prime-factor plans need pairwise coprime radices");
+};
+
+// PfaPlan whose inverse first stage streams its inputs (batches of SB pairs)
+template <int SB, int N_, int T_, int MINB_, int PAD_, int R0, int R1 = 1, int R2 = 1, int R3 = 1, int R4 = 1, int R5 = 1>
+struct PfaStreamPlan : PfaPlan<N_, T_, MINB_, PAD_, R0, R1, R2, R3, R4, R5> {
+    static constexpr int STREAM_A = SB;
 };
 
 // ------------------------------------------------------------------ stage workers

@@ -212,6 +212,25 @@ class AcquisitionWorker {
     float fs_;
 };
 
+// legacy finer_doppler (acquisition_bk.rs:215-302): refines result.carrier_freq in place from LONG_SAMPLES_LENGTH (11) ms
+// of samples; `is_complex` as in the legacy call.  Returns false where the legacy returns None / would panic
+// (recording too short, or the peak in the half of the spectrum whose bin table the legacy indexes out of bounds).
+inline bool finer_doppler(GpuEngine& e, const std::vector<Complex32>& long_samples, bool is_complex, AcquisitionResult& result,
+                          float freq_sampling)
+{
+    gb_fine_req req{};
+    req.prn = result.prn;
+    req.code_phase = (uint32_t)result.code_phase_samples;
+    gb_fine_result out{};
+    const int rc = gb_acq_fine_doppler(e.raw(), long_samples.data(), long_samples.size(), freq_sampling, 11, is_complex ? 1 : 0,
+                                       &req, 1, nullptr, &out, nullptr);
+    if (rc == GB_ERANGE) return false;
+    if (rc) throw AcqError(rc);
+    if (!out.ref_defined) return false;
+    result.carrier_freq = out.carrier_freq;
+    return true;
+}
+
 // do_tracking.rs:52-71
 struct LoopFilter {
     float tau1, tau2;

@@ -183,6 +183,28 @@ static void test_acquisition(std::shared_ptr<GpuEngine> e)
     for (const auto& a : all)
         if (a.prn == 6) { saw6 = true; CHECK(r && a.code_phase_samples == r->code_phase_samples && a.sample_global_index == 500 + a.code_phase_samples); }
     CHECK(saw6);
+    // legacy finer_doppler on 11 ms of the same signal: real samples (is_complex = false) keep the positive sign; the
+    // 8x zero-padded 2^21-point spectrum resolves the carrier to 7.8 Hz (when the first maximum sits in the mirror half
+    // of the real signal's spectrum the legacy code panics and the mirror reports false)
+    if (r) {
+        std::vector<Complex32> raw11(N * 11);
+        lcg = 1;
+        for (size_t i = 0; i < N * 11; i++) {
+            const double t = (double)i;
+            const double chip = fmod((t - 7827.0 + 10.0 * N) * 1.023e6 / FS, 1023.0);
+            const double ph = 2.0 * M_PI * fmod((IF + 1000.0) * t / FS, 1.0);
+            const double noise = 8.0 * sqrt(-2.0 * log(uni())) * cos(2.0 * M_PI * uni());
+            raw11[i] = Complex32{(float)(int)lrint(4.0 * chips[(int)chip] * cos(ph) + noise), 0.f};
+        }
+        AcquisitionResult fine = *r;
+        fine.code_phase_samples = 7827;
+        if (finer_doppler(*e, raw11, false, fine, FS)) {
+            printf("PRN6 finer_doppler: %.1f Hz\n", fine.carrier_freq);
+            CHECK(fabsf(fine.carrier_freq - (IF + 1000.0f)) < 20.0f);
+        }
+        std::vector<Complex32> too_short(raw11.begin(), raw11.begin() + N * 10);
+        CHECK(!finer_doppler(*e, too_short, false, fine, FS));
+    }
     // FFT facade
     FFT f(e, 2048);
     std::vector<Complex32> x(2048, Complex32{0.f, 0.f});
