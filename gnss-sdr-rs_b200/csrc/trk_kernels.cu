@@ -74,6 +74,28 @@ __device__ __forceinline__ float fmod_small(float x, float y, float inv_y)
     return copysignf(r, x);
 }
 
+// packed FP32 helpers (Blackwell FFMA2): (acc.x, acc.y) += (a.x, a.y) * s in one instruction
+typedef unsigned long long pk64;
+__device__ __forceinline__ pk64 pk2(float x, float y)
+{
+    pk64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y));
+    return r;
+}
+__device__ __forceinline__ void upk2(pk64 v, float& x, float& y) { asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(v)); }
+__device__ __forceinline__ pk64 fma2s(pk64 a, float s, pk64 c)
+{
+    pk64 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(pk2(s, s)), "l"(c));
+    return r;
+}
+__device__ __forceinline__ float lds_f32(unsigned addr)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+
 __device__ __forceinline__ float block_sum(float v, float* red)
 {
 #pragma unroll
@@ -177,6 +199,15 @@ template <int MODE, int TRK_T> __global__ void __launch_bounds__(TRK_T) trk_kern
             // the epoch's samples are contiguous unless they straddle the ring's wrap point
             const unsigned long long s0 = start & a.mask;
             const bool contiguous = (a.mask == ~0ull) || (s0 + (unsigned long long)n <= a.mask + 1ull);
+            // cycles per sample and start phase in turns: phase_i / 2 pi = cp_turn + i * f_turn (one FMA per sample).  Used
+            // while the epoch spans < 16 turns: the argument error is then < 1e-6 turn, two orders below the FAST-mode
+            // tolerance.
+            const float f_turn = st.carrier_freq * rcp_fs;
+            const float cp_turn = carrier_phase * inv_2pi;
+            const bool turns_ok = fabsf(f_turn) * i_end < 16.f && fabsf(cp_turn) < 2.f;   // baseband / low-IF carriers
+            // C/A row look-ups straight from the raw bits of the round-down add: index = bits - 0x4B000000, address =
+            // row + 4 * index = 4 * bits + row_bias (mod 2^32), one LEA per look-up
+            const unsigned row_bias = (unsigned)__cvta_generic_to_shared(row) - 4u * 0x4B000000u;
             if (contiguous && sane) {
                 // batches of 8 samples per thread, software-pipelined by hand: all loads, then all carrier
                 // phases / SFU sin-cos, then the code look-ups and the 48 FMAs -- so the load and SFU latencies
@@ -184,6 +215,7 @@ template <int MODE, int TRK_T> __global__ void __launch_bounds__(TRK_T) trk_kern
                 // Only the two MUFU calls per sample touch the quarter-rate XU pipe: sample indices are kept as floats
                 // (exact integers), floor / rint go through round-mode adds (floor_small / rint_small).
                 const float2* __restrict__ px = a.samples + s0;
+                pk64 accp = pk2(0.f, 0.f), acce = accp, accl = accp;
                 for (int base = threadIdx.x; base < n; base += U * TRK_T) {
                     float2 x[U];
                     float cs[U], sn[U];
@@ -193,17 +225,30 @@ template <int MODE, int TRK_T> __global__ void __launch_bounds__(TRK_T) trk_kern
                         const int i = base + u * TRK_T;
                         x[u] = i < n ? __ldg(px + i) : make_float2(0.f, 0.f);
                     }
+                    if (turns_ok) {
 #pragma unroll
-                    for (int u = 0; u < U; u++) {
-                        const float fi = fbase + (float)(u * TRK_T);   // exact: integers below 2^24
-                        const float t = w * fi;
-                        const float q0 = t * rcp_fs;
-                        const float q = fmaf(fmaf(-q0, fs, t), rcp_fs, q0);
-                        const float phase = carrier_phase + q;
-                        const float k = rint_small(phase * inv_2pi);
-                        const float r = fmaf(-k, c2, fmaf(-k, c1, phase));
-                        cs[u] = __cosf(r);
-                        sn[u] = __sinf(r);
+                        for (int u = 0; u < U; u++) {
+                            const float fi = fbase + (float)(u * TRK_T);   // exact: integers below 2^24
+                            const float ut = fmaf(fi, f_turn, cp_turn);
+                            const float r = (ut - rint_small(ut)) * c1;    // [-pi, pi]
+                            cs[u] = __cosf(r);
+                            sn[u] = __sinf(r);
+                        }
+                    } else {
+                        // IF carriers: thousands of turns per epoch -- follow the reference's f32 roundings of the phase
+                        // argument (the oracle shares them) and reduce with a two-term Cody-Waite step
+#pragma unroll
+                        for (int u = 0; u < U; u++) {
+                            const float fi = fbase + (float)(u * TRK_T);
+                            const float t = w * fi;
+                            const float q0 = t * rcp_fs;
+                            const float q = fmaf(fmaf(-q0, fs, t), rcp_fs, q0);     // (w * i) / fs, correctly rounded
+                            const float phase = carrier_phase + q;
+                            const float k = rint_small(phase * inv_2pi);
+                            const float r = fmaf(-k, c2, fmaf(-k, c1, phase));
+                            cs[u] = __cosf(r);
+                            sn[u] = __sinf(r);
+                        }
                     }
 #pragma unroll
                     for (int u = 0; u < U; u++) {
@@ -213,16 +258,22 @@ template <int MODE, int TRK_T> __global__ void __launch_bounds__(TRK_T) trk_kern
                         float tc = code_phase + (fi * code_step);
                         tc = tc >= 1023.f ? tc - 1023.f : tc;
                         tc = tc >= 1023.f ? tc - 1023.f : tc;
-                        const int ipx = floor_small(tc);                     // tc in [0, 1023)
-                        int iex = floor_small(tc + 0.5f);
-                        iex = iex >= 1023 ? iex - 1023 : iex;                 // (chip + 0.5).floor() % 1023
-                        const int ilx = max(floor_small(tc - 0.5f), 0);       // Q7: negative saturates to chip 0
-                        const float pc = row[ipx], ec = row[iex], lc = row[ilx];
-                        ip = fmaf(re, pc, ip); qp = fmaf(im, pc, qp);
-                        ie = fmaf(re, ec, ie); qe = fmaf(im, ec, qe);
-                        il = fmaf(re, lc, il); ql = fmaf(im, lc, ql);
+                        const int bp = __float_as_int(__fadd_rd(tc, 8388608.0f));             // tc in [0, 1023)
+                        int be = __float_as_int(__fadd_rd(tc + 0.5f, 8388608.0f));
+                        be = be >= 0x4B000000 + 1023 ? be - 1023 : be;                        // (chip + 0.5).floor() % 1023
+                        const int bl = max(__float_as_int(__fadd_rd(tc - 0.5f, 8388608.0f)), 0x4B000000);   // Q7
+                        const float pc = lds_f32(4u * (unsigned)bp + row_bias);
+                        const float ec = lds_f32(4u * (unsigned)be + row_bias);
+                        const float lc = lds_f32(4u * (unsigned)bl + row_bias);
+                        const pk64 z = pk2(re, im);
+                        accp = fma2s(z, pc, accp);
+                        acce = fma2s(z, ec, acce);
+                        accl = fma2s(z, lc, accl);
                     }
                 }
+                upk2(accp, ip, qp);
+                upk2(acce, ie, qe);
+                upk2(accl, il, ql);
             } else if (contiguous) {
                 const float2* __restrict__ px = a.samples + s0;
 #pragma unroll 4
