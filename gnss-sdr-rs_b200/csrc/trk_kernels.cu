@@ -361,9 +361,12 @@ template <int MODE, int TRK_T> __global__ void __launch_bounds__(TRK_T) trk_kern
                     if (locked) {
                         st.lost_counter = 0;
                         // run_loop_filters, carrier part (:279-290)
+                        // FAST: reciprocal-multiply division (2 ulp) and a multiply by 1/(2 pi) -- the serial section is a
+                        // dependent chain that competes with the other channels' sample loops for issue slots, so every
+                        // IEEE division (~10 dependent instructions) removed shortens the epoch
                         float pll_err;
                         if (MODE == GB_TRK_ORDERED) pll_err = (float)atan((double)(q_p / i_p)) / kTwoPi;
-                        else pll_err = atanf(q_p / i_p) / kTwoPi;
+                        else pll_err = atanf(__fdividef(q_p, i_p)) * 0.15915494309189535f;
                         st.carrier_nco = pll_err * pll_g1 + (pll_err - st.carrier_error) * pll_g2;
                         st.carrier_error = pll_err;
                         st.carrier_freq += st.carrier_nco;
@@ -386,7 +389,9 @@ template <int MODE, int TRK_T> __global__ void __launch_bounds__(TRK_T) trk_kern
                         // run_loop_filters, code part (:291-301)
                         const float pow_e = sqrtf(i_e * i_e + q_e * q_e);
                         const float pow_l = sqrtf(i_l * i_l + q_l * q_l);
-                        const float dll_err = ((pow_e + pow_l) != 0.f) ? (pow_e - pow_l) / (pow_e + pow_l) : 0.f;
+                        float dll_err;
+                        if (MODE == GB_TRK_ORDERED) dll_err = ((pow_e + pow_l) != 0.f) ? (pow_e - pow_l) / (pow_e + pow_l) : 0.f;
+                        else dll_err = ((pow_e + pow_l) != 0.f) ? __fdividef(pow_e - pow_l, pow_e + pow_l) : 0.f;
                         st.code_nco = dll_err * dll_g1 + (dll_err - st.code_error) * dll_g2;
                         st.code_error = dll_err;
                         st.code_rate += st.code_nco;
