@@ -260,12 +260,15 @@ template <class P> __global__ void __launch_bounds__(P::T, P::MINB) acq_forward_
     constexpr int LASTS = P::NSTAGE - 1;
     using GM = StageGeo<P, LASTS>;
     constexpr int N = P::N;
+    // one launch covers the groups [g_lo, g_lo + g_cnt) of every bin of the slab (the host-pointer search launches
+    // one per upload slice so that the H2D copy of slice s+1 overlaps the forward path of slice s)
     const int n_groups = a.K / a.n_coh;
-    const int d = a.d_lo + (int)(blockIdx.x / (unsigned)n_groups);
-    const int g = (int)(blockIdx.x % (unsigned)n_groups);
+    const int dl = (int)(blockIdx.x / (unsigned)a.g_cnt);
+    const int d = a.d_lo + dl;
+    const int g = a.g_lo + (int)(blockIdx.x % (unsigned)a.g_cnt);
     const float2* __restrict__ w = a.tables + (size_t)d * N;
     const float2* __restrict__ rot = a.rot ? a.rot + (size_t)d * a.n_coh : nullptr;
-    float2* __restrict__ out = a.spec + (size_t)blockIdx.x * N;
+    float2* __restrict__ out = a.spec + ((size_t)dl * n_groups + g) * N;
     stage0_wipe_forward<P>(a, w, rot, a.n_coh, g, line, a.tw);
     __syncthreads();
     DifRange<P, 1, LASTS, false>::run(line, a.tw);
@@ -454,19 +457,19 @@ __global__ void doppler_table_kernel(const float* __restrict__ steps, int n, flo
 // dst[b * n + l] = src[(start + b * n + npos[l]) & mask]: IQ blocks (from the ring or an uploaded chunk) and the
 // wipe-off tables are put into line order once, so every kernel's global access stays coalesced.
 __global__ void permute_blocks_kernel(const float2* __restrict__ src, unsigned long long start, unsigned long long mask,
-                                      const int* __restrict__ npos, int n, float2* __restrict__ dst)
+                                      const int* __restrict__ npos, int n, int b0, float2* __restrict__ dst)
 {
     const int l = blockIdx.x * blockDim.x + threadIdx.x;
     if (l < n) {
-        const unsigned long long b = blockIdx.y;
+        const unsigned long long b = (unsigned long long)b0 + blockIdx.y;
         dst[b * n + l] = src[(start + b * n + (unsigned long long)__ldg(&npos[l])) & mask];
     }
 }
 cudaError_t acq_launch_permute(const float2* src, unsigned long long start, unsigned long long mask, const int* npos, int n,
-                               int n_blocks, float2* dst, cudaStream_t st)
+                               int b0, int n_blocks, float2* dst, cudaStream_t st)
 {
     dim3 grid((n + 255) / 256, n_blocks);
-    permute_blocks_kernel<<<grid, 256, 0, st>>>(src, start, mask, npos, n, dst);
+    permute_blocks_kernel<<<grid, 256, 0, st>>>(src, start, mask, npos, n, b0, dst);
     return cudaGetLastError();
 }
 
@@ -569,13 +572,21 @@ template <class P> static cudaError_t launch_search(const AcqArgs& a, cudaStream
     acq_fused_kernel<P, false><<<a.n_active * a.D, P::T, smem, st>>>(a);
     return cudaGetLastError();
 }
-template <class P> static cudaError_t launch_shared(const AcqArgs& a, int n_d, cudaStream_t st)
+template <class P> static cudaError_t launch_forward(const AcqArgs& a, int n_d, cudaStream_t st)
 {
     const size_t smem = plan_smem<P>();
     cudaError_t e = set_smem(acq_forward_kernel<P>, smem);
     if (e != cudaSuccess) return e;
-    acq_forward_kernel<P><<<n_d * (a.K / a.n_coh), P::T, smem, st>>>(a);
-    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    acq_forward_kernel<P><<<n_d * a.g_cnt, P::T, smem, st>>>(a);
+    return cudaGetLastError();
+}
+template <class P> static cudaError_t launch_shared(const AcqArgs& a, int n_d, cudaStream_t st)
+{
+    const size_t smem = plan_smem<P>();
+    cudaError_t e;
+    if (a.g_cnt > 0) {   // g_cnt == 0: the forward path was already launched slice by slice (acq_launch_forward)
+        if ((e = launch_forward<P>(a, n_d, st)) != cudaSuccess) return e;
+    }
     // double-buffered line when two lines fit the 227 KB of one SM at the plan's CTA count
     constexpr bool kDB = P::DB;
     const size_t smem_inv = kDB ? 2 * smem : smem;
@@ -629,6 +640,16 @@ cudaError_t acq_launch_shared(int plan, const AcqArgs& a, int n_d, cudaStream_t 
     switch (plan) {
 #define X(i, P) \
     case i: return launch_shared<P>(a, n_d, st);
+        GB_FOR_EACH_PLAN(X)
+#undef X
+    }
+    return cudaErrorInvalidValue;
+}
+cudaError_t acq_launch_forward(int plan, const AcqArgs& a, int n_d, cudaStream_t st)
+{
+    switch (plan) {
+#define X(i, P) \
+    case i: return launch_forward<P>(a, n_d, st);
         GB_FOR_EACH_PLAN(X)
 #undef X
     }

@@ -23,6 +23,7 @@ struct AcqArgs {
     int d0;                  // Doppler bin for row_out
     float2* spec;            // shared-forward chain: n_d x n_groups x N scrambled spectra (scratch)
     int d_lo;                // shared-forward chain: first Doppler bin of this slab
+    int g_lo, g_cnt;         // shared-forward chain: groups covered by this forward launch (g_cnt == 0: none)
     const int* npos;         // prime-factor plans: code-phase index n(l) of line position l (else unused)
     const float2* otw;       // cluster plans: outer twiddles W_N^(i q), layout [q-1][i]
     float* acc_rows;         // cluster plans: (n_active*D) x N accumulated power rows (scratch)
@@ -51,9 +52,11 @@ cudaError_t acq_launch_shared(int plan, const AcqArgs& a, int n_d, cudaStream_t 
 cudaError_t acq_launch_row(int plan, const AcqArgs& a, cudaStream_t st);
 cudaError_t acq_launch_code_fft(int plan, const int8_t* codes, int n_prn, float2* code_fft, const float2* tw,
                                 const int* npos, cudaStream_t st);
-// prime-factor plans: dst[b*n + l] = src[(start + b*n + npos[l]) & mask] for b < n_blocks
+// prime-factor plans: dst[b*n + l] = src[(start + b*n + npos[l]) & mask] for b0 <= b < b0 + n_blocks
 cudaError_t acq_launch_permute(const float2* src, unsigned long long start, unsigned long long mask, const int* npos, int n,
-                               int n_blocks, float2* dst, cudaStream_t st);
+                               int b0, int n_blocks, float2* dst, cudaStream_t st);
+// forward kernel alone over n_d bins x groups [a.g_lo, a.g_lo + a.g_cnt)
+cudaError_t acq_launch_forward(int plan, const AcqArgs& a, int n_d, cudaStream_t st);
 cudaError_t acq_launch_fft(int plan, int inverse, const FftArgs& a, int batch, cudaStream_t st);
 // steps_dev[d] = 2*pi*(f_if+f_d)/fs (f32, host-evaluated in the reference's order)
 cudaError_t acq_launch_doppler_tables(const float* steps_dev, int D, int n, float2* tables, cudaStream_t st);

@@ -76,6 +76,7 @@ struct gb_handle {
     int *rows_dev = nullptr, *rows_pin = nullptr;
     float* row_dev = nullptr;
     float last_acq_ms = 0.f;
+    cudaEvent_t ev_slice[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // upload slices
 
     // fine Doppler (N3)
     float2* fine_x = nullptr;
@@ -483,6 +484,8 @@ extern "C" int gb_destroy(gb_handle* h)
     if (h->s_acq) cudaStreamDestroy(h->s_acq);
     if (h->s_trk) cudaStreamDestroy(h->s_trk);
     if (h->s_copy) cudaStreamDestroy(h->s_copy);
+    for (cudaEvent_t e : h->ev_slice)
+        if (e) cudaEventDestroy(e);
     cudaEvent_t evs[] = {h->ev_copy, h->ev_a0, h->ev_a1, h->ev_t0, h->ev_t1};
     for (cudaEvent_t e : evs)
         if (e) cudaEventDestroy(e);
@@ -735,7 +738,7 @@ static int permute_tables(gb_handle* h)
     if (!h->pfa || h->D == 0) return GB_OK;
     int rc = ensure(h, &h->tables_perm, &h->tables_perm_cap, (size_t)h->D * h->N);
     if (rc) return rc;
-    CK(gb::acq_launch_permute(h->tables, 0, ~0ull, h->npos, h->N, h->D, h->tables_perm, h->s_acq));
+    CK(gb::acq_launch_permute(h->tables, 0, ~0ull, h->npos, h->N, 0, h->D, h->tables_perm, h->s_acq));
     CK(cudaStreamSynchronize(h->s_acq));
     return GB_OK;
 }
@@ -850,14 +853,17 @@ static int build_rows(gb_handle* h, uint32_t prn_mask, const uint8_t* enable)
 // permuted copies; the kernels' global reads then stay as coalesced as in the Cooley-Tukey plans
 static cudaError_t pfa_inputs(gb_handle* h, gb::AcqArgs& a, int K)
 {
-    cudaError_t e = gb::acq_launch_permute(a.iq, a.iq_start, a.iq_mask, h->npos, h->N, K, h->iq_perm, h->s_acq);
+    cudaError_t e = gb::acq_launch_permute(a.iq, a.iq_start, a.iq_mask, h->npos, h->N, 0, K, h->iq_perm, h->s_acq);
     a.iq = h->iq_perm; a.iq_start = 0; a.iq_mask = ~0ull;
     a.tables = h->tables_perm;
     return e;
 }
 
+// host_iq != nullptr: the chunk has NOT been uploaded yet.  In the shared-forward chain it is then uploaded in slices of
+// whole coherent groups on the copy stream while the forward path (which needs only its own group's blocks) of the
+// previous slice runs: cudaMemcpyAsync on a dedicated stream, events to the acquisition stream.
 static int search_cells(gb_handle* h, const float2* iq_dev, uint64_t start, uint64_t mask, int K, uint32_t prn_mask,
-                        const uint8_t* enable, gb_acq_cell* cells_out)
+                        const uint8_t* enable, gb_acq_cell* cells_out, const gb_c32* host_iq = nullptr)
 {
     if (h->plan < 0 || h->D == 0) return GB_ESTATE;
     if (K < 1 || K % h->n_coh != 0) return GB_EINVAL;
@@ -881,11 +887,13 @@ static int search_cells(gb_handle* h, const float2* iq_dev, uint64_t start, uint
         a.rows = h->rows_dev;
         a.D = h->D; a.K = K; a.n_coh = h->n_coh; a.n_active = n_active; a.spc = h->spc;
         a.cells = h->cells_dev; a.row_out = nullptr; a.d0 = 0; a.spec = nullptr; a.d_lo = 0;
-        a.otw = h->otw; a.acc_rows = nullptr; a.npos = h->npos;
+        a.otw = h->otw; a.acc_rows = nullptr; a.npos = h->npos; a.g_lo = 0; a.g_cnt = K / h->n_coh;
         if (h->pfa) {
             int rc = ensure(h, &h->iq_perm, &h->iq_perm_cap, (size_t)K * h->N);
             if (rc) return rc;
         }
+        if (host_iq && (h->cluster || h->mode != GB_ACQ_SHARED))
+            CK(cudaMemcpyAsync(h->chunk, host_iq, (size_t)K * h->N * sizeof(float2), cudaMemcpyHostToDevice, h->s_acq));
         if (h->cluster) {
             if (h->n_coh != 1) return GB_EUNSUPPORTED;
             int rc = ensure(h, &h->acc_rows, &h->acc_cap, (size_t)n_active * h->D * h->N);
@@ -903,12 +911,37 @@ static int search_cells(gb_handle* h, const float2* iq_dev, uint64_t start, uint
             int rc = ensure(h, &h->spec, &h->spec_cap, slab * per_d);
             if (rc) return rc;
             a.spec = h->spec;
+            const int n_groups = K / h->n_coh;
+            a.g_lo = 0; a.g_cnt = n_groups;
             CK(cudaEventRecord(h->ev_a0, h->s_acq));
-            if (h->pfa) CK(pfa_inputs(h, a, K));
-            for (int d_lo = 0; d_lo < h->D; d_lo += (int)slab) {
-                a.d_lo = d_lo;
-                const int n_d = (h->D - d_lo) < (int)slab ? (h->D - d_lo) : (int)slab;
-                CK(gb::acq_launch_shared(h->plan, a, n_d, h->s_acq));
+            if (host_iq && slab >= (size_t)h->D) {
+                // sliced upload overlapped with the forward path
+                const int n_slices = n_groups >= 8 ? 4 : (n_groups >= 2 ? 2 : 1);
+                if (h->pfa) { a.iq = h->iq_perm; a.iq_start = 0; a.iq_mask = ~0ull; a.tables = h->tables_perm; }
+                a.d_lo = 0;
+                for (int sl = 0; sl < n_slices; sl++) {
+                    const int g0 = (int)((long long)n_groups * sl / n_slices), g1 = (int)((long long)n_groups * (sl + 1) / n_slices);
+                    const size_t b0 = (size_t)g0 * h->n_coh, nb = (size_t)(g1 - g0) * h->n_coh;
+                    if (!h->ev_slice[sl]) CK(cudaEventCreateWithFlags(&h->ev_slice[sl], cudaEventDisableTiming));
+                    CK(cudaMemcpyAsync(h->chunk + b0 * h->N, host_iq + b0 * h->N, nb * h->N * sizeof(float2),
+                                       cudaMemcpyHostToDevice, h->s_copy));
+                    CK(cudaEventRecord(h->ev_slice[sl], h->s_copy));
+                    CK(cudaStreamWaitEvent(h->s_acq, h->ev_slice[sl], 0));
+                    if (h->pfa)
+                        CK(gb::acq_launch_permute(h->chunk, 0, ~0ull, h->npos, h->N, (int)b0, (int)nb, h->iq_perm, h->s_acq));
+                    a.g_lo = g0; a.g_cnt = g1 - g0;
+                    CK(gb::acq_launch_forward(h->plan, a, h->D, h->s_acq));
+                }
+                a.g_lo = 0; a.g_cnt = 0;   // forward path done: inverse kernel only
+                CK(gb::acq_launch_shared(h->plan, a, h->D, h->s_acq));
+            } else {
+                if (host_iq) CK(cudaMemcpyAsync(h->chunk, host_iq, (size_t)K * h->N * sizeof(float2), cudaMemcpyHostToDevice, h->s_acq));
+                if (h->pfa) CK(pfa_inputs(h, a, K));
+                for (int d_lo = 0; d_lo < h->D; d_lo += (int)slab) {
+                    a.d_lo = d_lo;
+                    const int n_d = (h->D - d_lo) < (int)slab ? (h->D - d_lo) : (int)slab;
+                    CK(gb::acq_launch_shared(h->plan, a, n_d, h->s_acq));
+                }
             }
             CK(cudaEventRecord(h->ev_a1, h->s_acq));
         } else {
@@ -942,9 +975,11 @@ extern "C" int gb_acq_search_cells(gb_handle* h, const gb_c32* iq, int K, uint32
 {
     if (!h) return GB_EINVAL;
     CK(cudaSetDevice(h->device));
-    int rc = stage_chunk(h, iq, K);
+    if (!iq || K < 1) return GB_EINVAL;
+    if (h->plan < 0) return GB_ESTATE;
+    int rc = ensure(h, &h->chunk, &h->chunk_cap, (size_t)K * h->N);
     if (rc) return rc;
-    return search_cells(h, h->chunk, 0, ~0ull, K, prn_mask, enable, cells_out);
+    return search_cells(h, h->chunk, 0, ~0ull, K, prn_mask, enable, cells_out, iq);
 }
 
 static int ring_range_ok(gb_handle* h, uint64_t local_tail, uint64_t n)
@@ -1061,7 +1096,7 @@ extern "C" int gb_acq_bin_power(gb_handle* h, const gb_c32* iq, int K, int prn, 
     a.rows = h->rows_dev;
     a.D = h->D; a.K = K; a.n_coh = h->n_coh; a.n_active = 1; a.spc = 0;
     a.cells = nullptr; a.row_out = h->row_dev; a.d0 = doppler_bin; a.spec = nullptr; a.d_lo = 0;
-    a.otw = h->otw; a.acc_rows = nullptr; a.npos = h->npos;
+    a.otw = h->otw; a.acc_rows = nullptr; a.npos = h->npos; a.g_lo = 0; a.g_cnt = K / h->n_coh;
     if (h->pfa) {
         rc = ensure(h, &h->iq_perm, &h->iq_perm_cap, (size_t)K * h->N);
         if (rc) return rc;
