@@ -326,7 +326,8 @@ def run_ours(args, rank, world, local_rank):
 
     def step_device():
         flush.zero_()
-        torch.cuda.synchronize()
+        # re-align the ranks after the (untimed) L2 flush so the timed gather measures the collective, not flush skew
+        barrier()
         t0 = time.perf_counter()
         res = eng.search_ring(0, K_MS, prn_mask=prn_mask)
         ms = eng.last_kernel_ms()

@@ -42,13 +42,14 @@ def test_header_is_plain_c(tmp_path):
 
 def test_struct_layouts_match_header(ffi, tmp_path):
     src = tmp_path / "s.c"
-    src.write_text('#include <stdio.h>\n#include "gnss_b200.h"\nint main(void){printf("%zu %zu %zu %zu %zu\\n", sizeof(gb_acq_cell),'
-                   ' sizeof(gb_acq_result), sizeof(gb_trk_channel), sizeof(gb_trk_corr), sizeof(gb_config));return 0;}\n')
+    src.write_text('#include <stdio.h>\n#include "gnss_b200.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(gb_acq_cell),'
+                   ' sizeof(gb_acq_result), sizeof(gb_trk_channel), sizeof(gb_trk_corr), sizeof(gb_config), sizeof(gb_fine_req),'
+                   ' sizeof(gb_fine_result), sizeof(gb_nav_sync));return 0;}\n')
     exe = tmp_path / "s"
     subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
     sizes = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
     assert sizes == [ffi.CELL_DTYPE.itemsize, C.sizeof(ffi.AcqResult), C.sizeof(ffi.TrkChannel), ffi.CORR_DTYPE.itemsize,
-                     C.sizeof(ffi.Config)]
+                     C.sizeof(ffi.Config), ffi.FINE_REQ_DTYPE.itemsize, ffi.FINE_RES_DTYPE.itemsize, ffi.NAV_DTYPE.itemsize]
 
 
 def test_no_device_means_error_not_fallback(ffi):
