@@ -588,10 +588,14 @@ template <class P> static cudaError_t launch_shared(const AcqArgs& a, int n_d, c
         if ((e = launch_forward<P>(a, n_d, st)) != cudaSuccess) return e;
     }
     // double-buffered line when two lines fit the 227 KB of one SM at the plan's CTA count
-    constexpr bool kDB = P::DB;
-    const size_t smem_inv = kDB ? 2 * smem : smem;
-    if ((e = set_smem(acq_inverse_kernel<P, kDB>, smem_inv)) != cudaSuccess) return e;
-    acq_inverse_kernel<P, kDB><<<n_d * a.n_active, P::T, smem_inv, st>>>(a);
+    static const bool no_db = getenv("GB_ACQ_NODB") != nullptr;   // A/B switch (tools/time_acq.py)
+    if (P::DB && !no_db) {
+        if ((e = set_smem(acq_inverse_kernel<P, true>, 2 * smem)) != cudaSuccess) return e;
+        acq_inverse_kernel<P, true><<<n_d * a.n_active, P::T, 2 * smem, st>>>(a);
+    } else {
+        if ((e = set_smem(acq_inverse_kernel<P, false>, smem)) != cudaSuccess) return e;
+        acq_inverse_kernel<P, false><<<n_d * a.n_active, P::T, smem, st>>>(a);
+    }
     return cudaGetLastError();
 }
 template <class P> static cudaError_t launch_row(const AcqArgs& a, cudaStream_t st)
