@@ -11,8 +11,9 @@ using P1024 = Plan<1024, 64, 8, 4, 4, 16, 16>;
 using P2048 = Plan<2048, 128, 4, 4, 8, 16, 16>;
 using P4092 = PfaPlan<4092, 160, 4, 0, 12, 11, 31>;
 using P4096 = Plan<4096, 256, 2, 4, 16, 16, 16>;
-using P8184 = PfaPlan<8184, 288, 1, 0, 8, 3, 11, 31>;
-using P16368 = PfaPlan<16368, 544, 1, 0, 16, 3, 11, 31>;
+// 3 x 11 is one Good-Thomas radix-33 butterfly in registers (no internal twiddles): three shared-memory stages, not four
+using P8184 = PfaPlan<8184, 288, 1, 0, 8, 33, 31>;
+using P16368 = PfaPlan<16368, 544, 1, 0, 16, 33, 31>;
 using P20000 = Plan<20000, 512, 1, 0, 8, 4, 25, 25>;
 
 // tuning variants of the headline plan (selected with the environment variable GB_ACQ_VARIANT=1..4)
@@ -24,8 +25,8 @@ using P4092v5 = PfaStreamPlan<3, 4092, 160, 4, 0, 12, 11, 31>;
 using P4092v6 = PfaStreamPlan<5, 4092, 160, 4, 0, 12, 11, 31>;
 using P4092v7 = PfaStreamPlan<3, 4092, 160, 3, 0, 12, 11, 31>;
 using P4092v8 = PfaStreamPlan<5, 4092, 160, 3, 0, 12, 11, 31>;
-using P16368v1 = Plan<16368, 288, 1, 0, 16, 3, 11, 31>;
-using P16368v2 = Plan<16368, 416, 1, 0, 16, 3, 11, 31>;
+using P16368v1 = PfaPlan<16368, 544, 1, 0, 16, 3, 11, 31>;   // the four-stage form (A/B)
+using P16368v2 = PfaPlan<16368, 512, 1, 0, 16, 33, 31>;
 
 // reference arithmetic of multiply_simd_block (doppler_shift.rs:43-58): separate roundings, no FMA
 __device__ __forceinline__ float2 wipe(float2 x, float2 w)

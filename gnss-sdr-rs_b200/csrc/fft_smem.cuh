@@ -419,7 +419,48 @@ template <int A, int B, bool INV> struct DftComposite {
         }
     }
 };
+// Composite R = A*B with gcd(A, B) = 1 in registers, Good-Thomas form: input n = (B n1 + A n2) mod R, output k with
+// k = k1 (mod A), k = k2 (mod B).  All index maps are compile-time, so they are pure register renaming and the butterfly
+// has NO internal twiddle multiplies (DftComposite needs (A-1)(B-1) of them).
+constexpr int pfa_inv_mod(int a, int m)
+{
+    int x = 1;
+    while ((a % m) * x % m != 1) x++;
+    return x;
+}
+template <int A, int B, bool INV> struct DftPfaComposite {
+    static constexpr int R = A * B;
+    static constexpr int E1 = B * pfa_inv_mod(B, A);   // = 1 (mod A), 0 (mod B)
+    static constexpr int E2 = A * pfa_inv_mod(A, B);   // = 0 (mod A), 1 (mod B)
+    static __device__ __forceinline__ void run(float2 (&v)[R])
+    {
+        float2 t[A][B];
+#pragma unroll
+        for (int n2 = 0; n2 < B; n2++) {
+            float2 c[A];
+#pragma unroll
+            for (int n1 = 0; n1 < A; n1++) c[n1] = v[(B * n1 + A * n2) % R];
+            Dft<A, INV>::run(c);
+#pragma unroll
+            for (int k1 = 0; k1 < A; k1++) t[k1][n2] = c[k1];
+        }
+#pragma unroll
+        for (int k1 = 0; k1 < A; k1++) {
+            float2 c[B];
+#pragma unroll
+            for (int n2 = 0; n2 < B; n2++) c[n2] = t[k1][n2];
+            Dft<B, INV>::run(c);
+#pragma unroll
+            for (int k2 = 0; k2 < B; k2++) v[(k1 * E1 + k2 * E2) % R] = c[k2];
+        }
+    }
+};
+#ifdef GB_CT_RADIX12
 template <bool INV> struct Dft<12, INV> : DftComposite<4, 3, INV> {};
+#else
+template <bool INV> struct Dft<12, INV> : DftPfaComposite<4, 3, INV> {};
+#endif
+template <bool INV> struct Dft<33, INV> : DftPfaComposite<3, 11, INV> {};
 template <bool INV> struct Dft<25, INV> : DftComposite<5, 5, INV> {};
 template <bool INV> struct Dft<32, INV> : DftComposite<4, 8, INV> {};
 
