@@ -318,6 +318,7 @@ def run_ours(args, rank, world, local_rank):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     cuda_dev = torch.device("cuda", local_rank)
     gatherer = sharding.ResultGatherer(dist, cuda_dev, N_PRN) if dist is not None else None
+    raw_gatherer = sharding.RawResultGatherer(dist, cuda_dev, N_PRN, ffi.AcqResult) if dist is not None else None
 
     def barrier():
         if dist is not None:
@@ -329,20 +330,29 @@ def run_ours(args, rank, world, local_rank):
         # re-align the ranks after the (untimed) L2 flush so the timed gather measures the collective, not flush skew
         barrier()
         t0 = time.perf_counter()
-        res = eng.search_ring(0, K_MS, prn_mask=prn_mask)
-        ms = eng.last_kernel_ms()
         g_ms = 0.0
-        if dist is not None:
-            # the one collective of the path: per-PRN results of every rank, NCCL over NVLink
+        if dist is None:
+            res = eng.search_ring(0, K_MS, prn_mask=prn_mask)
+            ms = eng.last_kernel_ms()
+        else:
+            # results land in the gatherer's pinned buffer; the one collective of the path ships the raw structs of
+            # every rank, NCCL over NVLink
+            eng.search_ring_raw(0, K_MS, prn_mask=prn_mask, out=raw_gatherer.results)
+            ms = eng.last_kernel_ms()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            gathered = gatherer.gather(res)
+            per_rank = raw_gatherer.gather()
             e1.record()
             torch.cuda.synchronize()
             g_ms = e0.elapsed_time(e1)
-            if by_prn:
-                merged = sharding.merge_prn_shards(gathered)
-                res = [({"prn": p + 1, "found": 1} if merged[p, 0] else None) for p in range(N_PRN)]
+            if by_prn:   # every PRN is owned by exactly one rank
+                res = [None] * N_PRN
+                for arr in per_rank:
+                    for r in arr:
+                        if r.found:
+                            res[r.prn - 1] = r.as_dict()
+            else:
+                res = [r.as_dict() if r.found else None for r in per_rank[rank]]
         return ms + g_ms, (time.perf_counter() - t0) * 1e3, res
 
     for _ in range(max(args.warmup, 3)):

@@ -129,6 +129,14 @@ class AcquisitionEngine:
         self.hd.call("gb_acq_search_ring", int(local_tail), int(num_integrations), int(prn_mask), _ffi.ptr(en), res)
         return [r.as_dict() if r.found else None for r in res]
 
+    def search_ring_raw(self, local_tail, num_integrations, prn_mask=0xFFFFFFFF, enable=None, out=None):
+        """search_ring without the per-result Python objects: fills and returns a (gb_acq_result * n_prn) ctypes array
+        (the form the multi-GPU gather ships as raw bytes)."""
+        res = out if out is not None else (_ffi.AcqResult * self.n_prn)()
+        en = self._enable(enable)
+        self.hd.call("gb_acq_search_ring", int(local_tail), int(num_integrations), int(prn_mask), _ffi.ptr(en), res)
+        return res
+
     def bin_power(self, samples, num_integrations, prn, doppler_bin):
         x = np.ascontiguousarray(samples, np.complex64)
         out = np.zeros(self.n, np.float32)

@@ -112,3 +112,31 @@ def search_batch(engine, recordings, num_integrations, rank=0, world=1, dist=Non
              for i in mine]
     local = np.stack(local) if local else np.zeros((0, engine.n_prn, len(RESULT_FIELDS)))
     return gather_batch(local, n_total, dist, device)
+
+
+class RawResultGatherer:
+    """The per-search collective on the C-ABI's own result structs: the (gb_acq_result * n_prn) array of every rank
+    (1.8 KB) is viewed as bytes in a pinned host tensor, copied to the device and exchanged with ONE
+    all_gather_into_tensor (NCCL over NVLink; gloo in the CPU tests) -- no per-field packing on the host."""
+
+    def __init__(self, dist, device, n_prn, result_type):
+        import ctypes
+        import torch
+        self.dist, self.device, self.n_prn, self.result_type = dist, device, n_prn, result_type
+        self.world = dist.get_world_size()
+        self.nbytes = ctypes.sizeof(result_type) * n_prn
+        cuda = device is not None and str(device).startswith("cuda")
+        self.host_in = torch.zeros(self.nbytes, dtype=torch.uint8, pin_memory=cuda)
+        self.results = (result_type * n_prn).from_address(self.host_in.data_ptr())   # the search writes straight into it
+        self.dev_in = torch.zeros_like(self.host_in, device=device) if cuda else self.host_in
+        self.dev_out = torch.zeros(self.world * self.nbytes, dtype=torch.uint8, device=device if cuda else "cpu")
+        self.host_out = torch.zeros(self.world * self.nbytes, dtype=torch.uint8, pin_memory=cuda)
+
+    def gather(self):
+        """Exchange self.results; returns a list (one per rank) of (result_type * n_prn) arrays viewing the host copy."""
+        if self.dev_in is not self.host_in:
+            self.dev_in.copy_(self.host_in, non_blocking=True)
+        self.dist.all_gather_into_tensor(self.dev_out, self.dev_in)
+        self.host_out.copy_(self.dev_out)
+        base = self.host_out.data_ptr()
+        return [(self.result_type * self.n_prn).from_address(base + r * self.nbytes) for r in range(self.world)]

@@ -27,6 +27,22 @@ def _worker(rank, world, port, out_dir):
     merged = sharding.merge_prn_shards(gathered)
     again = sharding.ResultGatherer(dist, None, 32).gather(results)   # the preallocated form bench.py uses
     assert all((a == b).all() for a, b in zip(gathered, again))
+    # raw-struct form (what bench.py ships): the C-ABI result array goes over the wire as bytes
+    import gnss_sdr_rs_b200._ffi as ffi
+    rg = sharding.RawResultGatherer(dist, None, 32, ffi.AcqResult)
+    for p in range(32):
+        r = results[p]
+        rg.results[p].prn = p + 1
+        rg.results[p].found = 1 if r else 0
+        rg.results[p].code_phase_samples = r["code_phase_samples"] if r else 0
+        rg.results[p].carrier_freq = r["carrier_freq"] if r else 0.0
+    per_rank = rg.gather()
+    raw_found = sorted(int(x.prn) for arr in per_rank for x in arr if x.found)
+    assert raw_found == sorted(present - {5}), raw_found
+    for arr in per_rank:
+        for x in arr:
+            if x.found:
+                assert x.code_phase_samples == 100 * x.prn and x.carrier_freq == 500.0 * x.prn
     np.save(os.path.join(out_dir, "merged_%d.npy" % rank), merged)
     np.save(os.path.join(out_dir, "mask_%d.npy" % rank), np.array([mask], np.uint64))
     # batch snapshot acquisition (BASELINE configs[4]): 13 recordings dealt to the ranks, one padded gather at the end
