@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define GB_VERSION 100
+#define GB_VERSION 110
 
 /* ---- error codes ---- */
 #define GB_OK 0
@@ -160,7 +160,9 @@ int gb_acq_search_ring(gb_handle *h, uint64_t local_tail, int num_integrations, 
                        const uint8_t *enable, gb_acq_result *results);
 /* accumulated power row of one (prn, doppler bin) -- diagnostics / tests */
 int gb_acq_bin_power(gb_handle *h, const gb_c32 *iq, int num_integrations, int prn, int doppler_bin, float *power_out);
-/* device time of the last search's kernels in milliseconds (CUDA events on the acquisition stream) */
+/* device time of the last search in milliseconds (CUDA events on the acquisition stream).  For the ring-resident
+ * searches this is kernel time only; for the host-buffer searches the sliced upload is overlapped with the forward
+ * path inside the same pair of events, so the figure includes the part of the H2D copy that could not be hidden. */
 float gb_acq_last_kernel_ms(gb_handle *h);
 
 /* ------------------------------------------------------------------ fine Doppler

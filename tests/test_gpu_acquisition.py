@@ -250,3 +250,44 @@ def test_errors_and_edge_cases(gpu, ffi):
     with pytest.raises(ffi.GnssB200Error) as e:  # K not a multiple of n_coh
         eng.search_cells(np.zeros(3 * 2048, np.complex64), 3)
     assert e.value.code == ffi.GB_EINVAL
+
+
+def test_config2_full_size_properties(gpu):
+    """BASELINE configs[1] at full size (N = 4092, 32 PRNs, 201 Doppler bins, 10 ms coherent x 20 non-coherent, 200 ms of
+    signal) through properties that need no oracle: determinism; exact homogeneity (power-of-two scaling of the input is
+    exact in f32, so every cell scales by exactly 4 and no arg-max moves); shift equivariance (dropping s samples moves
+    every strong cell's code phase by -s mod N and leaves its Doppler bin); the eight satellites of the scene are found at
+    their code phases and nearest Doppler bins and nothing else passes the two-peak test."""
+    import bench
+    from gnss_sdr_rs_b200 import acquisition
+    n, K, s = bench.N_FFT, bench.K_MS, 1000
+    from gnss_sdr_rs_b200 import sdr_mock
+    sats = [{"prn": p, "doppler": d, "code_phase": c, "cn0_dbhz": cn} for p, d, c, cn in bench.SATS]
+    x = sdr_mock.baseband(bench.FS, K + 1, sats, seed=0x6E56, nav=False)
+    eng = acquisition.AcquisitionEngine(gpu, n, bench.FS)
+    eng.make_doppler_tables(0.0, bench.DOPPLERS)
+    eng.set_coherent(bench.N_COH)
+    eng.set_detector(7.0, 4)
+    a = eng.search_cells(x[:K * n], K)
+    b = eng.search_cells(x[:K * n], K)
+    assert a.tobytes() == b.tobytes()                                   # deterministic
+    c = eng.search_cells((x[:K * n] * np.complex64(2.0)), K)
+    assert (c["argmax"] == a["argmax"]).all()
+    assert (c["peak"] == a["peak"] * np.float32(4.0)).all() and (c["sum8"] == a["sum8"] * np.float32(4.0)).all()
+    d = eng.search_cells(x[s:s + K * n], K)
+    best = a["peak"].argmax(axis=1)
+    truth = {p: (dp, cp) for p, dp, cp, _ in bench.SATS}
+    found = []
+    for p in range(32):
+        bb = int(best[p])
+        ratio = np.sqrt(a["peak"][p, bb] / a["peak2"][p, bb])
+        if ratio > 1.4:                                                  # acquisition_bk.rs two-peak threshold
+            found.append(p + 1)
+            dp, cp = truth[p + 1]
+            assert abs(float(bench.DOPPLERS[bb]) - dp) <= 25.0 + 1e-3
+            assert min((int(a["argmax"][p, bb]) - cp) % n, (cp - int(a["argmax"][p, bb])) % n) <= 1
+            # shift equivariance on the detected cell
+            assert int(d["peak"][p].argmax()) == bb
+            assert (int(a["argmax"][p, bb]) - int(d["argmax"][p, bb])) % n in (s % n, (s - 1) % n, (s + 1) % n)
+            assert abs(d["peak"][p, bb] / a["peak"][p, bb] - 1) < 0.2
+    assert sorted(found) == sorted(truth), found
