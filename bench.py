@@ -428,7 +428,7 @@ def run_ours(args, rank, world, local_rank):
                              "kernel": ("acq_fused_kernel" if args.acq_mode == "fused" else "permute_blocks_kernel + acq_forward_kernel + acq_inverse_kernel") + "<PfaPlan<4092,160,4,12,11,31>>", "kernel_ms": kernel_ms_avg,
                              "kernel_shares_ncu": "acq_inverse_kernel 90% / acq_forward_kernel 10% / permute < 1% of the chain; "
                                                   "inverse kernel: FMA pipe 67% active, L1 data pipe 63%, issue 51% "
-                                                  "(profiles/round1_v5_pfa_ffma2.txt)",
+                                                  "(profiles/round1_v6_final.txt)",
                              "hbm_view": {"bound": "hbm", "algorithmic_bytes": acq_bytes(args.acq_mode != "fused"),
                                           "achieved": acq_bytes(args.acq_mode != "fused") / (kernel_ms_avg * 1e-3) / 1e9,
                                           "peak": hbm_peak, "unit": "GB/s",
