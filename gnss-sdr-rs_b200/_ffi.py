@@ -10,7 +10,7 @@ LIB_PATH = os.path.join(_HERE, "libgnss_b200.so")
 GB_OK, GB_EINVAL, GB_ENODEVICE, GB_ECUDA, GB_EUNSUPPORTED, GB_ESTATE, GB_ENOMEM, GB_ERANGE = 0, -1, -2, -3, -4, -5, -6, -7
 GB_TRK_IDLE, GB_TRK_TRACKING = 0, 1
 GB_TRK_FAST, GB_TRK_ORDERED = 0, 1
-GB_ACQ_FUSED, GB_ACQ_SHARED = 0, 1
+GB_ACQ_FUSED, GB_ACQ_SHARED, GB_ACQ_SHARED_PLAIN = 0, 1, 2
 
 
 class GnssB200Error(RuntimeError):

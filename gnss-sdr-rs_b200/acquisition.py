@@ -89,7 +89,8 @@ class AcquisitionEngine:
         self.n_coh = int(n_coh)
 
     def set_mode(self, mode):
-        """_ffi.GB_ACQ_FUSED (single kernel) or _ffi.GB_ACQ_SHARED (forward path shared by all PRNs, default)."""
+        """_ffi.GB_ACQ_FUSED (single kernel), _ffi.GB_ACQ_SHARED (forward path shared by all PRNs, default) or
+        _ffi.GB_ACQ_SHARED_PLAIN (the shared chain with the generic inverse kernel at every size, A/B)."""
         self.hd.call("gb_acq_set_mode", int(mode))
 
     def set_detector(self, threshold=7.0, samples_per_chip=0):

@@ -11,6 +11,8 @@
 
 #include <stdlib.h>
 
+#include <type_traits>
+
 namespace gb {
 
 #define GB_FOR_EACH_PLAN(X) X(0, P1024) X(1, P2048) X(2, P4092) X(3, P4096) X(4, P8184) X(5, P16368) X(6, P20000) \
@@ -61,125 +63,6 @@ __device__ __forceinline__ void stage0_wipe_forward(const AcqArgs& a, const floa
 #pragma unroll
             for (int q = 1; q < G0::R; q++)
                 line[P::phys(i + q * G0::SUB)] = P::PFA ? v[q] : cmul(v[q], __ldg(&tw[(q - 1) * G0::SUB + i]));
-        }
-    }
-}
-
-// Row reduction shared by the fused and the shared-forward kernels: peak / first argmax / 8-lane sum
-// (Q2: only the first 8*floor(N/8) bins) / second peak outside +-spc of the first.
-// For prime-factor plans the code-phase index of line position l is npos[l] (the Ruritanian map).
-template <class P>
-__device__ __forceinline__ void reduce_row_to_cell(float (&acc)[StageGeo<P, 0>::ITERS][StageGeo<P, 0>::R], float2* line,
-                                                   int spc, gb_acq_cell* out, const int* __restrict__ npos)
-{
-    using G0 = StageGeo<P, 0>;
-    constexpr int N = P::N;
-    constexpr int NSUM = (N / 8) * 8;
-    constexpr int NW = P::T / 32;
-    PeakIdx pk;
-    pk.v = 0.f;
-    pk.idx = 0u;
-    float sum = 0.f;
-#pragma unroll
-    for (int it = 0; it < G0::ITERS; it++) {
-        const int i = threadIdx.x + it * P::T;
-        if (G0::NB % P::T == 0 || i < G0::NB) {
-#pragma unroll
-            for (int j = 0; j < G0::R; j++) {
-                const int n = P::PFA ? __ldg(&npos[i + j * G0::SUB]) : i + j * G0::SUB;
-                const float v = acc[it][j];
-                PeakIdx c;
-                c.v = v;
-                c.idx = (unsigned)n;
-                if (v > 0.f) pk = peak_merge(pk, c);
-                if (NSUM == N || n < NSUM) sum += v;
-            }
-        }
-    }
-    pk = warp_peak(pk);
-    sum = warp_sum(sum);
-    float* red_v = reinterpret_cast<float*>(line);
-    unsigned* red_i = reinterpret_cast<unsigned*>(line) + 64;
-    float* red_s = reinterpret_cast<float*>(line) + 128;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (lane == 0) {
-        red_v[warp] = pk.v;
-        red_i[warp] = pk.idx;
-        red_s[warp] = sum;
-    }
-    __syncthreads();
-    if (warp == 0) {
-        PeakIdx q;
-        q.v = lane < NW ? red_v[lane] : 0.f;
-        q.idx = lane < NW ? red_i[lane] : 0u;
-        float s = lane < NW ? red_s[lane] : 0.f;
-        q = warp_peak(q);
-        s = warp_sum(s);
-        if (lane == 0) {
-            red_v[32] = q.v;
-            red_i[32] = q.idx;
-            red_s[32] = s;
-        }
-    }
-    __syncthreads();
-    const float peak = red_v[32];
-    const unsigned arg = red_i[32];
-    const float total = red_s[32];
-    float p2 = 0.f;
-    if (spc > 0) {
-#pragma unroll
-        for (int it = 0; it < G0::ITERS; it++) {
-            const int i = threadIdx.x + it * P::T;
-            if (G0::NB % P::T == 0 || i < G0::NB) {
-#pragma unroll
-                for (int j = 0; j < G0::R; j++) {
-                    const int n = P::PFA ? __ldg(&npos[i + j * G0::SUB]) : i + j * G0::SUB;
-                    if (two_peak_searched(n, (int)arg, spc, N)) p2 = fmaxf(p2, acc[it][j]);
-                }
-            }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) p2 = fmaxf(p2, __shfl_xor_sync(0xffffffffu, p2, o));
-        __syncthreads();
-        if (lane == 0) red_v[warp] = p2;
-        __syncthreads();
-        if (warp == 0) {
-            float v = lane < NW ? red_v[lane] : 0.f;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-            p2 = v;
-        }
-    }
-    if (threadIdx.x == 0) {
-        gb_acq_cell c;
-        c.peak = peak;
-        c.argmax = arg;
-        c.sum8 = total;
-        c.peak2 = p2;
-        *out = c;
-    }
-}
-
-// Final inverse stage (DIT, L = N) fused with |.|^2 accumulate; outputs are in natural order.
-template <class P>
-__device__ __forceinline__ void final_stage_accumulate(const float2* __restrict__ line, const float2* __restrict__ tw,
-                                                       float (&acc)[StageGeo<P, 0>::ITERS][StageGeo<P, 0>::R])
-{
-    using G0 = StageGeo<P, 0>;
-#pragma unroll
-    for (int it = 0; it < G0::ITERS; it++) {
-        const int i = threadIdx.x + it * P::T;
-        if (G0::NB % P::T == 0 || i < G0::NB) {
-            float2 v[G0::R];
-            v[0] = line[P::phys(i)];
-#pragma unroll
-            for (int q = 1; q < G0::R; q++) {
-                const float2 u = line[P::phys(i + q * G0::SUB)];
-                v[q] = P::PFA ? u : cmul_conj(u, __ldg(&tw[(q - 1) * G0::SUB + i]));
-            }
-            Dft<G0::R, true>::run(v);
-#pragma unroll
-            for (int j = 0; j < G0::R; j++) acc[it][j] += v[j].x * v[j].x + v[j].y * v[j].y;
         }
     }
 }
@@ -586,6 +469,12 @@ template <class P> static cudaError_t launch_shared(const AcqArgs& a, int n_d, c
     cudaError_t e;
     if (a.g_cnt > 0) {   // g_cnt == 0: the forward path was already launched slice by slice (acq_launch_forward)
         if ((e = launch_forward<P>(a, n_d, st)) != cudaSuccess) return e;
+    }
+    if constexpr (std::is_same<P, P4092>::value) {
+        static const bool no_lw = getenv("GB_ACQ_NOLW") != nullptr;   // A/B switch (tools/time_acq.py)
+        if (!no_lw && !a.plain_inverse) {
+            return acq_launch_inverse_lw4092(a, n_d, st);   // acq_lw.cu
+        }
     }
     // double-buffered line when two lines fit the 227 KB of one SM at the plan's CTA count
     static const bool no_db = getenv("GB_ACQ_NODB") != nullptr;   // A/B switch (tools/time_acq.py)

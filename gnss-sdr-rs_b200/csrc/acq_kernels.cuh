@@ -27,6 +27,7 @@ struct AcqArgs {
     const int* npos;         // prime-factor plans: code-phase index n(l) of line position l (else unused)
     const float2* otw;       // cluster plans: outer twiddles W_N^(i q), layout [q-1][i]
     float* acc_rows;         // cluster plans: (n_active*D) x N accumulated power rows (scratch)
+    int plain_inverse;       // shared-forward chain: 1 = acq_inverse_kernel even where a leftover-warp form exists (A/B)
 };
 
 struct FftArgs {
@@ -49,6 +50,8 @@ size_t acq_plan_smem(int plan);
 cudaError_t acq_launch_search(int plan, const AcqArgs& a, cudaStream_t st);
 // forward kernel over n_d bins [a.d_lo, a.d_lo+n_d) then inverse kernel over n_active x n_d cells
 cudaError_t acq_launch_shared(int plan, const AcqArgs& a, int n_d, cudaStream_t st);
+// N = 4092 shared chain: inverse kernel with a leftover warp (acq_lw.cu); the forward spectra must be in a.spec
+cudaError_t acq_launch_inverse_lw4092(const AcqArgs& a, int n_d, cudaStream_t st);
 cudaError_t acq_launch_row(int plan, const AcqArgs& a, cudaStream_t st);
 cudaError_t acq_launch_code_fft(int plan, const int8_t* codes, int n_prn, float2* code_fft, const float2* tw,
                                 const int* npos, cudaStream_t st);

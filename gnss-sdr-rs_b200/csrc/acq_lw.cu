@@ -1,0 +1,119 @@
+// acq_lw.cu -- leftover-warp form of the shared-chain inverse kernel for N = 4092 (its own translation unit: the
+// plan zoo of acq_kernels.cu takes two minutes to compile).
+#include "acq_common.cuh"
+
+namespace gb {
+
+// ------------------------------------------------------------------ leftover-warp form of the inverse kernel
+// 4092 / 31 = 132 first-stage butterflies per code period = 4 warps + 4 threads: in acq_inverse_kernel the fifth warp
+// runs the whole radix-31 instruction stream for 4 of its 32 lanes, a fifth of that stage's FMA-pipe time.  Here the CTA
+// is PW::T working threads (whole warps; PW = the same radices on T = 128, which also owns stages B and C) plus ONE
+// leftover warp that batches the REM = NB - PW::T ragged butterflies of 32 / REM consecutive groups into one full-warp
+// pass: lane l computes butterfly PW::T + l % REM of group g0 + l / REM, keeps the finished accumulators in registers
+// (OddPrimeAcc) and hands them to the line when their group comes round -- it runs one batch ahead of the working
+// warps, so its arithmetic overlaps their stages B and C.  20 groups: 83 radix-31 warp passes instead of 100.
+// Named barriers (the warp-specialised pattern): A_DONE = line of group g complete (working warps wait, the leftover
+// warp only arrives), MID = between stages B and C (working warps only), END = line free again (everybody).
+// Every output accumulates its terms in the same order as dft_odd_prime_emit, so cells are bit-identical to
+// acq_inverse_kernel's (tests/test_gpu_acquisition.py::test_leftover_warp_kernel_is_bit_identical).
+enum { BAR_A_DONE = 1, BAR_MID = 2, BAR_END = 3 };
+
+template <class PW>
+__device__ __noinline__ void lw_leftover_warp(const float2* __restrict__ spec, const float2* __restrict__ code,
+                                              float2* __restrict__ line, int n_groups)
+{
+    constexpr int LASTS = PW::NSTAGE - 1;
+    using GM = StageGeo<PW, LASTS>;
+    constexpr int N = PW::N;
+    constexpr int TW = PW::T, TALL = PW::T + 32;
+    constexpr int REM = GM::NB - TW;
+    constexpr int BATCH = 32 / REM;
+    const int lane = threadIdx.x - TW;
+    const int b = TW + lane % REM, slot = lane / REM;
+    OddPrimeAcc<GM::R> h;
+    auto compute = [&](int g0) {
+        const int g = g0 + slot;
+        if (g < n_groups) {
+            const float2* __restrict__ sg = spec + (size_t)g * N;
+            dft_odd_prime_stream_acc<GM::R, true, 3>(
+                [&](int q) { return cmul_conj(__ldg(&sg[q * GM::NB + b]), __ldg(&code[q * GM::NB + b])); }, h);
+        }
+    };
+    compute(0);
+    for (int g = 0; g < n_groups; g++) {
+        if (g > 0) named_bar_sync(BAR_END, TALL);   // group g-1 has left the line
+        if (slot == g % BATCH)
+            dft_odd_prime_stream_emit<GM::R>(h, [&](int j, float2 y) { line[PW::phys(b * GM::R + j)] = y; });
+        __threadfence_block();   // bar.arrive alone does not order the shared-memory stores before the arrival
+        __syncwarp();
+        named_bar_arrive(BAR_A_DONE, TALL);
+        if (g % BATCH == BATCH - 1 && g + 1 < n_groups) compute(g + 1);
+    }
+    named_bar_sync(BAR_END, TALL);
+}
+
+template <class PW> __global__ void __launch_bounds__(PW::T + 32, PW::MINB) acq_inverse_lw_kernel(const AcqArgs a)
+{
+    extern __shared__ float2 smem_line[];
+    constexpr int LASTS = PW::NSTAGE - 1;
+    using G0 = StageGeo<PW, 0>;
+    using GM = StageGeo<PW, LASTS>;
+    constexpr int N = PW::N;
+    constexpr int TW = PW::T, TALL = PW::T + 32;
+    constexpr int REM = GM::NB - TW;     // ragged butterflies per group
+    constexpr int BATCH = 32 / REM;      // groups per leftover pass
+    static_assert(PW::PFA && LASTS == 2, "three-stage prime-factor plans only");
+    static_assert(REM > 0 && REM <= 16 && 32 % REM == 0, "the ragged part must tile a warp");
+    const int n_groups = a.K / a.n_coh;
+    const int dl = (int)(blockIdx.x / (unsigned)a.n_active);
+    const int row = a.rows[blockIdx.x % (unsigned)a.n_active];
+    const float2* __restrict__ code = a.code_fft + (size_t)row * N;
+    const float2* __restrict__ spec = a.spec + (size_t)dl * n_groups * N;
+    float2* __restrict__ line = smem_line;
+
+    if (threadIdx.x >= TW) {
+        lw_leftover_warp<PW>(spec, code, line, n_groups);
+        return;
+    }
+    {
+        // ---- working warps
+        float acc[G0::ITERS][G0::R];
+#pragma unroll
+        for (int it = 0; it < G0::ITERS; it++)
+#pragma unroll
+            for (int j = 0; j < G0::R; j++) acc[it][j] = 0.f;
+        const int b = threadIdx.x;
+        for (int g = 0; g < n_groups; g++) {
+            const float2* __restrict__ sg = spec + (size_t)g * N;
+            {
+                float2 v[GM::R];
+#pragma unroll
+                for (int q = 0; q < GM::R; q++) v[q] = cmul_conj(__ldg(&sg[q * GM::NB + b]), __ldg(&code[q * GM::NB + b]));
+                dft_emit<GM::R, true>(v, [&](int j, float2 y) { line[PW::phys(b * GM::R + j)] = y; });
+            }
+            named_bar_sync(BAR_A_DONE, TALL);
+            dit_stage<PW, 1, true>(line, a.tw);
+            named_bar_sync(BAR_MID, TW);
+            final_stage_accumulate<PW>(line, a.tw, acc);
+            named_bar_sync(BAR_END, TALL);
+        }
+        reduce_row_to_cell<PW, BAR_MID>(acc, smem_line, a.spc, &a.cells[(size_t)row * a.D + a.d_lo + dl], a.npos);
+    }
+}
+
+cudaError_t acq_launch_inverse_lw4092(const AcqArgs& a, int n_d, cudaStream_t st)
+{
+    using PW = P4092W;
+    static_assert(PW::T + 32 == P4092::T && PW::LINE == P4092::LINE, "same line as the default plan, one extra warp");
+    const size_t smem = sizeof(float2) * (size_t)PW::LINE;
+    static bool attr_set = false;
+    if (!attr_set && smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(acq_inverse_lw_kernel<PW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    acq_inverse_lw_kernel<PW><<<n_d * a.n_active, PW::T + 32, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace gb

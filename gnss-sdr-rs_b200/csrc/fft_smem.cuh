@@ -91,13 +91,16 @@ __device__ __forceinline__ float2 cmul_conj(float2 a, float2 b)  // a * conj(b)
     return upk(fma2(pk(a.y, a.x), pk(b.y, -b.y), mul2(pk(a), pk(b.x, b.x))));
 }
 #else
+// Scalar forms with the contraction written out (one FMUL + one FFMA per component, the same roundings as the packed
+// forms above): left to the compiler, `a*b + c*d` is contracted differently in different inlining contexts, and the
+// kernels that must agree bit for bit (fused / shared / leftover-warp chains) would drift apart in the last ulp.
 __device__ __forceinline__ float2 cmul(float2 a, float2 b)
 {
-    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+    return make_float2(__fmaf_rn(-a.y, b.y, __fmul_rn(a.x, b.x)), __fmaf_rn(a.x, b.y, __fmul_rn(a.y, b.x)));
 }
 __device__ __forceinline__ float2 cmul_conj(float2 a, float2 b)  // a * conj(b)
 {
-    return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
+    return make_float2(__fmaf_rn(a.y, b.y, __fmul_rn(a.x, b.x)), __fmaf_rn(-a.x, b.y, __fmul_rn(a.y, b.x)));
 }
 #endif
 // c + i*s and c - i*s for packed complex c, s (i*s = (-s.y, s.x)): one FADD2 each, the rotation is an operand modifier
@@ -307,17 +310,22 @@ template <int R, bool INV, class Emit> __device__ __forceinline__ void dft_odd_p
 // ahead of the FFMA2s that consume them and the L2 latency of one batch hides behind the arithmetic of the previous
 // one inside the same thread.  Every accumulator receives its terms in the same order (j = 1, 2, ...) as in
 // dft_odd_prime_emit: the results are bit-identical.
-template <int R, bool INV, int BATCH, class Load, class Emit>
-__device__ __forceinline__ void dft_odd_prime_stream(Load load, Emit emit)
+// The accumulators are a value type so that a caller can keep a finished butterfly in registers and emit it later
+// (acq_inverse_lw_kernel's leftover warp holds one per lane across several groups).
+template <int R> struct OddPrimeAcc {
+    pk64 x0;
+    pk64 c2[(R - 1) / 2 + 1], s2[(R - 1) / 2 + 1];   // [0] unused
+};
+template <int R, bool INV, int BATCH, class Load>
+__device__ __forceinline__ void dft_odd_prime_stream_acc(Load load, OddPrimeAcc<R>& h)
 {
     constexpr int H = (R - 1) / 2;
-    pk64 c2[H + 1], s2[H + 1];
     const pk64 v0 = pk(load(0));
-    pk64 x0 = v0;
+    h.x0 = v0;
 #pragma unroll
     for (int q = 1; q <= H; q++) {
-        c2[q] = v0;
-        s2[q] = pk(0.f, 0.f);
+        h.c2[q] = v0;
+        h.s2[q] = pk(0.f, 0.f);
     }
     float2 p[BATCH], m[BATCH];
 #pragma unroll
@@ -349,25 +357,36 @@ __device__ __forceinline__ void dft_odd_prime_stream(Load load, Emit emit)
         for (int u = 0; u < BATCH; u++) {
             if (j0 + u <= H) {
                 const int j = j0 + u;
-                x0 = add2(x0, a[u]);
+                h.x0 = add2(h.x0, a[u]);
 #pragma unroll
                 for (int q = 1; q <= H; q++) {
                     const int k = (j * q) % R;
                     const float c = RT<R>::c(k);
                     const float s = INV ? RT<R>::s(k) : -RT<R>::s(k);
-                    c2[q] = fma2s(a[u], c, c2[q]);
-                    s2[q] = fma2s(b[u], s, s2[q]);
+                    h.c2[q] = fma2s(a[u], c, h.c2[q]);
+                    h.s2[q] = fma2s(b[u], s, h.s2[q]);
                 }
             }
         }
     }
-    emit(0, upk(x0));
+}
+template <int R, class Emit> __device__ __forceinline__ void dft_odd_prime_stream_emit(const OddPrimeAcc<R>& h, Emit emit)
+{
+    constexpr int H = (R - 1) / 2;
+    emit(0, upk(h.x0));
 #pragma unroll
     for (int q = 1; q <= H; q++) {
-        const float2 cc = upk(c2[q]), ss = upk(s2[q]);
+        const float2 cc = upk(h.c2[q]), ss = upk(h.s2[q]);
         emit(q, make_float2(cc.x - ss.y, cc.y + ss.x));
         emit(R - q, make_float2(cc.x + ss.y, cc.y - ss.x));
     }
+}
+template <int R, bool INV, int BATCH, class Load, class Emit>
+__device__ __forceinline__ void dft_odd_prime_stream(Load load, Emit emit)
+{
+    OddPrimeAcc<R> h;
+    dft_odd_prime_stream_acc<R, INV, BATCH>(load, h);
+    dft_odd_prime_stream_emit<R>(h, emit);
 }
 
 // dft_emit<R,INV>(v, emit): DFT of v with outputs delivered through emit(q, X_q).

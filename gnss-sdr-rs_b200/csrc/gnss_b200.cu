@@ -825,7 +825,7 @@ extern "C" int gb_acq_set_coherent(gb_handle* h, int n_coh)
 
 extern "C" int gb_acq_set_mode(gb_handle* h, int mode)
 {
-    if (!h || (mode != GB_ACQ_FUSED && mode != GB_ACQ_SHARED)) return GB_EINVAL;
+    if (!h || (mode != GB_ACQ_FUSED && mode != GB_ACQ_SHARED && mode != GB_ACQ_SHARED_PLAIN)) return GB_EINVAL;
     h->mode = mode;
     return GB_OK;
 }
@@ -888,11 +888,12 @@ static int search_cells(gb_handle* h, const float2* iq_dev, uint64_t start, uint
         a.D = h->D; a.K = K; a.n_coh = h->n_coh; a.n_active = n_active; a.spc = h->spc;
         a.cells = h->cells_dev; a.row_out = nullptr; a.d0 = 0; a.spec = nullptr; a.d_lo = 0;
         a.otw = h->otw; a.acc_rows = nullptr; a.npos = h->npos; a.g_lo = 0; a.g_cnt = K / h->n_coh;
+        a.plain_inverse = h->mode == GB_ACQ_SHARED_PLAIN;
         if (h->pfa) {
             int rc = ensure(h, &h->iq_perm, &h->iq_perm_cap, (size_t)K * h->N);
             if (rc) return rc;
         }
-        if (host_iq && (h->cluster || h->mode != GB_ACQ_SHARED))
+        if (host_iq && (h->cluster || h->mode == GB_ACQ_FUSED))
             CK(cudaMemcpyAsync(h->chunk, host_iq, (size_t)K * h->N * sizeof(float2), cudaMemcpyHostToDevice, h->s_acq));
         if (h->cluster) {
             if (h->n_coh != 1) return GB_EUNSUPPORTED;
@@ -902,7 +903,7 @@ static int search_cells(gb_handle* h, const float2* iq_dev, uint64_t start, uint
             CK(cudaEventRecord(h->ev_a0, h->s_acq));
             CK(gb::acq_cluster_launch_search(a, h->s_acq));
             CK(cudaEventRecord(h->ev_a1, h->s_acq));
-        } else if (h->mode == GB_ACQ_SHARED) {
+        } else if (h->mode != GB_ACQ_FUSED) {
             // scratch for the forward spectra, processed in Doppler slabs of at most 1 GiB
             const size_t per_d = (size_t)(K / h->n_coh) * h->N;
             size_t slab = ((size_t)1 << 27) / per_d;  // complex elements: 2^27 * 8 B = 1 GiB
@@ -1097,6 +1098,7 @@ extern "C" int gb_acq_bin_power(gb_handle* h, const gb_c32* iq, int K, int prn, 
     a.D = h->D; a.K = K; a.n_coh = h->n_coh; a.n_active = 1; a.spc = 0;
     a.cells = nullptr; a.row_out = h->row_dev; a.d0 = doppler_bin; a.spec = nullptr; a.d_lo = 0;
     a.otw = h->otw; a.acc_rows = nullptr; a.npos = h->npos; a.g_lo = 0; a.g_cnt = K / h->n_coh;
+    a.plain_inverse = h->mode == GB_ACQ_SHARED_PLAIN;
     if (h->pfa) {
         rc = ensure(h, &h->iq_perm, &h->iq_perm_cap, (size_t)K * h->N);
         if (rc) return rc;

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define GB_VERSION 110
+#define GB_VERSION 111
 
 /* ---- error codes ---- */
 #define GB_OK 0
@@ -134,9 +134,12 @@ int gb_acq_set_coherent(gb_handle *h, int n_coh);
  *   GB_ACQ_FUSED : one kernel, one CTA per (PRN, Doppler) does the whole chain in shared memory;
  *   GB_ACQ_SHARED: two-kernel chain -- the PRN-independent forward path (wipe-off, coherent sum,
  *                  forward FFT) once per (Doppler, group), spectra left in L2, then per (PRN, Doppler)
- *                  x conj(code) -> IFFT -> |.|^2 -> cell.  Default. */
+ *                  x conj(code) -> IFFT -> |.|^2 -> cell.  Default.  For fft_size 4092 the inverse kernel
+ *                  is the leftover-warp form (acq_lw.cu);
+ *   GB_ACQ_SHARED_PLAIN: GB_ACQ_SHARED with the generic inverse kernel for every size (A/B, tests). */
 #define GB_ACQ_FUSED 0
 #define GB_ACQ_SHARED 1
+#define GB_ACQ_SHARED_PLAIN 2
 int gb_acq_set_mode(gb_handle *h, int mode);
 /* samples_per_chip > 0 enables peak2; threshold is is_good_satellite's 7.0 */
 int gb_acq_set_detector(gb_handle *h, float threshold, int samples_per_chip);

@@ -23,6 +23,17 @@ def _engine(gpu, n, fs, **kw):
     return acquisition.AcquisitionEngine(gpu, n, fs, **kw)
 
 
+def _assert_same_cells(a, b, exact_sum=True):
+    """peak / argmax / peak2 are order-independent reductions and must agree bit for bit; sum8 is a float sum whose
+    association follows the CTA geometry, so kernels with different working-thread counts agree to rounding only."""
+    for f in ("peak", "argmax", "peak2"):
+        assert a[f].tobytes() == b[f].tobytes(), f
+    if exact_sum:
+        assert a["sum8"].tobytes() == b["sum8"].tobytes()
+    else:
+        np.testing.assert_allclose(a["sum8"], b["sum8"], rtol=2e-6)
+
+
 @pytest.mark.parametrize("n", [1024, 2048, 4092, 4096, 8184, 16368, 20000])
 def test_fused_and_shared_chains_are_bit_identical(gpu, oracle, ffi, n):
     """GB_ACQ_FUSED (one kernel) and GB_ACQ_SHARED (forward path shared by all PRNs) run the same arithmetic."""
@@ -39,8 +50,31 @@ def test_fused_and_shared_chains_are_bit_identical(gpu, oracle, ffi, n):
         for mode in (ffi.GB_ACQ_FUSED, ffi.GB_ACQ_SHARED):
             eng.set_mode(mode)
             out[(n_coh, mode)] = eng.search_cells(x, K, prn_mask=0x80000F0F)
-        assert out[(n_coh, 0)].tobytes() == out[(n_coh, 1)].tobytes()
+        # n = 4092: the default shared chain is the leftover-warp kernel (128 working threads, the fused one has 160)
+        _assert_same_cells(out[(n_coh, 0)], out[(n_coh, 1)], exact_sum=(n != 4092))
     assert out[(1, 0)]["peak"][0].max() > 0 and out[(1, 0)]["peak"][4].max() == 0
+
+
+@pytest.mark.parametrize("K,n_coh", [(1, 1), (7, 1), (8, 1), (9, 1), (20, 1), (40, 2), (33, 1)])
+def test_leftover_warp_kernel_is_bit_identical(gpu, ffi, K, n_coh):
+    """N = 4092: the default inverse kernel batches the 4 ragged radix-31 butterflies of 8 consecutive groups into one
+    pass of a fifth warp (acq_lw.cu).  Every group count around the batch boundaries must give the power rows of the
+    generic kernel (GB_ACQ_SHARED_PLAIN) and of the single fused kernel: peak, arg-max and second peak byte for byte
+    (they see every row element), the 8-lane sum to rounding (its association follows the CTA geometry)."""
+    from gnss_sdr_rs_b200 import sdr_mock
+    n, fs = 4092, 4.092e6
+    x = sdr_mock.baseband(fs, K, _sats(n, 5), seed=K)
+    eng = _engine(gpu, n, fs)
+    eng.make_doppler_tables(0.0, np.arange(-1500, 1501, 250, dtype=np.float32))
+    eng.set_detector(7.0, 4)
+    eng.set_coherent(n_coh)
+    out = []
+    for mode in (ffi.GB_ACQ_SHARED, ffi.GB_ACQ_SHARED_PLAIN, ffi.GB_ACQ_FUSED):
+        eng.set_mode(mode)
+        out.append(eng.search_cells(x, K).copy())
+    assert out[1].tobytes() == out[2].tobytes()
+    _assert_same_cells(out[0], out[1], exact_sum=False)
+    assert out[0]["peak"].min() > 0 and out[0]["peak2"].min() > 0
 
 
 @pytest.mark.parametrize("n", [1024, 2048, 4092, 4096, 8184, 16368, 20000])

@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Times the acquisition kernels (CUDA events inside the library) for one workload; tuning helper.
-usage: time_acq.py [config2|config1|n=<N>,k=<K>,d=<D>,coh=<n_coh>] [shared|fused] [reps]"""
+usage: time_acq.py [config2|config1|n=<N>,k=<K>,d=<D>,coh=<n_coh>] [shared|plain|fused] [reps]"""
 import os
 import sys
 
@@ -30,7 +30,7 @@ def main():
     eng = acquisition.AcquisitionEngine(hd, n, fs)
     eng.make_doppler_tables(0.0, np.linspace(-5000, 5000, D).astype(np.float32))
     eng.set_coherent(coh)
-    eng.set_mode(ffi.GB_ACQ_FUSED if mode == "fused" else ffi.GB_ACQ_SHARED)
+    eng.set_mode({"fused": ffi.GB_ACQ_FUSED, "plain": ffi.GB_ACQ_SHARED_PLAIN}.get(mode, ffi.GB_ACQ_SHARED))
     # samples resident in the device ring: the timed region holds kernels only (the host-pointer call overlaps its
     # sliced upload with the forward path inside the same events)
     cap = 1
