@@ -272,7 +272,9 @@ def extra_numbers(hd, ffi):
     dt = (time.perf_counter() - t0) / 4
     out["digital_frontend"] = {"samples_per_call": int(blk.size), "wall_ms_per_call": dt * 1e3,
                                "msamples_per_sec": blk.size / dt / 1e6,
-                               "note": "bit-exact sequential NCO/DC recurrences: one CTA per stream, latency-bound"}
+                               "note": "bit-exact: NCO indices from the precomputed f32 phase orbit, the 16 DC-bias recurrences "
+                                       "sequential (FMUL -> FADD per 8 samples): one CTA per stream, bound by that chain; "
+                                       "wall clock includes the pinned-less H2D of the block"}
     return out
 
 

@@ -106,11 +106,9 @@ cudaError_t acq_launch_inverse_lw4092(const AcqArgs& a, int n_d, cudaStream_t st
     using PW = P4092W;
     static_assert(PW::T + 32 == P4092::T && PW::LINE == P4092::LINE, "same line as the default plan, one extra warp");
     const size_t smem = sizeof(float2) * (size_t)PW::LINE;
-    static bool attr_set = false;
-    if (!attr_set && smem > 48 * 1024) {
+    if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(acq_inverse_lw_kernel<PW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        attr_set = true;
     }
     acq_inverse_lw_kernel<PW><<<n_d * a.n_active, PW::T + 32, smem, st>>>(a);
     return cudaGetLastError();

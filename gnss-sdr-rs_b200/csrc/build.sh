@@ -6,7 +6,7 @@ OUT=../libgnss_b200.so
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC"
 mkdir -p ../build
 need=0
-for f in acq_kernels acq_lw acq_cluster trk_kernels fine_doppler gnss_b200; do
+for f in acq_kernels acq_lw frontend acq_cluster trk_kernels fine_doppler gnss_b200; do
   if [ ! -f ../build/$f.o ] || [ -n "$(find . ../../include -newer ../build/$f.o \( -name '*.cu' -o -name '*.cuh' -o -name '*.h' \) | head -1)" ]; then need=1; fi
 done
 if [ $need -eq 0 ] && [ -f $OUT ] && [ "$1" != "-f" ]; then exit 0; fi
@@ -16,6 +16,7 @@ nvcc $FLAGS -c acq_cluster.cu -o ../build/acq_cluster.o & p4=$!
 nvcc $FLAGS -c gnss_b200.cu -o ../build/gnss_b200.o & p3=$!
 nvcc $FLAGS -c fine_doppler.cu -o ../build/fine_doppler.o & p5=$!
 nvcc $FLAGS -c acq_lw.cu -o ../build/acq_lw.o & p6=$!
-wait $p1; wait $p2; wait $p3; wait $p4; wait $p5; wait $p6
-nvcc -shared -o $OUT ../build/acq_kernels.o ../build/acq_lw.o ../build/acq_cluster.o ../build/trk_kernels.o ../build/fine_doppler.o ../build/gnss_b200.o
+nvcc $FLAGS -fmad=false -c frontend.cu -o ../build/frontend.o & p7=$!
+wait $p1; wait $p2; wait $p3; wait $p4; wait $p5; wait $p6; wait $p7
+nvcc -shared -o $OUT ../build/acq_kernels.o ../build/acq_lw.o ../build/frontend.o ../build/acq_cluster.o ../build/trk_kernels.o ../build/fine_doppler.o ../build/gnss_b200.o
 echo "built $OUT"

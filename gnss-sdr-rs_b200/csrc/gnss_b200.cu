@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -13,6 +14,7 @@
 #include "acq_kernels.cuh"
 #include "trk_kernels.cuh"
 #include "fine_doppler.cuh"
+#include "frontend.cuh"
 
 namespace {
 
@@ -51,6 +53,11 @@ struct gb_handle {
     size_t fe_cap = 0;
     float fe_step = 0.f;
     bool fe_ready = false;
+    // table-driven NCO (frontend.cu): orbit of the f32 phase accumulator, LUT indices on the device
+    bool fe_table = false;
+    uint16_t* fe_idx = nullptr;
+    std::vector<float> fe_phase;
+    uint64_t fe_mu = 0, fe_period = 0, fe_count = 0;
 
     // acquisition
     int plan = -1, N = 0, n_prn = 0, D = 0, n_coh = 1, spc = 0, mode = GB_ACQ_SHARED;
@@ -464,7 +471,7 @@ extern "C" int gb_destroy(gb_handle* h)
     if (!h) return GB_EINVAL;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
-    void* dev_ptrs[] = {h->fe_lut, h->fe_state, h->fe_stage, h->otw, h->acc_rows, h->spec, h->ring, h->i8_stage, h->tw, h->code_fft, h->tables, h->rot, h->chunk, h->codes_dev, h->cells_dev,
+    void* dev_ptrs[] = {h->fe_idx, h->fe_lut, h->fe_state, h->fe_stage, h->otw, h->acc_rows, h->spec, h->ring, h->i8_stage, h->tw, h->code_fft, h->tables, h->rot, h->chunk, h->codes_dev, h->cells_dev,
                         h->rows_dev, h->row_dev, h->ca_table_dev, h->ch_dev, h->corr_dev, h->ran_dev, h->lost_dev,
                         h->hist_dev, h->trk_data, h->offs_dev, h->fine_x, h->fine_y, h->fine_codes, h->fine_u64, h->fine_mean,
                         h->fine_mag, h->tables_perm, h->iq_perm};
@@ -614,6 +621,22 @@ extern "C" int gb_frontend_configure(gb_handle* h, float f_if, float fs_in)
     CK(cudaMemcpy(h->fe_lut, lut.data(), sizeof(float) * 4096, cudaMemcpyHostToDevice));
     CK(cudaMemset(h->fe_state, 0, sizeof(float) * 17));
     h->fe_step = (f_if / fs_in) * 2048.0f;  // nco_lut.rs:34
+    // The phase accumulator does not depend on the samples: its orbit from 0 (tail + cycle, at most 2^24 states) is
+    // computed here in the reference's f32 arithmetic and the kernel looks the LUT index up by sample number.
+    // GB_FE_SEQUENTIAL=1 (or an orbit longer than the cap) keeps the one-thread sequential accumulator.
+    h->fe_table = false;
+    h->fe_count = 0;
+    if (h->fe_idx) { cudaFree(h->fe_idx); h->fe_idx = nullptr; }
+    if (!getenv("GB_FE_SEQUENTIAL") &&
+        gb::fe_build_phase_orbit(h->fe_step, (uint64_t)1 << 24, 4096, h->fe_phase, &h->fe_mu, &h->fe_period)) {
+        std::vector<uint16_t> idx(h->fe_phase.size());
+        for (size_t i = 0; i < idx.size(); i++) idx[i] = gb::fe_lut_index(h->fe_phase[i]);
+        CK(cudaMalloc((void**)&h->fe_idx, idx.size() * sizeof(uint16_t)));
+        CK(cudaMemcpy(h->fe_idx, idx.data(), idx.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+        h->fe_table = true;
+    } else {
+        h->fe_phase.clear();
+    }
     h->fe_ready = true;
     return GB_OK;
 }
@@ -628,11 +651,30 @@ extern "C" int gb_frontend_write(gb_handle* h, const gb_c32* raw, uint64_t n)
     int rc = ensure(h, &h->fe_stage, &h->fe_cap, (size_t)n);
     if (rc) return rc;
     CK(cudaMemcpyAsync(h->fe_stage, raw, n * sizeof(float2), cudaMemcpyHostToDevice, h->s_copy));
-    frontend_kernel<<<1, 256, 0, h->s_copy>>>(h->fe_stage, h->ring, h->ring_head, h->ring_cap - 1, n, h->fe_lut, h->fe_state,
-                                               h->fe_step, 0.001f, 1.0f - 0.001f);
-    CK(cudaGetLastError());
+    if (h->fe_table) {
+        CK(gb::fe_launch_table(h->fe_stage, h->ring, h->ring_head, h->ring_cap - 1, n, h->fe_lut, h->fe_state + 1, h->fe_idx,
+                               gb::fe_orbit_pos(h->fe_count, h->fe_mu, h->fe_period), h->fe_mu, h->fe_period, 0.001f,
+                               1.0f - 0.001f, h->s_copy));
+    } else {
+        frontend_kernel<<<1, 256, 0, h->s_copy>>>(h->fe_stage, h->ring, h->ring_head, h->ring_cap - 1, n, h->fe_lut, h->fe_state,
+                                                   h->fe_step, 0.001f, 1.0f - 0.001f);
+        CK(cudaGetLastError());
+    }
     CK(cudaEventRecord(h->ev_copy, h->s_copy));
+    h->fe_count += n;
     h->ring_head += n;
+    return GB_OK;
+}
+
+extern "C" int gb_frontend_orbit(float f_if, float fs_in, uint64_t* mu, uint64_t* lambda, uint16_t* idx_out, uint64_t n_idx)
+{
+    if (!(fs_in > 0.f) || !mu || !lambda) return GB_EINVAL;
+    std::vector<float> phase;
+    uint64_t period = 0;
+    if (!gb::fe_build_phase_orbit((f_if / fs_in) * 2048.0f, (uint64_t)1 << 24, 1, phase, mu, &period)) return GB_EUNSUPPORTED;
+    *lambda = period;   // min_period 1: no replication
+    if (idx_out)
+        for (uint64_t i = 0; i < n_idx; i++) idx_out[i] = gb::fe_lut_index(phase[gb::fe_orbit_pos(i, *mu, period)]);
     return GB_OK;
 }
 
@@ -644,6 +686,7 @@ extern "C" int gb_frontend_state(gb_handle* h, float* state17)
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->s_copy));
     CK(cudaMemcpy(state17, h->fe_state, sizeof(float) * 17, cudaMemcpyDeviceToHost));
+    if (h->fe_table) state17[0] = h->fe_phase[gb::fe_orbit_pos(h->fe_count, h->fe_mu, h->fe_period)];
     return GB_OK;
 }
 

@@ -81,10 +81,19 @@ int gb_ring_reset(gb_handle *h);
  * NcoLut / mix_simd (rf/nco_lut.rs:8-42) and the per-block body of rf_thread (rf/rf_thread.rs:44-48): raw complex
  * samples -> DC removal (alpha 0.001, 8 interleaved lanes) -> 2048-entry NCO LUT mix -> appended to the ring.
  * Bit-exact with the reference arithmetic (sequential f32 phase accumulator and bias recurrences included).
- * n must be a multiple of 8 (the reference processes 16 floats at a time). */
+ * n must be a multiple of 8 (the reference processes 16 floats at a time).
+ * The phase accumulator (`acc = (acc + step) % 2048.0` per sample, frontend.rs:48-52) does not depend on the samples:
+ * gb_frontend_configure computes its orbit from 0 -- a tail of mu states then a cycle of lambda states, found with
+ * Brent's algorithm in the reference's f32 arithmetic -- and the kernel looks LUT indices up by sample number, so only
+ * the DC-bias recurrences stay sequential.  Orbits longer than 2^24 states (none met in practice) and the environment
+ * variable GB_FE_SEQUENTIAL=1 fall back to a one-thread sequential accumulator with identical results. */
 int gb_frontend_configure(gb_handle *h, float f_if, float fs_in);
 int gb_frontend_write(gb_handle *h, const gb_c32 *raw, uint64_t n);
 int gb_frontend_state(gb_handle *h, float *state17 /* phase_accumulator, bias_re[8], bias_im[8] */);
+/* Host-only diagnostic (no device needed): the orbit gb_frontend_configure would build.  mu / lambda receive the tail
+ * and cycle lengths; idx_out (may be NULL) receives the LUT index of samples 0 .. n_idx-1.  GB_EUNSUPPORTED if the
+ * orbit exceeds the 2^24-state cap. */
+int gb_frontend_orbit(float f_if, float fs_in, uint64_t *mu, uint64_t *lambda, uint16_t *idx_out, uint64_t n_idx);
 
 /* ------------------------------------------------------------------ acquisition
  * replaces AcquisitionWorker::{new, search_satellite, is_good_satellite}

@@ -145,3 +145,42 @@ def test_acquisition_manager_mirror():
     assert m.mode == m.STEADY
     m.update_mode(0)
     assert m.mode == m.COLD
+
+
+def test_frontend_phase_orbit_reproduces_the_sequential_accumulator(ffi, oracle):
+    """gb_frontend_orbit (host-only): the tail + cycle of `acc = (acc + step) % 2048.0` (rf/frontend.rs:48-52) found at
+    configure time yields, sample for sample, the LUT indices of the oracle's sequential accumulator -- also past the
+    point where the table wraps (lambda = 4, 512, 2048) and for a negative IF (saturating cast -> index 0)."""
+    L = ffi.lib()
+    n = 40000
+    for f_if, fs, want in ((4130400.0, 16367600.0, (3, 6313323)), (4092000.0, 16368000.0, (0, 4)),
+                           (420000.0, 2048000.0, (0, 512)), (1000.0, 2048000.0, (0, 2048)),
+                           (-4130400.0, 16367600.0, None), (38400.0, 2048000.0, None)):
+        mu, lam = C.c_uint64(), C.c_uint64()
+        idx = np.zeros(n, np.uint16)
+        assert L.gb_frontend_orbit(f_if, fs, C.byref(mu), C.byref(lam), idx.ctypes.data_as(C.c_void_p), n) == 0
+        if want:
+            assert (mu.value, lam.value) == want
+        assert 1 <= lam.value <= 1 << 24
+        f = oracle.frontend(f_if, fs)
+        # the oracle mixes (1, 0) samples with zero DC state only if alpha were 0; read the index sequence off its
+        # phase accumulator instead: one process_block of 8 samples advances it 8 steps
+        ref = np.zeros(n, np.uint16)
+        acc = np.float32(0.0)
+        step = np.float32(np.float32(f_if) / np.float32(fs)) * np.float32(2048.0)
+        assert step == np.float32(f.phase_step)
+        for i in range(n):
+            ref[i] = 0 if not acc > 0 else int(acc) % 2048
+            acc = np.float32(np.fmod(np.float32(acc + step), np.float32(2048.0)))
+        assert (idx == ref).all()
+        z = np.zeros(n - n % 8, np.complex64)
+        oracle.frontend_process(f, z)
+        assert np.float32(f.phase_accumulator) == np.float32(_phase_after(step, n - n % 8))
+    assert L.gb_frontend_orbit(1.0, 0.0, C.byref(mu), C.byref(lam), None, 0) == ffi.GB_EINVAL
+
+
+def _phase_after(step, n):
+    acc = np.float32(0.0)
+    for _ in range(n):
+        acc = np.float32(np.fmod(np.float32(acc + step), np.float32(2048.0)))
+    return acc

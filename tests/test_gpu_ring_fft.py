@@ -72,11 +72,18 @@ def test_fft_facade(gpu, n):
     assert np.abs(rf.execute(r) - ref_r).max() / np.abs(ref_r).max() < 5e-7
 
 
-def test_digital_frontend_bit_exact(gpu, oracle):
+@pytest.mark.parametrize("sequential", [False, True])
+@pytest.mark.parametrize("f_if,fs", [(4130400.0, 16367600.0), (4092000.0, 16368000.0), (-420000.0, 2048000.0)])
+def test_digital_frontend_bit_exact(gpu, oracle, monkeypatch, sequential, f_if, fs):
     """rf/frontend.rs process_block restated -- DC removal + NCO LUT mix, bit-exact incl. the sequential
-    f32 phase accumulator, across several rf_thread-sized blocks (2048) and one odd-sized write."""
+    f32 phase accumulator, across several rf_thread-sized blocks (2048) and one odd-sized write.  Both NCO forms: the
+    phase-orbit table (default; lambda = 6313323 / 4 / 512 for these steps, so the short cycles wrap many times inside
+    one write) and the one-thread sequential accumulator (GB_FE_SEQUENTIAL=1)."""
     from gnss_sdr_rs_b200 import ring
-    f_if, fs = 4130400.0, 16367600.0
+    if sequential:
+        monkeypatch.setenv("GB_FE_SEQUENTIAL", "1")
+    else:
+        monkeypatch.delenv("GB_FE_SEQUENTIAL", raising=False)
     rng = np.random.default_rng(3)
     raw = ((rng.standard_normal(5 * 2048 + 1000) * 20 + 3.0) + 1j * (rng.standard_normal(5 * 2048 + 1000) * 20 - 2.0)).astype(np.complex64)
     rb = ring.MulticastRingBuffer(gpu, 1 << 15)
@@ -98,3 +105,23 @@ def test_digital_frontend_bit_exact(gpu, oracle):
     import gnss_sdr_rs_b200._ffi as ffi
     with pytest.raises(ffi.GnssB200Error):
         fe.process_block_into_ring(raw[:13])  # not a multiple of 8
+
+
+def test_digital_frontend_long_write_and_reconfigure(gpu, oracle):
+    """One 64-tile write (131072 samples, the bench's call size) followed by a ragged one, then a reconfigure that must
+    restart the phase orbit and the DC state from zero."""
+    from gnss_sdr_rs_b200 import ring
+    f_if, fs = 4130400.0, 16367600.0
+    rng = np.random.default_rng(9)
+    n = 131072 + 8 * 333
+    raw = ((rng.standard_normal(n) * 30 - 5.0) + 1j * (rng.standard_normal(n) * 30 + 7.0)).astype(np.complex64)
+    rb = ring.MulticastRingBuffer(gpu, 1 << 18)
+    for _ in range(2):
+        fe = ring.DigitalFrontend(gpu, f_if, fs)
+        of = oracle.frontend(f_if, fs)
+        start = rb.get_head()
+        fe.process_block_into_ring(raw[:131072])
+        fe.process_block_into_ring(raw[131072:])
+        ref = np.concatenate([oracle.frontend_process(of, raw[:131072]), oracle.frontend_process(of, raw[131072:])])
+        assert rb.copy_to_slice(start, n).tobytes() == ref.tobytes()
+        assert fe.state()["phase_accumulator"] == of.phase_accumulator
