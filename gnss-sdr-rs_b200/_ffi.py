@@ -83,6 +83,8 @@ SIGNATURES = {
     "gb_acq_get_doppler_tables": (_i32, [_vp, _vp, _vp]),
     "gb_acq_set_coherent": (_i32, [_vp, _i32]),
     "gb_acq_set_mode": (_i32, [_vp, _i32]),
+    "gb_acq_set_doppler_aliasing": (_i32, [_vp, _i32]),
+    "gb_acq_forward_bins": (_i32, [_vp]),
     "gb_acq_set_detector": (_i32, [_vp, _f32, _i32]),
     "gb_acq_search_cells": (_i32, [_vp, _vp, _i32, _u32, _vp, _vp]),
     "gb_acq_search_cells_ring": (_i32, [_vp, _u64, _i32, _u32, _vp, _vp]),

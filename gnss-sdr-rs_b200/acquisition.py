@@ -88,6 +88,15 @@ class AcquisitionEngine:
         self.hd.call("gb_acq_set_coherent", int(n_coh))
         self.n_coh = int(n_coh)
 
+    def set_doppler_aliasing(self, on):
+        """Share one forward spectrum between Doppler bins a whole number of FFT bins apart (default on); off = every
+        bin runs the reference's own wipe-off table (include/gnss_b200.h, gb_acq_set_doppler_aliasing)."""
+        self.hd.call("gb_acq_set_doppler_aliasing", 1 if on else 0)
+
+    def forward_bins(self):
+        """Forward spectra per group the next shared-chain search computes."""
+        return int(self.hd.L.gb_acq_forward_bins(self.hd.h))
+
     def set_mode(self, mode):
         """_ffi.GB_ACQ_FUSED (single kernel), _ffi.GB_ACQ_SHARED (forward path shared by all PRNs, default) or
         _ffi.GB_ACQ_SHARED_PLAIN (the shared chain with the generic inverse kernel at every size, A/B)."""

@@ -147,7 +147,7 @@ template <class P> __global__ void __launch_bounds__(P::T, P::MINB) acq_forward_
     // one per upload slice so that the H2D copy of slice s+1 overlaps the forward path of slice s)
     const int n_groups = a.K / a.n_coh;
     const int dl = (int)(blockIdx.x / (unsigned)a.g_cnt);
-    const int d = a.d_lo + dl;
+    const int d = a.fwd_bins ? __ldg(&a.fwd_bins[dl]) : a.d_lo + dl;
     const int g = a.g_lo + (int)(blockIdx.x % (unsigned)a.g_cnt);
     const float2* __restrict__ w = a.tables + (size_t)d * N;
     const float2* __restrict__ rot = a.rot ? a.rot + (size_t)d * a.n_coh : nullptr;
@@ -182,9 +182,10 @@ template <class P, bool DB> __global__ void __launch_bounds__(P::T, P::MINB) acq
     // Doppler-major block order: the n_active CTAs that share one bin's spectra run together (L2 reuse)
     const int dl = (int)(blockIdx.x / (unsigned)a.n_active);
     const int row = a.rows[blockIdx.x % (unsigned)a.n_active];
-    const float2* __restrict__ code = a.code_fft + (size_t)row * N;
+    const int2 sm = a.inv_map ? __ldg(&a.inv_map[a.d_lo + dl]) : make_int2(dl, 0);   // {spectrum slot, shifted code set}
+    const float2* __restrict__ code = a.code_fft + ((size_t)sm.y * a.n_prn + row) * N;
     const float2* __restrict__ tw = a.tw;
-    const float2* __restrict__ spec = a.spec + (size_t)dl * n_groups * N;
+    const float2* __restrict__ spec = a.spec + (size_t)sm.x * n_groups * N;
 
     float acc[G0::ITERS][G0::R];
 #pragma unroll
@@ -347,6 +348,21 @@ __global__ void permute_blocks_kernel(const float2* __restrict__ src, unsigned l
         const unsigned long long b = (unsigned long long)b0 + blockIdx.y;
         dst[b * n + l] = src[(start + b * n + (unsigned long long)__ldg(&npos[l])) & mask];
     }
+}
+__global__ void shift_codes_kernel(const float2* __restrict__ src, const int* __restrict__ gidx, int n_prn, int n,
+                                   float2* __restrict__ dst)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) {
+        const int s = blockIdx.z, p = blockIdx.y;
+        dst[((size_t)s * n_prn + p) * n + t] = src[(size_t)p * n + __ldg(&gidx[(size_t)s * n + t])];
+    }
+}
+cudaError_t acq_launch_shift_codes(const float2* src, const int* gidx, int n_shift, int n_prn, int n, float2* dst, cudaStream_t st)
+{
+    dim3 grid((n + 255) / 256, n_prn, n_shift);
+    shift_codes_kernel<<<grid, 256, 0, st>>>(src, gidx, n_prn, n, dst);
+    return cudaGetLastError();
 }
 cudaError_t acq_launch_permute(const float2* src, unsigned long long start, unsigned long long mask, const int* npos, int n,
                                int b0, int n_blocks, float2* dst, cudaStream_t st)

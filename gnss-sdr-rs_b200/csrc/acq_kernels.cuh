@@ -27,6 +27,11 @@ struct AcqArgs {
     const int* npos;         // prime-factor plans: code-phase index n(l) of line position l (else unused)
     const float2* otw;       // cluster plans: outer twiddles W_N^(i q), layout [q-1][i]
     float* acc_rows;         // cluster plans: (n_active*D) x N accumulated power rows (scratch)
+    // Doppler aliasing (shared-forward chain): bins whose carriers differ by m * fs/N share ONE forward spectrum
+    // (X_d[k] = X_base[k + m]); the inverse kernel pairs it with the code spectrum shifted the other way.
+    const int* fwd_bins;     // forward launch: bin computed by slot dl (nullptr: d_lo + dl)
+    const int2* inv_map;     // inverse launch: per bin {spectrum slot, index of the shifted code-spectrum set} (nullptr: {dl, 0})
+    int n_prn;               // rows per code-spectrum set
     int plain_inverse;       // shared-forward chain: 1 = acq_inverse_kernel even where a leftover-warp form exists (A/B)
 };
 
@@ -62,6 +67,8 @@ cudaError_t acq_launch_permute(const float2* src, unsigned long long start, unsi
 cudaError_t acq_launch_forward(int plan, const AcqArgs& a, int n_d, cudaStream_t st);
 cudaError_t acq_launch_fft(int plan, int inverse, const FftArgs& a, int batch, cudaStream_t st);
 // steps_dev[d] = 2*pi*(f_if+f_d)/fs (f32, host-evaluated in the reference's order)
+// dst[(s * n_prn + p) * n + t] = src[p * n + gidx[s * n + t]]: the code spectra re-indexed for n_shift frequency shifts
+cudaError_t acq_launch_shift_codes(const float2* src, const int* gidx, int n_shift, int n_prn, int n, float2* dst, cudaStream_t st);
 cudaError_t acq_launch_doppler_tables(const float* steps_dev, int D, int n, float2* tables, cudaStream_t st);
 
 // cluster plans (code period larger than one CTA's shared memory): radix-RO outer stage over a thread-block cluster

@@ -2,7 +2,12 @@
 // plan zoo of acq_kernels.cu takes two minutes to compile).
 #include "acq_common.cuh"
 
+#include <stdlib.h>
+
 namespace gb {
+
+// spectra: L2 only (ld.global.cg), L1 is left to the code spectrum; CG = false is the A/B form
+#define LDSPEC(p) (CG ? __ldcg(p) : __ldg(p))
 
 // ------------------------------------------------------------------ leftover-warp form of the inverse kernel
 // 4092 / 31 = 132 first-stage butterflies per code period = 4 warps + 4 threads: in acq_inverse_kernel the fifth warp
@@ -18,7 +23,7 @@ namespace gb {
 // acq_inverse_kernel's (tests/test_gpu_acquisition.py::test_leftover_warp_kernel_is_bit_identical).
 enum { BAR_A_DONE = 1, BAR_MID = 2, BAR_END = 3 };
 
-template <class PW>
+template <class PW, bool CG>
 __device__ __noinline__ void lw_leftover_warp(const float2* __restrict__ spec, const float2* __restrict__ code,
                                               float2* __restrict__ line, int n_groups)
 {
@@ -36,7 +41,7 @@ __device__ __noinline__ void lw_leftover_warp(const float2* __restrict__ spec, c
         if (g < n_groups) {
             const float2* __restrict__ sg = spec + (size_t)g * N;
             dft_odd_prime_stream_acc<GM::R, true, 3>(
-                [&](int q) { return cmul_conj(__ldg(&sg[q * GM::NB + b]), __ldg(&code[q * GM::NB + b])); }, h);
+                [&](int q) { return cmul_conj(LDSPEC(&sg[q * GM::NB + b]), __ldg(&code[q * GM::NB + b])); }, h);
         }
     };
     compute(0);
@@ -52,7 +57,7 @@ __device__ __noinline__ void lw_leftover_warp(const float2* __restrict__ spec, c
     named_bar_sync(BAR_END, TALL);
 }
 
-template <class PW> __global__ void __launch_bounds__(PW::T + 32, PW::MINB) acq_inverse_lw_kernel(const AcqArgs a)
+template <class PW, bool CG> __global__ void __launch_bounds__(PW::T + 32, PW::MINB) acq_inverse_lw_kernel(const AcqArgs a)
 {
     extern __shared__ float2 smem_line[];
     constexpr int LASTS = PW::NSTAGE - 1;
@@ -61,18 +66,20 @@ template <class PW> __global__ void __launch_bounds__(PW::T + 32, PW::MINB) acq_
     constexpr int N = PW::N;
     constexpr int TW = PW::T, TALL = PW::T + 32;
     constexpr int REM = GM::NB - TW;     // ragged butterflies per group
-    constexpr int BATCH = 32 / REM;      // groups per leftover pass
     static_assert(PW::PFA && LASTS == 2, "three-stage prime-factor plans only");
     static_assert(REM > 0 && REM <= 16 && 32 % REM == 0, "the ragged part must tile a warp");
     const int n_groups = a.K / a.n_coh;
+    // Doppler-major block order: the n_active CTAs that share one bin's spectra run together (L2 reuse).  PRN-major
+    // Doppler tiles (co-resident CTAs sharing a code in L1) were measured and change nothing.
     const int dl = (int)(blockIdx.x / (unsigned)a.n_active);
     const int row = a.rows[blockIdx.x % (unsigned)a.n_active];
-    const float2* __restrict__ code = a.code_fft + (size_t)row * N;
-    const float2* __restrict__ spec = a.spec + (size_t)dl * n_groups * N;
+    const int2 sm = a.inv_map ? __ldg(&a.inv_map[a.d_lo + dl]) : make_int2(dl, 0);   // {spectrum slot, shifted code set}
+    const float2* __restrict__ code = a.code_fft + ((size_t)sm.y * a.n_prn + row) * N;
+    const float2* __restrict__ spec = a.spec + (size_t)sm.x * n_groups * N;
     float2* __restrict__ line = smem_line;
 
     if (threadIdx.x >= TW) {
-        lw_leftover_warp<PW>(spec, code, line, n_groups);
+        lw_leftover_warp<PW, CG>(spec, code, line, n_groups);
         return;
     }
     {
@@ -88,7 +95,7 @@ template <class PW> __global__ void __launch_bounds__(PW::T + 32, PW::MINB) acq_
             {
                 float2 v[GM::R];
 #pragma unroll
-                for (int q = 0; q < GM::R; q++) v[q] = cmul_conj(__ldg(&sg[q * GM::NB + b]), __ldg(&code[q * GM::NB + b]));
+                for (int q = 0; q < GM::R; q++) v[q] = cmul_conj(LDSPEC(&sg[q * GM::NB + b]), __ldg(&code[q * GM::NB + b]));
                 dft_emit<GM::R, true>(v, [&](int j, float2 y) { line[PW::phys(b * GM::R + j)] = y; });
             }
             named_bar_sync(BAR_A_DONE, TALL);
@@ -106,11 +113,15 @@ cudaError_t acq_launch_inverse_lw4092(const AcqArgs& a, int n_d, cudaStream_t st
     using PW = P4092W;
     static_assert(PW::T + 32 == P4092::T && PW::LINE == P4092::LINE, "same line as the default plan, one extra warp");
     const size_t smem = sizeof(float2) * (size_t)PW::LINE;
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(acq_inverse_lw_kernel<PW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
+    static const bool ldg = getenv("GB_ACQ_SPEC_LDG") != nullptr;   // A/B switch (tools/time_acq.py): 1.711 vs 1.697 ms
+    cudaError_t e;
+    if (ldg) {
+        if ((e = cudaFuncSetAttribute(acq_inverse_lw_kernel<PW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        acq_inverse_lw_kernel<PW, false><<<n_d * a.n_active, PW::T + 32, smem, st>>>(a);
+    } else {
+        if ((e = cudaFuncSetAttribute(acq_inverse_lw_kernel<PW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        acq_inverse_lw_kernel<PW, true><<<n_d * a.n_active, PW::T + 32, smem, st>>>(a);
     }
-    acq_inverse_lw_kernel<PW><<<n_d * a.n_active, PW::T + 32, smem, st>>>(a);
     return cudaGetLastError();
 }
 

@@ -7,6 +7,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -26,6 +27,7 @@ struct FftRes {
     float2* tw = nullptr;
     int* fop = nullptr;
     int* npos = nullptr;  // prime-factor plans: input index of line position l
+    std::vector<int> fop_host;  // natural frequency at scrambled position l (host copy of fop)
 };
 
 }  // namespace
@@ -84,6 +86,14 @@ struct gb_handle {
     float* row_dev = nullptr;
     float last_acq_ms = 0.f;
     cudaEvent_t ev_slice[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // upload slices
+    // Doppler aliasing: bins whose carriers differ by a whole number of FFT bins share one forward spectrum
+    bool alias_enabled = true, alias_ok = false;
+    int n_base = 0, n_shift = 0;
+    int* fwd_bins_dev = nullptr;
+    int2* inv_map_dev = nullptr;
+    size_t fwd_bins_cap = 0, inv_map_cap = 0;
+    float2* code_fft_shift = nullptr;
+    size_t code_fft_shift_cap = 0;
 
     // fine Doppler (N3)
     float2* fine_x = nullptr;
@@ -242,6 +252,7 @@ int fft_resources(gb_handle* h, int plan, int n, FftRes** out)
         CK(cudaMalloc((void**)&r.fop, sizeof(int) * n));
         CK(cudaMemcpy(r.tw, tw.data(), sizeof(float2) * tw.size(), cudaMemcpyHostToDevice));
         CK(cudaMemcpy(r.fop, fop.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
+        r.fop_host = fop;
     }
     *out = &r;
     return GB_OK;
@@ -471,7 +482,7 @@ extern "C" int gb_destroy(gb_handle* h)
     if (!h) return GB_EINVAL;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
-    void* dev_ptrs[] = {h->fe_idx, h->fe_lut, h->fe_state, h->fe_stage, h->otw, h->acc_rows, h->spec, h->ring, h->i8_stage, h->tw, h->code_fft, h->tables, h->rot, h->chunk, h->codes_dev, h->cells_dev,
+    void* dev_ptrs[] = {h->fwd_bins_dev, h->inv_map_dev, h->code_fft_shift, h->fe_idx, h->fe_lut, h->fe_state, h->fe_stage, h->otw, h->acc_rows, h->spec, h->ring, h->i8_stage, h->tw, h->code_fft, h->tables, h->rot, h->chunk, h->codes_dev, h->cells_dev,
                         h->rows_dev, h->row_dev, h->ca_table_dev, h->ch_dev, h->corr_dev, h->ran_dev, h->lost_dev,
                         h->hist_dev, h->trk_data, h->offs_dev, h->fine_x, h->fine_y, h->fine_codes, h->fine_u64, h->fine_mean,
                         h->fine_mag, h->tables_perm, h->iq_perm};
@@ -772,6 +783,8 @@ extern "C" int gb_acq_configure(gb_handle* h, int fft_size, float fs, int n_prn,
     h->npos = h->pfa ? fr->npos : nullptr;
     h->D = 0; h->n_coh = 1;
     h->carr.clear();
+    h->alias_ok = false;
+    h->alias_enabled = true;   // like n_coh, a per-configuration setting
     return GB_OK;
 }
 
@@ -806,6 +819,98 @@ static int upload_rotators(gb_handle* h)
     return GB_OK;
 }
 
+// Doppler aliasing.  With carr_d = carr_b + m * fs/N (m integer, exactly) the wiped block of bin d is the wiped block of
+// bin b times exp(-j 2 pi m n / N), so its spectrum is a circular shift: X_d[k] = X_b[k + m].  The forward path (wipe-
+// off, coherent pre-sum, forward FFT) is then needed for the base bin only, and
+//   IFFT_k{ X_d[k] conj(C[k]) }[n] = exp(-j 2 pi m n / N) * IFFT_j{ X_b[j] conj(C[j - m]) }[n]:
+// the inverse kernel pairs the base spectrum with the code spectrum shifted by m (one re-indexed copy of the code
+// spectra per distinct m, built here) and the unit-modulus ramp vanishes in |.|^2.  The coherent rotators
+// exp(-j 2 pi carr c N / fs) of d and b differ by whole turns.  Exact up to the f32 rounding of the reference's table
+// phases (cos(i * step_d) vs cos(i * step_b) shifted): ~1e-6 relative on the correlation power.
+// Only tables built by gb_acq_make_doppler_tables are analysed; caller-supplied tables are used as given.
+static int build_alias_map(gb_handle* h)
+{
+    h->alias_ok = false;
+    h->n_base = h->n_shift = 0;
+    if (h->cluster || h->D < 2 || h->plan < 0) return GB_OK;
+    const int D = h->D, N = h->N;
+    const double fs = (double)h->fs;
+    std::vector<int> bases, shift_of(D);
+    std::vector<int2> inv(D);
+    for (int d = 0; d < D; d++) {
+        bool found = false;
+        for (size_t bi = 0; bi < bases.size() && !found; bi++) {
+            const double mN = ((double)h->carr[d] - (double)h->carr[bases[bi]]) * (double)N;   // exact in f64
+            const double m = nearbyint(mN / fs);
+            if (fabs(m) < (double)N && m * fs == mN) {
+                inv[d].x = (int)bi;
+                shift_of[d] = (int)m;
+                found = true;
+            }
+        }
+        if (!found) {
+            inv[d].x = (int)bases.size();
+            shift_of[d] = 0;
+            bases.push_back(d);
+        }
+    }
+    if ((int)bases.size() == D) return GB_OK;   // no two bins a whole number of FFT bins apart
+    std::vector<int> shifts(shift_of);
+    std::sort(shifts.begin(), shifts.end());
+    shifts.erase(std::unique(shifts.begin(), shifts.end()), shifts.end());
+    const size_t set = (size_t)h->n_prn * N;
+    if (shifts.size() * set * sizeof(float2) > ((size_t)256 << 20)) return GB_OK;
+    for (int d = 0; d < D; d++)
+        inv[d].y = (int)(std::lower_bound(shifts.begin(), shifts.end(), shift_of[d]) - shifts.begin());
+    // code spectra are stored scrambled + transposed: element t = q * NB + b is line position l = b * R + q (R = last
+    // radix), which holds natural frequency fop[l].  Shifted set s: dst frequency j takes src frequency j - m.
+    const std::vector<int>& fop = h->fft[h->plan].fop_host;
+    if ((int)fop.size() != N) return GB_OK;
+    int radix[8];
+    const int ns = gb::acq_plan_radices(h->plan, radix);
+    const int R = radix[ns - 1], NB = N / R;
+    std::vector<int> pof(N);
+    for (int l = 0; l < N; l++) pof[fop[l]] = l;
+    std::vector<int> gidx(shifts.size() * (size_t)N);
+    for (size_t si = 0; si < shifts.size(); si++)
+        for (int t = 0; t < N; t++) {
+            const int l = (t % NB) * R + t / NB;
+            const int js = (int)((((long long)fop[l] - shifts[si]) % N + N) % N);
+            const int l2 = pof[js];
+            gidx[si * N + t] = (l2 % R) * NB + l2 / R;
+        }
+    int rc;
+    int* gidx_dev = nullptr;
+    if ((rc = ensure(h, &h->code_fft_shift, &h->code_fft_shift_cap, shifts.size() * set))) return rc;
+    if ((rc = ensure(h, &h->fwd_bins_dev, &h->fwd_bins_cap, bases.size()))) return rc;
+    if ((rc = ensure(h, &h->inv_map_dev, &h->inv_map_cap, (size_t)D))) return rc;
+    CK(cudaMalloc((void**)&gidx_dev, gidx.size() * sizeof(int)));
+    cudaError_t e = cudaMemcpyAsync(gidx_dev, gidx.data(), gidx.size() * sizeof(int), cudaMemcpyHostToDevice, h->s_acq);
+    if (e == cudaSuccess) e = gb::acq_launch_shift_codes(h->code_fft, gidx_dev, (int)shifts.size(), h->n_prn, N, h->code_fft_shift, h->s_acq);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h->fwd_bins_dev, bases.data(), bases.size() * sizeof(int), cudaMemcpyHostToDevice, h->s_acq);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h->inv_map_dev, inv.data(), (size_t)D * sizeof(int2), cudaMemcpyHostToDevice, h->s_acq);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->s_acq);
+    cudaFree(gidx_dev);
+    if (e != cudaSuccess) return fail(h, e, "build_alias_map");
+    h->n_base = (int)bases.size();
+    h->n_shift = (int)shifts.size();
+    h->alias_ok = true;
+    return GB_OK;
+}
+
+extern "C" int gb_acq_set_doppler_aliasing(gb_handle* h, int on)
+{
+    if (!h) return GB_EINVAL;
+    h->alias_enabled = on != 0;
+    return GB_OK;
+}
+// number of forward spectra the next shared-chain search computes (== n_doppler when nothing is shared)
+extern "C" int gb_acq_forward_bins(gb_handle* h)
+{
+    if (!h) return GB_EINVAL;
+    return (h->alias_ok && h->alias_enabled) ? h->n_base : h->D;
+}
+
 extern "C" int gb_acq_make_doppler_tables(gb_handle* h, float f_if, const float* dopplers, int D, float* carr_out)
 {
     if (!h || !dopplers || D < 1 || D > 32767) return GB_EINVAL;
@@ -830,7 +935,8 @@ extern "C" int gb_acq_make_doppler_tables(gb_handle* h, float f_if, const float*
     cudaFree(steps_dev);
     if (e != cudaSuccess) return fail(h, e, "doppler_table_kernel");
     h->D = D;
-    return upload_rotators(h);
+    if ((rc = upload_rotators(h))) return rc;
+    return build_alias_map(h);
 }
 
 extern "C" int gb_acq_set_doppler_tables(gb_handle* h, const gb_c32* tables, const float* carr, int D)
@@ -844,6 +950,7 @@ extern "C" int gb_acq_set_doppler_tables(gb_handle* h, const gb_c32* tables, con
     CK(cudaMemcpy(h->tables, tables, (size_t)D * h->N * sizeof(float2), cudaMemcpyHostToDevice));
     h->carr.assign(carr, carr + D);
     h->D = D;
+    h->alias_ok = false;   // caller-supplied tables are used as given
     return upload_rotators(h);
 }
 
@@ -932,6 +1039,7 @@ static int search_cells(gb_handle* h, const float2* iq_dev, uint64_t start, uint
         a.cells = h->cells_dev; a.row_out = nullptr; a.d0 = 0; a.spec = nullptr; a.d_lo = 0;
         a.otw = h->otw; a.acc_rows = nullptr; a.npos = h->npos; a.g_lo = 0; a.g_cnt = K / h->n_coh;
         a.plain_inverse = h->mode == GB_ACQ_SHARED_PLAIN;
+        a.fwd_bins = nullptr; a.inv_map = nullptr; a.n_prn = h->n_prn;
         if (h->pfa) {
             int rc = ensure(h, &h->iq_perm, &h->iq_perm_cap, (size_t)K * h->N);
             if (rc) return rc;
@@ -951,8 +1059,15 @@ static int search_cells(gb_handle* h, const float2* iq_dev, uint64_t start, uint
             const size_t per_d = (size_t)(K / h->n_coh) * h->N;
             size_t slab = ((size_t)1 << 27) / per_d;  // complex elements: 2^27 * 8 B = 1 GiB
             if (slab < 1) slab = 1;
+            // Doppler aliasing: forward spectra for the base bins only, every bin's inverse pass in one launch
+            const bool alias = h->alias_ok && h->alias_enabled && (size_t)h->n_base <= slab;
+            const int n_fwd = alias ? h->n_base : h->D;
+            if (alias) {
+                a.fwd_bins = h->fwd_bins_dev; a.inv_map = h->inv_map_dev; a.code_fft = h->code_fft_shift;
+                slab = h->D;
+            }
             if (slab > (size_t)h->D) slab = h->D;
-            int rc = ensure(h, &h->spec, &h->spec_cap, slab * per_d);
+            int rc = ensure(h, &h->spec, &h->spec_cap, (alias ? (size_t)n_fwd : slab) * per_d);
             if (rc) return rc;
             a.spec = h->spec;
             const int n_groups = K / h->n_coh;
@@ -974,17 +1089,24 @@ static int search_cells(gb_handle* h, const float2* iq_dev, uint64_t start, uint
                     if (h->pfa)
                         CK(gb::acq_launch_permute(h->chunk, 0, ~0ull, h->npos, h->N, (int)b0, (int)nb, h->iq_perm, h->s_acq));
                     a.g_lo = g0; a.g_cnt = g1 - g0;
-                    CK(gb::acq_launch_forward(h->plan, a, h->D, h->s_acq));
+                    CK(gb::acq_launch_forward(h->plan, a, n_fwd, h->s_acq));
                 }
                 a.g_lo = 0; a.g_cnt = 0;   // forward path done: inverse kernel only
                 CK(gb::acq_launch_shared(h->plan, a, h->D, h->s_acq));
             } else {
                 if (host_iq) CK(cudaMemcpyAsync(h->chunk, host_iq, (size_t)K * h->N * sizeof(float2), cudaMemcpyHostToDevice, h->s_acq));
                 if (h->pfa) CK(pfa_inputs(h, a, K));
-                for (int d_lo = 0; d_lo < h->D; d_lo += (int)slab) {
-                    a.d_lo = d_lo;
-                    const int n_d = (h->D - d_lo) < (int)slab ? (h->D - d_lo) : (int)slab;
-                    CK(gb::acq_launch_shared(h->plan, a, n_d, h->s_acq));
+                if (alias) {
+                    a.d_lo = 0;
+                    CK(gb::acq_launch_forward(h->plan, a, n_fwd, h->s_acq));
+                    a.g_cnt = 0;   // forward path done: inverse kernel only
+                    CK(gb::acq_launch_shared(h->plan, a, h->D, h->s_acq));
+                } else {
+                    for (int d_lo = 0; d_lo < h->D; d_lo += (int)slab) {
+                        a.d_lo = d_lo;
+                        const int n_d = (h->D - d_lo) < (int)slab ? (h->D - d_lo) : (int)slab;
+                        CK(gb::acq_launch_shared(h->plan, a, n_d, h->s_acq));
+                    }
                 }
             }
             CK(cudaEventRecord(h->ev_a1, h->s_acq));
@@ -1142,6 +1264,7 @@ extern "C" int gb_acq_bin_power(gb_handle* h, const gb_c32* iq, int K, int prn, 
     a.cells = nullptr; a.row_out = h->row_dev; a.d0 = doppler_bin; a.spec = nullptr; a.d_lo = 0;
     a.otw = h->otw; a.acc_rows = nullptr; a.npos = h->npos; a.g_lo = 0; a.g_cnt = K / h->n_coh;
     a.plain_inverse = h->mode == GB_ACQ_SHARED_PLAIN;
+    a.fwd_bins = nullptr; a.inv_map = nullptr; a.n_prn = h->n_prn;
     if (h->pfa) {
         rc = ensure(h, &h->iq_perm, &h->iq_perm_cap, (size_t)K * h->N);
         if (rc) return rc;

@@ -150,6 +150,18 @@ int gb_acq_set_coherent(gb_handle *h, int n_coh);
 #define GB_ACQ_SHARED 1
 #define GB_ACQ_SHARED_PLAIN 2
 int gb_acq_set_mode(gb_handle *h, int mode);
+/* Doppler aliasing (shared chain, on by default).  When two bins of a grid built by gb_acq_make_doppler_tables lie a
+ * whole number m of FFT bins (fs / fft_size) apart, the wiped block of one is the other's times exp(-j 2 pi m n / N):
+ * its spectrum is the other's circularly shifted by m.  The forward path (wipe-off, coherent sum, forward FFT) then
+ * runs for one bin per class only and the inverse kernel pairs that spectrum with the code spectrum shifted by m
+ * (the classic circular-shift Doppler search).  Mathematically identical to doppler_shift.rs:11-58; numerically it
+ * replaces the f32 rounding of cos(i * step_d) by that of the class's first bin (~1e-6 relative on the power, well
+ * inside the 1e-3 contract).  off = every bin runs its own forward path with its own table (reference arithmetic).
+ * BASELINE config 2 (50 Hz steps, 1 kHz FFT bins): 201 bins -> 20 forward spectra.  gb_acq_configure switches it
+ * back on (like n_coh, it is a per-configuration setting). */
+int gb_acq_set_doppler_aliasing(gb_handle *h, int on);
+/* number of forward spectra per group the next shared-chain search computes (== n_doppler when nothing is shared) */
+int gb_acq_forward_bins(gb_handle *h);
 /* samples_per_chip > 0 enables peak2; threshold is is_good_satellite's 7.0 */
 int gb_acq_set_detector(gb_handle *h, float threshold, int samples_per_chip);
 

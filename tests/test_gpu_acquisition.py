@@ -43,6 +43,7 @@ def test_fused_and_shared_chains_are_bit_identical(gpu, oracle, ffi, n):
     x = sdr_mock.baseband(fs, K, _sats(n, 7 * n), seed=n + 1)
     eng = _engine(gpu, n, fs)
     eng.make_doppler_tables(0.0, np.arange(-1000, 1001, 250, dtype=np.float32))
+    eng.set_doppler_aliasing(False)   # same wipe-off table per bin in both chains (aliasing: test_doppler_aliasing_*)
     eng.set_detector(7.0, 2)
     out = {}
     for n_coh in (1, 2):
@@ -66,6 +67,7 @@ def test_leftover_warp_kernel_is_bit_identical(gpu, ffi, K, n_coh):
     x = sdr_mock.baseband(fs, K, _sats(n, 5), seed=K)
     eng = _engine(gpu, n, fs)
     eng.make_doppler_tables(0.0, np.arange(-1500, 1501, 250, dtype=np.float32))
+    eng.set_doppler_aliasing(False)
     eng.set_detector(7.0, 4)
     eng.set_coherent(n_coh)
     out = []
@@ -75,6 +77,75 @@ def test_leftover_warp_kernel_is_bit_identical(gpu, ffi, K, n_coh):
     assert out[1].tobytes() == out[2].tobytes()
     _assert_same_cells(out[0], out[1], exact_sum=False)
     assert out[0]["peak"].min() > 0 and out[0]["peak2"].min() > 0
+
+
+@pytest.mark.parametrize("n", [1024, 2048, 4092, 4096, 8184, 16368, 20000])
+def test_doppler_aliasing_matches_per_bin_tables(gpu, oracle, ffi, n):
+    """Bins a whole number of FFT bins apart share one forward spectrum (gb_acq_set_doppler_aliasing, default on):
+    13 bins at 250 Hz over 1 kHz FFT bins -> 4 forward spectra, shifts -1..+2.  Against the same search with every
+    bin's own reference table: identical arg-max on every cell with a clear peak, powers within 2e-5 (the f32
+    rounding of the table phases is all that differs), through the ring path and the sliced host-pointer path,
+    with and without coherent pre-sum; and against the oracle within the 1e-3 contract."""
+    from gnss_sdr_rs_b200 import ring, sdr_mock
+    fs = float(n) * 1000.0
+    K = 4
+    x = sdr_mock.baseband(fs, K, _sats(n, 3 * n + 1), seed=n + 5)
+    dopplers = np.arange(-1500, 1501, 250, dtype=np.float32)
+    eng = _engine(gpu, n, fs)
+    eng.make_doppler_tables(0.0, dopplers)
+    eng.set_detector(7.0, 2)
+    assert eng.forward_bins() == 4
+    rb = ring.MulticastRingBuffer(gpu, 1 << 17)
+    rb.write_samples(x)
+    modes = (ffi.GB_ACQ_SHARED, ffi.GB_ACQ_SHARED_PLAIN) if n == 4092 else (ffi.GB_ACQ_SHARED,)
+    for n_coh in (1, 2):
+        eng.set_coherent(n_coh)
+        eng.set_doppler_aliasing(False)
+        assert eng.forward_bins() == len(dopplers)
+        ref = eng.search_cells(x, K).copy()
+        eng.set_doppler_aliasing(True)
+        for mode in modes:
+            eng.set_mode(mode)
+            for got in (eng.search_cells(x, K).copy(), eng.search_cells_ring(0, K).copy()):
+                np.testing.assert_allclose(got["peak"], ref["peak"], rtol=2e-5)
+                np.testing.assert_allclose(got["sum8"], ref["sum8"], rtol=2e-5)
+                np.testing.assert_allclose(got["peak2"], ref["peak2"], rtol=2e-5)
+                clear = ref["peak"] > 1.05 * ref["peak2"]
+                assert clear.mean() > 0.5
+                assert (got["argmax"][clear] == ref["argmax"][clear]).all()
+        eng.set_mode(ffi.GB_ACQ_SHARED)
+    # reference arithmetic (oracle) vs the aliased search, n_coh = 1
+    eng.set_coherent(1)
+    cells = eng.search_cells(x, K)
+    carr, tabs = oracle.doppler_tables(0.0, dopplers, fs, n)
+    for s in _sats(n, 3 * n + 1)[:2]:
+        w = oracle.AcqWorker(s["prn"], n, fs)
+        o = w.cells(x, tabs, K)
+        np.testing.assert_allclose(cells[s["prn"] - 1]["peak"], o["peak"], rtol=REL)
+        best = int(o["peak"].argmax())
+        assert int(cells[s["prn"] - 1]["argmax"][best]) == int(o["argmax"][best])
+        assert abs(int(o["argmax"][best]) - s["code_phase"]) <= max(1, n // 2046)   # within half a chip of the truth
+    # decisions through the public search are the oracle's
+    found = {r["prn"]: r for r in eng.search(x, K) if r}
+    for prn in sorted(found)[:3]:
+        r0 = oracle.AcqWorker(prn, n, fs).search_satellite(x, tabs, carr, 0, K)
+        assert r0 is not None and r0["code_phase_samples"] == found[prn]["code_phase_samples"]
+        assert r0["carrier_freq"] == found[prn]["carrier_freq"]
+
+
+def test_doppler_aliasing_needs_exact_bin_multiples(gpu):
+    """fs / fft_size of the reference recording is 999.97 Hz: bins 1 kHz apart are NOT whole FFT bins apart and every
+    bin keeps its own forward path; caller-supplied tables are never analysed."""
+    from gnss_sdr_rs_b200 import acquisition
+    eng = _engine(gpu, 16368, 16367600.0)
+    grid = np.array(acquisition.reference_doppler_grid(), np.float32)
+    eng.make_doppler_tables(4130400.0, grid)
+    assert eng.forward_bins() == len(grid)
+    eng2 = _engine(gpu, 4092, 4.092e6)
+    carr = eng2.make_doppler_tables(0.0, np.array([0.0, 1000.0, 2000.0, 500.0], np.float32))
+    assert eng2.forward_bins() == 2
+    eng2.set_doppler_tables(eng2.get_doppler_tables(), carr)
+    assert eng2.forward_bins() == 4
 
 
 @pytest.mark.parametrize("n", [1024, 2048, 4092, 4096, 8184, 16368, 20000])
