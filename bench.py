@@ -41,29 +41,38 @@ SATS = [(3, 1230.0, 100, 45.0), (7, -2210.0, 2000, 40.0), (11, 3370.0, 3100, 42.
         (19, 4120.0, 1500, 38.0), (22, -3900.0, 4000, 36.0), (28, 60.0, 2500, 47.0), (31, 2780.0, 300, 35.0)]
 
 
+# filled in from the ncu capture of the same command (profiles/round1_v7_alias_lw.txt)
+KERNEL_SHARES_NOTE = ("acq_inverse_lw_kernel ~98% / acq_forward_kernel (20 of 201 bins, Doppler aliasing) ~1% / permute < 1% "
+                      "of the chain (profiles/round1_v7_alias_lw.txt)")
+
+
 def make_recording(seed):
     from gnss_sdr_rs_b200 import sdr_mock
     sats = [{"prn": p, "doppler": d, "code_phase": c, "cn0_dbhz": cn} for p, d, c, cn in SATS]
     return sdr_mock.baseband(FS, K_MS, sats, seed=seed, nav=True)
 
 
-def acq_flops():
+def acq_flops(n_forward=None):
     """Algorithmic FLOPs of one step (conventions of SURVEY 8d: FFT = 5 N log2 N, cmul 6, |.|^2 3, add 1,
-    wipe-off cmul 6, rotate-accumulate 8)."""
+    wipe-off cmul 6, rotate-accumulate 8).  Returns (minimal, fused, as_run): `minimal` is SURVEY 8d's structure (one
+    forward path per Doppler bin, shared by the 32 PRNs) and stays the roofline numerator; `as_run` counts the forward
+    path only for the n_forward bins the shared chain really transforms (Doppler aliasing: 20 of 201)."""
     P, D, N, K, G = N_PRN, len(DOPPLERS), N_FFT, K_MS, N_NONCOH
     lg = math.log2(N)
     shared_per_d = K * N * 14 + G * 5 * N * lg          # wipe-off + coherent pre-sum + forward FFT
     per_pd = G * N * (6 + 5 * lg + 3 + 1)               # x conj(code), IFFT, |.|^2, accumulate
     minimal = D * shared_per_d + P * D * per_pd         # forward path shared by the 32 PRNs
     fused = P * D * (shared_per_d + per_pd)             # the single-kernel form repeats the forward path per PRN
-    return minimal, fused
+    as_run = (D if n_forward is None else n_forward) * shared_per_d + P * D * per_pd
+    return minimal, fused, as_run
 
 
-def acq_bytes(shared=True):
-    """Algorithmic HBM bytes of one search: IQ + code spectra + wipe-off tables + cells, plus (shared chain) the
-    forward spectra written once and read once."""
+def acq_bytes(shared=True, n_forward=None, n_shift=1):
+    """Algorithmic HBM bytes of one search: IQ + code spectra (one set per distinct alias shift) + wipe-off tables of
+    the transformed bins + cells, plus (shared chain) the forward spectra written once and read once."""
     P, D, N, K, G = N_PRN, len(DOPPLERS), N_FFT, K_MS, N_NONCOH
-    return 8 * N * K + 8 * N * P + 8 * N * D + 16 * P * D + (2 * 8 * N * D * G if shared else 0)
+    F = D if n_forward is None else n_forward
+    return 8 * N * K + 8 * N * P * n_shift + 8 * N * F + 16 * P * D + (2 * 8 * N * F * G if shared else 0)
 
 
 class ClockSampler(threading.Thread):
@@ -419,8 +428,11 @@ def run_ours(args, rank, world, local_rank):
 
     if rank == 0:
         peak_tf = ctypes_float(hd, "gb_bench_fp32_tflops")
-        minimal, fused_flops = acq_flops()
-        as_run = fused_flops if args.acq_mode == "fused" else minimal   # the shared chain runs the minimal structure
+        n_fwd = eng.forward_bins() if args.acq_mode != "fused" else len(DOPPLERS)
+        n_shift = int(math.ceil(len(DOPPLERS) / n_fwd)) if n_fwd < len(DOPPLERS) else 1
+        minimal, fused_flops, shared_flops = acq_flops(n_fwd)
+        as_run = fused_flops if args.acq_mode == "fused" else shared_flops
+        abytes = acq_bytes(args.acq_mode != "fused", n_fwd, n_shift)
         achieved = minimal / (kernel_ms_avg * 1e-3) / 1e12
         peaks = {}
         try:
@@ -450,14 +462,16 @@ def run_ours(args, rank, world, local_rank):
                              "peak_source": "measured live: gb_bench_fp32_tflops FMA probe (MEASURED_PEAKS.json has no "
                                             "FP32 figure; theoretical 148*128*2*1.965 GHz = 74.5)",
                              "flops_per_launch_minimal": minimal, "flops_per_launch_as_run": as_run,
-                             "kernel": ("acq_fused_kernel" if args.acq_mode == "fused" else "permute_blocks_kernel + acq_forward_kernel + acq_inverse_kernel") + "<PfaPlan<4092,160,4,12,11,31>>", "kernel_ms": kernel_ms_avg,
-                             "kernel_shares_ncu": "acq_inverse_kernel 90% / acq_forward_kernel 10% / permute < 1% of the chain; "
-                                                  "inverse kernel: FMA pipe 67% active, L1 data pipe 63%, issue 51% "
-                                                  "(profiles/round1_v6_final.txt)",
-                             "hbm_view": {"bound": "hbm", "algorithmic_bytes": acq_bytes(args.acq_mode != "fused"),
-                                          "achieved": acq_bytes(args.acq_mode != "fused") / (kernel_ms_avg * 1e-3) / 1e9,
+                             "forward_spectra_per_group": n_fwd,
+                             "kernel": ("acq_fused_kernel<PfaPlan<4092,160,4,12,11,31>>" if args.acq_mode == "fused" else
+                                        "permute_blocks_kernel + acq_forward_kernel<PfaPlan<4092,160,4,12,11,31>> + "
+                                        "acq_inverse_lw_kernel<PfaPlan<4092,128,4,12,11,31>> (128 working threads + leftover warp)"),
+                             "kernel_ms": kernel_ms_avg,
+                             "kernel_shares_ncu": KERNEL_SHARES_NOTE,
+                             "hbm_view": {"bound": "hbm", "algorithmic_bytes": abytes,
+                                          "achieved": abytes / (kernel_ms_avg * 1e-3) / 1e9,
                                           "peak": hbm_peak, "unit": "GB/s",
-                                          "frac": acq_bytes(args.acq_mode != "fused") / (kernel_ms_avg * 1e-3) / 1e9 / hbm_peak,
+                                          "frac": abytes / (kernel_ms_avg * 1e-3) / 1e9 / hbm_peak,
                                           "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback"}},
                 "clocks": clocks, "detected_prns": found}
         if trk_sharded is not None:

@@ -20,6 +20,11 @@ namespace gb {
     X(13, P4092v5) X(14, P4092v6) X(15, P4092v7) X(16, P4092v8)
 static const int kPlanSizes[] = {1024, 2048, 4092, 4096, 8184, 16368, 20000, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1};
 static const int kNumPlans = sizeof(kPlanSizes) / sizeof(int);
+// the default plan of each size (indices 0..6); the rest are tuning variants
+template <class P> constexpr bool kProductionPlan =
+    std::is_same<P, P1024>::value || std::is_same<P, P2048>::value || std::is_same<P, P4092>::value || std::is_same<P, P4096>::value ||
+    std::is_same<P, P8184>::value || std::is_same<P, P16368>::value || std::is_same<P, P20000>::value;
+int acq_plan_supports_alias(int plan) { return plan >= 0 && plan <= 6; }
 
 // Stage 0 of the forward DIF (L = N) with the carrier wipe-off (and, for n_coh > 1, the coherent
 // pre-sum of n_coh rotated blocks) fused into the global-memory load.
@@ -171,7 +176,10 @@ template <class P> __global__ void __launch_bounds__(P::T, P::MINB) acq_forward_
 // disappears: warps that finish the accumulate stage of group g early start loading and transforming group g+1 into
 // the other buffer, so the L2 latency at the head of stage A overlaps the slower warps' tail (the barrier after stage
 // A of g+1 is what guarantees everybody has left buffer g before stage A of g+2 overwrites it).
-template <class P, bool DB> __global__ void __launch_bounds__(P::T, P::MINB) acq_inverse_kernel(const AcqArgs a)
+// ALIAS = true: Doppler aliasing (AcqArgs::inv_map): the spectrum slot and the shifted code-spectrum set of the bin are
+// looked up.  A separate instantiation because these kernels sit on the register cliff: the three extra lines tripled
+// the spills of the ALIAS = false form (config 1: 0.62 -> 0.74 ms), which therefore stays exactly as it was.
+template <class P, bool DB, bool ALIAS> __global__ void __launch_bounds__(P::T, P::MINB) acq_inverse_kernel(const AcqArgs a)
 {
     extern __shared__ float2 smem_line[];
     constexpr int LASTS = P::NSTAGE - 1;
@@ -182,10 +190,18 @@ template <class P, bool DB> __global__ void __launch_bounds__(P::T, P::MINB) acq
     // Doppler-major block order: the n_active CTAs that share one bin's spectra run together (L2 reuse)
     const int dl = (int)(blockIdx.x / (unsigned)a.n_active);
     const int row = a.rows[blockIdx.x % (unsigned)a.n_active];
-    const int2 sm = a.inv_map ? __ldg(&a.inv_map[a.d_lo + dl]) : make_int2(dl, 0);   // {spectrum slot, shifted code set}
-    const float2* __restrict__ code = a.code_fft + ((size_t)sm.y * a.n_prn + row) * N;
+    // element offsets from a.code_fft / a.spec kept as 32-bit values (both buffers are far below 2^31 elements): the
+    // 64-bit pointers are re-formed per group from the uniform base, so ALIAS costs no extra long-lived register
+    unsigned code_off, spec_off;
+    if constexpr (ALIAS) {
+        const int2 sm = __ldg(&a.inv_map[a.d_lo + dl]);   // {spectrum slot, shifted code set}
+        code_off = ((unsigned)sm.y * (unsigned)a.n_prn + (unsigned)row) * (unsigned)N;
+        spec_off = (unsigned)sm.x * (unsigned)n_groups * (unsigned)N;
+    } else {
+        code_off = (unsigned)row * (unsigned)N;
+        spec_off = (unsigned)dl * (unsigned)n_groups * (unsigned)N;
+    }
     const float2* __restrict__ tw = a.tw;
-    const float2* __restrict__ spec = a.spec + (size_t)sm.x * n_groups * N;
 
     float acc[G0::ITERS][G0::R];
 #pragma unroll
@@ -195,7 +211,8 @@ template <class P, bool DB> __global__ void __launch_bounds__(P::T, P::MINB) acq
 
     for (int g = 0; g < n_groups; g++) {
         float2* __restrict__ line = DB ? smem_line + (g & 1) * P::LINE : smem_line;
-        const float2* __restrict__ sg = spec + (size_t)g * N;
+        const float2* __restrict__ sg = a.spec + (spec_off + (unsigned)g * (unsigned)N);
+        const float2* __restrict__ code = a.code_fft + code_off;
 #pragma unroll 1
         for (int it = 0; it < GM::ITERS; it++) {
             const int b = threadIdx.x + it * P::T;
@@ -494,12 +511,27 @@ template <class P> static cudaError_t launch_shared(const AcqArgs& a, int n_d, c
     }
     // double-buffered line when two lines fit the 227 KB of one SM at the plan's CTA count
     static const bool no_db = getenv("GB_ACQ_NODB") != nullptr;   // A/B switch (tools/time_acq.py)
+    if (a.inv_map) {
+        // aliased form: the seven production plans only (the tuning variants never request it, acq_plan_supports_alias)
+        if constexpr (kProductionPlan<P>) {
+            if (P::DB && !no_db) {
+                if ((e = set_smem(acq_inverse_kernel<P, true, true>, 2 * smem)) != cudaSuccess) return e;
+                acq_inverse_kernel<P, true, true><<<n_d * a.n_active, P::T, 2 * smem, st>>>(a);
+            } else {
+                if ((e = set_smem(acq_inverse_kernel<P, false, true>, smem)) != cudaSuccess) return e;
+                acq_inverse_kernel<P, false, true><<<n_d * a.n_active, P::T, smem, st>>>(a);
+            }
+            return cudaGetLastError();
+        } else {
+            return cudaErrorInvalidValue;
+        }
+    }
     if (P::DB && !no_db) {
-        if ((e = set_smem(acq_inverse_kernel<P, true>, 2 * smem)) != cudaSuccess) return e;
-        acq_inverse_kernel<P, true><<<n_d * a.n_active, P::T, 2 * smem, st>>>(a);
+        if ((e = set_smem(acq_inverse_kernel<P, true, false>, 2 * smem)) != cudaSuccess) return e;
+        acq_inverse_kernel<P, true, false><<<n_d * a.n_active, P::T, 2 * smem, st>>>(a);
     } else {
-        if ((e = set_smem(acq_inverse_kernel<P, false>, smem)) != cudaSuccess) return e;
-        acq_inverse_kernel<P, false><<<n_d * a.n_active, P::T, smem, st>>>(a);
+        if ((e = set_smem(acq_inverse_kernel<P, false, false>, smem)) != cudaSuccess) return e;
+        acq_inverse_kernel<P, false, false><<<n_d * a.n_active, P::T, smem, st>>>(a);
     }
     return cudaGetLastError();
 }

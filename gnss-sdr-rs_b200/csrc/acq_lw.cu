@@ -74,12 +74,13 @@ template <class PW, bool CG> __global__ void __launch_bounds__(PW::T + 32, PW::M
     const int dl = (int)(blockIdx.x / (unsigned)a.n_active);
     const int row = a.rows[blockIdx.x % (unsigned)a.n_active];
     const int2 sm = a.inv_map ? __ldg(&a.inv_map[a.d_lo + dl]) : make_int2(dl, 0);   // {spectrum slot, shifted code set}
-    const float2* __restrict__ code = a.code_fft + ((size_t)sm.y * a.n_prn + row) * N;
-    const float2* __restrict__ spec = a.spec + (size_t)sm.x * n_groups * N;
+    // 32-bit element offsets, pointers re-formed per group from the uniform bases (fewer long-lived registers)
+    const unsigned code_off = ((unsigned)sm.y * (unsigned)a.n_prn + (unsigned)row) * (unsigned)N;
+    const unsigned spec_off = (unsigned)sm.x * (unsigned)n_groups * (unsigned)N;
     float2* __restrict__ line = smem_line;
 
     if (threadIdx.x >= TW) {
-        lw_leftover_warp<PW, CG>(spec, code, line, n_groups);
+        lw_leftover_warp<PW, CG>(a.spec + spec_off, a.code_fft + code_off, line, n_groups);
         return;
     }
     {
@@ -91,7 +92,8 @@ template <class PW, bool CG> __global__ void __launch_bounds__(PW::T + 32, PW::M
             for (int j = 0; j < G0::R; j++) acc[it][j] = 0.f;
         const int b = threadIdx.x;
         for (int g = 0; g < n_groups; g++) {
-            const float2* __restrict__ sg = spec + (size_t)g * N;
+            const float2* __restrict__ sg = a.spec + (spec_off + (unsigned)g * (unsigned)N);
+            const float2* __restrict__ code = a.code_fft + code_off;
             {
                 float2 v[GM::R];
 #pragma unroll

@@ -832,7 +832,7 @@ static int build_alias_map(gb_handle* h)
 {
     h->alias_ok = false;
     h->n_base = h->n_shift = 0;
-    if (h->cluster || h->D < 2 || h->plan < 0) return GB_OK;
+    if (h->cluster || h->D < 2 || h->plan < 0 || !gb::acq_plan_supports_alias(h->plan)) return GB_OK;
     const int D = h->D, N = h->N;
     const double fs = (double)h->fs;
     std::vector<int> bases, shift_of(D);
