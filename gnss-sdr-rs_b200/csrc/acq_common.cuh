@@ -206,7 +206,8 @@ __device__ __forceinline__ void final_stage_accumulate(const float2* __restrict_
             }
             Dft<G0::R, true>::run(v);
 #pragma unroll
-            for (int j = 0; j < G0::R; j++) acc[it][j] = __fadd_rn(acc[it][j], __fmaf_rn(v[j].x, v[j].x, __fmul_rn(v[j].y, v[j].y)));
+            // two FMAs per point (acc + im^2, then + re^2): one instruction fewer than |.|^2 followed by an add
+            for (int j = 0; j < G0::R; j++) acc[it][j] = __fmaf_rn(v[j].x, v[j].x, __fmaf_rn(v[j].y, v[j].y, acc[it][j]));
         }
     }
 }
