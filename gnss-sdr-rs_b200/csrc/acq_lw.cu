@@ -98,14 +98,17 @@ template <class PW, bool CG> __global__ void __launch_bounds__(PW::T + 32, PW::M
                 float2 v[GM::R];
 #pragma unroll
                 for (int q = 0; q < GM::R; q++) v[q] = cmul_conj(LDSPEC(&sg[q * GM::NB + b]), __ldg(&code[q * GM::NB + b]));
+                // END of the previous group sits HERE, between this group's global loads and its first store to the
+                // line: a warp that leaves stage C early spends its L2 latency before the barrier instead of after it
+                if (g > 0) named_bar_sync(BAR_END, TALL);
                 dft_emit<GM::R, true>(v, [&](int j, float2 y) { line[PW::phys(b * GM::R + j)] = y; });
             }
             named_bar_sync(BAR_A_DONE, TALL);
             dit_stage<PW, 1, true>(line, a.tw);
             named_bar_sync(BAR_MID, TW);
             final_stage_accumulate<PW>(line, a.tw, acc);
-            named_bar_sync(BAR_END, TALL);
         }
+        named_bar_sync(BAR_END, TALL);   // the reduction reuses the line as scratch
         reduce_row_to_cell<PW, BAR_MID>(acc, smem_line, a.spc, &a.cells[(size_t)row * a.D + a.d_lo + dl], a.npos);
     }
 }
