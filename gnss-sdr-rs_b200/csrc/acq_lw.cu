@@ -23,31 +23,6 @@ namespace gb {
 // acq_inverse_kernel's (tests/test_gpu_acquisition.py::test_leftover_warp_kernel_is_bit_identical).
 enum { BAR_A_DONE = 1, BAR_MID = 2, BAR_END = 3 };
 
-// DIT stage S of a prime-factor plan (no twiddles) with ONE sub-block per warp pass: the SUB <= 32 butterflies of a block
-// read/write SUB consecutive complex per element index, so no request straddles a block boundary.  dit_stage's
-// thread-linear assignment does (SUB = 31 against 32 lanes) and pays a third wavefront on every shared-memory request of
-// the stage -- 19 % of the kernel's shared-memory wavefronts, on the busiest unit (L1 data pipe 78 %).  The number of
-// warp passes is the same (12 blocks of 31 = 372 butterflies = 11.6 warps).
-template <class P, int S, bool INV, int NWARPS> __device__ __forceinline__ void dit_stage_rows(float2* __restrict__ s)
-{
-    using G = StageGeo<P, S>;
-    static_assert(P::PFA && G::SUB <= 32, "one sub-block per warp pass");
-    constexpr int NBLK = P::N / G::L;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-#pragma unroll 1
-    for (int blk = warp; blk < NBLK; blk += NWARPS) {
-        if (lane < G::SUB) {
-            const int base = blk * G::L + lane;
-            float2 v[G::R];
-#pragma unroll
-            for (int q = 0; q < G::R; q++) v[q] = s[P::phys(base + q * G::SUB)];
-            Dft<G::R, INV>::run(v);
-#pragma unroll
-            for (int j = 0; j < G::R; j++) s[P::phys(base + j * G::SUB)] = v[j];
-        }
-    }
-}
-
 template <class PW, bool CG>
 __device__ __noinline__ void lw_leftover_warp(const float2* __restrict__ spec, const float2* __restrict__ code,
                                               float2* __restrict__ line, int n_groups)

@@ -610,6 +610,31 @@ template <class P, int S, bool INV> __device__ __forceinline__ void dit_stage(fl
     }
 }
 
+// DIT stage S of a prime-factor plan (no twiddles) with ONE sub-block per warp pass: the SUB <= 32 butterflies of a block
+// read/write SUB consecutive complex per element index, so no request straddles a block boundary.  dit_stage's
+// thread-linear assignment does (SUB = 31 against 32 lanes) and pays a third wavefront on every shared-memory request of
+// the stage -- 19 % of the kernel's shared-memory wavefronts, on the busiest unit (L1 data pipe 78 %).  The number of
+// warp passes is the same (12 blocks of 31 = 372 butterflies = 11.6 warps).
+template <class P, int S, bool INV, int NWARPS> __device__ __forceinline__ void dit_stage_rows(float2* __restrict__ s)
+{
+    using G = StageGeo<P, S>;
+    static_assert(P::PFA && G::SUB <= 32, "one sub-block per warp pass");
+    constexpr int NBLK = P::N / G::L;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll 1
+    for (int blk = warp; blk < NBLK; blk += NWARPS) {
+        if (lane < G::SUB) {
+            const int base = blk * G::L + lane;
+            float2 v[G::R];
+#pragma unroll
+            for (int q = 0; q < G::R; q++) v[q] = s[P::phys(base + q * G::SUB)];
+            Dft<G::R, INV>::run(v);
+#pragma unroll
+            for (int j = 0; j < G::R; j++) s[P::phys(base + j * G::SUB)] = v[j];
+        }
+    }
+}
+
 // DIF stages [S, LAST) with a barrier after each
 template <class P, int S, int LAST, bool INV> struct DifRange {
     static __device__ __forceinline__ void run(float2* s, const float2* tw)
@@ -626,6 +651,8 @@ template <class P, int S, int LAST, bool INV> struct DitRange {
     static __device__ __forceinline__ void run(float2* s, const float2* tw)
     {
         if constexpr (S > LAST) {
+            // (dit_stage_rows was measured in the one-CTA-per-SM kernels of 8184 / 16368 too: 0.609 -> 0.621 ms on config 1,
+            // so only the leftover-warp kernel uses it)
             dit_stage<P, S, INV>(s, tw);
             __syncthreads();
             DitRange<P, S - 1, LAST, INV>::run(s, tw);
