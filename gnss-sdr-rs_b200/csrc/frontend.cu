@@ -93,29 +93,55 @@ __global__ void __launch_bounds__(FE_THREADS) frontend_table_kernel(const float2
     const unsigned long long end = mu + period;
 
     auto tile_len = [&](int t) { return (int)((n - (unsigned long long)t * FE_TILE) < FE_TILE ? (n - (unsigned long long)t * FE_TILE) : FE_TILE); };
+    constexpr int PER = FE_TILE / FE_MOVERS;   // samples per mover and tile
     auto load = [&](int t) {
         float2* buf = fe_tiles + (t % 3) * FE_TILE;
         const int tn = tile_len(t);
         const float2* s = src + (unsigned long long)t * FE_TILE;
-        for (int i = m; i < tn; i += FE_MOVERS) buf[i] = __ldg(&s[i]);
+        float2 x[PER];
+#pragma unroll
+        for (int u = 0; u < PER; u++) {
+            const int i = m + u * FE_MOVERS;
+            if (i < tn) x[u] = __ldg(&s[i]);
+        }
+#pragma unroll
+        for (int u = 0; u < PER; u++) {
+            const int i = m + u * FE_MOVERS;
+            if (i < tn) buf[i] = x[u];
+        }
     };
     auto mix = [&](int t) {
-        // nco_lut.rs:8-15 verbatim: i' = I*re + Q*im, q' = I*im - Q*re with im = -sin; separate roundings
+        // nco_lut.rs:8-15 verbatim: i' = I*re + Q*im, q' = I*im - Q*re with im = -sin; separate roundings.
+        // The orbit-index and LUT look-ups of a thread's PER samples are issued together (two dependent global / L1
+        // latencies per tile instead of two per sample).
         const float2* buf = fe_tiles + (t % 3) * FE_TILE;
         const int tn = tile_len(t);
         const unsigned long long first = (unsigned long long)t * FE_TILE;
         unsigned long long pos = pos0 + first + m;                  // < end + n
         if (pos >= end) pos = mu + (pos - mu) % period;
-        for (int i = m; i < tn; i += FE_MOVERS) {
-            const unsigned k = __ldg(&idx_tab[pos]);
-            const float lc = __ldg(&lut[k]), ls = __ldg(&lut[2048 + k]);
-            const float2 x = buf[i];
-            float2 y;
-            y.x = __fadd_rn(__fmul_rn(x.x, lc), __fmul_rn(x.y, ls));
-            y.y = __fsub_rn(__fmul_rn(x.x, ls), __fmul_rn(x.y, lc));
-            ring[(head + first + i) & mask] = y;
+        unsigned k[PER];
+        float lc[PER], ls[PER];
+#pragma unroll
+        for (int u = 0; u < PER; u++) {
+            k[u] = (m + u * FE_MOVERS < tn) ? __ldg(&idx_tab[pos]) : 0u;
             pos += FE_MOVERS;                                       // period >= FE_MOVERS: one subtraction wraps
             if (pos >= end) pos -= period;
+        }
+#pragma unroll
+        for (int u = 0; u < PER; u++) {
+            lc[u] = __ldg(&lut[k[u]]);
+            ls[u] = __ldg(&lut[2048 + k[u]]);
+        }
+#pragma unroll
+        for (int u = 0; u < PER; u++) {
+            const int i = m + u * FE_MOVERS;
+            if (i < tn) {
+                const float2 x = buf[i];
+                float2 y;
+                y.x = __fadd_rn(__fmul_rn(x.x, lc[u]), __fmul_rn(x.y, ls[u]));
+                y.y = __fsub_rn(__fmul_rn(x.x, ls[u]), __fmul_rn(x.y, lc[u]));
+                ring[(head + first + i) & mask] = y;
+            }
         }
     };
 
