@@ -45,6 +45,18 @@ def full(path):
         for w in WANT:
             if w in hdr:
                 print("  %-78s %s %s" % (w, r[hdr.index(w)], rows[1][hdr.index(w)]))
+        # warp-state (PC sampling) shares: where the resident warps spend their time
+        samp = {}
+        for i, h in enumerate(hdr):
+            if h.startswith("smsp__pcsamp_warps_issue_stalled_") and not h.endswith("_not_issued"):
+                try:
+                    samp[h[len("smsp__pcsamp_warps_issue_stalled_"):]] = float(r[i].replace(",", ""))
+                except ValueError:
+                    pass
+        tot = sum(samp.values())
+        if tot > 0:
+            print("  warp-state samples: " + ", ".join("%s %.1f%%" % (k, 100 * v / tot)
+                                                       for k, v in sorted(samp.items(), key=lambda x: -x[1]) if v / tot >= 0.01))
 
 
 if __name__ == "__main__":
