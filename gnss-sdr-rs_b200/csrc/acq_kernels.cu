@@ -83,7 +83,7 @@ template <class P, bool WANT_ROW> __global__ void __launch_bounds__(P::T, P::MIN
     const int d = WANT_ROW ? a.d0 : (int)(blockIdx.x % (unsigned)a.D);
     const int row = a.rows[WANT_ROW ? 0 : (int)(blockIdx.x / (unsigned)a.D)];
     const float2* __restrict__ w = a.tables + (size_t)d * N;
-    const float2* __restrict__ code = a.code_fft + (size_t)row * N;
+    const float2* __restrict__ code = a.code_fft + (size_t)row * P::SPEC_LEN;
     const float2* __restrict__ tw = a.tw;
     const float2* __restrict__ rot = a.rot ? a.rot + (size_t)d * a.n_coh : nullptr;
     const int n_coh = a.n_coh;
@@ -111,7 +111,7 @@ template <class P, bool WANT_ROW> __global__ void __launch_bounds__(P::T, P::MIN
                 for (int j = 0; j < GM::R; j++) v[j] = line[P::phys(base + j)];
                 Dft<GM::R, false>::run(v);
 #pragma unroll
-                for (int q = 0; q < GM::R; q++) v[q] = cmul_conj(v[q], __ldg(&code[q * GM::NB + b]));
+                for (int q = 0; q < GM::R; q++) v[q] = cmul_conj(v[q], __ldg(&code[q * P::SPEC_STRIDE + b]));
                 dft_emit<GM::R, true>(v, [&](int j, float2 y) { line[P::phys(base + j)] = y; });
             }
         }
@@ -156,7 +156,7 @@ template <class P> __global__ void __launch_bounds__(P::T, P::MINB) acq_forward_
     const int g = a.g_lo + (int)(blockIdx.x % (unsigned)a.g_cnt);
     const float2* __restrict__ w = a.tables + (size_t)d * N;
     const float2* __restrict__ rot = a.rot ? a.rot + (size_t)d * a.n_coh : nullptr;
-    float2* __restrict__ out = a.spec + ((size_t)dl * n_groups + g) * N;
+    float2* __restrict__ out = a.spec + ((size_t)dl * n_groups + g) * P::SPEC_LEN;
     stage0_wipe_forward<P>(a, w, rot, a.n_coh, g, line, a.tw);
     __syncthreads();
     DifRange<P, 1, LASTS, false>::run(line, a.tw);
@@ -167,7 +167,7 @@ template <class P> __global__ void __launch_bounds__(P::T, P::MINB) acq_forward_
             float2 v[GM::R];
 #pragma unroll
             for (int j = 0; j < GM::R; j++) v[j] = line[P::phys(b * GM::R + j)];
-            dft_emit<GM::R, false>(v, [&](int q, float2 y) { out[q * GM::NB + b] = y; });
+            dft_emit<GM::R, false>(v, [&](int q, float2 y) { out[q * P::SPEC_STRIDE + b] = y; });
         }
     }
 }
@@ -195,11 +195,11 @@ template <class P, bool DB, bool ALIAS> __global__ void __launch_bounds__(P::T, 
     unsigned code_off, spec_off;
     if constexpr (ALIAS) {
         const int2 sm = __ldg(&a.inv_map[a.d_lo + dl]);   // {spectrum slot, shifted code set}
-        code_off = ((unsigned)sm.y * (unsigned)a.n_prn + (unsigned)row) * (unsigned)N;
-        spec_off = (unsigned)sm.x * (unsigned)n_groups * (unsigned)N;
+        code_off = ((unsigned)sm.y * (unsigned)a.n_prn + (unsigned)row) * (unsigned)P::SPEC_LEN;
+        spec_off = (unsigned)sm.x * (unsigned)n_groups * (unsigned)P::SPEC_LEN;
     } else {
-        code_off = (unsigned)row * (unsigned)N;
-        spec_off = (unsigned)dl * (unsigned)n_groups * (unsigned)N;
+        code_off = (unsigned)row * (unsigned)P::SPEC_LEN;
+        spec_off = (unsigned)dl * (unsigned)n_groups * (unsigned)P::SPEC_LEN;
     }
     const float2* __restrict__ tw = a.tw;
 
@@ -211,7 +211,7 @@ template <class P, bool DB, bool ALIAS> __global__ void __launch_bounds__(P::T, 
 
     for (int g = 0; g < n_groups; g++) {
         float2* __restrict__ line = DB ? smem_line + (g & 1) * P::LINE : smem_line;
-        const float2* __restrict__ sg = a.spec + (spec_off + (unsigned)g * (unsigned)N);
+        const float2* __restrict__ sg = a.spec + (spec_off + (unsigned)g * (unsigned)P::SPEC_LEN);
         const float2* __restrict__ code = a.code_fft + code_off;
 #pragma unroll 1
         for (int it = 0; it < GM::ITERS; it++) {
@@ -220,12 +220,12 @@ template <class P, bool DB, bool ALIAS> __global__ void __launch_bounds__(P::T, 
                 if constexpr (GM::R == 31 && P::STREAM_A > 0) {
                     // radix 31 from global memory: streamed inputs, accumulators in registers (see dft_odd_prime_stream)
                     dft_odd_prime_stream<GM::R, true, P::STREAM_A>(
-                        [&](int q) { return cmul_conj(__ldg(&sg[q * GM::NB + b]), __ldg(&code[q * GM::NB + b])); },
+                        [&](int q) { return cmul_conj(__ldg(&sg[q * P::SPEC_STRIDE + b]), __ldg(&code[q * P::SPEC_STRIDE + b])); },
                         [&](int j, float2 y) { line[P::phys(b * GM::R + j)] = y; });
                 } else {
                     float2 v[GM::R];
 #pragma unroll
-                    for (int q = 0; q < GM::R; q++) v[q] = cmul_conj(__ldg(&sg[q * GM::NB + b]), __ldg(&code[q * GM::NB + b]));
+                    for (int q = 0; q < GM::R; q++) v[q] = cmul_conj(__ldg(&sg[q * P::SPEC_STRIDE + b]), __ldg(&code[q * P::SPEC_STRIDE + b]));
                     dft_emit<GM::R, true>(v, [&](int j, float2 y) { line[P::phys(b * GM::R + j)] = y; });
                 }
             }
@@ -252,7 +252,7 @@ template <class P> __global__ void __launch_bounds__(P::T) code_fft_kernel(const
     using G0 = StageGeo<P, 0>;
     using GM = StageGeo<P, LASTS>;
     const int8_t* c = codes + (size_t)blockIdx.x * P::N;
-    float2* out = code_fft + (size_t)blockIdx.x * P::N;
+    float2* out = code_fft + (size_t)blockIdx.x * P::SPEC_LEN;
 #pragma unroll
     for (int it = 0; it < G0::ITERS; it++) {
         const int i = threadIdx.x + it * P::T;
@@ -279,7 +279,7 @@ template <class P> __global__ void __launch_bounds__(P::T) code_fft_kernel(const
             for (int j = 0; j < GM::R; j++) v[j] = line[P::phys(b * GM::R + j)];
             Dft<GM::R, false>::run(v);
 #pragma unroll
-            for (int q = 0; q < GM::R; q++) out[q * GM::NB + b] = v[q];
+            for (int q = 0; q < GM::R; q++) out[q * P::SPEC_STRIDE + b] = v[q];
         }
     }
 }
@@ -448,6 +448,26 @@ int acq_plan_twiddles(int plan)
     switch (plan) {
 #define X(i, P) \
     case i: return plan_twiddle_count<P>();
+        GB_FOR_EACH_PLAN(X)
+#undef X
+    }
+    return 0;
+}
+int acq_plan_spec_len(int plan)
+{
+    switch (plan) {
+#define X(i, P) \
+    case i: return P::SPEC_LEN;
+        GB_FOR_EACH_PLAN(X)
+#undef X
+    }
+    return 0;
+}
+int acq_plan_spec_stride(int plan)
+{
+    switch (plan) {
+#define X(i, P) \
+    case i: return P::SPEC_STRIDE;
         GB_FOR_EACH_PLAN(X)
 #undef X
     }

@@ -48,6 +48,8 @@ int acq_plan_index(int n);                    // -1 if there is no plan for n
 int acq_plan_sizes(int* sizes, int cap);      // list of planned sizes
 int acq_plan_radices(int plan, int* radices); // returns number of stages
 int acq_plan_threads(int plan);
+int acq_plan_spec_len(int plan);             // complex elements of one stored spectrum (rows padded to 128 B; >= n)
+int acq_plan_spec_stride(int plan);          // row stride of the stored [q][b] layout
 int acq_plan_twiddles(int plan);             // length of the per-stage twiddle buffer ([stage][q-1][i])
 int acq_plan_supports_alias(int plan);       // 1: the shared chain has a Doppler-aliasing inverse kernel for this plan
 int acq_plan_is_pfa(int plan);               // 1: Good-Thomas prime-factor plan (inputs in line order, see PfaPlan)

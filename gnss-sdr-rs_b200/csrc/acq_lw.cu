@@ -39,9 +39,9 @@ __device__ __noinline__ void lw_leftover_warp(const float2* __restrict__ spec, c
     auto compute = [&](int g0) {
         const int g = g0 + slot;
         if (g < n_groups) {
-            const float2* __restrict__ sg = spec + (size_t)g * N;
+            const float2* __restrict__ sg = spec + (size_t)g * PW::SPEC_LEN;
             dft_odd_prime_stream_acc<GM::R, true, 3>(
-                [&](int q) { return cmul_conj(LDSPEC(&sg[q * GM::NB + b]), __ldg(&code[q * GM::NB + b])); }, h);
+                [&](int q) { return cmul_conj(LDSPEC(&sg[q * PW::SPEC_STRIDE + b]), __ldg(&code[q * PW::SPEC_STRIDE + b])); }, h);
         }
     };
     compute(0);
@@ -75,8 +75,8 @@ template <class PW, bool CG> __global__ void __launch_bounds__(PW::T + 32, PW::M
     const int row = a.rows[blockIdx.x % (unsigned)a.n_active];
     const int2 sm = a.inv_map ? __ldg(&a.inv_map[a.d_lo + dl]) : make_int2(dl, 0);   // {spectrum slot, shifted code set}
     // 32-bit element offsets, pointers re-formed per group from the uniform bases (fewer long-lived registers)
-    const unsigned code_off = ((unsigned)sm.y * (unsigned)a.n_prn + (unsigned)row) * (unsigned)N;
-    const unsigned spec_off = (unsigned)sm.x * (unsigned)n_groups * (unsigned)N;
+    const unsigned code_off = ((unsigned)sm.y * (unsigned)a.n_prn + (unsigned)row) * (unsigned)PW::SPEC_LEN;
+    const unsigned spec_off = (unsigned)sm.x * (unsigned)n_groups * (unsigned)PW::SPEC_LEN;
     float2* __restrict__ line = smem_line;
 
     if (threadIdx.x >= TW) {
@@ -92,12 +92,12 @@ template <class PW, bool CG> __global__ void __launch_bounds__(PW::T + 32, PW::M
             for (int j = 0; j < G0::R; j++) acc[it][j] = 0.f;
         const int b = threadIdx.x;
         for (int g = 0; g < n_groups; g++) {
-            const float2* __restrict__ sg = a.spec + (spec_off + (unsigned)g * (unsigned)N);
+            const float2* __restrict__ sg = a.spec + (spec_off + (unsigned)g * (unsigned)PW::SPEC_LEN);
             const float2* __restrict__ code = a.code_fft + code_off;
             {
                 float2 v[GM::R];
 #pragma unroll
-                for (int q = 0; q < GM::R; q++) v[q] = cmul_conj(LDSPEC(&sg[q * GM::NB + b]), __ldg(&code[q * GM::NB + b]));
+                for (int q = 0; q < GM::R; q++) v[q] = cmul_conj(LDSPEC(&sg[q * PW::SPEC_STRIDE + b]), __ldg(&code[q * PW::SPEC_STRIDE + b]));
                 // END of the previous group sits HERE, between this group's global loads and its first store to the
                 // line: a warp that leaves stage C early spends its L2 latency before the barrier instead of after it
                 if (g > 0) named_bar_sync(BAR_END, TALL);

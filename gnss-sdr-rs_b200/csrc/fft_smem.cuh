@@ -496,6 +496,13 @@ template <int N_, int T_, int MINB_, int PAD_, int R0, int R1 = 1, int R2 = 1, i
     static constexpr int len(int s) { return s == 0 ? N : len(s - 1) / radix(s - 1); }
     static constexpr int sub(int s) { return len(s) / radix(s); }
     static constexpr int LINE = PAD ? N + (N >> PAD) + 1 : N;  // complex elements of shared memory
+    // Spectra in global memory (forward spectra, code spectra) are stored scrambled + transposed, [q][b] over the last
+    // radix: row q holds output q of every last-stage butterfly b.  Rows are padded to a multiple of 16 complex (128 B)
+    // so that a warp's 256-byte row segment never straddles a third cache line (4092: rows of 132 -> 144; 8184: 264 ->
+    // 272; every other plan is already aligned and SPEC_LEN == N).
+    static constexpr int SPEC_ROWS = radix(NSTAGE - 1);
+    static constexpr int SPEC_STRIDE = (N / SPEC_ROWS + 15) / 16 * 16;
+    static constexpr int SPEC_LEN = SPEC_ROWS * SPEC_STRIDE;
     // inverse kernel: double-buffer the line if MINB CTAs x 2 lines still fit one SM's shared memory
     static constexpr bool DB = (size_t)MINB_ * 2 * LINE * 8 + (size_t)MINB_ * 1024 <= 227 * 1024;
     static_assert(R0 * R1 * R2 * R3 * R4 * R5 == N, "radices must multiply to N");

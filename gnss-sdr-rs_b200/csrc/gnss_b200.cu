@@ -63,6 +63,7 @@ struct gb_handle {
 
     // acquisition
     int plan = -1, N = 0, n_prn = 0, D = 0, n_coh = 1, spc = 0, mode = GB_ACQ_SHARED;
+    int spec_len = 0;   // complex elements of one stored spectrum (rows padded to 128 B, Plan::SPEC_LEN; == N for cluster plans)
     float2* spec = nullptr;
     size_t spec_cap = 0;
     // cluster plans (code period > one CTA's shared memory)
@@ -770,7 +771,9 @@ extern "C" int gb_acq_configure(gb_handle* h, int fft_size, float fs, int n_prn,
     if (h->row_dev) cudaFree(h->row_dev);
     h->code_fft = nullptr; h->codes_dev = nullptr; h->row_dev = nullptr;
     const size_t total = (size_t)n_prn * fft_size;
-    CK(cudaMalloc((void**)&h->code_fft, total * sizeof(float2)));
+    const int spec_len = cluster ? fft_size : gb::acq_plan_spec_len(plan);
+    CK(cudaMalloc((void**)&h->code_fft, (size_t)n_prn * spec_len * sizeof(float2)));
+    CK(cudaMemsetAsync(h->code_fft, 0, (size_t)n_prn * spec_len * sizeof(float2), h->s_acq));   // row padding
     CK(cudaMalloc((void**)&h->codes_dev, total));
     CK(cudaMalloc((void**)&h->row_dev, sizeof(float) * fft_size));
     CK(cudaMemcpyAsync(h->codes_dev, codes, total, cudaMemcpyHostToDevice, h->s_acq));
@@ -779,6 +782,7 @@ extern "C" int gb_acq_configure(gb_handle* h, int fft_size, float fs, int n_prn,
     CK(cudaStreamSynchronize(h->s_acq));
     h->cluster = cluster;
     h->plan = plan; h->N = fft_size; h->n_prn = n_prn; h->fs = fs; h->tw = fr->tw;
+    h->spec_len = spec_len;
     h->pfa = !cluster && gb::acq_plan_is_pfa(plan) != 0;
     h->npos = h->pfa ? fr->npos : nullptr;
     h->D = 0; h->n_coh = 1;
@@ -858,26 +862,34 @@ static int build_alias_map(gb_handle* h)
     std::vector<int> shifts(shift_of);
     std::sort(shifts.begin(), shifts.end());
     shifts.erase(std::unique(shifts.begin(), shifts.end()), shifts.end());
-    const size_t set = (size_t)h->n_prn * N;
+    const int SL = h->spec_len;
+    const size_t set = (size_t)h->n_prn * SL;
     if (shifts.size() * set * sizeof(float2) > ((size_t)256 << 20)) return GB_OK;
     for (int d = 0; d < D; d++)
         inv[d].y = (int)(std::lower_bound(shifts.begin(), shifts.end(), shift_of[d]) - shifts.begin());
-    // code spectra are stored scrambled + transposed: element t = q * NB + b is line position l = b * R + q (R = last
-    // radix), which holds natural frequency fop[l].  Shifted set s: dst frequency j takes src frequency j - m.
+    // code spectra are stored scrambled + transposed with padded rows: element t = q * STRIDE + b (b < NB) is line position
+    // l = b * R + q (R = last radix), which holds natural frequency fop[l].  Shifted set s: dst frequency j takes src
+    // frequency j - m; padding elements map to themselves.
     const std::vector<int>& fop = h->fft[h->plan].fop_host;
     if ((int)fop.size() != N) return GB_OK;
     int radix[8];
     const int ns = gb::acq_plan_radices(h->plan, radix);
-    const int R = radix[ns - 1], NB = N / R;
+    const int R = radix[ns - 1], NB = N / R, STRIDE = gb::acq_plan_spec_stride(h->plan);
+    if (R * STRIDE != SL) return GB_OK;
     std::vector<int> pof(N);
     for (int l = 0; l < N; l++) pof[fop[l]] = l;
-    std::vector<int> gidx(shifts.size() * (size_t)N);
+    std::vector<int> gidx(shifts.size() * (size_t)SL);
     for (size_t si = 0; si < shifts.size(); si++)
-        for (int t = 0; t < N; t++) {
-            const int l = (t % NB) * R + t / NB;
+        for (int t = 0; t < SL; t++) {
+            const int q = t / STRIDE, b = t % STRIDE;
+            if (b >= NB) {
+                gidx[si * SL + t] = t;
+                continue;
+            }
+            const int l = b * R + q;
             const int js = (int)((((long long)fop[l] - shifts[si]) % N + N) % N);
             const int l2 = pof[js];
-            gidx[si * N + t] = (l2 % R) * NB + l2 / R;
+            gidx[si * SL + t] = (l2 % R) * STRIDE + l2 / R;
         }
     int rc;
     int* gidx_dev = nullptr;
@@ -886,7 +898,7 @@ static int build_alias_map(gb_handle* h)
     if ((rc = ensure(h, &h->inv_map_dev, &h->inv_map_cap, (size_t)D))) return rc;
     CK(cudaMalloc((void**)&gidx_dev, gidx.size() * sizeof(int)));
     cudaError_t e = cudaMemcpyAsync(gidx_dev, gidx.data(), gidx.size() * sizeof(int), cudaMemcpyHostToDevice, h->s_acq);
-    if (e == cudaSuccess) e = gb::acq_launch_shift_codes(h->code_fft, gidx_dev, (int)shifts.size(), h->n_prn, N, h->code_fft_shift, h->s_acq);
+    if (e == cudaSuccess) e = gb::acq_launch_shift_codes(h->code_fft, gidx_dev, (int)shifts.size(), h->n_prn, SL, h->code_fft_shift, h->s_acq);
     if (e == cudaSuccess) e = cudaMemcpyAsync(h->fwd_bins_dev, bases.data(), bases.size() * sizeof(int), cudaMemcpyHostToDevice, h->s_acq);
     if (e == cudaSuccess) e = cudaMemcpyAsync(h->inv_map_dev, inv.data(), (size_t)D * sizeof(int2), cudaMemcpyHostToDevice, h->s_acq);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->s_acq);
@@ -1056,7 +1068,7 @@ static int search_cells(gb_handle* h, const float2* iq_dev, uint64_t start, uint
             CK(cudaEventRecord(h->ev_a1, h->s_acq));
         } else if (h->mode != GB_ACQ_FUSED) {
             // scratch for the forward spectra, processed in Doppler slabs of at most 1 GiB
-            const size_t per_d = (size_t)(K / h->n_coh) * h->N;
+            const size_t per_d = (size_t)(K / h->n_coh) * h->spec_len;
             size_t slab = ((size_t)1 << 27) / per_d;  // complex elements: 2^27 * 8 B = 1 GiB
             if (slab < 1) slab = 1;
             // Doppler aliasing: forward spectra for the base bins only, every bin's inverse pass in one launch
