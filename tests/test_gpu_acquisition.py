@@ -357,6 +357,41 @@ def test_errors_and_edge_cases(gpu, ffi):
     assert e.value.code == ffi.GB_EINVAL
 
 
+def test_headline_kernel_edge_cases(gpu, oracle, ffi):
+    """N = 4092 through the default chain (leftover-warp kernel + Doppler aliasing): an IF offset with negative Dopplers,
+    a sparse PRN mask (masked rows stay zero), all-zero input (peak 0, arg-max 0, metric NaN -> None, Q1) and a grid
+    whose alias classes have different sizes (5 bins: shifts 0, +1, +2 for one class, 0 for the other two)."""
+    from gnss_sdr_rs_b200 import sdr_mock
+    n, fs, K = 4092, 4.092e6, 3
+    f_if = 1250.0
+    sats = [{"prn": 4, "doppler": f_if - 750.0, "code_phase": 4091, "cn0_dbhz": 52.0},
+            {"prn": 32, "doppler": f_if + 1250.0, "code_phase": 0, "cn0_dbhz": 50.0}]
+    x = sdr_mock.baseband(fs, K, sats, seed=77)
+    dopplers = np.array([-750.0, 250.0, 1250.0, -500.0, 100.0], np.float32)   # carriers 500, 1500, 2500 | 750 | 1350
+    eng = _engine(gpu, n, fs)
+    carr = eng.make_doppler_tables(f_if, dopplers)
+    assert eng.forward_bins() == 3
+    eng.set_detector(7.0, 4)
+    mask = (1 << 3) | (1 << 31) | (1 << 10)
+    cells = eng.search_cells(x, K, prn_mask=mask)
+    _, tabs = oracle.doppler_tables(f_if, dopplers, fs, n)
+    for prn in (4, 32, 11):
+        o = oracle.AcqWorker(prn, n, fs).cells(x, tabs, K)
+        np.testing.assert_allclose(cells[prn - 1]["peak"], o["peak"], rtol=REL)
+        np.testing.assert_allclose(cells[prn - 1]["sum8"], o["sum8"], rtol=REL)
+    assert int(cells[3]["argmax"][0]) == 4091 and int(cells[31]["argmax"][2]) == 0
+    untouched = np.ones(32, bool)
+    untouched[[3, 31, 10]] = False
+    assert (cells["peak"][untouched] == 0).all()
+    found = {r["prn"]: r for r in eng.search(x, K, prn_mask=mask) if r}
+    assert set(found) == {4, 32}
+    assert found[4]["carrier_freq"] == np.float32(carr[0]) and found[32]["carrier_freq"] == np.float32(carr[2])
+    z = np.zeros(K * n, np.complex64)
+    cz = eng.search_cells(z, K)
+    assert (cz["peak"] == 0).all() and (cz["argmax"] == 0).all() and (cz["sum8"] == 0).all()
+    assert all(r is None for r in eng.search(z, K))
+
+
 def test_config2_full_size_properties(gpu):
     """BASELINE configs[1] at full size (N = 4092, 32 PRNs, 201 Doppler bins, 10 ms coherent x 20 non-coherent, 200 ms of
     signal) through properties that need no oracle: determinism; exact homogeneity (power-of-two scaling of the input is
