@@ -13,7 +13,9 @@ recording) and the per-PRN results are all-gathered over NCCL each st
 `value`  : device time (CUDA events on the library's acquisition stream) with the IQ already in the
            HBM sample ring; L2 is flushed between timed steps.
 `e2e`    : wall clock through the C-ABI call gb_acq_search() with PINNED HOST IQ: H2D copy, kernel,
-           D2H of the cells and the host decision scan inside the timed region.
+           D2H of the cells and the host decision scan inside the timed region, every step.  The headline
+           figure runs the call from two host threads on two handles of the GPU (steps alternate, so one
+           search's upload overlaps the other's inverse kernel); `serial_*` is one thread, one call at a time.
 `roofline`: the fused kernel is FP32-pipe / shared-memory bound, so the denominator is the
            FP32 FMA rate measured live by gb_bench_fp32_tflops(); the HBM view is reported beside it.
 `cpu_baseline` / --impl reference: the CPU oracle (oracle/, the C restatement of the reference's
@@ -390,13 +392,72 @@ def run_ours(args, rank, world, local_rank):
         if dist is not None:
             gatherer.gather(res_e2e)
     barrier()
-    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    e2e_serial_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+
+    # e2e, pipelined: the same public call from TWO host threads on two handles of this GPU (each with its own streams
+    # and buffers), steps dealt alternately -- the upload of one search overlaps the inverse kernel of the other, as a
+    # receiver that acquires recording after recording would run it.  Every step still copies its 6.5 MB of pinned host
+    # IQ to the device and reads its cells / results back inside the timed region; with N GPUs the per-step gather is
+    # issued by the main thread in step order.
+    e2e_ms, e2e_api = e2e_serial_ms, "gb_acq_search (pinned host IQ -> results)"
+    if not args.no_pipeline:
+        hd2 = ffi.Handle(local_rank)
+        eng2 = acquisition.AcquisitionEngine(hd2, N_FFT, FS, N_PRN)
+        eng2.make_doppler_tables(0.0, DOPPLERS)
+        eng2.set_coherent(N_COH)
+        eng2.set_detector(7.0, 4)
+        eng2.set_mode(ffi.GB_ACQ_FUSED if args.acq_mode == "fused" else ffi.GB_ACQ_SHARED)
+        engines = (eng, eng2)
+
+        def pipelined(n_steps):
+            out = [None] * n_steps
+            done = [threading.Event() for _ in range(n_steps)]
+            errs = []
+
+            def worker(i):
+                try:
+                    for k in range(i, n_steps, 2):
+                        out[k] = engines[i].search(x_pin_ptr, K_MS, prn_mask=prn_mask)
+                        done[k].set()
+                except Exception as e:  # surface in the main thread
+                    errs.append(e)
+                    for ev in done:
+                        ev.set()
+
+            th = [threading.Thread(target=worker, args=(i,)) for i in range(2)]
+            for t_ in th:
+                t_.start()
+            for k in range(n_steps):
+                done[k].wait()
+                if errs:
+                    break
+                if dist is not None:
+                    gatherer.gather(out[k])
+            for t_ in th:
+                t_.join()
+            if errs:
+                raise errs[0]
+            return out
+
+        pipelined(4)
+        barrier()
+        t0 = time.perf_counter()
+        res_pipe = pipelined(args.steps)
+        barrier()
+        e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+        e2e_api = "gb_acq_search (pinned host IQ -> results), two host threads / two handles per GPU, steps alternating"
+        same = all((a is None) == (b is None) and (a is None or (a["code_phase_samples"] == b["code_phase_samples"] and
+                                                                   a["carrier_freq"] == b["carrier_freq"]))
+                   for a, b in zip(res_pipe[-1], res_e2e))
+        if not same:
+            raise RuntimeError("pipelined e2e search disagrees with the serial one")
+        hd2.close()
     clocks = sampler.finish()
 
     if dist is not None:
-        t = torch.tensor([dev_ms, e2e_ms, wall_ms], dtype=torch.float64, device="cuda")
+        t = torch.tensor([dev_ms, e2e_ms, wall_ms, e2e_serial_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, e2e_ms, wall_ms = [float(v) for v in t.cpu()]
+        dev_ms, e2e_ms, wall_ms, e2e_serial_ms = [float(v) for v in t.cpu()]
     cells = N_PRN * len(DOPPLERS) * N_FFT
     ms_per_step = dev_ms / args.steps
     units = 1 if by_prn else world   # recordings searched per step by the whole job
@@ -454,7 +515,9 @@ def run_ours(args, rank, world, local_rank):
                 "x_realtime": units * (K_MS * 1e-3) / (ms_per_step * 1e-3),
                 "e2e": {"value": e2e_value, "unit": "cells/s", "ms_per_step": e2e_ms,
                         "h2d_bytes_per_step": int(x.nbytes), "d2h_bytes_per_step": int(N_PRN * len(DOPPLERS) * 16),
-                        "api": "gb_acq_search (pinned host IQ -> results)"},
+                        "api": e2e_api, "serial_ms_per_step": e2e_serial_ms,
+                        "serial_value": units * cells / (e2e_serial_ms * 1e-3),
+                        "serial_api": "one host thread, one gb_acq_search call at a time"},
                 # per step: line-order permutation of the IQ blocks (prime-factor plan) + forward + inverse kernels
                 "gpu_launches": args.steps * (2 if args.acq_mode == "fused" else 3),
                 "roofline": {"bound": "fp32", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
@@ -520,6 +583,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--acq-mode", default="shared", choices=["shared", "fused"])
+    ap.add_argument("--no-pipeline", action="store_true", help="e2e from one host thread only")
     ap.add_argument("--shard", default="recording", choices=["recording", "prn"],
                     help="N>1: one recording per GPU (weak scaling, default) or the PRNs of ONE recording dealt to the GPUs (strong)")
     args = ap.parse_args()

@@ -483,7 +483,7 @@ extern "C" int gb_destroy(gb_handle* h)
     if (!h) return GB_EINVAL;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
-    void* dev_ptrs[] = {h->fwd_bins_dev, h->inv_map_dev, h->code_fft_shift, h->fe_idx, h->fe_lut, h->fe_state, h->fe_stage, h->otw, h->acc_rows, h->spec, h->ring, h->i8_stage, h->tw, h->code_fft, h->tables, h->rot, h->chunk, h->codes_dev, h->cells_dev,
+    void* dev_ptrs[] = {h->fwd_bins_dev, h->inv_map_dev, h->code_fft_shift, h->fe_idx, h->fe_lut, h->fe_state, h->fe_stage, h->otw, h->acc_rows, h->spec, h->ring, h->i8_stage, /* h->tw aliases fft[plan].tw, freed below */ h->code_fft, h->tables, h->rot, h->chunk, h->codes_dev, h->cells_dev,
                         h->rows_dev, h->row_dev, h->ca_table_dev, h->ch_dev, h->corr_dev, h->ran_dev, h->lost_dev,
                         h->hist_dev, h->trk_data, h->offs_dev, h->fine_x, h->fine_y, h->fine_codes, h->fine_u64, h->fine_mean,
                         h->fine_mag, h->tables_perm, h->iq_perm};
@@ -508,6 +508,7 @@ extern "C" int gb_destroy(gb_handle* h)
     cudaEvent_t evs[] = {h->ev_copy, h->ev_a0, h->ev_a1, h->ev_t0, h->ev_t1};
     for (cudaEvent_t e : evs)
         if (e) cudaEventDestroy(e);
+    cudaGetLastError();   // a failed free must not surface as the "last error" of another handle's next launch
     delete h;
     return GB_OK;
 }

@@ -357,6 +357,38 @@ def test_errors_and_edge_cases(gpu, ffi):
     assert e.value.code == ffi.GB_EINVAL
 
 
+def test_two_handles_on_one_device(ffi):
+    """Two handles (own streams and buffers) searched from two host threads give the single-handle results, and
+    destroying one leaves no stale CUDA error behind for the other's next launch (gb_destroy used to free the plan's
+    twiddles twice)."""
+    import threading
+    from gnss_sdr_rs_b200 import acquisition, sdr_mock
+    n, fs, K = 4092, 4.092e6, 4
+    x = sdr_mock.baseband(fs, K, _sats(n, 11), seed=3)
+    hs = [ffi.Handle(0), ffi.Handle(0)]
+    engs = []
+    for h in hs:
+        e = acquisition.AcquisitionEngine(h, n, fs)
+        e.make_doppler_tables(0.0, np.arange(-2000, 2001, 250, dtype=np.float32))
+        engs.append(e)
+    ref = engs[0].search_cells(x, K).copy()
+    out = [None, None]
+
+    def work(i):
+        for _ in range(5):
+            out[i] = engs[i].search_cells(x, K).copy()
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert out[0].tobytes() == ref.tobytes() and out[1].tobytes() == ref.tobytes()
+    hs[1].close()
+    assert engs[0].search_cells(x, K).tobytes() == ref.tobytes()
+    hs[0].close()
+
+
 def test_headline_kernel_edge_cases(gpu, oracle, ffi):
     """N = 4092 through the default chain (leftover-warp kernel + Doppler aliasing): an IF offset with negative Dopplers,
     a sparse PRN mask (masked rows stay zero), all-zero input (peak 0, arg-max 0, metric NaN -> None, Q1) and a grid
