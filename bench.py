@@ -43,9 +43,9 @@ SATS = [(3, 1230.0, 100, 45.0), (7, -2210.0, 2000, 40.0), (11, 3370.0, 3100, 42.
         (19, 4120.0, 1500, 38.0), (22, -3900.0, 4000, 36.0), (28, 60.0, 2500, 47.0), (31, 2780.0, 300, 35.0)]
 
 
-# filled in from the ncu capture of the same command (profiles/round1_v8_final.txt)
+# filled in from the ncu capture of the same command (profiles/round1_v9_final.txt)
 KERNEL_SHARES_NOTE = ("acq_inverse_lw_kernel ~98% / acq_forward_kernel (20 of 201 bins, Doppler aliasing) ~1% / permute < 1% "
-                      "of the chain (profiles/round1_v8_final.txt)")
+                      "of the chain (profiles/round1_v9_final.txt)")
 
 
 def make_recording(seed):
