@@ -421,3 +421,25 @@ def test_two_peak_window_matches_legacy_slices(oracle, cp):
     assert first.value == cp
     assert row[second.value] == np.float32(p2)
     assert abs(ratio - np.sqrt(p1) / np.sqrt(p2)) < 1e-5
+
+
+def test_doppler_aliasing_identity_f64():
+    """The algebra behind gb_acq_set_doppler_aliasing, checked in NumPy f64 on the reference's own
+    definitions (doppler_shift.rs:11-21 tables, do_acquisition.rs:176-192 chain): for carr_d = carr_b + m fs/N the
+    correlation power of bin d equals the power obtained from bin b's spectrum paired with the code spectrum shifted by m,
+    |IFFT(X_d conj C)|^2 == |IFFT(X_b conj C_m)|^2 with C_m[j] = C[j - m], for positive, negative and wrapping m."""
+    rng = np.random.default_rng(5)
+    n, fs = 4092, 4.092e6
+    x = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    code = np.sign(rng.standard_normal(n))
+    C = np.fft.fft(code)
+    i = np.arange(n)
+    carr_b = 150.0
+    Xb = np.fft.fft(x * np.exp(-2j * np.pi * carr_b * i / fs))
+    for m in (1, -1, 5, -4, 37):
+        carr_d = carr_b + m * fs / n
+        Xd = np.fft.fft(x * np.exp(-2j * np.pi * carr_d * i / fs))
+        np.testing.assert_allclose(Xd, np.roll(Xb, -m), atol=1e-7 * np.abs(Xb).max())      # X_d[k] = X_b[k + m]
+        direct = np.abs(np.fft.ifft(Xd * np.conj(C))) ** 2
+        aliased = np.abs(np.fft.ifft(Xb * np.conj(np.roll(C, m)))) ** 2                     # C_m[j] = C[j - m]
+        np.testing.assert_allclose(aliased, direct, rtol=1e-9, atol=1e-12 * direct.max())
