@@ -96,6 +96,13 @@ __device__ __forceinline__ float lds_f32(unsigned addr)
     return v;
 }
 
+__device__ __forceinline__ float4 lds_f32x4(unsigned addr)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+
 __device__ __forceinline__ float block_sum(float v, float* red)
 {
 #pragma unroll
@@ -105,11 +112,14 @@ __device__ __forceinline__ float block_sum(float v, float* red)
 
 template <int MODE, int TRK_T> __global__ void __launch_bounds__(TRK_T) trk_kernel(const TrkArgs a)
 {
-    extern __shared__ unsigned char smem_raw[];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     float* row = reinterpret_cast<float*>(smem_raw);          // 1024 floats: this channel's C/A row
     float* red = row + 1024;                                  // 8 + 6 x (TRK_T/32) partials (128 floats reserved)
     __shared__ gb_trk_channel st;
     __shared__ int s_go;
+    // FAST: {chip k-1 (chip 0 for k = 0, the saturating cast of Q7), chip k, chip k+1 (chip 0 for k = 1022), 0} per chip:
+    // ONE 16-byte look-up per sample delivers the prompt chip and both candidates of the early and the late replica
+    float4* row4 = reinterpret_cast<float4*>(red + 128);
     float2* rot = reinterpret_cast<float2*>(red + 128);       // ORDERED: n_max rotated samples
     int8_t* chips = reinterpret_cast<int8_t*>(rot + (MODE == GB_TRK_ORDERED ? a.n_max : 0));  // 3 x n_max
 
@@ -138,6 +148,11 @@ template <int MODE, int TRK_T> __global__ void __launch_bounds__(TRK_T) trk_kern
     };
     if (threadIdx.x == 0) s_go = may_go();
     __syncthreads();
+    if (MODE == GB_TRK_FAST) {
+        for (int i = threadIdx.x; i < 1023; i += TRK_T)
+            row4[i] = make_float4(row[i == 0 ? 0 : i - 1], row[i], row[i == 1022 ? 0 : i + 1], 0.f);
+        __syncthreads();
+    }
 
     for (int e = 0; e < a.n_epochs; e++) {
         if (!s_go) break;
@@ -165,7 +180,7 @@ template <int MODE, int TRK_T> __global__ void __launch_bounds__(TRK_T) trk_kern
             // range checks, so the loop is branch-free.
             // (the batched loop evaluates indices up to n - 1 + (U - 1) * TRK_T; samples past n are zeros)
             constexpr int U = TRK_T >= 512 ? 4 : 8;
-            const float i_end = (float)(n + (U - 1) * TRK_T);
+            const float i_end = (float)(((n + U * TRK_T - 1) / (U * TRK_T)) * (U * TRK_T));   // first index past the last batch
             const bool sane = code_phase >= 0.f && code_phase < 1023.f && code_step >= 0.f &&
                               code_step * i_end < 2040.f && fabsf(carrier_phase) + fabsf(w) * (i_end * rcp_fs) < 1.0e6f;
             auto body = [&](const float2 x, const float fi) {
@@ -205,9 +220,11 @@ template <int MODE, int TRK_T> __global__ void __launch_bounds__(TRK_T) trk_kern
             const float f_turn = st.carrier_freq * rcp_fs;
             const float cp_turn = carrier_phase * inv_2pi;
             const bool turns_ok = fabsf(f_turn) * i_end < 16.f && fabsf(cp_turn) < 2.f;   // baseband / low-IF carriers
-            // C/A row look-ups straight from the raw bits of the round-down add: index = bits - 0x4B000000, address =
-            // row + 4 * index = 4 * bits + row_bias (mod 2^32), one LEA per look-up
-            const unsigned row_bias = (unsigned)__cvta_generic_to_shared(row) - 4u * 0x4B000000u;
+            // C/A look-ups straight from the raw bits of the round-down add: index = bits - 0x4B000000, address =
+            // row4 + 16 * index = 16 * bits + row4_bias (mod 2^32), one LEA per look-up
+            const unsigned row4_bias = (unsigned)__cvta_generic_to_shared(row4) - 16u * 0x4B000000u;
+            // one exact conditional subtraction brings the chip argument into [0, 1023) when it stays below 2 * 1023
+            const bool single_wrap = code_phase + code_step * i_end < 2046.f;
             if (contiguous && sane) {
                 // batches of 8 samples per thread, software-pipelined by hand: all loads, then all carrier
                 // phases / SFU sin-cos, then the code look-ups and the 48 FMAs -- so the load and SFU latencies
@@ -257,14 +274,16 @@ template <int MODE, int TRK_T> __global__ void __launch_bounds__(TRK_T) trk_kern
                         const float im = fmaf(x[u].y, cs[u], -(x[u].x * sn[u]));
                         float tc = code_phase + (fi * code_step);
                         tc = tc >= 1023.f ? tc - 1023.f : tc;
-                        tc = tc >= 1023.f ? tc - 1023.f : tc;
-                        const int bp = __float_as_int(__fadd_rd(tc, 8388608.0f));             // tc in [0, 1023)
-                        int be = __float_as_int(__fadd_rd(tc + 0.5f, 8388608.0f));
-                        be = be >= 0x4B000000 + 1023 ? be - 1023 : be;                        // (chip + 0.5).floor() % 1023
-                        const int bl = max(__float_as_int(__fadd_rd(tc - 0.5f, 8388608.0f)), 0x4B000000);   // Q7
-                        const float pc = lds_f32(4u * (unsigned)bp + row_bias);
-                        const float ec = lds_f32(4u * (unsigned)be + row_bias);
-                        const float lc = lds_f32(4u * (unsigned)bl + row_bias);
+                        if (!single_wrap) tc = tc >= 1023.f ? tc - 1023.f : tc;
+                        // floor(tc) sits in the mantissa of the round-down add; the early / late chips are
+                        // floor(tc + 0.5) % 1023 in {k, k+1} and max(floor(tc - 0.5), 0) in {k-1, k} (Q7), decided on the
+                        // reference's own f32 sums tc + 0.5 and tc - 0.5
+                        const float pf = __fadd_rd(tc, 8388608.0f);
+                        const float4 q = lds_f32x4(16u * (unsigned)__float_as_int(pf) + row4_bias);
+                        const float fl = pf - 8388608.0f;                     // exact
+                        const float pc = q.y;
+                        const float ec = (tc + 0.5f) >= (fl + 1.0f) ? q.z : q.y;
+                        const float lc = (tc - 0.5f) >= fl ? q.y : q.x;
                         const pk64 z = pk2(re, im);
                         accp = fma2s(z, pc, accp);
                         acce = fma2s(z, ec, acce);
@@ -427,7 +446,7 @@ template <int MODE, int TRK_T> __global__ void __launch_bounds__(TRK_T) trk_kern
 
 template <int T> static cudaError_t launch_t(const TrkArgs& a, int mode, cudaStream_t st)
 {
-    size_t smem = (1024 + 128) * sizeof(float);
+    size_t smem = (1024 + 128) * sizeof(float) + (mode == GB_TRK_ORDERED ? 0 : 1024 * sizeof(float4));
     if (mode == GB_TRK_ORDERED) {
         smem += (size_t)a.n_max * (sizeof(float2) + 3) + 16;
         if (smem > 48 * 1024) {
