@@ -70,6 +70,29 @@ def test_get_ca_chip_quirks_q6_q7(gpu, oracle):
     assert scale > 0.5 * np.abs(x[:n]).sum()  # it really locked onto PRN 6's code
 
 
+@pytest.mark.parametrize("code_phase", [0.0, 0.25, 0.49999997, 0.5, 0.50000006, 1.0, 511.99997, 1022.0, 1022.4999, 1022.5, 1022.9999])
+@pytest.mark.parametrize("code_rate,n", [(1.023e6, 2048), (1.0235e6, 2047), (1.0e3, 2048)])
+def test_early_prompt_late_chip_selection_is_exact(gpu, oracle, code_phase, code_rate, n):
+    """FAST mode reads ONE {chip k-1, chip k, chip k+1} entry per sample and picks the early / late replicas with two
+    compares; the picks must be the reference's floor(chip +- 0.5) ones (get_ca_chip, do_tracking.rs:255-263, incl. the
+    1023 -> 0 wrap of the early replica and the Q7 saturation of the late one).  With x = 1 and no carrier the six sums
+    are sums of +-1 chips -- exact in f32 whatever the order -- so FAST, ORDERED and the oracle must agree exactly, at
+    code phases on and next to every decision boundary, for the nominal rate, a 2047-sample epoch at a faster code (the
+    ragged last batch, two wraps) and a crawl that advances one chip per epoch."""
+    from gnss_sdr_rs_b200 import tracking
+    fs = 2.048e6
+    for mode in (0, 1):
+        ch, och = _pair(oracle, fs, 9, 0.0, np.float32(0.0), 0, code_row=8)
+        ch[0].code_rate = och.code_rate = np.float32(code_rate)
+        ch[0].code_phase = och.code_phase = np.float32(code_phase)
+        ch[0].num_samples_per_code = och.num_samples_per_code = n
+        seg = np.ones(n, np.complex64)
+        ref = oracle.trk_early_late(och, seg)
+        got = _six(tracking.TrackingEngine(gpu).correlate(ch, [seg], mode=mode)[0])
+        assert (got == ref).all(), (mode, got, ref)
+        assert ch[0].code_phase == och.code_phase
+
+
 def test_do_work_epochs_closed_loop_ordered(gpu, oracle):
     """TrackingChannel::update via the ring, one launch per epoch, ORDERED mode, noise-free signal."""
     from gnss_sdr_rs_b200 import ring, sdr_mock, tracking
