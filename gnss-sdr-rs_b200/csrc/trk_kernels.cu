@@ -146,7 +146,39 @@ template <int MODE, int TRK_T> __global__ void __launch_bounds__(TRK_T) trk_kern
         if (n == 0 || n > (unsigned long long)a.n_max) go = 0;
         return go;
     };
-    if (threadIdx.x == 0) s_go = may_go();
+    // Per-epoch scalars every thread needs (carrier step, chip step with its IEEE division, window start, batch bound):
+    // computed ONCE per epoch by the thread that owns the fields they derive from -- the carrier half (thread 0) and the
+    // code half (thread 32) of the epoch end, for the NEXT epoch -- and broadcast through shared memory.  Evaluated by
+    // every thread they were ~100 of the ~900 instructions a thread issues per epoch at 16 samples per thread.
+    __shared__ struct {
+        float w, f_turn, cp_turn, carrier_phase;   // carrier half
+        float code_step, code_phase, i_end;        // code half
+        int n;
+        unsigned long long start;
+    } ep;
+    constexpr int U_BATCH = TRK_T >= 512 ? 4 : 8;
+    const float fs = st.fs;                        // never changes during a run
+    const float rcp_fs = 1.0f / fs;
+    auto prep_carrier = [&]() {
+        ep.carrier_phase = st.carrier_phase;
+        ep.w = kTwoPi * st.carrier_freq;                          // 2.0 * PI * carrier_freq
+        ep.f_turn = st.carrier_freq * rcp_fs;
+        ep.cp_turn = st.carrier_phase * 0.15915494309189535f;
+    };
+    auto prep_code = [&]() {
+        const int n = (int)st.num_samples_per_code;
+        ep.n = n;
+        ep.start = a.offsets ? a.offsets[c] : st.next_sample_index;
+        ep.code_phase = st.code_phase;
+        ep.code_step = st.code_rate / fs;                         // (code_rate / fs)
+        // the batched loop evaluates indices up to the end of the last batch; samples past n are zeros
+        ep.i_end = (float)(((n + U_BATCH * TRK_T - 1) / (U_BATCH * TRK_T)) * (U_BATCH * TRK_T));
+    };
+    if (threadIdx.x == 0) {
+        s_go = may_go();
+        prep_carrier();
+    }
+    if (threadIdx.x == 32) prep_code();
     __syncthreads();
     if (MODE == GB_TRK_FAST) {
         for (int i = threadIdx.x; i < 1023; i += TRK_T)
@@ -158,12 +190,12 @@ template <int MODE, int TRK_T> __global__ void __launch_bounds__(TRK_T) trk_kern
         if (!s_go) break;
 
         const unsigned lc_old = st.lost_counter;   // read before the carrier half rewrites it
-        const int n = (int)st.num_samples_per_code;
-        const unsigned long long start = a.offsets ? a.offsets[c] : st.next_sample_index;
-        const float carrier_phase = st.carrier_phase, fs = st.fs;
-        const float w = kTwoPi * st.carrier_freq;                 // 2.0 * PI * carrier_freq
-        const float code_phase = st.code_phase;
-        const float code_step = st.code_rate / fs;                 // (code_rate / fs)
+        const int n = ep.n;
+        const unsigned long long start = ep.start;
+        const float carrier_phase = ep.carrier_phase;
+        const float w = ep.w;
+        const float code_phase = ep.code_phase;
+        const float code_step = ep.code_step;
 
         float ip = 0.f, qp = 0.f, ie = 0.f, qe = 0.f, il = 0.f, ql = 0.f;
         if (MODE == GB_TRK_FAST) {
@@ -171,7 +203,6 @@ template <int MODE, int TRK_T> __global__ void __launch_bounds__(TRK_T) trk_kern
             // (same roundings; the division is a reciprocal + one FMA-residual correction, correctly rounded
             // in all but vanishingly rare halfway cases); sin/cos use a 2-term Cody-Waite reduction to
             // [-pi, pi] and the SFU (abs error < 1e-6); the six sums are per-thread partials + tree reduction.
-            const float rcp_fs = 1.0f / fs;
             const float inv_2pi = 0.15915494309189535f;
             const float c1 = 6.28318548202514648f;        // fl(2 pi)
             const float c2 = -1.74845553146951715e-7f;    // 2 pi - fl(2 pi)
@@ -179,8 +210,8 @@ template <int MODE, int TRK_T> __global__ void __launch_bounds__(TRK_T) trk_kern
             // lies in [0, 3*1023): then `% 1023` is at most two exact subtractions and the E/P/L indices need no
             // range checks, so the loop is branch-free.
             // (the batched loop evaluates indices up to n - 1 + (U - 1) * TRK_T; samples past n are zeros)
-            constexpr int U = TRK_T >= 512 ? 4 : 8;
-            const float i_end = (float)(((n + U * TRK_T - 1) / (U * TRK_T)) * (U * TRK_T));   // first index past the last batch
+            constexpr int U = U_BATCH;
+            const float i_end = ep.i_end;                                  // first index past the last batch
             const bool sane = code_phase >= 0.f && code_phase < 1023.f && code_step >= 0.f &&
                               code_step * i_end < 2040.f && fabsf(carrier_phase) + fabsf(w) * (i_end * rcp_fs) < 1.0e6f;
             auto body = [&](const float2 x, const float fi) {
@@ -217,8 +248,8 @@ template <int MODE, int TRK_T> __global__ void __launch_bounds__(TRK_T) trk_kern
             // cycles per sample and start phase in turns: phase_i / 2 pi = cp_turn + i * f_turn (one FMA per sample).  Used
             // while the epoch spans < 16 turns: the argument error is then < 1e-6 turn, two orders below the FAST-mode
             // tolerance.
-            const float f_turn = st.carrier_freq * rcp_fs;
-            const float cp_turn = carrier_phase * inv_2pi;
+            const float f_turn = ep.f_turn;
+            const float cp_turn = ep.cp_turn;
             const bool turns_ok = fabsf(f_turn) * i_end < 16.f && fabsf(cp_turn) < 2.f;   // baseband / low-IF carriers
             // C/A look-ups straight from the raw bits of the round-down add: index = bits - 0x4B000000, address =
             // row4 + 16 * index = 16 * bits + row4_bias (mod 2^32), one LEA per look-up
@@ -399,6 +430,7 @@ template <int MODE, int TRK_T> __global__ void __launch_bounds__(TRK_T) trk_kern
                     }
                 }
                 ran += 1;
+                prep_carrier();   // next epoch's carrier scalars
             } else {
                 // :265-267
                 const float cdp = st.code_phase + code_step * nf;
@@ -427,6 +459,7 @@ template <int MODE, int TRK_T> __global__ void __launch_bounds__(TRK_T) trk_kern
                     }
                 }
                 st.epochs_done += 1;
+                prep_code();      // next epoch's code scalars and sample window
                 s_go = (e + 1 < a.n_epochs) ? may_go() : 0;
             }
         }
