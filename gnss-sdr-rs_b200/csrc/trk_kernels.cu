@@ -363,13 +363,21 @@ template <int MODE, int TRK_T> __global__ void __launch_bounds__(TRK_T) trk_kern
             }
             __syncthreads();
         } else {
-            ip = block_sum(ip, red); qp = block_sum(qp, red); ie = block_sum(ie, red);
-            qe = block_sum(qe, red); il = block_sum(il, red); ql = block_sum(ql, red);
+            // Six sums per warp with 8 shuffles instead of 30: every exchange halves the number of values a lane still
+            // carries (xor 16: {ip, qp, ie} | {qe, il, ql}; xor 8: two | one of those three; xor 4: one of two), the last two
+            // exchanges finish the single value left.  Lane bits 4..2 then say which sum a lane holds.
             const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-            if (lane == 0) {
-                red[8 + warp * 6 + 0] = ip; red[8 + warp * 6 + 1] = qp; red[8 + warp * 6 + 2] = ie;
-                red[8 + warp * 6 + 3] = qe; red[8 + warp * 6 + 4] = il; red[8 + warp * 6 + 5] = ql;
-            }
+            const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+            float k0 = (h16 ? qe : ip) + __shfl_xor_sync(0xffffffffu, h16 ? ip : qe, 16);
+            float k1 = (h16 ? il : qp) + __shfl_xor_sync(0xffffffffu, h16 ? qp : il, 16);
+            float k2 = (h16 ? ql : ie) + __shfl_xor_sync(0xffffffffu, h16 ? ie : ql, 16);
+            float m0 = (h8 ? k2 : k0) + __shfl_xor_sync(0xffffffffu, h8 ? k0 : k2, 8);
+            float m1 = (h8 ? 0.f : k1) + __shfl_xor_sync(0xffffffffu, h8 ? k1 : 0.f, 8);
+            float r = (h4 ? m1 : m0) + __shfl_xor_sync(0xffffffffu, h4 ? m0 : m1, 4);
+            r += __shfl_xor_sync(0xffffffffu, r, 2);
+            r += __shfl_xor_sync(0xffffffffu, r, 1);
+            // lanes 0, 4, 8 (bits 4..2 = 000, 001, 010) hold ip, qp, ie; lanes 16, 20, 24 hold qe, il, ql
+            if ((lane & 3) == 0 && !(h8 && h4)) red[8 + warp * 6 + (h16 ? 3 : 0) + (h8 ? 2 : (h4 ? 1 : 0))] = r;
             __syncthreads();
         }
 
