@@ -268,10 +268,15 @@ template <int MODE, int TRK_T> __global__ void __launch_bounds__(TRK_T) trk_kern
                     float2 x[U];
                     float cs[U], sn[U];
                     const float fbase = (float)base;
+                    if (base + (U - 1) * TRK_T < n) {   // a full batch (all but the epoch's last one): no per-sample bound check
 #pragma unroll
-                    for (int u = 0; u < U; u++) {
-                        const int i = base + u * TRK_T;
-                        x[u] = i < n ? __ldg(px + i) : make_float2(0.f, 0.f);
+                        for (int u = 0; u < U; u++) x[u] = __ldg(px + base + u * TRK_T);
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < U; u++) {
+                            const int i = base + u * TRK_T;
+                            x[u] = i < n ? __ldg(px + i) : make_float2(0.f, 0.f);
+                        }
                     }
                     if (turns_ok) {
 #pragma unroll
