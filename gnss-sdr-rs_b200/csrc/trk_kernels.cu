@@ -89,24 +89,10 @@ __device__ __forceinline__ pk64 fma2s(pk64 a, float s, pk64 c)
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(pk2(s, s)), "l"(c));
     return r;
 }
-__device__ __forceinline__ float lds_f32(unsigned addr)
-{
-    float v;
-    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
-    return v;
-}
-
 __device__ __forceinline__ float4 lds_f32x4(unsigned addr)
 {
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-    return v;
-}
-
-__device__ __forceinline__ float block_sum(float v, float* red)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
 
