@@ -138,6 +138,7 @@ template <int MODE, int TRK_T> __global__ void __launch_bounds__(TRK_T) trk_kern
     // every thread they were ~100 of the ~900 instructions a thread issues per epoch at 16 samples per thread.
     __shared__ struct {
         float w, f_turn, cp_turn, carrier_phase;   // carrier half
+        float wc, ws;                              // cos / sin of the carrier advance over TRK_T samples
         float code_step, code_phase, i_end;        // code half
         int n;
         unsigned long long start;
@@ -150,6 +151,8 @@ template <int MODE, int TRK_T> __global__ void __launch_bounds__(TRK_T) trk_kern
         ep.w = kTwoPi * st.carrier_freq;                          // 2.0 * PI * carrier_freq
         ep.f_turn = st.carrier_freq * rcp_fs;
         ep.cp_turn = st.carrier_phase * 0.15915494309189535f;
+        const float dt = ep.f_turn * (float)TRK_T;                // turns between a thread's consecutive samples
+        sincosf((dt - rintf(dt)) * 6.28318548202514648f, &ep.ws, &ep.wc);
     };
     auto prep_code = [&]() {
         const int n = (int)st.num_samples_per_code;
@@ -236,6 +239,7 @@ template <int MODE, int TRK_T> __global__ void __launch_bounds__(TRK_T) trk_kern
             // tolerance.
             const float f_turn = ep.f_turn;
             const float cp_turn = ep.cp_turn;
+            const float wc = ep.wc, ws = ep.ws;
             const bool turns_ok = fabsf(f_turn) * i_end < 16.f && fabsf(cp_turn) < 2.f;   // baseband / low-IF carriers
             // C/A look-ups straight from the raw bits of the round-down add: index = bits - 0x4B000000, address =
             // row4 + 16 * index = 16 * bits + row4_bias (mod 2^32), one LEA per look-up
@@ -265,13 +269,30 @@ template <int MODE, int TRK_T> __global__ void __launch_bounds__(TRK_T) trk_kern
                         }
                     }
                     if (turns_ok) {
+                        // the batch's first sample through the SFU; in the throughput regime the other seven by rotating it with
+                        // the constant advance over TRK_T samples (4 instructions instead of 8; the 7-step recurrence adds
+                        // < 1e-6 rad)
+                        const float ut = fmaf(fbase, f_turn, cp_turn);
+                        const float r = (ut - rint_small(ut)) * c1;        // [-pi, pi]
+                        cs[0] = __cosf(r);
+                        sn[0] = __sinf(r);
+                        if constexpr (TRK_T <= 128) {
+                            // throughput regime (many channels per SM, issue-bound): fewer instructions win
 #pragma unroll
-                        for (int u = 0; u < U; u++) {
-                            const float fi = fbase + (float)(u * TRK_T);   // exact: integers below 2^24
-                            const float ut = fmaf(fi, f_turn, cp_turn);
-                            const float r = (ut - rint_small(ut)) * c1;    // [-pi, pi]
-                            cs[u] = __cosf(r);
-                            sn[u] = __sinf(r);
+                            for (int u = 1; u < U; u++) {
+                                cs[u] = fmaf(cs[u - 1], wc, -(sn[u - 1] * ws));
+                                sn[u] = fmaf(sn[u - 1], wc, cs[u - 1] * ws);
+                            }
+                        } else {
+                            // latency regime (one channel per SM): eight independent SFU evaluations beat a 7-step chain
+#pragma unroll
+                            for (int u = 1; u < U; u++) {
+                                const float fi = fbase + (float)(u * TRK_T);   // exact: integers below 2^24
+                                const float utu = fmaf(fi, f_turn, cp_turn);
+                                const float ru = (utu - rint_small(utu)) * c1;
+                                cs[u] = __cosf(ru);
+                                sn[u] = __sinf(ru);
+                            }
                         }
                     } else {
                         // IF carriers: thousands of turns per epoch -- follow the reference's f32 roundings of the phase
