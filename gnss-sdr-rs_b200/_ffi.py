@@ -60,6 +60,8 @@ SIGNATURES = {
     "gb_last_cuda_error": (C.c_char_p, [_vp]),
     "gb_version": (_i32, []),
     "gb_device_count": (_i32, []),
+    "gb_tuning_set": (_i32, [C.c_char_p, _i32]),
+    "gb_tuning_get": (_i32, [C.c_char_p, _i32]),
     "gb_create": (_i32, [_vp, _vp]),
     "gb_destroy": (_i32, [_vp]),
     "gb_synchronize": (_i32, [_vp]),
@@ -130,6 +132,11 @@ def lib():
             fn.argtypes = args
         _LIB = L
     return _LIB
+
+
+def tuning_set(key, value):
+    """Explicit A/B switch of the kernels (gb_tuning_set); the library reads no environment variables."""
+    check(lib().gb_tuning_set(key.encode(), int(value)), "gb_tuning_set")
 
 
 def _strerror(code):

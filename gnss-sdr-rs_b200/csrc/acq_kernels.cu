@@ -9,16 +9,21 @@
 // The only HBM/L2 reads are the IQ chunk, the wipe-off table and the code spectrum.
 #include "acq_common.cuh"
 
-#include <stdlib.h>
-
 #include <type_traits>
 
 namespace gb {
 
-#define GB_FOR_EACH_PLAN(X) X(0, P1024) X(1, P2048) X(2, P4092) X(3, P4096) X(4, P8184) X(5, P16368) X(6, P20000) \
+#define GB_FOR_EACH_PRODUCTION_PLAN(X) X(0, P1024) X(1, P2048) X(2, P4092) X(3, P4096) X(4, P8184) X(5, P16368) X(6, P20000)
+#ifdef GB_TUNING
+// A/B scaffolding (build.sh -DGB_TUNING; selected with gb_tuning_set("acq_variant", 1..8)): not part of the shipped library
+#define GB_FOR_EACH_PLAN(X) GB_FOR_EACH_PRODUCTION_PLAN(X) \
     X(7, P4092v1) X(8, P4092v2) X(9, P4092v3) X(10, P4092v4) X(11, P16368v1) X(12, P16368v2) \
     X(13, P4092v5) X(14, P4092v6) X(15, P4092v7) X(16, P4092v8)
 static const int kPlanSizes[] = {1024, 2048, 4092, 4096, 8184, 16368, 20000, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1};
+#else
+#define GB_FOR_EACH_PLAN(X) GB_FOR_EACH_PRODUCTION_PLAN(X)
+static const int kPlanSizes[] = {1024, 2048, 4092, 4096, 8184, 16368, 20000};
+#endif
 static const int kNumPlans = sizeof(kPlanSizes) / sizeof(int);
 // the default plan of each size (indices 0..6); the rest are tuning variants
 template <class P> constexpr bool kProductionPlan =
@@ -392,15 +397,12 @@ cudaError_t acq_launch_permute(const float2* src, unsigned long long start, unsi
 // ------------------------------------------------------------------ host-side dispatch
 int acq_plan_index(int n)
 {
-    if (n == 4092) {
-        const char* v = getenv("GB_ACQ_VARIANT");
-        if (v && v[0] >= '1' && v[0] <= '4' && !v[1]) return 6 + (v[0] - '0');
-        if (v && v[0] >= '5' && v[0] <= '8' && !v[1]) return 8 + (v[0] - '0');
-    }
-    if (n == 16368) {
-        const char* v = getenv("GB_ACQ_VARIANT");
-        if (v && v[0] >= '1' && v[0] <= '2' && !v[1]) return 10 + (v[0] - '0');
-    }
+#ifdef GB_TUNING
+    const int v = tuning("acq_variant", 0);
+    if (n == 4092 && v >= 1 && v <= 4) return 6 + v;
+    if (n == 4092 && v >= 5 && v <= 8) return 8 + v;
+    if (n == 16368 && v >= 1 && v <= 2) return 10 + v;
+#endif
     for (int i = 0; i < kNumPlans; i++)
         if (kPlanSizes[i] == n) return i;
     return -1;
@@ -524,13 +526,13 @@ template <class P> static cudaError_t launch_shared(const AcqArgs& a, int n_d, c
         if ((e = launch_forward<P>(a, n_d, st)) != cudaSuccess) return e;
     }
     if constexpr (std::is_same<P, P4092>::value) {
-        static const bool no_lw = getenv("GB_ACQ_NOLW") != nullptr;   // A/B switch (tools/time_acq.py)
+        const bool no_lw = tuning("acq_nolw", 0) != 0;   // A/B switch (tools/time_acq.py)
         if (!no_lw && !a.plain_inverse) {
             return acq_launch_inverse_lw4092(a, n_d, st);   // acq_lw.cu
         }
     }
     // double-buffered line when two lines fit the 227 KB of one SM at the plan's CTA count
-    static const bool no_db = getenv("GB_ACQ_NODB") != nullptr;   // A/B switch (tools/time_acq.py)
+    const bool no_db = tuning("acq_nodb", 0) != 0;   // A/B switch (tools/time_acq.py)
     if (a.inv_map) {
         // aliased form: the seven production plans only (the tuning variants never request it, acq_plan_supports_alias)
         if constexpr (kProductionPlan<P>) {

@@ -7,6 +7,9 @@
 
 namespace gb {
 
+// explicit tuning switches (gb_tuning_set, include/gnss_b200.h); defined in gnss_b200.cu
+int tuning(const char* key, int dflt);
+
 struct AcqArgs {
     const float2* iq;        // sample ring / chunk base
     unsigned long long iq_start;  // absolute index of sample 0 of block 0

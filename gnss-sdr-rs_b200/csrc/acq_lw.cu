@@ -2,7 +2,6 @@
 // plan zoo of acq_kernels.cu takes two minutes to compile).
 #include "acq_common.cuh"
 
-#include <stdlib.h>
 
 namespace gb {
 
@@ -118,7 +117,7 @@ cudaError_t acq_launch_inverse_lw4092(const AcqArgs& a, int n_d, cudaStream_t st
     using PW = P4092W;
     static_assert(PW::T + 32 == P4092::T && PW::LINE == P4092::LINE, "same line as the default plan, one extra warp");
     const size_t smem = sizeof(float2) * (size_t)PW::LINE;
-    static const bool ldg = getenv("GB_ACQ_SPEC_LDG") != nullptr;   // A/B switch (tools/time_acq.py): 1.711 vs 1.697 ms
+    const bool ldg = tuning("acq_spec_ldg", 0) != 0;   // A/B switch (tools/time_acq.py): 1.711 vs 1.697 ms
     cudaError_t e;
     if (ldg) {
         if ((e = cudaFuncSetAttribute(acq_inverse_lw_kernel<PW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;

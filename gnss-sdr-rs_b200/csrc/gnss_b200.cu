@@ -8,6 +8,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -31,6 +33,31 @@ struct FftRes {
 };
 
 }  // namespace
+
+// ------------------------------------------------------------------ tuning switches (explicit, process-wide)
+namespace {
+std::mutex g_tuning_mu;
+std::map<std::string, int> g_tuning;
+}  // namespace
+
+namespace gb {
+int tuning(const char* key, int dflt)
+{
+    std::lock_guard<std::mutex> lk(g_tuning_mu);
+    auto it = g_tuning.find(key);
+    return it == g_tuning.end() ? dflt : it->second;
+}
+}  // namespace gb
+
+extern "C" int gb_tuning_set(const char* key, int value)
+{
+    if (!key) return GB_EINVAL;
+    std::lock_guard<std::mutex> lk(g_tuning_mu);
+    g_tuning[key] = value;
+    return GB_OK;
+}
+
+extern "C" int gb_tuning_get(const char* key, int dflt) { return key ? gb::tuning(key, dflt) : dflt; }
 
 struct gb_handle {
     int device = 0;
@@ -636,11 +663,11 @@ extern "C" int gb_frontend_configure(gb_handle* h, float f_if, float fs_in)
     h->fe_step = (f_if / fs_in) * 2048.0f;  // nco_lut.rs:34
     // The phase accumulator does not depend on the samples: its orbit from 0 (tail + cycle, at most 2^24 states) is
     // computed here in the reference's f32 arithmetic and the kernel looks the LUT index up by sample number.
-    // GB_FE_SEQUENTIAL=1 (or an orbit longer than the cap) keeps the one-thread sequential accumulator.
+    // gb_tuning_set("fe_sequential", 1) (or an orbit longer than the cap) keeps the one-thread sequential accumulator.
     h->fe_table = false;
     h->fe_count = 0;
     if (h->fe_idx) { cudaFree(h->fe_idx); h->fe_idx = nullptr; }
-    if (!getenv("GB_FE_SEQUENTIAL") &&
+    if (!gb::tuning("fe_sequential", 0) &&
         gb::fe_build_phase_orbit(h->fe_step, (uint64_t)1 << 24, 4096, h->fe_phase, &h->fe_mu, &h->fe_period)) {
         std::vector<uint16_t> idx(h->fe_phase.size());
         for (size_t i = 0; i < idx.size(); i++) idx[i] = gb::fe_lut_index(h->fe_phase[i]);

@@ -23,5 +23,11 @@ struct TrkArgs {
 };
 
 cudaError_t trk_launch(const TrkArgs& a, int mode, cudaStream_t st);
+// warp-specialised FAST kernel for ring-fed epochs with loop filters (trk_ws.cu)
+bool trk_ws_supported(const TrkArgs& a);
+cudaError_t trk_ws_launch(const TrkArgs& a, cudaStream_t st, int variant);
+
+// explicit tuning switches (gb_tuning_set in include/gnss_b200.h; there are no environment-variable switches)
+int tuning(const char* key, int dflt);
 
 }  // namespace gb

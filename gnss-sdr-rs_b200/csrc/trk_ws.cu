@@ -1,0 +1,490 @@
+// trk_ws.cu -- warp-specialised form of the FAST tracking kernel (ring-fed do_work epochs with on-device loop filters).
+// Compile with -fmad=false like trk_kernels.cu.
+//
+// One CTA per channel, as in trk_kernels.cu, but the CTA is split into NSW *sample warps* and two *control warps*:
+//
+//   sample warps   early_late_correlation (do_tracking.rs:231-272): carrier / code replicas in registers, six partial
+//                  sums, 8-shuffle warp reduction, one float per (sum, warp) to shared memory.  They never execute the
+//                  serial code.  The FIRST batch of the next epoch's window is loaded while the current epoch is being
+//                  computed: its start (next_sample_index + n) is known when the epoch begins, only its length is not,
+//                  and samples past the length are masked at use -- the L2 latency of the window leaves the per-epoch
+//                  critical path (it was ~1/5 of it with one channel per SM).
+//   carrier warp   lane 0: lock test, atan-Costas PLL (run_loop_filters, :279-290), carrier_phase advance (:240-242),
+//                  prompt outputs; publishes the next epoch's carrier scalars.
+//   code warp      lane 0: lock test, envelope DLL (:291-301), code_phase advance (:265-267), sample bookkeeping of
+//                  do_work / update (:160-210), next epoch's go / no-go; publishes the code scalars.
+//
+// Everything the two control lanes can know before the sums arrive is computed while the sample warps run: the phase
+// advances (they use the PRE-filter carrier_freq / code_rate of the running epoch), the window start, the reset
+// bookkeeping.  Between "sums complete" and "next epoch may start" only the discriminator -> filter -> NCO -> per-sample
+// step chain remains (sum 8 partials, divide, atan, two multiply-adds | two square roots, divide, two multiply-adds,
+// one division by fs).  Hand-offs are named barriers, never a CTA-wide __syncthreads():
+//   PART  sample warps have stored their partials / control warps may read them;
+//   GO    control warps have published the epoch's scalars / sample warps may read them;
+//   X     code warp -> carrier warp (n and go of the epoch just published).
+// All of them are bar.sync on both sides (bar.arrive does not order the arriving thread's shared-memory stores, and a
+// fence costs more than the wait it would save: the side that "only arrives" is the one that waits next anyway --
+// sample warps go from PART straight to GO, and by the time a control warp reaches GO they are already parked there).
+#include "trk_common.cuh"
+
+namespace gb {
+
+namespace {
+
+enum { BAR_GO = 1, BAR_PART = 2, BAR_X = 3 };
+
+__device__ __forceinline__ void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+// scalars of one epoch, written by the control lanes and read by every sample thread after GO
+struct __align__(16) EpochParams {
+    // carrier warp
+    float f_turn, cp_turn, w, carrier_phase;
+    float wc, ws;
+    int carr_ok;        // the turns form of the carrier argument is valid for this epoch
+    int pad0;
+    // code warp
+    float code_step, code_phase;
+    int n;
+    int flags;          // bit 0: go, bit 1: chip arguments stay in [0, 3 * 1023), bit 2: ... in [0, 2 * 1023)
+    unsigned s0;        // (window start) & ring mask
+    int pad1[3];
+};
+
+__device__ __forceinline__ float sqrt_fast(float x)
+{
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float rcp_fast(float x)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+}  // namespace
+
+// NSW sample warps, U samples per thread and batch, ROT: carrier of a batch by rotating its first sample
+template <int NSW, int U, bool ROT> __global__ void __launch_bounds__((NSW + 2) * 32) trk_ws_kernel(const TrkArgs a)
+{
+    constexpr int T = NSW * 32;          // sample threads
+    constexpr int NT = T + 64;           // + two control warps
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4* row4 = reinterpret_cast<float4*>(smem_raw);               // 1024 x {chip k-1, chip k, chip k+1, 0}
+    float* row = reinterpret_cast<float*>(row4 + 1024);               // 1024: plain row (general path)
+    float* red = row + 1024;                                          // [6][NSW] per-warp sums
+    __shared__ gb_trk_channel st;
+    __shared__ EpochParams P;
+
+    const int c = blockIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) st = a.ch[c];
+    __syncthreads();
+    {
+        const int8_t* src = a.ca_table + (size_t)(st.code_row < 32 ? st.code_row : 0) * 1023;
+        for (int i = tid; i < 1023; i += NT) {
+            const float pk = (float)src[i];
+            row[i] = pk;
+            row4[i] = make_float4((float)src[i == 0 ? 0 : i - 1], pk, (float)src[i == 1022 ? 0 : i + 1], 0.f);
+        }
+    }
+    const float fs = st.fs;                          // never changes during a run
+    const float rcp_fs = 1.0f / fs;
+    const unsigned mask32 = (unsigned)a.mask;        // ring capacity <= 2^32 samples (checked by the launcher)
+    // first index past the last batch of the longest epoch this launch may see: bounds of the per-epoch range checks
+    const float i_end_max = (float)(((a.n_max + U * T - 1) / (U * T)) * (U * T));
+    __syncthreads();
+
+    if (warp < NSW) {
+        // ------------------------------------------------------------------------------------------- sample warps
+        const float2* __restrict__ smp = a.samples;
+        const unsigned row4_bias = (unsigned)__cvta_generic_to_shared(row4) - 16u * 0x4B000000u;
+        const float c1 = 6.28318548202514648f;        // fl(2 pi)
+        const float c2 = -1.74845553146951715e-7f;    // 2 pi - fl(2 pi)
+        const float inv_2pi = 0.15915494309189535f;
+        float2 x[U];
+        auto load_batch = [&](float2(&v)[U], unsigned base) {
+#pragma unroll
+            for (int u = 0; u < U; u++) v[u] = __ldg(smp + ((base + (unsigned)(tid + u * T)) & mask32));
+        };
+        named_sync(BAR_GO, NT);
+        bool first = true;
+        while (P.flags & 1) {
+            const float4 pc4 = *reinterpret_cast<const float4*>(&P.f_turn);
+            const float f_turn = pc4.x, cp_turn = pc4.y, w = pc4.z, carrier_phase = pc4.w;
+            const float wc = P.wc, ws = P.ws;
+            const float code_step = P.code_step, code_phase = P.code_phase;
+            const int n = P.n, flags = P.flags;
+            const unsigned s0 = P.s0;
+            const bool fastp = (flags & 2) && P.carr_ok;
+            const bool single_wrap = flags & 4;
+            if (first) {
+                load_batch(x, s0);
+                first = false;
+            }
+            float ip = 0.f, qp = 0.f, ie = 0.f, qe = 0.f, il = 0.f, ql = 0.f;
+            pk64 accp = pk2(0.f, 0.f), acce = accp, accl = accp;
+            for (int b0 = 0; b0 < n; b0 += U * T) {
+                // next batch of this epoch, or the first batch of the next epoch's window (it starts at start + n)
+                float2 xn[U];
+                load_batch(xn, (b0 + U * T < n) ? s0 + (unsigned)(b0 + U * T) : s0 + (unsigned)n);
+                const int base = b0 + tid;
+                if (base + (U - 1) * T >= n) {          // the epoch's ragged last batch: samples past n count as zeros
+#pragma unroll
+                    for (int u = 0; u < U; u++)
+                        if (base + u * T >= n) x[u] = make_float2(0.f, 0.f);
+                }
+                const float fbase = (float)base;
+                if (fastp) {
+                    float cs[U], sn[U];
+                    {
+                        const float ut = fmaf(fbase, f_turn, cp_turn);
+                        const float r = (ut - rint_small(ut)) * c1;        // [-pi, pi]
+                        cs[0] = __cosf(r);
+                        sn[0] = __sinf(r);
+                    }
+                    if constexpr (ROT) {
+#pragma unroll
+                        for (int u = 1; u < U; u++) {
+                            cs[u] = fmaf(cs[u - 1], wc, -(sn[u - 1] * ws));
+                            sn[u] = fmaf(sn[u - 1], wc, cs[u - 1] * ws);
+                        }
+                    } else {
+#pragma unroll
+                        for (int u = 1; u < U; u++) {
+                            const float fi = fbase + (float)(u * T);   // exact: integers below 2^24
+                            const float utu = fmaf(fi, f_turn, cp_turn);
+                            const float ru = (utu - rint_small(utu)) * c1;
+                            cs[u] = __cosf(ru);
+                            sn[u] = __sinf(ru);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; u++) {
+                        const float fi = fbase + (float)(u * T);
+                        const float re = fmaf(x[u].x, cs[u], x[u].y * sn[u]);
+                        const float im = fmaf(x[u].y, cs[u], -(x[u].x * sn[u]));
+                        float tc = code_phase + (fi * code_step);
+                        tc = tc >= 1023.f ? tc - 1023.f : tc;
+                        if (!single_wrap) tc = tc >= 1023.f ? tc - 1023.f : tc;
+                        // floor(tc) sits in the mantissa of the round-down add; early / late chips are
+                        // floor(tc + 0.5) % 1023 in {k, k+1} and max(floor(tc - 0.5), 0) in {k-1, k} (Q7), decided on the
+                        // reference's own f32 sums tc + 0.5 and tc - 0.5
+                        const float pf = __fadd_rd(tc, 8388608.0f);
+                        const float4 q = lds_f32x4(16u * (unsigned)__float_as_int(pf) + row4_bias);
+                        const float fl = pf - 8388608.0f;                     // exact
+                        const float pcv = q.y;
+                        const float ec = (tc + 0.5f) >= (fl + 1.0f) ? q.z : q.y;
+                        const float lc = (tc - 0.5f) >= fl ? q.y : q.x;
+                        const pk64 z = pk2(re, im);
+                        accp = fma2s(z, pcv, accp);
+                        acce = fma2s(z, ec, acce);
+                        accl = fma2s(z, lc, accl);
+                    }
+                } else {
+                    // general form (IF carriers spanning thousands of turns, chip arguments outside the checked range):
+                    // the reference's f32 roundings of both arguments, Cody-Waite reduction, full get_ca_chip
+#pragma unroll
+                    for (int u = 0; u < U; u++) {
+                        const float fi = fbase + (float)(u * T);
+                        const float t = w * fi;
+                        const float q0 = t * rcp_fs;
+                        const float q = fmaf(fmaf(-q0, fs, t), rcp_fs, q0);      // (w * i) / fs
+                        const float phase = carrier_phase + q;
+                        const float k = rintf(phase * inv_2pi);
+                        const float r = fmaf(-k, c2, fmaf(-k, c1, phase));
+                        float csv, snv;
+                        if (fabsf(phase) < 1.0e6f) {
+                            csv = __cosf(r);
+                            snv = __sinf(r);
+                        } else {
+                            sincosf(phase, &snv, &csv);
+                        }
+                        const float re = fmaf(x[u].x, csv, x[u].y * snv);
+                        const float im = fmaf(x[u].y, csv, -(x[u].x * snv));
+                        const float tc = fmodf(code_phase + (fi * code_step), 1023.f);
+                        const float pcv = ca_chip(row, tc), ec = ca_chip(row, tc + 0.5f), lc = ca_chip(row, tc - 0.5f);
+                        ip = fmaf(re, pcv, ip); qp = fmaf(im, pcv, qp);
+                        ie = fmaf(re, ec, ie); qe = fmaf(im, ec, qe);
+                        il = fmaf(re, lc, il); ql = fmaf(im, lc, ql);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; u++) x[u] = xn[u];
+            }
+            if (fastp) {
+                upk2(accp, ip, qp);
+                upk2(acce, ie, qe);
+                upk2(accl, il, ql);
+            }
+            // Six sums per warp with 8 shuffles: every exchange halves the number of values a lane still carries
+            // (xor 16: {ip, qp, ie} | {qe, il, ql}; xor 8: two | one of those three; xor 4: one of two), the last two
+            // exchanges finish the single value left.  Lane bits 4..2 then say which sum a lane holds.
+            const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+            float k0 = (h16 ? qe : ip) + __shfl_xor_sync(0xffffffffu, h16 ? ip : qe, 16);
+            float k1 = (h16 ? il : qp) + __shfl_xor_sync(0xffffffffu, h16 ? qp : il, 16);
+            float k2 = (h16 ? ql : ie) + __shfl_xor_sync(0xffffffffu, h16 ? ie : ql, 16);
+            float m0 = (h8 ? k2 : k0) + __shfl_xor_sync(0xffffffffu, h8 ? k0 : k2, 8);
+            float m1 = (h8 ? 0.f : k1) + __shfl_xor_sync(0xffffffffu, h8 ? k1 : 0.f, 8);
+            float r = (h4 ? m1 : m0) + __shfl_xor_sync(0xffffffffu, h4 ? m0 : m1, 4);
+            r += __shfl_xor_sync(0xffffffffu, r, 2);
+            r += __shfl_xor_sync(0xffffffffu, r, 1);
+            // lanes 0, 4, 8 (bits 4..2 = 000, 001, 010) hold ip, qp, ie; lanes 16, 20, 24 hold qe, il, ql
+            if ((lane & 3) == 0 && !(h8 && h4)) red[((h16 ? 3 : 0) + (h8 ? 2 : (h4 ? 1 : 0))) * NSW + warp] = r;
+            named_sync(BAR_PART, NT);
+            named_sync(BAR_GO, NT);
+        }
+    } else if (warp == NSW) {
+        // ------------------------------------------------------------------------------------------- carrier warp
+        float freq = st.carrier_freq, phi = st.carrier_phase, cerr = st.carrier_error, cnco = st.carrier_nco;
+        float i_prompt = st.i_prompt, q_prompt = st.q_prompt;
+        unsigned lostc = st.lost_counter;
+        int ran = 0, lost = 0;
+        const float g1 = 0.001f / st.pll_tau1, g2 = st.pll_tau2 / st.pll_tau1;   // as evaluated inside run_loop_filters (:286)
+        auto publish = [&]() {
+            const float f_turn = freq * rcp_fs;
+            const float cp_turn = phi * 0.15915494309189535f;
+            const float w = kTwoPi * freq;                                       // 2.0 * PI * carrier_freq
+            *reinterpret_cast<float4*>(&P.f_turn) = make_float4(f_turn, cp_turn, w, phi);
+            // turns form: the epoch spans < 16 turns (argument error < 1e-6 turn) and the general form would not overflow
+            P.carr_ok = (fabsf(f_turn) * i_end_max < 16.f && fabsf(cp_turn) < 2.f) ? 1 : 0;
+            if (ROT) {
+                const float dt = f_turn * (float)T;                              // turns between a thread's consecutive samples
+                float s, cth;
+                sincosf((dt - rintf(dt)) * 6.28318548202514648f, &s, &cth);
+                P.wc = cth;
+                P.ws = s;
+            }
+        };
+        if (lane == 0) publish();
+        __syncwarp();
+        named_sync(BAR_GO, NT);
+        named_sync(BAR_X, 64);
+        for (int e = 0;; e++) {
+            if (!(P.flags & 1)) break;                                           // published by the code warp before X
+            float phi_next = 0.f;
+            if (lane == 0) {
+                // :240-242 with the carrier_freq the running epoch uses (the filters update it afterwards)
+                const float nf = (float)P.n;
+                const float cph = phi + (kTwoPi * freq) * (nf / fs);
+                phi_next = fabsf(cph) < 1.0e6f ? fmod_small(cph, kTwoPi, 0.15915494309189535f) : fmodf(cph, kTwoPi);
+            }
+            named_sync(BAR_PART, NT);
+            float i_p = 0.f, q_p = 0.f;
+            if (lane == 0) {
+                if (NSW % 4 == 0) {
+                    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
+#pragma unroll
+                    for (int k = 0; k < NSW / 4; k++) {
+                        const float4 u = *reinterpret_cast<const float4*>(red + 0 * NSW + 4 * k);
+                        const float4 v = *reinterpret_cast<const float4*>(red + 1 * NSW + 4 * k);
+                        a0 += u.x; a1 += u.y; a2 += u.z; a3 += u.w;
+                        b0 += v.x; b1 += v.y; b2 += v.z; b3 += v.w;
+                    }
+                    i_p = (a0 + a1) + (a2 + a3);
+                    q_p = (b0 + b1) + (b2 + b3);
+                } else {
+                    for (int k = 0; k < NSW; k++) { i_p += red[k]; q_p += red[NSW + k]; }
+                }
+                const float power = i_p * i_p + q_p * q_p;                       // :186
+                const bool locked = power > 15.0f;
+                const bool resets = !locked && lostc + 1u >= 20u;                // reset() this epoch (:199-201)
+                phi = phi_next;
+                if (locked) {
+                    // run_loop_filters, carrier part (:279-290); FAST: reciprocal-multiply division, multiply by 1/(2 pi)
+                    const float pll_err = atanf(__fdividef(q_p, i_p)) * 0.15915494309189535f;
+                    cnco = pll_err * g1 + (pll_err - cerr) * g2;
+                    cerr = pll_err;
+                    freq += cnco;
+                }
+                if (resets) { freq = 0.f; phi = 0.f; }
+                publish();
+                // ---- off the critical path
+                i_prompt = i_p;
+                q_prompt = q_p;
+                if (a.prompt_hist)
+                    reinterpret_cast<float2*>(a.prompt_hist)[(size_t)e * a.n_channels + c] = make_float2(i_p, q_p);
+                if (locked) {
+                    lostc = 0;
+                } else if (resets) {                                             // reset(), carrier fields (:311-326, Q9)
+                    lostc = 0;
+                    cerr = 0.f; cnco = 0.f; i_prompt = 0.f; q_prompt = 0.f;
+                    lost = 1;
+                } else {
+                    lostc += 1;
+                }
+                ran += 1;
+            }
+            __syncwarp();
+            named_sync(BAR_GO, NT);
+            named_sync(BAR_X, 64);
+        }
+        if (lane == 0) {
+            st.carrier_freq = freq; st.carrier_phase = phi; st.carrier_error = cerr; st.carrier_nco = cnco;
+            st.i_prompt = i_prompt; st.q_prompt = q_prompt; st.lost_counter = lostc;
+            if (a.ran) a.ran[c] = (uint8_t)(ran > 255 ? 255 : ran);
+            if (a.lost) a.lost[c] = (uint8_t)lost;
+        }
+    } else {
+        // ------------------------------------------------------------------------------------------- code warp
+        float cphase = st.code_phase, cerr = st.code_error, cnco = st.code_nco, crate = st.code_rate;
+        unsigned long long next_idx = st.next_sample_index, n64 = st.num_samples_per_code;
+        unsigned epochs_done = st.epochs_done, lostc = st.lost_counter;
+        int state = st.state, prn = st.prn, code_row = st.code_row;
+        float step = crate / fs;                                                  // (code_rate / fs)
+        float six[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        int ran = 0;
+        const float g1 = 0.001f / st.dll_tau1, g2 = st.dll_tau2 / st.dll_tau1;    // :298
+        // "may this channel consume an epoch now?" -- TrackingChannel::update (do_tracking.rs:160-172)
+        auto may_go = [&]() -> int {
+            int go = state == GB_TRK_TRACKING;
+            if ((long long)(a.head - (next_idx + n64)) < 0) go = 0;               // the ring does not hold it yet
+            if (a.capacity && a.head - next_idx > a.capacity) go = 0;             // already overwritten
+            if (n64 == 0 || n64 > (unsigned long long)a.n_max) go = 0;
+            return go;
+        };
+        auto publish = [&](int go) {
+            const int n = (int)n64;
+            const float i_end = (float)(((n + U * T - 1) / (U * T)) * (U * T));
+            const bool sane = cphase >= 0.f && cphase < 1023.f && step >= 0.f && step * i_end < 2040.f;
+            const bool single = cphase + step * i_end < 2046.f;
+            P.code_step = step;
+            P.code_phase = cphase;
+            P.n = n;
+            P.s0 = (unsigned)(next_idx & a.mask);
+            P.flags = (go ? 1 : 0) | (sane ? 2 : 0) | (sane && single ? 4 : 0);
+        };
+        int go = 0;
+        if (lane == 0) {
+            go = a.n_epochs > 0 ? may_go() : 0;
+            publish(go);
+        }
+        go = __shfl_sync(0xffffffffu, go, 0);
+        named_sync(BAR_GO, NT);
+        named_sync(BAR_X, 64);
+        for (int e = 0; go; e++) {
+            float cphase_next = 0.f;
+            if (lane == 0) {
+                // :265-267 with the code_rate the running epoch uses
+                const float cdp = cphase + step * (float)n64;
+                cphase_next = fabsf(cdp) < 1.0e8f ? fmod_small(cdp, 1023.f, 9.775171065493646e-4f) : fmodf(cdp, 1023.f);
+            }
+            named_sync(BAR_PART, NT);
+            if (lane == 0) {
+#pragma unroll
+                for (int k = 0; k < 6; k++) {
+                    if (NSW % 4 == 0) {
+                        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+                        for (int j = 0; j < NSW / 4; j++) {
+                            const float4 u = *reinterpret_cast<const float4*>(red + k * NSW + 4 * j);
+                            a0 += u.x; a1 += u.y; a2 += u.z; a3 += u.w;
+                        }
+                        six[k] = (a0 + a1) + (a2 + a3);
+                    } else {
+                        float s = 0.f;
+                        for (int j = 0; j < NSW; j++) s += red[k * NSW + j];
+                        six[k] = s;
+                    }
+                }
+                const float i_p = six[0], q_p = six[1], i_e = six[2], q_e = six[3], i_l = six[4], q_l = six[5];
+                const float power = i_p * i_p + q_p * q_p;                        // :186
+                const bool locked = power > 15.0f;
+                const bool resets = !locked && lostc + 1u >= 20u;
+                if (locked) {
+                    // run_loop_filters, code part (:291-301); FAST: approximate square roots and division (2 ulp)
+                    const float pow_e = sqrt_fast(i_e * i_e + q_e * q_e);
+                    const float pow_l = sqrt_fast(i_l * i_l + q_l * q_l);
+                    const float dll_err = ((pow_e + pow_l) != 0.f) ? __fdividef(pow_e - pow_l, pow_e + pow_l) : 0.f;
+                    cnco = dll_err * g1 + (dll_err - cerr) * g2;
+                    cerr = dll_err;
+                    crate += cnco;
+                    lostc = 0;
+                } else if (resets) {
+                    lostc = 0;
+                } else {
+                    lostc += 1;
+                }
+                if (resets) {                                                     // reset(), code / bookkeeping fields
+                    prn = 0; code_row = 0; state = GB_TRK_IDLE;
+                    next_idx = 0;
+                    cphase = 0.f; cerr = 0.f; cnco = 0.f; crate = 0.f;
+                } else {
+                    cphase = cphase_next;
+                    next_idx += n64;
+                    {
+                        // round(fs / (code_rate / 1023)) as usize (:165 via generate_ca_code_samples' length): the quotient
+                        // from one reciprocal is within 2e-7 relative of the f32 double division, so away from a half-way
+                        // value both round to the same integer; otherwise the reference's two IEEE divisions decide
+                        const float qa = (fs * 1023.0f) * rcp_fast(crate);
+                        const float qr = rintf(qa);
+                        if (qa > 0.5f && qa < 2.0e5f && fabsf(qa - qr) < 0.45f) {
+                            n64 = (unsigned long long)(unsigned)qr;
+                        } else {
+                            const float spc = roundf(fs / (crate / 1023.0f));
+                            n64 = (spc >= 0.f && spc < 2.0e9f) ? (unsigned long long)(unsigned)spc : f32_as_usize(spc);
+                        }
+                    }
+                }
+                // (code_rate / fs): reciprocal + exact-residual correction = the correctly rounded quotient
+                {
+                    const float q0 = crate * rcp_fs;
+                    step = fmaf(fmaf(-q0, fs, crate), rcp_fs, q0);
+                }
+                epochs_done += 1;
+                ran += 1;
+                go = (e + 1 < a.n_epochs) ? may_go() : 0;
+                publish(go);
+            }
+            go = __shfl_sync(0xffffffffu, go, 0);
+            named_sync(BAR_GO, NT);
+            named_sync(BAR_X, 64);
+        }
+        if (lane == 0) {
+            st.code_phase = cphase; st.code_error = cerr; st.code_nco = cnco; st.code_rate = crate;
+            st.next_sample_index = next_idx; st.num_samples_per_code = n64; st.epochs_done = epochs_done;
+            st.state = (uint8_t)state; st.prn = (uint8_t)prn; st.code_row = (uint8_t)code_row;
+            if (ran > 0) {
+                gb_trk_corr out;
+                out.i_p = six[0]; out.q_p = six[1]; out.i_e = six[2]; out.q_e = six[3]; out.i_l = six[4]; out.q_l = six[5];
+                a.corr[c] = out;
+            }
+        }
+    }
+    __syncthreads();
+    if (tid == 0) a.ch[c] = st;
+}
+
+template <int NSW, int U, bool ROT> static cudaError_t launch_ws(const TrkArgs& a, cudaStream_t st)
+{
+    const size_t smem = 1024 * sizeof(float4) + 1024 * sizeof(float) + 6 * NSW * sizeof(float) + 64;
+    trk_ws_kernel<NSW, U, ROT><<<a.n_channels, (NSW + 2) * 32, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+bool trk_ws_supported(const TrkArgs& a)
+{
+    return a.filters && a.offsets == nullptr && a.mask != ~0ull && a.mask < (1ull << 32);
+}
+
+// variant: 0 = by channel count, else NSW * 100 + U * 10 + ROT (tuning, gb_tuning_set("trk_ws", v))
+cudaError_t trk_ws_launch(const TrkArgs& a, cudaStream_t st, int variant)
+{
+    if (a.n_channels <= 0) return cudaSuccess;
+    switch (variant) {
+    case 880: return launch_ws<8, 8, false>(a, st);
+    case 881: return launch_ws<8, 8, true>(a, st);
+    case 1640: return launch_ws<16, 4, false>(a, st);
+    case 1641: return launch_ws<16, 4, true>(a, st);
+    case 480: return launch_ws<4, 8, false>(a, st);
+    case 481: return launch_ws<4, 8, true>(a, st);
+    case 441: return launch_ws<4, 4, true>(a, st);
+    case 281: return launch_ws<2, 8, true>(a, st);
+    default: break;
+    }
+    if (a.n_channels > 300) return launch_ws<4, 8, true>(a, st);
+    return launch_ws<8, 8, false>(a, st);
+}
+
+}  // namespace gb

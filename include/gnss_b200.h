@@ -53,6 +53,13 @@ const char *gb_last_cuda_error(gb_handle *h);
 int gb_version(void);
 int gb_device_count(void);
 
+/* Explicit A/B and tuning switches of the kernels (process-wide, default = the shipped organisation).  The library
+ * reads NO environment variables.  Keys: "trk_ws" (-1 = generic tracking kernel everywhere, 0 = default, else
+ * NSW*100+U*10+ROT), "trk_t" (CTA size of the generic tracking kernel), "acq_variant", "acq_nolw", "acq_nodb",
+ * "acq_spec_ldg", "fe_sequential".  Unknown keys are stored and ignored. */
+int gb_tuning_set(const char *key, int value);
+int gb_tuning_get(const char *key, int dflt);
+
 int gb_create(const gb_config *cfg, gb_handle **out);
 int gb_destroy(gb_handle *h);
 int gb_synchronize(gb_handle *h);
@@ -85,8 +92,8 @@ int gb_ring_reset(gb_handle *h);
  * The phase accumulator (`acc = (acc + step) % 2048.0` per sample, frontend.rs:48-52) does not depend on the samples:
  * gb_frontend_configure computes its orbit from 0 -- a tail of mu states then a cycle of lambda states, found with
  * Brent's algorithm in the reference's f32 arithmetic -- and the kernel looks LUT indices up by sample number, so only
- * the DC-bias recurrences stay sequential.  Orbits longer than 2^24 states (none met in practice) and the environment
- * variable GB_FE_SEQUENTIAL=1 fall back to a one-thread sequential accumulator with identical results. */
+ * the DC-bias recurrences stay sequential.  Orbits longer than 2^24 states (none met in practice) and gb_tuning_set("fe_sequential", 1)
+ * fall back to a one-thread sequential accumulator with identical results. */
 int gb_frontend_configure(gb_handle *h, float f_if, float fs_in);
 int gb_frontend_write(gb_handle *h, const gb_c32 *raw, uint64_t n);
 int gb_frontend_state(gb_handle *h, float *state17 /* phase_accumulator, bias_re[8], bias_im[8] */);

@@ -74,16 +74,13 @@ def test_fft_facade(gpu, n):
 
 @pytest.mark.parametrize("sequential", [False, True])
 @pytest.mark.parametrize("f_if,fs", [(4130400.0, 16367600.0), (4092000.0, 16368000.0), (-420000.0, 2048000.0)])
-def test_digital_frontend_bit_exact(gpu, oracle, monkeypatch, sequential, f_if, fs):
+def test_digital_frontend_bit_exact(gpu, oracle, ffi, sequential, f_if, fs):
     """rf/frontend.rs process_block restated -- DC removal + NCO LUT mix, bit-exact incl. the sequential
     f32 phase accumulator, across several rf_thread-sized blocks (2048) and one odd-sized write.  Both NCO forms: the
     phase-orbit table (default; lambda = 6313323 / 4 / 512 for these steps, so the short cycles wrap many times inside
-    one write) and the one-thread sequential accumulator (GB_FE_SEQUENTIAL=1)."""
+    one write) and the one-thread sequential accumulator (gb_tuning_set("fe_sequential", 1))."""
     from gnss_sdr_rs_b200 import ring
-    if sequential:
-        monkeypatch.setenv("GB_FE_SEQUENTIAL", "1")
-    else:
-        monkeypatch.delenv("GB_FE_SEQUENTIAL", raising=False)
+    ffi.tuning_set("fe_sequential", 1 if sequential else 0)
     rng = np.random.default_rng(3)
     raw = ((rng.standard_normal(5 * 2048 + 1000) * 20 + 3.0) + 1j * (rng.standard_normal(5 * 2048 + 1000) * 20 - 2.0)).astype(np.complex64)
     rb = ring.MulticastRingBuffer(gpu, 1 << 15)

@@ -26,6 +26,9 @@ def main():
     fs = n * 1000.0
     rng = np.random.default_rng(0)
     x = (rng.standard_normal(n * K) + 1j * rng.standard_normal(n * K)).astype(np.complex64)
+    for kv in filter(None, os.environ.get("TUNE", "").split(",")):   # TUNE=acq_nolw=1,acq_variant=2 (tool-side only)
+        k, v = kv.split("=")
+        ffi.tuning_set(k, int(v))
     hd = ffi.Handle(0)
     eng = acquisition.AcquisitionEngine(hd, n, fs)
     eng.make_doppler_tables(0.0, np.linspace(-5000, 5000, D).astype(np.float32))
@@ -45,7 +48,7 @@ def main():
     ms = ms[2:]
     cells = 32 * D * n
     print("%s %s variant=%s  N=%d K=%d D=%d coh=%d  kernel_ms min %.3f med %.3f  cells/s %.3e" % (
-        wl, mode, os.environ.get("GB_ACQ_VARIANT", "0"), n, K, D, coh, min(ms), float(np.median(ms)), cells / (min(ms) * 1e-3)))
+        wl, mode, ffi.lib().gb_tuning_get(b"acq_variant", 0), n, K, D, coh, min(ms), float(np.median(ms)), cells / (min(ms) * 1e-3)))
     hd.close()
 
 
