@@ -435,11 +435,13 @@ template <int T> static cudaError_t launch_t(const TrkArgs& a, int mode, cudaStr
 // channels 128 threads keep every SM full of independent channels; with few the run is bound by the per-epoch latency
 // of one CTA, so each channel gets more threads.  gb_tuning_set("trk_ws", -1) selects trk_kernel everywhere (A/B),
 // gb_tuning_set("trk_t", 64 | 128 | 256 | 512) its CTA size.
-cudaError_t trk_launch(const TrkArgs& a, int mode, cudaStream_t st)
+cudaError_t trk_launch(const TrkArgs& a0, int mode, cudaStream_t st)
 {
-    if (a.n_channels <= 0) return cudaSuccess;
+    if (a0.n_channels <= 0) return cudaSuccess;
+    TrkArgs a = a0;
+    a.dbg = tuning("trk_dbg", 0);
     const int ws = tuning("trk_ws", 0);
-    if (mode == GB_TRK_FAST && ws >= 0 && trk_ws_supported(a)) return trk_ws_launch(a, st, ws);
+    if (mode == GB_TRK_FAST && trk_ws_supported(a) && (ws > 0 || (ws == 0 && a.n_channels <= 300))) return trk_ws_launch(a, st, ws);
     switch (tuning("trk_t", 0)) {
     case 64: return launch_t<64>(a, mode, st);
     case 128: return launch_t<128>(a, mode, st);

@@ -20,6 +20,7 @@ struct TrkArgs {
     float* prompt_hist;             // n_epochs x n_channels x 2 or nullptr
     uint8_t* ran;                   // per channel: epochs consumed in this launch (saturating at 255)
     uint8_t* lost;                  // per channel: SatelliteLost emitted
+    int dbg = 0;                    // tuning bits (gb_tuning_set("trk_dbg", v)): 1 = no L2 prefetch of the window after next
 };
 
 cudaError_t trk_launch(const TrkArgs& a, int mode, cudaStream_t st);

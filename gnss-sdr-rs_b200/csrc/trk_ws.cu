@@ -27,6 +27,8 @@
 // sample warps go from PART straight to GO, and by the time a control warp reaches GO they are already parked there).
 #include "trk_common.cuh"
 
+#include <type_traits>
+
 namespace gb {
 
 namespace {
@@ -65,11 +67,35 @@ __device__ __forceinline__ float rcp_fast(float x)
 
 }  // namespace
 
-// NSW sample warps, U samples per thread and batch, ROT: carrier of a batch by rotating its first sample
-template <int NSW, int U, bool ROT> __global__ void __launch_bounds__((NSW + 2) * 32) trk_ws_kernel(const TrkArgs a)
+// atan(q / i) for the Costas discriminator (FAST mode): ONE reciprocal (of the larger magnitude) instead of the two of
+// atanf(q / i), the minimax polynomial of atanf on [0, 1] evaluated in Estrin form (depth 5 instead of 9); <= 3 ulp.
+__device__ __forceinline__ float atan_ratio_fast(float q, float i)
+{
+    const float aq = fabsf(q), ai = fabsf(i);
+    const float mx = fmaxf(aq, ai), mn = fminf(aq, ai);
+    const float t = mn * rcp_fast(mx);                 // in [0, 1]; 0/0 -> NaN like atanf(0/0)
+    const float s = t * t, s2 = s * s, s4 = s2 * s2;
+    const float p01 = fmaf(0.19988775253295898438f, s, -0.33332940936088562012f);
+    const float p23 = fmaf(0.10518480092287063599f, s, -0.14171802997589111328f);
+    const float p45 = fmaf(0.039849750697612762451f, s, -0.072529748082160949707f);
+    const float p67 = fmaf(0.0024500258732587099075f, s, -0.014396979473531246185f);
+    const float lo = fmaf(s2, p23, p01), hi = fmaf(s2, p67, p45);
+    const float P = fmaf(s4, hi, lo);
+    float r = fmaf(t * s, P, t);
+    if (aq > ai) r = 1.57079637050628662109f - r;
+    // sign of q / i
+    return __int_as_float(__float_as_int(r) ^ ((__float_as_int(q) ^ __float_as_int(i)) & 0x80000000));
+}
+
+// NSW sample warps, U samples per thread and batch, NSFU carrier evaluations per batch through the SFU (the other samples
+// of each group of U / NSFU by rotating the previous one; NSFU == U: no rotation)
+template <int NSW, int U, int NSFU> __global__ void __launch_bounds__((NSW + 2) * 32) trk_ws_kernel(const TrkArgs a)
 {
     constexpr int T = NSW * 32;          // sample threads
     constexpr int NT = T + 64;           // + two control warps
+    constexpr bool ROT = NSFU < U;
+    constexpr int CHAIN = U / NSFU;
+    static_assert(U % NSFU == 0, "whole rotation chains");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4* row4 = reinterpret_cast<float4*>(smem_raw);               // 1024 x {chip k-1, chip k, chip k+1, 0}
     float* row = reinterpret_cast<float*>(row4 + 1024);               // 1024: plain row (general path)
@@ -103,85 +129,92 @@ template <int NSW, int U, bool ROT> __global__ void __launch_bounds__((NSW + 2) 
         const float c1 = 6.28318548202514648f;        // fl(2 pi)
         const float c2 = -1.74845553146951715e-7f;    // 2 pi - fl(2 pi)
         const float inv_2pi = 0.15915494309189535f;
-        float2 x[U];
+        // a batch: U samples per thread, sample u at base + tid + u * T; one pointer + immediate offsets unless the
+        // batch straddles the ring's wrap point
         auto load_batch = [&](float2(&v)[U], unsigned base) {
+            const unsigned b0 = base & mask32;
+            if (b0 + (unsigned)(U * T) <= mask32 + 1u && b0 + (unsigned)(U * T) >= b0) {
+                const float2* __restrict__ p = smp + b0 + tid;
 #pragma unroll
-            for (int u = 0; u < U; u++) v[u] = __ldg(smp + ((base + (unsigned)(tid + u * T)) & mask32));
-        };
-        named_sync(BAR_GO, NT);
-        bool first = true;
-        while (P.flags & 1) {
-            const float4 pc4 = *reinterpret_cast<const float4*>(&P.f_turn);
-            const float f_turn = pc4.x, cp_turn = pc4.y, w = pc4.z, carrier_phase = pc4.w;
-            const float wc = P.wc, ws = P.ws;
-            const float code_step = P.code_step, code_phase = P.code_phase;
-            const int n = P.n, flags = P.flags;
-            const unsigned s0 = P.s0;
-            const bool fastp = (flags & 2) && P.carr_ok;
-            const bool single_wrap = flags & 4;
-            if (first) {
-                load_batch(x, s0);
-                first = false;
+                for (int u = 0; u < U; u++) v[u] = __ldg(p + u * T);
+            } else {
+#pragma unroll
+                for (int u = 0; u < U; u++) v[u] = __ldg(smp + ((base + (unsigned)(tid + u * T)) & mask32));
             }
+        };
+        // One epoch on the batch already in `cur`; the batch that follows (this epoch's next one, or the first of the
+        // next epoch's window: it starts at start + n whatever the filters decide) is loaded into `nxt` meanwhile.
+        // Returns false when the channel stops.  Called alternately with (xa, xb) and (xb, xa): no register copies.
+        auto epoch = [&](float2(&cur)[U], float2(&nxt)[U]) -> bool {
+            const float4 pc4 = *reinterpret_cast<const float4*>(&P.f_turn);
+            const float4 pd4 = *reinterpret_cast<const float4*>(&P.code_step);
+            const float f_turn = pc4.x, cp_turn = pc4.y, w = pc4.z, carrier_phase = pc4.w;
+            const float code_step = pd4.x, code_phase = pd4.y;
+            const int n = __float_as_int(pd4.z), flags = __float_as_int(pd4.w);
+            const unsigned s0 = P.s0;
+            float wc = 1.f, ws = 0.f;
+            int carr_ok;
+            if (ROT) {
+                const float4 pr4 = *reinterpret_cast<const float4*>(&P.wc);
+                wc = pr4.x; ws = pr4.y; carr_ok = __float_as_int(pr4.z);
+            } else {
+                carr_ok = P.carr_ok;
+            }
+            const bool fastp = (flags & 2) && carr_ok;
+            const bool single_wrap = flags & 4;
+            // the window after next: into L2 now (its first touch would otherwise pay the DRAM latency inside an epoch)
+            if (!(a.dbg & 1) && tid * 16 < n + 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(smp + ((s0 + 2u * (unsigned)n + 16u * (unsigned)tid) & mask32)));
             float ip = 0.f, qp = 0.f, ie = 0.f, qe = 0.f, il = 0.f, ql = 0.f;
             pk64 accp = pk2(0.f, 0.f), acce = accp, accl = accp;
-            for (int b0 = 0; b0 < n; b0 += U * T) {
-                // next batch of this epoch, or the first batch of the next epoch's window (it starts at start + n)
-                float2 xn[U];
-                load_batch(xn, (b0 + U * T < n) ? s0 + (unsigned)(b0 + U * T) : s0 + (unsigned)n);
+            auto compute_batch = [&](int b0) {
                 const int base = b0 + tid;
                 if (base + (U - 1) * T >= n) {          // the epoch's ragged last batch: samples past n count as zeros
 #pragma unroll
                     for (int u = 0; u < U; u++)
-                        if (base + u * T >= n) x[u] = make_float2(0.f, 0.f);
+                        if (base + u * T >= n) cur[u] = make_float2(0.f, 0.f);
                 }
                 const float fbase = (float)base;
                 if (fastp) {
                     float cs[U], sn[U];
-                    {
-                        const float ut = fmaf(fbase, f_turn, cp_turn);
-                        const float r = (ut - rint_small(ut)) * c1;        // [-pi, pi]
-                        cs[0] = __cosf(r);
-                        sn[0] = __sinf(r);
-                    }
-                    if constexpr (ROT) {
 #pragma unroll
-                        for (int u = 1; u < U; u++) {
+                    for (int u = 0; u < U; u++) {
+                        if (u % CHAIN == 0) {
+                            const float fi = fbase + (float)(u * T);   // exact: integers below 2^24
+                            const float ut = fmaf(fi, f_turn, cp_turn);
+                            const float r = (ut - rint_small(ut)) * c1;        // [-pi, pi]
+                            cs[u] = __cosf(r);
+                            sn[u] = __sinf(r);
+                        } else {
                             cs[u] = fmaf(cs[u - 1], wc, -(sn[u - 1] * ws));
                             sn[u] = fmaf(sn[u - 1], wc, cs[u - 1] * ws);
                         }
-                    } else {
+                    }
+                    auto body = [&](auto sw) {
 #pragma unroll
-                        for (int u = 1; u < U; u++) {
-                            const float fi = fbase + (float)(u * T);   // exact: integers below 2^24
-                            const float utu = fmaf(fi, f_turn, cp_turn);
-                            const float ru = (utu - rint_small(utu)) * c1;
-                            cs[u] = __cosf(ru);
-                            sn[u] = __sinf(ru);
+                        for (int u = 0; u < U; u++) {
+                            const float fi = fbase + (float)(u * T);
+                            const float re = fmaf(cur[u].x, cs[u], cur[u].y * sn[u]);
+                            const float im = fmaf(cur[u].y, cs[u], -(cur[u].x * sn[u]));
+                            float tc = code_phase + (fi * code_step);
+                            tc = tc >= 1023.f ? tc - 1023.f : tc;
+                            if (!decltype(sw)::value) tc = tc >= 1023.f ? tc - 1023.f : tc;
+                            // floor(tc) sits in the mantissa of the round-down add; early / late chips are
+                            // floor(tc + 0.5) % 1023 in {k, k+1} and max(floor(tc - 0.5), 0) in {k-1, k} (Q7), decided on
+                            // the reference's own f32 sums tc + 0.5 and tc - 0.5
+                            const float pf = __fadd_rd(tc, 8388608.0f);
+                            const float4 q = lds_f32x4(16u * (unsigned)__float_as_int(pf) + row4_bias);
+                            const float fl = pf - 8388608.0f;                     // exact
+                            const float pcv = q.y;
+                            const float ec = (tc + 0.5f) >= (fl + 1.0f) ? q.z : q.y;
+                            const float lc = (tc - 0.5f) >= fl ? q.y : q.x;
+                            const pk64 z = pk2(re, im);
+                            accp = fma2s(z, pcv, accp);
+                            acce = fma2s(z, ec, acce);
+                            accl = fma2s(z, lc, accl);
                         }
-                    }
-#pragma unroll
-                    for (int u = 0; u < U; u++) {
-                        const float fi = fbase + (float)(u * T);
-                        const float re = fmaf(x[u].x, cs[u], x[u].y * sn[u]);
-                        const float im = fmaf(x[u].y, cs[u], -(x[u].x * sn[u]));
-                        float tc = code_phase + (fi * code_step);
-                        tc = tc >= 1023.f ? tc - 1023.f : tc;
-                        if (!single_wrap) tc = tc >= 1023.f ? tc - 1023.f : tc;
-                        // floor(tc) sits in the mantissa of the round-down add; early / late chips are
-                        // floor(tc + 0.5) % 1023 in {k, k+1} and max(floor(tc - 0.5), 0) in {k-1, k} (Q7), decided on the
-                        // reference's own f32 sums tc + 0.5 and tc - 0.5
-                        const float pf = __fadd_rd(tc, 8388608.0f);
-                        const float4 q = lds_f32x4(16u * (unsigned)__float_as_int(pf) + row4_bias);
-                        const float fl = pf - 8388608.0f;                     // exact
-                        const float pcv = q.y;
-                        const float ec = (tc + 0.5f) >= (fl + 1.0f) ? q.z : q.y;
-                        const float lc = (tc - 0.5f) >= fl ? q.y : q.x;
-                        const pk64 z = pk2(re, im);
-                        accp = fma2s(z, pcv, accp);
-                        acce = fma2s(z, ec, acce);
-                        accl = fma2s(z, lc, accl);
-                    }
+                    };
+                    if (single_wrap) body(std::true_type{});
+                    else body(std::false_type{});
                 } else {
                     // general form (IF carriers spanning thousands of turns, chip arguments outside the checked range):
                     // the reference's f32 roundings of both arguments, Cody-Waite reduction, full get_ca_chip
@@ -201,8 +234,8 @@ template <int NSW, int U, bool ROT> __global__ void __launch_bounds__((NSW + 2) 
                         } else {
                             sincosf(phase, &snv, &csv);
                         }
-                        const float re = fmaf(x[u].x, csv, x[u].y * snv);
-                        const float im = fmaf(x[u].y, csv, -(x[u].x * snv));
+                        const float re = fmaf(cur[u].x, csv, cur[u].y * snv);
+                        const float im = fmaf(cur[u].y, csv, -(cur[u].x * snv));
                         const float tc = fmodf(code_phase + (fi * code_step), 1023.f);
                         const float pcv = ca_chip(row, tc), ec = ca_chip(row, tc + 0.5f), lc = ca_chip(row, tc - 0.5f);
                         ip = fmaf(re, pcv, ip); qp = fmaf(im, pcv, qp);
@@ -210,8 +243,25 @@ template <int NSW, int U, bool ROT> __global__ void __launch_bounds__((NSW + 2) 
                         il = fmaf(re, lc, il); ql = fmaf(im, lc, ql);
                     }
                 }
+            };
+            if (n <= U * T) {
+                // One batch per epoch (the latency-critical case: 2.048 Msps on 8 x 256 threads).  The next window's loads
+                // are issued AFTER the arithmetic: a scoreboard wait covers every load in flight on that scoreboard, so
+                // loads issued before the first use of `cur` would make that use wait for them too.  They have the
+                // reduction, the control section and the next epoch's start-up to arrive.
+                compute_batch(0);
+                load_batch(nxt, s0 + (unsigned)n);
+            } else {
+                // several batches per epoch: the next batch (or the next window's first one) is loaded while this one is
+                // being computed
+                for (int b0 = 0;; b0 += U * T) {
+                    const bool last = b0 + U * T >= n;
+                    load_batch(nxt, last ? s0 + (unsigned)n : s0 + (unsigned)(b0 + U * T));
+                    compute_batch(b0);
+                    if (last) break;
 #pragma unroll
-                for (int u = 0; u < U; u++) x[u] = xn[u];
+                    for (int u = 0; u < U; u++) cur[u] = nxt[u];
+                }
             }
             if (fastp) {
                 upk2(accp, ip, qp);
@@ -234,6 +284,16 @@ template <int NSW, int U, bool ROT> __global__ void __launch_bounds__((NSW + 2) 
             if ((lane & 3) == 0 && !(h8 && h4)) red[((h16 ? 3 : 0) + (h8 ? 2 : (h4 ? 1 : 0))) * NSW + warp] = r;
             named_sync(BAR_PART, NT);
             named_sync(BAR_GO, NT);
+            return P.flags & 1;
+        };
+        float2 xa[U], xb[U];
+        named_sync(BAR_GO, NT);
+        if (P.flags & 1) {
+            load_batch(xa, P.s0);
+            while (true) {
+                if (!epoch(xa, xb)) break;
+                if (!epoch(xb, xa)) break;
+            }
         }
     } else if (warp == NSW) {
         // ------------------------------------------------------------------------------------------- carrier warp
@@ -242,64 +302,72 @@ template <int NSW, int U, bool ROT> __global__ void __launch_bounds__((NSW + 2) 
         unsigned lostc = st.lost_counter;
         int ran = 0, lost = 0;
         const float g1 = 0.001f / st.pll_tau1, g2 = st.pll_tau2 / st.pll_tau1;   // as evaluated inside run_loop_filters (:286)
-        auto publish = [&]() {
-            const float f_turn = freq * rcp_fs;
-            const float cp_turn = phi * 0.15915494309189535f;
-            const float w = kTwoPi * freq;                                       // 2.0 * PI * carrier_freq
-            *reinterpret_cast<float4*>(&P.f_turn) = make_float4(f_turn, cp_turn, w, phi);
-            // turns form: the epoch spans < 16 turns (argument error < 1e-6 turn) and the general form would not overflow
-            P.carr_ok = (fabsf(f_turn) * i_end_max < 16.f && fabsf(cp_turn) < 2.f) ? 1 : 0;
+        // publishes the scalars of the epoch that starts at phase `ph` with carrier `f`; ph_ok = |ph / 2 pi| < 2
+        auto publish = [&](float f, float ph, float ph_turn, bool ph_ok) {
+            const float f_turn = f * rcp_fs;
+            const float w = kTwoPi * f;                                          // 2.0 * PI * carrier_freq
+            *reinterpret_cast<float4*>(&P.f_turn) = make_float4(f_turn, ph_turn, w, ph);
+            // turns form: the epoch spans < 16 turns (argument error < 1e-6 turn)
+            const int ok = (fabsf(f_turn) * i_end_max < 16.f && ph_ok) ? 1 : 0;
             if (ROT) {
                 const float dt = f_turn * (float)T;                              // turns between a thread's consecutive samples
-                float s, cth;
-                sincosf((dt - rintf(dt)) * 6.28318548202514648f, &s, &cth);
-                P.wc = cth;
-                P.ws = s;
+                const float ang = (dt - rint_small(dt)) * 6.28318548202514648f;
+                *reinterpret_cast<float4*>(&P.wc) = make_float4(__cosf(ang), __sinf(ang), __int_as_float(ok), 0.f);
+            } else {
+                P.carr_ok = ok;
             }
         };
-        if (lane == 0) publish();
+        if (lane == 0) {
+            const float pt = phi * 0.15915494309189535f;
+            publish(freq, phi, pt, fabsf(pt) < 2.f);
+        }
         __syncwarp();
         named_sync(BAR_GO, NT);
         named_sync(BAR_X, 64);
         for (int e = 0;; e++) {
             if (!(P.flags & 1)) break;                                           // published by the code warp before X
-            float phi_next = 0.f;
+            float phi_next = 0.f, pt_next = 0.f;
+            bool pt_ok = true;
             if (lane == 0) {
                 // :240-242 with the carrier_freq the running epoch uses (the filters update it afterwards)
                 const float nf = (float)P.n;
                 const float cph = phi + (kTwoPi * freq) * (nf / fs);
                 phi_next = fabsf(cph) < 1.0e6f ? fmod_small(cph, kTwoPi, 0.15915494309189535f) : fmodf(cph, kTwoPi);
+                pt_next = phi_next * 0.15915494309189535f;
+                pt_ok = fabsf(pt_next) < 2.f;
             }
             named_sync(BAR_PART, NT);
-            float i_p = 0.f, q_p = 0.f;
             if (lane == 0) {
+                float i_p, q_p;
                 if (NSW % 4 == 0) {
-                    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
+                    float4 u = *reinterpret_cast<const float4*>(red + 0 * NSW);
+                    float4 v = *reinterpret_cast<const float4*>(red + 1 * NSW);
 #pragma unroll
-                    for (int k = 0; k < NSW / 4; k++) {
-                        const float4 u = *reinterpret_cast<const float4*>(red + 0 * NSW + 4 * k);
-                        const float4 v = *reinterpret_cast<const float4*>(red + 1 * NSW + 4 * k);
-                        a0 += u.x; a1 += u.y; a2 += u.z; a3 += u.w;
-                        b0 += v.x; b1 += v.y; b2 += v.z; b3 += v.w;
+                    for (int k = 1; k < NSW / 4; k++) {
+                        const float4 u2 = *reinterpret_cast<const float4*>(red + 0 * NSW + 4 * k);
+                        const float4 v2 = *reinterpret_cast<const float4*>(red + 1 * NSW + 4 * k);
+                        u.x += u2.x; u.y += u2.y; u.z += u2.z; u.w += u2.w;
+                        v.x += v2.x; v.y += v2.y; v.z += v2.z; v.w += v2.w;
                     }
-                    i_p = (a0 + a1) + (a2 + a3);
-                    q_p = (b0 + b1) + (b2 + b3);
+                    i_p = (u.x + u.y) + (u.z + u.w);
+                    q_p = (v.x + v.y) + (v.z + v.w);
                 } else {
-                    for (int k = 0; k < NSW; k++) { i_p += red[k]; q_p += red[NSW + k]; }
+                    i_p = red[0]; q_p = red[NSW];
+                    for (int k = 1; k < NSW; k++) { i_p += red[k]; q_p += red[NSW + k]; }
                 }
                 const float power = i_p * i_p + q_p * q_p;                       // :186
                 const bool locked = power > 15.0f;
                 const bool resets = !locked && lostc + 1u >= 20u;                // reset() this epoch (:199-201)
                 phi = phi_next;
                 if (locked) {
-                    // run_loop_filters, carrier part (:279-290); FAST: reciprocal-multiply division, multiply by 1/(2 pi)
-                    const float pll_err = atanf(__fdividef(q_p, i_p)) * 0.15915494309189535f;
+                    // run_loop_filters, carrier part (:279-290); FAST: one reciprocal, multiply by 1/(2 pi)
+                    const float pll_err = atan_ratio_fast(q_p, i_p) * 0.15915494309189535f;
                     cnco = pll_err * g1 + (pll_err - cerr) * g2;
                     cerr = pll_err;
                     freq += cnco;
                 }
-                if (resets) { freq = 0.f; phi = 0.f; }
-                publish();
+                if (resets) { freq = 0.f; phi = 0.f; pt_next = 0.f; pt_ok = true; }
+                publish(freq, phi, pt_next, pt_ok);
                 // ---- off the critical path
                 i_prompt = i_p;
                 q_prompt = q_p;
@@ -336,6 +404,7 @@ template <int NSW, int U, bool ROT> __global__ void __launch_bounds__((NSW + 2) 
         float six[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         int ran = 0;
         const float g1 = 0.001f / st.dll_tau1, g2 = st.dll_tau2 / st.dll_tau1;    // :298
+        const float fs1023 = fs * 1023.0f;
         // "may this channel consume an epoch now?" -- TrackingChannel::update (do_tracking.rs:160-172)
         auto may_go = [&]() -> int {
             int go = state == GB_TRK_TRACKING;
@@ -344,16 +413,15 @@ template <int NSW, int U, bool ROT> __global__ void __launch_bounds__((NSW + 2) 
             if (n64 == 0 || n64 > (unsigned long long)a.n_max) go = 0;
             return go;
         };
+        // the full evaluation of an epoch's code scalars (first epoch, and whenever the prediction below does not hold)
         auto publish = [&](int go) {
             const int n = (int)n64;
             const float i_end = (float)(((n + U * T - 1) / (U * T)) * (U * T));
             const bool sane = cphase >= 0.f && cphase < 1023.f && step >= 0.f && step * i_end < 2040.f;
             const bool single = cphase + step * i_end < 2046.f;
-            P.code_step = step;
-            P.code_phase = cphase;
-            P.n = n;
+            const int flags = (go ? 1 : 0) | (sane ? 2 : 0) | (sane && single ? 4 : 0);
+            *reinterpret_cast<float4*>(&P.code_step) = make_float4(step, cphase, __int_as_float(n), __int_as_float(flags));
             P.s0 = (unsigned)(next_idx & a.mask);
-            P.flags = (go ? 1 : 0) | (sane ? 2 : 0) | (sane && single ? 4 : 0);
         };
         int go = 0;
         if (lane == 0) {
@@ -364,27 +432,49 @@ template <int NSW, int U, bool ROT> __global__ void __launch_bounds__((NSW + 2) 
         named_sync(BAR_GO, NT);
         named_sync(BAR_X, 64);
         for (int e = 0; go; e++) {
-            float cphase_next = 0.f;
+            // ---- while the sample warps run: everything about the next epoch that does not depend on this epoch's sums.
+            // Its code phase and window start are exact (they use the running epoch's code_rate); its length n' and the
+            // range-check flags depend on the DLL output only through "code_rate' lies in (r_lo, r_hi)", the interval in
+            // which the length stays n and the checks hold -- the critical section then only compares.
+            float cphase_next = 0.f, r_lo = 1.f, r_hi = 0.f, r_single = 0.f;
+            unsigned long long next_idx_next = 0;
+            int go_pred = 0;
             if (lane == 0) {
                 // :265-267 with the code_rate the running epoch uses
-                const float cdp = cphase + step * (float)n64;
+                const float nf = (float)n64;
+                const float cdp = cphase + step * nf;
                 cphase_next = fabsf(cdp) < 1.0e8f ? fmod_small(cdp, 1023.f, 9.775171065493646e-4f) : fmodf(cdp, 1023.f);
+                next_idx_next = next_idx + n64;
+                // n' = round(fs / (code_rate' / 1023)) == n  <=  fs * 1023 / code_rate' in (n - 0.45, n + 0.45)
+                r_lo = fs1023 / (nf + 0.45f);
+                r_hi = fs1023 / (nf - 0.45f);
+                const int n = (int)n64;
+                const float i_end = (float)(((n + U * T - 1) / (U * T)) * (U * T));
+                // step' * i_end < 2040 and cphase' + step' * i_end < 2046, as bounds on code_rate' (a little inside)
+                const float r_sane = (2038.f / i_end) * fs;
+                r_single = (((2046.f - cphase_next) / i_end) * fs) * 0.999999f;
+                if (r_sane < r_hi) r_hi = r_sane;
+                if (!(cphase_next >= 0.f && cphase_next < 1023.f) || n64 >= 100000ull) r_hi = 0.f;   // no fast path
+                const unsigned long long saved_idx = next_idx;
+                next_idx = next_idx_next;
+                go_pred = (e + 1 < a.n_epochs) ? may_go() : 0;                    // with n' = n, state unchanged
+                next_idx = saved_idx;
             }
             named_sync(BAR_PART, NT);
             if (lane == 0) {
 #pragma unroll
                 for (int k = 0; k < 6; k++) {
                     if (NSW % 4 == 0) {
-                        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+                        float4 u = *reinterpret_cast<const float4*>(red + k * NSW);
 #pragma unroll
-                        for (int j = 0; j < NSW / 4; j++) {
-                            const float4 u = *reinterpret_cast<const float4*>(red + k * NSW + 4 * j);
-                            a0 += u.x; a1 += u.y; a2 += u.z; a3 += u.w;
+                        for (int j = 1; j < NSW / 4; j++) {
+                            const float4 u2 = *reinterpret_cast<const float4*>(red + k * NSW + 4 * j);
+                            u.x += u2.x; u.y += u2.y; u.z += u2.z; u.w += u2.w;
                         }
-                        six[k] = (a0 + a1) + (a2 + a3);
+                        six[k] = (u.x + u.y) + (u.z + u.w);
                     } else {
-                        float s = 0.f;
-                        for (int j = 0; j < NSW; j++) s += red[k * NSW + j];
+                        float s = red[k * NSW];
+                        for (int j = 1; j < NSW; j++) s += red[k * NSW + j];
                         six[k] = s;
                     }
                 }
@@ -396,7 +486,7 @@ template <int NSW, int U, bool ROT> __global__ void __launch_bounds__((NSW + 2) 
                     // run_loop_filters, code part (:291-301); FAST: approximate square roots and division (2 ulp)
                     const float pow_e = sqrt_fast(i_e * i_e + q_e * q_e);
                     const float pow_l = sqrt_fast(i_l * i_l + q_l * q_l);
-                    const float dll_err = ((pow_e + pow_l) != 0.f) ? __fdividef(pow_e - pow_l, pow_e + pow_l) : 0.f;
+                    const float dll_err = ((pow_e + pow_l) != 0.f) ? (pow_e - pow_l) * rcp_fast(pow_e + pow_l) : 0.f;
                     cnco = dll_err * g1 + (dll_err - cerr) * g2;
                     cerr = dll_err;
                     crate += cnco;
@@ -406,36 +496,34 @@ template <int NSW, int U, bool ROT> __global__ void __launch_bounds__((NSW + 2) 
                 } else {
                     lostc += 1;
                 }
-                if (resets) {                                                     // reset(), code / bookkeeping fields
-                    prn = 0; code_row = 0; state = GB_TRK_IDLE;
-                    next_idx = 0;
-                    cphase = 0.f; cerr = 0.f; cnco = 0.f; crate = 0.f;
-                } else {
-                    cphase = cphase_next;
-                    next_idx += n64;
-                    {
-                        // round(fs / (code_rate / 1023)) as usize (:165 via generate_ca_code_samples' length): the quotient
-                        // from one reciprocal is within 2e-7 relative of the f32 double division, so away from a half-way
-                        // value both round to the same integer; otherwise the reference's two IEEE divisions decide
-                        const float qa = (fs * 1023.0f) * rcp_fast(crate);
-                        const float qr = rintf(qa);
-                        if (qa > 0.5f && qa < 2.0e5f && fabsf(qa - qr) < 0.45f) {
-                            n64 = (unsigned long long)(unsigned)qr;
-                        } else {
-                            const float spc = roundf(fs / (crate / 1023.0f));
-                            n64 = (spc >= 0.f && spc < 2.0e9f) ? (unsigned long long)(unsigned)spc : f32_as_usize(spc);
-                        }
-                    }
-                }
                 // (code_rate / fs): reciprocal + exact-residual correction = the correctly rounded quotient
-                {
-                    const float q0 = crate * rcp_fs;
-                    step = fmaf(fmaf(-q0, fs, crate), rcp_fs, q0);
+                const float q0 = crate * rcp_fs;
+                step = fmaf(fmaf(-q0, fs, crate), rcp_fs, q0);
+                if (!resets && crate > r_lo && crate < r_hi) {
+                    // the prediction holds: n' = n, chip arguments in range, go as predicted
+                    cphase = cphase_next;
+                    next_idx = next_idx_next;
+                    go = go_pred;
+                    const int flags = (go ? 1 : 0) | 2 | (crate < r_single ? 4 : 0);
+                    *reinterpret_cast<float4*>(&P.code_step) = make_float4(step, cphase, __int_as_float((int)n64), __int_as_float(flags));
+                    P.s0 = (unsigned)(next_idx & a.mask);
+                } else {
+                    if (resets) {                                                 // reset(), code / bookkeeping fields
+                        prn = 0; code_row = 0; state = GB_TRK_IDLE;
+                        next_idx = 0;
+                        cphase = 0.f; cerr = 0.f; cnco = 0.f; crate = 0.f; step = 0.f;
+                    } else {
+                        cphase = cphase_next;
+                        next_idx = next_idx_next;
+                        // round(fs / (code_rate / 1023)) as usize (:165 via generate_ca_code_samples' length)
+                        const float spc = roundf(fs / (crate / 1023.0f));
+                        n64 = (spc >= 0.f && spc < 2.0e9f) ? (unsigned long long)(unsigned)spc : f32_as_usize(spc);
+                    }
+                    go = (e + 1 < a.n_epochs) ? may_go() : 0;
+                    publish(go);
                 }
                 epochs_done += 1;
                 ran += 1;
-                go = (e + 1 < a.n_epochs) ? may_go() : 0;
-                publish(go);
             }
             go = __shfl_sync(0xffffffffu, go, 0);
             named_sync(BAR_GO, NT);
@@ -456,10 +544,10 @@ template <int NSW, int U, bool ROT> __global__ void __launch_bounds__((NSW + 2) 
     if (tid == 0) a.ch[c] = st;
 }
 
-template <int NSW, int U, bool ROT> static cudaError_t launch_ws(const TrkArgs& a, cudaStream_t st)
+template <int NSW, int U, int NSFU> static cudaError_t launch_ws(const TrkArgs& a, cudaStream_t st)
 {
     const size_t smem = 1024 * sizeof(float4) + 1024 * sizeof(float) + 6 * NSW * sizeof(float) + 64;
-    trk_ws_kernel<NSW, U, ROT><<<a.n_channels, (NSW + 2) * 32, smem, st>>>(a);
+    trk_ws_kernel<NSW, U, NSFU><<<a.n_channels, (NSW + 2) * 32, smem, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -468,23 +556,23 @@ bool trk_ws_supported(const TrkArgs& a)
     return a.filters && a.offsets == nullptr && a.mask != ~0ull && a.mask < (1ull << 32);
 }
 
-// variant: 0 = by channel count, else NSW * 100 + U * 10 + ROT (tuning, gb_tuning_set("trk_ws", v))
+// variant: 0 = by channel count, else NSW * 100 + U * 10 + NSFU (tuning, gb_tuning_set("trk_ws", v))
 cudaError_t trk_ws_launch(const TrkArgs& a, cudaStream_t st, int variant)
 {
     if (a.n_channels <= 0) return cudaSuccess;
     switch (variant) {
-    case 880: return launch_ws<8, 8, false>(a, st);
-    case 881: return launch_ws<8, 8, true>(a, st);
-    case 1640: return launch_ws<16, 4, false>(a, st);
-    case 1641: return launch_ws<16, 4, true>(a, st);
-    case 480: return launch_ws<4, 8, false>(a, st);
-    case 481: return launch_ws<4, 8, true>(a, st);
-    case 441: return launch_ws<4, 4, true>(a, st);
-    case 281: return launch_ws<2, 8, true>(a, st);
+    case 888: return launch_ws<8, 8, 8>(a, st);
+    case 884: return launch_ws<8, 8, 4>(a, st);
+    case 882: return launch_ws<8, 8, 2>(a, st);
+    case 881: return launch_ws<8, 8, 1>(a, st);
+    case 1644: return launch_ws<16, 4, 4>(a, st);
+    case 1642: return launch_ws<16, 4, 2>(a, st);
+    case 488: return launch_ws<4, 8, 8>(a, st);
+    case 482: return launch_ws<4, 8, 2>(a, st);
+    case 481: return launch_ws<4, 8, 1>(a, st);
     default: break;
     }
-    if (a.n_channels > 300) return launch_ws<4, 8, true>(a, st);
-    return launch_ws<8, 8, false>(a, st);
+    return launch_ws<8, 8, 8>(a, st);
 }
 
 }  // namespace gb
