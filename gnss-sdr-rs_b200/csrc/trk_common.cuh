@@ -80,6 +80,30 @@ __device__ __forceinline__ pk64 fma2s(pk64 a, float s, pk64 c)
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(pk2(s, s)), "l"(c));
     return r;
 }
+__device__ __forceinline__ pk64 add2(pk64 a, pk64 b)
+{
+    pk64 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ pk64 add2_rm(pk64 a, pk64 b)   // round towards -inf (floor through the 2^23 magic constant)
+{
+    pk64 r;
+    asm("add.rm.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ pk64 mul2(pk64 a, pk64 b)
+{
+    pk64 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ pk64 fma2(pk64 a, pk64 b, pk64 c)
+{
+    pk64 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
 __device__ __forceinline__ float4 lds_f32x4(unsigned addr)
 {
     float4 v;

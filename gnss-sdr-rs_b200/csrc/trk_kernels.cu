@@ -441,7 +441,7 @@ cudaError_t trk_launch(const TrkArgs& a0, int mode, cudaStream_t st)
     TrkArgs a = a0;
     a.dbg = tuning("trk_dbg", 0);
     const int ws = tuning("trk_ws", 0);
-    if (mode == GB_TRK_FAST && trk_ws_supported(a) && (ws > 0 || (ws == 0 && a.n_channels <= 300))) return trk_ws_launch(a, st, ws);
+    if (mode == GB_TRK_FAST && ws >= 0 && trk_ws_supported(a)) return trk_ws_launch(a, st, ws);
     switch (tuning("trk_t", 0)) {
     case 64: return launch_t<64>(a, mode, st);
     case 128: return launch_t<128>(a, mode, st);

@@ -142,10 +142,11 @@ template <int NSW, int U, int NSFU> __global__ void __launch_bounds__((NSW + 2) 
                 for (int u = 0; u < U; u++) v[u] = __ldg(smp + ((base + (unsigned)(tid + u * T)) & mask32));
             }
         };
-        // One epoch on the batch already in `cur`; the batch that follows (this epoch's next one, or the first of the
-        // next epoch's window: it starts at start + n whatever the filters decide) is loaded into `nxt` meanwhile.
-        // Returns false when the channel stops.  Called alternately with (xa, xb) and (xb, xa): no register copies.
-        auto epoch = [&](float2(&cur)[U], float2(&nxt)[U]) -> bool {
+        // One epoch on the batch already in `cur`.  The first batch of the NEXT epoch's window (it starts at start + n
+        // whatever the filters decide) is loaded into the same registers as soon as this epoch's arithmetic has consumed
+        // them.  Returns false when the channel stops.
+        float2 cur[U];
+        auto epoch = [&]() -> bool {
             const float4 pc4 = *reinterpret_cast<const float4*>(&P.f_turn);
             const float4 pd4 = *reinterpret_cast<const float4*>(&P.code_step);
             const float f_turn = pc4.x, cp_turn = pc4.y, w = pc4.z, carrier_phase = pc4.w;
@@ -162,8 +163,6 @@ template <int NSW, int U, int NSFU> __global__ void __launch_bounds__((NSW + 2) 
             }
             const bool fastp = (flags & 2) && carr_ok;
             const bool single_wrap = flags & 4;
-            // the window after next: into L2 now (its first touch would otherwise pay the DRAM latency inside an epoch)
-            if (!(a.dbg & 1) && tid * 16 < n + 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(smp + ((s0 + 2u * (unsigned)n + 16u * (unsigned)tid) & mask32)));
             float ip = 0.f, qp = 0.f, ie = 0.f, qe = 0.f, il = 0.f, ql = 0.f;
             pk64 accp = pk2(0.f, 0.f), acce = accp, accl = accp;
             auto compute_batch = [&](int b0) {
@@ -175,42 +174,61 @@ template <int NSW, int U, int NSFU> __global__ void __launch_bounds__((NSW + 2) 
                 }
                 const float fbase = (float)base;
                 if (fastp) {
-                    float cs[U], sn[U];
+                    // Packed FP32 (FFMA2 / FADD2 / FMUL2): the carrier is kept as (cos, sin) pairs, the wiped sample as a
+                    // (re, im) pair, and the chip arguments of two consecutive samples of the thread share every add --
+                    // each lane rounds exactly like the scalar instruction.
+                    pk64 cs2[U];
+                    const pk64 wc2 = pk2(wc, wc), ws2 = pk2(ws, ws);
 #pragma unroll
                     for (int u = 0; u < U; u++) {
                         if (u % CHAIN == 0) {
                             const float fi = fbase + (float)(u * T);   // exact: integers below 2^24
                             const float ut = fmaf(fi, f_turn, cp_turn);
                             const float r = (ut - rint_small(ut)) * c1;        // [-pi, pi]
-                            cs[u] = __cosf(r);
-                            sn[u] = __sinf(r);
+                            cs2[u] = pk2(__cosf(r), __sinf(r));
                         } else {
-                            cs[u] = fmaf(cs[u - 1], wc, -(sn[u - 1] * ws));
-                            sn[u] = fmaf(sn[u - 1], wc, cs[u - 1] * ws);
+                            float cv, sv;
+                            upk2(cs2[u - 1], cv, sv);
+                            cs2[u] = fma2(pk2(-sv, cv), ws2, mul2(cs2[u - 1], wc2));   // rotate by the advance over T samples
                         }
                     }
                     auto body = [&](auto sw) {
+                        const pk64 fb2 = pk2(fbase, fbase), st2 = pk2(code_step, code_step), cp2 = pk2(code_phase, code_phase);
 #pragma unroll
-                        for (int u = 0; u < U; u++) {
-                            const float fi = fbase + (float)(u * T);
-                            const float re = fmaf(cur[u].x, cs[u], cur[u].y * sn[u]);
-                            const float im = fmaf(cur[u].y, cs[u], -(cur[u].x * sn[u]));
-                            float tc = code_phase + (fi * code_step);
-                            tc = tc >= 1023.f ? tc - 1023.f : tc;
-                            if (!decltype(sw)::value) tc = tc >= 1023.f ? tc - 1023.f : tc;
+                        for (int u = 0; u < U; u += 2) {
+                            const pk64 fi2 = add2(fb2, pk2((float)(u * T), (float)((u + 1) * T)));
+                            float t0, t1;
+                            upk2(add2(cp2, mul2(fi2, st2)), t0, t1);              // code_phase + (i * code_step)
+                            t0 = t0 >= 1023.f ? t0 - 1023.f : t0;
+                            t1 = t1 >= 1023.f ? t1 - 1023.f : t1;
+                            if (!decltype(sw)::value) {
+                                t0 = t0 >= 1023.f ? t0 - 1023.f : t0;
+                                t1 = t1 >= 1023.f ? t1 - 1023.f : t1;
+                            }
                             // floor(tc) sits in the mantissa of the round-down add; early / late chips are
                             // floor(tc + 0.5) % 1023 in {k, k+1} and max(floor(tc - 0.5), 0) in {k-1, k} (Q7), decided on
                             // the reference's own f32 sums tc + 0.5 and tc - 0.5
-                            const float pf = __fadd_rd(tc, 8388608.0f);
-                            const float4 q = lds_f32x4(16u * (unsigned)__float_as_int(pf) + row4_bias);
-                            const float fl = pf - 8388608.0f;                     // exact
-                            const float pcv = q.y;
-                            const float ec = (tc + 0.5f) >= (fl + 1.0f) ? q.z : q.y;
-                            const float lc = (tc - 0.5f) >= fl ? q.y : q.x;
-                            const pk64 z = pk2(re, im);
-                            accp = fma2s(z, pcv, accp);
-                            acce = fma2s(z, ec, acce);
-                            accl = fma2s(z, lc, accl);
+                            const pk64 tc2 = pk2(t0, t1);
+                            const pk64 pf2 = add2_rm(tc2, pk2(8388608.0f, 8388608.0f));
+                            const pk64 fl2 = add2(pf2, pk2(-8388608.0f, -8388608.0f));   // exact
+                            const pk64 hi2 = add2(tc2, pk2(0.5f, 0.5f)), lo2 = add2(tc2, pk2(-0.5f, -0.5f));
+                            const pk64 fl1 = add2(fl2, pk2(1.0f, 1.0f));
+                            float pf[2], fl[2], hi[2], lo[2], f1[2];
+                            upk2(pf2, pf[0], pf[1]); upk2(fl2, fl[0], fl[1]); upk2(hi2, hi[0], hi[1]);
+                            upk2(lo2, lo[0], lo[1]); upk2(fl1, f1[0], f1[1]);
+#pragma unroll
+                            for (int k = 0; k < 2; k++) {
+                                const float4 q = lds_f32x4(16u * (unsigned)__float_as_int(pf[k]) + row4_bias);
+                                const float ec = hi[k] >= f1[k] ? q.z : q.y;
+                                const float lc = lo[k] >= fl[k] ? q.y : q.x;
+                                float cv, sv;
+                                upk2(cs2[u + k], cv, sv);
+                                const float2 x = cur[u + k];
+                                const pk64 z = fma2(pk2(x.y, -x.x), pk2(sv, sv), mul2(pk2(x.x, x.y), pk2(cv, cv)));   // x * (cos, -sin)
+                                accp = fma2s(z, q.y, accp);
+                                acce = fma2s(z, ec, acce);
+                                accl = fma2s(z, lc, accl);
+                            }
                         }
                     };
                     if (single_wrap) body(std::true_type{});
@@ -247,20 +265,22 @@ template <int NSW, int U, int NSFU> __global__ void __launch_bounds__((NSW + 2) 
             if (n <= U * T) {
                 // One batch per epoch (the latency-critical case: 2.048 Msps on 8 x 256 threads).  The next window's loads
                 // are issued AFTER the arithmetic: a scoreboard wait covers every load in flight on that scoreboard, so
-                // loads issued before the first use of `cur` would make that use wait for them too.  They have the
-                // reduction, the control section and the next epoch's start-up to arrive.
+                // loads issued before the first use of `cur` would make that use wait for them too (and a predicated-off
+                // register copy waits as well).  They have the reduction, the control section and the next epoch's
+                // start-up to arrive.
                 compute_batch(0);
-                load_batch(nxt, s0 + (unsigned)n);
+                load_batch(cur, s0 + (unsigned)n);
             } else {
                 // several batches per epoch: the next batch (or the next window's first one) is loaded while this one is
                 // being computed
+                float2 nxt[U];
                 for (int b0 = 0;; b0 += U * T) {
                     const bool last = b0 + U * T >= n;
                     load_batch(nxt, last ? s0 + (unsigned)n : s0 + (unsigned)(b0 + U * T));
                     compute_batch(b0);
-                    if (last) break;
 #pragma unroll
                     for (int u = 0; u < U; u++) cur[u] = nxt[u];
+                    if (last) break;
                 }
             }
             if (fastp) {
@@ -286,14 +306,10 @@ template <int NSW, int U, int NSFU> __global__ void __launch_bounds__((NSW + 2) 
             named_sync(BAR_GO, NT);
             return P.flags & 1;
         };
-        float2 xa[U], xb[U];
         named_sync(BAR_GO, NT);
         if (P.flags & 1) {
-            load_batch(xa, P.s0);
-            while (true) {
-                if (!epoch(xa, xb)) break;
-                if (!epoch(xb, xa)) break;
-            }
+            load_batch(cur, P.s0);
+            while (epoch()) {}
         }
     } else if (warp == NSW) {
         // ------------------------------------------------------------------------------------------- carrier warp
@@ -461,23 +477,27 @@ template <int NSW, int U, int NSFU> __global__ void __launch_bounds__((NSW + 2) 
                 next_idx = saved_idx;
             }
             named_sync(BAR_PART, NT);
-            if (lane == 0) {
+            {
+                // lane k < 6 sums the per-warp partials of sum k; squares meet their partner through one shuffle, the
+                // three results (prompt power, |E|^2, |L|^2) and the six sums are then gathered on lane 0
+                const int k = lane < 6 ? lane : 0;
+                float v;
+                if (NSW % 4 == 0) {
+                    float4 u = *reinterpret_cast<const float4*>(red + k * NSW);
 #pragma unroll
-                for (int k = 0; k < 6; k++) {
-                    if (NSW % 4 == 0) {
-                        float4 u = *reinterpret_cast<const float4*>(red + k * NSW);
-#pragma unroll
-                        for (int j = 1; j < NSW / 4; j++) {
-                            const float4 u2 = *reinterpret_cast<const float4*>(red + k * NSW + 4 * j);
-                            u.x += u2.x; u.y += u2.y; u.z += u2.z; u.w += u2.w;
-                        }
-                        six[k] = (u.x + u.y) + (u.z + u.w);
-                    } else {
-                        float s = red[k * NSW];
-                        for (int j = 1; j < NSW; j++) s += red[k * NSW + j];
-                        six[k] = s;
+                    for (int j = 1; j < NSW / 4; j++) {
+                        const float4 u2 = *reinterpret_cast<const float4*>(red + k * NSW + 4 * j);
+                        u.x += u2.x; u.y += u2.y; u.z += u2.z; u.w += u2.w;
                     }
+                    v = (u.x + u.y) + (u.z + u.w);
+                } else {
+                    v = red[k * NSW];
+                    for (int j = 1; j < NSW; j++) v += red[k * NSW + j];
                 }
+#pragma unroll
+                for (int j = 0; j < 6; j++) six[j] = __shfl_sync(0xffffffffu, v, j);
+            }
+            if (lane == 0) {
                 const float i_p = six[0], q_p = six[1], i_e = six[2], q_e = six[3], i_l = six[4], q_l = six[5];
                 const float power = i_p * i_p + q_p * q_p;                        // :186
                 const bool locked = power > 15.0f;
@@ -572,7 +592,10 @@ cudaError_t trk_ws_launch(const TrkArgs& a, cudaStream_t st, int variant)
     case 481: return launch_ws<4, 8, 1>(a, st);
     default: break;
     }
-    return launch_ws<8, 8, 8>(a, st);
+    // up to two channels per SM: 8 sample warps per channel (latency regime, one batch per epoch at 2.048 Msps); more:
+    // 4 sample warps (throughput regime).  Carrier by rotation in both (measured: tools/time_trk.py).
+    if (a.n_channels <= 296) return launch_ws<8, 8, 1>(a, st);
+    return launch_ws<4, 8, 1>(a, st);
 }
 
 }  // namespace gb
