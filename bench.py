@@ -174,54 +174,185 @@ def workload_config():
                         "50 Hz Doppler step (+-5 kHz, D=201), 200 ms recording per step",
             "fft_size": N_FFT, "n_prn": N_PRN, "n_doppler": len(DOPPLERS), "n_coherent": N_COH,
             "n_noncoherent": N_NONCOH, "cells_per_step": N_PRN * len(DOPPLERS) * N_FFT,
-            "l2": "flushed between timed steps (256 MiB write)", "sharding": "one recording per GPU + NCCL all_gather"}
+            "l2": "flushed between timed steps (256 MiB write)",
+            "sharding": "one recording per GPU and step; ONE final all-gather of the per-PRN result tables of the whole batch "
+                        "(gb_group_gather_results: ncclAllGather inside libgnss_b200)",
+            "doppler_aliasing": "on (explicitly; the library default is the reference's per-bin tables)"}
 
 
-def tracking_numbers(hd, ffi, n_channels=1024, n_epochs=1000, want_state=False):
-    """BASELINE configs[2] shape, shortened: 1024 channels (32 PRN-slots x 32 hand-over perturbations) on one shared
-    2.048 Msps stream, persistent kernel, FAST mode.  Returns channel-epochs/s from the kernel's CUDA events."""
-    from gnss_sdr_rs_b200 import ring, sdr_mock, tracking
-    fs, n = 2.048e6, 2048
-    prns = [2, 5, 9, 12, 17, 21, 25, 30]
-    sats = [{"prn": p, "doppler": float(-2000 + 500 * i), "code_phase": 137 * (i + 1), "cn0_dbhz": 48.0}
-            for i, p in enumerate(prns)]
-    base_ms = 100
-    # periodic construction: Dopplers are multiples of 10 Hz and there is no code Doppler, so a 100 ms tile repeats
-    tile = np.zeros(n * base_ms, np.complex64)
-    rng = np.random.default_rng(0x6E57)
-    t = np.arange(n * base_ms, dtype=np.float64)
+TRK_FS, TRK_N = 2.048e6, 2048
+TRK_TILE_MS = 100
+
+
+def tracking_stream(n_ms, seed=0x6E57):
+    """BASELINE configs[2] / SURVEY 8d config 3: ONE shared 2.048 Msps complex stream carrying all 32 GPS PRNs at
+    48 dB-Hz (Dopplers multiples of 10 Hz, integer-sample code phases, no code Doppler, so a 100 ms tile repeats exactly)
+    in unit-variance noise that is fresh for every tile.  Returns (complex64 samples, satellite list)."""
+    from gnss_sdr_rs_b200 import sdr_mock
+    fs, n = TRK_FS, TRK_N
+    sats = [{"prn": p, "doppler": float(-4000 + 250 * (p - 1)), "code_phase": (137 * p) % n, "cn0_dbhz": 48.0}
+            for p in range(1, 33)]
+    tile = np.zeros(n * TRK_TILE_MS, np.complex64)
+    t = np.arange(n * TRK_TILE_MS, dtype=np.float64)
     for s in sats:
         code = sdr_mock.ca_code(s["prn"]).astype(np.float64)
         chip = ((t - s["code_phase"]) * 1.023e6 / fs) % 1023.0
         amp = np.sqrt(10.0 ** (s["cn0_dbhz"] / 10.0) / fs)
         tile += (amp * code[np.floor(chip).astype(np.int64) % 1023]
                  * np.exp(2j * np.pi * ((s["doppler"] * t / fs) % 1.0))).astype(np.complex64)
-    reps = (n_epochs + 2 + base_ms - 1) // base_ms + 1
-    rb = ring.MulticastRingBuffer(hd, 1 << int(math.ceil(math.log2(n * base_ms * reps))))
+    reps = (n_ms + TRK_TILE_MS - 1) // TRK_TILE_MS
+    rng = np.random.default_rng(seed)
+    x = np.empty(reps * len(tile), np.complex64)
+    xv = x.view(np.float32).reshape(reps, -1)
+    scale = np.float32(1 / np.sqrt(2))
     for r in range(reps):
-        noise = (rng.standard_normal(len(tile)) + 1j * rng.standard_normal(len(tile))).astype(np.complex64) * np.float32(
-            1 / np.sqrt(2))
-        rb.write_samples(tile + noise)
-    ch = tracking.channel_array(n_channels, fs)
+        xv[r] = rng.standard_normal(2 * len(tile), dtype=np.float32) * scale
+    x.reshape(reps, -1)[:] += tile
+    return x[:n * n_ms], sats
+
+
+def tracking_channels(n_channels, sats, seed=0x6E58, reference_row=False):
+    """n_channels = the 32 PRNs x (n_channels / 32) perturbations of the acquisition hand-over: carrier +-50 Hz, code
+    phase 0..0.3 chip.  reference_row: the reference's get_ca_chip row (prn, Q6) instead of the satellite's."""
+    from gnss_sdr_rs_b200 import tracking
+    rng = np.random.default_rng(seed)
+    ch = tracking.channel_array(n_channels, TRK_FS)
     for c in range(n_channels):
         s = sats[c % len(sats)]
         tracking.start(ch[c], s["prn"], s["doppler"] + float(rng.uniform(-50, 50)), float(rng.uniform(0, 0.3)),
-                       s["code_phase"], fs, code_row=s["prn"] - 1)
+                       s["code_phase"], TRK_FS, corrected=not reference_row)
+    return ch
+
+
+def tracking_numbers(hd, ffi, n_channels=1024, n_epochs=1000, want_state=False, mode=0, reference_row=False, stream=None):
+    """BASELINE configs[2] shape: n_channels channels on one shared 2.048 Msps stream resident in the HBM ring,
+    persistent kernel, loop filters on the device.  Returns channel-epochs/s from the kernel's CUDA events."""
+    from gnss_sdr_rs_b200 import ring, tracking
+    n = TRK_N
+    x, sats = stream if stream is not None else tracking_stream(n_epochs + 22)
+    assert len(x) >= (n_epochs + 22) * n
+    rb = ring.MulticastRingBuffer(hd, 1 << int(math.ceil(math.log2(len(x)))))
+    step = n * 2000
+    for i in range(0, len(x), step):
+        rb.write_samples(x[i:i + step])
+    ch = tracking_channels(n_channels, sats, reference_row=reference_row)
+    if reference_row:   # PRN 32 has no row 32 in the reference's table (it panics there): keep those channels out
+        for c in range(n_channels):
+            if ch[c].code_row >= 32:
+                ch[c].state = 0
     eng = tracking.TrackingEngine(hd)
     eng.upload(ch)
-    eng.run(20)  # warm-up epochs
-    eng.run(n_epochs)
+    eng.run(20, mode=mode)  # warm-up epochs
+    eng.run(n_epochs, mode=mode)
     ms = eng.last_kernel_ms()
     eng.download(ch)
-    locked = sum(1 for c in range(n_channels) if ch[c].state == 1)
-    done = sum(int(ch[c].epochs_done) for c in range(n_channels)) - 20 * n_channels
+    active = sum(1 for c in range(n_channels) if ch[c].state == 1)
+    done = sum(int(ch[c].epochs_done) for c in range(n_channels)) - 20 * sum(1 for c in range(n_channels) if ch[c].epochs_done >= 20)
     out = {"metric": "tracking_channel_epochs_per_sec", "value": done / (ms * 1e-3), "unit": "channel-epochs/s",
-           "channels": n_channels, "epochs": n_epochs, "kernel_ms": ms, "locked_channels": locked,
-           "x_realtime": (n_epochs * 1e-3) / (ms * 1e-3), "mode": "fast (persistent kernel, on-device loop filters)",
-           "fs": fs}
+           "channels": n_channels, "epochs": n_epochs, "kernel_ms": ms, "locked_channels": active,
+           "us_per_epoch": ms * 1e3 / n_epochs,
+           "x_realtime": (n_epochs * 1e-3) / (ms * 1e-3),
+           "mode": ("fast" if mode == 0 else "ordered") + " (persistent kernel, on-device loop filters)",
+           "code_row": "prn (reference quirk Q6)" if reference_row else "prn - 1 (corrected)",
+           "layout": "32 PRNs x %d hand-over perturbations on one shared stream" % max(1, n_channels // 32), "fs": TRK_FS}
     if want_state:
         out["state"], out["sats"] = ch, sats
     return out
+
+
+def tracking_roofline(r, peak_tf):
+    """a channel-epoch is N x (6 cmul-flops + 12 E/P/L MAC-flops + ~8 index / phase flops) = 26 N flops plus
+    N sin/cos pairs (reported separately: the FAST kernel evaluates one pair per thread and epoch through the SFU and
+    rotates the rest, 4 FMA-equivalents per sample that the 26 N figure does not credit).  Bound: FP32 issue."""
+    flops = 26.0 * TRK_N
+    achieved = r["value"] * flops / 1e12
+    return {"bound": "fp32", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None,
+            "flops_per_channel_epoch": flops, "sincos_per_channel_epoch": TRK_N,
+            "kernel": "trk_ws_kernel<4,8,1> (4 sample warps + carrier warp + code warp per channel)" if r["channels"] > 296
+                      else "trk_ws_kernel<8,8,1> (8 sample warps + carrier warp + code warp per channel)",
+            "bytes_per_channel_epoch": {"l2": 8 * TRK_N, "hbm_unique_per_stream_epoch": 8 * TRK_N, "state": 88},
+            "peak_source": "gb_bench_fp32_tflops FMA probe, measured live"}
+
+
+def tracking_cpu_baseline(stream, cores, n_epochs=400):
+    """The oracle's TrackingManager loop (go_trk_run_all: do_work per channel and epoch, channels spread over all host
+    threads like rayon at do_tracking.rs:364-371) on a bounded sample: 4 channels per thread, n_epochs epochs."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pyoracle as orc
+    x, sats = stream
+    n_ch = max(32, 4 * cores)
+    rng = np.random.default_rng(0x6E58)
+    och = (orc.TrkChannel * n_ch)()
+    for c in range(n_ch):
+        s = sats[c % len(sats)]
+        oc = orc.trk_channel(c, TRK_FS)
+        orc.trk_start(oc, s["prn"], s["doppler"] + float(rng.uniform(-50, 50)), float(rng.uniform(0, 0.3)), s["code_phase"], TRK_FS)
+        oc.code_row = s["prn"] - 1
+        och[c] = oc
+    t0 = time.perf_counter()
+    orc.trk_run_all(och, x[:(n_epochs + 2) * TRK_N], n_epochs, n_threads=cores, want_hist=False)
+    dt = time.perf_counter() - t0
+    return {"value": n_ch * n_epochs / dt, "unit": "channel-epochs/s", "cores": cores, "kind": "port",
+            "sample": "%d channels x %d epochs of the same stream, %.1f s" % (n_ch, n_epochs, dt),
+            "x_realtime_1024ch": (n_ch * n_epochs / dt) / 1024.0 / 1000.0}
+
+
+def tracking_e2e(hd, ffi, stream, n_channels=1024, n_ms=2000, chunk_ms=100):
+    """End to end through the public calls with HOST samples: a writer thread feeds the stream chunk by chunk from pinned
+    host memory into the HBM ring (gb_ring_write: staged cudaMemcpyAsync on the copy stream) while the tracking thread
+    runs gb_trk_run on whatever the ring already holds (do_tracking.rs:160-180: update() waits for head >= next + n).
+    Every sample crosses PCIe inside the timed region; state comes back with gb_trk_download at the end."""
+    import torch
+    from gnss_sdr_rs_b200 import ring, tracking
+    x, sats = stream
+    n = TRK_N
+    n_ms = min(n_ms, len(x) // n - 2)
+    x_pin = torch.from_numpy(x[:n * (n_ms + 1)].view(np.float32).copy()).pin_memory().numpy().view(np.complex64)
+    rb = ring.MulticastRingBuffer(hd, 1 << int(math.ceil(math.log2(n * (n_ms + 2)))))
+    ch = tracking_channels(n_channels, sats)
+    eng = tracking.TrackingEngine(hd)
+    rb.write_samples(x_pin[:n * 30])
+    eng.upload(ch)
+    eng.run(20)   # warm-up on the first 30 ms
+    written = [30 * n]
+    err = []
+
+    def writer():
+        try:
+            pos = 30 * n
+            while pos < len(x_pin):
+                k = min(chunk_ms * n, len(x_pin) - pos)
+                rb.write_samples(x_pin[pos:pos + k])
+                pos += k
+                written[0] = pos
+        except Exception as e:
+            err.append(e)
+
+    hd.call("gb_synchronize")
+    t0 = time.perf_counter()
+    th = threading.Thread(target=writer)
+    th.start()
+    target = n_ms - 2
+    done = 20
+    while done < target and not err:
+        avail = written[0] // n - 2 - done          # epochs whose samples are in the ring for every channel
+        if avail <= 0:
+            time.sleep(0)
+            continue
+        eng.run(min(avail, target - done))
+        done += min(avail, target - done)
+    th.join()
+    eng.download(ch)
+    dt = time.perf_counter() - t0
+    if err:
+        raise err[0]
+    epochs = sum(int(ch[c].epochs_done) for c in range(n_channels)) - 20 * n_channels
+    return {"value": epochs / dt, "unit": "channel-epochs/s", "channels": n_channels, "ms_of_signal": n_ms - 22,
+            "wall_ms": dt * 1e3, "x_realtime": (epochs / n_channels) * 1e-3 / dt,
+            "h2d_bytes_per_step": int(8 * n * chunk_ms), "d2h_bytes_per_step": 0, "step": "%d ms chunk" % chunk_ms,
+            "d2h_bytes_total": int(88 * n_channels),
+            "locked_channels": sum(1 for c in range(n_channels) if ch[c].state == 1),
+            "api": "gb_ring_write (writer thread, pinned host chunks) || gb_trk_run (tracking thread) on one handle"}
 
 
 def extra_numbers(hd, ffi):
@@ -289,7 +420,55 @@ def extra_numbers(hd, ffi):
     return out
 
 
+def decision_margins(cells_row, fft_size, threshold=7.0):
+    """search_satellite's early-exit scan (Q1) on one PRN's cells: returns (deciding bin or -1, the metric there,
+    min |metric - threshold| over the bins the scan visits) -- the margin SURVEY 7 asks for near-threshold decisions."""
+    gmax, gsum, margin = 0.0, 0.0, float("inf")
+    for d in range(len(cells_row)):
+        pk = float(cells_row["peak"][d])
+        if pk > gmax:
+            gmax, gsum = pk, float(cells_row["sum8"][d])
+        if gmax > 0:
+            metric = gmax / ((gsum - gmax) / (fft_size - 1))
+            margin = min(margin, abs(metric - threshold))
+            if metric > threshold:
+                return d, metric, margin
+    return -1, None, margin
+
+
+class NcclGroup:
+    """The library's own collective (gb_group_*: NCCL loaded inside libgnss_b200, one ncclAllGather on the group's
+    stream); torch.distributed only carries the 128-byte unique id to the peers."""
+
+    def __init__(self, hd, ffi, dist, rank, world, device):
+        import ctypes as C
+        import torch
+        self.hd, self.ffi, self.world, self.C = hd, ffi, world, C
+        idt = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            buf = (C.c_uint8 * 128)()
+            ffi.check(hd.L.gb_group_unique_id(buf), "gb_group_unique_id")
+            idt = torch.tensor(list(buf), dtype=torch.uint8)
+        idt = idt.to(device)
+        dist.broadcast(idt, 0)
+        ids = (C.c_uint8 * 128)(*idt.cpu().tolist())
+        self.g = C.c_void_p()
+        ffi.check(hd.L.gb_group_init(hd.h, ids, rank, world, C.byref(self.g)), "gb_group_init", hd.h)
+
+    def gather_results(self, mine, n):
+        """mine: (gb_acq_result * n) of this rank -> (gb_acq_result * (world * n)), rank-major, on every rank."""
+        out = (self.ffi.AcqResult * (self.world * n))()
+        self.ffi.check(self.hd.L.gb_group_gather_results(self.g, mine, n, out), "gb_group_gather_results", self.hd.h)
+        return out
+
+    def close(self):
+        if self.g:
+            self.hd.L.gb_group_destroy(self.g)
+            self.g = None
+
+
 def run_ours(args, rank, world, local_rank):
+    import ctypes as C
     import torch
     import gnss_sdr_rs_b200._ffi as ffi
     from gnss_sdr_rs_b200 import acquisition, ring
@@ -313,131 +492,122 @@ def run_ours(args, rank, world, local_rank):
             os.close(devnull)
             os.close(saved)
 
-    from gnss_sdr_rs_b200 import sharding
-    by_prn = args.shard == "prn" and world > 1
-    prn_mask = sharding.prn_mask_for_rank(rank, world, N_PRN) if by_prn else 0xFFFFFFFF
-    hd = ffi.Handle(local_rank)
-    x = make_recording(0x6E56 + (0 if by_prn else rank))
-    rb = ring.MulticastRingBuffer(hd, 1 << 20)
-    rb.write_samples(x)
-    x_pin = torch.from_numpy(x.view(np.float32).copy()).pin_memory()
-    x_pin_ptr = x_pin.data_ptr()
-
-    eng = acquisition.AcquisitionEngine(hd, N_FFT, FS, N_PRN)
-    carr = eng.make_doppler_tables(0.0, DOPPLERS)
-    eng.set_coherent(N_COH)
-    eng.set_detector(7.0, 4)
-    eng.set_mode(ffi.GB_ACQ_FUSED if args.acq_mode == "fused" else ffi.GB_ACQ_SHARED)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     cuda_dev = torch.device("cuda", local_rank)
-    gatherer = sharding.ResultGatherer(dist, cuda_dev, N_PRN) if dist is not None else None
-    raw_gatherer = sharding.RawResultGatherer(dist, cuda_dev, N_PRN, ffi.AcqResult) if dist is not None else None
+    hd = ffi.Handle(local_rank)
+    group = NcclGroup(hd, ffi, dist, rank, world, cuda_dev) if dist is not None else None
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_device():
-        flush.zero_()
-        # re-align the ranks after the (untimed) L2 flush so the timed gather measures the collective, not flush skew
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def configure(prn_mask):
+        eng = acquisition.AcquisitionEngine(hd, N_FFT, FS, N_PRN)
+        eng.make_doppler_tables(0.0, DOPPLERS)
+        eng.set_coherent(N_COH)
+        eng.set_detector(7.0, 4)
+        eng.set_doppler_aliasing(True)   # explicit: the library's default is the reference's per-bin tables
+        eng.set_mode(ffi.GB_ACQ_FUSED if args.acq_mode == "fused" else ffi.GB_ACQ_SHARED)
+        return eng
+
+    # ------------------------------------------------------------------ the timed workload
+    # N = 1, or N > 1 sharded by recording (default, weak scaling): every rank searches its own recording each step;
+    # --shard prn (strong scaling): ONE recording, its PRNs dealt round-robin to the ranks.
+    # No collective inside a step: the per-PRN result tables of all steps are gathered ONCE after the last step,
+    # inside the timed region ("a final NCCL gather of per-PRN peaks").
+    def timed_block(by_prn, steps, warmup):
+        prn_mask = int(hd.L.gb_shard_prn_mask(rank, world, N_PRN, 0xFFFFFFFF)) if by_prn else 0xFFFFFFFF
+        x = make_recording(0x6E56 + (0 if by_prn else rank))
+        rb = ring.MulticastRingBuffer(hd, 1 << 20)
+        rb.write_samples(x)
+        eng = configure(prn_mask)
+        table = (ffi.AcqResult * (steps * N_PRN))()   # this rank's results of every step
+
+        def step(k):
+            flush.zero_()
+            torch.cuda.synchronize()
+            out = (ffi.AcqResult * N_PRN).from_address(C.addressof(table) + (k % steps) * N_PRN * C.sizeof(ffi.AcqResult))
+            eng.search_ring_raw(0, K_MS, prn_mask=prn_mask, out=out)
+            return eng.last_kernel_ms()
+
+        for k in range(max(warmup, 3)):
+            step(k)
+        sampler = ClockSampler(local_rank)
+        sampler.start()
         barrier()
         t0 = time.perf_counter()
+        dev_ms = 0.0
+        for k in range(steps):
+            dev_ms += step(k)
         g_ms = 0.0
-        if dist is None:
-            res = eng.search_ring(0, K_MS, prn_mask=prn_mask)
-            ms = eng.last_kernel_ms()
-        else:
-            # results land in the gatherer's pinned buffer; the one collective of the path ships the raw structs of
-            # every rank, NCCL over NVLink
-            eng.search_ring_raw(0, K_MS, prn_mask=prn_mask, out=raw_gatherer.results)
-            ms = eng.last_kernel_ms()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            per_rank = raw_gatherer.gather()
-            e1.record()
+        gathered = None
+        if group is not None:
             torch.cuda.synchronize()
-            g_ms = e0.elapsed_time(e1)
-            if by_prn:   # every PRN is owned by exactly one rank
-                res = [None] * N_PRN
-                for arr in per_rank:
-                    for r in arr:
-                        if r.found:
-                            res[r.prn - 1] = r.as_dict()
-            else:
-                res = [r.as_dict() if r.found else None for r in per_rank[rank]]
-        return ms + g_ms, (time.perf_counter() - t0) * 1e3, res
+            tg = time.perf_counter()
+            gathered = group.gather_results(table, steps * N_PRN)   # ONE all-gather for the whole batch
+            g_ms = (time.perf_counter() - tg) * 1e3
+        barrier()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        clocks = sampler.finish()
+        dev_ms += g_ms
+        if dist is not None:
+            t = torch.tensor([dev_ms, wall_ms, g_ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dev_ms, wall_ms, g_ms = [float(v) for v in t.cpu()]
+        # results of the last step on this rank's recording (strong: merged over the ranks that own the PRNs)
+        last = (steps - 1) * N_PRN
+        if gathered is not None and by_prn:
+            res = [None] * N_PRN
+            for r_ in range(world):
+                for p in range(N_PRN):
+                    it = gathered[r_ * steps * N_PRN + last + p]
+                    if it.found:
+                        res[p] = it.as_dict()
+        else:
+            res = [table[last + p].as_dict() if table[last + p].found else None for p in range(N_PRN)]
+        return {"eng": eng, "x": x, "prn_mask": prn_mask, "dev_ms": dev_ms, "wall_ms": wall_ms, "gather_ms": g_ms,
+                "clocks": clocks, "res": res, "steps": steps}
 
-    for _ in range(max(args.warmup, 3)):
-        step_device()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    barrier()
-    t_wall0 = time.perf_counter()
-    dev_ms, res = 0.0, None
-    for _ in range(args.steps):
-        ms, _, res = step_device()
-        dev_ms += ms
-    barrier()
-    wall_ms = (time.perf_counter() - t_wall0) * 1e3
-    kernel_ms_avg = dev_ms / args.steps
+    by_prn = args.shard == "prn" and world > 1
+    main = timed_block(by_prn, args.steps, args.warmup)
+    eng, x, prn_mask = main["eng"], main["x"], main["prn_mask"]
+    kernel_ms_avg = (main["dev_ms"] - main["gather_ms"]) / args.steps
+    cells = N_PRN * len(DOPPLERS) * N_FFT
+    ms_per_step = main["dev_ms"] / args.steps
+    units = 1 if by_prn else world   # recordings searched per step by the whole job
+    value = units * cells / (ms_per_step * 1e-3)
 
-    # e2e: pinned host IQ -> gb_acq_search (H2D + kernel + D2H + decision) per step
+    # ------------------------------------------------------------------ e2e: pinned host IQ through the C-ABI
+    x_pin = torch.from_numpy(x.view(np.float32).copy()).pin_memory()
+    x_pin_ptr, n_x = x_pin.data_ptr(), int(x.size)
     for _ in range(2):
-        eng.search(x_pin_ptr, K_MS, prn_mask=prn_mask)
+        eng.search(x_pin_ptr, K_MS, prn_mask=prn_mask, n_samples=n_x)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        res_e2e = eng.search(x_pin_ptr, K_MS, prn_mask=prn_mask)
-        if dist is not None:
-            gatherer.gather(res_e2e)
+        res_e2e = eng.search(x_pin_ptr, K_MS, prn_mask=prn_mask, n_samples=n_x)
     barrier()
     e2e_serial_ms = (time.perf_counter() - t0) * 1e3 / args.steps
-
-    # e2e, pipelined: the same public call from TWO host threads on two handles of this GPU (each with its own streams
-    # and buffers), steps dealt alternately -- the upload of one search overlaps the inverse kernel of the other, as a
-    # receiver that acquires recording after recording would run it.  Every step still copies its 6.5 MB of pinned host
-    # IQ to the device and reads its cells / results back inside the timed region; with N GPUs the per-step gather is
-    # issued by the main thread in step order.
+    # the asynchronous pair on the SAME handle from ONE host thread: step k + 1 is enqueued (its upload runs on the copy
+    # stream) before step k is waited for.  Every step still moves its 6.5 MB of pinned host IQ to the device and reads
+    # its cells back inside the timed region; with N GPUs one final gather of the whole batch.
     e2e_ms, e2e_api = e2e_serial_ms, "gb_acq_search (pinned host IQ -> results)"
     if not args.no_pipeline:
-        hd2 = ffi.Handle(local_rank)
-        eng2 = acquisition.AcquisitionEngine(hd2, N_FFT, FS, N_PRN)
-        eng2.make_doppler_tables(0.0, DOPPLERS)
-        eng2.set_coherent(N_COH)
-        eng2.set_detector(7.0, 4)
-        eng2.set_mode(ffi.GB_ACQ_FUSED if args.acq_mode == "fused" else ffi.GB_ACQ_SHARED)
-        engines = (eng, eng2)
-
         def pipelined(n_steps):
-            out = [None] * n_steps
-            done = [threading.Event() for _ in range(n_steps)]
-            errs = []
-
-            def worker(i):
-                try:
-                    for k in range(i, n_steps, 2):
-                        out[k] = engines[i].search(x_pin_ptr, K_MS, prn_mask=prn_mask)
-                        done[k].set()
-                except Exception as e:  # surface in the main thread
-                    errs.append(e)
-                    for ev in done:
-                        ev.set()
-
-            th = [threading.Thread(target=worker, args=(i,)) for i in range(2)]
-            for t_ in th:
-                t_.start()
+            raws = [(ffi.AcqResult * N_PRN)() for _ in range(n_steps)]
+            eng.search_enqueue(x_pin_ptr, K_MS, 0, prn_mask=prn_mask, n_samples=n_x)
             for k in range(n_steps):
-                done[k].wait()
-                if errs:
-                    break
-                if dist is not None:
-                    gatherer.gather(out[k])
-            for t_ in th:
-                t_.join()
-            if errs:
-                raise errs[0]
-            return out
+                if k + 1 < n_steps:
+                    eng.search_enqueue(x_pin_ptr, K_MS, (k + 1) & 1, prn_mask=prn_mask, n_samples=n_x)
+                eng.search_wait(k & 1, raw=raws[k])
+            if group is not None:
+                flat = (ffi.AcqResult * (n_steps * N_PRN))()
+                for k in range(n_steps):
+                    C.memmove(C.addressof(flat) + k * C.sizeof(raws[0]), raws[k], C.sizeof(raws[0]))
+                group.gather_results(flat, n_steps * N_PRN)
+            return [r.as_dict() if r.found else None for r in raws[-1]]
 
         pipelined(4)
         barrier()
@@ -445,47 +615,54 @@ def run_ours(args, rank, world, local_rank):
         res_pipe = pipelined(args.steps)
         barrier()
         e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
-        e2e_api = "gb_acq_search (pinned host IQ -> results), two host threads / two handles per GPU, steps alternating"
+        e2e_api = ("gb_acq_search_enqueue / gb_acq_search_wait (pinned host IQ -> results): ONE handle, one host thread, "
+                   "two slots; upload of step k+1 overlaps the inverse kernel of step k")
         same = all((a is None) == (b is None) and (a is None or (a["code_phase_samples"] == b["code_phase_samples"] and
                                                                    a["carrier_freq"] == b["carrier_freq"]))
-                   for a, b in zip(res_pipe[-1], res_e2e))
+                   for a, b in zip(res_pipe, res_e2e))
         if not same:
             raise RuntimeError("pipelined e2e search disagrees with the serial one")
-        hd2.close()
-    clocks = sampler.finish()
-
     if dist is not None:
-        t = torch.tensor([dev_ms, e2e_ms, wall_ms, e2e_serial_ms], dtype=torch.float64, device="cuda")
+        t = torch.tensor([e2e_ms, e2e_serial_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, e2e_ms, wall_ms, e2e_serial_ms = [float(v) for v in t.cpu()]
-    cells = N_PRN * len(DOPPLERS) * N_FFT
-    ms_per_step = dev_ms / args.steps
-    units = 1 if by_prn else world   # recordings searched per step by the whole job
-    value = units * cells / (ms_per_step * 1e-3)
+        e2e_ms, e2e_serial_ms = [float(v) for v in t.cpu()]
     e2e_value = units * cells / (e2e_ms * 1e-3)
 
-    # BASELINE configs[2] on N GPUs: the 1024 channels are sharded by channel (no exchange between epochs);
-    # device time of the persistent kernel, max over ranks
-    trk_sharded = None
-    if dist is not None and 1024 % world == 0:
-        tr, err = None, None
+    # ------------------------------------------------------------------ N > 1: the other shardings of SURVEY 8e
+    strong = cfg4 = trk_sharded = None
+    if dist is not None:
+        if not by_prn:
+            sb = timed_block(True, max(10, args.steps // 2), 3)   # ONE recording, PRNs dealt to the ranks
+            strong = {"metric": "acq_cells_per_sec", "scaling": "strong", "sharding": "one recording, PRNs round-robin over the GPUs, "
+                      "one final all-gather", "value": cells / (sb["dev_ms"] / sb["steps"] * 1e-3), "unit": "cells/s",
+                      "ms_per_step": sb["dev_ms"] / sb["steps"], "gather_ms_total": sb["gather_ms"], "steps": sb["steps"],
+                      "x_realtime": (K_MS * 1e-3) / (sb["dev_ms"] / sb["steps"] * 1e-3),
+                      "detected_prns": sorted(r["prn"] for r in sb["res"] if r)}
         try:
-            tr = tracking_numbers(hd, ffi, 1024 // world, 1000)
-        except Exception as e:  # report, never hide; every rank still takes part in the reductions below
-            err = repr(e)
-        t = torch.tensor([tr["kernel_ms"] if tr else float("inf")], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t2 = torch.tensor([float(tr["locked_channels"]) if tr else 0.0], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t2, op=dist.ReduceOp.SUM)
-        ms_max = float(t[0])
-        if err or not math.isfinite(ms_max):
-            trk_sharded = {"error": err or "a rank failed"}
-        else:
-            trk_sharded = {"metric": "tracking_channel_epochs_per_sec", "value": 1024 * 1000 / (ms_max * 1e-3),
-                           "unit": "channel-epochs/s", "channels": 1024, "channels_per_gpu": 1024 // world, "epochs": 1000,
-                           "kernel_ms_max_over_ranks": ms_max, "locked_channels": int(t2[0]),
-                           "x_realtime": 1.0 / (ms_max * 1e-3), "mode": tr["mode"], "fs": tr["fs"],
-                           "sharding": "by channel, no collective between epochs"}
+            cfg4 = multi_gnss_20msps(hd, ffi, dist, group, rank, world)
+        except Exception as e:  # report, never hide
+            cfg4 = {"error": repr(e)}
+        # BASELINE configs[2] on N GPUs: the 1024 channels sharded by channel (no exchange between epochs)
+        if 1024 % world == 0:
+            tr, err = None, None
+            try:
+                tr = tracking_numbers(hd, ffi, 1024 // world, 2000)
+            except Exception as e:
+                err = repr(e)
+            t = torch.tensor([tr["kernel_ms"] if tr else float("inf")], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            t2 = torch.tensor([float(tr["locked_channels"]) if tr else 0.0], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t2, op=dist.ReduceOp.SUM)
+            ms_max = float(t[0])
+            if err or not math.isfinite(ms_max):
+                trk_sharded = {"error": err or "a rank failed"}
+            else:
+                trk_sharded = {"metric": "tracking_channel_epochs_per_sec", "value": 1024 * 2000 / (ms_max * 1e-3),
+                               "unit": "channel-epochs/s", "channels": 1024, "channels_per_gpu": 1024 // world, "epochs": 2000,
+                               "kernel_ms_max_over_ranks": ms_max, "us_per_epoch": ms_max * 1e3 / 2000,
+                               "locked_channels": int(t2[0]),
+                               "x_realtime": 2.0 / (ms_max * 1e-3), "mode": tr["mode"], "fs": tr["fs"], "layout": tr["layout"],
+                               "sharding": "by channel, no collective between epochs"}
 
     if rank == 0:
         peak_tf = ctypes_float(hd, "gb_bench_fp32_tflops")
@@ -494,7 +671,9 @@ def run_ours(args, rank, world, local_rank):
         minimal, fused_flops, shared_flops = acq_flops(n_fwd)
         as_run = fused_flops if args.acq_mode == "fused" else shared_flops
         abytes = acq_bytes(args.acq_mode != "fused", n_fwd, n_shift)
-        achieved = minimal / (kernel_ms_avg * 1e-3) / 1e12
+        # the numerator is the work the launch EXECUTES (the forward path runs for the n_fwd alias classes only), never
+        # more than SURVEY 8d's minimal count
+        achieved = min(as_run, minimal) / (kernel_ms_avg * 1e-3) / 1e12
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -507,17 +686,18 @@ def run_ours(args, rank, world, local_rank):
                 "acq_fused_4092_bytes_per_launch" if args.acq_mode == "fused" else "acq_chain_4092_bytes_per_launch")
         except Exception:
             pass
-        found = sorted(r["prn"] for r in res if r)
+        found = sorted(r["prn"] for r in main["res"] if r)
         line = {"metric": "acq_cells_per_sec", "value": value, "unit": "cells/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if by_prn else "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(),
-                "wall_ms_per_step_incl_l2_flush": wall_ms / args.steps,
+                "wall_ms_per_step_incl_l2_flush": main["wall_ms"] / args.steps,
+                "final_gather_ms": main["gather_ms"],
                 "x_realtime": units * (K_MS * 1e-3) / (ms_per_step * 1e-3),
                 "e2e": {"value": e2e_value, "unit": "cells/s", "ms_per_step": e2e_ms,
                         "h2d_bytes_per_step": int(x.nbytes), "d2h_bytes_per_step": int(N_PRN * len(DOPPLERS) * 16),
                         "api": e2e_api, "serial_ms_per_step": e2e_serial_ms,
                         "serial_value": units * cells / (e2e_serial_ms * 1e-3),
-                        "serial_api": "one host thread, one gb_acq_search call at a time"},
+                        "serial_api": "one gb_acq_search call at a time (upload, kernels and read-back in sequence)"},
                 # per step: line-order permutation of the IQ blocks (prime-factor plan) + forward + inverse kernels
                 "gpu_launches": args.steps * (2 if args.acq_mode == "fused" else 3),
                 "roofline": {"bound": "fp32", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
@@ -525,6 +705,7 @@ def run_ours(args, rank, world, local_rank):
                              "peak_source": "measured live: gb_bench_fp32_tflops FMA probe (MEASURED_PEAKS.json has no "
                                             "FP32 figure; theoretical 148*128*2*1.965 GHz = 74.5)",
                              "flops_per_launch_minimal": minimal, "flops_per_launch_as_run": as_run,
+                             "numerator": "flops_per_launch_as_run",
                              "forward_spectra_per_group": n_fwd,
                              "kernel": ("acq_fused_kernel<PfaPlan<4092,160,4,12,11,31>>" if args.acq_mode == "fused" else
                                         "permute_blocks_kernel + acq_forward_kernel<PfaPlan<4092,160,4,12,11,31>> + "
@@ -536,7 +717,11 @@ def run_ours(args, rank, world, local_rank):
                                           "peak": hbm_peak, "unit": "GB/s",
                                           "frac": abytes / (kernel_ms_avg * 1e-3) / 1e9 / hbm_peak,
                                           "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback"}},
-                "clocks": clocks, "detected_prns": found}
+                "clocks": main["clocks"], "detected_prns": found}
+        if strong is not None:
+            line["strong_scaling_one_recording"] = strong
+        if cfg4 is not None:
+            line["config4_multi_gnss_20msps"] = cfg4
         if trk_sharded is not None:
             line["tracking_sharded"] = trk_sharded
         if world == 1:
@@ -544,16 +729,22 @@ def run_ours(args, rank, world, local_rank):
             v, dt, n_prn, ocells = cpu_baseline_acq(x, cores)
             line["cpu_baseline"] = {"value": v, "unit": "cells/s", "cores": cores, "kind": "port",
                                     "sample": "%d of 32 PRNs x 201 bins x 200 ms, %.1f s" % (n_prn, dt)}
-            # the bench doubles as a full-size parity check on the sampled PRNs
-            gcells = eng.search_cells_ring(0, K_MS)
-            strong = ocells["peak"] > 4.0 * np.median(ocells["peak"], axis=1, keepdims=True)
-            line["parity_vs_oracle"] = {
-                "prns": n_prn, "max_rel_peak_err": float(np.abs(gcells["peak"][:n_prn] / ocells["peak"] - 1).max()),
-                "argmax_equal_frac": float((gcells["argmax"][:n_prn] == ocells["argmax"]).mean()),
-                "argmax_equal_strong_cells": bool((gcells["argmax"][:n_prn][strong] == ocells["argmax"][strong]).all())}
+            # the bench doubles as a full-size parity check on the sampled PRNs: cells, DECISIONS (the early-exit scan
+            # on the 10 ms-coherent cells) and the margin of every decision to the 7.0 threshold, aliasing on and off
+            line["parity_vs_oracle"] = full_size_parity(eng, ocells, n_prn)
             try:
-                line["tracking"] = tracking_numbers(hd, ffi)
-                line["tracking_128ch"] = tracking_numbers(hd, ffi, 128, 1000)
+                stream = tracking_stream(2100)
+                tr = tracking_numbers(hd, ffi, 1024, 2000, stream=stream)
+                tr["roofline"] = tracking_roofline(tr, peak_tf)
+                tr["cpu_baseline"] = tracking_cpu_baseline(stream, cores)
+                tr["e2e"] = tracking_e2e(hd, ffi, stream)
+                tr["ordered_mode"] = tracking_numbers(hd, ffi, 1024, 200, mode=1, stream=stream)
+                tr["reference_code_row"] = tracking_numbers(hd, ffi, 1024, 1000, reference_row=True, stream=stream)
+                line["tracking"] = tr
+                t128 = tracking_numbers(hd, ffi, 128, 2000, stream=stream)
+                t128["roofline"] = tracking_roofline(t128, peak_tf)
+                line["tracking_128ch"] = t128
+                del stream
                 # BASELINE configs[2] at full length: 1024 channels x 60 s = 61.44 M channel-epochs in one launch
                 line["tracking_config3_full_60s"] = tracking_numbers(hd, ffi, 1024, 60000)
             except Exception as e:  # report, never hide
@@ -563,10 +754,116 @@ def run_ours(args, rank, world, local_rank):
             except Exception as e:
                 line["extras"] = {"error": repr(e)}
         print(json.dumps(line), flush=True)
+    if group is not None:
+        group.close()
     hd.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def full_size_parity(eng, ocells, n_prn):
+    """GPU cells of the full config-2 search against the oracle's (same recording, same 10 ms x 20 plan): peaks, arg-max,
+    the early-exit DECISION of every sampled PRN and its margin to the threshold, with Doppler aliasing on (as timed)
+    and off (the reference's per-bin tables)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pyoracle as orc
+    carr = np.asarray(eng.carr, np.float32)
+    out = {"prns": n_prn, "threshold": 7.0}
+    odec = [decision_margins(ocells[p], N_FFT) for p in range(n_prn)]
+    ores = [orc.acq_decide(np.ascontiguousarray(ocells[p]), carr, p + 1, N_FFT, FS) for p in range(n_prn)]
+    for name, on in (("aliasing_on", True), ("aliasing_off", False)):
+        eng.set_doppler_aliasing(on)
+        g = eng.search_cells_ring(0, K_MS)
+        gres = eng.search_ring(0, K_MS)
+        strong = ocells["peak"] > 4.0 * np.median(ocells["peak"], axis=1, keepdims=True)
+        gdec = [decision_margins(g[p], N_FFT) for p in range(n_prn)]
+        same = []
+        for p in range(n_prn):
+            a, b = gres[p], ores[p]
+            same.append((a is None) == (b is None) and (a is None or (
+                a["code_phase_samples"] == b["code_phase_samples"] and a["carrier_freq"] == b["carrier_freq"] and
+                a["doppler_bin"] == b["bin"])))
+        out[name] = {
+            "max_rel_peak_err": float(np.abs(g["peak"][:n_prn] / ocells["peak"] - 1).max()),
+            "argmax_equal_frac": float((g["argmax"][:n_prn] == ocells["argmax"]).mean()),
+            "argmax_equal_strong_cells": bool((g["argmax"][:n_prn][strong] == ocells["argmax"][strong]).all()),
+            "decisions_equal": bool(all(same)), "decisions_checked": n_prn,
+            "detected_prns": [p + 1 for p in range(n_prn) if gres[p]],
+            "min_margin_to_threshold_gpu": float(min(m for _, _, m in gdec)),
+            "min_margin_to_threshold_oracle": float(min(m for _, _, m in odec)),
+            "deciding_bins_gpu": [d for d, _, _ in gdec], "deciding_bins_oracle": [d for d, _, _ in odec]}
+    eng.set_doppler_aliasing(True)
+    return out
+
+
+def multi_gnss_20msps(hd, ffi, dist, group, rank, world):
+    """BASELINE configs[3] shape on N GPUs: GPS L1 C/A (1023 chips) + BeiDou-B1I-like (2046 chips, 2.046 Mcps) at 20 Msps
+    (code period 20000 samples, radix 8*4*25*25 plan) and a Galileo-E1-like 4 ms BOC(1,1) code (80000 samples, 4-CTA
+    cluster plan), PRNs dealt round-robin to the ranks, +-5 kHz / 250 Hz (41 bins), 20 ms; one final gather.  No reference
+    semantics exist for these signals: throughput + the planted satellites must be found."""
+    import ctypes as C
+    import torch
+    from gnss_sdr_rs_b200 import acquisition, sdr_mock
+    fs, n = 20.0e6, 20000
+    K = 20
+    rng = np.random.default_rng(0x6E59)
+    n_gps, n_bds = 32, 32
+    codes = [sdr_mock.resample_code(sdr_mock.ca_code(p), 1.023e6, fs, n) for p in range(1, n_gps + 1)]
+    codes += [sdr_mock.resample_code(sdr_mock.b1i_code(p), 2.046e6, fs, n) for p in range(1, n_bds + 1)]
+    codes = np.stack(codes).astype(np.int8)
+    planted = [(3, 1250.0, 777), (40, -2000.0, 12345), (17, 500.0, 19000), (60, 3750.0, 4242)]   # rows (1-based)
+    x = (rng.standard_normal(K * n) + 1j * rng.standard_normal(K * n)).astype(np.complex64) * np.float32(1 / np.sqrt(2))
+    t = np.arange(K * n, dtype=np.float64)
+    for row, dop, cp in planted:
+        amp = np.sqrt(10.0 ** (47.0 / 10.0) / fs)
+        x += (amp * codes[row - 1][(np.arange(K * n) - cp) % n] * np.exp(2j * np.pi * ((dop * t / fs) % 1.0))).astype(np.complex64)
+    mine = [p for p in range(len(codes)) if p % world == rank]
+    eng = acquisition.AcquisitionEngine(hd, n, fs, n_prn=len(mine), codes=codes[mine])
+    eng.make_doppler_tables(0.0, np.arange(-5000, 5001, 250, dtype=np.float32))
+    eng.set_detector(7.0, 0)
+    ms = []
+    for _ in range(4):
+        res = eng.search(x, K)
+        ms.append(eng.last_kernel_ms())
+    found_local = [(mine[i] + 1, r["code_phase_samples"], r["carrier_freq"]) for i, r in enumerate(res) if r]
+    t_ms = torch.tensor([min(ms[1:])], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    # final gather of the per-code results through the library's collective (rows padded to the largest share)
+    per = (len(codes) + world - 1) // world
+    tab = (ffi.AcqResult * per)()
+    for i, r in enumerate(res):
+        if r:
+            tab[i].found, tab[i].prn = 1, (mine[i] + 1) & 0xFF
+            tab[i].code_phase_samples, tab[i].carrier_freq = r["code_phase_samples"], r["carrier_freq"]
+    allr = group.gather_results(tab, per)
+    found = sorted((int(a.prn), int(a.code_phase_samples), float(a.carrier_freq)) for a in allr if a.found)
+    ok = all(any(f[0] == row and abs(f[1] - cp) <= 10 for f in found) for row, _, cp in planted)
+    cells = len(codes) * 41 * n
+    out = {"signals": "GPS L1 C/A x32 + BeiDou-B1I-like x32 at 20 Msps (N = 20000), 41 bins, 20 x 1 ms",
+           "sharding": "codes round-robin over the GPUs, one final gb_group_gather_results", "kernel_ms_max_over_ranks": float(t_ms[0]),
+           "cells_per_sec": cells / (float(t_ms[0]) * 1e-3), "x_realtime_vs_20ms": 20.0 / float(t_ms[0]),
+           "planted_found": bool(ok), "n_found": len(found)}
+    # Galileo-E1-like: 4 ms code, 80000 samples, cluster plan, 8 codes dealt to the ranks (5 x 4 ms)
+    n2 = 80000
+    e1 = np.stack([sdr_mock.resample_code(sdr_mock.e1_surrogate_code(p), 1.023e6, fs, n2, boc11=True) for p in range(1, 9)])
+    mine2 = [p for p in range(8) if p % world == rank]
+    if mine2:
+        x2 = (rng.standard_normal(5 * n2) + 1j * rng.standard_normal(5 * n2)).astype(np.complex64)
+        eng2 = acquisition.AcquisitionEngine(hd, n2, fs, n_prn=len(mine2), codes=e1[mine2])
+        eng2.make_doppler_tables(0.0, np.arange(-2500, 2501, 125, dtype=np.float32))
+        m2 = []
+        for _ in range(3):
+            eng2.search_cells(x2, 5)
+            m2.append(eng2.last_kernel_ms())
+        e1_ms = min(m2[1:])
+    else:
+        e1_ms = 0.0
+    t2 = torch.tensor([e1_ms], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    out["galileo_e1_like"] = {"fft_size": n2, "codes": 8, "n_doppler": 41, "num_integrations": 5,
+                              "kernel_ms_max_over_ranks": float(t2[0]), "cells_per_sec": 8 * 41 * n2 / (float(t2[0]) * 1e-3)}
+    return out
 
 
 def ctypes_float(hd, name):

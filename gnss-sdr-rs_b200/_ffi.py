@@ -7,7 +7,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgnss_b200.so")
 
-GB_OK, GB_EINVAL, GB_ENODEVICE, GB_ECUDA, GB_EUNSUPPORTED, GB_ESTATE, GB_ENOMEM, GB_ERANGE = 0, -1, -2, -3, -4, -5, -6, -7
+GB_OK, GB_EINVAL, GB_ENODEVICE, GB_ECUDA, GB_EUNSUPPORTED, GB_ESTATE, GB_ENOMEM, GB_ERANGE, GB_ENCCL = 0, -1, -2, -3, -4, -5, -6, -7, -8
 GB_TRK_IDLE, GB_TRK_TRACKING = 0, 1
 GB_TRK_FAST, GB_TRK_ORDERED = 0, 1
 GB_ACQ_FUSED, GB_ACQ_SHARED, GB_ACQ_SHARED_PLAIN = 0, 1, 2
@@ -44,7 +44,8 @@ class TrkChannel(C.Structure):
 
 
 NAV_DTYPE = np.dtype([("flag_bit_sync", np.int32), ("frame_sync_ind", np.int32), ("sync_epoch", np.int32),
-                      ("n_bits", np.int32), ("bit_sync_buff", np.uint32, (20,))])
+                      ("n_bits", np.int32), ("bit_sync_buff", np.uint32, (20,)), ("preamble_bit", np.int32),
+                      ("polarity", np.int32), ("ref_frame_sync", np.int32), ("ref_polarity", np.int32)])
 FINE_REQ_DTYPE = np.dtype([("prn", np.uint8), ("reserved", np.uint8, (3,)), ("code_phase", np.uint32)])
 FINE_RES_DTYPE = np.dtype([("fft_size", np.uint32), ("idx", np.uint32), ("mag", np.float32), ("carrier_freq", np.float32),
                            ("ref_defined", np.int32)])
@@ -79,6 +80,7 @@ SIGNATURES = {
     "gb_frontend_state": (_i32, [_vp, _vp]),
     "gb_frontend_orbit": (_i32, [_f32, _f32, _vp, _vp, _vp, _u64]),
     "gb_acq_configure": (_i32, [_vp, _i32, _f32, _i32, _vp]),
+    "gb_acq_configure_once": (_i32, [_vp, _i32, _f32, _i32]),
     "gb_acq_supported_sizes": (_i32, [_vp, _i32]),
     "gb_acq_make_doppler_tables": (_i32, [_vp, _f32, _vp, _i32, _vp]),
     "gb_acq_set_doppler_tables": (_i32, [_vp, _vp, _vp, _i32]),
@@ -88,12 +90,15 @@ SIGNATURES = {
     "gb_acq_set_doppler_aliasing": (_i32, [_vp, _i32]),
     "gb_acq_forward_bins": (_i32, [_vp]),
     "gb_acq_set_detector": (_i32, [_vp, _f32, _i32]),
-    "gb_acq_search_cells": (_i32, [_vp, _vp, _i32, _u32, _vp, _vp]),
+    "gb_acq_search_cells": (_i32, [_vp, _vp, _u64, _i32, _u32, _vp, _vp]),
     "gb_acq_search_cells_ring": (_i32, [_vp, _u64, _i32, _u32, _vp, _vp]),
     "gb_acq_decide": (_i32, [_vp, _vp, _i32, _i32, _i32, _f32, _u64, _f32, _vp]),
-    "gb_acq_search": (_i32, [_vp, _vp, _i32, _u64, _u32, _vp, _vp]),
+    "gb_acq_search": (_i32, [_vp, _vp, _u64, _i32, _u64, _u32, _vp, _vp]),
+    "gb_acq_search_enqueue": (_i32, [_vp, _vp, _u64, _i32, _u64, _u32, _vp, _i32]),
+    "gb_acq_search_wait": (_i32, [_vp, _i32, _vp, _vp]),
+    "gb_acq_search_batch": (_i32, [_vp, _vp, _i32, _u64, _i32, _u64, _u32, _vp, _vp]),
     "gb_acq_search_ring": (_i32, [_vp, _u64, _i32, _u32, _vp, _vp]),
-    "gb_acq_bin_power": (_i32, [_vp, _vp, _i32, _i32, _i32, _vp]),
+    "gb_acq_bin_power": (_i32, [_vp, _vp, _u64, _i32, _i32, _i32, _vp]),
     "gb_acq_last_kernel_ms": (_f32, [_vp]),
     "gb_acq_fine_doppler": (_i32, [_vp, _vp, _u64, _f32, _i32, _i32, _vp, _i32, _vp, _vp, _vp]),
     "gb_acq_fine_doppler_ring": (_i32, [_vp, _u64, _u64, _f32, _i32, _i32, _vp, _i32, _vp, _vp]),
@@ -104,15 +109,28 @@ SIGNATURES = {
     "gb_rfft": (_i32, [_vp, _i32, _vp, _vp, _i32]),
     "gb_trk_channel_init": (_i32, [_vp, C.c_uint8, _f32]),
     "gb_trk_channel_start": (_i32, [_vp, _vp]),
+    "gb_trk_channel_start_corrected": (_i32, [_vp, _vp]),
     "gb_trk_channel_reset": (_i32, [_vp]),
     "gb_loop_filter_new": (_i32, [_f32, _f32, _f32, _vp, _vp]),
-    "gb_trk_correlate": (_i32, [_vp, _vp, _i32, _vp, _vp, _i32, _vp]),
+    "gb_trk_correlate": (_i32, [_vp, _vp, _i32, _vp, _u64, _vp, _i32, _vp]),
     "gb_trk_epoch": (_i32, [_vp, _vp, _i32, _i32, _vp, _vp, _vp]),
     "gb_trk_upload": (_i32, [_vp, _vp, _i32]),
     "gb_trk_run": (_i32, [_vp, _i32, _i32, _vp]),
+    "gb_trk_run_keep": (_i32, [_vp, _i32, _i32]),
     "gb_trk_download": (_i32, [_vp, _vp, _i32]),
     "gb_trk_last_kernel_ms": (_f32, [_vp]),
     "gb_nav_bit_sync": (_i32, [_vp, _vp, _i32, _i32, _vp, _vp, _i32]),
+    "gb_shard_prn_mask": (_u32, [_i32, _i32, _i32, _u32]),
+    "gb_shard_range": (_i32, [_i32, _i32, _i32, _vp, _vp]),
+    "gb_group_unique_id": (_i32, [_vp]),
+    "gb_group_init": (_i32, [_vp, _vp, _i32, _i32, _vp]),
+    "gb_group_rank": (_i32, [_vp]),
+    "gb_group_world": (_i32, [_vp]),
+    "gb_group_allgather": (_i32, [_vp, _vp, _u64, _vp]),
+    "gb_group_allgather_begin": (_i32, [_vp, _vp, _u64, _i32]),
+    "gb_group_allgather_end": (_i32, [_vp, _i32, _vp]),
+    "gb_group_gather_results": (_i32, [_vp, _vp, _i32, _vp]),
+    "gb_group_destroy": (_i32, [_vp]),
 }
 
 _LIB = None

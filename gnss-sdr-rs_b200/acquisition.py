@@ -89,7 +89,7 @@ class AcquisitionEngine:
         self.n_coh = int(n_coh)
 
     def set_doppler_aliasing(self, on):
-        """Share one forward spectrum between Doppler bins a whole number of FFT bins apart (default on); off = every
+        """Share one forward spectrum between Doppler bins a whole number of FFT bins apart; off (the default) = every
         bin runs the reference's own wipe-off table (include/gnss_b200.h, gb_acq_set_doppler_aliasing)."""
         self.hd.call("gb_acq_set_doppler_aliasing", 1 if on else 0)
 
@@ -108,12 +108,22 @@ class AcquisitionEngine:
     def _enable(self, enable):
         return None if enable is None else np.ascontiguousarray(enable, np.uint8)
 
-    def search_cells(self, samples, num_integrations, prn_mask=0xFFFFFFFF, enable=None):
+    def _chunk(self, samples, num_integrations, n_samples):
+        """Host chunk + its length in samples.  `samples` is an array, or the integer address of a (pinned) host buffer
+        whose length the caller states in n_samples; the library refuses a buffer shorter than K * fft_size."""
+        if isinstance(samples, int):
+            if n_samples is None:
+                raise ValueError("a raw host address needs n_samples")
+            return samples, int(n_samples)
+        x = np.ascontiguousarray(samples, np.complex64)
+        return x, int(x.size)
+
+    def search_cells(self, samples, num_integrations, prn_mask=0xFFFFFFFF, enable=None, n_samples=None):
         """Full PRN x Doppler grid -> structured array [n_prn, D] of {peak, argmax, sum8, peak2}."""
-        x = samples if isinstance(samples, int) else np.ascontiguousarray(samples, np.complex64)
+        x, n = self._chunk(samples, num_integrations, n_samples)
         cells = np.zeros((self.n_prn, len(self.carr)), _ffi.CELL_DTYPE)
         en = self._enable(enable)
-        self.hd.call("gb_acq_search_cells", _ffi.ptr(x), int(num_integrations), int(prn_mask), _ffi.ptr(en),
+        self.hd.call("gb_acq_search_cells", _ffi.ptr(x), n, int(num_integrations), int(prn_mask), _ffi.ptr(en),
                      _ffi.ptr(cells))
         return cells
 
@@ -124,14 +134,33 @@ class AcquisitionEngine:
                      _ffi.ptr(cells))
         return cells
 
-    def search(self, samples, num_integrations, local_tail=0, prn_mask=0xFFFFFFFF, enable=None):
+    def search(self, samples, num_integrations, local_tail=0, prn_mask=0xFFFFFFFF, enable=None, n_samples=None):
         """search_satellite for every selected PRN: list of AcquisitionResult dicts or None."""
-        x = samples if isinstance(samples, int) else np.ascontiguousarray(samples, np.complex64)
+        x, n = self._chunk(samples, num_integrations, n_samples)
         res = (_ffi.AcqResult * self.n_prn)()
         en = self._enable(enable)
-        self.hd.call("gb_acq_search", _ffi.ptr(x), int(num_integrations), int(local_tail), int(prn_mask),
+        self.hd.call("gb_acq_search", _ffi.ptr(x), n, int(num_integrations), int(local_tail), int(prn_mask),
                      _ffi.ptr(en), res)
         return [r.as_dict() if r.found else None for r in res]
+
+    # asynchronous pair on one handle (two slots): the upload of one search overlaps the inverse kernel of the other
+    def search_enqueue(self, samples, num_integrations, slot, local_tail=0, prn_mask=0xFFFFFFFF, enable=None, n_samples=None):
+        x, n = self._chunk(samples, num_integrations, n_samples)
+        self._keep = getattr(self, "_keep", {})
+        self._keep[slot] = x   # the buffer must outlive the call
+        en = self._enable(enable)
+        self.hd.call("gb_acq_search_enqueue", _ffi.ptr(x), n, int(num_integrations), int(local_tail), int(prn_mask),
+                     _ffi.ptr(en), int(slot))
+
+    def search_wait(self, slot, want_cells=False, raw=None):
+        res = raw if raw is not None else (_ffi.AcqResult * self.n_prn)()
+        cells = np.zeros((self.n_prn, len(self.carr)), _ffi.CELL_DTYPE) if want_cells else None
+        self.hd.call("gb_acq_search_wait", int(slot), res, _ffi.ptr(cells))
+        getattr(self, "_keep", {}).pop(slot, None)
+        if raw is not None:
+            return raw
+        out = [r.as_dict() if r.found else None for r in res]
+        return (out, cells) if want_cells else out
 
     def search_ring(self, local_tail, num_integrations, prn_mask=0xFFFFFFFF, enable=None):
         res = (_ffi.AcqResult * self.n_prn)()
@@ -150,7 +179,8 @@ class AcquisitionEngine:
     def bin_power(self, samples, num_integrations, prn, doppler_bin):
         x = np.ascontiguousarray(samples, np.complex64)
         out = np.zeros(self.n, np.float32)
-        self.hd.call("gb_acq_bin_power", _ffi.ptr(x), int(num_integrations), int(prn), int(doppler_bin), _ffi.ptr(out))
+        self.hd.call("gb_acq_bin_power", _ffi.ptr(x), int(x.size), int(num_integrations), int(prn), int(doppler_bin),
+                     _ffi.ptr(out))
         return out
 
     def last_kernel_ms(self):

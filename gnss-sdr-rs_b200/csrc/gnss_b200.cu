@@ -64,6 +64,10 @@ struct gb_handle {
     cudaStream_t s_acq = nullptr, s_trk = nullptr, s_copy = nullptr;
     cudaEvent_t ev_copy = nullptr, ev_a0 = nullptr, ev_a1 = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
     std::string last_err;
+    // One lock per call family: the reference calls search_satellite from 32 rayon threads (do_acquisition.rs:302-313)
+    // and runs acquisition, tracking and the sample writer on separate threads (main.rs:205-227).  Calls of one family
+    // on one handle are serialised here; different families run concurrently on their own streams.
+    std::recursive_mutex mu_acq, mu_trk, mu_ring;
 
     // sample ring
     float2* ring = nullptr;
@@ -108,14 +112,32 @@ struct gb_handle {
     int8_t* codes_dev = nullptr;
     size_t chunk_cap = 0, tables_cap = 0, rot_cap = 0;
     std::vector<float> carr;
-    gb_acq_cell *cells_dev = nullptr, *cells_pin = nullptr;
+    gb_acq_cell* cells_dev = nullptr;
     size_t cells_cap = 0;
-    int *rows_dev = nullptr, *rows_pin = nullptr;
+    int *rows_dev = nullptr, *rows_pin = nullptr;   // rows_pin = rows_pin_slot[0]
+    // two result slots: gb_acq_search_enqueue(slot) / gb_acq_search_wait(slot) keep one search in flight while the host
+    // consumes the previous one (the synchronous calls use slot 0)
+    struct Pending {
+        bool active = false;
+        uint64_t local_tail = 0;
+        uint32_t prn_mask = 0;
+        bool has_enable = false;
+        std::vector<uint8_t> enable;
+        int n_active = 0;
+        size_t n_cells = 0;
+    } pend[2];
+    gb_acq_cell* cells_pin_slot[2] = {nullptr, nullptr};
+    size_t cells_pin_cap[2] = {0, 0};
+    int* rows_pin_slot[2] = {nullptr, nullptr};
+    cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_s0[2] = {nullptr, nullptr}, ev_s1[2] = {nullptr, nullptr};
+    cudaEvent_t ev_chunk_free = nullptr;   // the last kernel that reads `chunk` has been enqueued behind this event
+    bool chunk_free_valid = false;
+    bool builtin_codes = false;            // configured with codes == NULL (GPS C/A): an identical re-configure is a no-op
     float* row_dev = nullptr;
     float last_acq_ms = 0.f;
     cudaEvent_t ev_slice[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // upload slices
     // Doppler aliasing: bins whose carriers differ by a whole number of FFT bins share one forward spectrum
-    bool alias_enabled = true, alias_ok = false;
+    bool alias_enabled = false, alias_ok = false;
     int n_base = 0, n_shift = 0;
     int* fwd_bins_dev = nullptr;
     int2* inv_map_dev = nullptr;
@@ -148,11 +170,14 @@ struct gb_handle {
     uint8_t *ran_dev = nullptr, *lost_dev = nullptr;
     float* hist_dev = nullptr;
     size_t hist_cap = 0;
+    int hist_epochs = 0, hist_channels = 0;   // shape of the prompt history the last gb_trk_run left on the device
     float2* trk_data = nullptr;
     size_t trk_data_cap = 0;
     unsigned long long* offs_dev = nullptr;
     float trk_fs_max = 0.f;
     float last_trk_ms = 0.f;
+    std::vector<uint8_t> trk_bad;            // channels idled by the last upload (code_row out of the table)
+    std::vector<gb_trk_channel> trk_stage;   // host copy the upload is made from
 };
 
 namespace {
@@ -401,6 +426,7 @@ __global__ void nav_bit_sync_kernel(const float* __restrict__ hist, int n_epochs
     if (c >= n_channels) return;
     gb_nav_sync s;
     s.flag_bit_sync = 0; s.frame_sync_ind = 0; s.sync_epoch = -1; s.n_bits = 0;
+    s.preamble_bit = -1; s.polarity = 0; s.ref_frame_sync = 0; s.ref_polarity = 0;
     unsigned buff[20];
 #pragma unroll
     for (int i = 0; i < 20; i++) buff[i] = 0u;
@@ -432,6 +458,25 @@ __global__ void nav_bit_sync_kernel(const float* __restrict__ hist, int n_epochs
     }
 #pragma unroll
     for (int i = 0; i < 20; i++) s.bit_sync_buff[i] = buff[i];
+    // Preamble search on the bit stream (check_preamble_syn, decoding.rs:215-226): correlation of 8 consecutive bits with
+    // GPS_CA_PREAMBLE, frame sync when it is +-8 (polarity = its sign).  The legacy pushes every bit into buff_preamble
+    // and tests only while its length is exactly 8 (:131-136) -- the VecDeque is never popped, so ONLY the first 8 bits
+    // are ever tested: that literal outcome is ref_frame_sync / ref_polarity.  preamble_bit / polarity are the intended
+    // sliding search: the first bit index at which the last 8 bits match.
+    {
+        const int pre[8] = {1, -1, -1, -1, 1, -1, 1, 1};
+        const int nb = s.n_bits < max_bits ? s.n_bits : max_bits;
+        const int8_t* b = bits + (size_t)c * max_bits;
+        for (int i0 = 0; i0 + 8 <= nb; i0++) {
+            int corr = 0;
+#pragma unroll
+            for (int x = 0; x < 8; x++) corr += (int)b[i0 + x] * pre[x];
+            const bool hit = corr == 8 || corr == -8;
+            if (i0 == 0 && hit) { s.ref_frame_sync = 1; s.ref_polarity = corr > 0 ? 1 : -1; }
+            if (hit && s.preamble_bit < 0) { s.preamble_bit = i0; s.polarity = corr > 0 ? 1 : -1; }
+            if (s.preamble_bit >= 0) break;
+        }
+    }
     st[c] = s;
 }
 
@@ -455,7 +500,8 @@ extern "C" const char* gb_strerror(int code)
         case GB_EUNSUPPORTED: return "fft_size has no sm_100a plan";
         case GB_ESTATE: return "call out of order";
         case GB_ENOMEM: return "out of memory";
-        case GB_ERANGE: return "samples not in the ring";
+        case GB_ENCCL: return "NCCL is not available or a collective failed";
+    case GB_ERANGE: return "samples not in the ring";
     }
     return "unknown error";
 }
@@ -499,8 +545,15 @@ extern "C" int gb_create(const gb_config* cfg, gb_handle** out)
         CK(cudaMallocHost((void**)&h->pin_stage[s], kStageSamples * sizeof(float2)));
         CK(cudaEventCreateWithFlags(&h->pin_free[s], cudaEventDisableTiming));
     }
-    CK(cudaMallocHost((void**)&h->rows_pin, sizeof(int) * 256));
-    CK(cudaMalloc((void**)&h->rows_dev, sizeof(int) * 256));
+    for (int s = 0; s < 2; s++) {
+        CK(cudaMallocHost((void**)&h->rows_pin_slot[s], sizeof(int) * 256));
+        CK(cudaEventCreateWithFlags(&h->ev_done[s], cudaEventDisableTiming));
+        CK(cudaEventCreate(&h->ev_s0[s]));
+        CK(cudaEventCreate(&h->ev_s1[s]));
+    }
+    h->rows_pin = h->rows_pin_slot[0];
+    CK(cudaEventCreateWithFlags(&h->ev_chunk_free, cudaEventDisableTiming));
+    CK(cudaMalloc((void**)&h->rows_dev, sizeof(int) * 2 * 256));
     if (cfg && cfg->ring_capacity) return gb_ring_create(h, cfg->ring_capacity);
     return GB_OK;
 }
@@ -525,8 +578,14 @@ extern "C" int gb_destroy(gb_handle* h)
         if (h->pin_stage[s]) cudaFreeHost(h->pin_stage[s]);
         if (h->pin_free[s]) cudaEventDestroy(h->pin_free[s]);
     }
-    if (h->cells_pin) cudaFreeHost(h->cells_pin);
-    if (h->rows_pin) cudaFreeHost(h->rows_pin);
+    for (int s = 0; s < 2; s++) {
+        if (h->cells_pin_slot[s]) cudaFreeHost(h->cells_pin_slot[s]);
+        if (h->rows_pin_slot[s]) cudaFreeHost(h->rows_pin_slot[s]);
+        cudaEvent_t es[] = {h->ev_done[s], h->ev_s0[s], h->ev_s1[s]};
+        for (cudaEvent_t e : es)
+            if (e) cudaEventDestroy(e);
+    }
+    if (h->ev_chunk_free) cudaEventDestroy(h->ev_chunk_free);
     if (h->s_acq) cudaStreamDestroy(h->s_acq);
     if (h->s_trk) cudaStreamDestroy(h->s_trk);
     if (h->s_copy) cudaStreamDestroy(h->s_copy);
@@ -577,7 +636,8 @@ extern "C" int gb_generate_ca_code_samples(int prn, float code_rate, float fs, i
 // ------------------------------------------------------------------ sample ring
 extern "C" int gb_ring_create(gb_handle* h, uint64_t cap)
 {
-    if (!h || cap == 0 || (cap & (cap - 1))) return GB_EINVAL;  // MulticastRingBuffer::new asserts power of two
+    if (!h || cap == 0 || (cap & (cap - 1))) return GB_EINVAL;
+    std::lock_guard<std::recursive_mutex> lk(h->mu_ring);  // MulticastRingBuffer::new asserts power of two
     CK(cudaSetDevice(h->device));
     if (h->ring) cudaFree(h->ring);
     h->ring = nullptr;
@@ -625,6 +685,7 @@ extern "C" int gb_ring_write(gb_handle* h, const gb_c32* samples, uint64_t n)
 {
     if (!h || !h->ring) return GB_ESTATE;
     if (!samples || n > h->ring_cap) return GB_EINVAL;
+    std::lock_guard<std::recursive_mutex> lk(h->mu_ring);
     CK(cudaSetDevice(h->device));
     return ring_put(h, reinterpret_cast<const float2*>(samples), n);
 }
@@ -632,6 +693,7 @@ extern "C" int gb_ring_write_i8(gb_handle* h, const int8_t* samples, uint64_t n)
 {
     if (!h || !h->ring) return GB_ESTATE;
     if (!samples || n > h->ring_cap) return GB_EINVAL;
+    std::lock_guard<std::recursive_mutex> lk(h->mu_ring);
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->s_copy));  // the staging buffer is reused
     int rc = ensure(h, &h->i8_stage, &h->i8_cap, (size_t)n);
@@ -648,6 +710,7 @@ extern "C" int gb_ring_write_i8(gb_handle* h, const int8_t* samples, uint64_t n)
 extern "C" int gb_frontend_configure(gb_handle* h, float f_if, float fs_in)
 {
     if (!h || !(fs_in > 0.f)) return GB_EINVAL;
+    std::lock_guard<std::recursive_mutex> lk(h->mu_ring);
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->s_copy));
     std::vector<float> lut(4096);
@@ -685,7 +748,8 @@ extern "C" int gb_frontend_configure(gb_handle* h, float f_if, float fs_in)
 extern "C" int gb_frontend_write(gb_handle* h, const gb_c32* raw, uint64_t n)
 {
     if (!h || !h->ring || !h->fe_ready) return GB_ESTATE;
-    if (!raw || n == 0 || n > h->ring_cap || (n % 8) != 0) return GB_EINVAL;  // chunks_exact_mut(16 floats)
+    if (!raw || n == 0 || n > h->ring_cap || (n % 8) != 0) return GB_EINVAL;
+    std::lock_guard<std::recursive_mutex> lk(h->mu_ring);  // chunks_exact_mut(16 floats)
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->s_copy));  // the staging buffer is reused
     int rc = ensure(h, &h->fe_stage, &h->fe_cap, (size_t)n);
@@ -722,6 +786,7 @@ extern "C" int gb_frontend_orbit(float f_if, float fs_in, uint64_t* mu, uint64_t
 extern "C" int gb_frontend_state(gb_handle* h, float* state17)
 {
     if (!h || !state17) return GB_EINVAL;
+    std::lock_guard<std::recursive_mutex> lk(h->mu_ring);
     if (!h->fe_ready) return GB_ESTATE;
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->s_copy));
@@ -736,6 +801,7 @@ extern "C" int gb_ring_copy_to_slice(gb_handle* h, uint64_t start, gb_c32* dest,
 {
     if (!h || !h->ring) return GB_ESTATE;
     if (!dest || n > h->ring_cap) return GB_EINVAL;
+    std::lock_guard<std::recursive_mutex> lk(h->mu_ring);
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->s_copy));
     const uint64_t ps = start & (h->ring_cap - 1);
@@ -757,6 +823,8 @@ extern "C" int gb_acq_configure(gb_handle* h, int fft_size, float fs, int n_prn,
 {
     if (!h || n_prn < 1 || n_prn > 255 || !(fs > 0.f)) return GB_EINVAL;
     if (!codes && n_prn > 32) return GB_EINVAL;
+    std::lock_guard<std::recursive_mutex> lk(h->mu_acq);
+    if (h->pend[0].active || h->pend[1].active) return GB_ESTATE;
     if (fft_size % 4 != 0) return GB_EUNSUPPORTED;  // apply_doppler_shift leaves len%4 samples stale (A3)
     const bool cluster = gb::acq_cluster_supported(fft_size) != 0;
     if (cluster && !codes) return GB_EINVAL;  // no built-in code has an 80000-sample period
@@ -816,8 +884,21 @@ extern "C" int gb_acq_configure(gb_handle* h, int fft_size, float fs, int n_prn,
     h->D = 0; h->n_coh = 1;
     h->carr.clear();
     h->alias_ok = false;
-    h->alias_enabled = true;   // like n_coh, a per-configuration setting
+    h->alias_enabled = false;   // like n_coh, a per-configuration setting; the default is the reference's per-bin arithmetic
+    h->builtin_codes = host_codes.size() != 0;
+    h->chunk_free_valid = false;
     return GB_OK;
+}
+
+// AcquisitionWorker::new runs once per PRN in the reference (32 workers built in a rayon loop, do_acquisition.rs:268-271):
+// the per-worker constructor of a drop-in calls THIS -- the first call plans, an identical later call (built-in GPS C/A
+// codes, same fft_size / fs / n_prn) returns at once and keeps the Doppler tables and settings.
+extern "C" int gb_acq_configure_once(gb_handle* h, int fft_size, float fs, int n_prn)
+{
+    if (!h) return GB_EINVAL;
+    std::lock_guard<std::recursive_mutex> lk(h->mu_acq);
+    if (h->builtin_codes && h->plan >= 0 && h->N == fft_size && h->fs == fs && h->n_prn == n_prn) return GB_OK;
+    return gb_acq_configure(h, fft_size, fs, n_prn, nullptr);
 }
 
 // prime-factor plans: keep a copy of the wipe-off tables in line order (tables_perm[d][l] = tables[d][n(l)])
@@ -941,6 +1022,7 @@ static int build_alias_map(gb_handle* h)
 extern "C" int gb_acq_set_doppler_aliasing(gb_handle* h, int on)
 {
     if (!h) return GB_EINVAL;
+    std::lock_guard<std::recursive_mutex> lk(h->mu_acq);
     h->alias_enabled = on != 0;
     return GB_OK;
 }
@@ -948,12 +1030,14 @@ extern "C" int gb_acq_set_doppler_aliasing(gb_handle* h, int on)
 extern "C" int gb_acq_forward_bins(gb_handle* h)
 {
     if (!h) return GB_EINVAL;
+    std::lock_guard<std::recursive_mutex> lk(h->mu_acq);
     return (h->alias_ok && h->alias_enabled) ? h->n_base : h->D;
 }
 
 extern "C" int gb_acq_make_doppler_tables(gb_handle* h, float f_if, const float* dopplers, int D, float* carr_out)
 {
     if (!h || !dopplers || D < 1 || D > 32767) return GB_EINVAL;
+    std::lock_guard<std::recursive_mutex> lk(h->mu_acq);
     if (h->plan < 0) return GB_ESTATE;
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->s_acq));
@@ -982,6 +1066,7 @@ extern "C" int gb_acq_make_doppler_tables(gb_handle* h, float f_if, const float*
 extern "C" int gb_acq_set_doppler_tables(gb_handle* h, const gb_c32* tables, const float* carr, int D)
 {
     if (!h || !tables || !carr || D < 1 || D > 32767) return GB_EINVAL;
+    std::lock_guard<std::recursive_mutex> lk(h->mu_acq);
     if (h->plan < 0) return GB_ESTATE;
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->s_acq));
@@ -997,6 +1082,7 @@ extern "C" int gb_acq_set_doppler_tables(gb_handle* h, const gb_c32* tables, con
 extern "C" int gb_acq_get_doppler_tables(gb_handle* h, gb_c32* tables_out, float* carr_out)
 {
     if (!h) return GB_EINVAL;
+    std::lock_guard<std::recursive_mutex> lk(h->mu_acq);
     if (h->plan < 0 || h->D == 0) return GB_ESTATE;
     CK(cudaSetDevice(h->device));
     if (tables_out) CK(cudaMemcpy(tables_out, h->tables, (size_t)h->D * h->N * sizeof(float2), cudaMemcpyDeviceToHost));
@@ -1007,6 +1093,7 @@ extern "C" int gb_acq_get_doppler_tables(gb_handle* h, gb_c32* tables_out, float
 extern "C" int gb_acq_set_coherent(gb_handle* h, int n_coh)
 {
     if (!h || n_coh < 1 || n_coh > 1024) return GB_EINVAL;
+    std::lock_guard<std::recursive_mutex> lk(h->mu_acq);
     if (h->plan < 0) return GB_ESTATE;
     CK(cudaSetDevice(h->device));
     h->n_coh = n_coh;
@@ -1016,6 +1103,7 @@ extern "C" int gb_acq_set_coherent(gb_handle* h, int n_coh)
 extern "C" int gb_acq_set_mode(gb_handle* h, int mode)
 {
     if (!h || (mode != GB_ACQ_FUSED && mode != GB_ACQ_SHARED && mode != GB_ACQ_SHARED_PLAIN)) return GB_EINVAL;
+    std::lock_guard<std::recursive_mutex> lk(h->mu_acq);
     h->mode = mode;
     return GB_OK;
 }
@@ -1023,18 +1111,19 @@ extern "C" int gb_acq_set_mode(gb_handle* h, int mode)
 extern "C" int gb_acq_set_detector(gb_handle* h, float threshold, int samples_per_chip)
 {
     if (!h || samples_per_chip < 0) return GB_EINVAL;
+    std::lock_guard<std::recursive_mutex> lk(h->mu_acq);
     h->threshold = threshold;
     h->spc = samples_per_chip;
     return GB_OK;
 }
 
 // ------------------------------------------------------------------ acquisition search
-static int build_rows(gb_handle* h, uint32_t prn_mask, const uint8_t* enable)
+static int build_rows(gb_handle* h, uint32_t prn_mask, const uint8_t* enable, int slot)
 {
     int n = 0;
     for (int p = 0; p < h->n_prn; p++) {
         const bool on = enable ? enable[p] != 0 : (p < 32 ? ((prn_mask >> p) & 1u) != 0 : true);
-        if (on) h->rows_pin[n++] = p;
+        if (on) h->rows_pin_slot[slot][n++] = p;
     }
     return n;
 }
@@ -1049,32 +1138,39 @@ static cudaError_t pfa_inputs(gb_handle* h, gb::AcqArgs& a, int K)
     return e;
 }
 
+// Enqueues one search on the acquisition stream and returns without waiting: memset of the cells, row list, (upload,)
+// kernels, D2H of the cells into the slot's pinned buffer, then the slot's "done" event.  search_finish() waits for it.
 // host_iq != nullptr: the chunk has NOT been uploaded yet.  In the shared-forward chain it is then uploaded in slices of
 // whole coherent groups on the copy stream while the forward path (which needs only its own group's blocks) of the
 // previous slice runs: cudaMemcpyAsync on a dedicated stream, events to the acquisition stream.
-static int search_cells(gb_handle* h, const float2* iq_dev, uint64_t start, uint64_t mask, int K, uint32_t prn_mask,
-                        const uint8_t* enable, gb_acq_cell* cells_out, const gb_c32* host_iq = nullptr)
+static int search_enqueue(gb_handle* h, const float2* iq_dev, uint64_t start, uint64_t mask, int K, uint32_t prn_mask,
+                          const uint8_t* enable, const gb_c32* host_iq, uint64_t local_tail, int slot)
 {
     if (h->plan < 0 || h->D == 0) return GB_ESTATE;
-    if (K < 1 || K % h->n_coh != 0) return GB_EINVAL;
+    if (K < 1 || K % h->n_coh != 0 || slot < 0 || slot > 1) return GB_EINVAL;
+    if (h->pend[slot].active) return GB_ESTATE;   // the slot still holds a search nobody waited for
     const size_t n_cells = (size_t)h->n_prn * h->D;
     if (h->cells_cap < n_cells) {
         if (h->cells_dev) cudaFree(h->cells_dev);
-        if (h->cells_pin) cudaFreeHost(h->cells_pin);
-        h->cells_dev = nullptr; h->cells_pin = nullptr; h->cells_cap = 0;
+        h->cells_dev = nullptr; h->cells_cap = 0;
         CK(cudaMalloc((void**)&h->cells_dev, n_cells * sizeof(gb_acq_cell)));
-        CK(cudaMallocHost((void**)&h->cells_pin, n_cells * sizeof(gb_acq_cell)));
         h->cells_cap = n_cells;
     }
-    const int n_active = build_rows(h, prn_mask, enable);
+    if (h->cells_pin_cap[slot] < n_cells) {
+        if (h->cells_pin_slot[slot]) cudaFreeHost(h->cells_pin_slot[slot]);
+        h->cells_pin_slot[slot] = nullptr; h->cells_pin_cap[slot] = 0;
+        CK(cudaMallocHost((void**)&h->cells_pin_slot[slot], n_cells * sizeof(gb_acq_cell)));
+        h->cells_pin_cap[slot] = n_cells;
+    }
+    const int n_active = build_rows(h, prn_mask, enable, slot);
     CK(cudaMemsetAsync(h->cells_dev, 0, n_cells * sizeof(gb_acq_cell), h->s_acq));
     if (n_active > 0) {
-        CK(cudaMemcpyAsync(h->rows_dev, h->rows_pin, sizeof(int) * n_active, cudaMemcpyHostToDevice, h->s_acq));
+        CK(cudaMemcpyAsync(h->rows_dev + 256 * slot, h->rows_pin_slot[slot], sizeof(int) * n_active, cudaMemcpyHostToDevice, h->s_acq));
         gb::AcqArgs a;
         a.iq = iq_dev; a.iq_start = start; a.iq_mask = mask;
         a.tables = h->tables; a.code_fft = h->code_fft; a.tw = h->tw;
         a.rot = h->n_coh > 1 ? h->rot : nullptr;
-        a.rows = h->rows_dev;
+        a.rows = h->rows_dev + 256 * slot;
         a.D = h->D; a.K = K; a.n_coh = h->n_coh; a.n_active = n_active; a.spc = h->spc;
         a.cells = h->cells_dev; a.row_out = nullptr; a.d0 = 0; a.spec = nullptr; a.d_lo = 0;
         a.otw = h->otw; a.acc_rows = nullptr; a.npos = h->npos; a.g_lo = 0; a.g_cnt = K / h->n_coh;
@@ -1091,9 +1187,9 @@ static int search_cells(gb_handle* h, const float2* iq_dev, uint64_t start, uint
             int rc = ensure(h, &h->acc_rows, &h->acc_cap, (size_t)n_active * h->D * h->N);
             if (rc) return rc;
             a.acc_rows = h->acc_rows;
-            CK(cudaEventRecord(h->ev_a0, h->s_acq));
+            CK(cudaEventRecord(h->ev_s0[slot], h->s_acq));
             CK(gb::acq_cluster_launch_search(a, h->s_acq));
-            CK(cudaEventRecord(h->ev_a1, h->s_acq));
+            CK(cudaEventRecord(h->ev_s1[slot], h->s_acq));
         } else if (h->mode != GB_ACQ_FUSED) {
             // scratch for the forward spectra, processed in Doppler slabs of at most 1 GiB
             const size_t per_d = (size_t)(K / h->n_coh) * h->spec_len;
@@ -1112,12 +1208,15 @@ static int search_cells(gb_handle* h, const float2* iq_dev, uint64_t start, uint
             a.spec = h->spec;
             const int n_groups = K / h->n_coh;
             a.g_lo = 0; a.g_cnt = n_groups;
-            CK(cudaEventRecord(h->ev_a0, h->s_acq));
+            CK(cudaEventRecord(h->ev_s0[slot], h->s_acq));
             if (host_iq && slab >= (size_t)h->D) {
                 // sliced upload overlapped with the forward path
                 const int n_slices = n_groups >= 8 ? 4 : (n_groups >= 2 ? 2 : 1);
                 if (h->pfa) { a.iq = h->iq_perm; a.iq_start = 0; a.iq_mask = ~0ull; a.tables = h->tables_perm; }
                 a.d_lo = 0;
+                // the previous search's last reader of `chunk` (its permute / forward kernels -- NOT its inverse kernel)
+                // must have run before this upload overwrites it; the upload then overlaps that inverse kernel
+                if (h->chunk_free_valid) CK(cudaStreamWaitEvent(h->s_copy, h->ev_chunk_free, 0));
                 for (int sl = 0; sl < n_slices; sl++) {
                     const int g0 = (int)((long long)n_groups * sl / n_slices), g1 = (int)((long long)n_groups * (sl + 1) / n_slices);
                     const size_t b0 = (size_t)g0 * h->n_coh, nb = (size_t)(g1 - g0) * h->n_coh;
@@ -1131,6 +1230,8 @@ static int search_cells(gb_handle* h, const float2* iq_dev, uint64_t start, uint
                     a.g_lo = g0; a.g_cnt = g1 - g0;
                     CK(gb::acq_launch_forward(h->plan, a, n_fwd, h->s_acq));
                 }
+                CK(cudaEventRecord(h->ev_chunk_free, h->s_acq));
+                h->chunk_free_valid = true;
                 a.g_lo = 0; a.g_cnt = 0;   // forward path done: inverse kernel only
                 CK(gb::acq_launch_shared(h->plan, a, h->D, h->s_acq));
             } else {
@@ -1149,41 +1250,61 @@ static int search_cells(gb_handle* h, const float2* iq_dev, uint64_t start, uint
                     }
                 }
             }
-            CK(cudaEventRecord(h->ev_a1, h->s_acq));
+            CK(cudaEventRecord(h->ev_s1[slot], h->s_acq));
         } else {
-            CK(cudaEventRecord(h->ev_a0, h->s_acq));
+            CK(cudaEventRecord(h->ev_s0[slot], h->s_acq));
             if (h->pfa) CK(pfa_inputs(h, a, K));
             CK(gb::acq_launch_search(h->plan, a, h->s_acq));
-            CK(cudaEventRecord(h->ev_a1, h->s_acq));
+            CK(cudaEventRecord(h->ev_s1[slot], h->s_acq));
         }
     }
-    CK(cudaMemcpyAsync(h->cells_pin, h->cells_dev, n_cells * sizeof(gb_acq_cell), cudaMemcpyDeviceToHost, h->s_acq));
-    CK(cudaStreamSynchronize(h->s_acq));
-    if (n_active > 0) CK(cudaEventElapsedTime(&h->last_acq_ms, h->ev_a0, h->ev_a1));
-    else h->last_acq_ms = 0.f;
-    if (cells_out) memcpy(cells_out, h->cells_pin, n_cells * sizeof(gb_acq_cell));
+    CK(cudaMemcpyAsync(h->cells_pin_slot[slot], h->cells_dev, n_cells * sizeof(gb_acq_cell), cudaMemcpyDeviceToHost, h->s_acq));
+    CK(cudaEventRecord(h->ev_done[slot], h->s_acq));
+    gb_handle::Pending& pd = h->pend[slot];
+    pd.active = true; pd.local_tail = local_tail; pd.prn_mask = prn_mask; pd.n_active = n_active; pd.n_cells = n_cells;
+    pd.has_enable = enable != nullptr;
+    if (enable) pd.enable.assign(enable, enable + h->n_prn);
     return GB_OK;
 }
 
-static int stage_chunk(gb_handle* h, const gb_c32* iq, int K)
+static int search_finish(gb_handle* h, int slot, gb_acq_cell* cells_out)
+{
+    if (slot < 0 || slot > 1 || !h->pend[slot].active) return GB_ESTATE;
+    gb_handle::Pending& pd = h->pend[slot];
+    pd.active = false;
+    CK(cudaEventSynchronize(h->ev_done[slot]));
+    if (pd.n_active > 0) CK(cudaEventElapsedTime(&h->last_acq_ms, h->ev_s0[slot], h->ev_s1[slot]));
+    else h->last_acq_ms = 0.f;
+    if (cells_out) memcpy(cells_out, h->cells_pin_slot[slot], pd.n_cells * sizeof(gb_acq_cell));
+    return GB_OK;
+}
+
+static int search_cells(gb_handle* h, const float2* iq_dev, uint64_t start, uint64_t mask, int K, uint32_t prn_mask,
+                        const uint8_t* enable, gb_acq_cell* cells_out, const gb_c32* host_iq = nullptr, uint64_t local_tail = 0)
+{
+    int rc = search_enqueue(h, iq_dev, start, mask, K, prn_mask, enable, host_iq, local_tail, 0);
+    if (rc) return rc;
+    return search_finish(h, 0, cells_out);
+}
+
+// Host sample buffers cross the boundary WITH their length: K * fft_size samples are read
+static int host_chunk_ok(gb_handle* h, const gb_c32* iq, uint64_t n_samples, int K)
 {
     if (!iq || K < 1) return GB_EINVAL;
     if (h->plan < 0) return GB_ESTATE;
-    const size_t n = (size_t)K * h->N;
-    int rc = ensure(h, &h->chunk, &h->chunk_cap, n);
-    if (rc) return rc;
-    CK(cudaMemcpyAsync(h->chunk, iq, n * sizeof(float2), cudaMemcpyHostToDevice, h->s_acq));
+    if (n_samples < (uint64_t)K * (uint64_t)h->N) return GB_ERANGE;
     return GB_OK;
 }
 
-extern "C" int gb_acq_search_cells(gb_handle* h, const gb_c32* iq, int K, uint32_t prn_mask, const uint8_t* enable,
-                                   gb_acq_cell* cells_out)
+extern "C" int gb_acq_search_cells(gb_handle* h, const gb_c32* iq, uint64_t n_samples, int K, uint32_t prn_mask,
+                                   const uint8_t* enable, gb_acq_cell* cells_out)
 {
     if (!h) return GB_EINVAL;
+    std::lock_guard<std::recursive_mutex> lk(h->mu_acq);
     CK(cudaSetDevice(h->device));
-    if (!iq || K < 1) return GB_EINVAL;
-    if (h->plan < 0) return GB_ESTATE;
-    int rc = ensure(h, &h->chunk, &h->chunk_cap, (size_t)K * h->N);
+    int rc = host_chunk_ok(h, iq, n_samples, K);
+    if (rc) return rc;
+    rc = ensure(h, &h->chunk, &h->chunk_cap, (size_t)K * h->N);
     if (rc) return rc;
     return search_cells(h, h->chunk, 0, ~0ull, K, prn_mask, enable, cells_out, iq);
 }
@@ -1200,11 +1321,15 @@ extern "C" int gb_acq_search_cells_ring(gb_handle* h, uint64_t local_tail, int K
                                         const uint8_t* enable, gb_acq_cell* cells_out)
 {
     if (!h || K < 1) return GB_EINVAL;
+    std::lock_guard<std::recursive_mutex> lk(h->mu_acq);
     if (h->plan < 0) return GB_ESTATE;
     CK(cudaSetDevice(h->device));
-    int rc = ring_range_ok(h, local_tail, (uint64_t)K * h->N);
-    if (rc) return rc;
-    CK(cudaStreamWaitEvent(h->s_acq, h->ev_copy, 0));
+    {
+        std::lock_guard<std::recursive_mutex> lr(h->mu_ring);   // the writer thread may be inside gb_ring_write
+        int rc = ring_range_ok(h, local_tail, (uint64_t)K * h->N);
+        if (rc) return rc;
+        CK(cudaStreamWaitEvent(h->s_acq, h->ev_copy, 0));
+    }
     return search_cells(h, h->ring, local_tail, h->ring_cap - 1, K, prn_mask, enable, cells_out);
 }
 
@@ -1250,13 +1375,13 @@ extern "C" int gb_acq_decide(const gb_acq_cell* cells, const float* carr, int D,
     return GB_OK;
 }
 
-static int decide_all(gb_handle* h, uint64_t local_tail, uint32_t prn_mask, const uint8_t* enable, gb_acq_result* results)
+static int decide_all(gb_handle* h, int slot, uint64_t local_tail, uint32_t prn_mask, const uint8_t* enable, gb_acq_result* results)
 {
     for (int p = 0; p < h->n_prn; p++) {
         const bool on = enable ? enable[p] != 0 : (p < 32 ? ((prn_mask >> p) & 1u) != 0 : true);
         if (on) {
-            int rc = gb_acq_decide(h->cells_pin + (size_t)p * h->D, h->carr.data(), h->D, p + 1, h->N, h->fs, local_tail,
-                                   h->threshold, &results[p]);
+            int rc = gb_acq_decide(h->cells_pin_slot[slot] + (size_t)p * h->D, h->carr.data(), h->D, p + 1, h->N, h->fs,
+                                   local_tail, h->threshold, &results[p]);
             if (rc) return rc;
         } else {
             memset(&results[p], 0, sizeof(gb_acq_result));
@@ -1267,31 +1392,97 @@ static int decide_all(gb_handle* h, uint64_t local_tail, uint32_t prn_mask, cons
     return GB_OK;
 }
 
-extern "C" int gb_acq_search(gb_handle* h, const gb_c32* iq, int K, uint64_t local_tail, uint32_t prn_mask,
+extern "C" int gb_acq_search(gb_handle* h, const gb_c32* iq, uint64_t n_samples, int K, uint64_t local_tail, uint32_t prn_mask,
                              const uint8_t* enable, gb_acq_result* results)
 {
-    if (!results) return GB_EINVAL;
-    int rc = gb_acq_search_cells(h, iq, K, prn_mask, enable, nullptr);
+    if (!h || !results) return GB_EINVAL;
+    std::lock_guard<std::recursive_mutex> lk(h->mu_acq);
+    int rc = gb_acq_search_cells(h, iq, n_samples, K, prn_mask, enable, nullptr);
     if (rc) return rc;
-    return decide_all(h, local_tail, prn_mask, enable, results);
+    return decide_all(h, 0, local_tail, prn_mask, enable, results);
 }
 
 extern "C" int gb_acq_search_ring(gb_handle* h, uint64_t local_tail, int K, uint32_t prn_mask, const uint8_t* enable,
                                   gb_acq_result* results)
 {
-    if (!results) return GB_EINVAL;
+    if (!h || !results) return GB_EINVAL;
+    std::lock_guard<std::recursive_mutex> lk(h->mu_acq);
     int rc = gb_acq_search_cells_ring(h, local_tail, K, prn_mask, enable, nullptr);
     if (rc) return rc;
-    return decide_all(h, local_tail, prn_mask, enable, results);
+    return decide_all(h, 0, local_tail, prn_mask, enable, results);
 }
 
-extern "C" int gb_acq_bin_power(gb_handle* h, const gb_c32* iq, int K, int prn, int doppler_bin, float* power_out)
+// Asynchronous pair on ONE handle (two slots): enqueue returns as soon as the copies and kernels are queued; the upload
+// of the next search overlaps the inverse kernel of the one in flight.  iq must stay valid (and should be pinned) until
+// the matching wait.
+extern "C" int gb_acq_search_enqueue(gb_handle* h, const gb_c32* iq, uint64_t n_samples, int K, uint64_t local_tail,
+                                     uint32_t prn_mask, const uint8_t* enable, int slot)
+{
+    if (!h) return GB_EINVAL;
+    std::lock_guard<std::recursive_mutex> lk(h->mu_acq);
+    CK(cudaSetDevice(h->device));
+    int rc = host_chunk_ok(h, iq, n_samples, K);
+    if (rc) return rc;
+    rc = ensure(h, &h->chunk, &h->chunk_cap, (size_t)K * h->N);
+    if (rc) return rc;
+    return search_enqueue(h, h->chunk, 0, ~0ull, K, prn_mask, enable, iq, local_tail, slot);
+}
+
+extern "C" int gb_acq_search_wait(gb_handle* h, int slot, gb_acq_result* results, gb_acq_cell* cells_out)
+{
+    if (!h || slot < 0 || slot > 1) return GB_EINVAL;
+    std::lock_guard<std::recursive_mutex> lk(h->mu_acq);
+    CK(cudaSetDevice(h->device));
+    const gb_handle::Pending pd = h->pend[slot];
+    int rc = search_finish(h, slot, cells_out);
+    if (rc) return rc;
+    if (results) return decide_all(h, slot, pd.local_tail, pd.prn_mask, pd.has_enable ? pd.enable.data() : nullptr, results);
+    return GB_OK;
+}
+
+// n_rec recordings searched back to back with the pair above (recording r + 1 uploads while r is being searched)
+extern "C" int gb_acq_search_batch(gb_handle* h, const gb_c32* const* recordings, int n_rec, uint64_t n_samples, int K,
+                                   uint64_t local_tail, uint32_t prn_mask, const uint8_t* enable, gb_acq_result* results)
+{
+    if (!h || !recordings || !results || n_rec < 1) return GB_EINVAL;
+    std::lock_guard<std::recursive_mutex> lk(h->mu_acq);
+    int rc = gb_acq_search_enqueue(h, recordings[0], n_samples, K, local_tail, prn_mask, enable, 0);
+    if (rc) return rc;
+    for (int r = 0; r < n_rec; r++) {
+        if (r + 1 < n_rec) {
+            rc = gb_acq_search_enqueue(h, recordings[r + 1], n_samples, K, local_tail, prn_mask, enable, (r + 1) & 1);
+            if (rc) {
+                gb_acq_search_wait(h, r & 1, nullptr, nullptr);
+                return rc;
+            }
+        }
+        rc = gb_acq_search_wait(h, r & 1, results + (size_t)r * h->n_prn, nullptr);
+        if (rc) return rc;
+    }
+    return GB_OK;
+}
+
+static int stage_chunk(gb_handle* h, const gb_c32* iq, int K)
+{
+    const size_t n = (size_t)K * h->N;
+    int rc = ensure(h, &h->chunk, &h->chunk_cap, n);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(h->chunk, iq, n * sizeof(float2), cudaMemcpyHostToDevice, h->s_acq));
+    return GB_OK;
+}
+
+extern "C" int gb_acq_bin_power(gb_handle* h, const gb_c32* iq, uint64_t n_samples, int K, int prn, int doppler_bin,
+                                float* power_out)
 {
     if (!h || !power_out) return GB_EINVAL;
+    std::lock_guard<std::recursive_mutex> lk(h->mu_acq);
     if (h->plan < 0 || h->D == 0) return GB_ESTATE;
     if (prn < 1 || prn > h->n_prn || doppler_bin < 0 || doppler_bin >= h->D || K % h->n_coh != 0) return GB_EINVAL;
+    if (h->pend[0].active || h->pend[1].active) return GB_ESTATE;   // not while an enqueued search is in flight
     CK(cudaSetDevice(h->device));
-    int rc = stage_chunk(h, iq, K);
+    int rc = host_chunk_ok(h, iq, n_samples, K);
+    if (rc) return rc;
+    rc = stage_chunk(h, iq, K);
     if (rc) return rc;
     h->rows_pin[0] = prn - 1;
     CK(cudaMemcpyAsync(h->rows_dev, h->rows_pin, sizeof(int), cudaMemcpyHostToDevice, h->s_acq));
@@ -1318,10 +1509,8 @@ extern "C" int gb_acq_bin_power(gb_handle* h, const gb_c32* iq, int K, int prn, 
         const size_t need = (size_t)h->n_prn * h->D;
         if (h->cells_cap < need) {
             if (h->cells_dev) cudaFree(h->cells_dev);
-            if (h->cells_pin) cudaFreeHost(h->cells_pin);
-            h->cells_dev = nullptr; h->cells_pin = nullptr; h->cells_cap = 0;
+            h->cells_dev = nullptr; h->cells_cap = 0;
             CK(cudaMalloc((void**)&h->cells_dev, need * sizeof(gb_acq_cell)));
-            CK(cudaMallocHost((void**)&h->cells_pin, need * sizeof(gb_acq_cell)));
             h->cells_cap = need;
         }
         a.tables = h->tables + (size_t)doppler_bin * h->N;
@@ -1413,6 +1602,7 @@ extern "C" int gb_acq_fine_doppler(gb_handle* h, const gb_c32* long_samples, uin
                                    gb_fine_result* out, float* mag_out)
 {
     if (!h || !long_samples || n_long < 1) return GB_EINVAL;
+    std::lock_guard<std::recursive_mutex> lk(h->mu_acq);
     CK(cudaSetDevice(h->device));
     int rc = ensure(h, &h->fine_x, &h->fine_x_cap, (size_t)n_long);
     if (rc) return rc;
@@ -1424,6 +1614,7 @@ extern "C" int gb_acq_fine_doppler_ring(gb_handle* h, uint64_t start, uint64_t n
                                         const gb_fine_req* req, int n_req, const int8_t* codes1023, gb_fine_result* out)
 {
     if (!h || n_long < 1) return GB_EINVAL;
+    std::lock_guard<std::recursive_mutex> lk(h->mu_acq);
     CK(cudaSetDevice(h->device));
     int rc = ring_range_ok(h, start, n_long);
     if (rc) return rc;
@@ -1440,6 +1631,7 @@ extern "C" float gb_acq_last_kernel_ms(gb_handle* h) { return h ? h->last_acq_ms
 extern "C" int gb_bench_fp32_tflops(gb_handle* h, float* tflops_out)
 {
     if (!h || !tflops_out) return GB_EINVAL;
+    std::lock_guard<std::recursive_mutex> lk(h->mu_acq);
     CK(cudaSetDevice(h->device));
     int sms = 0;
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
@@ -1469,6 +1661,7 @@ static int fft_common(gb_handle* h, int n, int inverse, const void* in, void* ou
                       int n_out)
 {
     if (!h || !in || !out || batch < 1) return GB_EINVAL;
+    std::lock_guard<std::recursive_mutex> lk(h->mu_acq);
     const int plan = gb::acq_plan_index(n);
     if (plan < 0) return GB_EUNSUPPORTED;
     CK(cudaSetDevice(h->device));
@@ -1542,6 +1735,16 @@ extern "C" int gb_trk_channel_start(gb_trk_channel* c, const gb_acq_result* r)
     c->state = GB_TRK_TRACKING;
     return GB_OK;
 }
+// the same hand-over with the C/A row of the satellite itself (prn - 1), i.e. without the reference's Q6 off-by-one
+extern "C" int gb_trk_channel_start_corrected(gb_trk_channel* c, const gb_acq_result* r)
+{
+    const int rc = gb_trk_channel_start(c, r);
+    if (rc) return rc;
+    if (r->prn < 1 || r->prn > 32) return GB_EINVAL;
+    c->code_row = (uint8_t)(r->prn - 1);
+    return GB_OK;
+}
+
 // TrackingChannel::reset (do_tracking.rs:311-326, Q9)
 extern "C" int gb_trk_channel_reset(gb_trk_channel* c)
 {
@@ -1571,11 +1774,19 @@ static int trk_reserve(gb_handle* h, int n)
     return GB_OK;
 }
 
-static int trk_validate(const gb_trk_channel* ch, int n, float* fs_max)
+// Largest sample rate of the batch.  A channel whose code_row is out of the table (the reference's get_ca_chip indexes
+// GPS_CA_CODE_32_PRN[prn], so PRN 32 panics there, Q6) does not fail the batch: it alone is idled (`bad[c]` = 1, handled
+// by the callers like a reset: state IDLE, lost = 1) and every other channel runs.
+static int trk_validate(const gb_trk_channel* ch, int n, float* fs_max, std::vector<uint8_t>* bad)
 {
     float m = 0.f;
+    if (bad) bad->assign(n, 0);
     for (int c = 0; c < n; c++) {
-        if (ch[c].code_row >= 32) return GB_EINVAL;  // GPS_CA_CODE_32_PRN[32] is out of bounds in the reference (Q6)
+        if (ch[c].code_row >= 32 && ch[c].state == GB_TRK_TRACKING) {
+            if (bad) (*bad)[c] = 1;
+            continue;
+        }
+        if (!(ch[c].fs > 0.f)) return GB_EINVAL;
         if (ch[c].fs > m) m = ch[c].fs;
     }
     *fs_max = m;
@@ -1591,12 +1802,17 @@ static int trk_n_max(float fs_max)
 extern "C" int gb_trk_upload(gb_handle* h, const gb_trk_channel* ch, int n)
 {
     if (!h || !ch || n < 1) return GB_EINVAL;
+    std::lock_guard<std::recursive_mutex> lk(h->mu_trk);
     CK(cudaSetDevice(h->device));
     float fs_max;
-    int rc = trk_validate(ch, n, &fs_max);
+    int rc = trk_validate(ch, n, &fs_max, &h->trk_bad);
     if (rc) return rc;
     rc = trk_reserve(h, n);
     if (rc) return rc;
+    h->trk_stage.assign(ch, ch + n);
+    for (int c = 0; c < n; c++)
+        if (h->trk_bad[c]) gb_trk_channel_reset(&h->trk_stage[c]);   // the offending channel idles, the others run
+    ch = h->trk_stage.data();
     CK(cudaMemcpyAsync(h->ch_dev, ch, sizeof(gb_trk_channel) * n, cudaMemcpyHostToDevice, h->s_trk));
     CK(cudaMemsetAsync(h->corr_dev, 0, sizeof(gb_trk_corr) * n, h->s_trk));
     CK(cudaStreamSynchronize(h->s_trk));
@@ -1608,6 +1824,7 @@ extern "C" int gb_trk_upload(gb_handle* h, const gb_trk_channel* ch, int n)
 extern "C" int gb_trk_download(gb_handle* h, gb_trk_channel* ch, int n)
 {
     if (!h || !ch || n < 1 || n > h->n_ch) return GB_EINVAL;
+    std::lock_guard<std::recursive_mutex> lk(h->mu_trk);
     CK(cudaSetDevice(h->device));
     CK(cudaMemcpyAsync(ch, h->ch_dev, sizeof(gb_trk_channel) * n, cudaMemcpyDeviceToHost, h->s_trk));
     CK(cudaStreamSynchronize(h->s_trk));
@@ -1617,26 +1834,37 @@ extern "C" int gb_trk_download(gb_handle* h, gb_trk_channel* ch, int n)
 static int trk_launch_ring(gb_handle* h, int n_epochs, int mode, int filters, float* hist_dev)
 {
     gb::TrkArgs a;
-    a.samples = h->ring; a.mask = h->ring_cap - 1; a.head = h->ring_head; a.capacity = h->ring_cap;
+    {
+        std::lock_guard<std::recursive_mutex> lr(h->mu_ring);   // the writer thread may be inside gb_ring_write
+        a.samples = h->ring; a.mask = h->ring_cap - 1; a.head = h->ring_head; a.capacity = h->ring_cap;
+        CK(cudaStreamWaitEvent(h->s_trk, h->ev_copy, 0));
+    }
     a.offsets = nullptr;
     a.ch = h->ch_dev; a.ca_table = h->ca_table_dev;
     a.n_channels = h->n_ch; a.n_epochs = n_epochs; a.filters = filters; a.n_max = trk_n_max(h->trk_fs_max);
     a.corr = h->corr_dev; a.prompt_hist = hist_dev; a.ran = h->ran_dev; a.lost = h->lost_dev;
-    CK(cudaStreamWaitEvent(h->s_trk, h->ev_copy, 0));
+    if (mode == GB_TRK_ORDERED) {
+        // the in-order sums keep n_max rotated samples + 3 chip rows in shared memory
+        int optin = 0;
+        CK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+        if (gb::trk_ordered_smem_bytes(a.n_max) > (size_t)optin) return GB_EUNSUPPORTED;
+    }
     CK(cudaEventRecord(h->ev_t0, h->s_trk));
     CK(gb::trk_launch(a, mode, h->s_trk));
     CK(cudaEventRecord(h->ev_t1, h->s_trk));
     return GB_OK;
 }
 
-extern "C" int gb_trk_run(gb_handle* h, int n_epochs, int mode, float* prompt_hist)
+static int trk_run_common(gb_handle* h, int n_epochs, int mode, float* prompt_hist, bool keep)
 {
     if (!h || n_epochs < 1 || (mode != GB_TRK_FAST && mode != GB_TRK_ORDERED)) return GB_EINVAL;
+    std::lock_guard<std::recursive_mutex> lk(h->mu_trk);
     if (!h->ring || h->n_ch == 0) return GB_ESTATE;
     CK(cudaSetDevice(h->device));
     float* hist_dev = nullptr;
     const size_t hist_n = (size_t)n_epochs * h->n_ch * 2;
-    if (prompt_hist) {
+    h->hist_epochs = 0; h->hist_channels = 0;
+    if (prompt_hist || keep) {
         int rc = ensure(h, &h->hist_dev, &h->hist_cap, hist_n);
         if (rc) return rc;
         CK(cudaMemsetAsync(h->hist_dev, 0, hist_n * sizeof(float), h->s_trk));
@@ -1647,12 +1875,22 @@ extern "C" int gb_trk_run(gb_handle* h, int n_epochs, int mode, float* prompt_hi
     if (prompt_hist) CK(cudaMemcpyAsync(prompt_hist, h->hist_dev, hist_n * sizeof(float), cudaMemcpyDeviceToHost, h->s_trk));
     CK(cudaStreamSynchronize(h->s_trk));
     CK(cudaEventElapsedTime(&h->last_trk_ms, h->ev_t0, h->ev_t1));
+    if (hist_dev) { h->hist_epochs = n_epochs; h->hist_channels = h->n_ch; }
     return GB_OK;
 }
+
+extern "C" int gb_trk_run(gb_handle* h, int n_epochs, int mode, float* prompt_hist)
+{
+    return trk_run_common(h, n_epochs, mode, prompt_hist, false);
+}
+
+// same run; the prompt history stays on the device for gb_nav_bit_sync(h, NULL, ...) (no D2H -> H2D bounce)
+extern "C" int gb_trk_run_keep(gb_handle* h, int n_epochs, int mode) { return trk_run_common(h, n_epochs, mode, nullptr, true); }
 
 extern "C" int gb_trk_epoch(gb_handle* h, gb_trk_channel* ch, int n, int mode, gb_trk_corr* out, uint8_t* ran, uint8_t* lost)
 {
     if (!h || !ch || n < 1 || (mode != GB_TRK_FAST && mode != GB_TRK_ORDERED)) return GB_EINVAL;
+    std::lock_guard<std::recursive_mutex> lk(h->mu_trk);
     if (!h->ring) return GB_ESTATE;
     int rc = gb_trk_upload(h, ch, n);
     if (rc) return rc;
@@ -1664,20 +1902,37 @@ extern "C" int gb_trk_epoch(gb_handle* h, gb_trk_channel* ch, int n, int mode, g
     if (lost) CK(cudaMemcpyAsync(lost, h->lost_dev, n, cudaMemcpyDeviceToHost, h->s_trk));
     CK(cudaStreamSynchronize(h->s_trk));
     CK(cudaEventElapsedTime(&h->last_trk_ms, h->ev_t0, h->ev_t1));
+    if (lost)
+        for (int c = 0; c < n; c++)
+            if (h->trk_bad[c]) lost[c] = 1;   // idled by the upload (code_row out of the table): reported like SatelliteLost
     return GB_OK;
 }
 
-extern "C" int gb_trk_correlate(gb_handle* h, gb_trk_channel* ch, int n, const gb_c32* data, const uint64_t* offsets,
-                                int mode, gb_trk_corr* out)
+extern "C" int gb_trk_correlate(gb_handle* h, gb_trk_channel* ch, int n, const gb_c32* data, uint64_t n_data,
+                                const uint64_t* offsets, int mode, gb_trk_corr* out)
 {
     if (!h || !ch || !data || !offsets || !out || n < 1 || (mode != GB_TRK_FAST && mode != GB_TRK_ORDERED))
         return GB_EINVAL;
+    std::lock_guard<std::recursive_mutex> lk(h->mu_trk);
+    // every channel's segment must lie inside the caller's buffer (the reference slices data_samples[0..n], :176)
+    size_t total = 0;
+    int n_max = 0;
+    for (int c = 0; c < n; c++) {
+        const uint64_t spc = ch[c].num_samples_per_code;
+        if (spc == 0 || spc > (1u << 22)) return GB_EINVAL;
+        if (offsets[c] > n_data || spc > n_data - offsets[c]) return GB_ERANGE;
+        const size_t end = (size_t)offsets[c] + (size_t)spc;
+        if (end > total) total = end;
+        if ((int)spc > n_max) n_max = (int)spc;
+    }
+    for (int c = 0; c < n; c++)
+        if (ch[c].code_row >= 32) return GB_EINVAL;   // open-loop call: nothing to idle, the row does not exist (Q6)
     int rc = gb_trk_upload(h, ch, n);
     if (rc) return rc;
-    size_t total = 0;
-    for (int c = 0; c < n; c++) {
-        const size_t end = (size_t)offsets[c] + (size_t)ch[c].num_samples_per_code;
-        if (end > total) total = end;
+    if (mode == GB_TRK_ORDERED) {
+        int optin = 0;
+        CK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+        if (gb::trk_ordered_smem_bytes(n_max) > (size_t)optin) return GB_EUNSUPPORTED;
     }
     rc = ensure(h, &h->trk_data, &h->trk_data_cap, total);
     if (rc) return rc;
@@ -1688,9 +1943,6 @@ extern "C" int gb_trk_correlate(gb_handle* h, gb_trk_channel* ch, int n, const g
     a.offsets = h->offs_dev;
     a.ch = h->ch_dev; a.ca_table = h->ca_table_dev;
     a.n_channels = n; a.n_epochs = 1; a.filters = 0;
-    int n_max = 0;
-    for (int c = 0; c < n; c++)
-        if ((int)ch[c].num_samples_per_code > n_max) n_max = (int)ch[c].num_samples_per_code;
     a.n_max = n_max;
     a.corr = h->corr_dev; a.prompt_hist = nullptr; a.ran = h->ran_dev; a.lost = h->lost_dev;
     CK(cudaEventRecord(h->ev_t0, h->s_trk));
@@ -1709,17 +1961,24 @@ extern "C" float gb_trk_last_kernel_ms(gb_handle* h) { return h ? h->last_trk_ms
 extern "C" int gb_nav_bit_sync(gb_handle* h, const float* prompt_hist, int n_epochs, int n_channels, gb_nav_sync* out,
                                int8_t* bits, int max_bits)
 {
-    if (!h || !prompt_hist || !out || !bits || n_epochs < 1 || n_channels < 1 || max_bits < 1) return GB_EINVAL;
+    if (!h || !out || !bits || n_epochs < 1 || n_channels < 1 || max_bits < 1) return GB_EINVAL;
+    std::lock_guard<std::recursive_mutex> lk(h->mu_trk);
     CK(cudaSetDevice(h->device));
     const size_t hist_n = (size_t)n_epochs * n_channels * 2;
-    int rc = ensure(h, &h->hist_dev, &h->hist_cap, hist_n);
-    if (rc) return rc;
+    if (!prompt_hist) {
+        // the history gb_trk_run_keep / gb_trk_run left on the device
+        if (!h->hist_dev || h->hist_epochs != n_epochs || h->hist_channels != n_channels) return GB_ESTATE;
+    } else {
+        int rc = ensure(h, &h->hist_dev, &h->hist_cap, hist_n);
+        if (rc) return rc;
+        h->hist_epochs = 0; h->hist_channels = 0;
+    }
     gb_nav_sync* st_dev = nullptr;
     int8_t* bits_dev = nullptr;
     CK(cudaMalloc((void**)&st_dev, sizeof(gb_nav_sync) * n_channels));
     cudaError_t e = cudaMalloc((void**)&bits_dev, (size_t)n_channels * max_bits);
     if (e != cudaSuccess) { cudaFree(st_dev); return fail(h, e, "cudaMalloc"); }
-    e = cudaMemcpyAsync(h->hist_dev, prompt_hist, hist_n * sizeof(float), cudaMemcpyHostToDevice, h->s_trk);
+    if (prompt_hist) e = cudaMemcpyAsync(h->hist_dev, prompt_hist, hist_n * sizeof(float), cudaMemcpyHostToDevice, h->s_trk);
     if (e == cudaSuccess) e = cudaMemsetAsync(bits_dev, 0, (size_t)n_channels * max_bits, h->s_trk);
     if (e == cudaSuccess) {
         nav_bit_sync_kernel<<<(n_channels + 63) / 64, 64, 0, h->s_trk>>>(h->hist_dev, n_epochs, n_channels, st_dev, bits_dev, max_bits);
@@ -1731,5 +1990,227 @@ extern "C" int gb_nav_bit_sync(gb_handle* h, const float* prompt_hist, int n_epo
     cudaFree(st_dev);
     cudaFree(bits_dev);
     if (e != cudaSuccess) return fail(h, e, "nav_bit_sync");
+    return GB_OK;
+}
+
+// ------------------------------------------------------------------ multi-GPU: sharding + the one collective
+// The units of both paths are independent (PRNs / recordings / channels), so ranks never exchange samples or spectra.
+// What the host needs from the library is (a) the partition and (b) the final gather of the per-PRN result tables --
+// "a final NCCL gather of per-PRN peaks over NVLink".  One process per GPU: rank 0 makes a unique id, the host ships its
+// 128 bytes to the peers by whatever transport it already has (the bench uses torch.distributed's store, a Rust host
+// would use its own channel), every rank calls gb_group_init.  NCCL is loaded with dlopen at that moment: the library has
+// no link-time NCCL dependency and single-GPU users never need it.
+#include <dlfcn.h>
+
+namespace {
+
+struct NcclId {
+    char internal[128];
+};
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(NcclId*) = nullptr;
+    int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool ok = false;
+};
+std::mutex g_nccl_mu;
+NcclApi g_nccl;
+
+const NcclApi* nccl_api()
+{
+    std::lock_guard<std::mutex> lk(g_nccl_mu);
+    if (g_nccl.ok) return &g_nccl;
+    if (!g_nccl.lib) {
+        // a process that already carries NCCL (PyTorch bundles one) resolves to that copy by SONAME
+        for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+            g_nccl.lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+            if (g_nccl.lib) break;
+        }
+    }
+    if (!g_nccl.lib) return nullptr;
+    g_nccl.GetUniqueId = (int (*)(NcclId*))dlsym(g_nccl.lib, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (int (*)(void**, int, NcclId, int))dlsym(g_nccl.lib, "ncclCommInitRank");
+    g_nccl.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(g_nccl.lib, "ncclAllGather");
+    g_nccl.CommDestroy = (int (*)(void*))dlsym(g_nccl.lib, "ncclCommDestroy");
+    g_nccl.GetErrorString = (const char* (*)(int))dlsym(g_nccl.lib, "ncclGetErrorString");
+    g_nccl.ok = g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.AllGather && g_nccl.CommDestroy;
+    return g_nccl.ok ? &g_nccl : nullptr;
+}
+
+}  // namespace
+
+struct gb_group {
+    gb_handle* h = nullptr;
+    void* comm = nullptr;
+    int rank = 0, world = 1;
+    cudaStream_t s = nullptr;            // its own stream: a gather overlaps the next search
+    uint8_t *send_dev = nullptr, *recv_dev = nullptr;
+    size_t send_cap = 0, recv_cap = 0;
+    uint8_t* send_pin[2] = {nullptr, nullptr};
+    uint8_t* recv_pin[2] = {nullptr, nullptr};
+    size_t pin_cap[2] = {0, 0};
+    size_t bytes[2] = {0, 0};
+    bool active[2] = {false, false};
+    cudaEvent_t done[2] = {nullptr, nullptr};
+    std::mutex mu;
+};
+
+extern "C" uint32_t gb_shard_prn_mask(int rank, int world, int n_prn, uint32_t base_mask)
+{
+    // bit (prn - 1) set for the PRNs this rank searches: the PRNs selected by base_mask dealt round-robin
+    // (the reference's mask convention, do_acquisition.rs:307)
+    if (world < 1 || rank < 0 || rank >= world || n_prn < 1) return 0;
+    uint32_t mask = 0;
+    int k = 0;
+    for (int p = 0; p < n_prn && p < 32; p++)
+        if ((base_mask >> p) & 1u) {
+            if (k % world == rank) mask |= 1u << p;
+            k++;
+        }
+    return mask;
+}
+
+extern "C" int gb_shard_range(int n_items, int rank, int world, int* first, int* count)
+{
+    // contiguous block partition of recordings / channels
+    if (n_items < 0 || world < 1 || rank < 0 || rank >= world || !first || !count) return GB_EINVAL;
+    const int per = (n_items + world - 1) / world;
+    const int lo = std::min(n_items, rank * per);
+    *first = lo;
+    *count = std::min(n_items, lo + per) - lo;
+    return GB_OK;
+}
+
+extern "C" int gb_group_unique_id(uint8_t* id128)
+{
+    if (!id128) return GB_EINVAL;
+    const NcclApi* api = nccl_api();
+    if (!api) return GB_ENCCL;
+    NcclId id;
+    if (api->GetUniqueId(&id) != 0) return GB_ENCCL;
+    memcpy(id128, id.internal, 128);
+    return GB_OK;
+}
+
+extern "C" int gb_group_init(gb_handle* h, const uint8_t* id128, int rank, int world, gb_group** out)
+{
+    if (!h || !id128 || !out || world < 1 || rank < 0 || rank >= world) return GB_EINVAL;
+    const NcclApi* api = nccl_api();
+    if (!api) return GB_ENCCL;
+    CK(cudaSetDevice(h->device));
+    gb_group* g = new gb_group();
+    g->h = h; g->rank = rank; g->world = world;
+    NcclId id;
+    memcpy(id.internal, id128, 128);
+    const int rc = api->CommInitRank(&g->comm, world, id, rank);
+    if (rc != 0) {
+        h->last_err = std::string("ncclCommInitRank: ") + (api->GetErrorString ? api->GetErrorString(rc) : "error");
+        delete g;
+        return GB_ENCCL;
+    }
+    cudaError_t e = cudaStreamCreateWithFlags(&g->s, cudaStreamNonBlocking);
+    for (int s = 0; s < 2 && e == cudaSuccess; s++) e = cudaEventCreateWithFlags(&g->done[s], cudaEventDisableTiming);
+    if (e != cudaSuccess) {
+        api->CommDestroy(g->comm);
+        delete g;
+        return fail(h, e, "gb_group_init");
+    }
+    *out = g;
+    return GB_OK;
+}
+
+extern "C" int gb_group_rank(gb_group* g) { return g ? g->rank : GB_EINVAL; }
+extern "C" int gb_group_world(gb_group* g) { return g ? g->world : GB_EINVAL; }
+
+// every rank contributes `bytes` bytes of host memory; after the matching _end, all_out holds world x bytes, rank-major,
+// on every rank.  H2D from pinned staging, ONE ncclAllGather on the group's stream, D2H -- nothing waits until _end.
+extern "C" int gb_group_allgather_begin(gb_group* g, const void* mine, uint64_t bytes, int slot)
+{
+    if (!g || !mine || bytes == 0 || slot < 0 || slot > 1) return GB_EINVAL;
+    std::lock_guard<std::mutex> lk(g->mu);
+    gb_handle* h = g->h;
+    if (g->active[slot]) return GB_ESTATE;
+    const NcclApi* api = nccl_api();
+    if (!api) return GB_ENCCL;
+    CK(cudaSetDevice(h->device));
+    const size_t total = (size_t)bytes * g->world;
+    if (g->pin_cap[slot] < total) {
+        if (g->send_pin[slot]) cudaFreeHost(g->send_pin[slot]);
+        if (g->recv_pin[slot]) cudaFreeHost(g->recv_pin[slot]);
+        g->send_pin[slot] = g->recv_pin[slot] = nullptr; g->pin_cap[slot] = 0;
+        CK(cudaMallocHost((void**)&g->send_pin[slot], bytes));
+        CK(cudaMallocHost((void**)&g->recv_pin[slot], total));
+        g->pin_cap[slot] = total;
+    }
+    if (g->send_cap < bytes || g->recv_cap < total) {
+        CK(cudaStreamSynchronize(g->s));
+        if (g->send_dev) cudaFree(g->send_dev);
+        if (g->recv_dev) cudaFree(g->recv_dev);
+        g->send_dev = g->recv_dev = nullptr; g->send_cap = g->recv_cap = 0;
+        CK(cudaMalloc((void**)&g->send_dev, bytes));
+        CK(cudaMalloc((void**)&g->recv_dev, total));
+        g->send_cap = bytes; g->recv_cap = total;
+    }
+    memcpy(g->send_pin[slot], mine, bytes);
+    CK(cudaMemcpyAsync(g->send_dev, g->send_pin[slot], bytes, cudaMemcpyHostToDevice, g->s));
+    const int rc = api->AllGather(g->send_dev, g->recv_dev, bytes, /* ncclUint8 */ 1, g->comm, g->s);
+    if (rc != 0) {
+        h->last_err = std::string("ncclAllGather: ") + (api->GetErrorString ? api->GetErrorString(rc) : "error");
+        return GB_ENCCL;
+    }
+    CK(cudaMemcpyAsync(g->recv_pin[slot], g->recv_dev, total, cudaMemcpyDeviceToHost, g->s));
+    CK(cudaEventRecord(g->done[slot], g->s));
+    g->bytes[slot] = bytes;
+    g->active[slot] = true;
+    return GB_OK;
+}
+
+extern "C" int gb_group_allgather_end(gb_group* g, int slot, void* all_out)
+{
+    if (!g || !all_out || slot < 0 || slot > 1) return GB_EINVAL;
+    std::lock_guard<std::mutex> lk(g->mu);
+    gb_handle* h = g->h;
+    if (!g->active[slot]) return GB_ESTATE;
+    g->active[slot] = false;
+    CK(cudaSetDevice(h->device));
+    CK(cudaEventSynchronize(g->done[slot]));
+    memcpy(all_out, g->recv_pin[slot], g->bytes[slot] * g->world);
+    return GB_OK;
+}
+
+extern "C" int gb_group_allgather(gb_group* g, const void* mine, uint64_t bytes, void* all_out)
+{
+    int rc = gb_group_allgather_begin(g, mine, bytes, 0);
+    if (rc) return rc;
+    return gb_group_allgather_end(g, 0, all_out);
+}
+
+// the final gather of the path: n result structs per rank -> world x n on every rank
+extern "C" int gb_group_gather_results(gb_group* g, const gb_acq_result* mine, int n, gb_acq_result* all)
+{
+    if (n < 1) return GB_EINVAL;
+    return gb_group_allgather(g, mine, (uint64_t)n * sizeof(gb_acq_result), all);
+}
+
+extern "C" int gb_group_destroy(gb_group* g)
+{
+    if (!g) return GB_EINVAL;
+    cudaSetDevice(g->h->device);
+    if (g->s) cudaStreamSynchronize(g->s);
+    const NcclApi* api = nccl_api();
+    if (api && g->comm) api->CommDestroy(g->comm);
+    if (g->send_dev) cudaFree(g->send_dev);
+    if (g->recv_dev) cudaFree(g->recv_dev);
+    for (int s = 0; s < 2; s++) {
+        if (g->send_pin[s]) cudaFreeHost(g->send_pin[s]);
+        if (g->recv_pin[s]) cudaFreeHost(g->recv_pin[s]);
+        if (g->done[s]) cudaEventDestroy(g->done[s]);
+    }
+    if (g->s) cudaStreamDestroy(g->s);
+    cudaGetLastError();
+    delete g;
     return GB_OK;
 }

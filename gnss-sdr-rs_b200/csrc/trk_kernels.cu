@@ -414,11 +414,13 @@ template <int MODE, int TRK_T> __global__ void __launch_bounds__(TRK_T) trk_kern
     }
 }
 
+size_t trk_ordered_smem_bytes(int n_max) { return (1024 + 128) * sizeof(float) + (size_t)n_max * (sizeof(float2) + 3) + 16; }
+
 template <int T> static cudaError_t launch_t(const TrkArgs& a, int mode, cudaStream_t st)
 {
     size_t smem = (1024 + 128) * sizeof(float) + (mode == GB_TRK_ORDERED ? 0 : 1024 * sizeof(float4));
     if (mode == GB_TRK_ORDERED) {
-        smem += (size_t)a.n_max * (sizeof(float2) + 3) + 16;
+        smem = trk_ordered_smem_bytes(a.n_max);
         if (smem > 48 * 1024) {
             cudaError_t e = cudaFuncSetAttribute(trk_kernel<GB_TRK_ORDERED, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;

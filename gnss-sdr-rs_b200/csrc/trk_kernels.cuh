@@ -24,6 +24,8 @@ struct TrkArgs {
 };
 
 cudaError_t trk_launch(const TrkArgs& a, int mode, cudaStream_t st);
+// dynamic shared memory of the ORDERED kernel for epochs of up to n_max samples
+size_t trk_ordered_smem_bytes(int n_max);
 // warp-specialised FAST kernel for ring-fed epochs with loop filters (trk_ws.cu)
 bool trk_ws_supported(const TrkArgs& a);
 cudaError_t trk_ws_launch(const TrkArgs& a, cudaStream_t st, int variant);

@@ -9,6 +9,7 @@
 #include <cstdint>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <optional>
 #include <set>
 #include <stdexcept>
@@ -47,9 +48,33 @@ class GpuEngine {
     GpuEngine& operator=(const GpuEngine&) = delete;
     gb_handle* raw() const { return h_; }
 
+    // Per-engine caches behind the kept per-worker API (AcquisitionWorker::search_satellite is called by 32 rayon
+    // threads with the SAME samples_chunk and the SAME doppler_table, do_acquisition.rs:302-313).  One lock; the first
+    // caller uploads the tables and runs ONE fused search for all PRNs, the other 31 read its results.
+    std::mutex mu;
+    uint64_t tables_key = 0;       // identity of the Doppler tables now on the device (0 = none)
+    uint64_t search_key = 0;       // identity of the (chunk, tables, local_tail, K) whose results are cached
+    std::vector<gb_acq_result> search_results;
+    void invalidate_caches() { std::lock_guard<std::mutex> lk(mu); tables_key = 0; search_key = 0; }
+
   private:
     gb_handle* h_ = nullptr;
 };
+
+// identity of a buffer: address, length and a strided sample of its contents (FNV-1a).  A buffer that is rewritten in
+// place between calls changes its content sample; GpuEngine::invalidate_caches() is there for the adversarial case.
+inline uint64_t buffer_key(const void* p, size_t bytes, uint64_t seed)
+{
+    uint64_t h = 1469598103934665603ull ^ seed;
+    auto mix = [&](uint64_t v) { h = (h ^ v) * 1099511628211ull; };
+    mix((uint64_t)(uintptr_t)p);
+    mix((uint64_t)bytes);
+    const unsigned char* b = static_cast<const unsigned char*>(p);
+    const size_t step = bytes > 4096 ? bytes / 509 : 1;   // ~500 probes spread over the buffer (+ its last bytes)
+    for (size_t i = 0; i < bytes; i += step) mix(b[i]);
+    for (size_t i = bytes > 64 ? bytes - 64 : 0; i < bytes; i++) mix(b[i]);
+    return h ? h : 1;
+}
 
 // constants (do_acquisition.rs:20-23, do_tracking.rs:16-29, gps_property_constants.rs:3-5)
 constexpr float FREQ_SEARCH_ACQUISITION_HZ = 14e3f;
@@ -155,32 +180,39 @@ class AcquisitionWorker {
     AcquisitionWorker(std::shared_ptr<GpuEngine> e, uint8_t prn, size_t fft_size, float freq_sampling_hz)
         : e_(std::move(e)), prn_(prn), fft_size_(fft_size), fs_(freq_sampling_hz)
     {
-        const int rc = gb_acq_configure(e_->raw(), (int)fft_size, freq_sampling_hz, PRN_SEARCH_ACQUISITION_TOTAL, nullptr);
+        // planned once per (fft_size, fs): the other 31 constructors of the reference's worker set return at once
+        const int rc = gb_acq_configure_once(e_->raw(), (int)fft_size, freq_sampling_hz, PRN_SEARCH_ACQUISITION_TOTAL);
         if (rc) throw AcqError(rc);
     }
 
-    static void upload_tables(GpuEngine& e, const std::vector<DopplerShiftTable>& t)
+    // Uploads the tables unless these very tables are already on the device.  Returns their identity.
+    static uint64_t upload_tables(GpuEngine& e, const std::vector<DopplerShiftTable>& t)
     {
-        std::vector<Complex32> flat;
-        std::vector<float> carr;
-        for (const auto& d : t) {
-            flat.insert(flat.end(), d.table.begin(), d.table.end());
-            carr.push_back(d.doppler_freq_hz);
-        }
-        const int rc = gb_acq_set_doppler_tables(e.raw(), flat.data(), carr.data(), (int)carr.size());
-        if (rc) throw AcqError(rc);
+        std::lock_guard<std::mutex> lk(e.mu);
+        return upload_tables_locked(e, t);
     }
 
+    // The reference signature.  Thread-safe: the 32 workers of one receiver may call it concurrently on one engine.
+    // The first call for a (samples_chunk, doppler_table, local_tail, num_integrations) runs ONE fused search for all
+    // 32 PRNs; every later call with the same arguments -- the other workers of the rayon loop -- reads that result.
     std::optional<AcquisitionResult> search_satellite(const std::vector<Complex32>& samples_chunk,
                                                       const std::vector<DopplerShiftTable>& doppler_table, size_t local_tail,
                                                       size_t num_integrations)
     {
-        upload_tables(*e_, doppler_table);
-        std::vector<gb_acq_result> res(PRN_SEARCH_ACQUISITION_TOTAL);
-        const int rc = gb_acq_search(e_->raw(), samples_chunk.data(), (int)num_integrations, local_tail, 1u << (prn_ - 1),
-                                     nullptr, res.data());
-        if (rc) throw AcqError(rc);
-        return convert(res[prn_ - 1]);
+        GpuEngine& e = *e_;
+        std::lock_guard<std::mutex> lk(e.mu);
+        const uint64_t tkey = upload_tables_locked(e, doppler_table);
+        uint64_t key = buffer_key(samples_chunk.data(), samples_chunk.size() * sizeof(Complex32), tkey);
+        key = buffer_key(&local_tail, 0, key ^ (uint64_t)local_tail * 0x9E3779B97F4A7C15ull ^ (uint64_t)num_integrations << 48);
+        if (key != e.search_key || e.search_results.size() != PRN_SEARCH_ACQUISITION_TOTAL) {
+            e.search_key = 0;
+            e.search_results.assign(PRN_SEARCH_ACQUISITION_TOTAL, gb_acq_result{});
+            const int rc = gb_acq_search(e.raw(), samples_chunk.data(), samples_chunk.size(), (int)num_integrations, local_tail,
+                                         0xFFFFFFFFu, nullptr, e.search_results.data());
+            if (rc) throw AcqError(rc);
+            e.search_key = key;
+        }
+        return convert(e.search_results[prn_ - 1]);
     }
 
     // all PRNs selected by `mask` in one fused launch (the rayon loop)
@@ -188,7 +220,8 @@ class AcquisitionWorker {
                                                      size_t num_integrations, uint32_t mask)
     {
         std::vector<gb_acq_result> res(PRN_SEARCH_ACQUISITION_TOTAL);
-        const int rc = gb_acq_search(e.raw(), samples_chunk.data(), (int)num_integrations, local_tail, mask, nullptr, res.data());
+        const int rc = gb_acq_search(e.raw(), samples_chunk.data(), samples_chunk.size(), (int)num_integrations, local_tail, mask,
+                                     nullptr, res.data());
         if (rc) throw AcqError(rc);
         std::vector<AcquisitionResult> out;
         for (const auto& r : res)
@@ -197,6 +230,29 @@ class AcquisitionWorker {
     }
 
   private:
+    static uint64_t upload_tables_locked(GpuEngine& e, const std::vector<DopplerShiftTable>& t)
+    {
+        if (t.empty()) throw AcqError(GB_EINVAL);
+        uint64_t key = buffer_key(t.data(), 0, (uint64_t)t.size());
+        for (const auto& d : t) {
+            key = buffer_key(d.table.data(), d.table.size() * sizeof(Complex32), key);
+            key = buffer_key(&d.doppler_freq_hz, sizeof(float), key);
+        }
+        if (key == e.tables_key) return key;
+        e.tables_key = 0;
+        e.search_key = 0;
+        std::vector<Complex32> flat;
+        std::vector<float> carr;
+        flat.reserve(t.size() * t[0].table.size());
+        for (const auto& d : t) {
+            flat.insert(flat.end(), d.table.begin(), d.table.end());
+            carr.push_back(d.doppler_freq_hz);
+        }
+        const int rc = gb_acq_set_doppler_tables(e.raw(), flat.data(), carr.data(), (int)carr.size());
+        if (rc) throw AcqError(rc);
+        e.tables_key = key;
+        return key;
+    }
     static std::optional<AcquisitionResult> convert(const gb_acq_result& r)
     {
         if (!r.found) return std::nullopt;
@@ -249,12 +305,16 @@ class TrackingChannel {
   public:
     gb_trk_channel s;
     TrackingChannel(uint8_t id, float fs) { gb_trk_channel_init(&s, id, fs); }
-    void start(const AcquisitionResult& r)
+    // start(AcquisitionResult) (do_tracking.rs:148-154).  The reference's get_ca_chip indexes the C/A table with `prn`
+    // instead of `prn - 1` (Q6): a channel started that way correlates with the NEXT satellite's code and never locks.
+    // The default here is the satellite's own row; reference_code_row = true reproduces the reference verbatim.
+    void start(const AcquisitionResult& r, bool reference_code_row = false)
     {
         gb_acq_result g{};
         g.prn = r.prn; g.found = 1; g.carrier_freq = r.carrier_freq; g.code_phase_chips = r.code_phase_chips;
         g.sample_global_index = r.sample_global_index; g.fs = r.fs;
-        gb_trk_channel_start(&s, &g);
+        const int rc = reference_code_row ? gb_trk_channel_start(&s, &g) : gb_trk_channel_start_corrected(&s, &g);
+        if (rc) throw TrackingError(rc);
     }
     bool is_active() const { return s.state == GB_TRK_TRACKING; }
     void reset() { gb_trk_channel_reset(&s); }
@@ -265,7 +325,7 @@ class TrackingChannel {
         s.num_samples_per_code = data_samples.size();
         const uint64_t off = 0;
         gb_trk_corr out{};
-        const int rc = gb_trk_correlate(e.raw(), &s, 1, data_samples.data(), &off, mode, &out);
+        const int rc = gb_trk_correlate(e.raw(), &s, 1, data_samples.data(), data_samples.size(), &off, mode, &out);
         if (rc) throw TrackingError(rc);
         return out;
     }
@@ -359,6 +419,14 @@ class RealFFT {
         std::vector<Complex32> out(len_ / 2 + 1);
         const int rc = gb_rfft(e_->raw(), (int)len_, input.data(), out.data(), 1);
         if (rc) throw AcqError(rc);
+        return out;
+    }
+    // fft.rs:47-55: norm_sqr of the len/2 + 1 bins
+    std::vector<float> power_spectrum(const std::vector<float>& input)
+    {
+        const std::vector<Complex32> y = execute(input);
+        std::vector<float> out(y.size());
+        for (size_t i = 0; i < y.size(); i++) out[i] = y[i].re * y[i].re + y[i].im * y[i].im;
         return out;
     }
 

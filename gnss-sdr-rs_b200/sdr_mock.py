@@ -38,7 +38,7 @@ def ca_code(prn):
 
 
 def _signal(prn, n_samples, fs, carrier_hz, code_phase_samples, amp, code_doppler=0.0, nav_seed=None, phase0=0.0,
-            real=False):
+            real=False, nav_bits=None):
     t = np.arange(n_samples, dtype=np.float64)
     code = ca_code(prn).astype(np.float64)
     rate = 1.023e6 * (1.0 + code_doppler)
@@ -50,6 +50,11 @@ def _signal(prn, n_samples, fs, carrier_hz, code_phase_samples, amp, code_dopple
         periods = np.floor((t - code_phase_samples) * rate / fs / 1023.0).astype(np.int64)
         bits = rng.integers(0, 2, size=int(periods.max() // 20 + 3)) * 2 - 1
         sig = sig * bits[(periods // 20) + 1]
+    elif nav_bits is not None:
+        # a caller-planted 50 bps stream (+-1), repeated as needed; bit k covers code periods 20 k .. 20 k + 19
+        periods = np.floor((t - code_phase_samples) * rate / fs / 1023.0).astype(np.int64)
+        nb = np.asarray(nav_bits, np.float64)
+        sig = sig * nb[((periods // 20) + 1) % len(nb)]
     ph = 2.0 * np.pi * ((carrier_hz * t / fs) % 1.0) + phase0
     if real:
         return amp * sig * np.cos(ph)
@@ -85,7 +90,8 @@ def baseband(fs, n_ms, sats, seed=0x6E56, noise_sigma=1.0, nav=False):
         # C/N0 = A^2 / (sigma^2 / fs)  =>  A = sigma * sqrt(10^(cn0/10) / fs)
         amp = noise_sigma * np.sqrt(10.0 ** (s["cn0_dbhz"] / 10.0) / fs)
         x += _signal(s["prn"], n, fs, s["doppler"], s["code_phase"], amp, code_doppler=s["doppler"] / 1575.42e6,
-                     nav_seed=(seed * 131 + k) if nav else None, phase0=rng.uniform(0, 2 * np.pi))
+                     nav_seed=(seed * 131 + k) if (nav and s.get("nav_bits") is None) else None,
+                     phase0=rng.uniform(0, 2 * np.pi), nav_bits=s.get("nav_bits"))
     return x.astype(np.complex64)
 
 

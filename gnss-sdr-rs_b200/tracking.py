@@ -20,13 +20,16 @@ def channel_array(n, fs):
     return arr
 
 
-def start(ch, prn, carrier_freq, code_phase_chips, sample_global_index, fs, code_row=None):
-    """TrackingChannel::start(AcquisitionResult).  code_row=None keeps the reference's row (= prn, Q6)."""
+def start(ch, prn, carrier_freq, code_phase_chips, sample_global_index, fs, code_row=None, corrected=False):
+    """TrackingChannel::start(AcquisitionResult).  By default the reference's row (= prn, Q6: the channel correlates
+    with PRN + 1's code); corrected=True uses the satellite's own row (prn - 1, gb_trk_channel_start_corrected);
+    code_row overrides both."""
     r = _ffi.AcqResult()
     r.prn, r.found = int(prn), 1
     r.carrier_freq, r.code_phase_chips, r.fs = float(carrier_freq), float(code_phase_chips), float(fs)
     r.sample_global_index = int(sample_global_index)
-    _ffi.check(_ffi.lib().gb_trk_channel_start(C.byref(ch), C.byref(r)), "gb_trk_channel_start")
+    fn = "gb_trk_channel_start_corrected" if corrected else "gb_trk_channel_start"
+    _ffi.check(getattr(_ffi.lib(), fn)(C.byref(ch), C.byref(r)), fn)
     if code_row is not None:
         ch.code_row = int(code_row)
 
@@ -54,7 +57,9 @@ class TrackingEngine:
             total += len(data_list[c])
         data = np.concatenate([np.ascontiguousarray(d, np.complex64) for d in data_list])
         out = np.zeros(n, _ffi.CORR_DTYPE)
-        self.hd.call("gb_trk_correlate", channels, n, _ffi.ptr(data), _ffi.ptr(offs), int(mode), _ffi.ptr(out))
+        # the library checks every segment against the buffer length (a short segment -> GB_ERANGE)
+        self.hd.call("gb_trk_correlate", channels, n, _ffi.ptr(data), int(data.size), _ffi.ptr(offs), int(mode),
+                     _ffi.ptr(out))
         return out
 
     def epoch(self, channels, mode=GB_TRK_FAST):
@@ -70,7 +75,13 @@ class TrackingEngine:
         self.n = len(channels)
         self.hd.call("gb_trk_upload", channels, self.n)
 
-    def run(self, n_epochs, mode=GB_TRK_FAST, want_hist=False):
+    def run(self, n_epochs, mode=GB_TRK_FAST, want_hist=False, keep_on_device=False):
+        """n_epochs do_work epochs per channel in one launch.  keep_on_device: the prompt history stays in HBM for
+        nav_bit_sync(handle, None, ...) instead of coming back to the host."""
+        if keep_on_device:
+            self.hd.call("gb_trk_run_keep", int(n_epochs), int(mode))
+            self.kept = (int(n_epochs), self.n)
+            return None
         hist = np.zeros((n_epochs, self.n, 2), np.float32) if want_hist else None
         self.hd.call("gb_trk_run", int(n_epochs), int(mode), _ffi.ptr(hist))
         return hist
@@ -83,11 +94,15 @@ class TrackingEngine:
         return float(self.hd.L.gb_trk_last_kernel_ms(self.hd.h))
 
 
-def nav_bit_sync(handle, prompt_hist, max_bits=4096):
-    """Bit sync + 20 ms prompt accumulation (N4) on a prompt history [n_epochs, n_channels, 2]."""
-    hist = np.ascontiguousarray(prompt_hist, np.float32)
-    n_epochs, n_channels = hist.shape[0], hist.shape[1]
+def nav_bit_sync(handle, prompt_hist, max_bits=4096, shape=None):
+    """Bit sync + 20 ms prompt accumulation + preamble search (N4) on a prompt history [n_epochs, n_channels, 2];
+    prompt_hist=None with shape=(n_epochs, n_channels): the history TrackingEngine.run(keep_on_device=True) left in HBM."""
+    if prompt_hist is None:
+        hist, (n_epochs, n_channels) = None, shape
+    else:
+        hist = np.ascontiguousarray(prompt_hist, np.float32)
+        n_epochs, n_channels = hist.shape[0], hist.shape[1]
     st = np.zeros(n_channels, _ffi.NAV_DTYPE)
     bits = np.zeros((n_channels, max_bits), np.int8)
-    handle.call("gb_nav_bit_sync", _ffi.ptr(hist), n_epochs, n_channels, _ffi.ptr(st), _ffi.ptr(bits), int(max_bits))
+    handle.call("gb_nav_bit_sync", _ffi.ptr(hist), int(n_epochs), int(n_channels), _ffi.ptr(st), _ffi.ptr(bits), int(max_bits))
     return st, bits

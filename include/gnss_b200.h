@@ -11,9 +11,12 @@
  *
  * Ownership: the caller owns every host buffer passed in or out; the library owns all device
  * memory behind gb_handle and frees it in gb_destroy().  No callbacks, no global state.
- * Threading: one handle may be used from an acquisition thread and a tracking thread at the same
- * time (separate CUDA streams, like main.rs:205-227); calls of the same family on one handle must
- * be serialised by the caller (the reference's &mut self).
+ * Threading: one handle may be used from an acquisition thread, a tracking thread and a sample-writer
+ * thread at the same time (separate CUDA streams, like main.rs:205-227).  Calls of the same family
+ * (gb_acq_* / gb_trk_* / gb_ring_*) on one handle are serialised inside the library by a per-family lock,
+ * so the reference's 32 rayon workers (do_acquisition.rs:302-313) may call into one handle concurrently.
+ * Host sample buffers always cross the boundary with their length; a buffer shorter than the call needs
+ * is refused with GB_ERANGE, never read past its end.
  * There is NO CPU fallback: every compute entry point returns GB_ENODEVICE without a CUDA device.
  */
 #ifndef GNSS_B200_H
@@ -26,7 +29,7 @@
 extern "C" {
 #endif
 
-#define GB_VERSION 111
+#define GB_VERSION 120
 
 /* ---- error codes ---- */
 #define GB_OK 0
@@ -36,7 +39,8 @@ extern "C" {
 #define GB_EUNSUPPORTED (-4) /* fft_size has no sm_100a plan */
 #define GB_ESTATE (-5)       /* call order (e.g. search before configure) */
 #define GB_ENOMEM (-6)
-#define GB_ERANGE (-7)       /* samples requested that the ring no longer / not yet holds */
+#define GB_ERANGE (-7)       /* samples requested that the ring (or the caller's buffer) does not hold */
+#define GB_ENCCL (-8)        /* NCCL could not be loaded or a collective failed (gb_group_*) */
 
 typedef struct gb_handle gb_handle;
 
@@ -133,7 +137,12 @@ typedef struct {
  * codes == NULL: GPS C/A resampled per ca_code.rs:12-27 (n_prn <= 32).
  * codes != NULL: n_prn x fft_size +-1 samples (other constellations / the reference's test codes).
  * Supported fft_size: see gb_acq_supported_sizes(). */
+/* Every call re-plans and resets the per-configuration settings (n_coh = 1, aliasing off, no Doppler tables). */
 int gb_acq_configure(gb_handle *h, int fft_size, float fs, int n_prn, const int8_t *codes);
+/* The per-worker constructor of a drop-in (the reference builds one AcquisitionWorker per PRN, :268-271): plans the
+ * built-in GPS C/A configuration unless exactly this one is already planned, in which case it returns GB_OK at once and
+ * keeps the Doppler tables and settings -- 32 workers cost one plan, not 32. */
+int gb_acq_configure_once(gb_handle *h, int fft_size, float fs, int n_prn);
 int gb_acq_supported_sizes(int *sizes, int cap);
 
 /* DopplerShiftTable::new for each f_d in dopplers[] (doppler_shift.rs:11-21), evaluated on the
@@ -157,26 +166,26 @@ int gb_acq_set_coherent(gb_handle *h, int n_coh);
 #define GB_ACQ_SHARED 1
 #define GB_ACQ_SHARED_PLAIN 2
 int gb_acq_set_mode(gb_handle *h, int mode);
-/* Doppler aliasing (shared chain, on by default).  When two bins of a grid built by gb_acq_make_doppler_tables lie a
+/* Doppler aliasing (shared chain; OFF by default: the default is the reference's own per-bin wipe-off arithmetic).  When two bins of a grid built by gb_acq_make_doppler_tables lie a
  * whole number m of FFT bins (fs / fft_size) apart, the wiped block of one is the other's times exp(-j 2 pi m n / N):
  * its spectrum is the other's circularly shifted by m.  The forward path (wipe-off, coherent sum, forward FFT) then
  * runs for one bin per class only and the inverse kernel pairs that spectrum with the code spectrum shifted by m
  * (the classic circular-shift Doppler search).  Mathematically identical to doppler_shift.rs:11-58; numerically it
  * replaces the f32 rounding of cos(i * step_d) by that of the class's first bin (~1e-6 relative on the power, well
  * inside the 1e-3 contract).  off = every bin runs its own forward path with its own table (reference arithmetic).
- * BASELINE config 2 (50 Hz steps, 1 kHz FFT bins): 201 bins -> 20 forward spectra.  gb_acq_configure switches it
- * back on (like n_coh, it is a per-configuration setting). */
+ * BASELINE config 2 (50 Hz steps, 1 kHz FFT bins): 201 bins -> 20 forward spectra.  A re-planning gb_acq_configure
+ * switches it back off (like n_coh, it is a per-configuration setting). */
 int gb_acq_set_doppler_aliasing(gb_handle *h, int on);
 /* number of forward spectra per group the next shared-chain search computes (== n_doppler when nothing is shared) */
 int gb_acq_forward_bins(gb_handle *h);
 /* samples_per_chip > 0 enables peak2; threshold is is_good_satellite's 7.0 */
 int gb_acq_set_detector(gb_handle *h, float threshold, int samples_per_chip);
 
-/* The fused search over the PRN x Doppler grid.  iq = num_integrations*fft_size host samples
- * (search_satellite's samples_chunk); prn_mask bit (prn-1) selects PRNs as at do_acquisition.rs:307
- * (for n_prn > 32 pass enable[] instead, NULL = all).  cells_out: n_prn x n_doppler, rows of PRNs
- * that were not searched are zero.  May be NULL. */
-int gb_acq_search_cells(gb_handle *h, const gb_c32 *iq, int num_integrations, uint32_t prn_mask,
+/* The fused search over the PRN x Doppler grid.  iq = n_samples host samples of which the first
+ * num_integrations*fft_size are searched (search_satellite's samples_chunk; fewer -> GB_ERANGE); prn_mask bit
+ * (prn-1) selects PRNs as at do_acquisition.rs:307 (for n_prn > 32 pass enable[] instead, NULL = all).
+ * cells_out: n_prn x n_doppler, rows of PRNs that were not searched are zero.  May be NULL. */
+int gb_acq_search_cells(gb_handle *h, const gb_c32 *iq, uint64_t n_samples, int num_integrations, uint32_t prn_mask,
                         const uint8_t *enable, gb_acq_cell *cells_out);
 /* same, reading the chunk from the device ring at absolute index local_tail (do_acquisition.rs:297-301) */
 int gb_acq_search_cells_ring(gb_handle *h, uint64_t local_tail, int num_integrations, uint32_t prn_mask,
@@ -185,12 +194,26 @@ int gb_acq_search_cells_ring(gb_handle *h, uint64_t local_tail, int num_integrat
 int gb_acq_decide(const gb_acq_cell *cells, const float *carr, int n_doppler, int prn, int fft_size, float fs,
                   uint64_t local_tail, float threshold, gb_acq_result *out);
 /* cells + decide for every selected PRN: results[n_prn] */
-int gb_acq_search(gb_handle *h, const gb_c32 *iq, int num_integrations, uint64_t local_tail, uint32_t prn_mask,
-                  const uint8_t *enable, gb_acq_result *results);
+int gb_acq_search(gb_handle *h, const gb_c32 *iq, uint64_t n_samples, int num_integrations, uint64_t local_tail,
+                  uint32_t prn_mask, const uint8_t *enable, gb_acq_result *results);
 int gb_acq_search_ring(gb_handle *h, uint64_t local_tail, int num_integrations, uint32_t prn_mask,
                        const uint8_t *enable, gb_acq_result *results);
+/* Asynchronous form on ONE handle (two slots, 0 / 1): gb_acq_search_enqueue returns as soon as the copies and kernels
+ * are queued, gb_acq_search_wait(slot) delivers that search's results (and, optionally, its cells).  With two searches
+ * alternating between the slots the upload of one overlaps the inverse kernel of the other (cudaMemcpyAsync on the copy
+ * stream, events to the acquisition stream) -- the receiver loop of do_acquisition.rs:297-320 without a stall per chunk.
+ * iq must stay valid and unchanged until the matching wait, and should be pinned host memory (a pageable buffer makes
+ * the copy synchronous).  GB_ESTATE: the slot is still occupied / nothing was enqueued on it. */
+int gb_acq_search_enqueue(gb_handle *h, const gb_c32 *iq, uint64_t n_samples, int num_integrations, uint64_t local_tail,
+                          uint32_t prn_mask, const uint8_t *enable, int slot);
+int gb_acq_search_wait(gb_handle *h, int slot, gb_acq_result *results /* n_prn, may be NULL */,
+                       gb_acq_cell *cells_out /* n_prn x n_doppler, may be NULL */);
+/* n_rec recordings of n_samples each, searched back to back through the pair above; results: n_rec x n_prn */
+int gb_acq_search_batch(gb_handle *h, const gb_c32 *const *recordings, int n_rec, uint64_t n_samples, int num_integrations,
+                        uint64_t local_tail, uint32_t prn_mask, const uint8_t *enable, gb_acq_result *results);
 /* accumulated power row of one (prn, doppler bin) -- diagnostics / tests */
-int gb_acq_bin_power(gb_handle *h, const gb_c32 *iq, int num_integrations, int prn, int doppler_bin, float *power_out);
+int gb_acq_bin_power(gb_handle *h, const gb_c32 *iq, uint64_t n_samples, int num_integrations, int prn, int doppler_bin,
+                     float *power_out);
 /* device time of the last search in milliseconds (CUDA events on the acquisition stream).  For the ring-resident
  * searches this is kernel time only; for the host-buffer searches the sliced upload is overlapped with the forward
  * path inside the same pair of events, so the figure includes the part of the H2D copy that could not be hidden. */
@@ -268,24 +291,32 @@ typedef struct { float i_p, q_p, i_e, q_e, i_l, q_l; } gb_trk_corr;
 
 /* host helpers (no device): TrackingChannel::new / start / reset, LoopFilter::new */
 int gb_trk_channel_init(gb_trk_channel *c, uint8_t id, float fs);
+/* TrackingChannel::start verbatim (do_tracking.rs:148-154): code_row = prn, the reference's Q6 off-by-one (the
+ * channel then correlates with PRN + 1's code; PRN 32 has no row -- the reference panics, here that channel is idled) */
 int gb_trk_channel_start(gb_trk_channel *c, const gb_acq_result *r);
+/* the same hand-over with the satellite's own C/A row (code_row = prn - 1): what a working receiver wants */
+int gb_trk_channel_start_corrected(gb_trk_channel *c, const gb_acq_result *r);
 int gb_trk_channel_reset(gb_trk_channel *c);
 int gb_loop_filter_new(float noise_bw, float damping, float gain, float *tau1, float *tau2);
 
 /* early_late_correlation for n_channels channels, each on its own n = num_samples_per_code host
- * samples laid out back to back in data (offsets[c] = start of channel c's samples).  Updates
- * carrier_phase, code_phase, i_prompt, q_prompt like the reference does; no loop filters. */
-int gb_trk_correlate(gb_handle *h, gb_trk_channel *ch, int n_channels, const gb_c32 *data, const uint64_t *offsets,
-                     int mode, gb_trk_corr *out);
+ * samples inside data[0 .. n_data) (offsets[c] = start of channel c's samples; a segment that leaves the buffer ->
+ * GB_ERANGE).  Updates carrier_phase, code_phase, i_prompt, q_prompt like the reference does; no loop filters. */
+int gb_trk_correlate(gb_handle *h, gb_trk_channel *ch, int n_channels, const gb_c32 *data, uint64_t n_data,
+                     const uint64_t *offsets, int mode, gb_trk_corr *out);
 /* do_work for every active channel whose samples are in the ring (TrackingChannel::update,
  * do_tracking.rs:160-210): one launch, correlators + lock test + loop filters + bookkeeping.
- * ran[c] = 1 if the channel consumed an epoch; lost[c] = 1 if it emitted SatelliteLost. */
+ * ran[c] = 1 if the channel consumed an epoch; lost[c] = 1 if it emitted SatelliteLost.  A channel whose code_row is
+ * outside the C/A table (the reference panics) is reset to idle and reported lost; the other channels run.
+ * GB_TRK_ORDERED keeps an epoch's samples in shared memory: sample rates above ~20 Msps return GB_EUNSUPPORTED. */
 int gb_trk_epoch(gb_handle *h, gb_trk_channel *ch, int n_channels, int mode, gb_trk_corr *out, uint8_t *ran,
                  uint8_t *lost);
 /* persistent form: state stays on the device; n_epochs epochs per channel (or until the ring head)
  * in one launch.  prompt_hist (optional): n_epochs x n_channels x {i_p, q_p}. */
 int gb_trk_upload(gb_handle *h, const gb_trk_channel *ch, int n_channels);
 int gb_trk_run(gb_handle *h, int n_epochs, int mode, float *prompt_hist);
+/* same run; the prompt history is kept on the device for gb_nav_bit_sync(h, NULL, ...) -- no copy to the host and back */
+int gb_trk_run_keep(gb_handle *h, int n_epochs, int mode);
 int gb_trk_download(gb_handle *h, gb_trk_channel *ch, int n_channels);
 float gb_trk_last_kernel_ms(gb_handle *h);
 
@@ -301,9 +332,40 @@ typedef struct {
     int32_t sync_epoch; /* epoch at which synchronisation was declared, -1 if never */
     int32_t n_bits;
     uint32_t bit_sync_buff[20];
+    /* preamble search on the bit stream (check_preamble_syn, decoding.rs:215-226): 8 consecutive bits correlated with
+     * GPS_CA_PREAMBLE {1,-1,-1,-1,1,-1,1,1}, frame sync when the sum is +-8, polarity = its sign. */
+    int32_t preamble_bit;   /* first bit index whose 8-bit window matches (the intended sliding search), -1 if none */
+    int32_t polarity;       /* +1 / -1, 0 if none */
+    int32_t ref_frame_sync; /* the legacy's literal outcome: its buff_preamble is never popped, so only the FIRST 8 bits
+                               are ever tested (decoding.rs:131-136, 207-209) */
+    int32_t ref_polarity;
 } gb_nav_sync;
+/* prompt_hist == NULL: the history the last gb_trk_run / gb_trk_run_keep left on the device (same n_epochs, n_channels) */
 int gb_nav_bit_sync(gb_handle *h, const float *prompt_hist /* n_epochs x n_channels x 2 */, int n_epochs, int n_channels,
                     gb_nav_sync *out, int8_t *bits, int max_bits);
+
+/* ------------------------------------------------------------------ multi-GPU: sharding + the final gather
+ * replaces the rayon fan-out of do_acquisition.rs:302-313 / do_tracking.rs:364-371 across the GPUs of one box.  The units
+ * are independent (PRNs of one recording, recordings of a batch, tracking channels), so there is NO data-path collective:
+ * every rank (one process / one gb_handle per GPU) works on its share and the per-PRN result tables are gathered ONCE at
+ * the end -- one ncclAllGather over NVLink on the group's own stream.  In a single process that drives several GPUs the
+ * handles simply write into the caller's memory and no collective is needed at all.
+ * NCCL is loaded with dlopen("libnccl.so.2") by the first gb_group_* call (GB_ENCCL if absent). */
+uint32_t gb_shard_prn_mask(int rank, int world, int n_prn, uint32_t base_mask); /* PRNs of base_mask dealt round-robin */
+int gb_shard_range(int n_items, int rank, int world, int *first, int *count);     /* contiguous blocks of recordings / channels */
+typedef struct gb_group gb_group;
+int gb_group_unique_id(uint8_t *id128);   /* rank 0; ship the 128 bytes to the peers by any host transport */
+int gb_group_init(gb_handle *h, const uint8_t *id128, int rank, int world, gb_group **out);
+int gb_group_rank(gb_group *g);
+int gb_group_world(gb_group *g);
+/* every rank contributes `bytes` bytes (host); all_out = world x bytes, rank-major, on every rank */
+int gb_group_allgather(gb_group *g, const void *mine, uint64_t bytes, void *all_out);
+/* asynchronous pair (two slots): the gather of batch k runs while batch k+1 is being searched */
+int gb_group_allgather_begin(gb_group *g, const void *mine, uint64_t bytes, int slot);
+int gb_group_allgather_end(gb_group *g, int slot, void *all_out);
+/* n results per rank -> world x n on every rank */
+int gb_group_gather_results(gb_group *g, const gb_acq_result *mine, int n, gb_acq_result *all);
+int gb_group_destroy(gb_group *g);
 
 #ifdef __cplusplus
 }

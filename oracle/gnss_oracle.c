@@ -806,6 +806,18 @@ void go_nav_bit_sync(const float *prompt_i, int n_epochs, int stride, go_nav_syn
         }
         old_ip = ip;
     }
+    /* check_preamble_syn, decoding.rs:215-226 (see gnss_oracle.h for the legacy's single test) */
+    static const int pre[8] = {1, -1, -1, -1, 1, -1, 1, 1};   /* GPS_CA_PREAMBLE, gps_property_constants.rs:12 */
+    st->preamble_bit = -1;
+    const int nb = st->n_bits < max_bits ? st->n_bits : max_bits;
+    for (int i0 = 0; i0 + 8 <= nb; i0++) {
+        int corr = 0;
+        for (int x = 0; x < 8; x++) corr += (int)bits[i0 + x] * pre[x % 8];
+        const int hit = corr == 8 || corr == -8;
+        if (i0 == 0 && hit) { st->ref_frame_sync = 1; st->ref_polarity = corr > 0 ? 1 : -1; }
+        if (hit && st->preamble_bit < 0) { st->preamble_bit = i0; st->polarity = corr > 0 ? 1 : -1; }
+        if (st->preamble_bit >= 0) break;
+    }
 }
 
 /* ------------------------------------------------------------------ fine Doppler (N3), acquisition_bk.rs:215-302 */

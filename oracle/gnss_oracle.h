@@ -210,6 +210,12 @@ typedef struct {
     int32_t sync_epoch;     /* cnt at which synchronisation was declared, -1 if never */
     int32_t n_bits;
     uint32_t bit_sync_buff[20];
+    /* check_preamble_syn (decoding.rs:215-226) on the emitted bits: corr = sum_{x<8} bits[i0+x] * GPS_CA_PREAMBLE[x % 8]
+     * (gps_property_constants.rs:12), frame sync iff |corr| == 8, polarity = signum(corr).  The legacy pushes every bit
+     * into buff_preamble (:207-209) and tests only while buff_preamble.len() == 8 (:131-136); the VecDeque is never popped,
+     * so only the FIRST 8 bits are ever tested: ref_frame_sync / ref_polarity.  preamble_bit / polarity are the intended
+     * sliding search (first window that matches). */
+    int32_t preamble_bit, polarity, ref_frame_sync, ref_polarity;
 } go_nav_sync;
 void go_nav_bit_sync(const float *prompt_i, int n_epochs, int stride, go_nav_sync *st, int8_t *bits, int max_bits);
 

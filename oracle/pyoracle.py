@@ -50,7 +50,8 @@ class Frontend(C.Structure):
 
 class NavSync(C.Structure):
     _fields_ = [("flag_bit_sync", C.c_int32), ("frame_sync_ind", C.c_int32), ("sync_epoch", C.c_int32),
-                ("n_bits", C.c_int32), ("bit_sync_buff", C.c_uint32 * 20)]
+                ("n_bits", C.c_int32), ("bit_sync_buff", C.c_uint32 * 20), ("preamble_bit", C.c_int32),
+                ("polarity", C.c_int32), ("ref_frame_sync", C.c_int32), ("ref_polarity", C.c_int32)]
 
 
 class FineResult(C.Structure):

@@ -6,6 +6,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
+#include <thread>
 
 #include "../../gnss-sdr-rs_b200/host/gnss_sdr_rs.hpp"
 
@@ -57,10 +59,19 @@ static void test_host_helpers()
     TrackingChannel c(0, 4.096e6f);
     CHECK(!c.is_active() && c.s.num_samples_per_code == 4096);
     AcquisitionResult r; r.prn = 7; r.carrier_freq = 10.f; r.code_phase_chips = 0.5f; r.sample_global_index = 99;
-    c.start(r);
-    CHECK(c.is_active() && c.s.prn == 7 && c.s.code_row == 7 && c.s.next_sample_index == 99);
+    c.start(r);   // default: the satellite's own C/A row
+    CHECK(c.is_active() && c.s.prn == 7 && c.s.code_row == 6 && c.s.next_sample_index == 99);
     c.reset();
     CHECK(!c.is_active() && c.s.code_rate == 0.0f);
+    c.start(r, /*reference_code_row=*/true);   // the reference's get_ca_chip row (Q6)
+    CHECK(c.s.code_row == 7);
+    c.reset();
+    // RealFFT::power_spectrum and the short-buffer refusal need a device; buffer_key is pure host code
+    std::vector<Complex32> a(5000, Complex32{1.f, 2.f}), b(a);
+    CHECK(buffer_key(a.data(), a.size() * sizeof(Complex32), 7) != buffer_key(b.data(), b.size() * sizeof(Complex32), 7));  // address
+    const uint64_t k0 = buffer_key(a.data(), a.size() * sizeof(Complex32), 7);
+    a[4999].im = 3.f;
+    CHECK(buffer_key(a.data(), a.size() * sizeof(Complex32), 7) != k0);   // contents (tail is always probed)
 }
 
 static void test_ring(std::shared_ptr<GpuEngine> e)
@@ -205,7 +216,51 @@ static void test_acquisition(std::shared_ptr<GpuEngine> e)
         std::vector<Complex32> too_short(raw11.begin(), raw11.begin() + N * 10);
         CHECK(!finer_doppler(*e, too_short, false, fine, FS));
     }
+    // The kept per-worker API from 32 threads on ONE engine (the rayon loop of do_acquisition.rs:302-313): every worker
+    // calls search_satellite with the same chunk and tables.  One fused search serves all 32; results equal search_all's.
+    {
+        std::vector<std::unique_ptr<AcquisitionWorker>> workers;
+        for (uint8_t prn = 1; prn <= 32; prn++) workers.emplace_back(new AcquisitionWorker(e, prn, N, FS));   // one plan, 32 cheap constructors
+        std::vector<std::optional<AcquisitionResult>> got(32);
+        std::vector<int> errs(32, 0);
+        const auto t0 = std::chrono::steady_clock::now();
+        std::vector<std::thread> th;
+        for (int p = 0; p < 32; p++)
+            th.emplace_back([&, p]() {
+                try { got[p] = workers[p]->search_satellite(raw, tables, 1234, K); } catch (const AcqError&) { errs[p] = 1; }
+            });
+        for (auto& t : th) t.join();
+        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        auto ref = AcquisitionWorker::search_all(*e, raw, 1234, K, 0xFFFFFFFFu);
+        size_t n_found = 0;
+        for (int p = 0; p < 32; p++) {
+            CHECK(!errs[p]);
+            if (got[p]) n_found++;
+            bool in_ref = false;
+            for (const auto& a : ref)
+                if (a.prn == p + 1) {
+                    in_ref = true;
+                    CHECK(got[p] && got[p]->code_phase_samples == a.code_phase_samples && got[p]->carrier_freq == a.carrier_freq &&
+                          got[p]->sample_global_index == a.sample_global_index && got[p]->mag_relative == a.mag_relative);
+                }
+            CHECK(in_ref == got[p].has_value());
+        }
+        CHECK(n_found == ref.size() && got[5].has_value());
+        printf("32 threads x search_satellite on one engine: %.1f ms, %zu found\n", ms, n_found);
+        // a short chunk is refused, not read past its end
+        std::vector<Complex32> short_chunk(raw.begin(), raw.begin() + N * K - 1);
+        bool threw = false;
+        try { workers[0]->search_satellite(short_chunk, tables, 0, K); } catch (const AcqError& err) { threw = err.code == GB_ERANGE; }
+        CHECK(threw);
+    }
     // FFT facade
+    RealFFT rf(e, 2048);
+    {
+        std::vector<float> xr(2048, 0.f);
+        for (int i = 0; i < 2048; i++) xr[i] = cosf(2.0f * 3.14159265358979323846f * 5.0f * (float)i / 2048.0f);
+        auto ps = rf.power_spectrum(xr);
+        CHECK(ps.size() == 1025 && fabsf(ps[5] - 1024.0f * 1024.0f) < 1.0f && ps[6] < 1e-3f);
+    }
     FFT f(e, 2048);
     std::vector<Complex32> x(2048, Complex32{0.f, 0.f});
     x[1] = Complex32{1.f, 0.f};

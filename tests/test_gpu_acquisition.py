@@ -81,7 +81,8 @@ def test_leftover_warp_kernel_is_bit_identical(gpu, ffi, K, n_coh):
 
 @pytest.mark.parametrize("n", [1024, 2048, 4092, 4096, 8184, 16368, 20000])
 def test_doppler_aliasing_matches_per_bin_tables(gpu, oracle, ffi, n):
-    """Bins a whole number of FFT bins apart share one forward spectrum (gb_acq_set_doppler_aliasing, default on):
+    """Bins a whole number of FFT bins apart share one forward spectrum (gb_acq_set_doppler_aliasing; off by default,
+    the default being the reference's per-bin tables):
     13 bins at 250 Hz over 1 kHz FFT bins -> 4 forward spectra, shifts -1..+2.  Against the same search with every
     bin's own reference table: identical arg-max on every cell with a clear peak, powers within 2e-5 (the f32
     rounding of the table phases is all that differs), through the ring path and the sliced host-pointer path,
@@ -94,6 +95,8 @@ def test_doppler_aliasing_matches_per_bin_tables(gpu, oracle, ffi, n):
     eng = _engine(gpu, n, fs)
     eng.make_doppler_tables(0.0, dopplers)
     eng.set_detector(7.0, 2)
+    assert eng.forward_bins() == len(dopplers)        # default: every bin its own forward path (reference arithmetic)
+    eng.set_doppler_aliasing(True)
     assert eng.forward_bins() == 4
     rb = ring.MulticastRingBuffer(gpu, 1 << 17)
     rb.write_samples(x)
@@ -140,9 +143,11 @@ def test_doppler_aliasing_needs_exact_bin_multiples(gpu):
     eng = _engine(gpu, 16368, 16367600.0)
     grid = np.array(acquisition.reference_doppler_grid(), np.float32)
     eng.make_doppler_tables(4130400.0, grid)
+    eng.set_doppler_aliasing(True)
     assert eng.forward_bins() == len(grid)
     eng2 = _engine(gpu, 4092, 4.092e6)
     carr = eng2.make_doppler_tables(0.0, np.array([0.0, 1000.0, 2000.0, 500.0], np.float32))
+    eng2.set_doppler_aliasing(True)
     assert eng2.forward_bins() == 2
     eng2.set_doppler_tables(eng2.get_doppler_tables(), carr)
     assert eng2.forward_bins() == 4
@@ -355,6 +360,15 @@ def test_errors_and_edge_cases(gpu, ffi):
     with pytest.raises(ffi.GnssB200Error) as e:  # K not a multiple of n_coh
         eng.search_cells(np.zeros(3 * 2048, np.complex64), 3)
     assert e.value.code == ffi.GB_EINVAL
+    eng.set_coherent(1)
+    # host buffers cross the boundary with their length: a chunk shorter than K * fft_size is refused, not read past
+    for call in (lambda: eng.search_cells(np.zeros(2 * 2048 - 1, np.complex64), 2),
+                 lambda: eng.search(np.zeros(2047, np.complex64), 1),
+                 lambda: eng.bin_power(np.zeros(2048, np.complex64), 2, 1, 0),
+                 lambda: eng.search_enqueue(np.zeros(100, np.complex64), 1, 0)):
+        with pytest.raises(ffi.GnssB200Error) as e:
+            call()
+        assert e.value.code == ffi.GB_ERANGE
 
 
 def test_two_handles_on_one_device(ffi):
@@ -402,6 +416,7 @@ def test_headline_kernel_edge_cases(gpu, oracle, ffi):
     dopplers = np.array([-750.0, 250.0, 1250.0, -500.0, 100.0], np.float32)   # carriers 500, 1500, 2500 | 750 | 1350
     eng = _engine(gpu, n, fs)
     carr = eng.make_doppler_tables(f_if, dopplers)
+    eng.set_doppler_aliasing(True)
     assert eng.forward_bins() == 3
     eng.set_detector(7.0, 4)
     mask = (1 << 3) | (1 << 31) | (1 << 10)

@@ -12,7 +12,7 @@ def _build(tmp_path, ffi):
     exe = str(tmp_path / "test_host_mirror")
     libdir = os.path.dirname(ffi.LIB_PATH)
     subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", os.path.join(ROOT, "tests", "cpp", "test_host_mirror.cpp"), "-o", exe,
-                    "-L", libdir, "-lgnss_b200", "-Wl,-rpath," + libdir], check=True)
+                    "-L", libdir, "-lgnss_b200", "-lpthread", "-Wl,-rpath," + libdir], check=True)
     return exe
 
 
