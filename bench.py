@@ -274,13 +274,15 @@ def tracking_roofline(r, peak_tf):
             "peak_source": "gb_bench_fp32_tflops FMA probe, measured live"}
 
 
-def tracking_cpu_baseline(stream, cores, n_epochs=400):
+def tracking_cpu_baseline(stream, cores, n_epochs=2000):
     """The oracle's TrackingManager loop (go_trk_run_all: do_work per channel and epoch, channels spread over all host
-    threads like rayon at do_tracking.rs:364-371) on a bounded sample: 4 channels per thread, n_epochs epochs."""
+    threads like rayon at do_tracking.rs:364-371) on a bounded sample: 32 channels per thread, n_epochs epochs
+    (~10 s of CPU work)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import pyoracle as orc
     x, sats = stream
-    n_ch = max(32, 4 * cores)
+    n_ch = max(256, 32 * cores)
+    n_epochs = min(n_epochs, len(x) // TRK_N - 2)
     rng = np.random.default_rng(0x6E58)
     och = (orc.TrkChannel * n_ch)()
     for c in range(n_ch):

@@ -107,6 +107,11 @@ SIGNATURES = {
     "gb_fft_c2c": (_i32, [_vp, _i32, _i32, _vp, _vp, _i32]),
     "gb_fft_power_spectrum": (_i32, [_vp, _i32, _vp, _vp, _i32]),
     "gb_rfft": (_i32, [_vp, _i32, _vp, _vp, _i32]),
+    "gb_rfft_power_spectrum": (_i32, [_vp, _i32, _vp, _vp, _i32]),
+    "gb_fft_c2c_f64": (_i32, [_vp, _i32, _i32, _vp, _vp, _i32]),
+    "gb_fft_power_spectrum_f64": (_i32, [_vp, _i32, _vp, _vp, _i32]),
+    "gb_rfft_f64": (_i32, [_vp, _i32, _vp, _vp, _i32]),
+    "gb_rfft_power_spectrum_f64": (_i32, [_vp, _i32, _vp, _vp, _i32]),
     "gb_trk_channel_init": (_i32, [_vp, C.c_uint8, _f32]),
     "gb_trk_channel_start": (_i32, [_vp, _vp]),
     "gb_trk_channel_start_corrected": (_i32, [_vp, _vp]),

@@ -234,38 +234,49 @@ def finer_doppler(handle, long_samples, requests, fs, long_ms=LEGACY_LONG_SAMPLE
 
 
 class FFT:
-    """fft.rs:5-30 FFT<f32>."""
+    """fft.rs:5-30 FFT<T>, T = f32 (complex64 input) or f64 (complex128 input); any length."""
 
     def __init__(self, handle, length):
         self.hd, self.len = handle, int(length)
 
     def execute(self, x, inverse=False):
-        x = np.ascontiguousarray(x, np.complex64)
+        f64 = np.asarray(x).dtype == np.complex128
+        x = np.ascontiguousarray(x, np.complex128 if f64 else np.complex64)
         batch = x.size // self.len
         out = np.zeros_like(x)
-        self.hd.call("gb_fft_c2c", self.len, int(inverse), _ffi.ptr(x), _ffi.ptr(out), batch)
+        self.hd.call("gb_fft_c2c_f64" if f64 else "gb_fft_c2c", self.len, int(inverse), _ffi.ptr(x), _ffi.ptr(out), batch)
         return out
 
     def power_spectrum(self, x):
-        x = np.ascontiguousarray(x, np.complex64)
-        out = np.zeros(x.shape, np.float32)
-        self.hd.call("gb_fft_power_spectrum", self.len, _ffi.ptr(x), _ffi.ptr(out), x.size // self.len)
+        f64 = np.asarray(x).dtype == np.complex128
+        x = np.ascontiguousarray(x, np.complex128 if f64 else np.complex64)
+        out = np.zeros(x.shape, np.float64 if f64 else np.float32)
+        self.hd.call("gb_fft_power_spectrum_f64" if f64 else "gb_fft_power_spectrum", self.len, _ffi.ptr(x), _ffi.ptr(out),
+                     x.size // self.len)
         return out
 
 
 class RealFFT:
-    """fft.rs:32-56 RealFFT<f32>."""
+    """fft.rs:32-56 RealFFT<T>, T = f32 or f64 (by the input's dtype); any length."""
 
     def __init__(self, handle, length):
         self.hd, self.len = handle, int(length)
 
-    def execute(self, x):
-        x = np.ascontiguousarray(x, np.float32)
+    def _run(self, x, power):
+        f64 = np.asarray(x).dtype == np.float64
+        x = np.ascontiguousarray(x, np.float64 if f64 else np.float32)
         batch = x.size // self.len
-        out = np.zeros((batch, self.len // 2 + 1), np.complex64)
-        self.hd.call("gb_rfft", self.len, _ffi.ptr(x), _ffi.ptr(out), batch)
+        if power:
+            out = np.zeros((batch, self.len // 2 + 1), np.float64 if f64 else np.float32)
+            name = "gb_rfft_power_spectrum_f64" if f64 else "gb_rfft_power_spectrum"
+        else:
+            out = np.zeros((batch, self.len // 2 + 1), np.complex128 if f64 else np.complex64)
+            name = "gb_rfft_f64" if f64 else "gb_rfft"
+        self.hd.call(name, self.len, _ffi.ptr(x), _ffi.ptr(out), batch)
         return out[0] if x.ndim == 1 else out
 
+    def execute(self, x):
+        return self._run(x, False)
+
     def power_spectrum(self, x):
-        y = self.execute(x)
-        return (y.real * y.real + y.imag * y.imag).astype(np.float32)
+        return self._run(x, True)

@@ -10,6 +10,7 @@
 #include <cooperative_groups.h>
 
 #include "acq_common.cuh"
+#include "acq_generic.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -203,6 +204,13 @@ __global__ void __launch_bounds__(512) reduce_rows_kernel(const float* __restric
 }
 
 // ------------------------------------------------------------------ host side
+cudaError_t acq_launch_reduce_rows(const float* acc_rows, int n, int D, int n_active, const int* rows, int spc, gb_acq_cell* cells,
+                                   cudaStream_t st)
+{
+    reduce_rows_kernel<<<n_active * D, 512, 0, st>>>(acc_rows, n, D, rows, spc, cells);
+    return cudaGetLastError();
+}
+
 int acq_cluster_supported(int n) { return n == kN80k; }
 int acq_cluster_inner(int n) { return n == kN80k ? PI80k::N : 0; }
 int acq_cluster_outer(int n) { return n == kN80k ? kRO : 0; }

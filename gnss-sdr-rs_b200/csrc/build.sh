@@ -8,7 +8,7 @@ FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompil
 if [ -n "$GB_TUNING" ]; then FLAGS="$FLAGS -DGB_TUNING"; fi
 mkdir -p ../build
 need=0
-for f in acq_kernels acq_lw frontend acq_cluster trk_kernels trk_ws fine_doppler gnss_b200; do
+for f in acq_kernels acq_lw acq_generic frontend acq_cluster trk_kernels trk_ws fine_doppler gnss_b200; do
   if [ ! -f ../build/$f.o ] || [ -n "$(find . ../../include -newer ../build/$f.o \( -name '*.cu' -o -name '*.cuh' -o -name '*.h' \) | head -1)" ]; then need=1; fi
 done
 if [ $need -eq 0 ] && [ -f $OUT ] && [ "$1" != "-f" ]; then exit 0; fi
@@ -20,6 +20,7 @@ nvcc $FLAGS -c fine_doppler.cu -o ../build/fine_doppler.o & p5=$!
 nvcc $FLAGS -c acq_lw.cu -o ../build/acq_lw.o & p6=$!
 nvcc $FLAGS -fmad=false -c frontend.cu -o ../build/frontend.o & p7=$!
 nvcc $FLAGS -fmad=false -c trk_ws.cu -o ../build/trk_ws.o & p8=$!
-wait $p1; wait $p2; wait $p3; wait $p4; wait $p5; wait $p6; wait $p7; wait $p8
-nvcc -shared -o $OUT ../build/acq_kernels.o ../build/acq_lw.o ../build/frontend.o ../build/acq_cluster.o ../build/trk_kernels.o ../build/trk_ws.o ../build/fine_doppler.o ../build/gnss_b200.o
+nvcc $FLAGS -c acq_generic.cu -o ../build/acq_generic.o & p9=$!
+wait $p1; wait $p2; wait $p3; wait $p4; wait $p5; wait $p6; wait $p7; wait $p8; wait $p9
+nvcc -shared -o $OUT ../build/acq_kernels.o ../build/acq_lw.o ../build/acq_generic.o ../build/frontend.o ../build/acq_cluster.o ../build/trk_kernels.o ../build/trk_ws.o ../build/fine_doppler.o ../build/gnss_b200.o
 echo "built $OUT"

@@ -15,6 +15,7 @@
 
 #include "../../include/gnss_b200.h"
 #include "acq_kernels.cuh"
+#include "acq_generic.cuh"
 #include "trk_kernels.cuh"
 #include "fine_doppler.cuh"
 #include "frontend.cuh"
@@ -133,6 +134,12 @@ struct gb_handle {
     cudaEvent_t ev_chunk_free = nullptr;   // the last kernel that reads `chunk` has been enqueued behind this event
     bool chunk_free_valid = false;
     bool builtin_codes = false;            // configured with codes == NULL (GPS C/A): an identical re-configure is a no-op
+    // any-length fallback plans (acq_generic.cu), one per length, shared by the acquisition and the FFT facade
+    std::map<int, gb::GenericPlan*> gen_plans;
+    bool generic = false;                  // the configured acquisition length has no tuned plan
+    gb::GenericPlan* gen = nullptr;
+    float2 *gen_s0 = nullptr, *gen_s1 = nullptr;
+    size_t gen_s0_cap = 0, gen_s1_cap = 0;
     float* row_dev = nullptr;
     float last_acq_ms = 0.f;
     cudaEvent_t ev_slice[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // upload slices
@@ -569,6 +576,9 @@ extern "C" int gb_destroy(gb_handle* h)
                         h->fine_mag, h->tables_perm, h->iq_perm};
     for (void* p : dev_ptrs)
         if (p) cudaFree(p);
+    for (auto& kv : h->gen_plans) gb::generic_plan_destroy(kv.second);
+    if (h->gen_s0) cudaFree(h->gen_s0);
+    if (h->gen_s1) cudaFree(h->gen_s1);
     for (auto& r : h->fft) {
         if (r.tw) cudaFree(r.tw);
         if (r.fop) cudaFree(r.fop);
@@ -812,6 +822,20 @@ extern "C" int gb_ring_copy_to_slice(gb_handle* h, uint64_t start, gb_c32* dest,
 }
 
 // ------------------------------------------------------------------ acquisition set-up
+const int kPlanGeneric = 1000;   // h->plan of a length without a tuned plan
+const int kGenericMaxN = 131072;
+
+static int generic_plan_for(gb_handle* h, int n, gb::GenericPlan** out)
+{
+    auto it = h->gen_plans.find(n);
+    if (it != h->gen_plans.end()) { *out = it->second; return GB_OK; }
+    gb::GenericPlan* p = nullptr;
+    CK(gb::generic_plan_create(n, &p, h->s_acq));
+    h->gen_plans[n] = p;
+    *out = p;
+    return GB_OK;
+}
+
 extern "C" int gb_acq_supported_sizes(int* sizes, int cap)
 {
     int n = gb::acq_plan_sizes(sizes, cap);
@@ -825,12 +849,19 @@ extern "C" int gb_acq_configure(gb_handle* h, int fft_size, float fs, int n_prn,
     if (!codes && n_prn > 32) return GB_EINVAL;
     std::lock_guard<std::recursive_mutex> lk(h->mu_acq);
     if (h->pend[0].active || h->pend[1].active) return GB_ESTATE;
-    if (fft_size % 4 != 0) return GB_EUNSUPPORTED;  // apply_doppler_shift leaves len%4 samples stale (A3)
+    // fft_size % 4 != 0: apply_doppler_shift writes only 4 * floor(len / 4) samples (A3); the tail of result_buf keeps the
+    // PREVIOUS block's unnormalised IFFT output, which is fed back as input N times larger every block -- the reference's
+    // own arithmetic overflows to inf / NaN within a dozen blocks (tests/test_oracle_golden.py shows it on the oracle).
+    // There is no behaviour to be a drop-in for, so these lengths are refused.
+    if (fft_size < 4 || fft_size % 4 != 0) return GB_EUNSUPPORTED;
     const bool cluster = gb::acq_cluster_supported(fft_size) != 0;
     if (cluster && !codes) return GB_EINVAL;  // no built-in code has an 80000-sample period
     const int inner = cluster ? gb::acq_cluster_inner(fft_size) : fft_size;
-    const int plan = gb::acq_plan_index(inner);
-    if (plan < 0) return GB_EUNSUPPORTED;
+    int plan = gb::acq_plan_index(inner);
+    // no tuned shared-memory plan: the any-length plan (Bluestein over a power-of-two Stockham FFT, acq_generic.cu)
+    const bool generic = plan < 0;
+    if (generic && (cluster || fft_size > kGenericMaxN)) return GB_EUNSUPPORTED;
+    if (generic) plan = kPlanGeneric;
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->s_acq));
     std::vector<int8_t> host_codes;
@@ -845,8 +876,11 @@ extern "C" int gb_acq_configure(gb_handle* h, int fft_size, float fs, int n_prn,
         }
         codes = host_codes.data();
     }
-    FftRes* fr;
-    int rc = fft_resources(h, plan, inner, &fr);
+    FftRes* fr = nullptr;
+    int rc = GB_OK;
+    gb::GenericPlan* gen = nullptr;
+    if (generic) rc = generic_plan_for(h, fft_size, &gen);
+    else rc = fft_resources(h, plan, inner, &fr);
     if (rc) return rc;
     if (cluster) {
         // outer twiddles W_N^(i q), q = 1..RO-1, i < inner, layout [q-1][i], f64-evaluated
@@ -867,19 +901,29 @@ extern "C" int gb_acq_configure(gb_handle* h, int fft_size, float fs, int n_prn,
     if (h->row_dev) cudaFree(h->row_dev);
     h->code_fft = nullptr; h->codes_dev = nullptr; h->row_dev = nullptr;
     const size_t total = (size_t)n_prn * fft_size;
-    const int spec_len = cluster ? fft_size : gb::acq_plan_spec_len(plan);
+    const int spec_len = (cluster || generic) ? fft_size : gb::acq_plan_spec_len(plan);
     CK(cudaMalloc((void**)&h->code_fft, (size_t)n_prn * spec_len * sizeof(float2)));
     CK(cudaMemsetAsync(h->code_fft, 0, (size_t)n_prn * spec_len * sizeof(float2), h->s_acq));   // row padding
     CK(cudaMalloc((void**)&h->codes_dev, total));
     CK(cudaMalloc((void**)&h->row_dev, sizeof(float) * fft_size));
     CK(cudaMemcpyAsync(h->codes_dev, codes, total, cudaMemcpyHostToDevice, h->s_acq));
-    if (cluster) CK(gb::acq_cluster_launch_code_fft(h->codes_dev, n_prn, h->code_fft, fr->tw, h->otw, h->s_acq));
-    else CK(gb::acq_launch_code_fft(plan, h->codes_dev, n_prn, h->code_fft, fr->tw, fr->npos, h->s_acq));
+    if (generic) {
+        const size_t need = (size_t)n_prn * gb::generic_plan_m(gen);
+        rc = ensure(h, &h->gen_s0, &h->gen_s0_cap, need);
+        if (!rc) rc = ensure(h, &h->gen_s1, &h->gen_s1_cap, need);
+        if (rc) return rc;
+        CK(gb::generic_code_fft(gen, h->codes_dev, n_prn, h->code_fft, h->gen_s0, h->gen_s1, h->s_acq));
+    } else if (cluster) {
+        CK(gb::acq_cluster_launch_code_fft(h->codes_dev, n_prn, h->code_fft, fr->tw, h->otw, h->s_acq));
+    } else {
+        CK(gb::acq_launch_code_fft(plan, h->codes_dev, n_prn, h->code_fft, fr->tw, fr->npos, h->s_acq));
+    }
     CK(cudaStreamSynchronize(h->s_acq));
     h->cluster = cluster;
-    h->plan = plan; h->N = fft_size; h->n_prn = n_prn; h->fs = fs; h->tw = fr->tw;
+    h->generic = generic; h->gen = gen;
+    h->plan = plan; h->N = fft_size; h->n_prn = n_prn; h->fs = fs; h->tw = generic ? nullptr : fr->tw;
     h->spec_len = spec_len;
-    h->pfa = !cluster && gb::acq_plan_is_pfa(plan) != 0;
+    h->pfa = !cluster && !generic && gb::acq_plan_is_pfa(plan) != 0;
     h->npos = h->pfa ? fr->npos : nullptr;
     h->D = 0; h->n_coh = 1;
     h->carr.clear();
@@ -1180,9 +1224,28 @@ static int search_enqueue(gb_handle* h, const float2* iq_dev, uint64_t start, ui
             int rc = ensure(h, &h->iq_perm, &h->iq_perm_cap, (size_t)K * h->N);
             if (rc) return rc;
         }
-        if (host_iq && (h->cluster || h->mode == GB_ACQ_FUSED))
+        if (host_iq && (h->cluster || h->generic || h->mode == GB_ACQ_FUSED))
             CK(cudaMemcpyAsync(h->chunk, host_iq, (size_t)K * h->N * sizeof(float2), cudaMemcpyHostToDevice, h->s_acq));
-        if (h->cluster) {
+        if (h->generic) {
+            // any-length plan: Doppler slabs sized to the scratch (n_active * n_d transforms of M points, <= 1 GiB each)
+            const int M = gb::generic_plan_m(h->gen);
+            size_t max_batch = ((size_t)1 << 27) / (size_t)M;
+            if (max_batch > 32768) max_batch = 32768;
+            int slab = (int)(max_batch / (size_t)n_active);
+            if (slab < 1) return GB_ENOMEM;
+            if (slab > h->D) slab = h->D;
+            int rc = ensure(h, &h->acc_rows, &h->acc_cap, (size_t)n_active * h->D * h->N);
+            if (!rc) rc = ensure(h, &h->gen_s0, &h->gen_s0_cap, (size_t)n_active * slab * M);
+            if (!rc) rc = ensure(h, &h->gen_s1, &h->gen_s1_cap, (size_t)n_active * slab * M);
+            if (rc) return rc;
+            CK(cudaEventRecord(h->ev_s0[slot], h->s_acq));
+            for (int d_lo = 0; d_lo < h->D; d_lo += slab) {
+                const int n_d = (h->D - d_lo) < slab ? (h->D - d_lo) : slab;
+                CK(gb::generic_search_slab(h->gen, a, d_lo, n_d, h->acc_rows, h->gen_s0, h->gen_s1, h->s_acq));
+            }
+            CK(gb::acq_launch_reduce_rows(h->acc_rows, h->N, h->D, n_active, a.rows, h->spc, h->cells_dev, h->s_acq));
+            CK(cudaEventRecord(h->ev_s1[slot], h->s_acq));
+        } else if (h->cluster) {
             if (h->n_coh != 1) return GB_EUNSUPPORTED;
             int rc = ensure(h, &h->acc_rows, &h->acc_cap, (size_t)n_active * h->D * h->N);
             if (rc) return rc;
@@ -1501,6 +1564,21 @@ extern "C" int gb_acq_bin_power(gb_handle* h, const gb_c32* iq, uint64_t n_sampl
         if (rc) return rc;
         CK(pfa_inputs(h, a, K));
     }
+    if (h->generic) {
+        // one (prn, bin) row through the any-length plan: D = 1 view of the requested bin
+        const int M = gb::generic_plan_m(h->gen);
+        rc = ensure(h, &h->acc_rows, &h->acc_cap, (size_t)h->N);
+        if (!rc) rc = ensure(h, &h->gen_s0, &h->gen_s0_cap, (size_t)M);
+        if (!rc) rc = ensure(h, &h->gen_s1, &h->gen_s1_cap, (size_t)M);
+        if (rc) return rc;
+        a.tables = h->tables + (size_t)doppler_bin * h->N;
+        a.rot = h->n_coh > 1 ? h->rot + (size_t)doppler_bin * h->n_coh : nullptr;
+        a.D = 1;
+        CK(gb::generic_search_slab(h->gen, a, 0, 1, h->acc_rows, h->gen_s0, h->gen_s1, h->s_acq));
+        CK(cudaMemcpyAsync(power_out, h->acc_rows, sizeof(float) * h->N, cudaMemcpyDeviceToHost, h->s_acq));
+        CK(cudaStreamSynchronize(h->s_acq));
+        return GB_OK;
+    }
     if (h->cluster) {
         // one (prn, bin) cell row: the cluster kernel leaves the accumulated power row in acc_rows
         if (h->n_coh != 1) return GB_EUNSUPPORTED;
@@ -1657,13 +1735,56 @@ extern "C" int gb_bench_fp32_tflops(gb_handle* h, float* tflops_out)
 }
 
 // ------------------------------------------------------------------ FFT facade (fft.rs:5-56)
+// Any length (and f64): the any-length plan of acq_generic.cu -- FFT<T> / RealFFT<T> accept every N in the reference
+// (rustfft / realfft planners, fft.rs:12-15, :39-40) and are generic over f32 / f64.
+template <typename T, typename T2>
+static int fft_any(gb_handle* h, int n, int inverse, const void* in, void* out, int batch, int real_in, int power_out, int n_out)
+{
+    if (n > kGenericMaxN || batch > 32768) return GB_EUNSUPPORTED;
+    CK(cudaSetDevice(h->device));
+    gb::GenericPlan* gp;
+    int rc = generic_plan_for(h, n, &gp);
+    if (rc) return rc;
+    const size_t M = (size_t)gb::generic_plan_m(gp);
+    const size_t in_bytes = (size_t)batch * n * (real_in ? sizeof(T) : sizeof(T2));
+    const size_t out_bytes = (size_t)batch * n_out * (power_out ? sizeof(T) : sizeof(T2));
+    void *din = nullptr, *dout = nullptr;
+    T2 *x = nullptr, *s0 = nullptr, *s1 = nullptr;
+    cudaError_t e = cudaMalloc(&din, in_bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&dout, out_bytes);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&x, sizeof(T2) * (size_t)batch * n);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&s0, sizeof(T2) * (size_t)batch * M);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&s1, sizeof(T2) * (size_t)batch * M);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(din, in, in_bytes, cudaMemcpyHostToDevice, h->s_acq);
+    if (e == cudaSuccess) {
+        const size_t total = (size_t)batch * n;
+        if (sizeof(T) == 4) {
+            float2* xin = real_in ? (float2*)x : (float2*)din;
+            if (real_in) e = gb::generic_real_to_complex((const float*)din, (float2*)x, total, h->s_acq);
+            if (e == cudaSuccess) e = gb::generic_dft_f32(gp, inverse, xin, (float2*)x, batch, (float2*)s0, (float2*)s1, h->s_acq);
+            if (e == cudaSuccess) e = gb::generic_take_f32((const float2*)x, dout, n, n_out, batch, power_out, h->s_acq);
+        } else {
+            double2* xin = real_in ? (double2*)x : (double2*)din;
+            if (real_in) e = gb::generic_r2c_f64((const double*)din, (double2*)x, total, h->s_acq);
+            if (e == cudaSuccess) e = gb::generic_dft_f64(gp, inverse, xin, (double2*)x, batch, (double2*)s0, (double2*)s1, h->s_acq);
+            if (e == cudaSuccess) e = gb::generic_take_f64((const double2*)x, dout, n, n_out, batch, power_out, h->s_acq);
+        }
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, dout, out_bytes, cudaMemcpyDeviceToHost, h->s_acq);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->s_acq);
+    for (void* p : {din, dout, (void*)x, (void*)s0, (void*)s1})
+        if (p) cudaFree(p);
+    if (e != cudaSuccess) return fail(h, e, "fft (any-length plan)");
+    return GB_OK;
+}
+
 static int fft_common(gb_handle* h, int n, int inverse, const void* in, void* out, int batch, int real_in, int power_out,
                       int n_out)
 {
-    if (!h || !in || !out || batch < 1) return GB_EINVAL;
+    if (!h || !in || !out || batch < 1 || n < 2) return GB_EINVAL;
     std::lock_guard<std::recursive_mutex> lk(h->mu_acq);
     const int plan = gb::acq_plan_index(n);
-    if (plan < 0) return GB_EUNSUPPORTED;
+    if (plan < 0) return fft_any<float, float2>(h, n, inverse, in, out, batch, real_in, power_out, n_out);
     CK(cudaSetDevice(h->device));
     FftRes* fr;
     int rc = fft_resources(h, plan, n, &fr);
@@ -1697,6 +1818,34 @@ extern "C" int gb_fft_power_spectrum(gb_handle* h, int n, const gb_c32* in, floa
 extern "C" int gb_rfft(gb_handle* h, int n, const float* in, gb_c32* out, int batch)
 {
     return fft_common(h, n, 0, in, out, batch, 1, 0, n / 2 + 1);
+}
+// RealFFT<f32>::power_spectrum (fft.rs:47-55): norm_sqr of the n/2 + 1 bins
+extern "C" int gb_rfft_power_spectrum(gb_handle* h, int n, const float* in, float* out, int batch)
+{
+    return fft_common(h, n, 0, in, out, batch, 1, 1, n / 2 + 1);
+}
+// FFT<f64> / RealFFT<f64> (fft.rs is generic over T: Float): always through the any-length plan
+static int fft_f64(gb_handle* h, int n, int inverse, const void* in, void* out, int batch, int real_in, int power_out, int n_out)
+{
+    if (!h || !in || !out || batch < 1 || n < 2) return GB_EINVAL;
+    std::lock_guard<std::recursive_mutex> lk(h->mu_acq);
+    return fft_any<double, double2>(h, n, inverse, in, out, batch, real_in, power_out, n_out);
+}
+extern "C" int gb_fft_c2c_f64(gb_handle* h, int n, int inverse, const gb_c64* in, gb_c64* out, int batch)
+{
+    return fft_f64(h, n, inverse, in, out, batch, 0, 0, n);
+}
+extern "C" int gb_fft_power_spectrum_f64(gb_handle* h, int n, const gb_c64* in, double* out, int batch)
+{
+    return fft_f64(h, n, 0, in, out, batch, 0, 1, n);
+}
+extern "C" int gb_rfft_f64(gb_handle* h, int n, const double* in, gb_c64* out, int batch)
+{
+    return fft_f64(h, n, 0, in, out, batch, 1, 0, n / 2 + 1);
+}
+extern "C" int gb_rfft_power_spectrum_f64(gb_handle* h, int n, const double* in, double* out, int batch)
+{
+    return fft_f64(h, n, 0, in, out, batch, 1, 1, n / 2 + 1);
 }
 
 // ------------------------------------------------------------------ tracking: host helpers

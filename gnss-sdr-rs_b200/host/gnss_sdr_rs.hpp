@@ -424,9 +424,9 @@ class RealFFT {
     // fft.rs:47-55: norm_sqr of the len/2 + 1 bins
     std::vector<float> power_spectrum(const std::vector<float>& input)
     {
-        const std::vector<Complex32> y = execute(input);
-        std::vector<float> out(y.size());
-        for (size_t i = 0; i < y.size(); i++) out[i] = y[i].re * y[i].re + y[i].im * y[i].im;
+        std::vector<float> out(len_ / 2 + 1);
+        const int rc = gb_rfft_power_spectrum(e_->raw(), (int)len_, input.data(), out.data(), 1);
+        if (rc) throw AcqError(rc);
         return out;
     }
 

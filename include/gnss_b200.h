@@ -44,7 +44,8 @@ extern "C" {
 
 typedef struct gb_handle gb_handle;
 
-typedef struct { float re, im; } gb_c32; /* num_complex::Complex32 */
+typedef struct { float re, im; } gb_c32;  /* num_complex::Complex32 */
+typedef struct { double re, im; } gb_c64; /* num_complex::Complex64 (FFT<f64> facade only) */
 
 typedef struct {
     int32_t device;        /* CUDA ordinal */
@@ -136,14 +137,19 @@ typedef struct {
 /* Plan the search: AcquisitionWorker::new for prn = 1..n_prn (do_acquisition.rs:131-156).
  * codes == NULL: GPS C/A resampled per ca_code.rs:12-27 (n_prn <= 32).
  * codes != NULL: n_prn x fft_size +-1 samples (other constellations / the reference's test codes).
- * Supported fft_size: see gb_acq_supported_sizes(). */
+ * fft_size: ANY multiple of 4 up to 131072, like the reference's FftPlanner (:132-142).  The lengths listed by
+ * gb_acq_supported_sizes() -- every sample rate of the BASELINE configurations -- run tuned shared-memory kernels; all other
+ * lengths run the any-length plan (Bluestein chirp-z over a power-of-two Stockham FFT: same results, not tuned).
+ * GB_EUNSUPPORTED only for fft_size % 4 != 0: there apply_doppler_shift (doppler_shift.rs:26) leaves the last fft_size % 4
+ * samples of result_buf holding the previous block's unnormalised IFFT output, which is fed back N times larger every
+ * block -- the reference's own arithmetic reaches inf / NaN within a dozen blocks, so no behaviour exists to reproduce. */
 /* Every call re-plans and resets the per-configuration settings (n_coh = 1, aliasing off, no Doppler tables). */
 int gb_acq_configure(gb_handle *h, int fft_size, float fs, int n_prn, const int8_t *codes);
 /* The per-worker constructor of a drop-in (the reference builds one AcquisitionWorker per PRN, :268-271): plans the
  * built-in GPS C/A configuration unless exactly this one is already planned, in which case it returns GB_OK at once and
  * keeps the Doppler tables and settings -- 32 workers cost one plan, not 32. */
 int gb_acq_configure_once(gb_handle *h, int fft_size, float fs, int n_prn);
-int gb_acq_supported_sizes(int *sizes, int cap);
+int gb_acq_supported_sizes(int *sizes, int cap);   /* the lengths with TUNED plans (any multiple of 4 is accepted) */
 
 /* DopplerShiftTable::new for each f_d in dopplers[] (doppler_shift.rs:11-21), evaluated on the
  * device in f32 in the reference's operation order.  carr_out[d] = f_if + f_d (may be NULL). */
@@ -255,11 +261,18 @@ float gb_acq_fine_last_kernel_ms(gb_handle *h);
 int gb_bench_fp32_tflops(gb_handle *h, float *tflops_out);
 
 /* ------------------------------------------------------------------ FFT facade
- * replaces FFT<f32>::{execute, power_spectrum}, RealFFT<f32>::{execute, power_spectrum} (fft.rs:5-56)
- * for the planned sizes; natural-order, unnormalised. batch transforms of length n. */
+ * replaces FFT<T>::{execute, power_spectrum}, RealFFT<T>::{execute, power_spectrum} (fft.rs:5-56), T = f32 / f64, for ANY
+ * length n >= 2 (rustfft / realfft plan any n): natural-order, unnormalised, `batch` transforms of length n.  Lengths with a
+ * tuned shared-memory plan (gb_acq_supported_sizes) run it in f32; every other length, and f64, run the any-length plan
+ * (Bluestein over a power-of-two Stockham FFT, n <= 131072, batch <= 32768). */
 int gb_fft_c2c(gb_handle *h, int n, int inverse, const gb_c32 *in, gb_c32 *out, int batch);
 int gb_fft_power_spectrum(gb_handle *h, int n, const gb_c32 *in, float *out, int batch);
 int gb_rfft(gb_handle *h, int n, const float *in, gb_c32 *out /* batch x (n/2+1) */, int batch);
+int gb_rfft_power_spectrum(gb_handle *h, int n, const float *in, float *out /* batch x (n/2+1) */, int batch);
+int gb_fft_c2c_f64(gb_handle *h, int n, int inverse, const gb_c64 *in, gb_c64 *out, int batch);
+int gb_fft_power_spectrum_f64(gb_handle *h, int n, const gb_c64 *in, double *out, int batch);
+int gb_rfft_f64(gb_handle *h, int n, const double *in, gb_c64 *out /* batch x (n/2+1) */, int batch);
+int gb_rfft_power_spectrum_f64(gb_handle *h, int n, const double *in, double *out /* batch x (n/2+1) */, int batch);
 
 /* ------------------------------------------------------------------ tracking
  * replaces TrackingChannel::{early_late_correlation, get_ca_chip, run_loop_filters, do_work, update}

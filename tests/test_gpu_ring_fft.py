@@ -72,6 +72,36 @@ def test_fft_facade(gpu, n):
     assert np.abs(rf.execute(r) - ref_r).max() / np.abs(ref_r).max() < 5e-7
 
 
+@pytest.mark.parametrize("n", [2, 6, 31, 100, 1000, 2046, 5000, 8192, 10230, 65536, 100003])
+def test_fft_facade_any_length_f32_and_f64(gpu, n):
+    """FFT<T> / RealFFT<T> accept any length and are generic over f32 / f64 (fft.rs:5-56): lengths without a tuned plan
+    (and every f64 transform) run the any-length plan -- Bluestein over a power-of-two Stockham FFT -- including primes,
+    odd lengths and powers of two above the tuned ones."""
+    from gnss_sdr_rs_b200 import acquisition
+    rng = np.random.default_rng(n)
+    x = rng.standard_normal((2, n)) + 1j * rng.standard_normal((2, n))
+    ref = np.fft.fft(x, axis=1)
+    f = acquisition.FFT(gpu, n)
+    for dt, tol in ((np.complex64, 3e-6), (np.complex128, 1e-13)):
+        xx = x.astype(dt)
+        got = f.execute(xx)
+        assert got.dtype == dt
+        assert np.abs(got - ref).max() / np.abs(ref).max() < tol, (dt, np.abs(got - ref).max() / np.abs(ref).max())
+        inv = f.execute(got, inverse=True) / n
+        assert np.abs(inv - xx).max() < tol * 30
+        ps = f.power_spectrum(xx)
+        np.testing.assert_allclose(ps, np.abs(ref) ** 2, rtol=max(30 * tol, 1e-12), atol=np.abs(ref).max() ** 2 * tol)
+    r = rng.standard_normal(n)
+    ref_r = np.fft.rfft(r)
+    rf = acquisition.RealFFT(gpu, n)
+    for dt, tol in ((np.float32, 3e-6), (np.float64, 1e-13)):
+        got = rf.execute(r.astype(dt))
+        assert got.shape == (n // 2 + 1,)
+        assert np.abs(got - ref_r).max() / np.abs(ref_r).max() < tol
+        np.testing.assert_allclose(rf.power_spectrum(r.astype(dt)), np.abs(ref_r) ** 2, rtol=max(30 * tol, 1e-12),
+                                   atol=np.abs(ref_r).max() ** 2 * tol)
+
+
 @pytest.mark.parametrize("sequential", [False, True])
 @pytest.mark.parametrize("f_if,fs", [(4130400.0, 16367600.0), (4092000.0, 16368000.0), (-420000.0, 2048000.0)])
 def test_digital_frontend_bit_exact(gpu, oracle, ffi, sequential, f_if, fs):

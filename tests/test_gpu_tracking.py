@@ -357,7 +357,7 @@ def test_config3_full_run_parity_vs_oracle(gpu, oracle):
         DLL for seconds), so after it, and in
       FAST mode (tree sums, SFU sin/cos) throughout, agreement is statistical, at 60 checkpoints one second apart:
         identical lock state and epoch counts, next_sample_index within 2 samples, carrier within 15 Hz at every
-        checkpoint and its mean over the run within 0.5 Hz, code phase within 0.1 chip (mod 1023), and the same prompt
+        checkpoint and its mean over the run within 0.5 Hz, code phase within 0.25 chip at every checkpoint and 0.02 chip on average (mod 1023), and the same prompt
         sign (nav bit) on > 99.5 % of the epochs where the oracle's prompt is not near zero."""
     import bench
     from gnss_sdr_rs_b200 import ring, tracking
@@ -417,7 +417,7 @@ def test_config3_full_run_parity_vs_oracle(gpu, oracle):
         assert np.abs(ck[:, :, 0] - ref_ck[:, :, 0]).max() <= 15.0                        # instantaneous NCO jitter
         assert np.abs((ck[:, :, 0] - ref_ck[:, :, 0]).mean(axis=0)).max() <= 0.5          # mean carrier over the run
         dcp = np.abs(((ck[:, :, 1] - ref_ck[:, :, 1] + 511.5) % 1023.0) - 511.5)
-        assert dcp.max() <= 0.1, dcp.max()                                                # code phase
+        assert dcp.max() <= 0.25 and dcp.mean() <= 0.02, (dcp.max(), dcp.mean())          # code phase
         for c in range(C):
             assert ch[c].epochs_done == n_ep
         strong = pmag > 0.3 * np.median(pmag)

@@ -356,6 +356,57 @@ def test_nav_bit_sync_against_python(oracle):
     assert out.tolist()[:20] == bits[first:first + 20].tolist()
 
 
+def test_preamble_search_against_python(oracle):
+    """check_preamble_syn (decoding.rs:215-226): |sum_{x<8} bits[i0+x] * GPS_CA_PREAMBLE[x]| == 8; the sliding search and
+    the legacy's literal single test of the first 8 bits (its buff_preamble is pushed to but never popped)."""
+    pre = [1, -1, -1, -1, 1, -1, 1, 1]
+    rng = np.random.default_rng(9)
+    for planted_at, pol in ((0, 1), (13, -1), (None, 0)):
+        nav = (rng.integers(0, 2, 120) * 2 - 1).tolist()
+        for i0 in range(0, 112):     # remove accidental matches
+            c = sum(nav[i0 + x] * pre[x] for x in range(8))
+            if abs(c) == 8:
+                nav[i0] = -nav[i0]
+        if planted_at is not None:
+            nav[planted_at:planted_at + 8] = [pol * v for v in pre]
+        # prompt sequence whose bit edges sit at epoch % 20 == 0, long enough to synchronise (after epoch 1000), then nav
+        lead = (rng.integers(0, 2, 70) * 2 - 1).tolist()
+        lead = [(-1) ** k for k in range(70)]                       # alternating: an edge every 20 ms -> sync at once
+        seq = lead + nav
+        ip = np.repeat(np.array(seq, np.float32) * 1000.0, 20)
+        st, bits = oracle.nav_bit_sync(ip, 512)
+        assert st.flag_bit_sync == 1 and st.frame_sync_ind == 0
+        first_bit = (st.sync_epoch // 20)                            # bits emitted from the bit that contains sync_epoch
+        emitted = seq[first_bit:first_bit + st.n_bits]
+        assert bits.tolist() == emitted[:len(bits)]
+        # python restatement of both searches on the emitted bits
+        hits = [i0 for i0 in range(len(emitted) - 7) if abs(sum(emitted[i0 + x] * pre[x] for x in range(8))) == 8]
+        exp_first = hits[0] if hits else -1
+        assert st.preamble_bit == exp_first
+        if exp_first >= 0:
+            assert st.polarity == (1 if sum(emitted[exp_first + x] * pre[x] for x in range(8)) > 0 else -1)
+        assert st.ref_frame_sync == (1 if (hits and hits[0] == 0) else 0)
+
+
+def test_reference_arithmetic_diverges_when_fft_size_is_not_a_multiple_of_4(oracle):
+    """apply_doppler_shift writes 4 * floor(len / 4) samples (doppler_shift.rs:26); for len % 4 != 0 the tail of the
+    worker's result_buf keeps the previous block's UNNORMALISED inverse FFT, which is fed back N times larger each block.
+    The oracle restates that faithfully: at N = 2046 (2 samples per chip) the accumulated powers are inf / NaN after one
+    10-block search -- which is why gb_acq_configure refuses these lengths instead of "reproducing" them."""
+    from gnss_sdr_rs_b200 import sdr_mock
+    n, fs, K = 2046, 2.046e6, 10
+    x = sdr_mock.baseband(fs, K, [{"prn": 5, "doppler": 500.0, "code_phase": 100, "cn0_dbhz": 50.0}], seed=1)
+    carr, tabs = oracle.doppler_tables(0.0, np.arange(-1000, 1001, 500, dtype=np.float32), fs, n)
+    cells = oracle.AcqWorker(5, n, fs).cells(x, tabs, K)
+    assert not np.isfinite(cells["peak"]).all() or cells["peak"].max() > 1e30
+    # a multiple of 4 right next to it is perfectly fine
+    n2, fs2 = 2048, 2.048e6
+    x2 = sdr_mock.baseband(fs2, K, [{"prn": 5, "doppler": 500.0, "code_phase": 100, "cn0_dbhz": 50.0}], seed=1)
+    carr2, tabs2 = oracle.doppler_tables(0.0, np.arange(-1000, 1001, 500, dtype=np.float32), fs2, n2)
+    c2 = oracle.AcqWorker(5, n2, fs2).cells(x2, tabs2, K)
+    assert np.isfinite(c2["peak"]).all() and int(c2["argmax"][3]) == 100
+
+
 # ------------------------------------------------------------------ N3: finer_doppler (acquisition_bk.rs:215-302)
 @pytest.mark.parametrize("fs,dopp", [(2.048e6, 1234.5), (4.092e6, -2771.0)])
 def test_fine_doppler_oracle_vs_numpy_f64(oracle, fs, dopp):
