@@ -2244,6 +2244,9 @@ extern "C" int gb_group_unique_id(uint8_t* id128)
     return GB_OK;
 }
 
+extern "C" int gb_group_allgather(gb_group* g, const void* mine, uint64_t bytes, void* all_out);
+extern "C" int gb_group_destroy(gb_group* g);
+
 extern "C" int gb_group_init(gb_handle* h, const uint8_t* id128, int rank, int world, gb_group** out)
 {
     if (!h || !id128 || !out || world < 1 || rank < 0 || rank >= world) return GB_EINVAL;
@@ -2268,6 +2271,22 @@ extern "C" int gb_group_init(gb_handle* h, const uint8_t* id128, int rank, int w
         return fail(h, e, "gb_group_init");
     }
     *out = g;
+    // NCCL builds its channels during the first collective (hundreds of milliseconds): pay that here, not inside the
+    // caller's first timed gather
+    uint64_t probe = (uint64_t)rank;
+    std::vector<uint64_t> all((size_t)world);
+    const int wrc = gb_group_allgather(g, &probe, sizeof(probe), all.data());
+    if (wrc) {
+        gb_group_destroy(g);
+        *out = nullptr;
+        return wrc;
+    }
+    for (int r = 0; r < world; r++)
+        if (all[r] != (uint64_t)r) {
+            gb_group_destroy(g);
+            *out = nullptr;
+            return GB_ENCCL;
+        }
     return GB_OK;
 }
 

@@ -132,6 +132,38 @@ def test_decide_matches_oracle_on_random_cells(ffi, oracle):
                 assert got[k] == ref[k], k
 
 
+def test_sharding_helpers_match_the_python_partition(ffi):
+    """gb_shard_prn_mask / gb_shard_range (host-only, no device): the partition the multi-GPU paths use, identical to
+    gnss_sdr_rs_b200.sharding (which the world-size-2 gloo test exercises); every item is owned by exactly one rank."""
+    from gnss_sdr_rs_b200 import sharding
+    L = ffi.lib()
+    for world in (1, 2, 3, 4, 8):
+        for base in (0xFFFFFFFF, 0xFFFFFFFF & ~(1 << 4), 0x0000F0F1):
+            seen = 0
+            for rank in range(world):
+                m = int(L.gb_shard_prn_mask(rank, world, 32, base))
+                assert m == sharding.prn_mask_for_rank(rank, world, 32, base)
+                assert seen & m == 0
+                seen |= m
+            assert seen == base
+        for n_items in (0, 1, 13, 512, 1024):
+            covered = []
+            for rank in range(world):
+                first, count = C.c_int(-1), C.c_int(-1)
+                assert L.gb_shard_range(n_items, rank, world, C.byref(first), C.byref(count)) == 0
+                assert list(range(first.value, first.value + count.value)) == list(sharding.items_for_rank(n_items, rank, world))
+                covered += list(range(first.value, first.value + count.value))
+            assert covered == list(range(n_items))
+    assert L.gb_shard_prn_mask(2, 2, 32, 0xFFFFFFFF) == 0          # rank out of range
+    f, c = C.c_int(), C.c_int()
+    assert L.gb_shard_range(10, 3, 2, C.byref(f), C.byref(c)) == ffi.GB_EINVAL
+    # without a GPU the collective cannot be set up, and says so (no silent fallback)
+    if L.gb_device_count() == 0:
+        g = C.c_void_p()
+        ids = (C.c_uint8 * 128)()
+        assert L.gb_group_init(None, ids, 0, 1, C.byref(g)) == ffi.GB_EINVAL
+
+
 def test_acquisition_manager_mirror():
     """do_acquisition.rs:339-395 on the host mirror."""
     from gnss_sdr_rs_b200.acquisition import AcquisitionManager
