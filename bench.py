@@ -519,7 +519,7 @@ def run_ours(args, rank, world, local_rank):
     # --shard prn (strong scaling): ONE recording, its PRNs dealt round-robin to the ranks.
     # No collective inside a step: the per-PRN result tables of all steps are gathered ONCE after the last step,
     # inside the timed region ("a final NCCL gather of per-PRN peaks").
-    def timed_block(by_prn, steps, warmup):
+    def timed_block(by_prn, steps, warmup, finish_sampler=True):
         prn_mask = int(hd.L.gb_shard_prn_mask(rank, world, N_PRN, 0xFFFFFFFF)) if by_prn else 0xFFFFFFFF
         x = make_recording(0x6E56 + (0 if by_prn else rank))
         rb = ring.MulticastRingBuffer(hd, 1 << 20)
@@ -552,7 +552,7 @@ def run_ours(args, rank, world, local_rank):
             g_ms = (time.perf_counter() - tg) * 1e3
         barrier()
         wall_ms = (time.perf_counter() - t0) * 1e3
-        clocks = sampler.finish()
+        clocks = sampler.finish() if finish_sampler else sampler   # the main block keeps sampling through the e2e legs
         dev_ms += g_ms
         if dist is not None:
             t = torch.tensor([dev_ms, wall_ms, g_ms], dtype=torch.float64, device="cuda")
@@ -573,7 +573,7 @@ def run_ours(args, rank, world, local_rank):
                 "clocks": clocks, "res": res, "steps": steps}
 
     by_prn = args.shard == "prn" and world > 1
-    main = timed_block(by_prn, args.steps, args.warmup)
+    main = timed_block(by_prn, args.steps, args.warmup, finish_sampler=False)
     eng, x, prn_mask = main["eng"], main["x"], main["prn_mask"]
     kernel_ms_avg = (main["dev_ms"] - main["gather_ms"]) / args.steps
     cells = N_PRN * len(DOPPLERS) * N_FFT
@@ -624,6 +624,7 @@ def run_ours(args, rank, world, local_rank):
                    for a, b in zip(res_pipe, res_e2e))
         if not same:
             raise RuntimeError("pipelined e2e search disagrees with the serial one")
+    main["clocks"] = main["clocks"].finish()
     if dist is not None:
         t = torch.tensor([e2e_ms, e2e_serial_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -735,6 +736,8 @@ def run_ours(args, rank, world, local_rank):
             # on the 10 ms-coherent cells) and the margin of every decision to the 7.0 threshold, aliasing on and off
             line["parity_vs_oracle"] = full_size_parity(eng, ocells, n_prn)
             try:
+                if args.acq_only:
+                    raise StopIteration
                 stream = tracking_stream(2100)
                 tr = tracking_numbers(hd, ffi, 1024, 2000, stream=stream)
                 tr["roofline"] = tracking_roofline(tr, peak_tf)
@@ -749,10 +752,13 @@ def run_ours(args, rank, world, local_rank):
                 del stream
                 # BASELINE configs[2] at full length: 1024 channels x 60 s = 61.44 M channel-epochs in one launch
                 line["tracking_config3_full_60s"] = tracking_numbers(hd, ffi, 1024, 60000)
+            except StopIteration:
+                pass
             except Exception as e:  # report, never hide
                 line["tracking"] = {"error": repr(e)}
             try:
-                line["extras"] = extra_numbers(hd, ffi)
+                if not args.acq_only:
+                    line["extras"] = extra_numbers(hd, ffi)
             except Exception as e:
                 line["extras"] = {"error": repr(e)}
         print(json.dumps(line), flush=True)
@@ -883,6 +889,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--acq-mode", default="shared", choices=["shared", "fused"])
     ap.add_argument("--no-pipeline", action="store_true", help="e2e from one host thread only")
+    ap.add_argument("--acq-only", action="store_true",
+                    help="skip the tracking / extras legs (the ncu launch-list pass of the headline step: profiles/)")
     ap.add_argument("--shard", default="recording", choices=["recording", "prn"],
                     help="N>1: one recording per GPU (weak scaling, default) or the PRNs of ONE recording dealt to the GPUs (strong)")
     args = ap.parse_args()

@@ -1274,7 +1274,11 @@ static int search_enqueue(gb_handle* h, const float2* iq_dev, uint64_t start, ui
             CK(cudaEventRecord(h->ev_s0[slot], h->s_acq));
             if (host_iq && slab >= (size_t)h->D) {
                 // sliced upload overlapped with the forward path
-                const int n_slices = n_groups >= 8 ? 4 : (n_groups >= 2 ? 2 : 1);
+                // one call at a time: slices, so that the forward path of slice s overlaps the upload of slice s + 1.  With
+                // another search in flight (enqueue / wait pair) the whole upload already hides behind that search's
+                // inverse kernel, and one full-size forward launch beats four small ones
+                const bool other_in_flight = h->pend[slot ^ 1].active;
+                const int n_slices = other_in_flight ? 1 : (n_groups >= 8 ? 4 : (n_groups >= 2 ? 2 : 1));
                 if (h->pfa) { a.iq = h->iq_perm; a.iq_start = 0; a.iq_mask = ~0ull; a.tables = h->tables_perm; }
                 a.d_lo = 0;
                 // the previous search's last reader of `chunk` (its permute / forward kernels -- NOT its inverse kernel)

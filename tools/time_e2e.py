@@ -25,13 +25,28 @@ rb.write_samples(x)
 eng = acquisition.AcquisitionEngine(hd, bench.N_FFT, bench.FS, 32)
 eng.make_doppler_tables(0.0, bench.DOPPLERS)
 eng.set_coherent(bench.N_COH)
+eng.set_doppler_aliasing(True)
+n_x = int(x.size)
 def timeit(f, n=20):
     for _ in range(3): f()
     t0 = time.perf_counter()
     for _ in range(n): f()
     return (time.perf_counter() - t0) / n * 1e3
 print("search_ring (results)      %.3f ms wall, kernel %.3f" % (timeit(lambda: eng.search_ring(0, bench.K_MS)), eng.last_kernel_ms()))
-print("search pinned host         %.3f ms wall, kernel %.3f" % (timeit(lambda: eng.search(x_pin.data_ptr(), bench.K_MS)), eng.last_kernel_ms()))
+print("search pinned host         %.3f ms wall, kernel %.3f" % (timeit(lambda: eng.search(x_pin.data_ptr(), bench.K_MS, n_samples=n_x)), eng.last_kernel_ms()))
 print("search pageable host       %.3f ms wall, kernel %.3f" % (timeit(lambda: eng.search(x, bench.K_MS)), eng.last_kernel_ms()))
 print("search_cells_ring no cells %.3f ms wall" % timeit(lambda: eng.search_cells_ring(0, bench.K_MS, want_cells=False)))
+def pipe(n):
+    eng.search_enqueue(x_pin.data_ptr(), bench.K_MS, 0, n_samples=n_x)
+    raw = (ffi.AcqResult * 32)()
+    for k in range(n):
+        if k + 1 < n:
+            eng.search_enqueue(x_pin.data_ptr(), bench.K_MS, (k + 1) & 1, n_samples=n_x)
+        eng.search_wait(k & 1, raw=raw)
+for n in (10, 20, 50, 200):
+    pipe(4)
+    t0 = time.perf_counter(); pipe(n); dt = (time.perf_counter() - t0) / n * 1e3
+    print("enqueue/wait pipeline, %3d steps: %.3f ms per step (kernel %.3f)" % (n, dt, eng.last_kernel_ms()))
+for n in (20, 100):
+    print("search pinned host x%d      %.3f ms wall" % (n, timeit(lambda: eng.search(x_pin.data_ptr(), bench.K_MS, n_samples=n_x), n)))
 hd.close()
