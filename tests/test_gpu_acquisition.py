@@ -251,6 +251,36 @@ def test_reference_recording_standin_config1(gpu, oracle):
         assert (p + 1) in truth_prns  # the reference's one-sided assertion (do_acquisition.rs:454)
     # the strong half of the table must be acquired
     assert {2, 3, 19, 14, 18}.issubset({p + 1 for p in range(32) if got[p]})
+    # BASELINE configs[0] as worded: +-5 kHz / 500 Hz (D = 21), ONE 1 ms block (K = 1) -- same comparison, plus the
+    # margin of every decision to the 7.0 threshold: cells agree to ~1e-6, so a decision can only differ
+    # when the metric sits that close to 7.0
+    d21 = np.arange(-5000.0, 5000.0 + 1.0, 500.0, dtype=np.float32)
+    carr21, tabs21 = oracle.doppler_tables(f_if, d21, fs, n)
+    assert len(d21) == 21
+    eng.set_doppler_tables(tabs21, carr21)
+    got1 = eng.search(x, 1, local_tail=7)
+    cells1 = eng.search_cells(x, 1)
+    ref1 = oracle.acq_search_all(workers, x, tabs21, carr21, 7, 1, early_exit=True)
+    margins = []
+    for p in range(32):
+        o = workers[p].cells(x, tabs21, 1)
+        np.testing.assert_allclose(cells1[p]["peak"], o["peak"], rtol=REL)
+        assert (cells1[p]["argmax"] == o["argmax"]).all()
+        gmax = gsum = 0.0
+        for b in range(21):                       # the early-exit scan (Q1) on the oracle's cells
+            if o["peak"][b] > gmax:
+                gmax, gsum = float(o["peak"][b]), float(o["sum8"][b])
+            metric = gmax / ((gsum - gmax) / (n - 1))
+            margins.append(abs(metric - 7.0))
+            if metric > 7.0:
+                break
+        assert (ref1[p] is None) == (got1[p] is None), "PRN %d detection differs (K = 1)" % (p + 1)
+        if ref1[p]:
+            for k in ("code_phase_samples", "carrier_freq", "sample_global_index", "code_phase_chips"):
+                assert got1[p][k] == ref1[p][k]
+    print("config 1 (D = 21, K = 1): detected %s, smallest |metric - 7.0| met by any scan: %.4f" % (
+        [p + 1 for p in range(32) if got1[p]], min(margins)))
+    assert min(margins) > 1e-3
 
 
 def test_prn_mask_and_decide(gpu, oracle):
