@@ -12,6 +12,8 @@ using P2048 = Plan<2048, 128, 4, 4, 8, 16, 16>;
 using P4092 = PfaPlan<4092, 160, 4, 0, 12, 11, 31>;
 // stage geometry of acq_inverse_lw_kernel: the same radices on 128 working threads (+ one leftover warp = P4092::T)
 using P4092W = PfaPlan<4092, 128, 4, 0, 12, 11, 31>;
+using P4092W3 = PfaPlan<4092, 128, 3, 0, 12, 11, 31>;   // the default: 3 CTAs per SM, 128 registers, no accumulator spills
+using P4092W2 = PfaPlan<4092, 128, 2, 0, 12, 11, 31>;
 using P4096 = Plan<4096, 256, 2, 4, 16, 16, 16>;
 // 3 x 11 is one Good-Thomas radix-33 butterfly in registers (no internal twiddles): three shared-memory stages, not four
 using P8184 = PfaPlan<8184, 288, 1, 0, 8, 33, 31>;

@@ -112,21 +112,27 @@ template <class PW, bool CG> __global__ void __launch_bounds__(PW::T + 32, PW::M
     }
 }
 
+template <class PW, bool CG> static cudaError_t launch_lw(const AcqArgs& a, int n_d, cudaStream_t st)
+{
+    const size_t smem = sizeof(float2) * (size_t)PW::LINE;
+    cudaError_t e = cudaFuncSetAttribute(acq_inverse_lw_kernel<PW, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    acq_inverse_lw_kernel<PW, CG><<<n_d * a.n_active, PW::T + 32, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
 cudaError_t acq_launch_inverse_lw4092(const AcqArgs& a, int n_d, cudaStream_t st)
 {
     using PW = P4092W;
     static_assert(PW::T + 32 == P4092::T && PW::LINE == P4092::LINE, "same line as the default plan, one extra warp");
-    const size_t smem = sizeof(float2) * (size_t)PW::LINE;
-    const bool ldg = tuning("acq_spec_ldg", 0) != 0;   // A/B switch (tools/time_acq.py): 1.711 vs 1.697 ms
-    cudaError_t e;
-    if (ldg) {
-        if ((e = cudaFuncSetAttribute(acq_inverse_lw_kernel<PW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-        acq_inverse_lw_kernel<PW, false><<<n_d * a.n_active, PW::T + 32, smem, st>>>(a);
-    } else {
-        if ((e = cudaFuncSetAttribute(acq_inverse_lw_kernel<PW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-        acq_inverse_lw_kernel<PW, true><<<n_d * a.n_active, PW::T + 32, smem, st>>>(a);
-    }
-    return cudaGetLastError();
+    // Three CTAs per SM with 128 registers: the 36 power accumulators stay in registers next to the 31 stage-A inputs
+    // (four CTAs per SM at 96 registers spill them: 72 local-memory accesses per thread and group through the L1 data
+    // pipe the kernel is bound by).  Config 2: 1.381 -> 1.304 ms.  gb_tuning_set("acq_lw_minb", 4 | 2) for A/B.
+    const int minb = tuning("acq_lw_minb", 3);
+    if (minb == 4) return launch_lw<PW, true>(a, n_d, st);
+    if (minb == 2) return launch_lw<P4092W2, true>(a, n_d, st);
+    if (tuning("acq_spec_ldg", 0)) return launch_lw<P4092W3, false>(a, n_d, st);   // A/B switch: spectra through L1
+    return launch_lw<P4092W3, true>(a, n_d, st);
 }
 
 }  // namespace gb

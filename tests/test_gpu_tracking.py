@@ -123,6 +123,56 @@ def test_do_work_epochs_closed_loop_ordered(gpu, oracle):
     assert abs(ch[0].carrier_freq - 1003.0) < 2.0  # the PLL pulled in
 
 
+@pytest.mark.parametrize("fs,f_if,prn,dop,cph", [(2.048e6, 0.0, 12, 1830.0, 437), (4.096e6, 0.0, 7, -2210.0, 1000),
+                                                 (16367600.0, 4130400.0, 2, 4.128460e6, 15041)])
+def test_ring_fed_fast_epochs_follow_the_oracle_state_by_state(gpu, oracle, fs, f_if, prn, dop, cph):
+    """The warp-specialised FAST kernel (gb_trk_epoch / gb_trk_run) on its three sample-loop forms: one batch per epoch
+    (2.048 Msps), several batches (4.096 Msps) and the general form for IF carriers that span thousands of turns per epoch
+    (16.3676 Msps, IF 4.1304 MHz: the reference's f32 phase roundings, Cody-Waite reduction).  Each epoch starts from the
+    ORACLE's state (open loop, so rounding differences cannot accumulate): six sums within 1e-4 |P|, phases and sample
+    bookkeeping exact, NCO updates within 0.05 Hz / 0.0625 chips/s x 4; and the persistent form agrees with the per-epoch one."""
+    from gnss_sdr_rs_b200 import ring, sdr_mock, tracking
+    n = int(round(fs / 1000.0))
+    n_ep = 24
+    if f_if:
+        raw, _ = sdr_mock.if_recording(n_ep + 3, prns={2})
+        x = sdr_mock.i8_to_c32(raw)
+    else:
+        x = sdr_mock.baseband(fs, n_ep + 3, [{"prn": prn, "doppler": dop, "code_phase": cph, "cn0_dbhz": 50.0}], seed=21)
+    cap = 1
+    while cap < len(x):
+        cap <<= 1
+    rb = ring.MulticastRingBuffer(gpu, cap)
+    rb.write_samples(x)
+    ch, och = _pair(oracle, fs, prn, dop + 4.0, np.float32(0.1), cph, code_row=prn - 1)
+    eng = tracking.TrackingEngine(gpu)
+    for e in range(n_ep):
+        # the GPU channel starts every epoch from the oracle's state
+        for f in ("carrier_freq", "carrier_phase", "carrier_error", "carrier_nco", "code_phase", "code_error", "code_nco",
+                  "code_rate", "next_sample_index", "num_samples_per_code", "lost_counter"):
+            setattr(ch[0], f, getattr(och, f))
+        seg = x[och.next_sample_index: och.next_sample_index + och.num_samples_per_code]
+        ref6, msg, _ = oracle.trk_do_work(och, seg)
+        out, ran, lost = eng.epoch(ch, mode=0)
+        assert ran[0] == 1 and lost[0] == 0 and msg == 0
+        scale = float(np.hypot(ref6[0], ref6[1]))
+        assert np.abs(_six(out[0]) - ref6).max() <= 1e-4 * scale, (e, _six(out[0]), ref6)
+        assert ch[0].carrier_phase == och.carrier_phase and ch[0].code_phase == och.code_phase
+        assert ch[0].next_sample_index == och.next_sample_index and ch[0].num_samples_per_code == och.num_samples_per_code
+        assert abs(ch[0].carrier_freq - och.carrier_freq) <= 0.05
+        assert abs(ch[0].code_rate - och.code_rate) <= 0.0625 * 4
+    # persistent launch == per-epoch launches (same kernel, prefetch across epochs included)
+    a, _ = _pair(oracle, fs, prn, dop + 4.0, np.float32(0.1), cph, code_row=prn - 1)
+    b, _ = _pair(oracle, fs, prn, dop + 4.0, np.float32(0.1), cph, code_row=prn - 1)
+    eng.upload(a)
+    eng.run(n_ep)
+    eng.download(a)
+    for _ in range(n_ep):
+        eng.epoch(b)
+    assert bytes(a[0]) == bytes(b[0])
+    assert a[0].epochs_done == n_ep
+
+
 def test_persistent_run_matches_per_epoch_and_oracle(gpu, oracle):
     """gb_trk_run: 64 channels x 300 epochs in ONE launch; same trajectory as per-epoch launches (bit-identical,
     same kernel code) and statistically the oracle's (FAST mode)."""

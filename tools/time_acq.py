@@ -33,6 +33,7 @@ def main():
     eng = acquisition.AcquisitionEngine(hd, n, fs)
     eng.make_doppler_tables(0.0, np.linspace(-5000, 5000, D).astype(np.float32))
     eng.set_coherent(coh)
+    eng.set_doppler_aliasing(os.environ.get('ALIAS', '1') != '0')
     eng.set_mode({"fused": ffi.GB_ACQ_FUSED, "plain": ffi.GB_ACQ_SHARED_PLAIN}.get(mode, ffi.GB_ACQ_SHARED))
     # samples resident in the device ring: the timed region holds kernels only (the host-pointer call overlaps its
     # sliced upload with the forward path inside the same events)
