@@ -22,7 +22,10 @@ namespace gb {
 // acq_inverse_kernel's (tests/test_gpu_acquisition.py::test_leftover_warp_kernel_is_bit_identical).
 enum { BAR_A_DONE = 1, BAR_MID = 2, BAR_END = 3 };
 
-template <class PW, bool CG>
+// DB: the line is double-buffered (group g lives in line + (g & 1) * LINE).  Passing A_DONE(g - 1) then proves that every
+// working warp has left stage C of group g - 2, the last reader of buffer g & 1, so END disappears from the loop and the
+// leftover warp waits on A_DONE instead of arriving at it (no fence needed: bar.sync orders its stores).
+template <class PW, bool CG, bool DB>
 __device__ __noinline__ void lw_leftover_warp(const float2* __restrict__ spec, const float2* __restrict__ code,
                                               float2* __restrict__ line, int n_groups)
 {
@@ -45,18 +48,28 @@ __device__ __noinline__ void lw_leftover_warp(const float2* __restrict__ spec, c
     };
     compute(0);
     for (int g = 0; g < n_groups; g++) {
-        if (g > 0) named_bar_sync(BAR_END, TALL);   // group g-1 has left the line
-        if (slot == g % BATCH)
-            dft_odd_prime_stream_emit<GM::R>(h, [&](int j, float2 y) { line[PW::phys(b * GM::R + j)] = y; });
-        __threadfence_block();   // bar.arrive alone does not order the shared-memory stores before the arrival
-        __syncwarp();
-        named_bar_arrive(BAR_A_DONE, TALL);
-        if (g % BATCH == BATCH - 1 && g + 1 < n_groups) compute(g + 1);
+        if (DB) {
+            float2* __restrict__ lg = line + (g & 1) * PW::LINE;
+            if (slot == g % BATCH)
+                dft_odd_prime_stream_emit<GM::R>(h, [&](int j, float2 y) { lg[PW::phys(b * GM::R + j)] = y; });
+            if (g % BATCH == BATCH - 1 && g + 1 < n_groups) compute(g + 1);
+            __syncwarp();
+            named_bar_sync(BAR_A_DONE, TALL);
+        } else {
+            if (g > 0) named_bar_sync(BAR_END, TALL);   // group g-1 has left the line
+            if (slot == g % BATCH)
+                dft_odd_prime_stream_emit<GM::R>(h, [&](int j, float2 y) { line[PW::phys(b * GM::R + j)] = y; });
+            __threadfence_block();   // bar.arrive alone does not order the shared-memory stores before the arrival
+            __syncwarp();
+            named_bar_arrive(BAR_A_DONE, TALL);
+            if (g % BATCH == BATCH - 1 && g + 1 < n_groups) compute(g + 1);
+        }
     }
     named_bar_sync(BAR_END, TALL);
 }
 
-template <class PW, bool CG> __global__ void __launch_bounds__(PW::T + 32, PW::MINB) acq_inverse_lw_kernel(const AcqArgs a)
+template <class PW, bool CG, bool DB = false>
+__global__ void __launch_bounds__(PW::T + 32, PW::MINB) acq_inverse_lw_kernel(const AcqArgs a)
 {
     extern __shared__ float2 smem_line[];
     constexpr int LASTS = PW::NSTAGE - 1;
@@ -79,7 +92,7 @@ template <class PW, bool CG> __global__ void __launch_bounds__(PW::T + 32, PW::M
     float2* __restrict__ line = smem_line;
 
     if (threadIdx.x >= TW) {
-        lw_leftover_warp<PW, CG>(a.spec + spec_off, a.code_fft + code_off, line, n_groups);
+        lw_leftover_warp<PW, CG, DB>(a.spec + spec_off, a.code_fft + code_off, line, n_groups);
         return;
     }
     {
@@ -99,25 +112,27 @@ template <class PW, bool CG> __global__ void __launch_bounds__(PW::T + 32, PW::M
                 for (int q = 0; q < GM::R; q++) v[q] = cmul_conj(LDSPEC(&sg[q * PW::SPEC_STRIDE + b]), __ldg(&code[q * PW::SPEC_STRIDE + b]));
                 // END of the previous group sits HERE, between this group's global loads and its first store to the
                 // line: a warp that leaves stage C early spends its L2 latency before the barrier instead of after it
-                if (g > 0) named_bar_sync(BAR_END, TALL);
-                dft_emit<GM::R, true>(v, [&](int j, float2 y) { line[PW::phys(b * GM::R + j)] = y; });
+                if (!DB && g > 0) named_bar_sync(BAR_END, TALL);
+                float2* __restrict__ lg = DB ? line + (g & 1) * PW::LINE : line;
+                dft_emit<GM::R, true>(v, [&](int j, float2 y) { lg[PW::phys(b * GM::R + j)] = y; });
             }
+            float2* __restrict__ lg = DB ? line + (g & 1) * PW::LINE : line;
             named_bar_sync(BAR_A_DONE, TALL);
-            dit_stage_rows<PW, 1, true, TW / 32>(line);
+            dit_stage_rows<PW, 1, true, TW / 32>(lg);
             named_bar_sync(BAR_MID, TW);
-            final_stage_accumulate<PW>(line, a.tw, acc);
+            final_stage_accumulate<PW>(lg, a.tw, acc);
         }
         named_bar_sync(BAR_END, TALL);   // the reduction reuses the line as scratch
         reduce_row_to_cell<PW, BAR_MID>(acc, smem_line, a.spc, &a.cells[(size_t)row * a.D + a.d_lo + dl], a.npos);
     }
 }
 
-template <class PW, bool CG> static cudaError_t launch_lw(const AcqArgs& a, int n_d, cudaStream_t st)
+template <class PW, bool CG, bool DB = false> static cudaError_t launch_lw(const AcqArgs& a, int n_d, cudaStream_t st)
 {
-    const size_t smem = sizeof(float2) * (size_t)PW::LINE;
-    cudaError_t e = cudaFuncSetAttribute(acq_inverse_lw_kernel<PW, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t smem = sizeof(float2) * (size_t)PW::LINE * (DB ? 2 : 1);
+    cudaError_t e = cudaFuncSetAttribute(acq_inverse_lw_kernel<PW, CG, DB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    acq_inverse_lw_kernel<PW, CG><<<n_d * a.n_active, PW::T + 32, smem, st>>>(a);
+    acq_inverse_lw_kernel<PW, CG, DB><<<n_d * a.n_active, PW::T + 32, smem, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -129,6 +144,7 @@ cudaError_t acq_launch_inverse_lw4092(const AcqArgs& a, int n_d, cudaStream_t st
     // (four CTAs per SM at 96 registers spill them: 72 local-memory accesses per thread and group through the L1 data
     // pipe the kernel is bound by).  Config 2: 1.381 -> 1.304 ms.  gb_tuning_set("acq_lw_minb", 4 | 2) for A/B.
     const int minb = tuning("acq_lw_minb", 3);
+    if (tuning("acq_lw_db", 0)) return launch_lw<P4092W3, true, true>(a, n_d, st);   // A/B: double-buffered line
     if (minb == 4) return launch_lw<PW, true>(a, n_d, st);
     if (minb == 2) return launch_lw<P4092W2, true>(a, n_d, st);
     if (tuning("acq_spec_ldg", 0)) return launch_lw<P4092W3, false>(a, n_d, st);   // A/B switch: spectra through L1

@@ -89,7 +89,8 @@ __device__ __forceinline__ float atan_ratio_fast(float q, float i)
 
 // NSW sample warps, U samples per thread and batch, NSFU carrier evaluations per batch through the SFU (the other samples
 // of each group of U / NSFU by rotating the previous one; NSFU == U: no rotation)
-template <int NSW, int U, int NSFU> __global__ void __launch_bounds__((NSW + 2) * 32) trk_ws_kernel(const TrkArgs a)
+template <int NSW, int U, int NSFU, int MINB = (NSW >= 8 ? 2 : 4)>
+__global__ void __launch_bounds__((NSW + 2) * 32, MINB) trk_ws_kernel(const TrkArgs a)
 {
     constexpr int T = NSW * 32;          // sample threads
     constexpr int NT = T + 64;           // + two control warps
@@ -564,10 +565,10 @@ template <int NSW, int U, int NSFU> __global__ void __launch_bounds__((NSW + 2) 
     if (tid == 0) a.ch[c] = st;
 }
 
-template <int NSW, int U, int NSFU> static cudaError_t launch_ws(const TrkArgs& a, cudaStream_t st)
+template <int NSW, int U, int NSFU, int MINB = (NSW >= 8 ? 2 : 4)> static cudaError_t launch_ws(const TrkArgs& a, cudaStream_t st)
 {
     const size_t smem = 1024 * sizeof(float4) + 1024 * sizeof(float) + 6 * NSW * sizeof(float) + 64;
-    trk_ws_kernel<NSW, U, NSFU><<<a.n_channels, (NSW + 2) * 32, smem, st>>>(a);
+    trk_ws_kernel<NSW, U, NSFU, MINB><<<a.n_channels, (NSW + 2) * 32, smem, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -590,6 +591,10 @@ cudaError_t trk_ws_launch(const TrkArgs& a, cudaStream_t st, int variant)
     case 488: return launch_ws<4, 8, 8>(a, st);
     case 482: return launch_ws<4, 8, 2>(a, st);
     case 481: return launch_ws<4, 8, 1>(a, st);
+    case 2817: return launch_ws<2, 8, 1, 7>(a, st);
+    case 2816: return launch_ws<2, 8, 1, 6>(a, st);
+    case 2418: return launch_ws<2, 4, 1, 8>(a, st);
+    case 2417: return launch_ws<2, 4, 1, 7>(a, st);
     default: break;
     }
     // up to two channels per SM: 8 sample warps per channel (latency regime, one batch per epoch at 2.048 Msps); more:
