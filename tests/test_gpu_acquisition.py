@@ -573,3 +573,91 @@ def test_config2_full_size_properties(gpu):
             assert (int(a["argmax"][p, bb]) - int(d["argmax"][p, bb])) % n in (s % n, (s - 1) % n, (s + 1) % n)
             assert abs(d["peak"][p, bb] / a["peak"][p, bb] - 1) < 0.2
     assert sorted(found) == sorted(truth), found
+
+
+def test_async_enqueue_wait_and_batch(gpu, oracle, ffi):
+    """gb_acq_search_enqueue / gb_acq_search_wait (two slots on one handle) and gb_acq_search_batch: the same results as
+    the synchronous call for every recording, in order, whatever is in flight; slot misuse is refused (GB_ESTATE)."""
+    import ctypes as C
+    from gnss_sdr_rs_b200 import sdr_mock
+    n, fs, K = 4092, 4.092e6, 4
+    recs = [sdr_mock.baseband(fs, K, _sats(n, 100 + i), seed=200 + i) for i in range(5)]
+    eng = _engine(gpu, n, fs)
+    eng.make_doppler_tables(0.0, np.arange(-2500, 2501, 250, dtype=np.float32))
+    eng.set_detector(7.0, 4)
+    for alias in (False, True):
+        eng.set_doppler_aliasing(alias)
+        sync = [eng.search(r, K, local_tail=10 * i) for i, r in enumerate(recs)]
+        sync_cells = [eng.search_cells(r, K).copy() for r in recs]
+        got, got_cells = [], []
+        eng.search_enqueue(recs[0], K, 0, local_tail=0)
+        for i in range(len(recs)):
+            if i + 1 < len(recs):
+                eng.search_enqueue(recs[i + 1], K, (i + 1) & 1, local_tail=10 * (i + 1))
+            res, cells = eng.search_wait(i & 1, want_cells=True)
+            got.append(res)
+            got_cells.append(cells)
+        for i in range(len(recs)):
+            assert got_cells[i].tobytes() == sync_cells[i].tobytes()
+            for a, b in zip(got[i], sync[i]):
+                assert (a is None) == (b is None)
+                if a:
+                    assert a == b
+        assert any(r is not None for res in got for r in res)
+    # batch form: n_rec recordings back to back
+    ptrs = (C.c_void_p * len(recs))(*[r.ctypes.data for r in recs])
+    out = (ffi.AcqResult * (len(recs) * 32))()
+    gpu.call("gb_acq_search_batch", ptrs, len(recs), recs[0].size, K, 0, 0xFFFFFFFF, None, out)
+    for i in range(len(recs)):
+        ref = eng.search(recs[i], K, local_tail=0)
+        for p in range(32):
+            r = out[i * 32 + p]
+            assert bool(r.found) == (ref[p] is not None)
+            if r.found:
+                assert r.code_phase_samples == ref[p]["code_phase_samples"] and r.carrier_freq == ref[p]["carrier_freq"]
+    # misuse: waiting on an empty slot, enqueueing twice on one slot
+    with pytest.raises(ffi.GnssB200Error) as e:
+        eng.search_wait(1)
+    assert e.value.code == ffi.GB_ESTATE
+    eng.search_enqueue(recs[0], K, 0)
+    with pytest.raises(ffi.GnssB200Error) as e:
+        eng.search_enqueue(recs[1], K, 0)
+    assert e.value.code == ffi.GB_ESTATE
+    with pytest.raises(ffi.GnssB200Error) as e:      # no re-planning / single-bin diagnostics while a search is in flight
+        eng.bin_power(recs[0], K, 1, 0)
+    assert e.value.code == ffi.GB_ESTATE
+    eng.search_wait(0)
+
+
+def test_group_collective_single_rank(gpu, ffi):
+    """gb_group_* with a world of one (NCCL is loaded inside the library and set up through the same calls the multi-GPU
+    bench makes): unique id, init + warm-up gather, all-gather of bytes, the asynchronous slots, gather of result structs."""
+    import ctypes as C
+    L = ffi.lib()
+    ids = (C.c_uint8 * 128)()
+    ffi.check(L.gb_group_unique_id(ids), "gb_group_unique_id")
+    g = C.c_void_p()
+    ffi.check(L.gb_group_init(gpu.h, ids, 0, 1, C.byref(g)), "gb_group_init", gpu.h)
+    try:
+        assert L.gb_group_rank(g) == 0 and L.gb_group_world(g) == 1
+        mine = np.arange(1000, dtype=np.uint8)
+        out = np.zeros(1000, np.uint8)
+        ffi.check(L.gb_group_allgather(g, ffi.ptr(mine), mine.size, ffi.ptr(out)), "gb_group_allgather", gpu.h)
+        assert (out == mine).all()
+        a, b = np.full(64, 7, np.uint8), np.full(4096, 9, np.uint8)
+        oa, ob = np.zeros_like(a), np.zeros_like(b)
+        ffi.check(L.gb_group_allgather_begin(g, ffi.ptr(a), a.size, 0), "begin0", gpu.h)
+        ffi.check(L.gb_group_allgather_begin(g, ffi.ptr(b), b.size, 1), "begin1", gpu.h)
+        assert L.gb_group_allgather_begin(g, ffi.ptr(a), a.size, 0) == ffi.GB_ESTATE      # slot still occupied
+        ffi.check(L.gb_group_allgather_end(g, 1, ffi.ptr(ob)), "end1", gpu.h)
+        ffi.check(L.gb_group_allgather_end(g, 0, ffi.ptr(oa)), "end0", gpu.h)
+        assert (oa == 7).all() and (ob == 9).all()
+        assert L.gb_group_allgather_end(g, 0, ffi.ptr(oa)) == ffi.GB_ESTATE               # nothing pending
+        res = (ffi.AcqResult * 32)()
+        for p in range(32):
+            res[p].prn, res[p].found, res[p].code_phase_samples = p + 1, p % 2, 100 * p
+        allr = (ffi.AcqResult * 32)()
+        ffi.check(L.gb_group_gather_results(g, res, 32, allr), "gb_group_gather_results", gpu.h)
+        assert bytes(allr) == bytes(res)
+    finally:
+        L.gb_group_destroy(g)
