@@ -207,21 +207,27 @@ __global__ void __launch_bounds__((NSW + 2) * 32, MINB) trk_ws_kernel(const TrkA
                                 t1 = t1 >= 1023.f ? t1 - 1023.f : t1;
                             }
                             // floor(tc) sits in the mantissa of the round-down add; early / late chips are
-                            // floor(tc + 0.5) % 1023 in {k, k+1} and max(floor(tc - 0.5), 0) in {k-1, k} (Q7), decided on
-                            // the reference's own f32 sums tc + 0.5 and tc - 0.5
+                            // floor(tc + 0.5) % 1023 in {k, k+1} and max(floor(tc - 0.5), 0) in {k-1, k} (Q7).  The reference
+                            // decides on its f32 sums tc + 0.5 and tc - 0.5; with frac = tc - floor(tc) (exact) those
+                            // decisions are frac >= 0.5 - 2^-25 (the one value whose sum ties up to the next integer:
+                            // tc = 0.49999997) and frac >= 0.5 -- checked against the literal sums on every float within
+                            // 4 ulp of every half chip and 2.5 M random arguments, and by the exact-selection test
                             const pk64 tc2 = pk2(t0, t1);
                             const pk64 pf2 = add2_rm(tc2, pk2(8388608.0f, 8388608.0f));
-                            const pk64 fl2 = add2(pf2, pk2(-8388608.0f, -8388608.0f));   // exact
-                            const pk64 hi2 = add2(tc2, pk2(0.5f, 0.5f)), lo2 = add2(tc2, pk2(-0.5f, -0.5f));
-                            const pk64 fl1 = add2(fl2, pk2(1.0f, 1.0f));
-                            float pf[2], fl[2], hi[2], lo[2], f1[2];
-                            upk2(pf2, pf[0], pf[1]); upk2(fl2, fl[0], fl[1]); upk2(hi2, hi[0], hi[1]);
-                            upk2(lo2, lo[0], lo[1]); upk2(fl1, f1[0], f1[1]);
+                            float pf[2], fr[2];
+                            upk2(pf2, pf[0], pf[1]);
+                            {
+                                // frac = tc - (pf - 2^23): two exact subtractions folded into one packed add chain
+                                const pk64 fl2 = add2(pf2, pk2(-8388608.0f, -8388608.0f));   // exact
+                                float f0, f1;
+                                upk2(fl2, f0, f1);
+                                upk2(add2(tc2, pk2(-f0, -f1)), fr[0], fr[1]);                 // exact (Sterbenz)
+                            }
 #pragma unroll
                             for (int k = 0; k < 2; k++) {
                                 const float4 q = lds_f32x4(16u * (unsigned)__float_as_int(pf[k]) + row4_bias);
-                                const float ec = hi[k] >= f1[k] ? q.z : q.y;
-                                const float lc = lo[k] >= fl[k] ? q.y : q.x;
+                                const float ec = fr[k] >= 0.49999997f ? q.z : q.y;
+                                const float lc = fr[k] >= 0.5f ? q.y : q.x;
                                 float cv, sv;
                                 upk2(cs2[u + k], cv, sv);
                                 const float2 x = cur[u + k];
@@ -319,6 +325,8 @@ __global__ void __launch_bounds__((NSW + 2) * 32, MINB) trk_ws_kernel(const TrkA
         unsigned lostc = st.lost_counter;
         int ran = 0, lost = 0;
         const float g1 = 0.001f / st.pll_tau1, g2 = st.pll_tau2 / st.pll_tau1;   // as evaluated inside run_loop_filters (:286)
+        int n_cached = -1;
+        float n_over_fs = 0.f;
         // publishes the scalars of the epoch that starts at phase `ph` with carrier `f`; ph_ok = |ph / 2 pi| < 2
         auto publish = [&](float f, float ph, float ph_turn, bool ph_ok) {
             const float f_turn = f * rcp_fs;
@@ -347,8 +355,12 @@ __global__ void __launch_bounds__((NSW + 2) * 32, MINB) trk_ws_kernel(const TrkA
             bool pt_ok = true;
             if (lane == 0) {
                 // :240-242 with the carrier_freq the running epoch uses (the filters update it afterwards)
-                const float nf = (float)P.n;
-                const float cph = phi + (kTwoPi * freq) * (nf / fs);
+                const int n_now = P.n;
+                if (n_now != n_cached) {                                         // (n as f32 / fs): one IEEE division per length
+                    n_cached = n_now;
+                    n_over_fs = (float)n_now / fs;
+                }
+                const float cph = phi + (kTwoPi * freq) * n_over_fs;
                 phi_next = fabsf(cph) < 1.0e6f ? fmod_small(cph, kTwoPi, 0.15915494309189535f) : fmodf(cph, kTwoPi);
                 pt_next = phi_next * 0.15915494309189535f;
                 pt_ok = fabsf(pt_next) < 2.f;
@@ -422,6 +434,8 @@ __global__ void __launch_bounds__((NSW + 2) * 32, MINB) trk_ws_kernel(const TrkA
         int ran = 0;
         const float g1 = 0.001f / st.dll_tau1, g2 = st.dll_tau2 / st.dll_tau1;    // :298
         const float fs1023 = fs * 1023.0f;
+        unsigned long long iv_n = ~0ull;   // epoch length the cached interval belongs to
+        float iv_lo = 1.f, iv_hi = 0.f, iv_scale = 0.f;
         // "may this channel consume an epoch now?" -- TrackingChannel::update (do_tracking.rs:160-172)
         auto may_go = [&]() -> int {
             int go = state == GB_TRK_TRACKING;
@@ -462,16 +476,24 @@ __global__ void __launch_bounds__((NSW + 2) * 32, MINB) trk_ws_kernel(const TrkA
                 const float cdp = cphase + step * nf;
                 cphase_next = fabsf(cdp) < 1.0e8f ? fmod_small(cdp, 1023.f, 9.775171065493646e-4f) : fmodf(cdp, 1023.f);
                 next_idx_next = next_idx + n64;
-                // n' = round(fs / (code_rate' / 1023)) == n  <=  fs * 1023 / code_rate' in (n - 0.45, n + 0.45)
-                r_lo = fs1023 / (nf + 0.45f);
-                r_hi = fs1023 / (nf - 0.45f);
-                const int n = (int)n64;
-                const float i_end = (float)(((n + U * T - 1) / (U * T)) * (U * T));
-                // step' * i_end < 2040 and cphase' + step' * i_end < 2046, as bounds on code_rate' (a little inside)
-                const float r_sane = (2038.f / i_end) * fs;
-                r_single = (((2046.f - cphase_next) / i_end) * fs) * 0.999999f;
-                if (r_sane < r_hi) r_hi = r_sane;
-                if (!(cphase_next >= 0.f && cphase_next < 1023.f) || n64 >= 100000ull) r_hi = 0.f;   // no fast path
+                // n' = round(fs / (code_rate' / 1023)) == n  <=  fs * 1023 / code_rate' in (n - 0.45, n + 0.45); and
+                // step' * i_end < 2040, cphase' + step' * i_end < 2046 as bounds on code_rate' (a little inside).  All of it
+                // depends on n alone (but for one multiply): re-derived only when the epoch length changes
+                if (n64 != iv_n) {
+                    iv_n = n64;
+                    iv_lo = fs1023 / (nf + 0.45f);
+                    iv_hi = fs1023 / (nf - 0.45f);
+                    const int n = (int)n64;
+                    const float i_end = (float)(((n + U * T - 1) / (U * T)) * (U * T));
+                    const float r_sane = (2038.f / i_end) * fs;
+                    if (r_sane < iv_hi) iv_hi = r_sane;
+                    if (n64 >= 100000ull) iv_hi = 0.f;
+                    iv_scale = (fs / i_end) * 0.999999f;
+                }
+                r_lo = iv_lo;
+                r_hi = iv_hi;
+                r_single = (2046.f - cphase_next) * iv_scale;
+                if (!(cphase_next >= 0.f && cphase_next < 1023.f)) r_hi = 0.f;   // no fast path
                 const unsigned long long saved_idx = next_idx;
                 next_idx = next_idx_next;
                 go_pred = (e + 1 < a.n_epochs) ? may_go() : 0;                    // with n' = n, state unchanged

@@ -91,6 +91,21 @@ def test_early_prompt_late_chip_selection_is_exact(gpu, oracle, code_phase, code
         got = _six(tracking.TrackingEngine(gpu).correlate(ch, [seg], mode=mode)[0])
         assert (got == ref).all(), (mode, got, ref)
         assert ch[0].code_phase == och.code_phase
+    # the same decisions through the ring-fed epoch path (FAST: the warp-specialised kernel, whose early / late picks
+    # compare frac = tc - floor(tc) with 0.5 - 2^-25 and 0.5 instead of forming tc +- 0.5)
+    from gnss_sdr_rs_b200 import ring
+    rb = ring.MulticastRingBuffer(gpu, 1 << 13)
+    rb.write_samples(np.ones(4096, np.complex64))
+    for mode in (0, 1):
+        ch, och = _pair(oracle, fs, 9, 0.0, np.float32(0.0), 0, code_row=8)
+        ch[0].code_rate = och.code_rate = np.float32(code_rate)
+        ch[0].code_phase = och.code_phase = np.float32(code_phase)
+        ch[0].num_samples_per_code = och.num_samples_per_code = n
+        ref, _, _ = oracle.trk_do_work(och, np.ones(n, np.complex64))
+        out, ran, _ = tracking.TrackingEngine(gpu).epoch(ch, mode=mode)
+        assert ran[0] == 1
+        assert (_six(out[0]) == ref).all(), (mode, _six(out[0]), ref)
+        assert ch[0].code_phase == och.code_phase and ch[0].num_samples_per_code == och.num_samples_per_code
 
 
 def test_do_work_epochs_closed_loop_ordered(gpu, oracle):
