@@ -103,10 +103,14 @@ __global__ void __launch_bounds__((NSW + 2) * 32, MINB) trk_ws_kernel(const TrkA
     float* red = row + 1024;                                          // [6][NSW] per-warp sums
     __shared__ gb_trk_channel st;
     __shared__ EpochParams P;
+    __shared__ unsigned s_bias;
 
     const int c = blockIdx.x;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (tid == 0) st = a.ch[c];
+    if (tid == 0) {
+        st = a.ch[c];
+        s_bias = (unsigned)__cvta_generic_to_shared(row4) - 16u * 0x4B000000u;
+    }
     __syncthreads();
     {
         const int8_t* src = a.ca_table + (size_t)(st.code_row < 32 ? st.code_row : 0) * 1023;
@@ -126,7 +130,10 @@ __global__ void __launch_bounds__((NSW + 2) * 32, MINB) trk_ws_kernel(const TrkA
     if (warp < NSW) {
         // ------------------------------------------------------------------------------------------- sample warps
         const float2* __restrict__ smp = a.samples;
-        const unsigned row4_bias = (unsigned)__cvta_generic_to_shared(row4) - 16u * 0x4B000000u;
+        // look-up address = 16 * (bits of the round-down add) + bias, ONE integer multiply-add per sample: the bias comes
+        // back from shared memory, so the assembler cannot split it into "window base + constant" again (it then adds the
+        // constant part with a second instruction per look-up)
+        const unsigned row4_bias = *reinterpret_cast<volatile unsigned*>(&s_bias);
         const float c1 = 6.28318548202514648f;        // fl(2 pi)
         const float c2 = -1.74845553146951715e-7f;    // 2 pi - fl(2 pi)
         const float inv_2pi = 0.15915494309189535f;
@@ -225,7 +232,9 @@ __global__ void __launch_bounds__((NSW + 2) * 32, MINB) trk_ws_kernel(const TrkA
                             }
 #pragma unroll
                             for (int k = 0; k < 2; k++) {
-                                const float4 q = lds_f32x4(16u * (unsigned)__float_as_int(pf[k]) + row4_bias);
+                                unsigned qa;
+                                asm("mad.lo.u32 %0, %1, 16, %2;" : "=r"(qa) : "r"((unsigned)__float_as_int(pf[k])), "r"(row4_bias));
+                                const float4 q = lds_f32x4(qa);
                                 const float ec = fr[k] >= 0.49999997f ? q.z : q.y;
                                 const float lc = fr[k] >= 0.5f ? q.y : q.x;
                                 float cv, sv;
