@@ -299,7 +299,7 @@ def tracking_cpu_baseline(stream, cores, n_epochs=2000):
             "x_realtime_1024ch": (n_ch * n_epochs / dt) / 1024.0 / 1000.0}
 
 
-def tracking_e2e(hd, ffi, stream, n_channels=1024, n_ms=2000, chunk_ms=100):
+def tracking_e2e(hd, ffi, stream, n_channels=1024, n_ms=2000, chunk_ms=200):
     """End to end through the public calls with HOST samples: a writer thread feeds the stream chunk by chunk from pinned
     host memory into the HBM ring (gb_ring_write: staged cudaMemcpyAsync on the copy stream) while the tracking thread
     runs gb_trk_run on whatever the ring already holds (do_tracking.rs:160-180: update() waits for head >= next + n).
