@@ -419,6 +419,20 @@ def extra_numbers(hd, ffi):
                                "note": "bit-exact: NCO indices from the precomputed f32 phase orbit, the 16 DC-bias recurrences "
                                        "sequential (FMUL -> FADD per 8 samples): one CTA per stream, bound by that chain; "
                                        "wall clock includes the pinned-less H2D of the block"}
+    # the same calls in tolerance mode (GB_FE_PARALLEL: segmented-scan DC removal over many CTAs), and one large call
+    # (2^24 samples = 128 MiB in, 128 MiB out) where the three kernels, not the launches, set the time
+    fe = ring.DigitalFrontend(hd, 4130400.0, 16367600.0, parallel=True)
+    fe.process_block_into_ring(blk)
+    hd.call("gb_synchronize")
+    t0 = time.perf_counter()
+    for _ in range(8):
+        fe.process_block_into_ring(blk)
+    hd.call("gb_synchronize")
+    dt = (time.perf_counter() - t0) / 8
+    out["digital_frontend_parallel"] = {"samples_per_call": int(blk.size), "wall_ms_per_call": dt * 1e3,
+                                        "msamples_per_sec": blk.size / dt / 1e6,
+                                        "note": "tolerance mode (samples within 1e-5 * max|x| of the reference): partial / "
+                                                "scan / apply launches; wall clock includes the H2D of the block"}
     return out
 
 

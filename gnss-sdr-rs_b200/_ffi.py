@@ -78,6 +78,7 @@ SIGNATURES = {
     "gb_frontend_configure": (_i32, [_vp, _f32, _f32]),
     "gb_frontend_write": (_i32, [_vp, _vp, _u64]),
     "gb_frontend_state": (_i32, [_vp, _vp]),
+    "gb_frontend_set_mode": (_i32, [_vp, _i32]),
     "gb_frontend_orbit": (_i32, [_f32, _f32, _vp, _vp, _vp, _u64]),
     "gb_acq_configure": (_i32, [_vp, _i32, _f32, _i32, _vp]),
     "gb_acq_configure_once": (_i32, [_vp, _i32, _f32, _i32]),

@@ -30,4 +30,12 @@ cudaError_t fe_launch_table(const float2* src, float2* ring, unsigned long long 
                             unsigned long long pos0, unsigned long long mu, unsigned long long period, float alpha,
                             float con, cudaStream_t st);
 
+// Tolerance mode (frontend.cu, "segmented scan"): the same call as three multi-CTA launches.  scratch: at least
+// fe_parallel_scratch(n) float2 elements on the device.
+size_t fe_parallel_scratch(unsigned long long n);
+cudaError_t fe_launch_parallel(const float2* src, float2* ring, unsigned long long head, unsigned long long mask,
+                               unsigned long long n, const float* lut, float* bias, const uint16_t* idx_tab,
+                               unsigned long long pos0, unsigned long long mu, unsigned long long period, float alpha,
+                               float con, float2* scratch, cudaStream_t st);
+
 }  // namespace gb

@@ -89,6 +89,9 @@ struct gb_handle {
     bool fe_ready = false;
     // table-driven NCO (frontend.cu): orbit of the f32 phase accumulator, LUT indices on the device
     bool fe_table = false;
+    int fe_mode = 0;             // GB_FE_EXACT | GB_FE_PARALLEL
+    float2* fe_scratch = nullptr;
+    size_t fe_scratch_cap = 0;
     uint16_t* fe_idx = nullptr;
     std::vector<float> fe_phase;
     uint64_t fe_mu = 0, fe_period = 0, fe_count = 0;
@@ -570,7 +573,7 @@ extern "C" int gb_destroy(gb_handle* h)
     if (!h) return GB_EINVAL;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
-    void* dev_ptrs[] = {h->fwd_bins_dev, h->inv_map_dev, h->code_fft_shift, h->fe_idx, h->fe_lut, h->fe_state, h->fe_stage, h->otw, h->acc_rows, h->spec, h->ring, h->i8_stage, /* h->tw aliases fft[plan].tw, freed below */ h->code_fft, h->tables, h->rot, h->chunk, h->codes_dev, h->cells_dev,
+    void* dev_ptrs[] = {h->fwd_bins_dev, h->inv_map_dev, h->code_fft_shift, h->fe_idx, h->fe_lut, h->fe_state, h->fe_stage, h->fe_scratch, h->otw, h->acc_rows, h->spec, h->ring, h->i8_stage, /* h->tw aliases fft[plan].tw, freed below */ h->code_fft, h->tables, h->rot, h->chunk, h->codes_dev, h->cells_dev,
                         h->rows_dev, h->row_dev, h->ca_table_dev, h->ch_dev, h->corr_dev, h->ran_dev, h->lost_dev,
                         h->hist_dev, h->trk_data, h->offs_dev, h->fine_x, h->fine_y, h->fine_codes, h->fine_u64, h->fine_mean,
                         h->fine_mag, h->tables_perm, h->iq_perm};
@@ -765,7 +768,12 @@ extern "C" int gb_frontend_write(gb_handle* h, const gb_c32* raw, uint64_t n)
     int rc = ensure(h, &h->fe_stage, &h->fe_cap, (size_t)n);
     if (rc) return rc;
     CK(cudaMemcpyAsync(h->fe_stage, raw, n * sizeof(float2), cudaMemcpyHostToDevice, h->s_copy));
-    if (h->fe_table) {
+    if (h->fe_table && h->fe_mode == GB_FE_PARALLEL) {
+        if ((rc = ensure(h, &h->fe_scratch, &h->fe_scratch_cap, gb::fe_parallel_scratch(n)))) return rc;
+        CK(gb::fe_launch_parallel(h->fe_stage, h->ring, h->ring_head, h->ring_cap - 1, n, h->fe_lut, h->fe_state + 1, h->fe_idx,
+                                  gb::fe_orbit_pos(h->fe_count, h->fe_mu, h->fe_period), h->fe_mu, h->fe_period, 0.001f,
+                                  1.0f - 0.001f, h->fe_scratch, h->s_copy));
+    } else if (h->fe_table) {
         CK(gb::fe_launch_table(h->fe_stage, h->ring, h->ring_head, h->ring_cap - 1, n, h->fe_lut, h->fe_state + 1, h->fe_idx,
                                gb::fe_orbit_pos(h->fe_count, h->fe_mu, h->fe_period), h->fe_mu, h->fe_period, 0.001f,
                                1.0f - 0.001f, h->s_copy));
@@ -777,6 +785,17 @@ extern "C" int gb_frontend_write(gb_handle* h, const gb_c32* raw, uint64_t n)
     CK(cudaEventRecord(h->ev_copy, h->s_copy));
     h->fe_count += n;
     h->ring_head += n;
+    return GB_OK;
+}
+
+extern "C" int gb_frontend_set_mode(gb_handle* h, int mode)
+{
+    if (!h) return GB_ESTATE;
+    if (mode != GB_FE_EXACT && mode != GB_FE_PARALLEL) return GB_EINVAL;
+    std::lock_guard<std::recursive_mutex> lk(h->mu_ring);
+    // the segmented scan looks the NCO up by sample number: without an orbit table there is nothing to parallelise
+    if (mode == GB_FE_PARALLEL && h->fe_ready && !h->fe_table) return GB_EUNSUPPORTED;
+    h->fe_mode = mode;
     return GB_OK;
 }
 

@@ -101,6 +101,14 @@ int gb_ring_reset(gb_handle *h);
  * fall back to a one-thread sequential accumulator with identical results. */
 int gb_frontend_configure(gb_handle *h, float f_if, float fs_in);
 int gb_frontend_write(gb_handle *h, const gb_c32 *raw, uint64_t n);
+/* GB_FE_EXACT (default): one CTA walks the 16 DC-bias recurrences in the reference's order -- bit-identical output.
+ * GB_FE_PARALLEL: the recurrences as a segmented scan over many CTAs (three launches per call).  Every step inside a
+ * 256-sample segment is rounded like dc_remove.rs:23-29, the composition across segments is not: samples and bias
+ * state agree with the reference to 1e-5 * max|x| (measured 1e-6; tests/test_gpu_ring_fft.py), the NCO phase stays
+ * exact.  Returns GB_EUNSUPPORTED when the configured (f_if, fs) has no orbit table (sequential fallback active). */
+#define GB_FE_EXACT 0
+#define GB_FE_PARALLEL 1
+int gb_frontend_set_mode(gb_handle *h, int mode);
 int gb_frontend_state(gb_handle *h, float *state17 /* phase_accumulator, bias_re[8], bias_im[8] */);
 /* Host-only diagnostic (no device needed): the orbit gb_frontend_configure would build.  mu / lambda receive the tail
  * and cycle lengths; idx_out (may be NULL) receives the LUT index of samples 0 .. n_idx-1.  GB_EUNSUPPORTED if the

@@ -152,3 +152,42 @@ def test_digital_frontend_long_write_and_reconfigure(gpu, oracle):
         ref = np.concatenate([oracle.frontend_process(of, raw[:131072]), oracle.frontend_process(of, raw[131072:])])
         assert rb.copy_to_slice(start, n).tobytes() == ref.tobytes()
         assert fe.state()["phase_accumulator"] == of.phase_accumulator
+
+
+@pytest.mark.parametrize("f_if,fs", [(4130400.0, 16367600.0), (4092000.0, 16368000.0)])
+def test_digital_frontend_parallel_mode_within_tolerance(gpu, oracle, ffi, f_if, fs):
+    """GB_FE_PARALLEL (segmented-scan DC removal, three multi-CTA launches): NOT bit-exact by construction -- samples
+    and bias state within 1e-5 * max|x| of rf/frontend.rs (float32 rounding of the segment composition), the NCO phase
+    exact.  Call sizes: one step, a ragged segment, several segments + ragged tail, the bench's 131072, and a ring wrap."""
+    from gnss_sdr_rs_b200 import ring
+    ffi.tuning_set("fe_sequential", 0)
+    rng = np.random.default_rng(17)
+    sizes = (8, 8 * 5, 256, 8 * 100, 2048, 131072, 8 * 4097, 131072)
+    n = sum(sizes)
+    raw = ((rng.standard_normal(n) * 25 + 40.0) + 1j * (rng.standard_normal(n) * 25 - 60.0)).astype(np.complex64)
+    scale = float(np.abs(raw.view(np.float32)).max())
+    rb = ring.MulticastRingBuffer(gpu, 1 << 18)     # 262144 < n: the last writes wrap
+    fe = ring.DigitalFrontend(gpu, f_if, fs, parallel=True)
+    of = oracle.frontend(f_if, fs)
+    pos = 0
+    worst = 0.0
+    for blk in sizes:
+        fe.process_block_into_ring(raw[pos:pos + blk])
+        ref = oracle.frontend_process(of, raw[pos:pos + blk])
+        got = rb.copy_to_slice(pos, blk)
+        worst = max(worst, float(np.abs(got.view(np.float32) - ref.view(np.float32)).max()))
+        pos += blk
+        st = fe.state()
+        assert st["phase_accumulator"] == of.phase_accumulator
+        np.testing.assert_allclose(st["bias_re"], np.array(of.bias_re[:], np.float32), rtol=0, atol=1e-5 * scale)
+        np.testing.assert_allclose(st["bias_im"], np.array(of.bias_im[:], np.float32), rtol=0, atol=1e-5 * scale)
+    assert worst <= 1e-5 * scale, (worst, scale)
+    print("parallel front-end: worst |delta| = %.3g (%.3g of max|x|)" % (worst, worst / scale))
+    # back to the default: bit-exact again from a fresh configure
+    fe = ring.DigitalFrontend(gpu, f_if, fs)
+    of = oracle.frontend(f_if, fs)
+    start = rb.get_head()
+    fe.process_block_into_ring(raw[:4096])
+    assert rb.copy_to_slice(start, 4096).tobytes() == oracle.frontend_process(of, raw[:4096]).tobytes()
+    with pytest.raises(ffi.GnssB200Error):
+        gpu.call("gb_frontend_set_mode", 7)
