@@ -20,6 +20,22 @@ for _ in range(20):
     dev.copy_(x_pin, non_blocking=True); torch.cuda.synchronize()
 dt = (time.perf_counter() - t0) / 20
 print("torch pinned H2D %.3f ms for %.1f MB = %.1f GB/s" % (dt * 1e3, x.nbytes / 1e6, x.nbytes / dt / 1e9))
+# pinned H2D against transfer size: the per-copy fixed cost (~8-10 us of submission + DMA start) and the link's asymptote
+big = torch.empty(1 << 28, dtype=torch.uint8).pin_memory()
+bigd = torch.empty(1 << 28, dtype=torch.uint8, device="cuda")
+for sz in (1 << 16, 1 << 18, 1 << 20, 6547200, 1 << 24, 1 << 26, 1 << 28):
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(2):
+        bigd[:sz].copy_(big[:sz], non_blocking=True)
+    torch.cuda.synchronize()
+    reps = 20 if sz <= (1 << 24) else 4
+    ev0.record()
+    for _ in range(reps):
+        bigd[:sz].copy_(big[:sz], non_blocking=True)
+    ev1.record(); torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / reps
+    print("pinned H2D %10d B: %8.1f us  %6.1f GB/s" % (sz, ms * 1e3, sz / ms / 1e6))
+del big, bigd
 rb = ring.MulticastRingBuffer(hd, 1 << 20)
 rb.write_samples(x)
 eng = acquisition.AcquisitionEngine(hd, bench.N_FFT, bench.FS, 32)
