@@ -646,7 +646,9 @@ def run_ours(args, rank, world, local_rank):
     e2e_value = units * cells / (e2e_ms * 1e-3)
 
     # ------------------------------------------------------------------ N > 1: the other shardings of SURVEY 8e
-    strong = cfg4 = trk_sharded = None
+    strong = cfg4 = trk_sharded = snaps = None
+    # read before the other configurations below re-plan the handle
+    n_fwd_main = eng.forward_bins() if args.acq_mode != "fused" else len(DOPPLERS)
     if dist is not None:
         if not by_prn:
             sb = timed_block(True, max(10, args.steps // 2), 3)   # ONE recording, PRNs dealt to the ranks
@@ -680,10 +682,15 @@ def run_ours(args, rank, world, local_rank):
                                "locked_channels": int(t2[0]),
                                "x_realtime": 2.0 / (ms_max * 1e-3), "mode": tr["mode"], "fs": tr["fs"], "layout": tr["layout"],
                                "sharding": "by channel, no collective between epochs"}
+        if not args.acq_only:
+            try:
+                snaps = batch_snapshots(hd, ffi, dist, group, rank, world)
+            except Exception as e:  # report, never hide
+                snaps = {"error": repr(e)}
 
     if rank == 0:
         peak_tf = ctypes_float(hd, "gb_bench_fp32_tflops")
-        n_fwd = eng.forward_bins() if args.acq_mode != "fused" else len(DOPPLERS)
+        n_fwd = n_fwd_main
         n_shift = int(math.ceil(len(DOPPLERS) / n_fwd)) if n_fwd < len(DOPPLERS) else 1
         minimal, fused_flops, shared_flops = acq_flops(n_fwd)
         as_run = fused_flops if args.acq_mode == "fused" else shared_flops
@@ -741,6 +748,8 @@ def run_ours(args, rank, world, local_rank):
             line["config4_multi_gnss_20msps"] = cfg4
         if trk_sharded is not None:
             line["tracking_sharded"] = trk_sharded
+        if snaps is not None:
+            line["config5_batch_snapshots"] = snaps
         if world == 1:
             cores = os.cpu_count() or 1
             v, dt, n_prn, ocells = cpu_baseline_acq(x, cores)
@@ -775,6 +784,11 @@ def run_ours(args, rank, world, local_rank):
                     line["extras"] = extra_numbers(hd, ffi)
             except Exception as e:
                 line["extras"] = {"error": repr(e)}
+            try:
+                if not args.acq_only:
+                    line["config5_batch_snapshots"] = batch_snapshots(hd, ffi, None, None, 0, 1)
+            except Exception as e:
+                line["config5_batch_snapshots"] = {"error": repr(e)}
         print(json.dumps(line), flush=True)
     if group is not None:
         group.close()
@@ -886,6 +900,120 @@ def multi_gnss_20msps(hd, ffi, dist, group, rank, world):
     out["galileo_e1_like"] = {"fft_size": n2, "codes": 8, "n_doppler": 41, "num_integrations": 5,
                               "kernel_ms_max_over_ranks": float(t2[0]), "cells_per_sec": 8 * 41 * n2 / (float(t2[0]) * 1e-3)}
     return out
+
+
+def batch_snapshots(hd, ffi, dist, group, rank, world, per_gpu=64):
+    """BASELINE configs[4]: batch snapshot acquisition of 512 synthetic 100 ms recordings, all constellations, on 8 GPUs
+    (64 recordings per GPU at any N: weak scaling; 512 at N = 8).  Every recording is 100 ms at 20 Msps (2 M complex
+    samples, 16 MB) and is searched for GPS L1 C/A x32 + BeiDou-B1I-like x32 (N = 20000, 41 bins, 100 x 1 ms
+    non-coherent) and 8 Galileo-E1-like 4 ms BOC(1,1) codes (N = 80000, 41 bins, 25 x 4 ms).  The recordings of a rank
+    sit in its HBM ring (1 GB); recordings are independent, so the only exchange is one final gather of the result
+    rows.  No reference semantics exist for these signals: throughput + every planted satellite must be found."""
+    import torch
+    from gnss_sdr_rs_b200 import acquisition, ring, sdr_mock
+    fs, n1, n4, rec = 20.0e6, 20000, 80000, 2000000
+    k1, k4 = rec // n1, rec // n4
+    codes = [sdr_mock.resample_code(sdr_mock.ca_code(p), 1.023e6, fs, n1) for p in range(1, 33)]
+    codes += [sdr_mock.resample_code(sdr_mock.b1i_code(p), 2.046e6, fs, n1) for p in range(1, 33)]
+    codes = np.stack(codes).astype(np.int8)
+    e1 = np.stack([sdr_mock.resample_code(sdr_mock.e1_surrogate_code(p), 1.023e6, fs, n4, boc11=True) for p in range(1, 9)]).astype(np.int8)
+    # eight signal templates (one GPS, one BeiDou, one Galileo satellite each, 45 dB-Hz); recording i = template i % 8
+    # rotated by its own number of samples (a different code phase in every recording) in fresh noise
+    t = np.arange(rec, dtype=np.float64)
+    amp = np.sqrt(10.0 ** (45.0 / 10.0) / fs)
+    templates, plants = [], []
+    for k in range(8):
+        g, b, e = (5 * k + 3) % 32, 32 + (7 * k + 1) % 32, k % 8
+        pl = [(g, 250.0 * (k - 4), 1000 + 2111 * k, n1), (b, -250.0 * (2 * k - 7), 300 + 1777 * k, n1), (64 + e, 125.0 * (3 * k - 10), 5000 + 9001 * k, n4)]
+        sig = np.zeros(rec, np.complex64)
+        for row, dop, cp, n in pl:
+            c = codes[row] if row < 64 else e1[row - 64]
+            sig += (amp * c[(np.arange(rec) - cp) % n] * np.exp(2j * np.pi * ((dop * t / fs) % 1.0))).astype(np.complex64)
+        templates.append(sig)
+        plants.append(pl)
+    rb = ring.MulticastRingBuffer(hd, 1 << 27)
+    shifts = []
+    scale = np.float32(1 / np.sqrt(2))
+    for i in range(per_gpu):
+        gi = rank * per_gpu + i
+        rng = np.random.default_rng(0x6E5A + gi)
+        x = (rng.standard_normal(2 * rec, dtype=np.float32) * scale).view(np.complex64)
+        sh = (gi * 7919) % n4
+        x += np.roll(templates[gi % 8], sh)
+        shifts.append(sh)
+        rb.write_samples(x)
+    del templates
+    hd.call("gb_synchronize")
+
+    def one_pass(eng, k):
+        raws = []
+        eng.search_ring_raw(0, k)   # warm-up (plan, buffers)
+        hd.call("gb_synchronize")
+        t0 = time.perf_counter()
+        dev = 0.0
+        for i in range(per_gpu):
+            raws.append(eng.search_ring_raw(i * rec, k))
+            dev += eng.last_kernel_ms()
+        hd.call("gb_synchronize")
+        return raws, (time.perf_counter() - t0) * 1e3, dev
+
+    err = None
+    try:
+        eng = acquisition.AcquisitionEngine(hd, n1, fs, n_prn=64, codes=codes)
+        eng.make_doppler_tables(0.0, np.arange(-5000, 5001, 250, dtype=np.float32))
+        eng.set_detector(7.0, 0)
+        r1, wall1, dev1 = one_pass(eng, k1)
+        eng = acquisition.AcquisitionEngine(hd, n4, fs, n_prn=8, codes=e1)
+        eng.make_doppler_tables(0.0, np.arange(-2500, 2501, 125, dtype=np.float32))
+        eng.set_detector(7.0, 0)
+        r4, wall4, dev4 = one_pass(eng, k4)
+    except Exception as e:
+        err = repr(e)
+    if dist is not None:   # a rank that failed must not leave its peers waiting in the gather
+        okf = torch.tensor([0.0 if err else 1.0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(okf, op=dist.ReduceOp.MIN)
+        if float(okf[0]) == 0.0:
+            return {"error": err or "a rank failed"}
+    elif err:
+        return {"error": err}
+    # result table of this rank: per recording 64 + 8 rows
+    rows = 72
+    tab = (ffi.AcqResult * (per_gpu * rows))()
+    n_ok = n_found = 0
+    for i in range(per_gpu):
+        for j in range(64):
+            tab[i * rows + j] = r1[i][j]
+        for j in range(8):
+            tab[i * rows + 64 + j] = r4[i][j]
+        got = {j: tab[i * rows + j] for j in range(rows) if tab[i * rows + j].found}
+        n_found += len(got)
+        for row, _, cp, n in plants[(rank * per_gpu + i) % 8]:
+            if row in got and min((int(got[row].code_phase_samples) - cp - shifts[i]) % n, (cp + shifts[i] - int(got[row].code_phase_samples)) % n) <= 10:
+                n_ok += 1
+    wall = wall1 + wall4
+    gather_ms = 0.0
+    if dist is not None:
+        t0 = time.perf_counter()
+        allr = group.gather_results(tab, per_gpu * rows)
+        gather_ms = (time.perf_counter() - t0) * 1e3
+        v = torch.tensor([wall + gather_ms, dev1 + dev4], dtype=torch.float64, device="cuda")
+        dist.all_reduce(v, op=dist.ReduceOp.MAX)
+        c = torch.tensor([float(n_ok), float(n_found)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        wall_max, dev_max = [float(a) for a in v.cpu()]
+        n_ok, n_found = [int(a) for a in c.cpu()]
+        n_rows_gathered = len(allr)
+    else:
+        wall_max, dev_max, n_rows_gathered = wall, dev1 + dev4, per_gpu * rows
+    n_rec = per_gpu * world
+    cells = n_rec * (64 * 41 * n1 + 8 * 41 * n4)
+    return {"recordings": n_rec, "recordings_per_gpu": per_gpu, "recording_ms": 100, "fs": fs,
+            "signals": "GPS L1 C/A x32 + BeiDou-B1I-like x32 (N = 20000, 41 bins, 100 x 1 ms) + Galileo-E1-like x8 (N = 80000, 41 bins, 25 x 4 ms)",
+            "sharding": "recordings dealt to the GPUs (resident in each GPU's HBM ring, 1 GB), one final gather of %d result rows" % n_rows_gathered,
+            "wall_ms_max_over_ranks": wall_max, "kernel_ms_max_over_ranks": dev_max, "final_gather_ms": gather_ms,
+            "cells_per_sec": cells / (wall_max * 1e-3), "x_realtime": n_rec * 100.0 / wall_max,
+            "rank0_pass_ms": {"gps_beidou_n20000": wall1, "galileo_n80000": wall4},
+            "planted": 3 * n_rec, "planted_found": n_ok, "rows_found": n_found, "scaling": "weak"}
 
 
 def ctypes_float(hd, name):
