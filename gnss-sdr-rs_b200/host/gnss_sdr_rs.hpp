@@ -14,6 +14,7 @@
 #include <set>
 #include <stdexcept>
 #include <utility>
+#include <array>
 #include <vector>
 
 #include "../../include/gnss_b200.h"
@@ -118,6 +119,40 @@ class MulticastRingBuffer {
         if (rc) throw MulticastRingBuffError(rc);
     }
     const std::shared_ptr<GpuEngine>& engine() const { return e_; }
+
+  private:
+    std::shared_ptr<GpuEngine> e_;
+};
+
+// rf/frontend.rs:6-62 + rf/rf_thread.rs:44-48 -- DC removal + NCO-LUT mix; the processed block goes straight into the ring
+// (process_block and write_samples of rf_thread's loop body in one call; the raw block is NOT modified in place).
+class DigitalFrontend {
+  public:
+    DigitalFrontend(std::shared_ptr<GpuEngine> e, float f_if, float fs_in, float /*fs_out*/) : e_(std::move(e))
+    {
+        const int rc = gb_frontend_configure(e_->raw(), f_if, fs_in);
+        if (rc) throw MulticastRingBuffError(rc);
+    }
+    // false (default): bit-identical to the reference.  true: segmented-scan DC removal, 1e-6 * max|x| from it, 5x the rate.
+    void set_parallel(bool on)
+    {
+        const int rc = gb_frontend_set_mode(e_->raw(), on ? GB_FE_PARALLEL : GB_FE_EXACT);
+        if (rc) throw MulticastRingBuffError(rc);
+    }
+    // raw_floats: interleaved I/Q, a multiple of 16 floats (chunks_exact_mut(16), frontend.rs:34)
+    void process_block(const std::vector<float>& raw_floats)
+    {
+        const int rc = gb_frontend_write(e_->raw(), reinterpret_cast<const gb_c32*>(raw_floats.data()), raw_floats.size() / 2);
+        if (rc) throw MulticastRingBuffError(rc);
+    }
+    // phase_accumulator, bias_re[8], bias_im[8]
+    std::array<float, 17> state() const
+    {
+        std::array<float, 17> st{};
+        const int rc = gb_frontend_state(e_->raw(), st.data());
+        if (rc) throw MulticastRingBuffError(rc);
+        return st;
+    }
 
   private:
     std::shared_ptr<GpuEngine> e_;

@@ -8,6 +8,8 @@
 #include <cstring>
 #include <chrono>
 #include <thread>
+#include <algorithm>
+#include <cmath>
 
 #include "../../gnss-sdr-rs_b200/host/gnss_sdr_rs.hpp"
 
@@ -268,6 +270,42 @@ static void test_acquisition(std::shared_ptr<GpuEngine> e)
     CHECK(fabsf(X[512].re - 0.f) < 1e-6f && fabsf(X[512].im + 1.f) < 1e-6f);  // exp(-j pi/2)
 }
 
+// rf/frontend.rs through the mirror: the exact and the tolerance mode agree to 1e-5 * max|x|, the DC offset is gone
+// after a few time constants, a block that is not a multiple of 16 floats is refused (chunks_exact_mut(16)).
+static void test_frontend(std::shared_ptr<GpuEngine> e)
+{
+    const size_t n = 65536;
+    std::vector<float> raw(2 * n);
+    uint32_t lcg = 12345;
+    for (size_t i = 0; i < 2 * n; i++) {
+        lcg = lcg * 1664525u + 1013904223u;
+        raw[i] = ((float)(lcg >> 8) / 16777216.0f - 0.5f) * 8.0f + ((i & 1) ? -20.0f : 30.0f);
+    }
+    std::vector<Complex32> a(n), b(n);
+    for (int pass = 0; pass < 2; pass++) {
+        MulticastRingBuffer ring(e, 1 << 17);
+        DigitalFrontend fe(e, 4130400.0f, 16367600.0f, 16367600.0f);
+        fe.set_parallel(pass == 1);
+        fe.process_block(std::vector<float>(raw.begin(), raw.begin() + n));        // two calls: the state carries over
+        fe.process_block(std::vector<float>(raw.begin() + n, raw.end()));
+        CHECK(ring.get_head() == n);
+        ring.copy_to_slice(0, pass ? b.data() : a.data(), n);
+        const auto st = fe.state();
+        CHECK(std::fabs(st[1] - 30.0f) < 1.0f && std::fabs(st[9] + 20.0f) < 1.0f);   // bias lanes converged to the offsets
+        bool threw = false;
+        try { fe.process_block(std::vector<float>(24)); } catch (const MulticastRingBuffError&) { threw = true; }
+        CHECK(threw);
+    }
+    float worst = 0.f;
+    double tail = 0.0;
+    for (size_t i = 0; i < n; i++) {
+        worst = std::max(worst, std::max(std::fabs(a[i].re - b[i].re), std::fabs(a[i].im - b[i].im)));
+        if (i >= n - 4096) tail += a[i].re;
+    }
+    CHECK(worst < 1e-5f * 34.0f);
+    CHECK(std::fabs(tail / 4096.0) < 0.5);   // |x| ~ 36 with the offset, ~0 mean without
+}
+
 int main(int argc, char** argv)
 {
     const bool cpu_only = argc > 1 && !strcmp(argv[1], "--cpu");
@@ -282,6 +320,7 @@ int main(int argc, char** argv)
     } else {
         auto e = std::make_shared<GpuEngine>(0);
         test_ring(e);
+        test_frontend(e);
         test_pll_frequency_pull_in(e);
         test_dll_code_phase_tracking(e);
         test_acquisition(e);
