@@ -21,6 +21,20 @@ def test_cpp_host_mirror_cpu_part(tmp_path, ffi):
     assert r.returncode == 0, r.stdout + r.stderr
 
 
+def test_static_archive_links(tmp_path, ffi):
+    """the reference's build.rs links a static archive from src/c_lib (libconvenience.a); libgnss_b200.a is the
+    same objects as the shared library and must link with cudart_static alone (no NCCL: it is dlopen'ed on demand)."""
+    libdir = os.path.dirname(ffi.LIB_PATH)
+    arch = os.path.join(libdir, "libgnss_b200.a")
+    assert os.path.exists(arch), "build.sh did not produce the static archive"
+    cuda_lib = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "lib64")
+    exe = str(tmp_path / "test_host_mirror_static")
+    subprocess.run(["g++", "-std=c++17", "-O1", os.path.join(ROOT, "tests", "cpp", "test_host_mirror.cpp"), "-o", exe, arch,
+                    "-L", cuda_lib, "-lcudart_static", "-ldl", "-lrt", "-lpthread"], check=True)
+    r = subprocess.run([exe, "--cpu"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+
+
 @pytest.mark.gpu
 def test_cpp_host_mirror_reference_tests(tmp_path, ffi):
     r = subprocess.run([_build(tmp_path, ffi)], capture_output=True, text=True)
