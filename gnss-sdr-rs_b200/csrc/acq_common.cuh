@@ -20,7 +20,7 @@ using P8184 = PfaPlan<8184, 288, 1, 0, 8, 33, 31>;
 using P16368 = PfaPlan<16368, 544, 1, 0, 16, 33, 31>;
 using P20000 = Plan<20000, 512, 1, 0, 8, 4, 25, 25>;
 
-// tuning variants of the headline plan (selected with the environment variable GB_ACQ_VARIANT=1..4)
+// tuning variants of the headline plan (GB_TUNING builds only; selected with gb_tuning_set("acq_variant", 1..))
 using P4092v1 = Plan<4092, 160, 4, 0, 12, 11, 31>;   // the Cooley-Tukey form of the default plan (A/B)
 using P4092v2 = PfaPlan<4092, 160, 3, 0, 12, 11, 31>;
 using P4092v3 = Plan<4092, 192, 2, 0, 12, 11, 31>;
