@@ -92,6 +92,12 @@ __device__ __forceinline__ pk64 add2_rm(pk64 a, pk64 b)   // round towards -inf 
     asm("add.rm.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
     return r;
 }
+__device__ __forceinline__ pk64 fma2_rm(pk64 a, pk64 b, pk64 c)   // a * b + c rounded towards -inf (one rounding)
+{
+    pk64 r;
+    asm("fma.rm.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
 __device__ __forceinline__ pk64 mul2(pk64 a, pk64 b)
 {
     pk64 r;

@@ -98,8 +98,8 @@ __global__ void __launch_bounds__((NSW + 2) * 32, MINB) trk_ws_kernel(const TrkA
     constexpr int CHAIN = U / NSFU;
     static_assert(U % NSFU == 0, "whole rotation chains");
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float4* row4 = reinterpret_cast<float4*>(smem_raw);               // 1024 x {chip k-1, chip k, chip k+1, 0}
-    float* row = reinterpret_cast<float*>(row4 + 1024);               // 1024: plain row (general path)
+    float4* row4 = reinterpret_cast<float4*>(smem_raw);               // 2048 half chips x {early, prompt, late, 0}
+    float* row = reinterpret_cast<float*>(row4 + 2048);               // 1024: plain row (general path)
     float* red = row + 1024;                                          // [6][NSW] per-warp sums
     __shared__ gb_trk_channel st;
     __shared__ EpochParams P;
@@ -114,10 +114,12 @@ __global__ void __launch_bounds__((NSW + 2) * 32, MINB) trk_ws_kernel(const TrkA
     __syncthreads();
     {
         const int8_t* src = a.ca_table + (size_t)(st.code_row < 32 ? st.code_row : 0) * 1023;
-        for (int i = tid; i < 1023; i += NT) {
-            const float pk = (float)src[i];
-            row[i] = pk;
-            row4[i] = make_float4((float)src[i == 0 ? 0 : i - 1], pk, (float)src[i == 1022 ? 0 : i + 1], 0.f);
+        for (int i = tid; i < 1023; i += NT) row[i] = (float)src[i];
+        // entry h = floor(2 * chip argument): the chips get_ca_chip returns for tc + 0.5, tc and tc - 0.5 when tc lies in
+        // [h / 2, (h + 1) / 2) -- floor(tc + 0.5) % 1023 (1023 -> 0), floor(tc), max(floor(tc - 0.5), 0) (Q7)
+        for (int h = tid; h < 2048; h += NT) {
+            const int e = ((h + 1) >> 1) % 1023, p = (h >> 1) % 1023, l = h == 0 ? 0 : ((h - 1) >> 1) % 1023;
+            row4[h] = make_float4((float)src[e], (float)src[p], (float)src[l], 0.f);
         }
     }
     const float fs = st.fs;                          // never changes during a run
@@ -213,30 +215,22 @@ __global__ void __launch_bounds__((NSW + 2) * 32, MINB) trk_ws_kernel(const TrkA
                                 t0 = t0 >= 1023.f ? t0 - 1023.f : t0;
                                 t1 = t1 >= 1023.f ? t1 - 1023.f : t1;
                             }
-                            // floor(tc) sits in the mantissa of the round-down add; early / late chips are
-                            // floor(tc + 0.5) % 1023 in {k, k+1} and max(floor(tc - 0.5), 0) in {k-1, k} (Q7).  The reference
-                            // decides on its f32 sums tc + 0.5 and tc - 0.5; with frac = tc - floor(tc) (exact) those
-                            // decisions are frac >= 0.5 - 2^-25 (the one value whose sum ties up to the next integer:
-                            // tc = 0.49999997) and frac >= 0.5 -- checked against the literal sums on every float within
-                            // 4 ulp of every half chip and 2.5 M random arguments, and by the exact-selection test
-                            const pk64 tc2 = pk2(t0, t1);
-                            const pk64 pf2 = add2_rm(tc2, pk2(8388608.0f, 8388608.0f));
-                            float pf[2], fr[2];
+                            // floor(2 tc) sits in the mantissa of ONE round-down multiply-add (2 tc is exact); the table
+                            // entry of that half chip holds the three chips.  The reference decides on its f32 sums
+                            // tc + 0.5 and tc - 0.5: floor(tc - 0.5) changes exactly at frac(tc) = 0.5, floor(tc + 0.5) at
+                            // frac(tc) = 0.5 too EXCEPT for tc = 0.49999997 = 0.5 - 2^-25, whose sum ties up to 1.0 -- the
+                            // code warp looks for that one argument and corrects the early sums (checked against the literal
+                            // sums on every float within 4 ulp of every half chip and 2.5 M random arguments, DESIGN 4.3,
+                            // and by the exact-selection test)
+                            const pk64 pf2 = fma2_rm(pk2(t0, t1), pk2(2.0f, 2.0f), pk2(8388608.0f, 8388608.0f));
+                            float pf[2];
                             upk2(pf2, pf[0], pf[1]);
-                            {
-                                // frac = tc - (pf - 2^23): two exact subtractions folded into one packed add chain
-                                const pk64 fl2 = add2(pf2, pk2(-8388608.0f, -8388608.0f));   // exact
-                                float f0, f1;
-                                upk2(fl2, f0, f1);
-                                upk2(add2(tc2, pk2(-f0, -f1)), fr[0], fr[1]);                 // exact (Sterbenz)
-                            }
 #pragma unroll
                             for (int k = 0; k < 2; k++) {
                                 unsigned qa;
                                 asm("mad.lo.u32 %0, %1, 16, %2;" : "=r"(qa) : "r"((unsigned)__float_as_int(pf[k])), "r"(row4_bias));
                                 const float4 q = lds_f32x4(qa);
-                                const float ec = fr[k] >= 0.49999997f ? q.z : q.y;
-                                const float lc = fr[k] >= 0.5f ? q.y : q.x;
+                                const float ec = q.x, lc = q.z;
                                 float cv, sv;
                                 upk2(cs2[u + k], cv, sv);
                                 const float2 x = cur[u + k];
@@ -508,6 +502,46 @@ __global__ void __launch_bounds__((NSW + 2) * 32, MINB) trk_ws_kernel(const TrkA
                 go_pred = (e + 1 < a.n_epochs) ? may_go() : 0;                    // with n' = n, state unchanged
                 next_idx = saved_idx;
             }
+            // ---- the one chip argument the half-chip table gets wrong (see the sample warps): tc == 0.5 - 2^-25, where the
+            // reference's early replica is already the next chip.  Only a sample before the first code wrap can produce it
+            // (after a wrap tc = t - 1023 with t in [1023, 1024) is a multiple of 2^-14), and tc is monotonic there, so at
+            // most one sample hits: three lanes test the samples around the crossing of 0.5 with the sample warps' own
+            // arithmetic; a hit (about once in 1e7 epochs) adds x * carrier * (chip 1 - chip 0) to the early sums.
+            float fix_re = 0.f, fix_im = 0.f;
+            {
+                const float4 pd4 = *reinterpret_cast<const float4*>(&P.code_step);
+                const float step_r = pd4.x, cph_r = pd4.y;
+                const int n_r = __float_as_int(pd4.z), fl_r = __float_as_int(pd4.w);
+                bool hit = false;
+                int i_hit = 0;
+                if (lane < 3 && (fl_r & 2) && cph_r < 0.5f) {
+                    const float est = step_r > 0.f ? (0.5f - cph_r) * rcp_fast(step_r) : 0.f;
+                    if (est < 1.0e6f) {
+                        const int i = (int)rintf(est) + lane - 1;
+                        if (i >= 0 && i < n_r) {
+                            const float t = __fadd_rn(cph_r, __fmul_rn((float)i, step_r));
+                            hit = __float_as_int(t) == 0x3EFFFFFF;
+                            i_hit = i;
+                        }
+                    }
+                }
+                if (__ballot_sync(0xffffffffu, hit)) {
+                    if (hit && P.carr_ok) {
+                        const float2 x = __ldg(a.samples + ((P.s0 + (unsigned)i_hit) & mask32));
+                        const float ut = fmaf((float)i_hit, P.f_turn, P.cp_turn);
+                        const float r = (ut - rint_small(ut)) * 6.28318548202514648f;
+                        const float cv = __cosf(r), sv = __sinf(r);
+                        const float d = row[1] - row[0];
+                        fix_re = (x.x * cv + x.y * sv) * d;
+                        fix_im = (x.y * cv - x.x * sv) * d;
+                    }
+                    // lanes 0..3 all end with the total (lanes 2 and 3 own the early sums below)
+                    fix_re += __shfl_xor_sync(0xffffffffu, fix_re, 1);
+                    fix_im += __shfl_xor_sync(0xffffffffu, fix_im, 1);
+                    fix_re += __shfl_xor_sync(0xffffffffu, fix_re, 2);
+                    fix_im += __shfl_xor_sync(0xffffffffu, fix_im, 2);
+                }
+            }
             named_sync(BAR_PART, NT);
             {
                 // lane k < 6 sums the per-warp partials of sum k; squares meet their partner through one shuffle, the
@@ -526,6 +560,8 @@ __global__ void __launch_bounds__((NSW + 2) * 32, MINB) trk_ws_kernel(const TrkA
                     v = red[k * NSW];
                     for (int j = 1; j < NSW; j++) v += red[k * NSW + j];
                 }
+                if (lane == 2) v += fix_re;
+                if (lane == 3) v += fix_im;
 #pragma unroll
                 for (int j = 0; j < 6; j++) six[j] = __shfl_sync(0xffffffffu, v, j);
             }
@@ -598,7 +634,7 @@ __global__ void __launch_bounds__((NSW + 2) * 32, MINB) trk_ws_kernel(const TrkA
 
 template <int NSW, int U, int NSFU, int MINB = (NSW >= 8 ? 2 : 4)> static cudaError_t launch_ws(const TrkArgs& a, cudaStream_t st)
 {
-    const size_t smem = 1024 * sizeof(float4) + 1024 * sizeof(float) + 6 * NSW * sizeof(float) + 64;
+    const size_t smem = 2048 * sizeof(float4) + 1024 * sizeof(float) + 6 * NSW * sizeof(float) + 64;
     trk_ws_kernel<NSW, U, NSFU, MINB><<<a.n_channels, (NSW + 2) * 32, smem, st>>>(a);
     return cudaGetLastError();
 }
@@ -622,6 +658,10 @@ cudaError_t trk_ws_launch(const TrkArgs& a, cudaStream_t st, int variant)
     case 488: return launch_ws<4, 8, 8>(a, st);
     case 482: return launch_ws<4, 8, 2>(a, st);
     case 481: return launch_ws<4, 8, 1>(a, st);
+    case 4415: return launch_ws<4, 4, 1, 5>(a, st);
+    case 4416: return launch_ws<4, 4, 1, 6>(a, st);
+    case 4815: return launch_ws<4, 8, 1, 5>(a, st);
+    case 8413: return launch_ws<8, 4, 1, 3>(a, st);
     case 2817: return launch_ws<2, 8, 1, 7>(a, st);
     case 2816: return launch_ws<2, 8, 1, 6>(a, st);
     case 2418: return launch_ws<2, 4, 1, 8>(a, st);

@@ -70,8 +70,10 @@ def test_get_ca_chip_quirks_q6_q7(gpu, oracle):
     assert scale > 0.5 * np.abs(x[:n]).sum()  # it really locked onto PRN 6's code
 
 
-@pytest.mark.parametrize("code_phase", [0.0, 0.25, 0.49999997, 0.5, 0.50000006, 1.0, 511.99997, 1022.0, 1022.4999, 1022.5, 1022.9999])
-@pytest.mark.parametrize("code_rate,n", [(1.023e6, 2048), (1.0235e6, 2047), (1.0e3, 2048)])
+# 0.31249997 with the 128 kchip/s crawl (1/16 chip per sample) puts sample 3 on 0.5 - 2^-25, the one chip argument whose
+# early replica the half-chip table of the FAST kernel does not give (the code warp corrects it)
+@pytest.mark.parametrize("code_phase", [0.0, 0.25, 0.31249997, 0.49999997, 0.5, 0.50000006, 1.0, 511.99997, 1022.0, 1022.4999, 1022.5, 1022.9999])
+@pytest.mark.parametrize("code_rate,n", [(1.023e6, 2048), (1.0235e6, 2047), (1.0e3, 2048), (128000.0, 2048)])
 def test_early_prompt_late_chip_selection_is_exact(gpu, oracle, code_phase, code_rate, n):
     """FAST mode reads ONE {chip k-1, chip k, chip k+1} entry per sample and picks the early / late replicas with two
     compares; the picks must be the reference's floor(chip +- 0.5) ones (get_ca_chip, do_tracking.rs:255-263, incl. the
@@ -106,6 +108,31 @@ def test_early_prompt_late_chip_selection_is_exact(gpu, oracle, code_phase, code
         assert ran[0] == 1
         assert (_six(out[0]) == ref).all(), (mode, _six(out[0]), ref)
         assert ch[0].code_phase == och.code_phase and ch[0].num_samples_per_code == och.num_samples_per_code
+
+
+@pytest.mark.parametrize("code_phase,code_rate", [(0.49999997, 1.023e6), (0.31249997, 128000.0), (0.25, 128000.0)])
+def test_half_chip_tie_is_corrected_on_real_samples(gpu, oracle, code_phase, code_rate):
+    """The FAST ring-fed kernel reads early / prompt / late from a table indexed by floor(2 * chip argument); the
+    reference's early chip differs from it for the single f32 argument 0.5 - 2^-25 (tc + 0.5 ties up to 1.0).  The code
+    warp finds that sample and adds x * carrier * (chip 1 - chip 0) to the early sums: with random samples and a 1 kHz
+    carrier one missed sample would move the early sums by ~2 |x| = 4e-2 |P|, far outside the 1e-4 |P| open-loop bound.
+    PRN 2's first two chips differ (row 1: +1, -1 ...), so the correction is not zero."""
+    from gnss_sdr_rs_b200 import ring, sdr_mock, tracking
+    fs, n = 2.048e6, 2048
+    rng = np.random.default_rng(77)
+    x = (rng.standard_normal(2 * n) + 1j * rng.standard_normal(2 * n)).astype(np.complex64)
+    rb = ring.MulticastRingBuffer(gpu, 1 << 13)
+    rb.write_samples(x)
+    row = next(r for r in range(32) if sdr_mock.ca_code(r + 1)[0] != sdr_mock.ca_code(r + 1)[1])
+    ch, och = _pair(oracle, fs, row + 1, 1000.0, np.float32(0.3), 0, code_row=row)
+    ch[0].code_rate = och.code_rate = np.float32(code_rate)
+    ch[0].code_phase = och.code_phase = np.float32(code_phase)
+    ch[0].num_samples_per_code = och.num_samples_per_code = n
+    ref, _, _ = oracle.trk_do_work(och, x[:n])
+    out, ran, _ = tracking.TrackingEngine(gpu).epoch(ch, mode=0)
+    assert ran[0] == 1
+    scale = float(np.hypot(ref[0], ref[1])) + float(np.hypot(ref[2], ref[3]))
+    assert np.abs(_six(out[0]) - ref).max() <= 2e-4 * scale, (_six(out[0]), ref)
 
 
 def test_do_work_epochs_closed_loop_ordered(gpu, oracle):
