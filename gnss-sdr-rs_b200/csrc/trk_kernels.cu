@@ -13,7 +13,11 @@
 
 namespace gb {
 
-template <int MODE, int TRK_T> __global__ void __launch_bounds__(TRK_T) trk_kernel(const TrkArgs a)
+// WIDE (ORDERED only): the six product sequences of an epoch are stored as six float arrays instead of rotated samples +
+// int8 chips, so that the ordered sums are one 16-byte load per four additions (24 instead of 11 bytes per sample).
+__host__ __device__ inline int trk_wide_stride(int n_max) { return ((n_max + 31) / 32) * 32 + 4; }   // = 4 mod 32: six lanes, six bank groups
+
+template <int MODE, int TRK_T, bool WIDE = false> __global__ void __launch_bounds__(TRK_T) trk_kernel(const TrkArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* row = reinterpret_cast<float*>(smem_raw);          // 1024 floats: this channel's C/A row
@@ -25,6 +29,8 @@ template <int MODE, int TRK_T> __global__ void __launch_bounds__(TRK_T) trk_kern
     float4* row4 = reinterpret_cast<float4*>(red + 128);
     float2* rot = reinterpret_cast<float2*>(red + 128);       // ORDERED: n_max rotated samples
     int8_t* chips = reinterpret_cast<int8_t*>(rot + (MODE == GB_TRK_ORDERED ? a.n_max : 0));  // 3 x n_max
+    float* prod = reinterpret_cast<float*>(red + 128);        // ORDERED + WIDE: 6 x trk_wide_stride(n_max) products
+    const int wstride = trk_wide_stride(a.n_max);
 
     const int c = blockIdx.x;
     if (threadIdx.x == 0) st = a.ch[c];
@@ -272,16 +278,40 @@ template <int MODE, int TRK_T> __global__ void __launch_bounds__(TRK_T) trk_kern
                 const float re = x.x * cs - x.y * sin_p;   // Complex32 multiply (:237)
                 const float im = x.x * sin_p + x.y * cs;
                 const float chip_idx = mod1023(code_phase + ((float)i * code_step));  // :251
-                rot[i] = make_float2(re, im);
-                chips[i] = (int8_t)ca_chip(row, chip_idx);
-                chips[a.n_max + i] = (int8_t)ca_chip(row, chip_idx + 0.5f);
-                chips[2 * a.n_max + i] = (int8_t)ca_chip(row, chip_idx - 0.5f);
+                if (WIDE) {
+                    // the six terms of :256-262, each an exact product with +-1
+                    const float pc = ca_chip(row, chip_idx), ec = ca_chip(row, chip_idx + 0.5f), lc = ca_chip(row, chip_idx - 0.5f);
+                    prod[i] = re * pc; prod[wstride + i] = im * pc;
+                    prod[2 * wstride + i] = re * ec; prod[3 * wstride + i] = im * ec;
+                    prod[4 * wstride + i] = re * lc; prod[5 * wstride + i] = im * lc;
+                } else {
+                    rot[i] = make_float2(re, im);
+                    chips[i] = (int8_t)ca_chip(row, chip_idx);
+                    chips[a.n_max + i] = (int8_t)ca_chip(row, chip_idx + 0.5f);
+                    chips[2 * a.n_max + i] = (int8_t)ca_chip(row, chip_idx - 0.5f);
+                }
             }
         }
         if (MODE == GB_TRK_ORDERED) {
             __syncthreads();
             // six sums in sample order, one thread each (do_tracking.rs:256-262)
-            if (threadIdx.x < 6) {
+            if (WIDE && threadIdx.x < 6) {
+                // one dependent chain of additions per sum; a single warp issues an instruction every ~3.5 cycles, so
+                // the chain is fed with one 16-byte load per four additions and nothing else
+                const float* v = prod + threadIdx.x * wstride;
+                float acc = 0.f;
+                int i = 0;
+#pragma unroll 4
+                for (; i + 4 <= n; i += 4) {
+                    const float4 q = *reinterpret_cast<const float4*>(v + i);
+                    acc = acc + q.x;
+                    acc = acc + q.y;
+                    acc = acc + q.z;
+                    acc = acc + q.w;
+                }
+                for (; i < n; i++) acc = acc + v[i];
+                red[threadIdx.x] = acc;
+            } else if (threadIdx.x < 6) {
                 const int comp = threadIdx.x & 1, which = threadIdx.x >> 1;
                 const float* xs = reinterpret_cast<const float*>(rot) + comp;
                 const int8_t* ch = chips + which * a.n_max;
@@ -415,11 +445,18 @@ template <int MODE, int TRK_T> __global__ void __launch_bounds__(TRK_T) trk_kern
 }
 
 size_t trk_ordered_smem_bytes(int n_max) { return (1024 + 128) * sizeof(float) + (size_t)n_max * (sizeof(float2) + 3) + 16; }
+static size_t trk_ordered_wide_bytes(int n_max) { return (1024 + 128) * sizeof(float) + 6 * (size_t)trk_wide_stride(n_max) * sizeof(float) + 16; }
 
 template <int T> static cudaError_t launch_t(const TrkArgs& a, int mode, cudaStream_t st)
 {
     size_t smem = (1024 + 128) * sizeof(float) + (mode == GB_TRK_ORDERED ? 0 : 1024 * sizeof(float4));
-    if (mode == GB_TRK_ORDERED) {
+    // the wide layout while four channels still fit an SM (n_max up to ~2300 samples: the 2.048 Msps configs)
+    if (mode == GB_TRK_ORDERED && trk_ordered_wide_bytes(a.n_max) <= 56 * 1024 && tuning("trk_narrow", 0) == 0) {
+        smem = trk_ordered_wide_bytes(a.n_max);
+        cudaError_t e = cudaFuncSetAttribute(trk_kernel<GB_TRK_ORDERED, T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        trk_kernel<GB_TRK_ORDERED, T, true><<<a.n_channels, T, smem, st>>>(a);
+    } else if (mode == GB_TRK_ORDERED) {
         smem = trk_ordered_smem_bytes(a.n_max);
         if (smem > 48 * 1024) {
             cudaError_t e = cudaFuncSetAttribute(trk_kernel<GB_TRK_ORDERED, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -450,6 +487,11 @@ cudaError_t trk_launch(const TrkArgs& a0, int mode, cudaStream_t st)
     case 256: return launch_t<256>(a, mode, st);
     case 512: return launch_t<512>(a, mode, st);
     default: break;
+    }
+    if (mode == GB_TRK_ORDERED) {
+        // the parallel part of an ORDERED epoch is the f64 sin/cos per sample: one channel per SM takes 512 threads for
+        // it, more channels 256 (measured: 128 ch 10.3 us / epoch, 1024 ch 28.1 us; tools/time_trk_ordered.py)
+        return a.n_channels <= 148 ? launch_t<512>(a, mode, st) : launch_t<256>(a, mode, st);
     }
     if (a.n_channels > 300) return launch_t<128>(a, mode, st);
     return launch_t<256>(a, mode, st);
