@@ -219,6 +219,15 @@ template <class T> int ensure(gb_handle* h, T** p, size_t* cap, size_t need)
     return GB_OK;
 }
 
+// Set-up copies from pageable host memory.  cudaMemcpy returns once the bytes are staged, not necessarily once the DMA has
+// landed, and it runs on the legacy default stream, which the handle's non-blocking streams do not wait for: finish it.
+static cudaError_t h2d_blocking(void* dst, const void* src, size_t bytes)
+{
+    cudaError_t e = cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return e;
+    return cudaStreamSynchronize(cudaStreamLegacy);
+}
+
 // Rust `as usize` on f32 (saturating, NaN -> 0)
 size_t f32_as_usize(float v)
 {
@@ -307,14 +316,14 @@ int fft_resources(gb_handle* h, int plan, int n, FftRes** out)
                 fop[l] = (int)(ko % n);
             }
             CK(cudaMalloc((void**)&r.npos, sizeof(int) * n));
-            CK(cudaMemcpy(r.npos, npos.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
+            CK(h2d_blocking(r.npos, npos.data(), sizeof(int) * n));
         } else {
             for (int k = 0; k < n; k++) fop[scrambled_pos(k, n, radix, ns)] = k;
         }
         CK(cudaMalloc((void**)&r.tw, sizeof(float2) * tw.size()));
         CK(cudaMalloc((void**)&r.fop, sizeof(int) * n));
-        CK(cudaMemcpy(r.tw, tw.data(), sizeof(float2) * tw.size(), cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(r.fop, fop.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
+        CK(h2d_blocking(r.tw, tw.data(), sizeof(float2) * tw.size()));
+        CK(h2d_blocking(r.fop, fop.data(), sizeof(int) * n));
         r.fop_host = fop;
     }
     *out = &r;
@@ -549,7 +558,7 @@ extern "C" int gb_create(const gb_config* cfg, gb_handle** out)
         std::vector<int8_t> tab(32 * 1023);
         for (int p = 1; p <= 32; p++) ca_chips(p, tab.data() + (p - 1) * 1023);
         CK(cudaMalloc((void**)&h->ca_table_dev, tab.size()));
-        CK(cudaMemcpy(h->ca_table_dev, tab.data(), tab.size(), cudaMemcpyHostToDevice));
+        CK(h2d_blocking(h->ca_table_dev, tab.data(), tab.size()));
     }
     for (int s = 0; s < 2; s++) {
         CK(cudaMallocHost((void**)&h->pin_stage[s], kStageSamples * sizeof(float2)));
@@ -655,7 +664,10 @@ extern "C" int gb_ring_create(gb_handle* h, uint64_t cap)
     if (h->ring) cudaFree(h->ring);
     h->ring = nullptr;
     CK(cudaMalloc((void**)&h->ring, cap * sizeof(float2)));
-    CK(cudaMemset(h->ring, 0, cap * sizeof(float2)));
+    // on the copy stream: cudaMemset runs asynchronously on the legacy default stream, which the (non-blocking) copy
+    // stream does not wait for -- a late memset would wipe samples written right after the ring was created
+    CK(cudaMemsetAsync(h->ring, 0, cap * sizeof(float2), h->s_copy));
+    CK(cudaEventRecord(h->ev_copy, h->s_copy));
     h->ring_cap = cap;
     h->ring_head = 0;
     return GB_OK;
@@ -734,8 +746,8 @@ extern "C" int gb_frontend_configure(gb_handle* h, float f_if, float fs_in)
     }
     if (!h->fe_lut) CK(cudaMalloc((void**)&h->fe_lut, sizeof(float) * 4096));
     if (!h->fe_state) CK(cudaMalloc((void**)&h->fe_state, sizeof(float) * 17));
-    CK(cudaMemcpy(h->fe_lut, lut.data(), sizeof(float) * 4096, cudaMemcpyHostToDevice));
-    CK(cudaMemset(h->fe_state, 0, sizeof(float) * 17));
+    CK(h2d_blocking(h->fe_lut, lut.data(), sizeof(float) * 4096));
+    CK(cudaMemsetAsync(h->fe_state, 0, sizeof(float) * 17, h->s_copy));   // the stream the front-end kernels run on
     h->fe_step = (f_if / fs_in) * 2048.0f;  // nco_lut.rs:34
     // The phase accumulator does not depend on the samples: its orbit from 0 (tail + cycle, at most 2^24 states) is
     // computed here in the reference's f32 arithmetic and the kernel looks the LUT index up by sample number.
@@ -748,7 +760,7 @@ extern "C" int gb_frontend_configure(gb_handle* h, float f_if, float fs_in)
         std::vector<uint16_t> idx(h->fe_phase.size());
         for (size_t i = 0; i < idx.size(); i++) idx[i] = gb::fe_lut_index(h->fe_phase[i]);
         CK(cudaMalloc((void**)&h->fe_idx, idx.size() * sizeof(uint16_t)));
-        CK(cudaMemcpy(h->fe_idx, idx.data(), idx.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+        CK(h2d_blocking(h->fe_idx, idx.data(), idx.size() * sizeof(uint16_t)));
         h->fe_table = true;
     } else {
         h->fe_phase.clear();
@@ -913,7 +925,7 @@ extern "C" int gb_acq_configure(gb_handle* h, int fft_size, float fs, int n_prn,
         if (h->otw) cudaFree(h->otw);
         h->otw = nullptr;
         CK(cudaMalloc((void**)&h->otw, otw.size() * sizeof(float2)));
-        CK(cudaMemcpy(h->otw, otw.data(), otw.size() * sizeof(float2), cudaMemcpyHostToDevice));
+        CK(h2d_blocking(h->otw, otw.data(), otw.size() * sizeof(float2)));
     }
     if (h->code_fft) cudaFree(h->code_fft);
     if (h->codes_dev) cudaFree(h->codes_dev);
@@ -1135,7 +1147,7 @@ extern "C" int gb_acq_set_doppler_tables(gb_handle* h, const gb_c32* tables, con
     CK(cudaStreamSynchronize(h->s_acq));
     int rc = ensure(h, &h->tables, &h->tables_cap, (size_t)D * h->N);
     if (rc) return rc;
-    CK(cudaMemcpy(h->tables, tables, (size_t)D * h->N * sizeof(float2), cudaMemcpyHostToDevice));
+    CK(h2d_blocking(h->tables, tables, (size_t)D * h->N * sizeof(float2)));
     h->carr.assign(carr, carr + D);
     h->D = D;
     h->alias_ok = false;   // caller-supplied tables are used as given
@@ -1148,6 +1160,7 @@ extern "C" int gb_acq_get_doppler_tables(gb_handle* h, gb_c32* tables_out, float
     std::lock_guard<std::recursive_mutex> lk(h->mu_acq);
     if (h->plan < 0 || h->D == 0) return GB_ESTATE;
     CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->s_acq));   // the tables may still be being built (doppler_table_kernel)
     if (tables_out) CK(cudaMemcpy(tables_out, h->tables, (size_t)h->D * h->N * sizeof(float2), cudaMemcpyDeviceToHost));
     if (carr_out) memcpy(carr_out, h->carr.data(), sizeof(float) * h->D);
     return GB_OK;
