@@ -191,3 +191,30 @@ def test_digital_frontend_parallel_mode_within_tolerance(gpu, oracle, ffi, f_if,
     assert rb.copy_to_slice(start, 4096).tobytes() == oracle.frontend_process(of, raw[:4096]).tobytes()
     with pytest.raises(ffi.GnssB200Error):
         gpu.call("gb_frontend_set_mode", 7)
+
+
+def test_fresh_ring_survives_a_busy_default_stream(gpu):
+    """Regression: gb_ring_create used to clear the ring with cudaMemset, which runs asynchronously on the legacy default
+    stream; the handle's copy stream is non-blocking and does not wait for it, so with the default stream busy (here: a
+    few large torch matmuls, torch's current stream IS the legacy default stream) the memset landed after the first
+    write_samples and wiped them.  The same holds for the front-end state cleared by gb_frontend_configure."""
+    import torch
+    from gnss_sdr_rs_b200 import ring
+    rng = np.random.default_rng(5)
+    x = (rng.standard_normal(1 << 16) + 1j * rng.standard_normal(1 << 16)).astype(np.complex64)
+    a = torch.randn(8192, 8192, device="cuda")
+    torch.cuda.synchronize()
+    for _ in range(3):
+        b = a
+        for _ in range(4):
+            b = b @ a                                   # ~40 ms of queued work on the default stream
+        rb = ring.MulticastRingBuffer(gpu, 1 << 22)     # 32 MB to clear
+        rb.write_samples(x)
+        fe = ring.DigitalFrontend(gpu, 0.0, 2.048e6)
+        fe.process_block_into_ring(x[:4096])
+        st = fe.state()
+        got = rb.copy_to_slice(0, x.size)
+        assert got.tobytes() == x.tobytes()
+        assert np.abs(st["bias_re"]).max() > 0.0        # the state the kernel left, not a late memset's zeros
+        del b
+    torch.cuda.synchronize()
