@@ -36,6 +36,12 @@ struct AcqArgs {
     const int2* inv_map;     // inverse launch: per bin {spectrum slot, index of the shifted code-spectrum set} (nullptr: {dl, 0})
     int n_prn;               // rows per code-spectrum set
     int plain_inverse;       // shared-forward chain: 1 = acq_inverse_kernel even where a leftover-warp form exists (A/B)
+    // tensor-pipe A/B of the N = 4092 inverse kernel (gb_tuning_set("acq_tc", 1), acq_lw.cu): scratch for the spectra / code
+    // spectra in fragment order (nullptr = off), forward slots in a.spec when aliased (0: the slab's n_d), code-spectrum
+    // sets behind a.code_fft, 1 = code_tc already holds them
+    float2* spec_tc;
+    float2* code_tc;
+    int tc_n_fwd, tc_n_code_sets, tc_code_fresh;
 };
 
 struct FftArgs {
@@ -63,6 +69,7 @@ cudaError_t acq_launch_search(int plan, const AcqArgs& a, cudaStream_t st);
 cudaError_t acq_launch_shared(int plan, const AcqArgs& a, int n_d, cudaStream_t st);
 // N = 4092 shared chain: inverse kernel with a leftover warp (acq_lw.cu); the forward spectra must be in a.spec
 cudaError_t acq_launch_inverse_lw4092(const AcqArgs& a, int n_d, cudaStream_t st);
+int acq_tc_spec_len();   // complex elements of one spectrum in the fragment order of the tensor-pipe A/B
 cudaError_t acq_launch_row(int plan, const AcqArgs& a, cudaStream_t st);
 cudaError_t acq_launch_code_fft(int plan, const int8_t* codes, int n_prn, float2* code_fft, const float2* tw,
                                 const int* npos, cudaStream_t st);

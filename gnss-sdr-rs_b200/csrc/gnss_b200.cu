@@ -101,6 +101,12 @@ struct gb_handle {
     int spec_len = 0;   // complex elements of one stored spectrum (rows padded to 128 B, Plan::SPEC_LEN; == N for cluster plans)
     float2* spec = nullptr;
     size_t spec_cap = 0;
+    // tensor-pipe A/B (gb_tuning_set("acq_tc", 1)): spectra / code spectra in fragment order; code_gen counts rebuilds of
+    // code_fft / code_fft_shift, code_tc_gen / code_tc_src say what code_tc holds
+    float2 *spec_tc = nullptr, *code_tc = nullptr;
+    size_t spec_tc_cap = 0, code_tc_cap = 0;
+    uint64_t code_gen = 1, code_tc_gen = 0;
+    const float2* code_tc_src = nullptr;
     // cluster plans (code period > one CTA's shared memory)
     bool cluster = false;
     float2* otw = nullptr;
@@ -582,7 +588,7 @@ extern "C" int gb_destroy(gb_handle* h)
     if (!h) return GB_EINVAL;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
-    void* dev_ptrs[] = {h->fwd_bins_dev, h->inv_map_dev, h->code_fft_shift, h->fe_idx, h->fe_lut, h->fe_state, h->fe_stage, h->fe_scratch, h->otw, h->acc_rows, h->spec, h->ring, h->i8_stage, /* h->tw aliases fft[plan].tw, freed below */ h->code_fft, h->tables, h->rot, h->chunk, h->codes_dev, h->cells_dev,
+    void* dev_ptrs[] = {h->fwd_bins_dev, h->inv_map_dev, h->code_fft_shift, h->fe_idx, h->fe_lut, h->fe_state, h->fe_stage, h->fe_scratch, h->otw, h->acc_rows, h->spec, h->spec_tc, h->code_tc, h->ring, h->i8_stage, /* h->tw aliases fft[plan].tw, freed below */ h->code_fft, h->tables, h->rot, h->chunk, h->codes_dev, h->cells_dev,
                         h->rows_dev, h->row_dev, h->ca_table_dev, h->ch_dev, h->corr_dev, h->ran_dev, h->lost_dev,
                         h->hist_dev, h->trk_data, h->offs_dev, h->fine_x, h->fine_y, h->fine_codes, h->fine_u64, h->fine_mean,
                         h->fine_mag, h->tables_perm, h->iq_perm};
@@ -934,6 +940,7 @@ extern "C" int gb_acq_configure(gb_handle* h, int fft_size, float fs, int n_prn,
     const size_t total = (size_t)n_prn * fft_size;
     const int spec_len = (cluster || generic) ? fft_size : gb::acq_plan_spec_len(plan);
     CK(cudaMalloc((void**)&h->code_fft, (size_t)n_prn * spec_len * sizeof(float2)));
+    h->code_gen++;
     CK(cudaMemsetAsync(h->code_fft, 0, (size_t)n_prn * spec_len * sizeof(float2), h->s_acq));   // row padding
     CK(cudaMalloc((void**)&h->codes_dev, total));
     CK(cudaMalloc((void**)&h->row_dev, sizeof(float) * fft_size));
@@ -1078,6 +1085,7 @@ static int build_alias_map(gb_handle* h)
     int rc;
     int* gidx_dev = nullptr;
     if ((rc = ensure(h, &h->code_fft_shift, &h->code_fft_shift_cap, shifts.size() * set))) return rc;
+    h->code_gen++;
     if ((rc = ensure(h, &h->fwd_bins_dev, &h->fwd_bins_cap, bases.size()))) return rc;
     if ((rc = ensure(h, &h->inv_map_dev, &h->inv_map_cap, (size_t)D))) return rc;
     CK(cudaMalloc((void**)&gidx_dev, gidx.size() * sizeof(int)));
@@ -1252,6 +1260,7 @@ static int search_enqueue(gb_handle* h, const float2* iq_dev, uint64_t start, ui
         a.otw = h->otw; a.acc_rows = nullptr; a.npos = h->npos; a.g_lo = 0; a.g_cnt = K / h->n_coh;
         a.plain_inverse = h->mode == GB_ACQ_SHARED_PLAIN;
         a.fwd_bins = nullptr; a.inv_map = nullptr; a.n_prn = h->n_prn;
+        a.spec_tc = nullptr; a.code_tc = nullptr; a.tc_n_fwd = 0; a.tc_n_code_sets = 0; a.tc_code_fresh = 0;
         if (h->pfa) {
             int rc = ensure(h, &h->iq_perm, &h->iq_perm_cap, (size_t)K * h->N);
             if (rc) return rc;
@@ -1303,6 +1312,17 @@ static int search_enqueue(gb_handle* h, const float2* iq_dev, uint64_t start, ui
             a.spec = h->spec;
             const int n_groups = K / h->n_coh;
             a.g_lo = 0; a.g_cnt = n_groups;
+            if (h->N == 4092 && !a.plain_inverse && gb::tuning("acq_tc", 0) && !gb::tuning("acq_nolw", 0)) {
+                const size_t tl = (size_t)gb::acq_tc_spec_len();
+                const int n_sets = (alias ? h->n_shift : 1) * h->n_prn;
+                rc = ensure(h, &h->spec_tc, &h->spec_tc_cap, (alias ? (size_t)n_fwd : slab) * n_groups * tl);
+                if (!rc) rc = ensure(h, &h->code_tc, &h->code_tc_cap, (size_t)n_sets * tl);
+                if (rc) return rc;
+                a.spec_tc = h->spec_tc; a.code_tc = h->code_tc;
+                a.tc_n_fwd = alias ? n_fwd : 0; a.tc_n_code_sets = n_sets;
+                a.tc_code_fresh = h->code_tc_gen == h->code_gen && h->code_tc_src == a.code_fft;
+                h->code_tc_gen = h->code_gen; h->code_tc_src = a.code_fft;
+            }
             CK(cudaEventRecord(h->ev_s0[slot], h->s_acq));
             if (host_iq && slab >= (size_t)h->D) {
                 // sliced upload overlapped with the forward path
@@ -1595,6 +1615,7 @@ extern "C" int gb_acq_bin_power(gb_handle* h, const gb_c32* iq, uint64_t n_sampl
     a.otw = h->otw; a.acc_rows = nullptr; a.npos = h->npos; a.g_lo = 0; a.g_cnt = K / h->n_coh;
     a.plain_inverse = h->mode == GB_ACQ_SHARED_PLAIN;
     a.fwd_bins = nullptr; a.inv_map = nullptr; a.n_prn = h->n_prn;
+    a.spec_tc = nullptr; a.code_tc = nullptr; a.tc_n_fwd = 0; a.tc_n_code_sets = 0; a.tc_code_fresh = 0;
     if (h->pfa) {
         rc = ensure(h, &h->iq_perm, &h->iq_perm_cap, (size_t)K * h->N);
         if (rc) return rc;

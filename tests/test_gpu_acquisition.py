@@ -79,6 +79,48 @@ def test_leftover_warp_kernel_is_bit_identical(gpu, ffi, K, n_coh):
     assert out[0]["peak"].min() > 0 and out[0]["peak2"].min() > 0
 
 
+@pytest.mark.parametrize("K,n_coh,alias", [(1, 1, False), (9, 1, False), (20, 1, True), (40, 2, True), (40, 2, False)])
+def test_tensor_stage_matches_fp32_kernel(gpu, oracle, ffi, K, n_coh, alias):
+    """A/B switch gb_tuning_set("acq_tc", 1): the radix-31 stage of the N = 4092 inverse kernel as 3 x TF32 products on the
+    warp-level tensor path (acq_lw.cu; not the default, outside the north star).  Against the FP32 leftover-warp kernel
+    on the same input: every peak, second peak and 8-lane sum within 2e-6 relative (stated bound of the split: 1e-6 of a
+    butterfly's largest input), arg-max identical on every cell with a clear peak, decisions identical; and against the
+    oracle within the 1e-3 contract.  The switch is per process, so it is always put back."""
+    from gnss_sdr_rs_b200 import sdr_mock
+    n, fs = 4092, 4.092e6
+    x = sdr_mock.baseband(fs, K, _sats(n, 5), seed=100 + K)
+    dopplers = np.arange(-1500, 1501, 250, dtype=np.float32)
+    eng = _engine(gpu, n, fs)
+    eng.make_doppler_tables(0.0, dopplers)
+    eng.set_doppler_aliasing(alias)
+    eng.set_detector(7.0, 4)
+    eng.set_coherent(n_coh)
+    ref = eng.search_cells(x, K).copy()
+    dec_ref = eng.search(x, K)
+    ffi.tuning_set("acq_tc", 1)
+    try:
+        got = eng.search_cells(x, K).copy()
+        got2 = eng.search_cells(x, K).copy()     # second search: the cached code spectra in fragment order
+        dec = eng.search(x, K)
+        sub = eng.search_cells(x, K, prn_mask=(1 << 4) | (1 << 30)).copy()   # sparse PRN mask
+    finally:
+        ffi.tuning_set("acq_tc", 0)
+    assert got.tobytes() == got2.tobytes()
+    for f in ("peak", "peak2", "sum8"):
+        err = np.abs(got[f].astype(np.float64) - ref[f]) / np.maximum(ref[f], 1e-30)
+        assert err.max() < 2e-6, (f, err.max())
+    clear = ref["peak"] > 1.5 * ref["peak2"]
+    assert clear.sum() >= 5 and (got["argmax"][clear] == ref["argmax"][clear]).all()
+    assert (got["argmax"] == ref["argmax"]).mean() > 0.99
+    key = lambda r: None if r is None else (r["prn"], r["code_phase_samples"], r["carrier_freq"])
+    assert [key(r) for r in dec] == [key(r) for r in dec_ref]
+    assert sub[4].tobytes() == got[4].tobytes() and sub[30].tobytes() == got[30].tobytes() and sub["peak"][0].max() == 0
+    carr, tabs = oracle.doppler_tables(0.0, dopplers, fs, n)
+    for prn in (1, 7, 32) if n_coh == 1 else ():
+        o = oracle.AcqWorker(prn, n, fs).cells(x, tabs, K)
+        assert np.allclose(o["peak"], got[prn - 1]["peak"], rtol=1e-3)
+
+
 @pytest.mark.parametrize("n", [1024, 2048, 4092, 4096, 8184, 16368, 20000])
 def test_doppler_aliasing_matches_per_bin_tables(gpu, oracle, ffi, n):
     """Bins a whole number of FFT bins apart share one forward spectrum (gb_acq_set_doppler_aliasing; off by default,
