@@ -377,6 +377,37 @@ def extra_numbers(hd, ffi):
                                      "cells_per_sec": 32 * 29 * 16368 / (min(ms) * 1e-3),
                                      "detected_prns": sorted(r["prn"] for r in res if r),
                                      "x_realtime_vs_10ms_dwell": 10.0 / min(ms)}
+    # config 2 with the REFERENCE's semantics: coherent = 1 ms, K = 200 non-coherent blocks, the reference's
+    # per-bin wipe-off tables (no Doppler aliasing): 200 inverse transforms per (PRN, bin) instead of 20, one forward
+    # path per bin and block.  Decisions of two PRNs (one present, one absent) against the oracle's search_satellite.
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pyoracle as orc
+    x2 = make_recording(0x6E56)
+    rb2 = ring.MulticastRingBuffer(hd, 1 << 20)
+    rb2.write_samples(x2)
+    eng = acquisition.AcquisitionEngine(hd, N_FFT, FS)
+    eng.make_doppler_tables(0.0, DOPPLERS)
+    eng.set_coherent(1)
+    ms = []
+    for _ in range(3):
+        res = eng.search_ring(0, K_MS)
+        ms.append(eng.last_kernel_ms())
+    lg = math.log2(N_FFT)
+    D = len(DOPPLERS)
+    flops = D * K_MS * N_FFT * (6 + 5 * lg) + N_PRN * D * K_MS * N_FFT * (6 + 5 * lg + 4)   # minimal == as run (no pre-sum)
+    carr, tabs = orc.doppler_tables(0.0, DOPPLERS, FS, N_FFT)
+    dec_equal = True
+    for prn in (SATS[0][0], 1):
+        r0 = orc.AcqWorker(prn, N_FFT, FS).search_satellite(x2, tabs, carr, 0, K_MS)
+        r1 = res[prn - 1]
+        dec_equal &= (r0 is None) == (r1 is None) and (r0 is None or (
+            r0["code_phase_samples"] == r1["code_phase_samples"] and r0["carrier_freq"] == r1["carrier_freq"]))
+    out["config2_reference_semantics_1ms_coherent"] = {
+        "fft_size": N_FFT, "n_doppler": D, "num_integrations": K_MS, "n_coherent": 1, "doppler_aliasing": "off",
+        "kernel_ms": min(ms), "cells_per_sec": N_PRN * D * N_FFT / (min(ms) * 1e-3),
+        "cell_integrations_per_sec": N_PRN * D * N_FFT * K_MS / (min(ms) * 1e-3), "x_realtime": K_MS / min(ms),
+        "flops": flops, "tflops": flops / (min(ms) * 1e-3) * 1e-12,
+        "detected_prns": sorted(r["prn"] for r in res if r), "decisions_equal_oracle_2_prns": bool(dec_equal)}
     # Galileo-E1-like 4 ms code at 20 Msps: cluster / DSMEM plan, 8 PRNs x 41 bins x 5 blocks (20 ms)
     n = 80000
     codes = np.stack([sdr_mock.resample_code(sdr_mock.e1_surrogate_code(p), 1.023e6, 20e6, n, boc11=True) for p in range(1, 9)])
