@@ -764,7 +764,7 @@ def run_ours(args, rank, world, local_rank):
                              "forward_spectra_per_group": n_fwd,
                              "kernel": ("acq_fused_kernel<PfaPlan<4092,160,4,12,11,31>>" if args.acq_mode == "fused" else
                                         "permute_blocks_kernel + acq_forward_kernel<PfaPlan<4092,160,4,12,11,31>> + "
-                                        "acq_inverse_lw_kernel<PfaPlan<4092,128,3,12,11,31>> (128 working threads + leftover warp; 3 CTAs/SM, 128 registers)"),
+                                        "acq_inverse_lwt_kernel<PfaPlan<4092,128,4,12,11,31>> (128 working threads + leftover warp; power accumulators in tensor memory via tcgen05.ld/st; 4 CTAs/SM, 96 registers)"),
                              "kernel_ms": kernel_ms_avg,
                              "kernel_shares_ncu": KERNEL_SHARES_NOTE,
                              "hbm_view": {"bound": "hbm", "algorithmic_bytes": abytes,

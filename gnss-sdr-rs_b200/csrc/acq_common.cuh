@@ -14,11 +14,20 @@ using P4092 = PfaPlan<4092, 160, 4, 0, 12, 11, 31>;
 using P4092W = PfaPlan<4092, 128, 4, 0, 12, 11, 31>;
 using P4092W3 = PfaPlan<4092, 128, 3, 0, 12, 11, 31>;   // the default: 3 CTAs per SM, 128 registers, no accumulator spills
 using P4092W2 = PfaPlan<4092, 128, 2, 0, 12, 11, 31>;
+using P4092W5 = PfaPlan<4092, 128, 5, 0, 12, 11, 31>;   // A/B: five CTAs per SM with the accumulators in tensor memory (80 registers)
 using P4096 = Plan<4096, 256, 2, 4, 16, 16, 16>;
 // 3 x 11 is one Good-Thomas radix-33 butterfly in registers (no internal twiddles): three shared-memory stages, not four
 using P8184 = PfaPlan<8184, 288, 1, 0, 8, 33, 31>;
 using P16368 = PfaPlan<16368, 544, 1, 0, 16, 33, 31>;
+#if defined(GB_P20000_ALT) && GB_P20000_ALT == 1     // A/B builds (tools/build_alt.sh): three shared-memory stages instead of four
+using P20000 = Plan<20000, 320, 1, 0, 32, 25, 25>;
+#elif defined(GB_P20000_ALT) && GB_P20000_ALT == 2
+using P20000 = Plan<20000, 400, 1, 0, 32, 25, 25>;
+#elif defined(GB_P20000_ALT) && GB_P20000_ALT == 3
+using P20000 = Plan<20000, 640, 1, 0, 32, 25, 25>;
+#else
 using P20000 = Plan<20000, 512, 1, 0, 8, 4, 25, 25>;
+#endif
 
 // tuning variants of the headline plan (GB_TUNING builds only; selected with gb_tuning_set("acq_variant", 1..))
 using P4092v1 = Plan<4092, 160, 4, 0, 12, 11, 31>;   // the Cooley-Tukey form of the default plan (A/B)

@@ -131,6 +131,155 @@ __global__ void __launch_bounds__(PW::T + 32, PW::MINB) acq_inverse_lw_kernel(co
     }
 }
 
+// ------------------------------------------------------------------ power accumulators in tensor memory
+// gb_tuning_set("acq_lw_tmem", 1).  The 36 power accumulators of a working thread are touched once per group (stage C) and
+// otherwise only occupy registers: with them the kernel needs 128 registers (3 CTAs per SM), without them it fits 96
+// (4 CTAs per SM, 16 working warps instead of 12).  Blackwell's tensor memory is a 256 KB per-SM accumulator store with
+// its own datapath (tcgen05.ld / tcgen05.st, SASS LDTM / STTM; no L1 data-pipe traffic, unlike a spill): each CTA
+// allocates 64 columns, thread (warp w, lane l) owns TMEM lane 32 w + l, columns 0 .. 35.  Stage C loads twelve
+// accumulators per radix-12 butterfly while the butterfly's inputs come from the line, adds |.|^2 in the same order as
+// final_stage_accumulate (results are bit-identical) and stores them back.
+__device__ __forceinline__ void tmem_ld4(float (&a)[12], int o, uint32_t taddr)
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(a[o]), "=f"(a[o + 1]), "=f"(a[o + 2]), "=f"(a[o + 3]) : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld8(float (&a)[12], int o, uint32_t taddr)
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(a[o]), "=f"(a[o + 1]), "=f"(a[o + 2]), "=f"(a[o + 3]), "=f"(a[o + 4]), "=f"(a[o + 5]), "=f"(a[o + 6]), "=f"(a[o + 7])
+                 : "r"(taddr));
+}
+// the loaded registers are operands of the wait so that no use of them can be scheduled ahead of it
+__device__ __forceinline__ void tmem_wait_ld12(float (&a)[12])
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+f"(a[0]), "+f"(a[1]), "+f"(a[2]), "+f"(a[3]), "+f"(a[4]), "+f"(a[5]), "+f"(a[6]), "+f"(a[7]), "+f"(a[8]), "+f"(a[9]),
+                   "+f"(a[10]), "+f"(a[11])
+                 :: "memory");
+}
+__device__ __forceinline__ void tmem_st12(uint32_t taddr, const float (&a)[12])
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 :: "r"(taddr), "f"(a[0]), "f"(a[1]), "f"(a[2]), "f"(a[3]), "f"(a[4]), "f"(a[5]), "f"(a[6]), "f"(a[7]) : "memory");
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
+                 :: "r"(taddr + 8), "f"(a[8]), "f"(a[9]), "f"(a[10]), "f"(a[11]) : "memory");
+}
+
+template <class P>
+__device__ __forceinline__ void final_stage_accumulate_tmem(const float2* __restrict__ line, uint32_t taddr)
+{
+    using G0 = StageGeo<P, 0>;
+    static_assert(P::PFA && G0::R == 12, "radix-12 last stage of the prime-factor plan");
+    const int warp0 = threadIdx.x & ~31;
+    // the previous group's stores (or the zero fill) must have landed before these loads: by now they long have
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int it = 0; it < G0::ITERS; it++) {
+        if (warp0 + it * P::T >= G0::NB) continue;   // the whole warp is past the last butterfly (warp-uniform)
+        const int i = threadIdx.x + it * P::T;
+        const bool active = G0::NB % P::T == 0 || i < G0::NB;
+        float a[12];
+        tmem_ld8(a, 0, taddr + it * 12);
+        tmem_ld4(a, 8, taddr + it * 12 + 8);
+        float2 v[G0::R];
+        if (active) {
+#pragma unroll
+            for (int q = 0; q < G0::R; q++) v[q] = line[P::phys(i + q * G0::SUB)];
+            Dft<G0::R, true>::run(v);
+        }
+        tmem_wait_ld12(a);
+        if (active) {
+#pragma unroll
+            for (int j = 0; j < G0::R; j++) a[j] = __fmaf_rn(v[j].x, v[j].x, __fmaf_rn(v[j].y, v[j].y, a[j]));
+        }
+        tmem_st12(taddr + it * 12, a);
+    }
+}
+
+template <class PW, bool CG>
+__global__ void __launch_bounds__(PW::T + 32, PW::MINB) acq_inverse_lwt_kernel(const AcqArgs a)
+{
+    extern __shared__ float2 smem_line[];
+    __shared__ uint32_t tmem_base_smem;
+    constexpr int LASTS = PW::NSTAGE - 1;
+    using G0 = StageGeo<PW, 0>;
+    using GM = StageGeo<PW, LASTS>;
+    constexpr int TW = PW::T, TALL = PW::T + 32;
+    constexpr uint32_t TMEM_COLS = 64;
+    static_assert(PW::PFA && LASTS == 2 && TW == 128 && G0::ITERS * G0::R <= 64, "N = 4092 plan, 36 accumulators per thread");
+    const int n_groups = a.K / a.n_coh;
+    const int dl = (int)(blockIdx.x / (unsigned)a.n_active);
+    const int row = a.rows[blockIdx.x % (unsigned)a.n_active];
+    const int2 sm = a.inv_map ? __ldg(&a.inv_map[a.d_lo + dl]) : make_int2(dl, 0);
+    const unsigned code_off = ((unsigned)sm.y * (unsigned)a.n_prn + (unsigned)row) * (unsigned)PW::SPEC_LEN;
+    const unsigned spec_off = (unsigned)sm.x * (unsigned)n_groups * (unsigned)PW::SPEC_LEN;
+    float2* __restrict__ line = smem_line;
+    const int warp = threadIdx.x >> 5;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     :: "r"((uint32_t)__cvta_generic_to_shared(&tmem_base_smem)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_smem;
+
+    if (threadIdx.x >= TW) {
+        lw_leftover_warp<PW, CG, false>(a.spec + spec_off, a.code_fft + code_off, line, n_groups);
+        return;
+    }
+    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);   // this warp's lane quarter, column 0
+    {   // tensor memory comes uninitialised: zero this thread's accumulators
+        float z[12];
+#pragma unroll
+        for (int j = 0; j < 12; j++) z[j] = 0.f;
+#pragma unroll
+        for (int it = 0; it < G0::ITERS; it++) tmem_st12(taddr + it * 12, z);
+    }
+    const int b = threadIdx.x;
+    for (int g = 0; g < n_groups; g++) {
+        const float2* __restrict__ sg = a.spec + (spec_off + (unsigned)g * (unsigned)PW::SPEC_LEN);
+        const float2* __restrict__ code = a.code_fft + code_off;
+        {
+            float2 v[GM::R];
+#pragma unroll
+            for (int q = 0; q < GM::R; q++) v[q] = cmul_conj(LDSPEC(&sg[q * PW::SPEC_STRIDE + b]), __ldg(&code[q * PW::SPEC_STRIDE + b]));
+            if (g > 0) named_bar_sync(BAR_END, TALL);
+            dft_emit<GM::R, true>(v, [&](int j, float2 y) { line[PW::phys(b * GM::R + j)] = y; });
+        }
+        named_bar_sync(BAR_A_DONE, TALL);
+        dit_stage_rows<PW, 1, true, TW / 32>(line);
+        named_bar_sync(BAR_MID, TW);
+        final_stage_accumulate_tmem<PW>(line, taddr);
+    }
+    named_bar_sync(BAR_END, TALL);   // the reduction reuses the line as scratch
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    float acc[G0::ITERS][G0::R];
+#pragma unroll
+    for (int it = 0; it < G0::ITERS; it++) {
+        tmem_ld8(acc[it], 0, taddr + it * 12);
+        tmem_ld4(acc[it], 8, taddr + it * 12 + 8);
+    }
+#pragma unroll
+    for (int it = 0; it < G0::ITERS; it++) tmem_wait_ld12(acc[it]);
+    reduce_row_to_cell<PW, BAR_MID>(acc, smem_line, a.spc, &a.cells[(size_t)row * a.D + a.d_lo + dl], a.npos);
+    if (warp == 0) {   // every working warp has passed reduce_row_to_cell's barriers after its last TMEM read
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+template <class PW, bool CG> static cudaError_t launch_lwt(const AcqArgs& a, int n_d, cudaStream_t st)
+{
+    const size_t smem = sizeof(float2) * (size_t)PW::LINE;
+    cudaError_t e = cudaFuncSetAttribute(acq_inverse_lwt_kernel<PW, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    acq_inverse_lwt_kernel<PW, CG><<<n_d * a.n_active, PW::T + 32, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
 template <class PW, bool CG, bool DB = false> static cudaError_t launch_lw(const AcqArgs& a, int n_d, cudaStream_t st)
 {
     const size_t smem = sizeof(float2) * (size_t)PW::LINE * (DB ? 2 : 1);
@@ -386,7 +535,13 @@ cudaError_t acq_launch_inverse_lw4092(const AcqArgs& a, int n_d, cudaStream_t st
         return acq_launch_inverse_tc4092(a, n_d, (a.tc_n_fwd ? a.tc_n_fwd : n_d) * n_groups, a.tc_n_code_sets, a.tc_code_fresh,
                                          a.spec_tc, a.code_tc, st);
     }
+    // The default: power accumulators in tensor memory, 96 registers, four CTAs per SM (config 2: 1.304 -> 1.259 ms).
+    // gb_tuning_set("acq_lw_tmem", 0) selects the register forms below for A/B (three CTAs per SM at 128 registers: the 36
+    // accumulators next to the 31 stage-A inputs; four CTAs at 96 registers spill them: 1.382 ms), 5 = five CTAs (spills).
+    const int tm = tuning("acq_lw_tmem", 1);
     const int minb = tuning("acq_lw_minb", 3);
+    if (tm == 5) return launch_lwt<P4092W5, true>(a, n_d, st);
+    if (tm) return launch_lwt<P4092W, true>(a, n_d, st);
     if (tuning("acq_lw_db", 0)) return launch_lw<P4092W3, true, true>(a, n_d, st);   // A/B: double-buffered line
     if (minb == 4) return launch_lw<PW, true>(a, n_d, st);
     if (minb == 2) return launch_lw<P4092W2, true>(a, n_d, st);

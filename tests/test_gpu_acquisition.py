@@ -79,6 +79,35 @@ def test_leftover_warp_kernel_is_bit_identical(gpu, ffi, K, n_coh):
     assert out[0]["peak"].min() > 0 and out[0]["peak2"].min() > 0
 
 
+@pytest.mark.parametrize("K,n_coh,alias", [(1, 1, False), (9, 1, False), (20, 1, True), (40, 2, True)])
+def test_tmem_accumulators_are_bit_identical(gpu, ffi, K, n_coh, alias):
+    """The default N = 4092 inverse kernel keeps the 36 power accumulators of a working thread in tensor memory
+    (tcgen05.alloc / ld / st: 64 columns per CTA) instead of registers, so it fits 96 registers and four CTAs per SM;
+    gb_tuning_set("acq_lw_tmem", 0) selects the register form.  Same arithmetic in the same order: every cell byte for
+    byte, also with a sparse PRN mask and over repeated searches (TMEM is allocated and freed by every CTA)."""
+    from gnss_sdr_rs_b200 import sdr_mock
+    n, fs = 4092, 4.092e6
+    x = sdr_mock.baseband(fs, K, _sats(n, 5), seed=200 + K)
+    eng = _engine(gpu, n, fs)
+    eng.make_doppler_tables(0.0, np.arange(-1500, 1501, 250, dtype=np.float32))
+    eng.set_doppler_aliasing(alias)
+    eng.set_detector(7.0, 4)
+    eng.set_coherent(n_coh)
+    ffi.tuning_set("acq_lw_tmem", 0)
+    try:
+        ref = eng.search_cells(x, K).copy()
+        ref_sub = eng.search_cells(x, K, prn_mask=(1 << 4) | (1 << 30)).copy()
+    finally:
+        ffi.tuning_set("acq_lw_tmem", 1)
+    assert ffi.lib().gb_tuning_get(b"acq_lw_tmem", 1) == 1
+    got = [eng.search_cells(x, K).copy() for _ in range(3)]
+    sub = eng.search_cells(x, K, prn_mask=(1 << 4) | (1 << 30)).copy()
+    for g in got:
+        assert g.tobytes() == ref.tobytes()
+    assert sub.tobytes() == ref_sub.tobytes()
+    assert ref["peak"].min() > 0
+
+
 @pytest.mark.parametrize("K,n_coh,alias", [(1, 1, False), (9, 1, False), (20, 1, True), (40, 2, True), (40, 2, False)])
 def test_tensor_stage_matches_fp32_kernel(gpu, oracle, ffi, K, n_coh, alias):
     """A/B switch gb_tuning_set("acq_tc", 1): the radix-31 stage of the N = 4092 inverse kernel as 3 x TF32 products on the

@@ -9,6 +9,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import gnss_sdr_rs_b200._ffi as ffi  # noqa: E402
+if os.environ.get("GB_LIB"):   # tool-side only: an A/B build of the library (tools/build_alt.sh)
+    ffi.LIB_PATH = os.path.abspath(os.environ["GB_LIB"])
 from gnss_sdr_rs_b200 import acquisition, ring  # noqa: E402
 
 
