@@ -44,8 +44,8 @@ SATS = [(3, 1230.0, 100, 45.0), (7, -2210.0, 2000, 40.0), (11, 3370.0, 3100, 42.
 
 
 # filled in from the ncu capture of the same command (profiles/round1_v9_final.txt)
-KERNEL_SHARES_NOTE = ("acq_inverse_lw_kernel 96.8% / acq_forward_kernel (20 of 201 bins, Doppler aliasing) 2.9% / permute 0.4% "
-                      "of the chain (profiles/round2_launches_acq_step.txt, round2_acq_lw.txt)")
+KERNEL_SHARES_NOTE = ("acq_inverse_lwt_kernel 96.4% / acq_forward_kernel (20 of 201 bins, Doppler aliasing) 3.3% / permute 0.4% "
+                      "of the chain (profiles/round2_acq_lwt_tmem.txt)")
 
 
 def make_recording(seed):
