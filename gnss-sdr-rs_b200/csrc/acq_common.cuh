@@ -223,4 +223,134 @@ __device__ __forceinline__ void final_stage_accumulate(const float2* __restrict_
     }
 }
 
+// ------------------------------------------------------------------ power accumulators in tensor memory
+// Tensor memory (256 KB per SM: 128 lanes x 512 columns x 32 bit) is an accumulator store with its own datapath
+// (tcgen05.ld / tcgen05.st, SASS LDTM / STTM): no register, no L1 data-pipe traffic.  A warp may touch the 32 lanes of its
+// quarter (warp id % 4) only, so thread (warp w, lane l) owns TMEM lane 32 (w % 4) + l; warps that share a quarter take
+// different column ranges.  The accumulate is the same two-FMA form in the same order as final_stage_accumulate.
+template <uint32_t COLS> __device__ __forceinline__ uint32_t tmem_alloc_cta(uint32_t* base_smem)
+{
+    static_assert(COLS >= 32 && COLS <= 512 && (COLS & (COLS - 1)) == 0, "power of two, 32 .. 512 columns");
+    if ((threadIdx.x >> 5) == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     :: "r"((uint32_t)__cvta_generic_to_shared(base_smem)), "r"(COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    return *base_smem;
+}
+// by the warp that allocated (warp 0), after every warp's last TMEM access
+template <uint32_t COLS> __device__ __forceinline__ void tmem_dealloc_warp(uint32_t base)
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(base), "r"(COLS) : "memory");
+}
+template <int R> __device__ __forceinline__ void tmem_ld(float (&a)[R], uint32_t taddr)
+{
+    static_assert(R == 4 || R == 8 || R == 12 || R == 16, "radix of the last inverse stage");
+    if constexpr (R == 16) {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                     : "=f"(a[0]), "=f"(a[1]), "=f"(a[2]), "=f"(a[3]), "=f"(a[4]), "=f"(a[5]), "=f"(a[6]), "=f"(a[7]), "=f"(a[8]), "=f"(a[9]),
+                       "=f"(a[10]), "=f"(a[11]), "=f"(a[12]), "=f"(a[13]), "=f"(a[14]), "=f"(a[15])
+                     : "r"(taddr));
+    } else {
+        if constexpr (R >= 8)
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                         : "=f"(a[0]), "=f"(a[1]), "=f"(a[2]), "=f"(a[3]), "=f"(a[4]), "=f"(a[5]), "=f"(a[6]), "=f"(a[7]) : "r"(taddr));
+        if constexpr (R != 8)
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(a[R - 4]), "=f"(a[R - 3]), "=f"(a[R - 2]), "=f"(a[R - 1]) : "r"(taddr + (R - 4)));
+    }
+}
+// the loaded registers are operands of the wait so that no use of them can be scheduled ahead of it
+template <int R> __device__ __forceinline__ void tmem_wait_ld(float (&a)[R])
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int j = 0; j < R; j++) asm volatile("" : "+f"(a[j]));
+}
+template <int R> __device__ __forceinline__ void tmem_st(uint32_t taddr, const float (&a)[R])
+{
+    static_assert(R == 4 || R == 8 || R == 12 || R == 16, "radix of the last inverse stage");
+    if constexpr (R == 16) {
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+                     :: "r"(taddr), "f"(a[0]), "f"(a[1]), "f"(a[2]), "f"(a[3]), "f"(a[4]), "f"(a[5]), "f"(a[6]), "f"(a[7]), "f"(a[8]), "f"(a[9]),
+                        "f"(a[10]), "f"(a[11]), "f"(a[12]), "f"(a[13]), "f"(a[14]), "f"(a[15])
+                     : "memory");
+    } else {
+        if constexpr (R >= 8)
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                         :: "r"(taddr), "f"(a[0]), "f"(a[1]), "f"(a[2]), "f"(a[3]), "f"(a[4]), "f"(a[5]), "f"(a[6]), "f"(a[7]) : "memory");
+        if constexpr (R != 8)
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
+                         :: "r"(taddr + (R - 4)), "f"(a[R - 4]), "f"(a[R - 3]), "f"(a[R - 2]), "f"(a[R - 1]) : "memory");
+    }
+}
+// TMEM columns one thread needs, and the CTA's allocation (warps that share a lane quarter stack their column ranges)
+template <class P> __host__ __device__ constexpr uint32_t tmem_cols_per_thread() { return StageGeo<P, 0>::ITERS * StageGeo<P, 0>::R; }
+template <class P, int T_ = P::T> __host__ __device__ constexpr uint32_t tmem_cols_cta()
+{
+    uint32_t need = ((T_ + 127) / 128) * tmem_cols_per_thread<P>(), c = 32;
+    while (c < need) c *= 2;
+    return c;
+}
+// this thread's first column: base + (lane quarter << 16) + column range of its warp
+template <class P> __device__ __forceinline__ uint32_t tmem_thread_addr(uint32_t base)
+{
+    const uint32_t w = threadIdx.x >> 5;
+    return base + (((w & 3u) * 32u) << 16) + (w >> 2) * tmem_cols_per_thread<P>();
+}
+template <class P> __device__ __forceinline__ void tmem_zero_accumulators(uint32_t taddr)
+{
+    using G0 = StageGeo<P, 0>;
+    float z[G0::R];
+#pragma unroll
+    for (int j = 0; j < G0::R; j++) z[j] = 0.f;
+#pragma unroll
+    for (int it = 0; it < G0::ITERS; it++) tmem_st<G0::R>(taddr + it * G0::R, z);
+}
+template <class P> __device__ __forceinline__ void tmem_load_accumulators(uint32_t taddr, float (&acc)[StageGeo<P, 0>::ITERS][StageGeo<P, 0>::R])
+{
+    using G0 = StageGeo<P, 0>;
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int it = 0; it < G0::ITERS; it++) tmem_ld<G0::R>(acc[it], taddr + it * G0::R);
+#pragma unroll
+    for (int it = 0; it < G0::ITERS; it++) tmem_wait_ld<G0::R>(acc[it]);
+}
+// final inverse stage fused with |.|^2 accumulate, accumulators in tensor memory (see final_stage_accumulate)
+template <class P>
+__device__ __forceinline__ void final_stage_accumulate_tmem(const float2* __restrict__ line, const float2* __restrict__ tw, uint32_t taddr)
+{
+    using G0 = StageGeo<P, 0>;
+    const int warp0 = threadIdx.x & ~31;
+    // the previous group's stores (or the zero fill) must have landed before these loads: by now they long have
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int it = 0; it < G0::ITERS; it++) {
+        if (warp0 + it * P::T >= G0::NB) continue;   // the whole warp is past the last butterfly (warp-uniform)
+        const int i = threadIdx.x + it * P::T;
+        const bool active = G0::NB % P::T == 0 || i < G0::NB;
+        float a[G0::R];
+        tmem_ld<G0::R>(a, taddr + it * G0::R);
+        float2 v[G0::R];
+        if (active) {
+            v[0] = line[P::phys(i)];
+#pragma unroll
+            for (int q = 1; q < G0::R; q++) {
+                const float2 u = line[P::phys(i + q * G0::SUB)];
+                v[q] = P::PFA ? u : cmul_conj(u, __ldg(&tw[(q - 1) * G0::SUB + i]));
+            }
+            Dft<G0::R, true>::run(v);
+        }
+        tmem_wait_ld<G0::R>(a);
+        if (active) {
+#pragma unroll
+            for (int j = 0; j < G0::R; j++) a[j] = __fmaf_rn(v[j].x, v[j].x, __fmaf_rn(v[j].y, v[j].y, a[j]));
+        }
+        tmem_st<G0::R>(taddr + it * G0::R, a);
+    }
+}
+
 }  // namespace gb

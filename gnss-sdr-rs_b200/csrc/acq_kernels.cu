@@ -184,9 +184,12 @@ template <class P> __global__ void __launch_bounds__(P::T, P::MINB) acq_forward_
 // ALIAS = true: Doppler aliasing (AcqArgs::inv_map): the spectrum slot and the shifted code-spectrum set of the bin are
 // looked up.  A separate instantiation because these kernels sit on the register cliff: the three extra lines tripled
 // the spills of the ALIAS = false form (config 1: 0.62 -> 0.74 ms), which therefore stays exactly as it was.
-template <class P, bool DB, bool ALIAS> __global__ void __launch_bounds__(P::T, P::MINB) acq_inverse_kernel(const AcqArgs a)
+// TM = true: the power accumulators live in tensor memory instead of registers (acq_common.cuh; A/B through
+// gb_tuning_set("acq_tmem", 1): identical cells, fewer registers / spills).
+template <class P, bool DB, bool ALIAS, bool TM = false> __global__ void __launch_bounds__(P::T, P::MINB) acq_inverse_kernel(const AcqArgs a)
 {
     extern __shared__ float2 smem_line[];
+    __shared__ uint32_t tmem_base_smem;
     constexpr int LASTS = P::NSTAGE - 1;
     using G0 = StageGeo<P, 0>;
     using GM = StageGeo<P, LASTS>;
@@ -209,10 +212,17 @@ template <class P, bool DB, bool ALIAS> __global__ void __launch_bounds__(P::T, 
     const float2* __restrict__ tw = a.tw;
 
     float acc[G0::ITERS][G0::R];
+    uint32_t tmem_base = 0, taddr = 0;
+    if constexpr (TM) {
+        tmem_base = tmem_alloc_cta<tmem_cols_cta<P>()>(&tmem_base_smem);
+        taddr = tmem_thread_addr<P>(tmem_base);
+        tmem_zero_accumulators<P>(taddr);
+    } else {
 #pragma unroll
-    for (int it = 0; it < G0::ITERS; it++)
+        for (int it = 0; it < G0::ITERS; it++)
 #pragma unroll
-        for (int j = 0; j < G0::R; j++) acc[it][j] = 0.f;
+            for (int j = 0; j < G0::R; j++) acc[it][j] = 0.f;
+    }
 
     for (int g = 0; g < n_groups; g++) {
         float2* __restrict__ line = DB ? smem_line + (g & 1) * P::LINE : smem_line;
@@ -237,11 +247,16 @@ template <class P, bool DB, bool ALIAS> __global__ void __launch_bounds__(P::T, 
         }
         __syncthreads();
         DitRange<P, LASTS - 1, 0, true>::run(line, tw);
-        final_stage_accumulate<P>(line, tw, acc);
+        if constexpr (TM) final_stage_accumulate_tmem<P>(line, tw, taddr);
+        else final_stage_accumulate<P>(line, tw, acc);
         if (!DB) __syncthreads();
     }
     if (DB) __syncthreads();  // reduce_row_to_cell reuses the line as scratch
+    if constexpr (TM) tmem_load_accumulators<P>(taddr, acc);
     reduce_row_to_cell<P>(acc, smem_line, a.spc, &a.cells[(size_t)row * a.D + a.d_lo + dl], a.npos);
+    if constexpr (TM) {
+        if ((threadIdx.x >> 5) == 0) tmem_dealloc_warp<tmem_cols_cta<P>()>(tmem_base);   // after reduce_row_to_cell's barriers
+    }
 }
 
 // ------------------------------------------------------------------ code spectra (AcquisitionWorker::new, :133-138)
@@ -533,6 +548,31 @@ template <class P> static cudaError_t launch_shared(const AcqArgs& a, int n_d, c
     }
     // double-buffered line when two lines fit the 227 KB of one SM at the plan's CTA count
     const bool no_db = tuning("acq_nodb", 0) != 0;   // A/B switch (tools/time_acq.py)
+    if constexpr (kProductionPlan<P>) {
+        // Accumulators in tensor memory: the default where the register form spills them -- the power-of-two plans (2 to 8
+        // CTAs per SM at 128 registers: N = 4096 0.177 -> 0.133 ms, 2048 0.087 -> 0.068, 1024 0.057 -> 0.046 for 32 PRNs x
+        // 41 bins x 10 blocks) -- and off for the one-CTA-per-SM plans, which do not spill them and have no second CTA to
+        // hide the TMEM round trip behind (16368: 0.613 -> 0.640 ms, 8184: 0.444 -> 0.461, 20000: 2.14 -> 2.21).
+        // gb_tuning_set("acq_tmem", 0 | 1) forces the form for A/B; cells are identical either way.
+        constexpr bool tm_default = (P::N & (P::N - 1)) == 0;
+        const int tm = tuning("acq_tmem", -1);
+        if ((tm < 0 ? tm_default : tm != 0) && tmem_cols_cta<P>() * P::MINB <= 512) {
+            const bool db = P::DB && !no_db;
+            const size_t sm = db ? 2 * smem : smem;
+            const dim3 grid(n_d * a.n_active);
+#define GB_LAUNCH_TM(DBV, ALV)                                                                          \
+    do {                                                                                                \
+        if ((e = set_smem(acq_inverse_kernel<P, DBV, ALV, true>, sm)) != cudaSuccess) return e;         \
+        acq_inverse_kernel<P, DBV, ALV, true><<<grid, P::T, sm, st>>>(a);                               \
+    } while (0)
+            if (db && a.inv_map) GB_LAUNCH_TM(true, true);
+            else if (db) GB_LAUNCH_TM(true, false);
+            else if (a.inv_map) GB_LAUNCH_TM(false, true);
+            else GB_LAUNCH_TM(false, false);
+#undef GB_LAUNCH_TM
+            return cudaGetLastError();
+        }
+    }
     if (a.inv_map) {
         // aliased form: the seven production plans only (the tuning variants never request it, acq_plan_supports_alias)
         if constexpr (kProductionPlan<P>) {

@@ -139,64 +139,6 @@ __global__ void __launch_bounds__(PW::T + 32, PW::MINB) acq_inverse_lw_kernel(co
 // allocates 64 columns, thread (warp w, lane l) owns TMEM lane 32 w + l, columns 0 .. 35.  Stage C loads twelve
 // accumulators per radix-12 butterfly while the butterfly's inputs come from the line, adds |.|^2 in the same order as
 // final_stage_accumulate (results are bit-identical) and stores them back.
-__device__ __forceinline__ void tmem_ld4(float (&a)[12], int o, uint32_t taddr)
-{
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
-                 : "=f"(a[o]), "=f"(a[o + 1]), "=f"(a[o + 2]), "=f"(a[o + 3]) : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld8(float (&a)[12], int o, uint32_t taddr)
-{
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=f"(a[o]), "=f"(a[o + 1]), "=f"(a[o + 2]), "=f"(a[o + 3]), "=f"(a[o + 4]), "=f"(a[o + 5]), "=f"(a[o + 6]), "=f"(a[o + 7])
-                 : "r"(taddr));
-}
-// the loaded registers are operands of the wait so that no use of them can be scheduled ahead of it
-__device__ __forceinline__ void tmem_wait_ld12(float (&a)[12])
-{
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+f"(a[0]), "+f"(a[1]), "+f"(a[2]), "+f"(a[3]), "+f"(a[4]), "+f"(a[5]), "+f"(a[6]), "+f"(a[7]), "+f"(a[8]), "+f"(a[9]),
-                   "+f"(a[10]), "+f"(a[11])
-                 :: "memory");
-}
-__device__ __forceinline__ void tmem_st12(uint32_t taddr, const float (&a)[12])
-{
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
-                 :: "r"(taddr), "f"(a[0]), "f"(a[1]), "f"(a[2]), "f"(a[3]), "f"(a[4]), "f"(a[5]), "f"(a[6]), "f"(a[7]) : "memory");
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
-                 :: "r"(taddr + 8), "f"(a[8]), "f"(a[9]), "f"(a[10]), "f"(a[11]) : "memory");
-}
-
-template <class P>
-__device__ __forceinline__ void final_stage_accumulate_tmem(const float2* __restrict__ line, uint32_t taddr)
-{
-    using G0 = StageGeo<P, 0>;
-    static_assert(P::PFA && G0::R == 12, "radix-12 last stage of the prime-factor plan");
-    const int warp0 = threadIdx.x & ~31;
-    // the previous group's stores (or the zero fill) must have landed before these loads: by now they long have
-    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int it = 0; it < G0::ITERS; it++) {
-        if (warp0 + it * P::T >= G0::NB) continue;   // the whole warp is past the last butterfly (warp-uniform)
-        const int i = threadIdx.x + it * P::T;
-        const bool active = G0::NB % P::T == 0 || i < G0::NB;
-        float a[12];
-        tmem_ld8(a, 0, taddr + it * 12);
-        tmem_ld4(a, 8, taddr + it * 12 + 8);
-        float2 v[G0::R];
-        if (active) {
-#pragma unroll
-            for (int q = 0; q < G0::R; q++) v[q] = line[P::phys(i + q * G0::SUB)];
-            Dft<G0::R, true>::run(v);
-        }
-        tmem_wait_ld12(a);
-        if (active) {
-#pragma unroll
-            for (int j = 0; j < G0::R; j++) a[j] = __fmaf_rn(v[j].x, v[j].x, __fmaf_rn(v[j].y, v[j].y, a[j]));
-        }
-        tmem_st12(taddr + it * 12, a);
-    }
-}
-
 template <class PW, bool CG>
 __global__ void __launch_bounds__(PW::T + 32, PW::MINB) acq_inverse_lwt_kernel(const AcqArgs a)
 {
@@ -217,28 +159,14 @@ __global__ void __launch_bounds__(PW::T + 32, PW::MINB) acq_inverse_lwt_kernel(c
     float2* __restrict__ line = smem_line;
     const int warp = threadIdx.x >> 5;
 
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                     :: "r"((uint32_t)__cvta_generic_to_shared(&tmem_base_smem)), "r"(TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_base = tmem_base_smem;
+    const uint32_t tmem_base = tmem_alloc_cta<TMEM_COLS>(&tmem_base_smem);
 
     if (threadIdx.x >= TW) {
         lw_leftover_warp<PW, CG, false>(a.spec + spec_off, a.code_fft + code_off, line, n_groups);
         return;
     }
     const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);   // this warp's lane quarter, column 0
-    {   // tensor memory comes uninitialised: zero this thread's accumulators
-        float z[12];
-#pragma unroll
-        for (int j = 0; j < 12; j++) z[j] = 0.f;
-#pragma unroll
-        for (int it = 0; it < G0::ITERS; it++) tmem_st12(taddr + it * 12, z);
-    }
+    tmem_zero_accumulators<PW>(taddr);   // tensor memory comes uninitialised
     const int b = threadIdx.x;
     for (int g = 0; g < n_groups; g++) {
         const float2* __restrict__ sg = a.spec + (spec_off + (unsigned)g * (unsigned)PW::SPEC_LEN);
@@ -253,22 +181,13 @@ __global__ void __launch_bounds__(PW::T + 32, PW::MINB) acq_inverse_lwt_kernel(c
         named_bar_sync(BAR_A_DONE, TALL);
         dit_stage_rows<PW, 1, true, TW / 32>(line);
         named_bar_sync(BAR_MID, TW);
-        final_stage_accumulate_tmem<PW>(line, taddr);
+        final_stage_accumulate_tmem<PW>(line, a.tw, taddr);
     }
     named_bar_sync(BAR_END, TALL);   // the reduction reuses the line as scratch
-    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     float acc[G0::ITERS][G0::R];
-#pragma unroll
-    for (int it = 0; it < G0::ITERS; it++) {
-        tmem_ld8(acc[it], 0, taddr + it * 12);
-        tmem_ld4(acc[it], 8, taddr + it * 12 + 8);
-    }
-#pragma unroll
-    for (int it = 0; it < G0::ITERS; it++) tmem_wait_ld12(acc[it]);
+    tmem_load_accumulators<PW>(taddr, acc);
     reduce_row_to_cell<PW, BAR_MID>(acc, smem_line, a.spc, &a.cells[(size_t)row * a.D + a.d_lo + dl], a.npos);
-    if (warp == 0) {   // every working warp has passed reduce_row_to_cell's barriers after its last TMEM read
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(TMEM_COLS) : "memory");
-    }
+    if (warp == 0) tmem_dealloc_warp<TMEM_COLS>(tmem_base);   // every working warp has passed reduce_row_to_cell's barriers after its last TMEM read
 }
 
 template <class PW, bool CG> static cudaError_t launch_lwt(const AcqArgs& a, int n_d, cudaStream_t st)

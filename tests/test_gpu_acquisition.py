@@ -108,6 +108,37 @@ def test_tmem_accumulators_are_bit_identical(gpu, ffi, K, n_coh, alias):
     assert ref["peak"].min() > 0
 
 
+@pytest.mark.parametrize("n", [1024, 2048, 4092, 4096, 8184, 16368, 20000])
+def test_generic_kernel_tmem_accumulators_are_bit_identical(gpu, ffi, n):
+    """gb_tuning_set("acq_tmem", 1): the generic inverse kernel of every plan with its power accumulators in tensor memory
+    (warps that share a TMEM lane quarter stack their column ranges; 32 ... 256 columns per CTA, up to 8 CTAs per SM; the
+    default for the power-of-two plans, whose register form spills them): cells byte for byte those of the register form
+    ("acq_tmem", 0), Doppler aliasing on and off, with and without coherent pre-sum."""
+    from gnss_sdr_rs_b200 import sdr_mock
+    fs = float(n) * 1000.0
+    K = 6
+    x = sdr_mock.baseband(fs, K, _sats(n, n + 3), seed=n + 9)
+    eng = _engine(gpu, n, fs)
+    eng.make_doppler_tables(0.0, np.arange(-1500, 1501, 250, dtype=np.float32))
+    eng.set_detector(7.0, 2)
+    eng.set_mode(ffi.GB_ACQ_SHARED_PLAIN)     # N = 4092: the generic kernel, not the leftover-warp form
+    for alias, n_coh in ((False, 1), (True, 1), (True, 2)):
+        eng.set_doppler_aliasing(alias)
+        eng.set_coherent(n_coh)
+        try:
+            ffi.tuning_set("acq_tmem", 0)
+            ref = eng.search_cells(x, K).copy()
+            ffi.tuning_set("acq_tmem", 1)
+            got = eng.search_cells(x, K).copy()
+            got2 = eng.search_cells(x, K, prn_mask=0x80000001).copy()
+        finally:
+            ffi.tuning_set("acq_tmem", -1)    # per-plan default: on for the power-of-two plans
+        assert got.tobytes() == ref.tobytes(), (alias, n_coh)
+        assert eng.search_cells(x, K).tobytes() == ref.tobytes()
+        assert got2[0].tobytes() == ref[0].tobytes() and got2[31].tobytes() == ref[31].tobytes()
+    assert ref["peak"].min() > 0
+
+
 @pytest.mark.parametrize("K,n_coh,alias", [(1, 1, False), (9, 1, False), (20, 1, True), (40, 2, True), (40, 2, False)])
 def test_tensor_stage_matches_fp32_kernel(gpu, oracle, ffi, K, n_coh, alias):
     """A/B switch gb_tuning_set("acq_tc", 1): the radix-31 stage of the N = 4092 inverse kernel as 3 x TF32 products on the
