@@ -139,7 +139,22 @@ __global__ void __launch_bounds__(PW::T + 32, PW::MINB) acq_inverse_lw_kernel(co
 // allocates 64 columns, thread (warp w, lane l) owns TMEM lane 32 w + l, columns 0 .. 35.  Stage C loads twelve
 // accumulators per radix-12 butterfly while the butterfly's inputs come from the line, adds |.|^2 in the same order as
 // final_stage_accumulate (results are bit-identical) and stores them back.
-template <class PW, bool CG>
+// CT = true (A/B, gb_tuning_set("acq_lw_tmem", 2)): the thread's 31 code-spectrum values -- the same for every group of the
+// search -- are kept in tensor memory as well (columns 64 .. 125 of a 128-column allocation: four CTAs fill the SM's 512
+// columns) and read back in chunks of four values per group instead of 31 loads through L1 / L2.
+__device__ __forceinline__ void tmem_ld8_nm(float (&a)[8], uint32_t taddr)
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(a[0]), "=f"(a[1]), "=f"(a[2]), "=f"(a[3]), "=f"(a[4]), "=f"(a[5]), "=f"(a[6]), "=f"(a[7]) : "r"(taddr));
+}
+// no "memory" clobber: the spectrum loads of the group may be scheduled across it
+__device__ __forceinline__ void tmem_wait_ld8_nm(float (&a)[8])
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+f"(a[0]), "+f"(a[1]), "+f"(a[2]), "+f"(a[3]), "+f"(a[4]), "+f"(a[5]), "+f"(a[6]), "+f"(a[7]));
+}
+
+template <class PW, bool CG, bool CT = false>
 __global__ void __launch_bounds__(PW::T + 32, PW::MINB) acq_inverse_lwt_kernel(const AcqArgs a)
 {
     extern __shared__ float2 smem_line[];
@@ -148,8 +163,9 @@ __global__ void __launch_bounds__(PW::T + 32, PW::MINB) acq_inverse_lwt_kernel(c
     using G0 = StageGeo<PW, 0>;
     using GM = StageGeo<PW, LASTS>;
     constexpr int TW = PW::T, TALL = PW::T + 32;
-    constexpr uint32_t TMEM_COLS = 64;
+    constexpr uint32_t TMEM_COLS = CT ? 128 : 64, CODE_COL = 64;
     static_assert(PW::PFA && LASTS == 2 && TW == 128 && G0::ITERS * G0::R <= 64, "N = 4092 plan, 36 accumulators per thread");
+    static_assert(!CT || (GM::R == 31 && PW::MINB * 128 <= 512), "31 code values per thread in 62 columns");
     const int n_groups = a.K / a.n_coh;
     const int dl = (int)(blockIdx.x / (unsigned)a.n_active);
     const int row = a.rows[blockIdx.x % (unsigned)a.n_active];
@@ -168,13 +184,46 @@ __global__ void __launch_bounds__(PW::T + 32, PW::MINB) acq_inverse_lwt_kernel(c
     const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);   // this warp's lane quarter, column 0
     tmem_zero_accumulators<PW>(taddr);   // tensor memory comes uninitialised
     const int b = threadIdx.x;
+    if constexpr (CT) {
+        const float2* __restrict__ code = a.code_fft + code_off;
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            float cv[8];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int q = 4 * c + u;
+                const float2 w = q < GM::R ? __ldg(&code[q * PW::SPEC_STRIDE + b]) : make_float2(0.f, 0.f);
+                cv[2 * u] = w.x;
+                cv[2 * u + 1] = w.y;
+            }
+            tmem_st<8>(taddr + CODE_COL + 8 * c, cv);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
     for (int g = 0; g < n_groups; g++) {
         const float2* __restrict__ sg = a.spec + (spec_off + (unsigned)g * (unsigned)PW::SPEC_LEN);
         const float2* __restrict__ code = a.code_fft + code_off;
         {
             float2 v[GM::R];
+            if constexpr (CT) {
+                float cv[2][8];
+                tmem_ld8_nm(cv[0], taddr + CODE_COL);
 #pragma unroll
-            for (int q = 0; q < GM::R; q++) v[q] = cmul_conj(LDSPEC(&sg[q * PW::SPEC_STRIDE + b]), __ldg(&code[q * PW::SPEC_STRIDE + b]));
+                for (int q = 0; q < GM::R; q++) v[q] = LDSPEC(&sg[q * PW::SPEC_STRIDE + b]);
+#pragma unroll
+                for (int c = 0; c < 8; c++) {
+                    tmem_wait_ld8_nm(cv[c & 1]);
+                    if (c < 7) tmem_ld8_nm(cv[(c + 1) & 1], taddr + CODE_COL + 8 * (c + 1));
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const int q = 4 * c + u;
+                        if (q < GM::R) v[q] = cmul_conj(v[q], make_float2(cv[c & 1][2 * u], cv[c & 1][2 * u + 1]));
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < GM::R; q++) v[q] = cmul_conj(LDSPEC(&sg[q * PW::SPEC_STRIDE + b]), __ldg(&code[q * PW::SPEC_STRIDE + b]));
+            }
             if (g > 0) named_bar_sync(BAR_END, TALL);
             dft_emit<GM::R, true>(v, [&](int j, float2 y) { line[PW::phys(b * GM::R + j)] = y; });
         }
@@ -190,12 +239,12 @@ __global__ void __launch_bounds__(PW::T + 32, PW::MINB) acq_inverse_lwt_kernel(c
     if (warp == 0) tmem_dealloc_warp<TMEM_COLS>(tmem_base);   // every working warp has passed reduce_row_to_cell's barriers after its last TMEM read
 }
 
-template <class PW, bool CG> static cudaError_t launch_lwt(const AcqArgs& a, int n_d, cudaStream_t st)
+template <class PW, bool CG, bool CT = false> static cudaError_t launch_lwt(const AcqArgs& a, int n_d, cudaStream_t st)
 {
     const size_t smem = sizeof(float2) * (size_t)PW::LINE;
-    cudaError_t e = cudaFuncSetAttribute(acq_inverse_lwt_kernel<PW, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(acq_inverse_lwt_kernel<PW, CG, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    acq_inverse_lwt_kernel<PW, CG><<<n_d * a.n_active, PW::T + 32, smem, st>>>(a);
+    acq_inverse_lwt_kernel<PW, CG, CT><<<n_d * a.n_active, PW::T + 32, smem, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -454,12 +503,15 @@ cudaError_t acq_launch_inverse_lw4092(const AcqArgs& a, int n_d, cudaStream_t st
         return acq_launch_inverse_tc4092(a, n_d, (a.tc_n_fwd ? a.tc_n_fwd : n_d) * n_groups, a.tc_n_code_sets, a.tc_code_fresh,
                                          a.spec_tc, a.code_tc, st);
     }
-    // The default: power accumulators in tensor memory, 96 registers, four CTAs per SM (config 2: 1.304 -> 1.259 ms).
-    // gb_tuning_set("acq_lw_tmem", 0) selects the register forms below for A/B (three CTAs per SM at 128 registers: the 36
-    // accumulators next to the 31 stage-A inputs; four CTAs at 96 registers spill them: 1.382 ms), 5 = five CTAs (spills).
-    const int tm = tuning("acq_lw_tmem", 1);
+    // The default (2): power accumulators AND the thread's 31 code-spectrum values in tensor memory, 96 registers, four CTAs
+    // per SM (config 2: 1.304 -> 1.228 ms with the accumulators there, -> 1.193 ms with the code spectrum as well).
+    // gb_tuning_set("acq_lw_tmem", 1) = accumulators only, 0 = the register forms below (three CTAs per SM at 128 registers:
+    // the 36 accumulators next to the 31 stage-A inputs; four CTAs at 96 registers spill them: 1.382 ms), 5 = five CTAs
+    // (spills: 1.68 ms).  Cells are identical in every form.
+    const int tm = tuning("acq_lw_tmem", 2);
     const int minb = tuning("acq_lw_minb", 3);
     if (tm == 5) return launch_lwt<P4092W5, true>(a, n_d, st);
+    if (tm == 2) return launch_lwt<P4092W, true, true>(a, n_d, st);
     if (tm) return launch_lwt<P4092W, true>(a, n_d, st);
     if (tuning("acq_lw_db", 0)) return launch_lw<P4092W3, true, true>(a, n_d, st);   // A/B: double-buffered line
     if (minb == 4) return launch_lw<PW, true>(a, n_d, st);

@@ -61,8 +61,8 @@ int gb_device_count(void);
 /* Explicit A/B and tuning switches of the kernels (process-wide, default = the shipped organisation).  The library
  * reads NO environment variables.  Keys: "trk_ws" (-1 = generic tracking kernel everywhere, 0 = default, else
  * NSW*100+U*10+ROT), "trk_t" (CTA size of the generic tracking kernel), "acq_variant", "acq_nolw", "acq_nodb",
- * "acq_spec_ldg", "acq_lw_tmem" (default 1: the power accumulators of the N = 4092 inverse kernel live in tensor memory;
- * 0 = the register forms selected by "acq_lw_minb" / "acq_lw_db"; cells are identical), "acq_tmem" (the same for the generic
+ * "acq_spec_ldg", "acq_lw_tmem" (default 2: the power accumulators and the per-thread code spectrum of the N = 4092 inverse kernel
+ * live in tensor memory; 1 = the accumulators alone; 0 = the register forms selected by "acq_lw_minb" / "acq_lw_db"; cells are identical), "acq_tmem" (the same for the generic
  * inverse kernel of the other plans: -1 = per-plan default, on for the power-of-two plans; 0 / 1 force it), "fe_sequential", and "acq_tc"
  * (1 = the radix-31 stage of the N = 4092 inverse
  * kernel as 3 x TF32 products on the warp-level tensor path: a measured A/B, slower than the FP32 default and outside

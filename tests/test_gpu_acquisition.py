@@ -81,9 +81,10 @@ def test_leftover_warp_kernel_is_bit_identical(gpu, ffi, K, n_coh):
 
 @pytest.mark.parametrize("K,n_coh,alias", [(1, 1, False), (9, 1, False), (20, 1, True), (40, 2, True)])
 def test_tmem_accumulators_are_bit_identical(gpu, ffi, K, n_coh, alias):
-    """The default N = 4092 inverse kernel keeps the 36 power accumulators of a working thread in tensor memory
-    (tcgen05.alloc / ld / st: 64 columns per CTA) instead of registers, so it fits 96 registers and four CTAs per SM;
-    gb_tuning_set("acq_lw_tmem", 0) selects the register form.  Same arithmetic in the same order: every cell byte for
+    """The default N = 4092 inverse kernel keeps the 36 power accumulators of a working thread -- and its 31 code-spectrum
+    values, the same for every group -- in tensor memory (tcgen05.alloc / ld / st: 128 columns per CTA) instead of
+    registers / L1, so it fits 96 registers and four CTAs per SM; gb_tuning_set("acq_lw_tmem", 0) selects the register
+    form, 1 the accumulators alone.  Same arithmetic in the same order: every cell byte for
     byte, also with a sparse PRN mask and over repeated searches (TMEM is allocated and freed by every CTA)."""
     from gnss_sdr_rs_b200 import sdr_mock
     n, fs = 4092, 4.092e6
@@ -98,9 +99,14 @@ def test_tmem_accumulators_are_bit_identical(gpu, ffi, K, n_coh, alias):
         ref = eng.search_cells(x, K).copy()
         ref_sub = eng.search_cells(x, K, prn_mask=(1 << 4) | (1 << 30)).copy()
     finally:
-        ffi.tuning_set("acq_lw_tmem", 1)
-    assert ffi.lib().gb_tuning_get(b"acq_lw_tmem", 1) == 1
-    got = [eng.search_cells(x, K).copy() for _ in range(3)]
+        ffi.tuning_set("acq_lw_tmem", 2)
+    assert ffi.lib().gb_tuning_get(b"acq_lw_tmem", 2) == 2
+    got = [eng.search_cells(x, K).copy() for _ in range(3)]      # the default: accumulators + code spectrum in tensor memory
+    ffi.tuning_set("acq_lw_tmem", 1)        # accumulators only
+    try:
+        got.append(eng.search_cells(x, K).copy())
+    finally:
+        ffi.tuning_set("acq_lw_tmem", 2)
     sub = eng.search_cells(x, K, prn_mask=(1 << 4) | (1 << 30)).copy()
     for g in got:
         assert g.tobytes() == ref.tobytes()
