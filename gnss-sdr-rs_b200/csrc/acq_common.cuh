@@ -287,19 +287,39 @@ template <int R> __device__ __forceinline__ void tmem_st(uint32_t taddr, const f
                          :: "r"(taddr + (R - 4)), "f"(a[R - 4]), "f"(a[R - 3]), "f"(a[R - 2]), "f"(a[R - 1]) : "memory");
     }
 }
-// TMEM columns one thread needs, and the CTA's allocation (warps that share a lane quarter stack their column ranges)
-template <class P> __host__ __device__ constexpr uint32_t tmem_cols_per_thread() { return StageGeo<P, 0>::ITERS * StageGeo<P, 0>::R; }
-template <class P, int T_ = P::T> __host__ __device__ constexpr uint32_t tmem_cols_cta()
+__device__ __forceinline__ void tmem_ld8_nm(float (&a)[8], uint32_t taddr)
 {
-    uint32_t need = ((T_ + 127) / 128) * tmem_cols_per_thread<P>(), c = 32;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(a[0]), "=f"(a[1]), "=f"(a[2]), "=f"(a[3]), "=f"(a[4]), "=f"(a[5]), "=f"(a[6]), "=f"(a[7]) : "r"(taddr));
+}
+// no "memory" clobber: the spectrum loads of the group may be scheduled across it
+__device__ __forceinline__ void tmem_wait_ld8_nm(float (&a)[8])
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+f"(a[0]), "+f"(a[1]), "+f"(a[2]), "+f"(a[3]), "+f"(a[4]), "+f"(a[5]), "+f"(a[6]), "+f"(a[7]));
+}
+
+// TMEM columns one thread needs, and the CTA's allocation (warps that share a lane quarter stack their column ranges)
+// MODE bit 0: the power accumulators (ITERS0 x R0 columns), bit 1: the thread's code-spectrum values of the first inverse
+// stage (per iteration ceil(RM / 4) chunks of four complex values = eight columns), stacked in that order
+template <class P> __host__ __device__ constexpr uint32_t tmem_acc_cols() { return StageGeo<P, 0>::ITERS * StageGeo<P, 0>::R; }
+template <class P> __host__ __device__ constexpr uint32_t tmem_code_chunks() { return (StageGeo<P, P::NSTAGE - 1>::R + 3) / 4; }
+template <class P> __host__ __device__ constexpr uint32_t tmem_code_cols() { return StageGeo<P, P::NSTAGE - 1>::ITERS * tmem_code_chunks<P>() * 8; }
+template <class P, int MODE = 1> __host__ __device__ constexpr uint32_t tmem_cols_per_thread()
+{
+    return ((MODE & 1) ? tmem_acc_cols<P>() : 0) + ((MODE & 2) ? tmem_code_cols<P>() : 0);
+}
+template <class P, int MODE = 1, int T_ = P::T> __host__ __device__ constexpr uint32_t tmem_cols_cta()
+{
+    uint32_t need = ((T_ + 127) / 128) * tmem_cols_per_thread<P, MODE>(), c = 32;
     while (c < need) c *= 2;
     return c;
 }
 // this thread's first column: base + (lane quarter << 16) + column range of its warp
-template <class P> __device__ __forceinline__ uint32_t tmem_thread_addr(uint32_t base)
+template <class P, int MODE = 1> __device__ __forceinline__ uint32_t tmem_thread_addr(uint32_t base)
 {
     const uint32_t w = threadIdx.x >> 5;
-    return base + (((w & 3u) * 32u) << 16) + (w >> 2) * tmem_cols_per_thread<P>();
+    return base + (((w & 3u) * 32u) << 16) + (w >> 2) * tmem_cols_per_thread<P, MODE>();
 }
 template <class P> __device__ __forceinline__ void tmem_zero_accumulators(uint32_t taddr)
 {

@@ -184,10 +184,12 @@ template <class P> __global__ void __launch_bounds__(P::T, P::MINB) acq_forward_
 // ALIAS = true: Doppler aliasing (AcqArgs::inv_map): the spectrum slot and the shifted code-spectrum set of the bin are
 // looked up.  A separate instantiation because these kernels sit on the register cliff: the three extra lines tripled
 // the spills of the ALIAS = false form (config 1: 0.62 -> 0.74 ms), which therefore stays exactly as it was.
-// TM = true: the power accumulators live in tensor memory instead of registers (acq_common.cuh; A/B through
-// gb_tuning_set("acq_tmem", 1): identical cells, fewer registers / spills).
-template <class P, bool DB, bool ALIAS, bool TM = false> __global__ void __launch_bounds__(P::T, P::MINB) acq_inverse_kernel(const AcqArgs a)
+// TMODE bit 0: the power accumulators live in tensor memory instead of registers; bit 1: so do the thread's code-spectrum
+// values of the first inverse stage, which are the same for every group (acq_common.cuh; gb_tuning_set("acq_tmem", 0..3):
+// identical cells in every mode).
+template <class P, bool DB, bool ALIAS, int TMODE = 0> __global__ void __launch_bounds__(P::T, P::MINB) acq_inverse_kernel(const AcqArgs a)
 {
+    constexpr bool TM = (TMODE & 1) != 0, CT = (TMODE & 2) != 0;
     extern __shared__ float2 smem_line[];
     __shared__ uint32_t tmem_base_smem;
     constexpr int LASTS = P::NSTAGE - 1;
@@ -212,10 +214,37 @@ template <class P, bool DB, bool ALIAS, bool TM = false> __global__ void __launc
     const float2* __restrict__ tw = a.tw;
 
     float acc[G0::ITERS][G0::R];
-    uint32_t tmem_base = 0, taddr = 0;
+    uint32_t tmem_base = 0, taddr = 0, tcode = 0;
+    if constexpr (TMODE != 0) {
+        tmem_base = tmem_alloc_cta<tmem_cols_cta<P, TMODE>()>(&tmem_base_smem);
+        taddr = tmem_thread_addr<P, TMODE>(tmem_base);
+        tcode = taddr + (TM ? tmem_acc_cols<P>() : 0);
+    }
+    if constexpr (CT) {
+        // park this thread's code-spectrum values: iteration it, chunk c holds values 4 c .. 4 c + 3 (zeros past the end)
+        const float2* __restrict__ code = a.code_fft + code_off;
+        const int warp0 = threadIdx.x & ~31;
+#pragma unroll 1
+        for (int it = 0; it < GM::ITERS; it++) {
+            if (warp0 + it * P::T >= GM::NB) continue;
+            const int b = threadIdx.x + it * P::T;
+            const bool active = GM::NB % P::T == 0 || b < GM::NB;
+#pragma unroll
+            for (int c = 0; c < (int)tmem_code_chunks<P>(); c++) {
+                float cv[8];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int q = 4 * c + u;
+                    const float2 w = (q < GM::R && active) ? __ldg(&code[q * P::SPEC_STRIDE + b]) : make_float2(0.f, 0.f);
+                    cv[2 * u] = w.x;
+                    cv[2 * u + 1] = w.y;
+                }
+                tmem_st<8>(tcode + (it * tmem_code_chunks<P>() + c) * 8, cv);
+            }
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
     if constexpr (TM) {
-        tmem_base = tmem_alloc_cta<tmem_cols_cta<P>()>(&tmem_base_smem);
-        taddr = tmem_thread_addr<P>(tmem_base);
         tmem_zero_accumulators<P>(taddr);
     } else {
 #pragma unroll
@@ -237,11 +266,40 @@ template <class P, bool DB, bool ALIAS, bool TM = false> __global__ void __launc
                     dft_odd_prime_stream<GM::R, true, P::STREAM_A>(
                         [&](int q) { return cmul_conj(__ldg(&sg[q * P::SPEC_STRIDE + b]), __ldg(&code[q * P::SPEC_STRIDE + b])); },
                         [&](int j, float2 y) { line[P::phys(b * GM::R + j)] = y; });
-                } else {
+                } else if constexpr (!CT) {
                     float2 v[GM::R];
 #pragma unroll
                     for (int q = 0; q < GM::R; q++) v[q] = cmul_conj(__ldg(&sg[q * P::SPEC_STRIDE + b]), __ldg(&code[q * P::SPEC_STRIDE + b]));
                     dft_emit<GM::R, true>(v, [&](int j, float2 y) { line[P::phys(b * GM::R + j)] = y; });
+                }
+            }
+            if constexpr (CT) {
+                // code values from tensor memory in double-buffered chunks; the tcgen05 operations are warp-wide, so they
+                // sit outside the per-thread guard (a warp entirely past the last butterfly skips the iteration)
+                if ((int)(threadIdx.x & ~31) + it * P::T < GM::NB) {
+                    const bool active = GM::NB % P::T == 0 || b < GM::NB;
+                    constexpr int NCH = (int)tmem_code_chunks<P>();
+                    const uint32_t tc = tcode + it * NCH * 8;
+                    float cv[2][8];
+                    tmem_ld8_nm(cv[0], tc);
+                    float2 v[GM::R];
+                    if (active) {
+#pragma unroll
+                        for (int q = 0; q < GM::R; q++) v[q] = __ldg(&sg[q * P::SPEC_STRIDE + b]);
+                    }
+#pragma unroll
+                    for (int c = 0; c < NCH; c++) {
+                        tmem_wait_ld8_nm(cv[c & 1]);
+                        if (c + 1 < NCH) tmem_ld8_nm(cv[(c + 1) & 1], tc + 8 * (c + 1));
+                        if (active) {
+#pragma unroll
+                            for (int u = 0; u < 4; u++) {
+                                const int q = 4 * c + u;
+                                if (q < GM::R) v[q] = cmul_conj(v[q], make_float2(cv[c & 1][2 * u], cv[c & 1][2 * u + 1]));
+                            }
+                        }
+                    }
+                    if (active) dft_emit<GM::R, true>(v, [&](int j, float2 y) { line[P::phys(b * GM::R + j)] = y; });
                 }
             }
         }
@@ -254,8 +312,8 @@ template <class P, bool DB, bool ALIAS, bool TM = false> __global__ void __launc
     if (DB) __syncthreads();  // reduce_row_to_cell reuses the line as scratch
     if constexpr (TM) tmem_load_accumulators<P>(taddr, acc);
     reduce_row_to_cell<P>(acc, smem_line, a.spc, &a.cells[(size_t)row * a.D + a.d_lo + dl], a.npos);
-    if constexpr (TM) {
-        if ((threadIdx.x >> 5) == 0) tmem_dealloc_warp<tmem_cols_cta<P>()>(tmem_base);   // after reduce_row_to_cell's barriers
+    if constexpr (TMODE != 0) {
+        if ((threadIdx.x >> 5) == 0) tmem_dealloc_warp<tmem_cols_cta<P, TMODE>()>(tmem_base);   // after reduce_row_to_cell's barriers
     }
 }
 
@@ -533,6 +591,33 @@ template <class P> static cudaError_t launch_forward(const AcqArgs& a, int n_d, 
     acq_forward_kernel<P><<<n_d * a.g_cnt, P::T, smem, st>>>(a);
     return cudaGetLastError();
 }
+// the generic inverse kernel with tensor-memory mode MODE (acq_inverse_kernel's TMODE), if MINB allocations fit the SM's 512 columns
+template <class P, int MODE> constexpr bool tmem_mode_fits()
+{
+    return ((P::T + 127) / 128) * tmem_cols_per_thread<P, MODE>() <= 512 && tmem_cols_cta<P, MODE>() * P::MINB <= 512 &&
+           ((MODE & 2) == 0 || P::STREAM_A == 0);
+}
+template <class P, int MODE>
+static cudaError_t launch_inverse_tm(const AcqArgs& a, dim3 grid, size_t sm, bool db, cudaStream_t st, bool* launched)
+{
+    *launched = false;
+    if constexpr (kProductionPlan<P> && tmem_mode_fits<P, MODE>()) {
+        cudaError_t e;
+#define GB_LAUNCH_TM(DBV, ALV)                                                                           \
+    do {                                                                                                 \
+        if ((e = set_smem(acq_inverse_kernel<P, DBV, ALV, MODE>, sm)) != cudaSuccess) return e;          \
+        acq_inverse_kernel<P, DBV, ALV, MODE><<<grid, P::T, sm, st>>>(a);                                \
+    } while (0)
+        *launched = true;
+        if (db && a.inv_map) GB_LAUNCH_TM(true, true);
+        else if (db) GB_LAUNCH_TM(true, false);
+        else if (a.inv_map) GB_LAUNCH_TM(false, true);
+        else GB_LAUNCH_TM(false, false);
+#undef GB_LAUNCH_TM
+        return cudaGetLastError();
+    }
+    return cudaSuccess;
+}
 template <class P> static cudaError_t launch_shared(const AcqArgs& a, int n_d, cudaStream_t st)
 {
     const size_t smem = plan_smem<P>();
@@ -549,29 +634,27 @@ template <class P> static cudaError_t launch_shared(const AcqArgs& a, int n_d, c
     // double-buffered line when two lines fit the 227 KB of one SM at the plan's CTA count
     const bool no_db = tuning("acq_nodb", 0) != 0;   // A/B switch (tools/time_acq.py)
     if constexpr (kProductionPlan<P>) {
-        // Accumulators in tensor memory: the default where the register form spills them -- the power-of-two plans (2 to 8
-        // CTAs per SM at 128 registers: N = 4096 0.177 -> 0.133 ms, 2048 0.087 -> 0.068, 1024 0.057 -> 0.046 for 32 PRNs x
-        // 41 bins x 10 blocks) -- and off for the one-CTA-per-SM plans, which do not spill them and have no second CTA to
-        // hide the TMEM round trip behind (16368: 0.613 -> 0.640 ms, 8184: 0.444 -> 0.461, 20000: 2.14 -> 2.21).
-        // gb_tuning_set("acq_tmem", 0 | 1) forces the form for A/B; cells are identical either way.
-        constexpr bool tm_default = (P::N & (P::N - 1)) == 0;
-        const int tm = tuning("acq_tmem", -1);
-        if ((tm < 0 ? tm_default : tm != 0) && tmem_cols_cta<P>() * P::MINB <= 512) {
-            const bool db = P::DB && !no_db;
-            const size_t sm = db ? 2 * smem : smem;
-            const dim3 grid(n_d * a.n_active);
-#define GB_LAUNCH_TM(DBV, ALV)                                                                          \
-    do {                                                                                                \
-        if ((e = set_smem(acq_inverse_kernel<P, DBV, ALV, true>, sm)) != cudaSuccess) return e;         \
-        acq_inverse_kernel<P, DBV, ALV, true><<<grid, P::T, sm, st>>>(a);                               \
-    } while (0)
-            if (db && a.inv_map) GB_LAUNCH_TM(true, true);
-            else if (db) GB_LAUNCH_TM(true, false);
-            else if (a.inv_map) GB_LAUNCH_TM(false, true);
-            else GB_LAUNCH_TM(false, false);
-#undef GB_LAUNCH_TM
-            return cudaGetLastError();
-        }
+        // Tensor memory (acq_inverse_kernel's TMODE; 32 PRNs x 41 bins x 10 blocks, cells identical in every mode):
+        //   accumulators (1): the default where the register form spills them -- the power-of-two plans, 2 to 8 CTAs per SM
+        //     at 128 registers: N = 4096 0.177 -> 0.133 ms, 2048 0.087 -> 0.068, 1024 0.057 -> 0.045 -- and a loss for the
+        //     one-CTA-per-SM plans, which do not spill them and have no second CTA to hide the TMEM round trip behind
+        //     (16368: 0.613 -> 0.637 ms, 8184: 0.448 -> 0.462, 20000: 2.14 -> 2.21);
+        //   code spectrum (2): the default for N = 20000 (128 registers, 25-point first stage: 2.142 -> 2.028 ms for 20 blocks);
+        //     the 31-point first stage of 16368 at its 96-register cap spills the extra chunk buffers (0.613 -> 0.84 ms),
+        //     8184 and the power-of-two plans are indifferent;
+        //   both (3): never better than the better of the two.
+        // gb_tuning_set("acq_tmem", 0 .. 3) forces a mode for A/B (a mode that does not fit the 512 columns runs mode 0).
+        constexpr int tm_default = (P::N & (P::N - 1)) == 0 ? 1 : (P::N == 20000 ? 2 : 0);
+        const int tmq = tuning("acq_tmem", -1);
+        const int tm = tmq < 0 ? tm_default : (tmq & 3);
+        const bool db = P::DB && !no_db;
+        const size_t sm = db ? 2 * smem : smem;
+        const dim3 grid(n_d * a.n_active);
+        bool launched = false;
+        if (tm == 1) e = launch_inverse_tm<P, 1>(a, grid, sm, db, st, &launched);
+        else if (tm == 2) e = launch_inverse_tm<P, 2>(a, grid, sm, db, st, &launched);
+        else if (tm == 3) e = launch_inverse_tm<P, 3>(a, grid, sm, db, st, &launched);
+        if (launched) return e;
     }
     if (a.inv_map) {
         // aliased form: the seven production plans only (the tuning variants never request it, acq_plan_supports_alias)

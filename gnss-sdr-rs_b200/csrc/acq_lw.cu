@@ -142,18 +142,6 @@ __global__ void __launch_bounds__(PW::T + 32, PW::MINB) acq_inverse_lw_kernel(co
 // CT = true (A/B, gb_tuning_set("acq_lw_tmem", 2)): the thread's 31 code-spectrum values -- the same for every group of the
 // search -- are kept in tensor memory as well (columns 64 .. 125 of a 128-column allocation: four CTAs fill the SM's 512
 // columns) and read back in chunks of four values per group instead of 31 loads through L1 / L2.
-__device__ __forceinline__ void tmem_ld8_nm(float (&a)[8], uint32_t taddr)
-{
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=f"(a[0]), "=f"(a[1]), "=f"(a[2]), "=f"(a[3]), "=f"(a[4]), "=f"(a[5]), "=f"(a[6]), "=f"(a[7]) : "r"(taddr));
-}
-// no "memory" clobber: the spectrum loads of the group may be scheduled across it
-__device__ __forceinline__ void tmem_wait_ld8_nm(float (&a)[8])
-{
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+f"(a[0]), "+f"(a[1]), "+f"(a[2]), "+f"(a[3]), "+f"(a[4]), "+f"(a[5]), "+f"(a[6]), "+f"(a[7]));
-}
-
 template <class PW, bool CG, bool CT = false>
 __global__ void __launch_bounds__(PW::T + 32, PW::MINB) acq_inverse_lwt_kernel(const AcqArgs a)
 {

@@ -134,8 +134,10 @@ def test_generic_kernel_tmem_accumulators_are_bit_identical(gpu, ffi, n):
         try:
             ffi.tuning_set("acq_tmem", 0)
             ref = eng.search_cells(x, K).copy()
-            ffi.tuning_set("acq_tmem", 1)
-            got = eng.search_cells(x, K).copy()
+            for tmode in (2, 3, 1):     # code spectrum | both | accumulators in tensor memory (a mode that does not fit runs the default)
+                ffi.tuning_set("acq_tmem", tmode)
+                got = eng.search_cells(x, K).copy()
+                assert got.tobytes() == ref.tobytes(), (alias, n_coh, tmode)
             got2 = eng.search_cells(x, K, prn_mask=0x80000001).copy()
         finally:
             ffi.tuning_set("acq_tmem", -1)    # per-plan default: on for the power-of-two plans
