@@ -31,16 +31,33 @@ template <bool INV> __device__ __forceinline__ float2 rot4(float2 a, int k)
 }
 
 // outer forward stage for sub-block r: V_r[i] = (sum_j x[i + j*NI] W_4^(j r)) * W_N^(i r)
-template <class PI, class Load>
+// UNR butterflies per thread are in flight together (their kRO loads each are issued before the first use): with one CTA
+// per SM nothing else hides the L2 latency of this streaming loop -- it was 35 % of the kernel's time at one butterfly
+// per trip (round 2 profile: long-scoreboard stalls 52 % of the warp samples).
+template <class PI, int UNR = 4, class Load>
 __device__ __forceinline__ void outer_forward(int r, const float2* __restrict__ otw, float2* __restrict__ line, Load load)
 {
     constexpr int NI = PI::N;
-    for (int i = threadIdx.x; i < NI; i += PI::T) {
-        float2 v = load(i);
+    // every trip is full: an index past the end (the last butterflies of the last trip) is clamped for the loads and its
+    // store skipped, so no array element is conditionally defined (which would send the arrays to local memory)
+    for (int i0 = threadIdx.x; i0 < NI; i0 += UNR * PI::T) {
+        float2 x[UNR][kRO], t[UNR];
 #pragma unroll
-        for (int j = 1; j < kRO; j++) v = cadd(v, rot4<false>(load(i + j * NI), j * r));
-        if (r > 0) v = cmul(v, __ldg(&otw[(r - 1) * NI + i]));
-        line[PI::phys(i)] = v;
+        for (int u = 0; u < UNR; u++) {
+            const int i = min(i0 + u * PI::T, NI - 1);
+#pragma unroll
+            for (int j = 0; j < kRO; j++) x[u][j] = load(i + j * NI);
+            if (r > 0) t[u] = __ldg(&otw[(r - 1) * NI + i]);
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; u++) {
+            const int i = i0 + u * PI::T;
+            float2 v = x[u][0];
+#pragma unroll
+            for (int j = 1; j < kRO; j++) v = cadd(v, rot4<false>(x[u][j], j * r));
+            if (r > 0) v = cmul(v, t[u]);
+            if (i < NI) line[PI::phys(i)] = v;
+        }
     }
 }
 
@@ -70,11 +87,22 @@ __device__ __forceinline__ void inner_chain(float2* __restrict__ line, const flo
     DitRange<PI, LASTS - 1, -1, true>::run(line, tw);
 }
 
+// The accumulated power of the NI outputs a CTA owns lives in TENSOR MEMORY while the periods run (thread t keeps outputs
+// t + m T, m = 0 .. ACC_COLS - 1, in ACC_COLS columns of its TMEM lane; warps that share a lane quarter stack their column
+// ranges: 4 x 40 = 160 -> 256 columns) and goes to the global row once, after the last period: the per-period
+// read-modify-write of the row through L2 (and its latency in the middle of the last stage) is gone.
 template <class PI> __global__ void __cluster_dims__(kRO, 1, 1) __launch_bounds__(PI::T, 1) acq_cluster_kernel(const AcqArgs a)
 {
     extern __shared__ float2 line[];
+    __shared__ uint32_t tmem_base_smem;
     constexpr int NI = PI::N;
     constexpr int N = NI * kRO;
+    constexpr int UNR = 8;                                                   // outputs per thread and trip of the last stage
+    constexpr int TRIPS = (NI + UNR * PI::T - 1) / (UNR * PI::T);
+    constexpr int ACC_COLS = TRIPS * UNR;
+    constexpr uint32_t TMEM_COLS = ((PI::T + 127) / 128) * ACC_COLS <= 32 ? 32 : ((PI::T + 127) / 128) * ACC_COLS <= 64 ? 64 :
+                                   ((PI::T + 127) / 128) * ACC_COLS <= 128 ? 128 : ((PI::T + 127) / 128) * ACC_COLS <= 256 ? 256 : 512;
+    static_assert(((PI::T + 127) / 128) * ACC_COLS <= 512, "accumulators must fit the SM's tensor memory");
     cg::cluster_group cluster = cg::this_cluster();
     const int r = (int)cluster.block_rank();
     const int cell = (int)(blockIdx.x / kRO);
@@ -87,6 +115,9 @@ template <class PI> __global__ void __cluster_dims__(kRO, 1, 1) __launch_bounds_
     const float2* peer[kRO];
 #pragma unroll
     for (int q = 0; q < kRO; q++) peer[q] = cluster.map_shared_rank(line, q);
+    const uint32_t tmem_base = tmem_alloc_cta<TMEM_COLS>(&tmem_base_smem);
+    const uint32_t warp = threadIdx.x >> 5;
+    const uint32_t taddr = tmem_base + (((warp & 3u) * 32u) << 16) + (warp >> 2) * ACC_COLS;
 
     for (int k = 0; k < a.K; k++) {
         const unsigned long long blk0 = (unsigned long long)k * N;
@@ -94,19 +125,49 @@ template <class PI> __global__ void __cluster_dims__(kRO, 1, 1) __launch_bounds_
         __syncthreads();
         inner_chain<PI>(line, a.tw, code);
         cluster.sync();  // every sub-block now holds u_q[i] in natural order
-        // outer inverse stage (DIT radix 4) for the outputs this CTA owns: n = i + r*NI
-        for (int i = threadIdx.x; i < NI; i += PI::T) {
-            float2 y = peer[0][PI::phys(i)];
+        // outer inverse stage (DIT radix 4) for the outputs this CTA owns: n = i + r*NI; UNR outputs per trip, all of
+        // their distributed-shared-memory and twiddle loads in flight together
+        if (k > 0) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+#pragma unroll 1
+        for (int m = 0; m < TRIPS; m++) {
+            const int i0 = threadIdx.x + m * UNR * PI::T;
+            float p[UNR];
+            if (k > 0) tmem_ld8_nm(p, taddr + m * UNR);
+            // two half-trips of HALF outputs: HALF x (kRO distributed-shared-memory + kRO - 1 twiddle) loads in flight
+            constexpr int HALF = UNR / 2;
 #pragma unroll
-            for (int q = 1; q < kRO; q++) {
-                const float2 u = cmul_conj(peer[q][PI::phys(i)], __ldg(&otw[(q - 1) * NI + i]));
-                y = cadd(y, rot4<true>(u, q * r));
+            for (int h = 0; h < 2; h++) {
+                float2 u[HALF][kRO], t[HALF][kRO];
+                // an index past the end (only the last output of the last trip, for threads >= NI % T) is clamped: its
+                // value is computed and kept in tensor memory but never written to the row
+#pragma unroll
+                for (int e = 0; e < HALF; e++) {
+                    const int i = min(i0 + (h * HALF + e) * PI::T, NI - 1);
+#pragma unroll
+                    for (int q = 0; q < kRO; q++) u[e][q] = peer[q][PI::phys(i)];
+#pragma unroll
+                    for (int q = 1; q < kRO; q++) t[e][q] = __ldg(&otw[(q - 1) * NI + i]);
+                }
+                if (h == 0 && k > 0) tmem_wait_ld8_nm(p);
+#pragma unroll
+                for (int e = 0; e < HALF; e++) {
+                    const int i = i0 + (h * HALF + e) * PI::T;
+                    float2 y = u[e][0];
+#pragma unroll
+                    for (int q = 1; q < kRO; q++) y = cadd(y, rot4<true>(cmul_conj(u[e][q], t[e][q]), q * r));
+                    const float pw = y.x * y.x + y.y * y.y;
+                    const float pe = (k == 0) ? pw : p[h * HALF + e] + pw;
+                    p[h * HALF + e] = pe;
+                    if (k == a.K - 1 && i < NI) acc[i] = pe;
+                }
             }
-            const float p = y.x * y.x + y.y * y.y;
-            acc[i] = (k == 0) ? p : acc[i] + p;
+            if (k < a.K - 1) tmem_st<8>(taddr + m * UNR, p);
         }
         cluster.sync();  // peers are done reading this CTA's line before the next block overwrites it
     }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) tmem_dealloc_warp<TMEM_COLS>(tmem_base);
 }
 
 // code spectra for the cluster plan: same forward path on the +-1 code samples, one CTA per (PRN, sub-block)
