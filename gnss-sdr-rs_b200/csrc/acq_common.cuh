@@ -25,6 +25,8 @@ using P20000 = Plan<20000, 320, 1, 0, 32, 25, 25>;
 using P20000 = Plan<20000, 400, 1, 0, 32, 25, 25>;
 #elif defined(GB_P20000_ALT) && GB_P20000_ALT == 3
 using P20000 = Plan<20000, 640, 1, 0, 32, 25, 25>;
+#elif defined(GB_P20000_ALT) && GB_P20000_ALT == 4
+using P20000 = Plan<20000, 512, 1, 0, 32, 25, 25>;   // with the accumulators in tensor memory (acq_tmem 1): no 64-register accumulator block
 #else
 using P20000 = Plan<20000, 512, 1, 0, 8, 4, 25, 25>;
 #endif
@@ -248,8 +250,11 @@ template <uint32_t COLS> __device__ __forceinline__ void tmem_dealloc_warp(uint3
 }
 template <int R> __device__ __forceinline__ void tmem_ld(float (&a)[R], uint32_t taddr)
 {
-    static_assert(R == 4 || R == 8 || R == 12 || R == 16, "radix of the last inverse stage");
-    if constexpr (R == 16) {
+    static_assert(R == 4 || R == 8 || R == 12 || R == 16 || R == 32, "radix of the last inverse stage");
+    if constexpr (R == 32) {
+        tmem_ld<16>(*reinterpret_cast<float(*)[16]>(&a[0]), taddr);
+        tmem_ld<16>(*reinterpret_cast<float(*)[16]>(&a[16]), taddr + 16);
+    } else if constexpr (R == 16) {
         asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
                      : "=f"(a[0]), "=f"(a[1]), "=f"(a[2]), "=f"(a[3]), "=f"(a[4]), "=f"(a[5]), "=f"(a[6]), "=f"(a[7]), "=f"(a[8]), "=f"(a[9]),
                        "=f"(a[10]), "=f"(a[11]), "=f"(a[12]), "=f"(a[13]), "=f"(a[14]), "=f"(a[15])
@@ -272,8 +277,11 @@ template <int R> __device__ __forceinline__ void tmem_wait_ld(float (&a)[R])
 }
 template <int R> __device__ __forceinline__ void tmem_st(uint32_t taddr, const float (&a)[R])
 {
-    static_assert(R == 4 || R == 8 || R == 12 || R == 16, "radix of the last inverse stage");
-    if constexpr (R == 16) {
+    static_assert(R == 4 || R == 8 || R == 12 || R == 16 || R == 32, "radix of the last inverse stage");
+    if constexpr (R == 32) {
+        tmem_st<16>(taddr, *reinterpret_cast<const float(*)[16]>(&a[0]));
+        tmem_st<16>(taddr + 16, *reinterpret_cast<const float(*)[16]>(&a[16]));
+    } else if constexpr (R == 16) {
         asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
                      :: "r"(taddr), "f"(a[0]), "f"(a[1]), "f"(a[2]), "f"(a[3]), "f"(a[4]), "f"(a[5]), "f"(a[6]), "f"(a[7]), "f"(a[8]), "f"(a[9]),
                         "f"(a[10]), "f"(a[11]), "f"(a[12]), "f"(a[13]), "f"(a[14]), "f"(a[15])
