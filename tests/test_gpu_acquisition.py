@@ -608,6 +608,42 @@ def test_two_handles_on_one_device(ffi):
     hs[0].close()
 
 
+def test_tensor_memory_is_shared_between_concurrent_searches(ffi):
+    """Tensor memory is a per-SM resource the inverse kernels allocate per CTA (N = 4092: 128 columns, four CTAs fill the
+    SM's 512; power-of-two plans: 32 columns; the cluster plan: 256): searches of three handles running at the same time
+    on one GPU -- different plans, different allocation sizes, more CTAs than fit -- must wait for each other's columns
+    (tcgen05.alloc blocks, every CTA frees what it took) and give the results of the same searches run alone."""
+    import threading
+    from gnss_sdr_rs_b200 import acquisition, sdr_mock
+    dopplers = np.arange(-5000, 5001, 250, dtype=np.float32)     # 41 bins x 32 PRNs = 1312 CTAs per search
+    jobs = []
+    for n, K in ((4092, 8), (2048, 8), (4092, 6)):
+        fs = float(n) * 1000.0
+        h = ffi.Handle(0)
+        e = acquisition.AcquisitionEngine(h, n, fs)
+        e.make_doppler_tables(0.0, dopplers)
+        x = sdr_mock.baseband(fs, K, _sats(n, n + K), seed=n + K)
+        jobs.append((h, e, x, K, e.search_cells(x, K).copy()))
+    out = [None] * len(jobs)
+
+    def work(i):
+        _, e, x, K, ref = jobs[i]
+        ok = True
+        for _ in range(6):
+            ok &= e.search_cells(x, K).tobytes() == ref.tobytes()
+        out[i] = ok
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(len(jobs))]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(timeout=120)
+    assert all(not t.is_alive() for t in th), "a search did not finish: tensor-memory allocation must never deadlock"
+    assert out == [True] * len(jobs)
+    for h, *_ in jobs:
+        h.close()
+
+
 def test_headline_kernel_edge_cases(gpu, oracle, ffi):
     """N = 4092 through the default chain (leftover-warp kernel + Doppler aliasing): an IF offset with negative Dopplers,
     a sparse PRN mask (masked rows stay zero), all-zero input (peak 0, arg-max 0, metric NaN -> None, Q1) and a grid
