@@ -500,6 +500,7 @@ cudaError_t acq_launch_inverse_lw4092(const AcqArgs& a, int n_d, cudaStream_t st
     const int minb = tuning("acq_lw_minb", 3);
     if (tm == 5) return launch_lwt<P4092W5, true>(a, n_d, st);
     if (tm == 2) return launch_lwt<P4092W, true, true>(a, n_d, st);
+    if (tm == 3) return launch_lwt<P4092W3, true, true>(a, n_d, st);   // A/B: the same at three CTAs per SM and 128 registers
     if (tm) return launch_lwt<P4092W, true>(a, n_d, st);
     if (tuning("acq_lw_db", 0)) return launch_lw<P4092W3, true, true>(a, n_d, st);   // A/B: double-buffered line
     if (minb == 4) return launch_lw<PW, true>(a, n_d, st);
