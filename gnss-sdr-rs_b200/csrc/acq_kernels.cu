@@ -114,10 +114,11 @@ template <class P, bool WANT_ROW> __global__ void __launch_bounds__(P::T, P::MIN
                 float2 v[GM::R];
 #pragma unroll
                 for (int j = 0; j < GM::R; j++) v[j] = line[P::phys(base + j)];
-                Dft<GM::R, false>::run(v);
+                if constexpr (GM::R == 31 && P::NESTED31) dft_run_like_emit<GM::R, false, true>(v);   // = acq_forward_kernel's last stage
+                else Dft<GM::R, false>::run(v);
 #pragma unroll
                 for (int q = 0; q < GM::R; q++) v[q] = cmul_conj(v[q], __ldg(&code[q * P::SPEC_STRIDE + b]));
-                dft_emit<GM::R, true>(v, [&](int j, float2 y) { line[P::phys(base + j)] = y; });
+                dft_emit<GM::R, true, P::NESTED31>(v, [&](int j, float2 y) { line[P::phys(base + j)] = y; });
             }
         }
         __syncthreads();
@@ -172,7 +173,7 @@ template <class P> __global__ void __launch_bounds__(P::T, P::MINB) acq_forward_
             float2 v[GM::R];
 #pragma unroll
             for (int j = 0; j < GM::R; j++) v[j] = line[P::phys(b * GM::R + j)];
-            dft_emit<GM::R, false>(v, [&](int q, float2 y) { out[q * P::SPEC_STRIDE + b] = y; });
+            dft_emit<GM::R, false, P::NESTED31>(v, [&](int q, float2 y) { out[q * P::SPEC_STRIDE + b] = y; });
         }
     }
 }
@@ -270,7 +271,7 @@ template <class P, bool DB, bool ALIAS, int TMODE = 0> __global__ void __launch_
                     float2 v[GM::R];
 #pragma unroll
                     for (int q = 0; q < GM::R; q++) v[q] = cmul_conj(__ldg(&sg[q * P::SPEC_STRIDE + b]), __ldg(&code[q * P::SPEC_STRIDE + b]));
-                    dft_emit<GM::R, true>(v, [&](int j, float2 y) { line[P::phys(b * GM::R + j)] = y; });
+                    dft_emit<GM::R, true, P::NESTED31>(v, [&](int j, float2 y) { line[P::phys(b * GM::R + j)] = y; });
                 }
             }
             if constexpr (CT) {
@@ -299,7 +300,7 @@ template <class P, bool DB, bool ALIAS, int TMODE = 0> __global__ void __launch_
                             }
                         }
                     }
-                    if (active) dft_emit<GM::R, true>(v, [&](int j, float2 y) { line[P::phys(b * GM::R + j)] = y; });
+                    if (active) dft_emit<GM::R, true, P::NESTED31>(v, [&](int j, float2 y) { line[P::phys(b * GM::R + j)] = y; });
                 }
             }
         }

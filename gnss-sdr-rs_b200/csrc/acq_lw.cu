@@ -17,52 +17,63 @@ namespace gb {
 // runs the whole radix-31 instruction stream for 4 of its 32 lanes, a fifth of that stage's FMA-pipe time.  Here the CTA
 // is PW::T working threads (whole warps; PW = the same radices on T = 128, which also owns stages B and C) plus ONE
 // leftover warp that batches the REM = NB - PW::T ragged butterflies of 32 / REM consecutive groups into one full-warp
-// pass: lane l computes butterfly PW::T + l % REM of group g0 + l / REM, keeps the finished accumulators in registers
-// (OddPrimeAcc) and hands them to the line when their group comes round -- it runs one batch ahead of the working
+// pass: lane l computes butterfly PW::T + l % REM of group g0 + l / REM, parks the finished outputs in a shared-memory
+// stash and the warp hands them to the line when their group comes round -- it runs one batch ahead of the working
 // warps, so its arithmetic overlaps their stages B and C.  20 groups: 83 radix-31 warp passes instead of 100.
 // Named barriers (the warp-specialised pattern): A_DONE = line of group g complete (working warps wait, the leftover
 // warp only arrives), MID = between stages B and C (working warps only), END = line free again (everybody).
-// Every output accumulates its terms in the same order as dft_odd_prime_emit, so cells are bit-identical to
+// The leftover warp runs the same butterfly code as the working warps (dft_emit), so cells are bit-identical to
 // acq_inverse_kernel's (tests/test_gpu_acquisition.py::test_leftover_warp_kernel_is_bit_identical).
 enum { BAR_A_DONE = 1, BAR_MID = 2, BAR_END = 3 };
 
 // DB: the line is double-buffered (group g lives in line + (g & 1) * LINE).  Passing A_DONE(g - 1) then proves that every
 // working warp has left stage C of group g - 2, the last reader of buffer g & 1, so END disappears from the loop and the
 // leftover warp waits on A_DONE instead of arriving at it (no fence needed: bar.sync orders its stores).
+// The leftover warp computes its batch with the SAME butterfly as the working warps (dft_emit: resident inputs, the
+// plan's radix-31 form), so every butterfly of the line rounds alike whatever warp made it; the finished outputs wait in a
+// shared-memory stash (32 lanes x 31 complex behind the line) and the REM butterflies of a group -- one contiguous run of
+// REM x 31 complex in the stash and in the line -- are copied by the whole warp when their group comes round.
+constexpr int LW_STASH = 32 * 31;   // complex elements
 template <class PW, bool CG, bool DB>
 __device__ __noinline__ void lw_leftover_warp(const float2* __restrict__ spec, const float2* __restrict__ code,
                                               float2* __restrict__ line, int n_groups)
 {
     constexpr int LASTS = PW::NSTAGE - 1;
     using GM = StageGeo<PW, LASTS>;
-    constexpr int N = PW::N;
     constexpr int TW = PW::T, TALL = PW::T + 32;
     constexpr int REM = GM::NB - TW;
     constexpr int BATCH = 32 / REM;
+    static_assert(GM::R == 31 && PW::PAD == 0, "31-point first stage, unpadded line");
     const int lane = threadIdx.x - TW;
     const int b = TW + lane % REM, slot = lane / REM;
-    OddPrimeAcc<GM::R> h;
+    float2* __restrict__ stash = line + PW::LINE * (DB ? 2 : 1);
     auto compute = [&](int g0) {
         const int g = g0 + slot;
         if (g < n_groups) {
             const float2* __restrict__ sg = spec + (size_t)g * PW::SPEC_LEN;
-            dft_odd_prime_stream_acc<GM::R, true, 3>(
-                [&](int q) { return cmul_conj(LDSPEC(&sg[q * PW::SPEC_STRIDE + b]), __ldg(&code[q * PW::SPEC_STRIDE + b])); }, h);
+            float2 v[GM::R];
+#pragma unroll
+            for (int q = 0; q < GM::R; q++) v[q] = cmul_conj(LDSPEC(&sg[q * PW::SPEC_STRIDE + b]), __ldg(&code[q * PW::SPEC_STRIDE + b]));
+            dft_emit<GM::R, true, PW::NESTED31>(v, [&](int j, float2 y) { stash[lane * GM::R + j] = y; });
         }
+        __syncwarp();
+    };
+    // group g: the REM x 31 outputs of slot g % BATCH go to line positions TW * 31 ...
+    auto hand_over = [&](int g, float2* __restrict__ lg) {
+        const float2* __restrict__ src = stash + (g % BATCH) * REM * GM::R;
+        float2* __restrict__ dst = lg + TW * GM::R;
+        for (int e = lane; e < REM * GM::R; e += 32) dst[e] = src[e];
     };
     compute(0);
     for (int g = 0; g < n_groups; g++) {
         if (DB) {
-            float2* __restrict__ lg = line + (g & 1) * PW::LINE;
-            if (slot == g % BATCH)
-                dft_odd_prime_stream_emit<GM::R>(h, [&](int j, float2 y) { lg[PW::phys(b * GM::R + j)] = y; });
-            if (g % BATCH == BATCH - 1 && g + 1 < n_groups) compute(g + 1);
+            hand_over(g, line + (g & 1) * PW::LINE);
             __syncwarp();
+            if (g % BATCH == BATCH - 1 && g + 1 < n_groups) compute(g + 1);
             named_bar_sync(BAR_A_DONE, TALL);
         } else {
             if (g > 0) named_bar_sync(BAR_END, TALL);   // group g-1 has left the line
-            if (slot == g % BATCH)
-                dft_odd_prime_stream_emit<GM::R>(h, [&](int j, float2 y) { line[PW::phys(b * GM::R + j)] = y; });
+            hand_over(g, line);
             __threadfence_block();   // bar.arrive alone does not order the shared-memory stores before the arrival
             __syncwarp();
             named_bar_arrive(BAR_A_DONE, TALL);
@@ -118,7 +129,7 @@ __global__ void __launch_bounds__(PW::T + 32, PW::MINB) acq_inverse_lw_kernel(co
                 // line: a warp that leaves stage C early spends its L2 latency before the barrier instead of after it
                 if (!DB && g > 0) named_bar_sync(BAR_END, TALL);
                 float2* __restrict__ lg = DB ? line + (g & 1) * PW::LINE : line;
-                dft_emit<GM::R, true>(v, [&](int j, float2 y) { lg[PW::phys(b * GM::R + j)] = y; });
+                dft_emit<GM::R, true, PW::NESTED31>(v, [&](int j, float2 y) { lg[PW::phys(b * GM::R + j)] = y; });
             }
             float2* __restrict__ lg = DB ? line + (g & 1) * PW::LINE : line;
             named_bar_sync(BAR_A_DONE, TALL);
@@ -213,7 +224,7 @@ __global__ void __launch_bounds__(PW::T + 32, PW::MINB) acq_inverse_lwt_kernel(c
                 for (int q = 0; q < GM::R; q++) v[q] = cmul_conj(LDSPEC(&sg[q * PW::SPEC_STRIDE + b]), __ldg(&code[q * PW::SPEC_STRIDE + b]));
             }
             if (g > 0) named_bar_sync(BAR_END, TALL);
-            dft_emit<GM::R, true>(v, [&](int j, float2 y) { line[PW::phys(b * GM::R + j)] = y; });
+            dft_emit<GM::R, true, PW::NESTED31>(v, [&](int j, float2 y) { line[PW::phys(b * GM::R + j)] = y; });
         }
         named_bar_sync(BAR_A_DONE, TALL);
         dit_stage_rows<PW, 1, true, TW / 32>(line);
@@ -229,7 +240,7 @@ __global__ void __launch_bounds__(PW::T + 32, PW::MINB) acq_inverse_lwt_kernel(c
 
 template <class PW, bool CG, bool CT = false> static cudaError_t launch_lwt(const AcqArgs& a, int n_d, cudaStream_t st)
 {
-    const size_t smem = sizeof(float2) * (size_t)PW::LINE;
+    const size_t smem = sizeof(float2) * ((size_t)PW::LINE + LW_STASH);   // line + the leftover warp's stash
     cudaError_t e = cudaFuncSetAttribute(acq_inverse_lwt_kernel<PW, CG, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     acq_inverse_lwt_kernel<PW, CG, CT><<<n_d * a.n_active, PW::T + 32, smem, st>>>(a);
@@ -238,7 +249,7 @@ template <class PW, bool CG, bool CT = false> static cudaError_t launch_lwt(cons
 
 template <class PW, bool CG, bool DB = false> static cudaError_t launch_lw(const AcqArgs& a, int n_d, cudaStream_t st)
 {
-    const size_t smem = sizeof(float2) * (size_t)PW::LINE * (DB ? 2 : 1);
+    const size_t smem = sizeof(float2) * ((size_t)PW::LINE * (DB ? 2 : 1) + LW_STASH);   // line(s) + the leftover warp's stash
     cudaError_t e = cudaFuncSetAttribute(acq_inverse_lw_kernel<PW, CG, DB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     acq_inverse_lw_kernel<PW, CG, DB><<<n_d * a.n_active, PW::T + 32, smem, st>>>(a);
@@ -472,7 +483,7 @@ static cudaError_t acq_launch_inverse_tc4092(const AcqArgs& a, int n_d, int n_sp
     tc_relayout_kernel<<<(unsigned)((n_spec + 255) / 256), 256, 0, st>>>(a.spec, spec_tc, PW::SPEC_LEN, PW::SPEC_STRIDE, n_spec_sets);
     if (!code_fresh)
         tc_relayout_kernel<<<(unsigned)((n_code + 255) / 256), 256, 0, st>>>(a.code_fft, code_tc, PW::SPEC_LEN, PW::SPEC_STRIDE, n_code_sets);
-    const size_t smem = sizeof(float2) * (size_t)PW::LINE;
+    const size_t smem = sizeof(float2) * ((size_t)PW::LINE + LW_STASH);   // line + the leftover warp's stash
     e = cudaFuncSetAttribute(acq_inverse_tc_kernel<PW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     acq_inverse_tc_kernel<PW><<<n_d * a.n_active, PW::T + 32, smem, st>>>(a, spec_tc, code_tc);

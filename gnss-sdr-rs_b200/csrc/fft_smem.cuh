@@ -389,16 +389,36 @@ __device__ __forceinline__ void dft_odd_prime_stream(Load load, Emit emit)
     dft_odd_prime_stream_emit<R>(h, emit);
 }
 
+}  // namespace gb
+#include "dft31_nested.cuh"
+namespace gb {
+
 // dft_emit<R,INV>(v, emit): DFT of v with outputs delivered through emit(q, X_q).
-template <int R, bool INV, class Emit> __device__ __forceinline__ void dft_emit(float2 (&v)[R], Emit emit)
+// NESTED (Plan::NESTED31) selects the nested 31-point butterfly of dft31_nested.cuh: 27 % fewer FP32 pipe slots, ~100 live
+// registers -- a gain where the kernel has them (N = 4092: 1.193 -> 1.070 ms), a loss at the 96-register cap of the
+// one-CTA-per-SM plan of 16368 (0.613 -> 0.680 ms), hence a per-plan switch.  Every kernel of a plan uses the same form,
+// so the chains of one plan stay bit-identical among themselves.
+template <int R, bool INV, bool NESTED = false, class Emit> __device__ __forceinline__ void dft_emit(float2 (&v)[R], Emit emit)
 {
-    if constexpr (R == 3 || R == 5 || R == 7 || R == 11 || R == 13 || R == 17 || R == 19 || R == 23 || R == 29 || R == 31) {
+    if constexpr (R == 31 && NESTED) {
+        dft31_nested_emit<INV>(v, emit);
+    } else if constexpr (R == 3 || R == 5 || R == 7 || R == 11 || R == 13 || R == 17 || R == 19 || R == 23 || R == 29 || R == 31) {
         dft_odd_prime_emit<R, INV>(v, emit);
     } else {
         Dft<R, INV>::run(v);
 #pragma unroll
         for (int q = 0; q < R; q++) emit(q, v[q]);
     }
+}
+
+// In-place form with the same arithmetic as dft_emit<R, INV, NESTED> (kernels that must agree bit for bit with a chain
+// that emits, e.g. the fused kernel's last forward stage against acq_forward_kernel).
+template <int R, bool INV, bool NESTED> __device__ __forceinline__ void dft_run_like_emit(float2 (&v)[R])
+{
+    float2 o[R];
+    dft_emit<R, INV, NESTED>(v, [&](int q, float2 y) { o[q] = y; });
+#pragma unroll
+    for (int q = 0; q < R; q++) v[q] = o[q];
 }
 
 template <bool INV> struct Dft<3, INV> : DftOddPrime<3, INV> {};
@@ -513,6 +533,8 @@ template <int N_, int T_, int MINB_, int PAD_, int R0, int R1 = 1, int R2 = 1, i
     // inverse kernel, radix-31 first stage: 0 = all inputs resident (dft_odd_prime_emit), n > 0 = streamed in batches of
     // n input pairs (dft_odd_prime_stream)
     static constexpr int STREAM_A = 0;
+    // radix-31 butterflies of this plan in the nested form (dft_emit's NESTED): the headline size only
+    static constexpr bool NESTED31 = N_ == 4092;
 };
 
 // Good-Thomas prime-factor plan: the stage radices are pairwise coprime, so with the index maps

@@ -7,7 +7,7 @@ TAG=$1; shift
 OUT=../build_$TAG
 mkdir -p $OUT
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC $*"
-for f in acq_kernels acq_cluster; do nvcc $FLAGS -Xptxas -v -c $f.cu -o $OUT/$f.o > $OUT/$f.ptxas 2>&1 & done
+for f in acq_kernels acq_cluster acq_lw; do nvcc $FLAGS -Xptxas -v -c $f.cu -o $OUT/$f.o > $OUT/$f.ptxas 2>&1 & done
 wait
-nvcc -shared -o $OUT/libgnss_b200.so $OUT/acq_kernels.o $OUT/acq_cluster.o ../build/acq_lw.o ../build/acq_generic.o ../build/frontend.o ../build/trk_kernels.o ../build/trk_ws.o ../build/fine_doppler.o ../build/gnss_b200.o
+nvcc -shared -o $OUT/libgnss_b200.so $OUT/acq_kernels.o $OUT/acq_cluster.o $OUT/acq_lw.o ../build/acq_generic.o ../build/frontend.o ../build/trk_kernels.o ../build/trk_ws.o ../build/fine_doppler.o ../build/gnss_b200.o
 echo "built $OUT/libgnss_b200.so"
