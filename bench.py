@@ -44,7 +44,7 @@ SATS = [(3, 1230.0, 100, 45.0), (7, -2210.0, 2000, 40.0), (11, 3370.0, 3100, 42.
 
 
 # filled in from the ncu capture of the same command (profiles/round1_v9_final.txt)
-KERNEL_SHARES_NOTE = ("acq_inverse_lwt_kernel 96.2% / acq_forward_kernel (20 of 201 bins, Doppler aliasing) 3.4% / permute 0.4% "
+KERNEL_SHARES_NOTE = ("acq_inverse_lwt_kernel 95.9% / acq_forward_kernel (20 of 201 bins, Doppler aliasing) 3.6% / permute 0.5% "
                       "of the chain (profiles/round2_acq_lwt_tmem.txt)")
 
 
@@ -764,7 +764,7 @@ def run_ours(args, rank, world, local_rank):
                              "forward_spectra_per_group": n_fwd,
                              "kernel": ("acq_fused_kernel<PfaPlan<4092,160,4,12,11,31>>" if args.acq_mode == "fused" else
                                         "permute_blocks_kernel + acq_forward_kernel<PfaPlan<4092,160,4,12,11,31>> + "
-                                        "acq_inverse_lwt_kernel<PfaPlan<4092,128,4,12,11,31>> (128 working threads + leftover warp; power accumulators and per-thread code spectrum in tensor memory via tcgen05.ld/st; 4 CTAs/SM, 96 registers)"),
+                                        "acq_inverse_lwt_kernel<PfaPlan<4092,128,4,12,11,31>> (128 working threads + leftover warp; nested radix-31 butterfly; power accumulators and per-thread code spectrum in tensor memory via tcgen05.ld/st; 4 CTAs/SM, 96 registers)"),
                              "kernel_ms": kernel_ms_avg,
                              "kernel_shares_ncu": KERNEL_SHARES_NOTE,
                              "hbm_view": {"bound": "hbm", "algorithmic_bytes": abytes,
