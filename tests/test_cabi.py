@@ -216,3 +216,20 @@ def _phase_after(step, n):
     for _ in range(n):
         acc = np.float32(np.fmod(np.float32(acc + step), np.float32(2048.0)))
     return acc
+
+
+def test_nested_radix31_butterfly_is_generated_and_correct(tmp_path):
+    """dft31_nested.cuh (the 31-point butterfly of the N = 4092 plan: two 15-point cyclic correlations nested 3 x 5) is the
+    output of gen_dft31_nested.py, and the generator's own checks hold: the nested correlation equals its definition, the
+    butterfly equals numpy's FFT in f64 for both signs, and a float32 emulation of the emitted operation order is within
+    1e-6 of the f64 DFT."""
+    import re
+    import subprocess
+    import sys
+    csrc = os.path.join(ROOT, "gnss-sdr-rs_b200", "csrc")
+    out = tmp_path / "dft31_nested.cuh"
+    r = subprocess.run([sys.executable, os.path.join(csrc, "gen_dft31_nested.py"), str(out)], capture_output=True, text=True, check=True)
+    assert out.read_text() == open(os.path.join(csrc, "dft31_nested.cuh")).read()
+    errs = [float(x) for x in re.findall(r"err ([0-9.e+-]+)", r.stdout)]
+    assert len(errs) == 5 and max(errs[:3]) < 1e-12 and max(errs[3:]) < 1e-6, r.stdout
+
