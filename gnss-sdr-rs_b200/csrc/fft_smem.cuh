@@ -533,8 +533,13 @@ template <int N_, int T_, int MINB_, int PAD_, int R0, int R1 = 1, int R2 = 1, i
     // inverse kernel, radix-31 first stage: 0 = all inputs resident (dft_odd_prime_emit), n > 0 = streamed in batches of
     // n input pairs (dft_odd_prime_stream)
     static constexpr int STREAM_A = 0;
-    // radix-31 butterflies of this plan in the nested form (dft_emit's NESTED): the headline size only
-    static constexpr bool NESTED31 = N_ == 4092;
+    // radix-31 butterflies of this plan in the nested form (dft_emit's NESTED): where the kernel has the registers for it
+    // (N = 4092: 1.193 -> 1.064 ms, N = 8184: 0.446 -> 0.404 ms; the 96-register cap of 16368's 17 warps spills it: 0.613 -> 0.680)
+#ifdef GB_NESTED31_ALL   // A/B builds (tools/build_alt.sh): every plan with a 31-point stage
+    static constexpr bool NESTED31 = true;
+#else
+    static constexpr bool NESTED31 = N_ == 4092 || N_ == 8184;
+#endif
 };
 
 // Good-Thomas prime-factor plan: the stage radices are pairwise coprime, so with the index maps
